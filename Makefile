@@ -1,0 +1,32 @@
+# Builds libsz3b200.so (CUDA kernels + host tail + C ABI) for sm_100a, in-tree.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+# -fmad=false: the reference arithmetic has no FMA contraction (SURVEY.md Appendix A / hard part 1)
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-unused-function \
+           -Xptxas -v --expt-relaxed-constexpr
+SRC := sz3_b200/csrc
+OBJDIR := build/obj
+LIB := sz3_b200/lib/libsz3b200.so
+CU := api.cu pipeline.cu interp_kernels.cu encode_kernels.cu misc_kernels.cu blockwise.cu decompress.cu
+CPP := huffman_host.cpp stream_host.cpp
+OBJS := $(CU:%.cu=$(OBJDIR)/%.o) $(CPP:%.cpp=$(OBJDIR)/%.o)
+HDRS := $(wildcard $(SRC)/*.hpp $(SRC)/*.cuh $(SRC)/*.h) include/sz3b.h
+
+all: $(LIB)
+
+$(OBJDIR)/%.o: $(SRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(OBJDIR)/%.o: $(SRC)/%.cpp $(HDRS)
+	@mkdir -p $(OBJDIR)
+	g++ -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -c $< -o $@
+
+$(LIB): $(OBJS)
+	@mkdir -p sz3_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -l:libzstd.so.1 -lpthread
+
+clean:
+	rm -rf build sz3_b200/lib/*.so
+
+.PHONY: all clean

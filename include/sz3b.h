@@ -1,0 +1,141 @@
+/* include/sz3b.h -- C ABI of libsz3b200.so, the B200-native implementation of SZ3's predict -> quantize -> encode
+ * hot path.  Plain pointers and sizes only; every entry point names the reference interface it stands in for
+ * (paths relative to the SZ3 v3.3.2 source tree).
+ *
+ * The drop-in C++ headers (sz3_b200/include/SZ3/api/sz.hpp, SZ3/utils/Config.hpp) and the sz3c shim
+ * (sz3_b200/sz3c) are thin forwarders onto these functions; INTEGRATION.md shows the bindings.
+ *
+ * All functions return 0 on success or a negative SZ3B_E_* code; sz3b_last_error() gives the message for the
+ * calling thread.  `loc` arguments say where a buffer lives: SZ3B_HOST (0) or SZ3B_DEVICE (1, a CUDA device pointer
+ * on the current device).  Compressed streams always live in host memory (the final zstd pass runs on the host).
+ */
+#ifndef SZ3B_H
+#define SZ3B_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SZ3B_HOST 0
+#define SZ3B_DEVICE 1
+
+#define SZ3B_FLOAT 0  /* SZ_FLOAT,  include/SZ3/def.hpp */
+#define SZ3B_DOUBLE 1 /* SZ_DOUBLE */
+
+#define SZ3B_OK 0
+#define SZ3B_E_INVALID_ARGUMENT (-1) /* the reference throws std::invalid_argument */
+#define SZ3B_E_RUNTIME (-2)          /* the reference throws std::runtime_error */
+#define SZ3B_E_CUDA (-3)             /* CUDA runtime failure / no device: there is no CPU fallback */
+#define SZ3B_E_UNSUPPORTED (-4)      /* configuration outside the GPU path built so far */
+
+/* enum EB / ALGO / INTERP_ALGO, include/SZ3/utils/Config.hpp:54,68,77 */
+enum { SZ3B_EB_ABS, SZ3B_EB_REL, SZ3B_EB_PSNR, SZ3B_EB_L2NORM, SZ3B_EB_ABS_AND_REL, SZ3B_EB_ABS_OR_REL };
+enum { SZ3B_ALGO_LORENZO_REG, SZ3B_ALGO_INTERP_LORENZO, SZ3B_ALGO_INTERP, SZ3B_ALGO_NOPRED, SZ3B_ALGO_LOSSLESS };
+enum { SZ3B_INTERP_LINEAR, SZ3B_INTERP_CUBIC };
+
+/* POD mirror of SZ3::Config (include/SZ3/utils/Config.hpp:441-478). */
+typedef struct sz3b_config {
+    int32_t N;
+    uint64_t dims[4];
+    int32_t cmprAlgo;
+    int32_t errorBoundMode;
+    double absErrorBound;
+    double relErrorBound;
+    double psnrErrorBound;
+    double l2normErrorBound;
+    int32_t openmp;      /* 0 = single stream; >0 = emit the OpenMP slab container (SZImplOMP.hpp) with this many slabs */
+    int32_t quantbinCnt;
+    int32_t blockSize;
+    int32_t lorenzo;
+    int32_t lorenzo2;
+    int32_t regression;
+    int32_t regression2;
+    int32_t interpAlgo;
+    int32_t interpDirection;
+    int32_t interpAnchorStride;
+    double interpAlpha;
+    double interpBeta;
+    int32_t dataType;
+    int32_t predDim;
+} sz3b_config;
+
+/* SZ3::Config(dims...) + setDims (Config.hpp:146-177): drops size-1 dims, sets defaults. */
+int sz3b_config_init(sz3b_config *c, int ndims, const size_t *dims);
+
+/* Config::save / Config::load (Config.hpp:312-413): the blob appended to every stream. */
+size_t sz3b_config_save(const sz3b_config *c, unsigned char *out);
+int sz3b_config_load(sz3b_config *c, const unsigned char *in, size_t len);
+
+/* SZ_compress_size_bound<T> (include/SZ3/api/impl/SZImpl.hpp:34-44). */
+size_t sz3b_compress_bound(int dtype, const sz3b_config *c);
+
+/* SZ_compress<T>(conf, data, cmpData, cmpCap) (include/SZ3/api/sz.hpp:43-82).  `conf_out`, if not NULL, receives the
+ * configuration actually used (tuned interpolation parameters, resolved absolute bound) -- the reference keeps that
+ * private to the call. */
+int sz3b_compress(int dtype, const sz3b_config *c, const void *data, int data_loc, char *cmp, size_t cmp_cap,
+                  size_t *cmp_size, sz3b_config *conf_out);
+
+/* SZ_decompress<T>(conf, cmpData, cmpSize, decData) (include/SZ3/api/sz.hpp:117-157).  `out` must hold conf.num
+ * elements (query with sz3b_peek_config). */
+int sz3b_decompress(int dtype, const char *cmp, size_t cmp_size, void *out, int out_loc, sz3b_config *conf_out);
+
+/* Header + trailing Config of a stream (sz.hpp:119-141) without decompressing. */
+int sz3b_peek_config(const char *cmp, size_t cmp_size, sz3b_config *conf_out);
+
+/* calAbsErrorBound (include/SZ3/utils/Statistic.hpp:32-56); the min/max scan runs on the GPU. */
+int sz3b_abs_error_bound(int dtype, const sz3b_config *c, const void *data, int data_loc, double *abs_eb);
+
+/* ---- stage-level entry points (parity tests, bench) --------------------------------------------------------------- */
+
+/* InterpolationDecomposition::compress + save (decomposition/InterpolationDecomposition.hpp:79-159).
+ * quant_out: conf.num int32 indices in reference traversal order (host).  blob_out: what save() writes (dims,
+ * blocksize, interp id, direction, anchor stride, alpha, beta, quantizer incl. unpredictable values).
+ * schedule: 0 = automatic, 1 = force the generic per-pass kernels, 2 = force the tile kernel (N == 3 only). */
+int sz3b_interp_decompose(int dtype, const sz3b_config *c, double abs_eb, const void *data, int data_loc, int schedule,
+                          int32_t *quant_out, unsigned char *blob_out, size_t blob_cap, size_t *blob_len);
+
+/* BlockwiseDecomposition::compress + save (decomposition/BlockwiseDecomposition.hpp:28-46,69-73) with the predictor
+ * stack of make_compressor_lorenzo_regression (api/impl/SZAlgoLorenzoReg.hpp:22-64). */
+int sz3b_blockwise_decompose(int dtype, const sz3b_config *c, double abs_eb, const void *data, int data_loc,
+                             int32_t *quant_out, unsigned char *blob_out, size_t blob_cap, size_t *blob_len);
+
+/* HuffmanEncoder<int>::preprocess_encode + save + encode (encoder/HuffmanEncoder.hpp:96-218): histogram and bit
+ * packing on the GPU, tree on the host.  out = tree blob | size_t outSize | bits. */
+int sz3b_huffman_encode(const int32_t *q, size_t n, int q_loc, unsigned char *out, size_t out_cap, size_t *out_len,
+                        size_t *tree_len);
+
+/* The auto-tuner inside SZ_compress_Interp_lorenzo (api/impl/SZAlgoInterp.hpp:122-286): fills in cmprAlgo,
+ * interpAlgo, interpDirection, interpAlpha, interpBeta (and absErrorBound) exactly as the reference would choose. */
+int sz3b_tune(int dtype, sz3b_config *c, const void *data, int data_loc);
+
+/* ---- multi-GPU slab container (api/impl/SZImplOMP.hpp:16-117) -------------------------------------------------------
+ * Rank r of `nslabs` compresses rows [r*d0/nslabs, (r+1)*d0/nslabs) of the outermost dimension as an independent
+ * stream.  `slab` points at that slab only.  `range` is the global max-min (only read when the error-bound mode is
+ * not ABS; ranks obtain it with an all-reduce of sz3b_minmax results).  The rank gets back its payload and its Config
+ * blob; rank 0 concatenates them with sz3b_omp_assemble after a gather of the sizes. */
+int sz3b_minmax(int dtype, const void *data, int data_loc, size_t num, double *min_out, double *max_out);
+int sz3b_compress_slab(int dtype, const sz3b_config *c, int rank, int nslabs, const void *slab, int data_loc,
+                       double range, char *payload, size_t payload_cap, size_t *payload_size,
+                       unsigned char *conf_blob, size_t *conf_blob_size);
+size_t sz3b_omp_header_size(int nslabs, const size_t *conf_blob_sizes);
+int sz3b_omp_assemble(int dtype, const sz3b_config *c, int nslabs, const unsigned char *const *conf_blobs,
+                      const size_t *conf_blob_sizes, const size_t *payload_sizes, const char *const *payloads,
+                      char *cmp, size_t cmp_cap, size_t *cmp_size);
+
+/* ---- diagnostics -------------------------------------------------------------------------------------------------- */
+const char *sz3b_last_error(void);
+const char *sz3b_version(void);           /* "3.3.2" data format */
+int sz3b_device_count(void);
+
+/* Per-stage device times (CUDA events on the library's stream) of the calling thread's last compress call.
+ * names/ms arrays of capacity `cap`; returns the number of stages recorded.  Launch counts in `launches`. */
+int sz3b_last_profile(const char **names, double *ms, int *launches, int cap);
+/* zstd worker threads for the host tail (0 = hardware concurrency). */
+void sz3b_set_host_threads(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,59 @@
+// sz3_b200/csrc/device_ctx.cuh -- per-thread execution context handed to the kernel bodies on the device:
+// thread ids, the CTA barrier and the fused quantization-index histogram (replaces the frequency count of
+// HuffmanEncoder::init, reference include/SZ3/encoder/HuffmanEncoder.hpp:516-527).
+//
+// Histogram strategy: smooth data puts most indices exactly on `radius`; those are counted in a register and
+// reduced once per warp at the end (no atomics on the hot bin).  Indices inside a kWindow-wide window around the
+// radius go to a shared-memory histogram, everything else (rare) straight to the global 64-bit histogram.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sz3b {
+
+constexpr int kHistWindow = 1024;
+constexpr int kTileThreads = 512;
+
+struct DevCtx {
+    unsigned *shist;
+    unsigned long long *ghist;
+    int center;
+    int lo;
+    unsigned center_cnt;
+
+    __device__ __forceinline__ DevCtx(unsigned *sh, unsigned long long *gh, int radius)
+        : shist(sh), ghist(gh), center(radius), lo(radius - kHistWindow / 2), center_cnt(0) {}
+
+    __device__ __forceinline__ uint32_t tid() const { return threadIdx.x; }
+    __device__ __forceinline__ uint32_t nthreads() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+
+    __device__ __forceinline__ void clear() {
+        for (int i = threadIdx.x; i < kHistWindow; i += blockDim.x) shist[i] = 0;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void hist_add(int sym, bool active) {
+        if (!active) return;
+        if (sym == center) {
+            center_cnt++;
+            return;
+        }
+        unsigned k = static_cast<unsigned>(sym - lo);
+        if (k < static_cast<unsigned>(kHistWindow))
+            atomicAdd(&shist[k], 1u);
+        else
+            atomicAdd(&ghist[sym], 1ull);
+    }
+    __device__ __forceinline__ void flush() {
+        unsigned c = center_cnt;
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&shist[center - lo], c);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kHistWindow; i += blockDim.x) {
+            unsigned v = shist[i];
+            if (v) atomicAdd(&ghist[lo + i], static_cast<unsigned long long>(v));
+        }
+    }
+};
+
+}  // namespace sz3b

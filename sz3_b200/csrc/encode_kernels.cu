@@ -1,0 +1,364 @@
+// sz3_b200/csrc/encode_kernels.cu -- GPU replacement of HuffmanEncoder's data-proportional loops
+// (reference include/SZ3/encoder/HuffmanEncoder.hpp): the frequency count of init() (:516-527) and the serial bit
+// concatenation of encode() (:140-218).  The tree itself (a few thousand nodes) is built on the host
+// (huffman_host.cpp) from the histogram these kernels produce.
+//
+//   k_histogram      warp-aggregated atomics into a shared-memory window, spill to a 64-bit global histogram
+//                    (stand-alone variant for side streams; the main stream's histogram is fused into the
+//                    predict+quantize kernels, see device_ctx.cuh)
+//   k_pack_count     per-chunk code-length sums and unpredictable counts
+//   k_pack_scan      exclusive scan of the chunk sums (single CTA)
+//   k_pack_write     warp-prefix-scan bit packer: every thread concatenates its symbols in registers, the CTA
+//                    assembles its bit range in shared memory and stores it coalesced, MSB-first as the reference
+//                    decoder expects (:239-243); the same pass compacts the unpredictable values in stream order.
+#include <cuda_runtime.h>
+
+#include "launch.hpp"
+
+namespace sz3b {
+
+constexpr int kPackThreads = 256;
+constexpr int kPackPerThread = 16;
+constexpr int kPackChunk = kPackThreads * kPackPerThread;  // 4096 symbols per CTA
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <class QT>
+__global__ void __launch_bounds__(256) k_histogram(const QT *__restrict__ q, uint64_t n, int sym_min, int nbins,
+                                                   int center, unsigned long long *__restrict__ ghist) {
+    constexpr int W = 2048;
+    __shared__ unsigned sh[W];
+    for (int i = threadIdx.x; i < W; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int lo = center - W / 2;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    const uint64_t nround = (n + stride - 1) / stride;
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (uint64_t r = 0; r < nround; r++, i += stride) {
+        bool active = i < n;
+        int sym = active ? static_cast<int>(q[i]) - sym_min : -1;
+        // warp-aggregated: one atomic per distinct symbol per warp
+        unsigned peers = __match_any_sync(0xffffffffu, sym);
+        int leader = __ffs(peers) - 1;
+        if (active && static_cast<int>(threadIdx.x & 31) == leader) {
+            unsigned c = __popc(peers);
+            unsigned k = static_cast<unsigned>(sym - lo);
+            if (k < static_cast<unsigned>(W))
+                atomicAdd(&sh[k], c);
+            else if (sym >= 0 && sym < nbins)
+                atomicAdd(&ghist[sym], static_cast<unsigned long long>(c));
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < W; k += blockDim.x) {
+        unsigned v = sh[k];
+        int sym = lo + k;
+        if (v && sym >= 0 && sym < nbins) atomicAdd(&ghist[sym], static_cast<unsigned long long>(v));
+    }
+}
+
+template <class QT>
+__global__ void __launch_bounds__(256) k_minmax_int(const QT *__restrict__ q, uint64_t n, int *__restrict__ mm) {
+    int lo = 0x7fffffff, hi = static_cast<int>(0x80000000);
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int v = static_cast<int>(q[i]);
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[0], lo);
+        atomicMax(&mm[1], hi);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one 32-bit value per thread (256 threads); returns the exclusive prefix, total in *tot
+__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned *warp_sums, unsigned *tot) {
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= static_cast<unsigned>(o)) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned w = lane < (kPackThreads / 32) ? warp_sums[lane] : 0;
+        unsigned winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= static_cast<unsigned>(o)) winc += t;
+        }
+        if (lane < (kPackThreads / 32)) warp_sums[lane] = winc - w;
+        if (lane == (kPackThreads / 32) - 1) *tot = winc;
+    }
+    __syncthreads();
+    unsigned r = warp_sums[wid] + inc - v;
+    return r;
+}
+
+template <class QT>
+__global__ void __launch_bounds__(kPackThreads) k_pack_count(const QT *__restrict__ q, uint64_t n, int sym_min,
+                                                             int zero_sym, const uint8_t *__restrict__ len,
+                                                             unsigned *__restrict__ chunk_bits,
+                                                             unsigned *__restrict__ chunk_zeros) {
+    __shared__ unsigned ws[kPackThreads / 32];
+    __shared__ unsigned wz[kPackThreads / 32];
+    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kPackChunk + static_cast<uint64_t>(threadIdx.x) * kPackPerThread;
+    unsigned bits = 0, zeros = 0;
+#pragma unroll
+    for (int k = 0; k < kPackPerThread; k++) {
+        uint64_t i = base + k;
+        if (i < n) {
+            int v = static_cast<int>(q[i]);
+            bits += len[v - sym_min];
+            zeros += (v == zero_sym);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        bits += __shfl_xor_sync(0xffffffffu, bits, o);
+        zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        ws[threadIdx.x >> 5] = bits;
+        wz[threadIdx.x >> 5] = zeros;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned b = 0, z = 0;
+        for (int w = 0; w < kPackThreads / 32; w++) {
+            b += ws[w];
+            z += wz[w];
+        }
+        chunk_bits[blockIdx.x] = b;
+        chunk_zeros[blockIdx.x] = z;
+    }
+}
+
+// single CTA; off arrays get nchunks+1 entries (last = total)
+__global__ void __launch_bounds__(1024) k_pack_scan(const unsigned *__restrict__ chunk_bits,
+                                                    const unsigned *__restrict__ chunk_zeros, uint64_t nchunks,
+                                                    unsigned long long *__restrict__ bit_off,
+                                                    unsigned long long *__restrict__ zero_off) {
+    __shared__ unsigned long long wsum[2][32];
+    __shared__ unsigned long long carry[2];
+    if (threadIdx.x == 0) carry[0] = carry[1] = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < nchunks; base += 1024) {
+        uint64_t i = base + threadIdx.x;
+        unsigned long long v[2] = {i < nchunks ? chunk_bits[i] : 0ull, i < nchunks ? chunk_zeros[i] : 0ull};
+        unsigned long long inc[2] = {v[0], v[1]};
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t0 = __shfl_up_sync(0xffffffffu, inc[0], o);
+            unsigned long long t1 = __shfl_up_sync(0xffffffffu, inc[1], o);
+            if (lane >= static_cast<unsigned>(o)) {
+                inc[0] += t0;
+                inc[1] += t1;
+            }
+        }
+        if (lane == 31) {
+            wsum[0][wid] = inc[0];
+            wsum[1][wid] = inc[1];
+        }
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long w0 = wsum[0][lane], w1 = wsum[1][lane];
+            unsigned long long i0 = w0, i1 = w1;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long t0 = __shfl_up_sync(0xffffffffu, i0, o);
+                unsigned long long t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                if (lane >= static_cast<unsigned>(o)) {
+                    i0 += t0;
+                    i1 += t1;
+                }
+            }
+            wsum[0][lane] = i0 - w0;
+            wsum[1][lane] = i1 - w1;
+        }
+        __syncthreads();
+        unsigned long long e0 = carry[0] + wsum[0][wid] + inc[0] - v[0];
+        unsigned long long e1 = carry[1] + wsum[1][wid] + inc[1] - v[1];
+        if (i < nchunks) {
+            bit_off[i] = e0;
+            zero_off[i] = e1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            carry[0] = e0 + v[0];
+            carry[1] = e1 + v[1];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        bit_off[nchunks] = carry[0];
+        zero_off[nchunks] = carry[1];
+    }
+}
+
+// Bit accumulator: `acc` holds `nacc` (< 32 between appends) pending bits, left-aligned in a 64-bit register.
+struct BitAcc {
+    unsigned long long acc;
+    unsigned nacc;
+    unsigned w;       // next word index in the CTA buffer
+    bool first;       // the next flushed word may be shared with the previous thread
+};
+
+__device__ __forceinline__ void acc_flush(BitAcc &a, unsigned *sbits) {
+    if (a.nacc >= 32) {
+        unsigned word = static_cast<unsigned>(a.acc >> 32);
+        if (a.first) {
+            atomicOr(&sbits[a.w], word);
+            a.first = false;
+        } else {
+            sbits[a.w] = word;
+        }
+        a.w++;
+        a.acc <<= 32;
+        a.nacc -= 32;
+    }
+}
+__device__ __forceinline__ void acc_put(BitAcc &a, unsigned bits, unsigned l, unsigned *sbits) {  // l <= 32
+    if (l == 0) return;
+    a.acc |= static_cast<unsigned long long>(bits) << (64 - a.nacc - l);
+    a.nacc += l;
+    acc_flush(a, sbits);
+}
+
+template <class QT, class T>
+__global__ void __launch_bounds__(kPackThreads) k_pack_write(const QT *__restrict__ q, uint64_t n, int sym_min,
+                                                             int zero_sym, const uint8_t *__restrict__ len,
+                                                             const unsigned long long *__restrict__ code,
+                                                             const unsigned long long *__restrict__ bit_off,
+                                                             const unsigned long long *__restrict__ zero_off,
+                                                             unsigned *__restrict__ out_words,
+                                                             const T *__restrict__ unpred_tmp,
+                                                             T *__restrict__ unpred_out) {
+    // worst case 4096 symbols x 64 bits + 31 leading bits
+    __shared__ unsigned sbits[kPackChunk * 2 + 2];
+    __shared__ unsigned warp_sums[kPackThreads / 32];
+    __shared__ unsigned tot_bits, tot_zeros;
+    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kPackChunk + static_cast<uint64_t>(threadIdx.x) * kPackPerThread;
+    int sym[kPackPerThread];
+    unsigned bits = 0, zeros = 0;
+#pragma unroll
+    for (int k = 0; k < kPackPerThread; k++) {
+        uint64_t i = base + k;
+        sym[k] = -1;
+        if (i < n) {
+            int v = static_cast<int>(q[i]);
+            sym[k] = v - sym_min;
+            bits += len[v - sym_min];
+            zeros += (v == zero_sym);
+        }
+    }
+    const unsigned long long B0 = bit_off[blockIdx.x];
+    const unsigned lead = static_cast<unsigned>(B0 & 31);
+    unsigned my_bit = block_excl_scan(bits, warp_sums, &tot_bits);
+    __syncthreads();
+    const unsigned nwords = (lead + tot_bits + 31) >> 5;
+    for (unsigned i = threadIdx.x; i < nwords; i += kPackThreads) sbits[i] = 0;
+    __syncthreads();
+    if (bits) {
+        unsigned b = lead + my_bit;
+        BitAcc a;
+        a.acc = 0;
+        a.nacc = b & 31;
+        a.w = b >> 5;
+        a.first = true;
+#pragma unroll
+        for (int k = 0; k < kPackPerThread; k++) {
+            if (sym[k] >= 0) {
+                unsigned l = len[sym[k]];
+                unsigned long long c = code[sym[k]];
+                if (l > 32) {
+                    acc_put(a, static_cast<unsigned>(c >> 32), l - 32, sbits);
+                    acc_put(a, static_cast<unsigned>(c), 32, sbits);
+                } else {
+                    acc_put(a, static_cast<unsigned>(c), l, sbits);
+                }
+            }
+        }
+        if (a.nacc) atomicOr(&sbits[a.w], static_cast<unsigned>(a.acc >> 32));
+    }
+    __syncthreads();
+    // store: stream bit 0 of a word is its MSB -> byte-swap to memory order
+    const unsigned long long W0 = B0 >> 5;
+    for (unsigned i = threadIdx.x; i < nwords; i += kPackThreads) {
+        unsigned w = __byte_perm(sbits[i], 0, 0x0123);
+        if (i == 0 || i == nwords - 1) {
+            if (w) atomicOr(&out_words[W0 + i], w);
+        } else {
+            out_words[W0 + i] = w;
+        }
+    }
+    // ordered compaction of the unpredictable values (LinearQuantizer::unpred, reference LinearQuantizer.hpp:63,68)
+    if (unpred_out != nullptr) {
+        unsigned my_zero = block_excl_scan(zeros, warp_sums, &tot_zeros);
+        if (zeros) {
+            unsigned long long zo = zero_off[blockIdx.x] + my_zero;
+#pragma unroll
+            for (int k = 0; k < kPackPerThread; k++) {
+                if (sym[k] >= 0 && sym[k] + sym_min == zero_sym) unpred_out[zo++] = unpred_tmp[base + k];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <class QT>
+void launch_histogram(const QT *q, uint64_t n, int sym_min, int nbins, int center, unsigned long long *ghist,
+                      cudaStream_t st) {
+    if (n == 0) return;
+    uint64_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_histogram<QT><<<static_cast<unsigned>(blocks), 256, 0, st>>>(q, n, sym_min, nbins, center, ghist);
+}
+
+template <class QT>
+void launch_minmax_int(const QT *q, uint64_t n, int *mm, cudaStream_t st) {
+    if (n == 0) return;
+    uint64_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_minmax_int<QT><<<static_cast<unsigned>(blocks), 256, 0, st>>>(q, n, mm);
+}
+
+uint64_t pack_num_chunks(uint64_t n) { return (n + kPackChunk - 1) / kPackChunk; }
+
+template <class QT, class T>
+void launch_pack(const QT *q, uint64_t n, int sym_min, int zero_sym, const uint8_t *len,
+                 const unsigned long long *code, unsigned *chunk_bits, unsigned *chunk_zeros,
+                 unsigned long long *bit_off, unsigned long long *zero_off, unsigned *out_words, const T *unpred_tmp,
+                 T *unpred_out, cudaStream_t st, cudaEvent_t after_scan) {
+    const uint64_t nchunks = pack_num_chunks(n);
+    if (nchunks == 0) return;
+    k_pack_count<QT><<<static_cast<unsigned>(nchunks), kPackThreads, 0, st>>>(q, n, sym_min, zero_sym, len, chunk_bits,
+                                                                             chunk_zeros);
+    k_pack_scan<<<1, 1024, 0, st>>>(chunk_bits, chunk_zeros, nchunks, bit_off, zero_off);
+    if (after_scan) cudaEventRecord(after_scan, st);
+    k_pack_write<QT, T><<<static_cast<unsigned>(nchunks), kPackThreads, 0, st>>>(
+        q, n, sym_min, zero_sym, len, code, bit_off, zero_off, out_words, unpred_tmp, unpred_out);
+}
+
+#define SZ3B_INST_Q(QT)                                                                                              \
+    template void launch_histogram<QT>(const QT *, uint64_t, int, int, int, unsigned long long *, cudaStream_t);    \
+    template void launch_minmax_int<QT>(const QT *, uint64_t, int *, cudaStream_t);
+SZ3B_INST_Q(uint16_t)
+SZ3B_INST_Q(uint32_t)
+SZ3B_INST_Q(int32_t)
+#define SZ3B_INST_P(QT, T)                                                                                           \
+    template void launch_pack<QT, T>(const QT *, uint64_t, int, int, const uint8_t *, const unsigned long long *,    \
+                                     unsigned *, unsigned *, unsigned long long *, unsigned long long *, unsigned *, \
+                                     const T *, T *, cudaStream_t, cudaEvent_t);
+SZ3B_INST_P(uint16_t, float)
+SZ3B_INST_P(uint16_t, double)
+SZ3B_INST_P(uint32_t, float)
+SZ3B_INST_P(uint32_t, double)
+SZ3B_INST_P(int32_t, float)
+SZ3B_INST_P(int32_t, double)
+
+}  // namespace sz3b

@@ -1,0 +1,255 @@
+// sz3_b200/csrc/huffman_host.cpp -- see huffman_host.hpp.
+#include "huffman_host.hpp"
+
+#include <string.h>
+
+#include <utility>
+
+namespace sz3b {
+namespace {
+
+struct Node {
+    int left = -1, right = -1;
+    uint64_t freq = 0;
+    int sym = 0;      // state for leaves, 0 for internal nodes (the reference's pool is zero-initialised)
+    uint8_t leaf = 0;
+};
+
+// 1-indexed binary min-heap of node ids keyed by freq, with the reference's exact sift rules
+// (HuffmanEncoder.hpp:440-470): ties keep insertion-dependent order, which fixes the tree shape.
+struct Heap {
+    std::vector<int> a;
+    const std::vector<Node> *nodes;
+    explicit Heap(const std::vector<Node> *n, size_t cap) : a(cap + 2), nodes(n) {}
+    int end = 1;
+    uint64_t f(int id) const { return (*nodes)[id].freq; }
+    void push(int id) {
+        int i = end++;
+        for (int j; (j = i >> 1) != 0; i = j) {
+            if (f(a[j]) <= f(id)) break;
+            a[i] = a[j];
+        }
+        a[i] = id;
+    }
+    int pop() {
+        if (end < 2) return -1;
+        int top = a[1];
+        end--;
+        a[1] = a[end];
+        int i = 1, l;
+        while ((l = i << 1) < end) {
+            if (l + 1 < end && f(a[l + 1]) < f(a[l])) l++;
+            if (f(a[i]) > f(a[l])) {
+                std::swap(a[i], a[l]);
+                i = l;
+            } else {
+                break;
+            }
+        }
+        return top;
+    }
+};
+
+inline void put_be32(uint8_t *p, uint32_t v) {
+    p[0] = static_cast<uint8_t>(v >> 24);
+    p[1] = static_cast<uint8_t>(v >> 16);
+    p[2] = static_cast<uint8_t>(v >> 8);
+    p[3] = static_cast<uint8_t>(v);
+}
+inline uint32_t get_be32(const uint8_t *p) {
+    return (static_cast<uint32_t>(p[0]) << 24) | (static_cast<uint32_t>(p[1]) << 16) |
+           (static_cast<uint32_t>(p[2]) << 8) | p[3];
+}
+
+template <class W>
+void write_links(uint8_t *dst, const std::vector<uint32_t> &v) {
+    for (size_t i = 0; i < v.size(); i++) {
+        W w = static_cast<W>(v[i]);
+        memcpy(dst + i * sizeof(W), &w, sizeof(W));
+    }
+}
+
+}  // namespace
+
+bool huffman_build(const unsigned long long *hist, size_t nbins, int sym_base, HuffmanBook &book, const char **err) {
+    size_t lo = nbins, hi = 0;
+    for (size_t k = 0; k < nbins; k++) {
+        if (hist[k]) {
+            if (lo == nbins) lo = k;
+            hi = k;
+        }
+    }
+    if (lo == nbins) {
+        if (err) *err = "Huffman bins should not be empty";
+        return false;
+    }
+    book.offset = sym_base + static_cast<int>(lo);
+    book.state_num = static_cast<uint32_t>(hi - lo + 2);
+    const size_t states = book.state_num;
+    book.code.assign(states, 0);
+    book.len.assign(states, 0);
+
+    std::vector<Node> nodes;
+    nodes.reserve(2 * states);
+    Heap heap(&nodes, 2 * states);
+    size_t distinct = 0;
+    for (size_t k = lo; k <= hi; k++) {
+        if (!hist[k]) continue;
+        Node nd;
+        nd.freq = hist[k];
+        nd.sym = static_cast<int>(k - lo);
+        nd.leaf = 1;
+        nodes.push_back(nd);
+        heap.push(static_cast<int>(nodes.size()) - 1);
+        distinct++;
+    }
+    while (heap.end > 2) {
+        int l = heap.pop();
+        int r = heap.pop();
+        Node nd;
+        nd.left = l;
+        nd.right = r;
+        nd.freq = nodes[l].freq + nodes[r].freq;
+        nodes.push_back(nd);
+        heap.push(static_cast<int>(nodes.size()) - 1);
+    }
+    const int root = heap.a[1];
+    book.node_count = static_cast<uint32_t>(2 * distinct - 1);
+
+    // pre-order walk: assigns the serialisation ids of pad_tree and the codes of build_code in one pass
+    const uint32_t nc = book.node_count;
+    std::vector<uint32_t> L(nc, 0), R(nc, 0);
+    std::vector<int> C(nc, 0);
+    std::vector<uint8_t> t(nc, 0);
+    uint32_t next_id = 0;
+    book.total_bits = 0;
+    book.max_len = 0;
+    // pad_tree numbers a node when it is first visited in pre-order (the whole left subtree before the right
+    // child); an explicit stack with the left child pushed last pops nodes in exactly that order.
+    struct Frame {
+        int node;
+        int depth;
+        uint64_t bits;
+        int parent_id;   // serialisation id of the parent, -1 for the root
+        bool is_right;
+    };
+    std::vector<Frame> st;
+    st.push_back({root, 0, 0, -1, false});
+    bool too_long = false;
+    while (!st.empty()) {
+        Frame fr = st.back();
+        st.pop_back();
+        uint32_t id = next_id++;
+        if (fr.parent_id >= 0) {
+            if (fr.is_right)
+                R[fr.parent_id] = id;
+            else
+                L[fr.parent_id] = id;
+        }
+        const Node &nd = nodes[fr.node];
+        C[id] = nd.sym;
+        t[id] = nd.leaf;
+        if (nd.leaf) {
+            if (fr.depth > 64) {
+                too_long = true;
+            } else {
+                book.code[nd.sym] = fr.bits;
+                book.len[nd.sym] = static_cast<uint8_t>(fr.depth);
+                book.total_bits += nd.freq * static_cast<uint64_t>(fr.depth);
+                if (fr.depth > book.max_len) book.max_len = fr.depth;
+            }
+        } else {
+            uint64_t b = fr.depth < 64 ? (fr.bits << 1) : 0;
+            // push right first so that the left subtree is numbered first
+            st.push_back({nd.right, fr.depth + 1, b | 1, static_cast<int>(id), true});
+            st.push_back({nd.left, fr.depth + 1, b, static_cast<int>(id), false});
+        }
+    }
+    if (too_long) {
+        if (err) *err = "Huffman code longer than 64 bits is not supported by the GPU packer";
+        return false;
+    }
+
+    // HuffmanEncoder::save (:108-125)
+    const size_t lw = nc <= 256 ? 1 : (nc <= 65536 ? 2 : 4);
+    const size_t blob = 4 + 4 + 4 + 1 + 2 * nc * lw + nc * sizeof(int) + nc;
+    book.tree_blob.assign(blob, 0);
+    uint8_t *p = book.tree_blob.data();
+    memcpy(p, &book.offset, 4);
+    put_be32(p + 4, nc);
+    put_be32(p + 8, book.state_num / 2);
+    p += 12;
+    *p++ = 0;  // sysEndianType: little endian host
+    if (lw == 1) {
+        write_links<uint8_t>(p, L);
+        write_links<uint8_t>(p + nc, R);
+    } else if (lw == 2) {
+        write_links<uint16_t>(p, L);
+        write_links<uint16_t>(p + 2 * nc, R);
+    } else {
+        write_links<uint32_t>(p, L);
+        write_links<uint32_t>(p + 4 * static_cast<size_t>(nc), R);
+    }
+    p += 2 * nc * lw;
+    memcpy(p, C.data(), nc * sizeof(int));
+    p += nc * sizeof(int);
+    memcpy(p, t.data(), nc);
+    return true;
+}
+
+bool huffman_decode(const uint8_t *&pos, size_t &remaining, size_t n, std::vector<int> &out, const char **err) {
+    auto fail = [&](const char *m) {
+        if (err) *err = m;
+        return false;
+    };
+    if (remaining < 13) return fail("huffman: truncated header");
+    int offset;
+    memcpy(&offset, pos, 4);
+    const uint32_t nc = get_be32(pos + 4);
+    const uint8_t *p = pos + 13;
+    const size_t lw = nc <= 256 ? 1 : (nc <= 65536 ? 2 : 4);
+    const size_t body = 2 * static_cast<size_t>(nc) * lw + static_cast<size_t>(nc) * 5;
+    if (nc == 0 || remaining < 13 + body + 8) return fail("huffman: truncated tree");
+    std::vector<uint32_t> L(nc), R(nc);
+    for (uint32_t i = 0; i < nc; i++) {
+        uint32_t l = 0, r = 0;
+        memcpy(&l, p + i * lw, lw);
+        memcpy(&r, p + (nc + static_cast<size_t>(i)) * lw, lw);
+        L[i] = l;
+        R[i] = r;
+    }
+    const uint8_t *pc = p + 2 * static_cast<size_t>(nc) * lw;
+    const uint8_t *pt = pc + static_cast<size_t>(nc) * 4;
+    std::vector<int> C(nc);
+    memcpy(C.data(), pc, static_cast<size_t>(nc) * 4);
+    p = pt + nc;
+    uint64_t enc_len;
+    memcpy(&enc_len, p, 8);
+    p += 8;
+    size_t used = static_cast<size_t>(p - pos);
+    if (remaining < used + enc_len) return fail("huffman: truncated bitstream");
+    out.resize(n);
+    if (pt[0]) {  // single-symbol tree (:233-237)
+        for (size_t i = 0; i < n; i++) out[i] = C[0] + offset;
+    } else {
+        uint32_t node = 0;
+        size_t cnt = 0;
+        const uint64_t nbits = enc_len * 8;
+        for (uint64_t b = 0; cnt < n; b++) {
+            if (b >= nbits) return fail("huffman: bitstream exhausted");
+            uint32_t bit = (p[b >> 3] >> (7 - (b & 7))) & 1u;
+            node = bit ? R[node] : L[node];
+            if (node == 0 || node >= nc) return fail("huffman: bad tree link");
+            if (pt[node]) {
+                out[cnt++] = C[node] + offset;
+                node = 0;
+            }
+        }
+    }
+    p += enc_len;
+    remaining -= static_cast<size_t>(p - pos);
+    pos = p;
+    return true;
+}
+
+}  // namespace sz3b

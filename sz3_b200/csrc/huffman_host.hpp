@@ -1,0 +1,35 @@
+// sz3_b200/csrc/huffman_host.hpp -- host part of the Huffman stage: tree construction from a histogram, the tree
+// blob of HuffmanEncoder::save and the (code, length) table the GPU bit packer consumes.
+//
+// Restates reference include/SZ3/encoder/HuffmanEncoder.hpp:516-561 (init), :440-470 (priority queue),
+// :478-508 (build_code), :563-579 + :601-628 (pad_tree / tree bytes), :108-125 (save), :261-279 (load).
+// The tree must be *identical* to the reference's (same heap tie-breaks, leaves inserted in ascending symbol
+// order), otherwise the bitstream differs; the data-proportional work (histogram, packing) runs on the GPU.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <vector>
+
+namespace sz3b {
+
+struct HuffmanBook {
+    int offset = 0;                 // smallest symbol (HuffmanEncoder::offset)
+    uint32_t state_num = 0;         // max - offset + 2
+    uint32_t node_count = 0;        // 2 * distinct - 1
+    std::vector<uint64_t> code;     // per state (symbol - offset): code bits, right-aligned
+    std::vector<uint8_t> len;       // per state: code length in bits (0 for absent symbols and for the 1-symbol tree)
+    std::vector<uint8_t> tree_blob; // exactly what HuffmanEncoder::save writes
+    uint64_t total_bits = 0;        // sum over symbols of freq * len
+    int max_len = 0;
+};
+
+// hist[k] = frequency of symbol (sym_base + k), k in [0, nbins).  Returns false (with *err set) when the histogram
+// is empty or a code is longer than 64 bits (the GPU packer's limit; unreachable below ~1e13 symbols).
+bool huffman_build(const unsigned long long *hist, size_t nbins, int sym_base, HuffmanBook &book, const char **err);
+
+// Decoder side (used by decompression): parses the blob written by save and decodes n symbols from a bitstream
+// laid out as `size_t outSize | bits`.  Advances *pos past everything it consumed.  Returns false on malformed input.
+bool huffman_decode(const uint8_t *&pos, size_t &remaining, size_t n, std::vector<int> &out, const char **err);
+
+}  // namespace sz3b

@@ -1,0 +1,122 @@
+// sz3_b200/csrc/interp_kernels.cu -- __global__ wrappers + launchers of the fused interpolation predict+quantize
+// kernels (bodies in interp_body.cuh).  Compiled with -fmad=false: the reference arithmetic has no FMA contraction.
+#include <cuda_runtime.h>
+
+#include "device_ctx.cuh"
+#include "interp_body.cuh"
+#include "launch.hpp"
+
+namespace sz3b {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// anchors / first element (reference InterpolationDecomposition.hpp:92-98, 215-222)
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, class QT>
+__global__ void __launch_bounds__(256) k_interp_anchor(InterpArgs<T, QT> A, uint32_t anchor_stride, uint64_t n_anchor) {
+    const uint32_t batch = blockIdx.y;
+    const uint64_t gid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= n_anchor) return;
+    const InterpShape &sh = A.sh;
+    const T *dat = A.data + batch * A.data_bstride;
+    if (anchor_stride == 0) {
+        // no anchor grid: the first element is quantized against a zero prediction (:92-93)
+        T rec;
+        int qv = quantize<T>(dat[0], static_cast<T>(0), A.qp, rec);
+        uint64_t pos = batch * A.q_bstride;
+        A.q[pos] = static_cast<QT>(qv);
+        if (qv == 0) A.unpred_tmp[pos] = dat[0];
+        if (A.work) A.work[batch * A.data_bstride] = rec;
+        if (A.recon2) A.recon2[batch * A.recon2_bstride] = rec;
+        atomicAdd(&A.hist[qv], 1ull);
+        return;
+    }
+    uint64_t r = gid, off = 0, off2 = 0;
+    bool even = true;
+    for (int d = sh.N - 1; d >= 0; d--) {
+        uint32_t ext = (sh.dims[d] - 1) / anchor_stride + 1;
+        uint32_t x = static_cast<uint32_t>(r % ext) * anchor_stride;
+        r /= ext;
+        off += x * sh.stride[d];
+        off2 += (x >> 1) * A.stride2[d];
+        even = even && !(x & 1);
+    }
+    T v = dat[off];
+    uint64_t pos = batch * A.q_bstride + gid;
+    A.q[pos] = 0;
+    A.unpred_tmp[pos] = v;
+    if (A.work) A.work[batch * A.data_bstride + off] = v;
+    if (A.recon2 && even) A.recon2[batch * A.recon2_bstride + off2] = v;
+    if (gid == 0) atomicAdd(&A.hist[0], static_cast<unsigned long long>(n_anchor));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tile schedule, N == 3
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, class QT>
+__global__ void __launch_bounds__(kTileThreads) k_interp_tile(InterpArgs<T, QT> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    unsigned *shist = reinterpret_cast<unsigned *>(smem_raw + sizeof(T) * kTileSmemElems);
+    __shared__ TileGeom tg;
+    DevCtx ctx(shist, A.hist, A.qp.radius);
+    ctx.clear();
+    if (threadIdx.x == 0) tile_geom(A, blockIdx.x, blockIdx.y, tg);
+    __syncthreads();
+    tile_body(A, ctx, sm, tg, blockIdx.y);
+    ctx.flush();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// generic schedule, any N
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, class QT>
+__global__ void __launch_bounds__(256) k_interp_pass(InterpArgs<T, QT> A, int p, uint64_t total) {
+    __shared__ unsigned shist[kHistWindow];
+    DevCtx ctx(shist, A.hist, A.qp.radius);
+    ctx.clear();
+    const uint64_t gid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    pass_point(A, ctx, p, gid, total, blockIdx.y);
+    ctx.flush();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, class QT>
+void interp_launch_anchors(const InterpArgs<T, QT> &A, uint32_t anchor_stride, uint64_t n_anchor, uint32_t nbatch,
+                           cudaStream_t st) {
+    dim3 grid(static_cast<unsigned>((n_anchor + 255) / 256), nbatch);
+    k_interp_anchor<T, QT><<<grid, 256, 0, st>>>(A, anchor_stride, n_anchor);
+}
+
+template <class T, class QT>
+void interp_launch_tiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_interp_tile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        attr_set = true;
+    }
+    dim3 grid(static_cast<unsigned>(ntiles), nbatch);
+    k_interp_tile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
+}
+
+template <class T, class QT>
+void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cudaStream_t st) {
+    uint64_t total = pass_points(A, p);
+    if (total == 0) return;
+    dim3 grid(static_cast<unsigned>((total + 255) / 256), nbatch);
+    k_interp_pass<T, QT><<<grid, 256, 0, st>>>(A, p, total);
+}
+
+#define SZ3B_INST(T, QT)                                                                                         \
+    template void interp_launch_anchors<T, QT>(const InterpArgs<T, QT> &, uint32_t, uint64_t, uint32_t,        \
+                                               cudaStream_t);                                                   \
+    template void interp_launch_tiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);      \
+    template void interp_launch_pass<T, QT>(const InterpArgs<T, QT> &, int, uint32_t, cudaStream_t);
+SZ3B_INST(float, uint16_t)
+SZ3B_INST(float, uint32_t)
+SZ3B_INST(double, uint16_t)
+SZ3B_INST(double, uint32_t)
+
+}  // namespace sz3b

@@ -1,0 +1,47 @@
+// sz3_b200/csrc/launch.hpp -- host-callable launchers of every CUDA kernel in the library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "core.cuh"
+
+namespace sz3b {
+
+template <class T, class QT>
+struct InterpArgs;
+
+// interp_kernels.cu
+template <class T, class QT>
+void interp_launch_anchors(const InterpArgs<T, QT> &A, uint32_t anchor_stride, uint64_t n_anchor, uint32_t nbatch,
+                           cudaStream_t st);
+template <class T, class QT>
+void interp_launch_tiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st);
+template <class T, class QT>
+void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cudaStream_t st);
+
+// encode_kernels.cu
+template <class QT>
+void launch_histogram(const QT *q, uint64_t n, int sym_min, int nbins, int center, unsigned long long *ghist,
+                      cudaStream_t st);
+template <class QT>
+void launch_minmax_int(const QT *q, uint64_t n, int *mm, cudaStream_t st);
+uint64_t pack_num_chunks(uint64_t n);
+template <class QT, class T>
+void launch_pack(const QT *q, uint64_t n, int sym_min, int zero_sym, const uint8_t *len,
+                 const unsigned long long *code, unsigned *chunk_bits, unsigned *chunk_zeros,
+                 unsigned long long *bit_off, unsigned long long *zero_off, unsigned *out_words, const T *unpred_tmp,
+                 T *unpred_out, cudaStream_t st, cudaEvent_t after_scan);
+
+// misc_kernels.cu
+template <class T>
+void launch_minmax(const T *data, uint64_t n, T *mm /* device: [min, max] */, cudaStream_t st);
+template <class T>
+void launch_profile_blocks(const T *data, int N, const uint32_t *dims, uint32_t block, uint32_t pstride, double abs_eb,
+                           uint8_t *flags, uint64_t nblocks, cudaStream_t st);
+template <class T>
+void launch_gather_cubes(const T *data, int N, const uint32_t *dims, uint32_t edge, const uint64_t *starts,
+                         uint32_t ncubes, T *out, cudaStream_t st);
+template <class QT>
+void launch_widen(const QT *q, uint64_t n, int32_t *out, cudaStream_t st);
+
+}  // namespace sz3b

@@ -1,0 +1,748 @@
+// sz3_b200/csrc/pipeline.cu -- host orchestration of the GPU compression pipelines.
+//
+// Mirrors, stage by stage, the reference call stack:
+//   SZ_compress_dispatcher      include/SZ3/api/impl/SZDispatcher.hpp:13-76
+//   SZ_compress_Interp          include/SZ3/api/impl/SZAlgoInterp.hpp:17-30
+//   SZ_compress_Interp_lorenzo  include/SZ3/api/impl/SZAlgoInterp.hpp:122-286   (auto-tuner)
+//   SZGenericCompressor         include/SZ3/compressor/SZGenericCompressor.hpp:38-63
+//   SZ_compress_OMP             include/SZ3/api/impl/SZImplOMP.hpp:16-117
+// but every data-proportional loop is a CUDA kernel; the host only builds the Huffman tree from the histogram,
+// lays out the byte stream and runs zstd.  There is no CPU implementation of the kernels to fall back to.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "huffman_host.hpp"
+#include "interp_body.cuh"
+#include "interp_plan.hpp"
+#include "launch.hpp"
+#include "pipeline.hpp"
+#include "stream_host.hpp"
+
+namespace sz3b {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// workspace pool
+// ---------------------------------------------------------------------------------------------------------------------
+static std::mutex g_pool_mu;
+static std::vector<Workspace *> g_pool;
+
+Workspace *workspace_acquire() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) throw CudaError{e, "cudaGetDevice (is a CUDA device visible? this library has no CPU path)", __FILE__, __LINE__};
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); i++) {
+            if (g_pool[i]->device == dev) {
+                Workspace *ws = g_pool[i];
+                g_pool.erase(g_pool.begin() + i);
+                ws->prof_reset();
+                return ws;
+            }
+        }
+    }
+    Workspace *ws = new Workspace();
+    ws->device = dev;
+    SZ3B_CUDA(cudaStreamCreateWithFlags(&ws->st, cudaStreamNonBlocking));
+    return ws;
+}
+
+void workspace_release(Workspace *ws) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.push_back(ws);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T>
+static const T *to_device(Workspace &ws, const T *data, int loc, size_t num) {
+    if (loc == SZ3B_DEVICE) return data;
+    T *d = ws.data.as<T>(num);
+    size_t h = ws.stage_begin("h2d_input");
+    SZ3B_CUDA(cudaMemcpyAsync(d, data, num * sizeof(T), cudaMemcpyHostToDevice, ws.st));
+    ws.stage_end(h, 0);
+    return d;
+}
+
+template <class T>
+void minmax_stage(Workspace &ws, const T *data, int loc, size_t num, double *mn, double *mx) {
+    const T *d = to_device(ws, data, loc, num);
+    T *mm = ws.misc.as<T>(2);
+    size_t h = ws.stage_begin("minmax");
+    launch_minmax<T>(d, num, mm, ws.st);
+    ws.stage_end(h, 2);
+    T hmm[2];
+    SZ3B_CUDA(cudaMemcpyAsync(hmm, mm, sizeof(hmm), cudaMemcpyDeviceToHost, ws.st));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    *mn = static_cast<double>(hmm[0]);
+    *mx = static_cast<double>(hmm[1]);
+}
+
+// calAbsErrorBound (Statistic.hpp:24-56); `range` > 0 skips the scan (OMP path).  d_data is device resident.
+template <class T>
+static void resolve_abs_eb(Workspace &ws, sz3b_config &conf, const T *d_data, T range) {
+    if (conf.errorBoundMode == SZ3B_EB_ABS) return;
+    auto get_range = [&]() -> T {
+        if (range > 0) return range;
+        double mn, mx;
+        minmax_stage<T>(ws, d_data, SZ3B_DEVICE, config_num(conf), &mn, &mx);
+        return static_cast<T>(static_cast<T>(mx) - static_cast<T>(mn));   // T subtraction as data_range()
+    };
+    switch (conf.errorBoundMode) {
+        case SZ3B_EB_REL:
+            conf.absErrorBound = conf.relErrorBound * get_range();
+            break;
+        case SZ3B_EB_PSNR: {
+            double v1 = conf.psnrErrorBound + 10 * log10(1 - 2.0 / 3.0 * 0.99);
+            double v2 = v1 / (-20);
+            double v3 = pow(10, v2);
+            conf.absErrorBound = get_range() * v3;
+            break;
+        }
+        case SZ3B_EB_L2NORM:
+            conf.absErrorBound = sqrt(3.0 / config_num(conf)) * conf.l2normErrorBound;
+            break;
+        case SZ3B_EB_ABS_AND_REL:
+            conf.absErrorBound = std::min(conf.absErrorBound, conf.relErrorBound * get_range());
+            break;
+        case SZ3B_EB_ABS_OR_REL:
+            conf.absErrorBound = std::max(conf.absErrorBound, conf.relErrorBound * get_range());
+            break;
+        default:
+            fail(SZ3B_E_INVALID_ARGUMENT, "Error bound mode not supported");
+    }
+    conf.errorBoundMode = SZ3B_EB_ABS;
+}
+
+template <class T>
+double abs_eb_stage(Workspace &ws, const sz3b_config &conf, const T *data, int loc) {
+    sz3b_config c = conf;
+    const T *d = c.errorBoundMode == SZ3B_EB_ABS || c.errorBoundMode == SZ3B_EB_L2NORM
+                     ? data
+                     : to_device(ws, data, loc, config_num(c));
+    resolve_abs_eb<T>(ws, c, d, static_cast<T>(0));
+    return c.absErrorBound;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// interpolation decomposition on the device
+// ---------------------------------------------------------------------------------------------------------------------
+struct IndexStream {       // device-resident result of a decomposition
+    void *q = nullptr;     // QT[n]
+    void *unpred_tmp = nullptr;
+    unsigned long long *hist = nullptr;
+    uint64_t n = 0;
+    int radius = 0;
+    bool wide = false;     // QT = uint32 (radius > 32768)
+};
+
+template <class T, class QT>
+static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uint32_t nbatch, int radius, QT *d_q,
+                       T *d_unpred_tmp, unsigned long long *d_hist, DevBuf &recon_buf, int *launches) {
+    InterpArgs<T, QT> A;
+    memset(&A, 0, sizeof(A));
+    A.sh = pl.sh;
+    A.data = d_data;
+    A.data_bstride = pl.num;
+    A.q_bstride = pl.num;
+    A.recon2_bstride = pl.num2;
+    for (int d = 0; d < kMaxDim; d++) {
+        A.dims2[d] = pl.dims2[d];
+        A.stride2[d] = pl.stride2[d];
+    }
+    if (pl.tile) {
+        A.recon2 = recon_buf.as<T>(pl.num2 * nbatch);
+        A.work = nullptr;
+    } else {
+        A.work = recon_buf.as<T>(pl.num * nbatch);
+        A.recon2 = nullptr;
+    }
+    A.q = d_q;
+    A.unpred_tmp = d_unpred_tmp;
+    A.hist = d_hist;
+    uint64_t *d_table = ws.tables.as<uint64_t>(pl.table.size() + 1);
+    if (!pl.table.empty())
+        SZ3B_CUDA(cudaMemcpyAsync(d_table, pl.table.data(), pl.table.size() * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                  ws.st));
+    A.qp = make_quant(pl.eb, radius);
+    A.s = 0;
+    interp_launch_anchors<T, QT>(A, pl.anchor_stride, pl.n_first, nbatch, ws.st);
+    (*launches)++;
+    for (const LevelPlan &L : pl.levels) {
+        A.qp = make_quant(L.eb, radius);
+        A.s = L.s;
+        for (int d = 0; d < kMaxDim; d++) A.nb[d] = L.nb[d];
+        A.block_base = d_table + L.table_off;
+        if (pl.tile) {
+            interp_launch_tiles<T, QT>(A, L.nblocks, nbatch, ws.st);
+            (*launches)++;
+        } else {
+            for (int p = 0; p < pl.sh.N; p++) {
+                if (pass_points(A, p) == 0) continue;
+                interp_launch_pass<T, QT>(A, p, nbatch, ws.st);
+                (*launches)++;
+            }
+        }
+    }
+    SZ3B_CUDA(cudaGetLastError());
+}
+
+// InterpolationDecomposition::save (:149-159) + LinearQuantizer::save (:95-104) up to (excluding) the unpred values
+template <class T>
+static size_t interp_save_header(const InterpPlan &pl, int radius, uint64_t n_unpred, uint8_t *out) {
+    uint8_t *p = out;
+    for (int d = 0; d < pl.sh.N; d++) put<uint64_t>(p, pl.sh.dims[d]);
+    put<uint32_t>(p, kInterpBlock);
+    put<int32_t>(p, pl.interp_id);
+    put<int32_t>(p, pl.direction);
+    put<uint64_t>(p, pl.anchor_stride);
+    put<double>(p, pl.alpha);
+    put<double>(p, pl.beta);
+    put<uint8_t>(p, 2);  // LinearQuantizer uid
+    put<double>(p, pl.eb);
+    put<int32_t>(p, radius);
+    put<uint64_t>(p, n_unpred);
+    return static_cast<size_t>(p - out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Huffman stage: histogram (already on the device) -> host tree -> GPU bit packer.  Produces, in pinned host memory
+// at `dst`:  tree blob | size_t n | size_t outSize | bits ; and the unpredictable values (stream order) at unpred_dst.
+// ---------------------------------------------------------------------------------------------------------------------
+struct EncodeLayout {
+    size_t tree_len = 0;
+    size_t out_size = 0;     // bytes of Huffman bits
+    uint64_t n_unpred = 0;
+};
+
+template <class QT, class T>
+static void encode_indices(Workspace &ws, const QT *d_q, uint64_t n, const unsigned long long *d_hist, int nbins,
+                           int sym_base, bool has_unpred, const T *d_unpred_tmp, HuffmanBook &book, EncodeLayout &lay) {
+    unsigned long long *h_hist = static_cast<unsigned long long *>(ws.hist_host.ensure(sizeof(unsigned long long) * nbins));
+    SZ3B_CUDA(cudaMemcpyAsync(h_hist, d_hist, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToHost, ws.st));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    double t0 = now_ms();
+    const char *err = nullptr;
+    if (!huffman_build(h_hist, nbins, sym_base, book, &err))
+        fail(strstr(err, "empty") ? SZ3B_E_INVALID_ARGUMENT : SZ3B_E_UNSUPPORTED, err);
+    ws.host_stage("huffman_tree_host", now_ms() - t0);
+    lay.tree_len = book.tree_blob.size();
+    lay.out_size = (book.total_bits + 7) / 8;
+    lay.n_unpred = has_unpred && sym_base == 0 ? h_hist[0] : 0;
+
+    size_t h = ws.stage_begin("huffman_pack");
+    const size_t states = book.state_num;
+    unsigned long long *d_code = ws.code.as<unsigned long long>(states);
+    uint8_t *d_len = ws.len.as<uint8_t>(states);
+    SZ3B_CUDA(cudaMemcpyAsync(d_code, book.code.data(), states * sizeof(uint64_t), cudaMemcpyHostToDevice, ws.st));
+    SZ3B_CUDA(cudaMemcpyAsync(d_len, book.len.data(), states, cudaMemcpyHostToDevice, ws.st));
+    const uint64_t nchunks = pack_num_chunks(n);
+    unsigned *d_cb = ws.chunk_bits.as<unsigned>(nchunks + 1);
+    unsigned *d_cz = ws.chunk_zeros.as<unsigned>(nchunks + 1);
+    unsigned long long *d_bo = ws.bit_off.as<unsigned long long>(nchunks + 2);
+    unsigned long long *d_zo = ws.zero_off.as<unsigned long long>(nchunks + 2);
+    const size_t nwords = (book.total_bits + 31) / 32 + 2;
+    unsigned *d_words = ws.out_words.as<unsigned>(nwords);
+    SZ3B_CUDA(cudaMemsetAsync(d_words, 0, nwords * sizeof(unsigned), ws.st));
+    T *d_unpred_out = lay.n_unpred ? ws.unpred_out.as<T>(lay.n_unpred) : nullptr;
+    launch_pack<QT, T>(d_q, n, book.offset, 0, d_len, d_code, d_cb, d_cz, d_bo, d_zo, d_words, d_unpred_tmp,
+                       d_unpred_out, ws.st, nullptr);
+    SZ3B_CUDA(cudaGetLastError());
+    ws.stage_end(h, 3);
+}
+
+// D2H of the packed bits / unpredictables into an assembled (pinned) buffer laid out as SZGenericCompressor does:
+//   decomposition.save | encoder.save | size_t n | size_t outSize | bits          (SZGenericCompressor.hpp:51-56)
+template <class T>
+static size_t assemble_stream(Workspace &ws, const uint8_t *decomp_hdr, size_t decomp_hdr_len, const EncodeLayout &lay,
+                              const HuffmanBook &book, uint64_t n, PinBuf &dstbuf, uint8_t **dst_out) {
+    const size_t total = decomp_hdr_len + lay.n_unpred * sizeof(T) + lay.tree_len + 16 + lay.out_size;
+    uint8_t *dst = static_cast<uint8_t *>(dstbuf.ensure(total + 16));
+    uint8_t *p = dst;
+    memcpy(p, decomp_hdr, decomp_hdr_len);
+    p += decomp_hdr_len;
+    size_t h = ws.stage_begin("d2h_stream");
+    if (lay.n_unpred)
+        SZ3B_CUDA(cudaMemcpyAsync(p, ws.unpred_out.p, lay.n_unpred * sizeof(T), cudaMemcpyDeviceToHost, ws.st));
+    p += lay.n_unpred * sizeof(T);
+    memcpy(p, book.tree_blob.data(), lay.tree_len);
+    p += lay.tree_len;
+    put<uint64_t>(p, n);
+    put<uint64_t>(p, lay.out_size);
+    if (lay.out_size) SZ3B_CUDA(cudaMemcpyAsync(p, ws.out_words.p, lay.out_size, cudaMemcpyDeviceToHost, ws.st));
+    p += lay.out_size;
+    ws.stage_end(h, 0);
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    *dst_out = dst;
+    return total;
+}
+
+struct TooSmall {};   // stands in for std::length_error(SZ3_ERROR_COMP_BUFFER_NOT_LARGE_ENOUGH)
+
+static size_t zstd_stage(Workspace &ws, const uint8_t *src, size_t len, uint8_t *dst, size_t cap, int threads) {
+    double t0 = now_ms();
+    bool small = false;
+    size_t r = zstd_compress_framed(src, len, dst, cap, threads, &small);
+    ws.host_stage("zstd_host", now_ms() - t0);
+    if (small) throw TooSmall{};
+    if (r == 0) fail(SZ3B_E_RUNTIME, "zstd compression failed");
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SZ_compress_Interp (SZAlgoInterp.hpp:17-30) for `nbatch` arrays of identical shape (nbatch > 1 only in the tuner,
+// where the index streams of all sampled cubes are merged before encoding, :50-56).
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, class QT>
+static size_t interp_compress_t(Workspace &ws, const sz3b_config &conf, const T *d_data, uint32_t nbatch, uint8_t *dst,
+                                size_t cap, int zstd_threads, bool tuner) {
+    InterpPlan pl;
+    if (const char *e = build_interp_plan(conf, conf.absErrorBound, 0, pl)) fail(SZ3B_E_INVALID_ARGUMENT, e);
+    const int radius = conf.quantbinCnt / 2;
+    const int nbins = 2 * radius;
+    const uint64_t n = pl.num * nbatch;
+    DevBuf &qb = tuner ? ws.cube_q : ws.q;
+    DevBuf &ub = tuner ? ws.cube_unpred : ws.unpred_tmp;
+    DevBuf &rb = tuner ? ws.cube_recon : ws.recon;
+    QT *d_q = qb.as<QT>(n);
+    T *d_unpred_tmp = ub.as<T>(n);
+    unsigned long long *d_hist = ws.hist.as<unsigned long long>(nbins);
+    size_t h = ws.stage_begin(tuner ? "tune_predict_quantize" : "predict_quantize");
+    SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
+    int launches = 0;
+    run_interp<T, QT>(ws, pl, d_data, nbatch, radius, d_q, d_unpred_tmp, d_hist, rb, &launches);
+    ws.stage_end(h, launches);
+
+    HuffmanBook book;
+    EncodeLayout lay;
+    encode_indices<QT, T>(ws, d_q, n, d_hist, nbins, 0, true, d_unpred_tmp, book, lay);
+    uint8_t hdr[128];
+    size_t hdr_len = interp_save_header<T>(pl, radius, lay.n_unpred, hdr);
+    uint8_t *buf = nullptr;
+    size_t len = assemble_stream<T>(ws, hdr, hdr_len, lay, book, n, tuner ? ws.stage2 : ws.stage, &buf);
+    return zstd_stage(ws, buf, len, dst, cap, zstd_threads);
+}
+
+template <class T>
+static size_t interp_compress(Workspace &ws, const sz3b_config &conf, const T *d_data, uint32_t nbatch, uint8_t *dst,
+                              size_t cap, int zstd_threads, bool tuner) {
+    if (conf.quantbinCnt < 2) fail(SZ3B_E_INVALID_ARGUMENT, "quantbinCnt must be >= 2");
+    if (conf.quantbinCnt / 2 <= 32768)
+        return interp_compress_t<T, uint16_t>(ws, conf, d_data, nbatch, dst, cap, zstd_threads, tuner);
+    return interp_compress_t<T, uint32_t>(ws, conf, d_data, nbatch, dst, cap, zstd_threads, tuner);
+}
+
+static void set_default_anchor(sz3b_config &conf) {
+    if (conf.interpAnchorStride < 0) {
+        static const int def[4] = {4096, 128, 32, 16};
+        conf.interpAnchorStride = def[conf.N - 1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// auto-tuner (SZAlgoInterp.hpp:122-286).  Returns true when conf was tuned (cmprAlgo is then ALGO_INTERP or
+// ALGO_LORENZO_REG); all trial compressions run through the same GPU kernels on the sampled cubes.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T>
+static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
+    const int N = conf.N;
+    const uint64_t num = config_num(conf);
+    set_default_anchor(conf);
+    const double sampleRate = 0.005;
+    static const size_t sbs_def[4] = {4096, 128, 32, 16};
+    size_t sbs = sbs_def[N - 1];
+    size_t shortest = conf.dims[0];
+    for (int i = 0; i < N; i++) shortest = std::min<size_t>(shortest, conf.dims[i]);
+    while (sbs >= shortest) sbs /= 2;
+    while (sbs >= 16 && (pow(sbs + 1, N) / num) > 1.5 * sampleRate) sbs /= 2;
+    if (sbs < 8) sbs = 8;
+    bool to_tune = pow(sbs + 1, N) <= 0.05 * num;
+    for (int i = 0; i < N; i++)
+        if (conf.dims[i] < sbs) {
+            to_tune = false;
+            break;
+        }
+    if (!to_tune) {
+        conf.cmprAlgo = SZ3B_ALGO_INTERP;
+        return;
+    }
+    const size_t per_block = static_cast<size_t>(pow(sbs + 1, N));
+    // ---- profiling_block (Sample.hpp:9-127): non-constant candidate blocks, row-major --------------------------------
+    uint32_t dims32[4] = {1, 1, 1, 1};
+    uint64_t stride[4] = {0, 0, 0, 0};
+    uint64_t acc = 1;
+    for (int d = N - 1; d >= 0; d--) {
+        dims32[d] = static_cast<uint32_t>(conf.dims[d]);
+        stride[d] = acc;
+        acc *= conf.dims[d];
+    }
+    uint64_t cb[4] = {1, 1, 1, 1};
+    uint64_t ncand = 1;
+    for (int d = 0; d < N; d++) {
+        // i = 0, sbs, ... while i < dim - sbs
+        cb[d] = conf.dims[d] > sbs ? (conf.dims[d] - sbs - 1) / sbs + 1 : 0;
+        ncand *= cb[d];
+    }
+    std::vector<uint64_t> starts;   // flattened element offset of each selected cube
+    auto cand_offset = [&](uint64_t b) {
+        uint64_t off = 0;
+        for (int d = N - 1; d >= 0; d--) {
+            off += (b % cb[d]) * sbs * stride[d];
+            b /= cb[d];
+        }
+        return off;
+    };
+    std::vector<uint64_t> filtered;
+    if (ncand > 0) {
+        uint8_t *d_flags = ws.flags.as<uint8_t>(ncand);
+        size_t h = ws.stage_begin("tune_profile_blocks");
+        launch_profile_blocks<T>(d_data, N, dims32, static_cast<uint32_t>(sbs), static_cast<uint32_t>(sbs / 4),
+                                 conf.absErrorBound, d_flags, ncand, ws.st);
+        ws.stage_end(h, 1);
+        std::vector<uint8_t> flags(ncand);
+        SZ3B_CUDA(cudaMemcpyAsync(flags.data(), d_flags, ncand, cudaMemcpyDeviceToHost, ws.st));
+        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        for (uint64_t b = 0; b < ncand; b++)
+            if (flags[b]) filtered.push_back(b);
+    }
+    const size_t nfilt = filtered.size();
+    const bool profiling = nfilt * per_block >= 0.5 * sampleRate * num;
+    // ---- sampleBlocks (Sample.hpp:202-289) -----------------------------------------------------------------------------
+    {
+        size_t totalblock = 1;
+        for (int d = 0; d < N; d++) totalblock *= static_cast<int>((conf.dims[d] - 1) / sbs);
+        if (profiling) {
+            size_t sstride = static_cast<size_t>(nfilt / (totalblock * sampleRate));
+            if (sstride <= 0) sstride = 1;
+            for (size_t i = 0; i < nfilt; i += sstride) starts.push_back(cand_offset(filtered[i]));
+        } else {
+            size_t sstride = static_cast<size_t>(1.0 / sampleRate);
+            if (sstride <= 0) sstride = 1;
+            for (uint64_t idx = 0; idx < ncand; idx++)   // the nested start loops enumerate the same candidates
+                if (idx % sstride == 0) starts.push_back(cand_offset(idx));
+        }
+    }
+    const size_t sampling_num = starts.size() * per_block;
+    if (sampling_num == 0 || sampling_num >= num * 0.2) {
+        conf.cmprAlgo = SZ3B_ALGO_INTERP;
+        return;
+    }
+    const uint32_t ncubes = static_cast<uint32_t>(starts.size());
+    if (ncubes > 65535) fail(SZ3B_E_UNSUPPORTED, "tuner sample exceeds 65535 cubes");
+    T *d_cubes = ws.cubes.as<T>(sampling_num);
+    {
+        uint64_t *d_starts = ws.starts.as<uint64_t>(ncubes);
+        SZ3B_CUDA(cudaMemcpyAsync(d_starts, starts.data(), ncubes * sizeof(uint64_t), cudaMemcpyHostToDevice, ws.st));
+        size_t h = ws.stage_begin("tune_gather");
+        launch_gather_cubes<T>(d_data, N, dims32, static_cast<uint32_t>(sbs + 1), d_starts, ncubes, d_cubes, ws.st);
+        ws.stage_end(h, 1);
+        SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // `starts` must outlive the copy
+    }
+    std::vector<uint8_t> trial_out(sizeof(T) * sampling_num + (1u << 20));
+    {
+        size_t need = ZSTD_compressBound(sizeof(T) * sampling_num + 65536 * 16) + 64;
+        if (trial_out.size() < need) trial_out.resize(need);
+    }
+    auto trial = [&](const sz3b_config &tc) -> double {
+        size_t sz = interp_compress<T>(ws, tc, d_cubes, ncubes, trial_out.data(), trial_out.size(), 1, true);
+        return per_block * static_cast<double>(ncubes) * sizeof(T) * 1.0 / sz;
+    };
+    double best_interp = 0, best_lorenzo = 0, ratio;
+    conf.interpDirection = 0;
+    conf.interpAlpha = 1.25;
+    conf.interpBeta = 2.0;
+    sz3b_config tc = conf;
+    {
+        uint64_t cd[4];
+        for (int d = 0; d < N; d++) cd[d] = sbs + 1;
+        config_set_dims(tc, N, cd);
+    }
+    for (int op : {SZ3B_INTERP_LINEAR, SZ3B_INTERP_CUBIC}) {
+        tc.interpAlgo = op;
+        ratio = trial(tc);
+        if (ratio > best_interp) {
+            best_interp = ratio;
+            conf.interpAlgo = op;
+        }
+    }
+    tc.interpAlgo = conf.interpAlgo;
+    int fact = 1;
+    for (int i = 2; i <= N; i++) fact *= i;
+    tc.interpDirection = fact - 1;
+    ratio = trial(tc);
+    if (ratio > best_interp * 1.02) {
+        best_interp = ratio;
+        conf.interpDirection = tc.interpDirection;
+    }
+    tc.interpDirection = conf.interpDirection;
+    const double alphas[3] = {1.0, 1.5, 2.0}, betas[3] = {1.0, 2.5, 3.0};
+    for (int i = 0; i < 3; i++) {
+        tc.interpAlpha = alphas[i];
+        tc.interpBeta = betas[i];
+        ratio = trial(tc);
+        if (ratio > best_interp * 1.02) {
+            best_interp = ratio;
+            conf.interpAlpha = alphas[i];
+            conf.interpBeta = betas[i];
+        }
+    }
+    if (N == 1 && best_interp < 50) {
+        // the reference additionally tries Lorenzo(1st+2nd order) on 1-D data (:227-241); that predictor stack is
+        // not on the GPU path yet, so say so instead of silently choosing differently.
+        fail(SZ3B_E_UNSUPPORTED, "1-D ALGO_INTERP_LORENZO needs the Lorenzo trial (not on the GPU path yet); use ALGO_INTERP");
+    }
+    (void)best_lorenzo;
+    conf.cmprAlgo = SZ3B_ALGO_INTERP;
+}
+
+template <class T>
+void tune_stage(Workspace &ws, sz3b_config &conf, const T *data, int loc) {
+    const T *d = to_device(ws, data, loc, config_num(conf));
+    resolve_abs_eb<T>(ws, conf, d, static_cast<T>(0));
+    tune_interp<T>(ws, conf, d);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// lossless path (SZDispatcher.hpp:54-59): size_t | zstd(raw bytes)
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T>
+static size_t lossless_compress(Workspace &ws, const sz3b_config &conf, const T *data, int loc, uint8_t *dst,
+                                size_t cap) {
+    const size_t bytes = config_num(conf) * sizeof(T);
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(data);
+    if (loc == SZ3B_DEVICE) {
+        uint8_t *h = static_cast<uint8_t *>(ws.stage.ensure(bytes));
+        SZ3B_CUDA(cudaMemcpyAsync(h, data, bytes, cudaMemcpyDeviceToHost, ws.st));
+        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        src = h;
+    }
+    try {
+        return zstd_stage(ws, src, bytes, dst, cap, host_threads());
+    } catch (TooSmall &) {
+        fail(SZ3B_E_RUNTIME, "compressed buffer not large enough");   // std::length_error escapes in the reference
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SZ_compress_dispatcher (SZDispatcher.hpp:13-76).  `range` > 0: precomputed value range (OMP slabs).
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T>
+size_t blockwise_compress(Workspace &ws, const sz3b_config &conf, const T *d_data, uint8_t *dst, size_t cap,
+                          int zstd_threads);   // blockwise.cu
+
+template <class T>
+static size_t dispatch_compress(Workspace &ws, sz3b_config &conf, const T *data, int loc, uint8_t *dst, size_t cap,
+                                T range) {
+    const uint64_t num = config_num(conf);
+    const T *d_data = nullptr;
+    auto dev = [&]() {
+        if (!d_data) d_data = to_device(ws, data, loc, num);
+        return d_data;
+    };
+    if (conf.errorBoundMode != SZ3B_EB_ABS) resolve_abs_eb<T>(ws, conf, range > 0 ? nullptr : dev(), range);
+    size_t cmp_size = 0;
+    if (conf.absErrorBound == 0) conf.cmprAlgo = SZ3B_ALGO_LOSSLESS;
+    bool cap_ok = true;
+    if (conf.cmprAlgo != SZ3B_ALGO_LOSSLESS) {
+        try {
+            if (conf.cmprAlgo == SZ3B_ALGO_INTERP_LORENZO) {
+                tune_interp<T>(ws, conf, dev());   // rewrites cmprAlgo to ALGO_INTERP (N >= 2)
+            }
+            if (conf.cmprAlgo == SZ3B_ALGO_INTERP) {
+                set_default_anchor(conf);
+                cmp_size = interp_compress<T>(ws, conf, dev(), 1, dst, cap, host_threads(), false);
+            } else if (conf.cmprAlgo == SZ3B_ALGO_LORENZO_REG) {
+                cmp_size = blockwise_compress<T>(ws, conf, dev(), dst, cap, host_threads());
+            } else if (conf.cmprAlgo == SZ3B_ALGO_NOPRED || conf.cmprAlgo == 5 || conf.cmprAlgo == 6) {
+                fail(SZ3B_E_UNSUPPORTED, "ALGO_NOPRED / ALGO_BIOMD* are outside the GPU hot path (DESIGN.md, scope)");
+            } else {
+                fail(SZ3B_E_INVALID_ARGUMENT, "Unknown compression algorithm");
+            }
+        } catch (TooSmall &) {
+            cap_ok = false;
+        }
+    }
+    if (conf.cmprAlgo == SZ3B_ALGO_LOSSLESS || !cap_ok) {
+        conf.cmprAlgo = SZ3B_ALGO_LOSSLESS;
+        return lossless_compress<T>(ws, conf, data, loc, dst, cap);
+    }
+    if (num * sizeof(T) / 1.0 / cmp_size < 3) {
+        size_t zcap = ZSTD_compressBound(num * sizeof(T)) + sizeof(uint64_t);
+        std::vector<uint8_t> tmp(zcap);
+        size_t zsize = lossless_compress<T>(ws, conf, data, loc, tmp.data(), zcap);
+        if (zsize < cmp_size && zsize <= cap) {
+            conf.cmprAlgo = SZ3B_ALGO_LOSSLESS;
+            memcpy(dst, tmp.data(), zsize);
+            cmp_size = zsize;
+        }
+    }
+    return cmp_size;
+}
+
+template <class T>
+size_t compress_slab(Workspace &ws, sz3b_config &slab_conf, const T *slab, int loc, double range, uint8_t *payload,
+                     size_t cap) {
+    return dispatch_compress<T>(ws, slab_conf, slab, loc, payload, cap, static_cast<T>(range));
+}
+
+// SZ_compress_OMP (SZImplOMP.hpp:16-117) executed on ONE device: the slabs are independent streams, compressed one
+// after the other; the container is what the reference's SZ_decompress_OMP expects.  (Across GPUs the ranks call
+// sz3b_compress_slab themselves and rank 0 assembles, see api.cpp.)
+template <class T>
+static size_t omp_compress(Workspace &ws, sz3b_config &conf, const T *data, int loc, uint8_t *dst, size_t cap) {
+    int nslabs = conf.openmp;
+    if (static_cast<uint64_t>(nslabs) > conf.dims[0]) nslabs = static_cast<int>(conf.dims[0]);
+    const uint64_t num = config_num(conf);
+    const uint64_t row = num / conf.dims[0];
+    const T *d_all = to_device(ws, data, loc, num);
+    if (conf.errorBoundMode != SZ3B_EB_ABS) {
+        // per-thread minmax + reduction (:57-68) == global range
+        resolve_abs_eb<T>(ws, conf, d_all, static_cast<T>(0));
+    }
+    std::vector<std::vector<uint8_t>> parts(nslabs);
+    std::vector<size_t> sizes(nslabs);
+    std::vector<sz3b_config> confs(nslabs, conf);
+    for (int t = 0; t < nslabs; t++) {
+        int lo = static_cast<int>(static_cast<uint64_t>(t) * conf.dims[0] / nslabs);
+        int hi = static_cast<int>(static_cast<uint64_t>(t + 1) * conf.dims[0] / nslabs);
+        uint64_t d[4];
+        for (int i = 0; i < conf.N; i++) d[i] = conf.dims[i];
+        d[0] = hi - lo;
+        int keep_block = confs[t].blockSize;
+        (void)keep_block;
+        config_set_dims(confs[t], conf.N, d);
+        const uint64_t n_t = config_num(confs[t]);
+        size_t pcap = ZSTD_compressBound(n_t * sizeof(T));
+        parts[t].resize(pcap);
+        sizes[t] = dispatch_compress<T>(ws, confs[t], d_all + static_cast<uint64_t>(lo) * row, SZ3B_DEVICE,
+                                        parts[t].data(), pcap, static_cast<T>(0));
+    }
+    uint8_t *p = dst;
+    size_t need = 4;
+    uint8_t blob[256];
+    for (int t = 0; t < nslabs; t++) need += config_save(confs[t], blob) + 8 + sizes[t];
+    if (need > cap) fail(SZ3B_E_RUNTIME, "compressed buffer not large enough for the OpenMP container");
+    put<int32_t>(p, nslabs);
+    for (int t = 0; t < nslabs; t++) p += config_save(confs[t], p);
+    for (int t = 0; t < nslabs; t++) put<uint64_t>(p, sizes[t]);
+    for (int t = 0; t < nslabs; t++) {
+        memcpy(p, parts[t].data(), sizes[t]);
+        p += sizes[t];
+    }
+    return static_cast<size_t>(p - dst);
+}
+
+template <class T>
+size_t compress_any(Workspace &ws, sz3b_config &conf, const T *data, int loc, uint8_t *cmp, size_t cap) {
+    if (conf.openmp) return omp_compress<T>(ws, conf, data, loc, cmp, cap);
+    return dispatch_compress<T>(ws, conf, data, loc, cmp, cap, static_cast<T>(0));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage-level entry points
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, class QT>
+static void interp_decompose_t(Workspace &ws, const sz3b_config &conf, double eb, const T *d_data, int schedule,
+                               int32_t *quant_out, std::vector<uint8_t> &blob) {
+    sz3b_config c = conf;
+    set_default_anchor(c);
+    InterpPlan pl;
+    if (const char *e = build_interp_plan(c, eb, schedule, pl)) fail(SZ3B_E_INVALID_ARGUMENT, e);
+    const int radius = c.quantbinCnt / 2;
+    const int nbins = 2 * radius;
+    const uint64_t n = pl.num;
+    QT *d_q = ws.q.as<QT>(n);
+    T *d_unpred_tmp = ws.unpred_tmp.as<T>(n);
+    unsigned long long *d_hist = ws.hist.as<unsigned long long>(nbins);
+    size_t h = ws.stage_begin("predict_quantize");
+    SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
+    int launches = 0;
+    run_interp<T, QT>(ws, pl, d_data, 1, radius, d_q, d_unpred_tmp, d_hist, ws.recon, &launches);
+    ws.stage_end(h, launches);
+    // indices -> host int32
+    int32_t *d_wide = ws.side_q.as<int32_t>(n);
+    launch_widen<QT>(d_q, n, d_wide, ws.st);
+    SZ3B_CUDA(cudaMemcpyAsync(quant_out, d_wide, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ws.st));
+    // unpredictables: reuse the packer's ordered compaction with a trivial (all length 0) code book
+    HuffmanBook book;
+    EncodeLayout lay;
+    encode_indices<QT, T>(ws, d_q, n, d_hist, nbins, 0, true, d_unpred_tmp, book, lay);
+    uint8_t hdr[128];
+    size_t hdr_len = interp_save_header<T>(pl, radius, lay.n_unpred, hdr);
+    blob.resize(hdr_len + lay.n_unpred * sizeof(T));
+    memcpy(blob.data(), hdr, hdr_len);
+    if (lay.n_unpred)
+        SZ3B_CUDA(cudaMemcpyAsync(blob.data() + hdr_len, ws.unpred_out.p, lay.n_unpred * sizeof(T),
+                                  cudaMemcpyDeviceToHost, ws.st));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+}
+
+template <class T>
+void interp_decompose_stage(Workspace &ws, const sz3b_config &conf, double eb, const T *data, int loc, int schedule,
+                            int32_t *quant_out, std::vector<uint8_t> &blob) {
+    const T *d = to_device(ws, data, loc, config_num(conf));
+    if (conf.quantbinCnt / 2 <= 32768)
+        interp_decompose_t<T, uint16_t>(ws, conf, eb, d, schedule, quant_out, blob);
+    else
+        interp_decompose_t<T, uint32_t>(ws, conf, eb, d, schedule, quant_out, blob);
+}
+
+// HuffmanEncoder<int> on an arbitrary int32 stream (side streams, tests)
+void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vector<uint8_t> &out, size_t *tree_len) {
+    if (n == 0) fail(SZ3B_E_INVALID_ARGUMENT, "Huffman bins should not be empty");
+    int *d_mm = ws.misc.as<int>(2);
+    int init[2] = {0x7fffffff, static_cast<int>(0x80000000)};
+    SZ3B_CUDA(cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ws.st));
+    size_t h = ws.stage_begin("huffman_histogram");
+    launch_minmax_int<int32_t>(d_q, n, d_mm, ws.st);
+    int mm[2];
+    SZ3B_CUDA(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ws.st));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    const int64_t span = static_cast<int64_t>(mm[1]) - mm[0] + 1;
+    if (span > (1 << 26)) fail(SZ3B_E_UNSUPPORTED, "Huffman symbol range above 2^26");
+    const int nbins = static_cast<int>(span);
+    unsigned long long *d_hist = ws.hist.as<unsigned long long>(nbins);
+    SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
+    launch_histogram<int32_t>(d_q, n, mm[0], nbins, nbins / 2, d_hist, ws.st);
+    ws.stage_end(h, 2);
+    HuffmanBook book;
+    EncodeLayout lay;
+    encode_indices<int32_t, float>(ws, d_q, n, d_hist, nbins, mm[0], false, nullptr, book, lay);
+    out.resize(lay.tree_len + 8 + lay.out_size);
+    memcpy(out.data(), book.tree_blob.data(), lay.tree_len);
+    uint8_t *p = out.data() + lay.tree_len;
+    put<uint64_t>(p, lay.out_size);
+    if (lay.out_size) SZ3B_CUDA(cudaMemcpyAsync(p, ws.out_words.p, lay.out_size, cudaMemcpyDeviceToHost, ws.st));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    if (tree_len) *tree_len = lay.tree_len;
+}
+
+void huffman_encode_stage(Workspace &ws, const int32_t *q, size_t n, int loc, std::vector<uint8_t> &out,
+                          size_t *tree_len) {
+    const int32_t *d_q = q;
+    if (loc == SZ3B_HOST) {
+        int32_t *d = ws.side_q.as<int32_t>(n);
+        SZ3B_CUDA(cudaMemcpyAsync(d, q, n * sizeof(int32_t), cudaMemcpyHostToDevice, ws.st));
+        d_q = d;
+    }
+    huffman_encode_device(ws, d_q, n, out, tree_len);
+}
+
+#define SZ3B_INST_PIPE(T)                                                                                             \
+    template size_t compress_any<T>(Workspace &, sz3b_config &, const T *, int, uint8_t *, size_t);                  \
+    template void interp_decompose_stage<T>(Workspace &, const sz3b_config &, double, const T *, int, int, int32_t *, \
+                                            std::vector<uint8_t> &);                                                  \
+    template void tune_stage<T>(Workspace &, sz3b_config &, const T *, int);                                         \
+    template double abs_eb_stage<T>(Workspace &, const sz3b_config &, const T *, int);                               \
+    template void minmax_stage<T>(Workspace &, const T *, int, size_t, double *, double *);                          \
+    template size_t compress_slab<T>(Workspace &, sz3b_config &, const T *, int, double, uint8_t *, size_t);
+SZ3B_INST_PIPE(float)
+SZ3B_INST_PIPE(double)
+
+}  // namespace sz3b

@@ -1,0 +1,167 @@
+// sz3_b200/csrc/workspace.hpp -- per-call device/pinned scratch memory, stream and stage profile.
+//
+// cudaMalloc/cudaHostAlloc cost milliseconds, so buffers are cached per device in a small pool and only grow.
+// A call borrows one Workspace for its whole duration (the library is reentrant: concurrent host threads get
+// distinct workspaces and distinct streams).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+namespace sz3b {
+
+struct CudaError {
+    cudaError_t code;
+    const char *what;
+    const char *file;
+    int line;
+};
+
+#define SZ3B_CUDA(expr)                                                         \
+    do {                                                                        \
+        cudaError_t _e = (expr);                                                \
+        if (_e != cudaSuccess) throw sz3b::CudaError{_e, #expr, __FILE__, __LINE__}; \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void *ensure(size_t bytes) {
+        if (bytes > cap) {
+            if (p) SZ3B_CUDA(cudaFree(p));
+            p = nullptr;
+            cap = 0;
+            size_t want = bytes + bytes / 16 + 256;
+            SZ3B_CUDA(cudaMalloc(&p, want));
+            cap = want;
+        }
+        return p;
+    }
+    template <class V>
+    V *as(size_t count) {
+        return static_cast<V *>(ensure(count * sizeof(V)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void *ensure(size_t bytes) {
+        if (bytes > cap) {
+            if (p) SZ3B_CUDA(cudaFreeHost(p));
+            p = nullptr;
+            cap = 0;
+            size_t want = bytes + bytes / 16 + 4096;
+            SZ3B_CUDA(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+            cap = want;
+        }
+        return p;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct StageRecord {
+    std::string name;
+    double ms = 0;       // device time (CUDA events) or host wall time for host stages
+    int launches = 0;    // kernels launched by this stage
+    bool host = false;
+};
+
+struct Workspace {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    // inputs / index stream
+    DevBuf data, q, unpred_tmp, recon, hist, tables;
+    // encoder
+    DevBuf code, len, chunk_bits, chunk_zeros, bit_off, zero_off, out_words, unpred_out;
+    // tuner
+    DevBuf cubes, cube_q, cube_unpred, cube_recon, flags, starts;
+    // side streams / blockwise
+    DevBuf coef, coef_q, side_q, misc;
+    // pinned staging
+    PinBuf stage, stage2, hist_host;
+    // profiling
+    std::vector<StageRecord> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Pending {
+        size_t rec;
+        cudaEvent_t a, b;
+    };
+    std::vector<Pending> pending;
+
+    cudaEvent_t event() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            SZ3B_CUDA(cudaEventCreate(&e));
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
+    void prof_reset() {
+        prof.clear();
+        pending.clear();
+        ev_used = 0;
+    }
+    // device stage: records events around the enclosed launches
+    size_t stage_begin(const char *name) {
+        StageRecord r;
+        r.name = name;
+        prof.push_back(r);
+        Pending pd;
+        pd.rec = prof.size() - 1;
+        pd.a = event();
+        pd.b = event();
+        SZ3B_CUDA(cudaEventRecord(pd.a, st));
+        pending.push_back(pd);
+        return pending.size() - 1;
+    }
+    void stage_end(size_t h, int launches) {
+        SZ3B_CUDA(cudaEventRecord(pending[h].b, st));
+        prof[pending[h].rec].launches += launches;
+    }
+    void host_stage(const char *name, double ms) {
+        StageRecord r;
+        r.name = name;
+        r.ms = ms;
+        r.host = true;
+        prof.push_back(r);
+    }
+    void prof_finish() {
+        for (auto &pd : pending) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, pd.a, pd.b) == cudaSuccess) prof[pd.rec].ms = ms;
+        }
+        pending.clear();
+    }
+};
+
+Workspace *workspace_acquire();
+void workspace_release(Workspace *ws);
+
+struct WorkspaceLease {
+    Workspace *ws;
+    WorkspaceLease() : ws(workspace_acquire()) {}
+    ~WorkspaceLease() { workspace_release(ws); }
+    Workspace *operator->() { return ws; }
+    Workspace &operator*() { return *ws; }
+};
+
+inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace sz3b

@@ -1,0 +1,21 @@
+/* sz3_b200/csrc/zstd_decl.h -- prototypes of the libzstd entry points the host tail calls.
+ *
+ * The image ships the zstd runtime (libzstd.so.1, v1.5.5) without its development header; the stream format only
+ * needs these functions (reference include/SZ3/lossless/Lossless_zstd.hpp:32,35,44).  Link with -l:libzstd.so.1.
+ */
+#ifndef SZ3B_ZSTD_DECL_H
+#define SZ3B_ZSTD_DECL_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+size_t ZSTD_compressBound(size_t srcSize);
+size_t ZSTD_compress(void *dst, size_t dstCapacity, const void *src, size_t srcSize, int compressionLevel);
+size_t ZSTD_decompress(void *dst, size_t dstCapacity, const void *src, size_t compressedSize);
+unsigned ZSTD_isError(size_t code);
+const char *ZSTD_getErrorName(size_t code);
+unsigned ZSTD_versionNumber(void);
+#ifdef __cplusplus
+}
+#endif
+#endif

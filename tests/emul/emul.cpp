@@ -1,0 +1,142 @@
+// tests/emul/emul.cpp -- TEST INFRASTRUCTURE: runs the kernel *bodies* of sz3_b200/csrc/interp_body.cuh with host
+// threads so that the traversal/indexing logic can be checked against the reference on a machine without a GPU.
+// Never linked into the product library (which has no CPU path); built by tests/conftest.py into tests/emul/_build/.
+#include <atomic>
+#include <barrier>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../sz3_b200/csrc/interp_body.cuh"
+#include "../../sz3_b200/csrc/interp_plan.hpp"
+
+using namespace sz3b;
+
+struct HostCtx {
+    uint32_t t, nt;
+    std::barrier<> *bar;
+    unsigned long long *hist;
+    uint32_t tid() const { return t; }
+    uint32_t nthreads() const { return nt; }
+    void sync() { bar->arrive_and_wait(); }
+    void hist_add(int sym, bool active) {
+        if (active) __atomic_fetch_add(&hist[sym], 1ull, __ATOMIC_RELAXED);
+    }
+};
+
+template <class T, class QT>
+static int run(const sz3b_config &c, double eb, const T *data, int schedule, int nthreads, int32_t *quant_out,
+               T *unpred_out, size_t *n_unpred, unsigned long long *hist_out) {
+    InterpPlan pl;
+    if (const char *e = build_interp_plan(c, eb, schedule, pl)) {
+        fprintf(stderr, "[emul] plan: %s\n", e);
+        return -1;
+    }
+    const int radius = c.quantbinCnt / 2;
+    const uint64_t n = pl.num;
+    std::vector<QT> q(n, static_cast<QT>(0xFFFF));
+    std::vector<T> unpred_tmp(n);
+    std::vector<T> recon(pl.tile ? pl.num2 : pl.num);
+    std::vector<unsigned long long> hist(2 * radius, 0);
+    InterpArgs<T, QT> A;
+    memset(&A, 0, sizeof(A));
+    A.sh = pl.sh;
+    A.data = data;
+    A.data_bstride = pl.num;
+    A.q_bstride = pl.num;
+    A.recon2_bstride = pl.num2;
+    for (int d = 0; d < kMaxDim; d++) {
+        A.dims2[d] = pl.dims2[d];
+        A.stride2[d] = pl.stride2[d];
+    }
+    if (pl.tile) A.recon2 = recon.data(); else A.work = recon.data();
+    A.q = q.data();
+    A.unpred_tmp = unpred_tmp.data();
+    A.hist = hist.data();
+    A.qp = make_quant(eb, radius);
+    // anchors / first element (same logic as k_interp_anchor)
+    if (pl.anchor_stride == 0) {
+        T rec;
+        int qv = quantize<T>(data[0], static_cast<T>(0), A.qp, rec);
+        q[0] = static_cast<QT>(qv);
+        if (qv == 0) unpred_tmp[0] = data[0];
+        recon[0] = rec;
+        hist[qv]++;
+    } else {
+        for (uint64_t gid = 0; gid < pl.n_first; gid++) {
+            uint64_t r = gid, off = 0, off2 = 0;
+            for (int d = pl.sh.N - 1; d >= 0; d--) {
+                uint32_t ext = (pl.sh.dims[d] - 1) / pl.anchor_stride + 1;
+                uint32_t x = static_cast<uint32_t>(r % ext) * pl.anchor_stride;
+                r /= ext;
+                off += x * pl.sh.stride[d];
+                off2 += (x >> 1) * pl.stride2[d];
+            }
+            q[gid] = 0;
+            unpred_tmp[gid] = data[off];
+            if (pl.tile) recon[off2] = data[off]; else recon[off] = data[off];
+        }
+        hist[0] += pl.n_first;
+    }
+    std::vector<T> sm(kTileSmemElems);
+    for (const LevelPlan &L : pl.levels) {
+        A.qp = make_quant(L.eb, radius);
+        A.s = L.s;
+        for (int d = 0; d < kMaxDim; d++) A.nb[d] = L.nb[d];
+        A.block_base = pl.table.data() + L.table_off;
+        std::barrier<> bar(nthreads);
+        if (pl.tile) {
+            auto worker = [&](int t) {
+                HostCtx ctx{static_cast<uint32_t>(t), static_cast<uint32_t>(nthreads), &bar, hist.data()};
+                for (uint64_t tile = 0; tile < L.nblocks; tile++) {
+                    TileGeom tg;
+                    tile_geom(A, static_cast<uint32_t>(tile), 0, tg);
+                    tile_body(A, ctx, sm.data(), tg, 0);
+                    ctx.sync();
+                }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < nthreads; t++) th.emplace_back(worker, t);
+            worker(0);
+            for (auto &x : th) x.join();
+        } else {
+            for (int p = 0; p < pl.sh.N; p++) {
+                uint64_t total = pass_points(A, p);
+                auto worker = [&](int t) {
+                    HostCtx ctx{static_cast<uint32_t>(t), static_cast<uint32_t>(nthreads), &bar, hist.data()};
+                    // reverse order inside each thread to shake out order dependences
+                    for (uint64_t g = total; g-- > 0;)
+                        if (g % nthreads == static_cast<uint64_t>(t)) pass_point(A, ctx, p, g, total, 0);
+                };
+                std::vector<std::thread> th;
+                for (int t = 1; t < nthreads; t++) th.emplace_back(worker, t);
+                worker(0);
+                for (auto &x : th) x.join();
+            }
+        }
+    }
+    size_t nu = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        quant_out[i] = static_cast<int32_t>(q[i]);
+        if (q[i] == 0) unpred_out[nu++] = unpred_tmp[i];
+    }
+    *n_unpred = nu;
+    if (hist_out) memcpy(hist_out, hist.data(), sizeof(unsigned long long) * 2 * radius);
+    return 0;
+}
+
+extern "C" int emul_interp_decompose(int dtype, const sz3b_config *c, double eb, const void *data, int schedule,
+                                     int nthreads, int32_t *quant_out, void *unpred_out, size_t *n_unpred,
+                                     unsigned long long *hist_out) {
+    sz3b_config cc = *c;
+    if (cc.interpAnchorStride < 0) {
+        static const int def[4] = {4096, 128, 32, 16};
+        cc.interpAnchorStride = def[cc.N - 1];
+    }
+    if (dtype == 0)
+        return run<float, uint16_t>(cc, eb, static_cast<const float *>(data), schedule, nthreads, quant_out,
+                                    static_cast<float *>(unpred_out), n_unpred, hist_out);
+    return run<double, uint16_t>(cc, eb, static_cast<const double *>(data), schedule, nthreads, quant_out,
+                                 static_cast<double *>(unpred_out), n_unpred, hist_out);
+}
