@@ -1,0 +1,130 @@
+"""GPU end-to-end parity through sz3b_compress (the SZ_compress boundary) against the reference.
+
+* every stream produced on the GPU is decompressed by the UNMODIFIED reference decoder and must honour the bound;
+* for inputs whose pre-zstd stream is below the multi-frame threshold the whole compressed file is byte-identical;
+* compression ratio within 1 % of the reference at the same bound (north_star).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import (ALGO_INTERP, ALGO_INTERP_LORENZO, ALGO_LOSSLESS, EB_ABS, EB_PSNR, EB_REL, Config, dtype_code, field_g3,
+                    field_g4, field_nd, make_config, product_lib, ref_lib)
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_compress(data, conf):
+    L = product_lib()
+    cap = L.sz3b_compress_bound(dtype_code(data), C.byref(conf))
+    out = np.empty(cap, dtype=np.uint8)
+    size = C.c_size_t(0)
+    used = Config()
+    rc = L.sz3b_compress(dtype_code(data), C.byref(conf), data.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_char_p),
+                         C.c_size_t(cap), C.byref(size), C.byref(used))
+    assert rc == 0, L.sz3b_last_error()
+    return out[:size.value].copy(), used
+
+
+def ref_compress(data, conf):
+    R = ref_lib()
+    cap = R.ref_size_bound(dtype_code(data), C.byref(conf))
+    out = np.empty(cap, dtype=np.uint8)
+    n = R.ref_compress(dtype_code(data), C.byref(conf), data.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_char_p), C.c_size_t(cap))
+    assert n > 0
+    return out[:n].copy()
+
+
+def ref_decompress(cmp, like):
+    R = ref_lib()
+    out = np.empty_like(like)
+    conf = Config()
+    rc = R.ref_decompress(dtype_code(like), cmp.ctypes.data_as(C.c_char_p), C.c_size_t(cmp.size), out.ctypes.data_as(C.c_void_p), C.byref(conf))
+    assert rc == 0
+    return out, conf
+
+
+needs_ref = pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref/libsz3ref.so not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("algo", [ALGO_INTERP, ALGO_INTERP_LORENZO])
+@pytest.mark.parametrize("shape,dtype,eb", [((100, 70, 130), np.float32, 1e-3), ((64, 80, 96), np.float64, 1e-5),
+                                            ((128, 128, 128), np.float32, 1e-2), ((8, 8, 128), np.float32, 1.0),
+                                            ((12, 40, 40, 40), np.float32, 1e-2), ((300, 500), np.float32, 1e-3)])
+def test_stream_identical_small(shape, dtype, eb, algo):
+    data = field_nd(shape, dtype)
+    conf = make_config(shape, cmprAlgo=algo, absErrorBound=eb)
+    ours, used = gpu_compress(data, conf)
+    theirs = ref_compress(data, conf)
+    assert ours.size == theirs.size and np.array_equal(ours, theirs), (ours.size, theirs.size)
+    dec, _ = ref_decompress(ours, data)
+    assert np.max(np.abs(dec.astype(np.float64) - data.astype(np.float64))) <= eb
+
+
+@needs_ref
+@pytest.mark.parametrize("mode,val", [(EB_REL, 1e-4), (EB_PSNR, 80.0)])
+def test_error_bound_modes(mode, val):
+    data = field_g3((96, 96, 96))
+    conf = make_config(data.shape, cmprAlgo=ALGO_INTERP_LORENZO, errorBoundMode=mode, relErrorBound=val, psnrErrorBound=val)
+    ours, used = gpu_compress(data, conf)
+    theirs = ref_compress(data, conf)
+    assert np.array_equal(ours, theirs)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.max(np.abs(dec - data)) <= dconf.absErrorBound
+
+
+@needs_ref
+def test_noise_falls_back_to_lossless():
+    rng = np.random.default_rng(3)
+    data = rng.standard_normal((64, 64, 64)).astype(np.float32)
+    conf = make_config(data.shape, absErrorBound=1e-7)
+    ours, used = gpu_compress(data, conf)
+    theirs = ref_compress(data, conf)
+    assert used.cmprAlgo == ALGO_LOSSLESS
+    assert np.array_equal(ours, theirs)
+    dec, _ = ref_decompress(ours, data)
+    assert np.array_equal(dec, data)
+
+
+@needs_ref
+def test_zero_bound_is_lossless():
+    data = field_nd((40, 40, 40), np.float32)
+    conf = make_config(data.shape, absErrorBound=0.0)
+    ours, used = gpu_compress(data, conf)
+    assert used.cmprAlgo == ALGO_LOSSLESS
+    dec, _ = ref_decompress(ours, data)
+    assert np.array_equal(dec, data)
+
+
+@needs_ref
+def test_g3_256_ratio_and_bound():
+    data = field_g3((256, 256, 256))
+    conf = make_config(data.shape, absErrorBound=1e-3)
+    ours, used = gpu_compress(data, conf)
+    theirs = ref_compress(data, conf)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.max(np.abs(dec - data)) <= 1e-3
+    r_ours, r_ref = data.nbytes / ours.size, data.nbytes / theirs.size
+    assert abs(r_ours - r_ref) / r_ref < 0.01, (r_ours, r_ref)
+    assert dconf.cmprAlgo == ALGO_INTERP
+
+
+@needs_ref
+def test_omp_container_decodes_with_reference():
+    data = field_g3((100, 64, 64))
+    conf = make_config(data.shape, absErrorBound=1e-3, openmp=4)
+    ours, used = gpu_compress(data, conf)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.max(np.abs(dec - data)) <= 1e-3
+
+
+def test_capacity_check():
+    L = product_lib()
+    data = field_nd((20, 20, 20), np.float32)
+    conf = make_config(data.shape)
+    out = np.empty(64, dtype=np.uint8)
+    size = C.c_size_t(0)
+    rc = L.sz3b_compress(0, C.byref(conf), data.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_char_p), C.c_size_t(64), C.byref(size), None)
+    assert rc == -1  # std::invalid_argument in the reference (sz.hpp:47-49)
