@@ -132,6 +132,8 @@ int sz3b_device_count(void);
 /* Per-stage device times (CUDA events on the library's stream) of the calling thread's last compress call.
  * names/ms arrays of capacity `cap`; returns the number of stages recorded.  Launch counts in `launches`. */
 int sz3b_last_profile(const char **names, double *ms, int *launches, int cap);
+/* Bytes the calling thread's last call moved host->device and device->host (cudaMemcpyAsync on the call's stream). */
+void sz3b_last_transfer(size_t *h2d_bytes, size_t *d2h_bytes);
 /* zstd worker threads for the host tail (0 = hardware concurrency). */
 void sz3b_set_host_threads(int n);
 

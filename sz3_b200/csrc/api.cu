@@ -19,6 +19,7 @@ using namespace sz3b;
 namespace {
 thread_local std::string t_last_error;
 thread_local std::vector<StageRecord> t_profile;
+thread_local size_t t_h2d = 0, t_d2h = 0;
 
 template <class F>
 int guarded(F &&f) {
@@ -54,6 +55,8 @@ void check_conf(const sz3b_config *c) {
 void finish_profile(Workspace &ws) {
     ws.prof_finish();
     t_profile = ws.prof;
+    t_h2d = ws.h2d_bytes;
+    t_d2h = ws.d2h_bytes;
 }
 
 size_t size_bound(int dtype, const sz3b_config &c) {
@@ -393,6 +396,11 @@ int sz3b_omp_assemble(int dtype, const sz3b_config *c, int nslabs, const unsigne
         p += config_save(oc, p);
         *cmp_size = static_cast<size_t>(p - reinterpret_cast<uint8_t *>(cmp));
     });
+}
+
+void sz3b_last_transfer(size_t *h2d_bytes, size_t *d2h_bytes) {
+    if (h2d_bytes) *h2d_bytes = t_h2d;
+    if (d2h_bytes) *d2h_bytes = t_d2h;
 }
 
 int sz3b_last_profile(const char **names, double *ms, int *launches, int cap) {

@@ -65,7 +65,7 @@ static const T *to_device(Workspace &ws, const T *data, int loc, size_t num) {
     if (loc == SZ3B_DEVICE) return data;
     T *d = ws.data.as<T>(num);
     size_t h = ws.stage_begin("h2d_input");
-    SZ3B_CUDA(cudaMemcpyAsync(d, data, num * sizeof(T), cudaMemcpyHostToDevice, ws.st));
+    ws.h2d(d, data, num * sizeof(T));
     ws.stage_end(h, 0);
     return d;
 }
@@ -78,7 +78,7 @@ void minmax_stage(Workspace &ws, const T *data, int loc, size_t num, double *mn,
     launch_minmax<T>(d, num, mm, ws.st);
     ws.stage_end(h, 2);
     T hmm[2];
-    SZ3B_CUDA(cudaMemcpyAsync(hmm, mm, sizeof(hmm), cudaMemcpyDeviceToHost, ws.st));
+    ws.d2h(hmm, mm, sizeof(hmm));
     SZ3B_CUDA(cudaStreamSynchronize(ws.st));
     *mn = static_cast<double>(hmm[0]);
     *mx = static_cast<double>(hmm[1]);
@@ -168,8 +168,7 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
     A.hist = d_hist;
     uint64_t *d_table = ws.tables.as<uint64_t>(pl.table.size() + 1);
     if (!pl.table.empty())
-        SZ3B_CUDA(cudaMemcpyAsync(d_table, pl.table.data(), pl.table.size() * sizeof(uint64_t), cudaMemcpyHostToDevice,
-                                  ws.st));
+        ws.h2d(d_table, pl.table.data(), pl.table.size() * sizeof(uint64_t));
     A.qp = make_quant(pl.eb, radius);
     A.s = 0;
     interp_launch_anchors<T, QT>(A, pl.anchor_stride, pl.n_first, nbatch, ws.st);
@@ -225,7 +224,7 @@ template <class QT, class T>
 static void encode_indices(Workspace &ws, const QT *d_q, uint64_t n, const unsigned long long *d_hist, int nbins,
                            int sym_base, bool has_unpred, const T *d_unpred_tmp, HuffmanBook &book, EncodeLayout &lay) {
     unsigned long long *h_hist = static_cast<unsigned long long *>(ws.hist_host.ensure(sizeof(unsigned long long) * nbins));
-    SZ3B_CUDA(cudaMemcpyAsync(h_hist, d_hist, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToHost, ws.st));
+    ws.d2h(h_hist, d_hist, sizeof(unsigned long long) * nbins);
     SZ3B_CUDA(cudaStreamSynchronize(ws.st));
     double t0 = now_ms();
     const char *err = nullptr;
@@ -240,8 +239,8 @@ static void encode_indices(Workspace &ws, const QT *d_q, uint64_t n, const unsig
     const size_t states = book.state_num;
     unsigned long long *d_code = ws.code.as<unsigned long long>(states);
     uint8_t *d_len = ws.len.as<uint8_t>(states);
-    SZ3B_CUDA(cudaMemcpyAsync(d_code, book.code.data(), states * sizeof(uint64_t), cudaMemcpyHostToDevice, ws.st));
-    SZ3B_CUDA(cudaMemcpyAsync(d_len, book.len.data(), states, cudaMemcpyHostToDevice, ws.st));
+    ws.h2d(d_code, book.code.data(), states * sizeof(uint64_t));
+    ws.h2d(d_len, book.len.data(), states);
     const uint64_t nchunks = pack_num_chunks(n);
     unsigned *d_cb = ws.chunk_bits.as<unsigned>(nchunks + 1);
     unsigned *d_cz = ws.chunk_zeros.as<unsigned>(nchunks + 1);
@@ -269,13 +268,13 @@ static size_t assemble_stream(Workspace &ws, const uint8_t *decomp_hdr, size_t d
     p += decomp_hdr_len;
     size_t h = ws.stage_begin("d2h_stream");
     if (lay.n_unpred)
-        SZ3B_CUDA(cudaMemcpyAsync(p, ws.unpred_out.p, lay.n_unpred * sizeof(T), cudaMemcpyDeviceToHost, ws.st));
+        ws.d2h(p, ws.unpred_out.p, lay.n_unpred * sizeof(T));
     p += lay.n_unpred * sizeof(T);
     memcpy(p, book.tree_blob.data(), lay.tree_len);
     p += lay.tree_len;
     put<uint64_t>(p, n);
     put<uint64_t>(p, lay.out_size);
-    if (lay.out_size) SZ3B_CUDA(cudaMemcpyAsync(p, ws.out_words.p, lay.out_size, cudaMemcpyDeviceToHost, ws.st));
+    if (lay.out_size) ws.d2h(p, ws.out_words.p, lay.out_size);
     p += lay.out_size;
     ws.stage_end(h, 0);
     SZ3B_CUDA(cudaStreamSynchronize(ws.st));
@@ -406,7 +405,7 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
                                  conf.absErrorBound, d_flags, ncand, ws.st);
         ws.stage_end(h, 1);
         std::vector<uint8_t> flags(ncand);
-        SZ3B_CUDA(cudaMemcpyAsync(flags.data(), d_flags, ncand, cudaMemcpyDeviceToHost, ws.st));
+        ws.d2h(flags.data(), d_flags, ncand);
         SZ3B_CUDA(cudaStreamSynchronize(ws.st));
         for (uint64_t b = 0; b < ncand; b++)
             if (flags[b]) filtered.push_back(b);
@@ -438,7 +437,7 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
     T *d_cubes = ws.cubes.as<T>(sampling_num);
     {
         uint64_t *d_starts = ws.starts.as<uint64_t>(ncubes);
-        SZ3B_CUDA(cudaMemcpyAsync(d_starts, starts.data(), ncubes * sizeof(uint64_t), cudaMemcpyHostToDevice, ws.st));
+        ws.h2d(d_starts, starts.data(), ncubes * sizeof(uint64_t));
         size_t h = ws.stage_begin("tune_gather");
         launch_gather_cubes<T>(d_data, N, dims32, static_cast<uint32_t>(sbs + 1), d_starts, ncubes, d_cubes, ws.st);
         ws.stage_end(h, 1);
@@ -518,7 +517,7 @@ static size_t lossless_compress(Workspace &ws, const sz3b_config &conf, const T 
     const uint8_t *src = reinterpret_cast<const uint8_t *>(data);
     if (loc == SZ3B_DEVICE) {
         uint8_t *h = static_cast<uint8_t *>(ws.stage.ensure(bytes));
-        SZ3B_CUDA(cudaMemcpyAsync(h, data, bytes, cudaMemcpyDeviceToHost, ws.st));
+        ws.d2h(h, data, bytes);
         SZ3B_CUDA(cudaStreamSynchronize(ws.st));
         src = h;
     }
@@ -668,7 +667,7 @@ static void interp_decompose_t(Workspace &ws, const sz3b_config &conf, double eb
     // indices -> host int32
     int32_t *d_wide = ws.side_q.as<int32_t>(n);
     launch_widen<QT>(d_q, n, d_wide, ws.st);
-    SZ3B_CUDA(cudaMemcpyAsync(quant_out, d_wide, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ws.st));
+    ws.d2h(quant_out, d_wide, n * sizeof(int32_t));
     // unpredictables: reuse the packer's ordered compaction with a trivial (all length 0) code book
     HuffmanBook book;
     EncodeLayout lay;
@@ -678,8 +677,7 @@ static void interp_decompose_t(Workspace &ws, const sz3b_config &conf, double eb
     blob.resize(hdr_len + lay.n_unpred * sizeof(T));
     memcpy(blob.data(), hdr, hdr_len);
     if (lay.n_unpred)
-        SZ3B_CUDA(cudaMemcpyAsync(blob.data() + hdr_len, ws.unpred_out.p, lay.n_unpred * sizeof(T),
-                                  cudaMemcpyDeviceToHost, ws.st));
+        ws.d2h(blob.data() + hdr_len, ws.unpred_out.p, lay.n_unpred * sizeof(T));
     SZ3B_CUDA(cudaStreamSynchronize(ws.st));
 }
 
@@ -698,11 +696,11 @@ void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vec
     if (n == 0) fail(SZ3B_E_INVALID_ARGUMENT, "Huffman bins should not be empty");
     int *d_mm = ws.misc.as<int>(2);
     int init[2] = {0x7fffffff, static_cast<int>(0x80000000)};
-    SZ3B_CUDA(cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ws.st));
+    ws.h2d(d_mm, init, sizeof(init));
     size_t h = ws.stage_begin("huffman_histogram");
     launch_minmax_int<int32_t>(d_q, n, d_mm, ws.st);
     int mm[2];
-    SZ3B_CUDA(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ws.st));
+    ws.d2h(mm, d_mm, sizeof(mm));
     SZ3B_CUDA(cudaStreamSynchronize(ws.st));
     const int64_t span = static_cast<int64_t>(mm[1]) - mm[0] + 1;
     if (span > (1 << 26)) fail(SZ3B_E_UNSUPPORTED, "Huffman symbol range above 2^26");
@@ -718,7 +716,7 @@ void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vec
     memcpy(out.data(), book.tree_blob.data(), lay.tree_len);
     uint8_t *p = out.data() + lay.tree_len;
     put<uint64_t>(p, lay.out_size);
-    if (lay.out_size) SZ3B_CUDA(cudaMemcpyAsync(p, ws.out_words.p, lay.out_size, cudaMemcpyDeviceToHost, ws.st));
+    if (lay.out_size) ws.d2h(p, ws.out_words.p, lay.out_size);
     SZ3B_CUDA(cudaStreamSynchronize(ws.st));
     if (tree_len) *tree_len = lay.tree_len;
 }
@@ -728,7 +726,7 @@ void huffman_encode_stage(Workspace &ws, const int32_t *q, size_t n, int loc, st
     const int32_t *d_q = q;
     if (loc == SZ3B_HOST) {
         int32_t *d = ws.side_q.as<int32_t>(n);
-        SZ3B_CUDA(cudaMemcpyAsync(d, q, n * sizeof(int32_t), cudaMemcpyHostToDevice, ws.st));
+        ws.h2d(d, q, n * sizeof(int32_t));
         d_q = d;
     }
     huffman_encode_device(ws, d_q, n, out, tree_len);

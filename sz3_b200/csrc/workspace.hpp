@@ -111,7 +111,18 @@ struct Workspace {
         }
         return ev_pool[ev_used++];
     }
+    // bytes moved across PCIe by the current call (reported by sz3b_last_transfer)
+    size_t h2d_bytes = 0, d2h_bytes = 0;
+    void h2d(void *dst, const void *src, size_t bytes) {
+        SZ3B_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        h2d_bytes += bytes;
+    }
+    void d2h(void *dst, const void *src, size_t bytes) {
+        SZ3B_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        d2h_bytes += bytes;
+    }
     void prof_reset() {
+        h2d_bytes = d2h_bytes = 0;
         prof.clear();
         pending.clear();
         ev_used = 0;

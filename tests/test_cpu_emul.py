@@ -1,0 +1,48 @@
+"""CPU-only check of the kernel bodies' traversal/indexing logic: sz3_b200/csrc/interp_body.cuh compiled with g++ and
+driven by host threads (tests/emul) must reproduce the reference's quantization indices, order and unpredictables.
+This is test infrastructure; the product only instantiates those bodies inside __global__ kernels."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import ALGO_INTERP, dtype_code, emul_lib, field_nd, interp_blob_unpred, make_config, ref_interp, ref_lib
+
+pytestmark = pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref not built")
+
+
+def emul(data, conf, eb, schedule, nthreads=4):
+    E = emul_lib()
+    q = np.empty(data.size, np.int32)
+    un = np.empty(data.size, data.dtype)
+    nun = C.c_size_t(0)
+    rc = E.emul_interp_decompose(dtype_code(data), C.byref(conf), C.c_double(eb), data.ctypes.data_as(C.c_void_p), schedule,
+                                 nthreads, q.ctypes.data_as(C.c_void_p), un.ctypes.data_as(C.c_void_p), C.byref(nun), None)
+    assert rc == 0
+    return q, un[:nun.value]
+
+
+@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("shape,dtype,kw", [
+    ((40, 50, 70), np.float32, dict(interpAlgo=1, interpDirection=0)),
+    ((33, 65, 97), np.float32, dict(interpAlgo=0, interpDirection=5)),
+    ((20, 37, 66), np.float64, dict(interpAlgo=1, interpDirection=3, interpAlpha=2.0, interpBeta=3.0)),
+    ((8, 8, 128), np.float32, dict(interpAlgo=1, interpDirection=0)),
+])
+def test_emul_matches_reference_3d(shape, dtype, kw, schedule):
+    data = field_nd(shape, dtype)
+    conf = make_config(shape, cmprAlgo=ALGO_INTERP, interpAnchorStride=32, **kw)
+    q_ref, blob_ref, _ = ref_interp(ref_lib(), data, conf, 1e-2)
+    q, un = emul(data, conf, 1e-2, schedule)
+    assert np.array_equal(q, q_ref)
+    _, un_ref = interp_blob_unpred(blob_ref, conf.N, dtype)
+    assert np.array_equal(un, un_ref)
+
+
+@pytest.mark.parametrize("shape", [(9, 12, 20, 18), (100, 333), (5000,)])
+def test_emul_matches_reference_other_ranks(shape):
+    data = field_nd(shape, np.float32)
+    conf = make_config(shape, cmprAlgo=ALGO_INTERP, interpAnchorStride=[4096, 128, 32, 16][len(shape) - 1])
+    q_ref, blob_ref, _ = ref_interp(ref_lib(), data, conf, 1e-3)
+    q, un = emul(data, conf, 1e-3, 0)
+    assert np.array_equal(q, q_ref)
