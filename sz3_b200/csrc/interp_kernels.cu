@@ -4,6 +4,7 @@
 
 #include "device_ctx.cuh"
 #include "interp_body.cuh"
+#include "interp_fast.cuh"
 #include "launch.hpp"
 
 namespace sz3b {
@@ -66,6 +67,21 @@ __global__ void __launch_bounds__(kTileThreads) k_interp_tile(InterpArgs<T, QT> 
     ctx.flush();
 }
 
+// lean tile schedule (interp_fast.cuh): two CTAs per SM
+template <class T, class QT>
+__global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 2 : 1) k_interp_ftile(InterpArgs<T, QT> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    unsigned *shist = reinterpret_cast<unsigned *>(smem_raw + sizeof(T) * kTileSmemElems);
+    __shared__ FastTile ft;
+    DevCtx ctx(shist, A.hist, A.qp.radius);
+    ctx.clear();
+    if (threadIdx.x == 0) fast_tile_setup(A, blockIdx.x, blockIdx.y, ft);
+    __syncthreads();
+    fast_tile_body(A, ctx, sm, ft);
+    ctx.flush();
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // generic schedule, any N
 // ---------------------------------------------------------------------------------------------------------------------
@@ -102,6 +118,18 @@ void interp_launch_tiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t n
 }
 
 template <class T, class QT>
+void interp_launch_ftiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_interp_ftile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        attr_set = true;
+    }
+    dim3 grid(static_cast<unsigned>(ntiles), nbatch);
+    k_interp_ftile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
+}
+
+template <class T, class QT>
 void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cudaStream_t st) {
     uint64_t total = pass_points(A, p);
     if (total == 0) return;
@@ -113,6 +141,7 @@ void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cuda
     template void interp_launch_anchors<T, QT>(const InterpArgs<T, QT> &, uint32_t, uint64_t, uint32_t,        \
                                                cudaStream_t);                                                   \
     template void interp_launch_tiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);      \
+    template void interp_launch_ftiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);     \
     template void interp_launch_pass<T, QT>(const InterpArgs<T, QT> &, int, uint32_t, cudaStream_t);
 SZ3B_INST(float, uint16_t)
 SZ3B_INST(float, uint32_t)

@@ -179,7 +179,10 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         for (int d = 0; d < kMaxDim; d++) A.nb[d] = L.nb[d];
         A.block_base = d_table + L.table_off;
         if (pl.tile) {
-            interp_launch_tiles<T, QT>(A, L.nblocks, nbatch, ws.st);
+            if (pl.fast)
+                interp_launch_ftiles<T, QT>(A, L.nblocks, nbatch, ws.st);
+            else
+                interp_launch_tiles<T, QT>(A, L.nblocks, nbatch, ws.st);
             (*launches)++;
         } else {
             for (int p = 0; p < pl.sh.N; p++) {

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../sz3_b200/csrc/interp_body.cuh"
+#include "../../sz3_b200/csrc/interp_fast.cuh"
 #include "../../sz3_b200/csrc/interp_plan.hpp"
 
 using namespace sz3b;
@@ -90,9 +91,15 @@ static int run(const sz3b_config &c, double eb, const T *data, int schedule, int
             auto worker = [&](int t) {
                 HostCtx ctx{static_cast<uint32_t>(t), static_cast<uint32_t>(nthreads), &bar, hist.data()};
                 for (uint64_t tile = 0; tile < L.nblocks; tile++) {
-                    TileGeom tg;
-                    tile_geom(A, static_cast<uint32_t>(tile), 0, tg);
-                    tile_body(A, ctx, sm.data(), tg, 0);
+                    if (pl.fast) {
+                        FastTile ft;
+                        fast_tile_setup(A, static_cast<uint32_t>(tile), 0, ft);
+                        fast_tile_body(A, ctx, sm.data(), ft);
+                    } else {
+                        TileGeom tg;
+                        tile_geom(A, static_cast<uint32_t>(tile), 0, tg);
+                        tile_body(A, ctx, sm.data(), tg, 0);
+                    }
                     ctx.sync();
                 }
             };

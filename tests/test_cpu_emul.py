@@ -22,7 +22,7 @@ def emul(data, conf, eb, schedule, nthreads=4):
     return q, un[:nun.value]
 
 
-@pytest.mark.parametrize("schedule", [1, 2])
+@pytest.mark.parametrize("schedule", [1, 2, 3])
 @pytest.mark.parametrize("shape,dtype,kw", [
     ((40, 50, 70), np.float32, dict(interpAlgo=1, interpDirection=0)),
     ((33, 65, 97), np.float32, dict(interpAlgo=0, interpDirection=5)),
