@@ -44,10 +44,62 @@ struct DevCtx {
         else
             atomicAdd(&ghist[sym], 1ull);
     }
+    __device__ __forceinline__ void pass_end() {}
     __device__ __forceinline__ void flush() {
         unsigned c = center_cnt;
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if ((threadIdx.x & 31) == 0 && c) atomicAdd(&shist[center - lo], c);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kHistWindow; i += blockDim.x) {
+            unsigned v = shist[i];
+            if (v) atomicAdd(&ghist[lo + i], static_cast<unsigned long long>(v));
+        }
+    }
+};
+
+// Context of the line-walker kernel: the 8 bins around the radius are counted in one packed 64-bit register
+// (8 bits per bin; a thread handles far fewer than 255 points per pass) and reduced across the warp at pass_end().
+struct DevCtx2 {
+    unsigned *shist;
+    unsigned long long *ghist;
+    int lo, lo8;
+    unsigned long long packed;
+
+    __device__ __forceinline__ DevCtx2(unsigned *sh, unsigned long long *gh, int radius)
+        : shist(sh), ghist(gh), lo(radius - kHistWindow / 2), lo8(radius - 4), packed(0) {}
+
+    __device__ __forceinline__ uint32_t tid() const { return threadIdx.x; }
+    __device__ __forceinline__ uint32_t nthreads() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+
+    __device__ __forceinline__ void clear() {
+        for (int i = threadIdx.x; i < kHistWindow; i += blockDim.x) shist[i] = 0;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void hist_add(int sym, bool active) {
+        if (!active) return;
+        const unsigned k8 = static_cast<unsigned>(sym - lo8);
+        if (k8 < 8u) {
+            packed += 1ull << (k8 * 8u);
+            return;
+        }
+        const unsigned k = static_cast<unsigned>(sym - lo);
+        if (k < static_cast<unsigned>(kHistWindow))
+            atomicAdd(&shist[k], 1u);
+        else
+            atomicAdd(&ghist[sym], 1ull);
+    }
+    // all threads of the CTA, converged
+    __device__ __forceinline__ void pass_end() {
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            unsigned v = static_cast<unsigned>(packed >> (8 * b)) & 0xffu;
+            v = __reduce_add_sync(0xffffffffu, v);
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&shist[lo8 - lo + b], v);
+        }
+        packed = 0;
+    }
+    __device__ __forceinline__ void flush() {
         __syncthreads();
         for (int i = threadIdx.x; i < kHistWindow; i += blockDim.x) {
             unsigned v = shist[i];

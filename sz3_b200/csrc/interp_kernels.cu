@@ -5,6 +5,7 @@
 #include "device_ctx.cuh"
 #include "interp_body.cuh"
 #include "interp_fast.cuh"
+#include "interp_line.cuh"
 #include "launch.hpp"
 
 namespace sz3b {
@@ -82,6 +83,26 @@ __global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 2 : 1) k_interp
     ctx.flush();
 }
 
+// line-walker tile schedule (interp_line.cuh): two CTAs per SM; three lanes build the pass tables while the
+// rest of the CTA already fills shared memory
+template <class T, class QT>
+__global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 2 : 1) k_interp_ltile(InterpArgs<T, QT> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    unsigned *shist = reinterpret_cast<unsigned *>(smem_raw + sizeof(T) * kTileSmemElems);
+    __shared__ LineTile lt;
+    DevCtx2 ctx(shist, A.hist, A.qp.radius);
+    for (int i = threadIdx.x; i < kHistWindow; i += blockDim.x) shist[i] = 0;
+    LineGeom lg;
+    line_geom(A, blockIdx.x, blockIdx.y, lg);
+    if ((threadIdx.x & 31u) == 0 && (threadIdx.x >> 5) < 3)
+        line_pass_setup(A, blockIdx.x, blockIdx.y, static_cast<int>(threadIdx.x >> 5), blockDim.x, lt.ps[threadIdx.x >> 5]);
+    line_fill(A, ctx, lg, sm);
+    __syncthreads();
+    line_tile_passes(A, ctx, sm, lg, lt);
+    ctx.flush();
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // generic schedule, any N
 // ---------------------------------------------------------------------------------------------------------------------
@@ -130,6 +151,18 @@ void interp_launch_ftiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t 
 }
 
 template <class T, class QT>
+void interp_launch_ltiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_interp_ltile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        attr_set = true;
+    }
+    dim3 grid(static_cast<unsigned>(ntiles), nbatch);
+    k_interp_ltile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
+}
+
+template <class T, class QT>
 void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cudaStream_t st) {
     uint64_t total = pass_points(A, p);
     if (total == 0) return;
@@ -142,6 +175,7 @@ void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cuda
                                                cudaStream_t);                                                   \
     template void interp_launch_tiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);      \
     template void interp_launch_ftiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);     \
+    template void interp_launch_ltiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);     \
     template void interp_launch_pass<T, QT>(const InterpArgs<T, QT> &, int, uint32_t, cudaStream_t);
 SZ3B_INST(float, uint16_t)
 SZ3B_INST(float, uint32_t)

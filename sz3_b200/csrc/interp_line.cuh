@@ -1,0 +1,413 @@
+// sz3_b200/csrc/interp_line.cuh -- third-generation N == 3 tile schedule of the fused interpolation-predict +
+// LinearQuantizer kernel (InterpolationDecomposition::compress, reference
+// include/SZ3/decomposition/InterpolationDecomposition.hpp:79-147, :309-454).
+//
+// Same closed-tile mathematics as tile_body (interp_body.cuh); the work is re-cut so that a thread never decodes an
+// index per point.  A pass along direction D is executed as
+//
+//   line items (D != fastest dim): the thread owns a segment of one line along D; lanes of a warp sit on consecutive
+//       x, so shared-memory reads, the 16-bit index stores and the recon2 stores are contiguous; the four stencil
+//       taps slide through registers (one new shared-memory load per point), every offset advances by a constant.
+//   row items  (D == fastest dim): 16 lanes cover the 16 targets of one row along x, the thread walks over rows
+//       (y, z) with constant increments; its stencil type (cubic / quad_1 / quad_2 / linear / copy) is fixed, so it
+//       is evaluated branch-free as a 4-tap filter whose coefficients reproduce the reference's evaluation order.
+//
+// The quantization-index histogram of HuffmanEncoder::init is accumulated in packed per-thread registers for the
+// 8 bins around the radius (Ctx::hist_add) and reduced once per pass.
+#pragma once
+#include "core.cuh"
+#include "interp_body.cuh"
+#include "interp_fast.cuh"
+
+namespace sz3b {
+
+struct LinePass {
+    uint32_t kind;             // 0 = line items, 1 = row items
+    uint32_t D, n, cD, jmax;   // direction, points along it, targets (n/2), largest even local index / 2
+    uint32_t cu, cv;           // items along the two other dims (u slower than v in natural order)
+    uint32_t mgu, mgv;
+    uint32_t skipu, skipv;     // items below skip lie on a low face owned by the previous tile
+    uint32_t sU, sV, sC;       // smem offset of (iu, iv, local index 0 along D)
+    uint32_t hS, tS;           // neighbour j (local 2j) at + j*hS; target k (local 2k+1) at + k*hS + tS (passes 0/1)
+    uint32_t mU, mV, mD;       // emission rank multipliers, main sub-phase
+    uint32_t bU, bV;           // ... boundary sub-phases
+    uint32_t kfirst;           // k of the first main target (cubic 1, linear 0)
+    uint32_t bnd[3], bbase[3]; // boundary sub-phases: local index and start offset inside the pass
+    uint32_t nseg, seglen;     // line items: segments per line
+    uint64_t base;             // position of the pass in the index stream
+    uint64_t gU, gV, gD, gC;   // data element offset (from the tile origin) = iu*gU + iv*gV + gC + l_D*gD
+    uint64_t hU, hV, hD, hC;   // same for recon2 (level stride >= 2)
+};
+
+struct LineTile {
+    LinePass ps[3];
+};
+
+SZ_HD uint32_t magic_u32_fast(uint32_t c) { return c <= 1 ? 0u : 0xffffffffu / c + 1u; }
+
+// Tile geometry every thread keeps in registers (fill phase).
+struct LineGeom {
+    uint32_t begin[3], n[3], E[3];
+    uint32_t last;
+    uint64_t gbase, g2base;
+};
+
+template <class T, class QT>
+SZ_HD void line_geom(const InterpArgs<T, QT> &A, uint32_t tile, uint32_t batch, LineGeom &lg) {
+    const InterpShape &sh = A.sh;
+    const uint32_t s = A.s;
+    uint32_t bidx[3];
+    uint32_t r = tile;
+    bidx[2] = r % A.nb[2];
+    r /= A.nb[2];
+    bidx[1] = r % A.nb[1];
+    bidx[0] = r / A.nb[1];
+    lg.last = static_cast<uint32_t>(sh.perm[2]);
+    lg.gbase = batch * A.data_bstride;
+    lg.g2base = batch * A.recon2_bstride;
+    const uint32_t B = kInterpBlock * s;
+    for (int d = 0; d < 3; d++) {
+        const uint32_t b = bidx[d] * B;
+        uint32_t e = b + B;
+        if (e > sh.dims[d] - 1) e = sh.dims[d] - 1;
+        lg.begin[d] = b;
+        lg.n[d] = (e - b) / s + 1;
+        lg.E[d] = static_cast<uint32_t>(d) == lg.last ? (lg.n[d] + 1) / 2 : lg.n[d];
+        lg.gbase += static_cast<uint64_t>(b) * sh.stride[d];
+        lg.g2base += static_cast<uint64_t>(b >> 1) * A.stride2[d];
+    }
+}
+
+// Pass table p of one tile (thread p of the CTA runs this while the others fill shared memory).
+template <class T, class QT>
+SZ_HD void line_pass_setup(const InterpArgs<T, QT> &A, uint32_t tile, uint32_t batch, int p, uint32_t nthreads,
+                           LinePass &P) {
+    const InterpShape &sh = A.sh;
+    const uint32_t s = A.s;
+    TileGeom tg;
+    tile_geom(A, tile, batch, tg);
+    const int last = tg.a[2];
+    const int D = tg.a[p];
+    const PassGeom &pg = tg.pg[p];
+    P.D = static_cast<uint32_t>(D);
+    P.n = pg.n;
+    P.cD = pg.n / 2;
+    P.jmax = (pg.n - 1) / 2;
+    P.kind = D == 2 ? 1u : 0u;
+    P.base = tg.pass_base[p];
+    P.kfirst = sh.cubic ? 1u : 0u;
+    for (uint32_t k = 0; k < 3; k++) {
+        P.bnd[k] = k < pg.nbnd ? pg.bnd[k] : 0xffffffffu;
+        P.bbase[k] = static_cast<uint32_t>((pg.main_cnt + k) * pg.other);
+    }
+    // the two other dims in natural order
+    int u = -1, v = -1;
+    for (int d = 0; d < 3; d++)
+        if (d != D) {
+            if (u < 0) u = d; else v = d;
+        }
+    uint32_t cnt[3] = {0, 0, 0}, mul[3] = {0, 0, 0}, add[3] = {0, 0, 0}, skip[3] = {0, 0, 0};
+    for (int q = 0; q < 3; q++) {
+        const int d = tg.a[q];
+        const uint32_t n = tg.g.n[d];
+        const uint32_t low = tg.g.begin[d] ? 1u : 0u;
+        if (q == p) continue;
+        if (q < p) {          // refined to step s; the low face is neither owned nor read later
+            cnt[d] = n - low; mul[d] = 1; add[d] = low; skip[d] = 0;
+        } else {              // still on the 2s lattice; low face feeds the later pass along d
+            cnt[d] = (n + 1) / 2; mul[d] = 2; add[d] = 0; skip[d] = low;
+        }
+    }
+    // smem: local index l of dim d sits at l (d != last) or l/2 (d == last, l even)
+    auto sm_step = [&](int d, uint32_t lstep) -> uint32_t {
+        return d == last ? (lstep / 2) * tg.sst[d] : lstep * tg.sst[d];
+    };
+    P.cu = cnt[u]; P.cv = cnt[v];
+    P.mgu = magic_u32_fast(P.cu); P.mgv = magic_u32_fast(P.cv);
+    P.skipu = skip[u]; P.skipv = skip[v];
+    // (add is 0 or 1 and only 1 when the dim is not `last`... a dim with add == 1 was interpolated earlier, the
+    //  last pass dim never is)
+    P.sU = sm_step(u, mul[u]); P.sV = sm_step(v, mul[v]);
+    P.sC = add[u] * tg.sst[u] + add[v] * tg.sst[v];
+    if (p < 2) {
+        P.hS = 2 * tg.sst[D];
+        P.tS = tg.sst[D];
+    } else {
+        P.hS = tg.sst[D];
+        P.tS = 0;
+    }
+    // emission multipliers: rank = (r0*X1 + r1)*X2 + r2 over natural dims, r_D = main index (or 0 on a boundary)
+    {
+        const uint32_t em[3] = {D == 0 ? pg.main_cnt : pg.cnt[0], D == 1 ? pg.main_cnt : pg.cnt[1],
+                                D == 2 ? pg.main_cnt : pg.cnt[2]};
+        const uint32_t eb[3] = {D == 0 ? 1u : pg.cnt[0], D == 1 ? 1u : pg.cnt[1], D == 2 ? 1u : pg.cnt[2]};
+        const uint32_t mm[3] = {em[1] * em[2], em[2], 1u};
+        const uint32_t bm[3] = {eb[1] * eb[2], eb[2], 1u};
+        P.mU = mm[u]; P.mV = mm[v]; P.mD = mm[D];
+        P.bU = bm[u]; P.bV = bm[v];
+    }
+    // global offsets relative to the tile origin
+    const uint64_t gs[3] = {static_cast<uint64_t>(s) * sh.stride[0], static_cast<uint64_t>(s) * sh.stride[1],
+                            static_cast<uint64_t>(s) * sh.stride[2]};
+    const uint64_t hs[3] = {static_cast<uint64_t>(s >> 1) * A.stride2[0], static_cast<uint64_t>(s >> 1) * A.stride2[1],
+                            static_cast<uint64_t>(s >> 1) * A.stride2[2]};
+    P.gU = mul[u] * gs[u]; P.gV = mul[v] * gs[v]; P.gD = gs[D];
+    P.gC = add[u] * gs[u] + add[v] * gs[v];
+    P.hU = mul[u] * hs[u]; P.hV = mul[v] * hs[v]; P.hD = hs[D];
+    P.hC = add[u] * hs[u] + add[v] * hs[v];
+    // segments of a line: keep every round of the CTA reasonably full, never shorter than 2 targets
+    P.nseg = 1;
+    P.seglen = P.cD;
+    if (P.kind == 0 && P.cD >= 4) {
+        const uint32_t lines = P.cu * P.cv;
+        uint32_t best = 1;
+        uint64_t best_cost = ~0ull;
+        for (uint32_t ns = 1; ns <= 4 && P.cD / ns >= 2; ns *= 2) {
+            const uint32_t items = lines * ns;
+            const uint32_t rounds = (items + nthreads - 1) / nthreads;
+            const uint32_t len = P.cD / ns + P.cD % ns;
+            const uint64_t cost = static_cast<uint64_t>(rounds) * (len + 2);   // +2: window priming per segment
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = ns;
+            }
+        }
+        P.nseg = best;
+        P.seglen = P.cD / best;
+    }
+    if (pg.n <= 1) P.cu = 0;   // nothing to do along a degenerate direction
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// line items: the thread walks targets k0 <= k < k1 of one line along D
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, class QT, class Ctx, bool LAST>
+SZ_HD void line_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, const LinePass &P, T *sm, bool cubic,
+                      bool write2) {
+    const uint32_t tid = ctx.tid(), nt = ctx.nthreads();
+    const uint32_t cu = P.cu, cv = P.cv, mgu = P.mgu, mgv = P.mgv, n = P.n, cD = P.cD, jmax = P.jmax;
+    const uint32_t hS = P.hS, tS = P.tS, mD = P.mD, nseg = P.nseg, seglen = P.seglen;
+    const uint32_t bnd0 = P.bnd[0], bnd1 = P.bnd[1], bb0 = P.bbase[0], bb1 = P.bbase[1], bb2 = P.bbase[2];
+    const uint32_t kfirst = P.kfirst;
+    const uint64_t base = P.base;
+    const uint32_t nitems = nseg * cu * cv;
+    for (uint32_t it = tid; it < nitems; it += nt) {
+        const uint32_t t = fast_div(it, mgv);
+        const uint32_t iv = it - t * cv;
+        const uint32_t sg = fast_div(t, mgu);
+        const uint32_t iu = t - sg * cu;
+        const uint32_t k0 = sg * seglen;
+        const uint32_t k1 = sg + 1 == nseg ? cD : k0 + seglen;
+        const bool owned = iu >= P.skipu && iv >= P.skipv;
+        const uint32_t ru = iu - P.skipu, rv = iv - P.skipv;
+        uint32_t pm = ru * P.mU + rv * P.mV + (k0 - kfirst) * mD;
+        const uint32_t pb = ru * P.bU + rv * P.bV;
+        const T *gp = A.data + lg.gbase + iu * P.gU + iv * P.gV + P.gC + (2 * k0 + 1) * P.gD;
+        T *hp = A.recon2 + lg.g2base + iu * P.hU + iv * P.hV + P.hC + (2 * k0 + 1) * P.hD;
+        const uint64_t gstep = 2 * P.gD, hstep = 2 * P.hD;
+        T *nb = sm + (iu * P.sU + iv * P.sV + P.sC + k0 * hS);   // neighbour j = k (local index i-1)
+        T w0 = 0, w1 = nb[0], w2 = 0, w3 = 0;
+        if (k0 >= 1) w0 = nb[-static_cast<int>(hS)];
+        if (k0 + 1 <= jmax) w2 = nb[hS];
+        if (k0 + 2 <= jmax) w3 = nb[2 * hS];
+        T prev_rec = 0;
+        for (uint32_t k = k0; k < k1; k++) {
+            const uint32_t i = 2 * k + 1;
+            T pred;
+            bool in_main;
+            if (cubic) {
+                if (k >= 1) {
+                    if (i + 3 < n) {
+                        pred = interp_cubic<T>(w0, w1, w2, w3);
+                        in_main = true;
+                    } else {
+                        in_main = false;
+                        pred = i + 1 < n ? interp_quad_2<T>(w0, w1, w2) : interp_linear1<T>(w0, w1);
+                    }
+                } else {
+                    in_main = false;
+                    pred = i + 3 < n ? interp_quad_1<T>(w1, w2, w3) : (i + 1 < n ? interp_linear<T>(w1, w2) : w1);
+                }
+            } else {
+                if (i + 1 < n) {
+                    pred = interp_linear<T>(w1, w2);
+                    in_main = true;
+                } else {
+                    in_main = false;
+                    pred = n < 3 ? w1 : interp_linear1<T>(prev_rec, w1);
+                }
+            }
+            const T orig = LAST ? *gp : nb[tS];
+            T rec;
+            const int qv = quantize<T>(orig, pred, A.qp, rec);
+            if (!LAST) nb[tS] = rec;
+            const uint32_t pos = in_main ? pm : pb + (i == bnd0 ? bb0 : (i == bnd1 ? bb1 : bb2));
+            emit(A, ctx, base + pos, qv, orig, owned);
+            if (write2 && owned) *hp = rec;
+            prev_rec = rec;
+            pm += mD;
+            w0 = w1;
+            w1 = w2;
+            w2 = w3;
+            nb += hS;
+            w3 = k + 3 <= jmax ? nb[2 * hS] : static_cast<T>(0);
+            gp += gstep;
+            hp += hstep;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// row items (D == 2): 16 lanes on the targets of one row, the thread walks over rows
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, class QT, class Ctx, bool LAST>
+SZ_HD void row_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, const LinePass &P, T *sm, bool cubic,
+                     bool write2) {
+    const uint32_t tid = ctx.tid(), nt = ctx.nthreads();
+    const uint32_t cu = P.cu, cv = P.cv, n = P.n, cD = P.cD;
+    const uint32_t hS = P.hS, tS = P.tS;
+    const uint32_t k = tid & 15u, slot = tid >> 4, nslots = nt >> 4;
+    const uint32_t i = 2 * k + 1;
+    const bool merge_tail = !cubic && !(n & 1u) && n >= 4;   // linear mode: target n-1 is done by the lane of n-3
+    bool act = k < cD && !(merge_tail && k + 1 == cD);
+    // stencil of this lane as a 4-tap filter over (l-3, l-1, l+1, l+3); coefficients of unused taps are 0 and the
+    // taps themselves are not loaded (an infinite neighbour times 0 would poison the sum)
+    T c0 = 0, c1 = 0, c2 = 0, c3 = 0, sc = 1;
+    bool use_l1 = false, in_main = false;
+    if (cubic) {
+        if (k >= 1) {
+            if (i + 3 < n) {
+                c0 = -1; c1 = 9; c2 = 9; c3 = -1; sc = static_cast<T>(0.0625);
+                in_main = true;
+            } else if (i + 1 < n) {
+                c0 = -1; c1 = 6; c2 = 3; sc = static_cast<T>(0.125);
+            } else {
+                use_l1 = true;
+            }
+        } else {
+            if (i + 3 < n) {
+                c1 = 3; c2 = 6; c3 = -1; sc = static_cast<T>(0.125);
+            } else if (i + 1 < n) {
+                c1 = 1; c2 = 1; sc = static_cast<T>(0.5);
+            } else {
+                c1 = 1;
+            }
+        }
+    } else {
+        if (i + 1 < n) {
+            c1 = 1; c2 = 1; sc = static_cast<T>(0.5);
+            in_main = true;
+        } else {
+            c1 = 1;   // n < 3 (n >= 4 is the merged tail)
+        }
+    }
+    const bool ld0 = c0 != 0 || use_l1, ld2 = c2 != 0, ld3 = c3 != 0;
+    const uint32_t bsel = i == P.bnd[0] ? P.bbase[0] : (i == P.bnd[1] ? P.bbase[1] : P.bbase[2]);
+    const uint32_t posk = in_main ? (k - P.kfirst) * P.mD : bsel;
+    const uint32_t pU = in_main ? P.mU : P.bU, pV = in_main ? P.mV : P.bV;
+    const uint64_t base = P.base;
+    const uint32_t nrows = cu * cv;
+    const uint32_t dU = cv ? nslots / cv : 0, dV = cv ? nslots % cv : 0;
+    uint32_t iu = fast_div(slot, P.mgv), iv = slot - iu * cv;
+    const uint32_t soff_k = P.sC + k * hS;
+    const uint64_t goff_k = lg.gbase + P.gC + static_cast<uint64_t>(i) * P.gD;
+    const uint64_t hoff_k = lg.g2base + P.hC + static_cast<uint64_t>(i) * P.hD;
+    const bool do_tail = merge_tail && k + 2 == cD;
+    for (uint32_t row = slot; row < nrows; row += nslots) {
+        int qv = 0;
+        uint64_t pos = 0;
+        T orig = 0;
+        bool owned = false;
+        if (act) {
+            const T *nb = sm + (iu * P.sU + iv * P.sV + soff_k);
+            const T w1 = nb[0];
+            const T w0 = ld0 ? nb[-static_cast<int>(hS)] : static_cast<T>(0);
+            const T w2 = ld2 ? nb[hS] : static_cast<T>(0);
+            const T w3 = ld3 ? nb[2 * hS] : static_cast<T>(0);
+            const T pred = use_l1 ? interp_linear1<T>(w0, w1) : (((c0 * w0 + c1 * w1) + c2 * w2) + c3 * w3) * sc;
+            const uint64_t goff = goff_k + iu * P.gU + iv * P.gV;
+            const uint64_t hoff = hoff_k + iu * P.hU + iv * P.hV;
+            orig = LAST ? A.data[goff] : nb[tS];
+            T rec;
+            qv = quantize<T>(orig, pred, A.qp, rec);
+            if (!LAST) const_cast<T *>(nb)[tS] = rec;
+            owned = iu >= P.skipu && iv >= P.skipv;
+            const uint32_t ru = iu - P.skipu, rv = iv - P.skipv;
+            pos = base + (ru * pU + rv * pV + posk);
+            if (write2 && owned) A.recon2[hoff] = rec;
+            if (do_tail) {
+                // flush this target, then the linear tail i+2 = n-1: linear1(recon(i), value(i+1))
+                emit(A, ctx, pos, qv, orig, owned);
+                const T pred2 = interp_linear1<T>(rec, w2);
+                orig = LAST ? A.data[goff + 2 * P.gD] : nb[tS + hS];
+                qv = quantize<T>(orig, pred2, A.qp, rec);
+                if (!LAST) const_cast<T *>(nb)[tS + hS] = rec;
+                pos = base + (ru * P.bU + rv * P.bV + P.bbase[0]);
+                if (write2 && owned) A.recon2[hoff + 2 * P.hD] = rec;
+            }
+        }
+        emit(A, ctx, pos, qv, orig, act && owned);
+        iv += dV;
+        iu += dU;
+        if (iv >= cv) {
+            iv -= cv;
+            iu++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fill: the sub-lattice even along the last pass dimension; coarse points (all local indices even) from recon2,
+// everything else from the immutable input
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T, class QT, class Ctx>
+SZ_HD void line_fill(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, T *sm) {
+    const uint32_t tid = ctx.tid(), nt = ctx.nthreads();
+    const uint32_t E1 = lg.E[1], E2 = lg.E[2];
+    const uint32_t total = lg.E[0] * E1 * E2;
+    const uint32_t mg1 = magic_u32_fast(E1), mg2 = magic_u32_fast(E2);
+    const uint32_t s = A.s;
+    const uint32_t m0 = lg.last == 0 ? 2u : 1u, m1 = lg.last == 1 ? 2u : 1u, m2 = lg.last == 2 ? 2u : 1u;
+    const uint64_t g0 = m0 * s * A.sh.stride[0], g1 = m1 * s * A.sh.stride[1], g2 = static_cast<uint64_t>(m2) * s;
+    // recon2 offset of local index l (even): (begin + l*s)/2 = begin/2 + (l/2)*s
+    const uint64_t h0 = s * A.stride2[0], h1 = s * A.stride2[1], h2 = s;
+    const T *dat = A.data + lg.gbase;
+    const T *rc2 = A.recon2 + lg.g2base;
+    for (uint32_t it = tid; it < total; it += nt) {
+        const uint32_t r = fast_div(it, mg2);
+        const uint32_t e2 = it - r * E2;
+        const uint32_t e0 = fast_div(r, mg1);
+        const uint32_t e1 = r - e0 * E1;
+        const uint32_t l0 = e0 * m0, l1 = e1 * m1, l2 = e2 * m2;
+        const bool coarse = !((l0 | l1 | l2) & 1u);
+        const T *src = coarse ? rc2 + ((l0 >> 1) * h0 + (l1 >> 1) * h1 + (l2 >> 1) * h2)
+                              : dat + (e0 * g0 + e1 * g1 + e2 * g2);
+        sm[it] = *src;
+    }
+}
+
+template <class T, class QT, class Ctx>
+SZ_HD void line_tile_passes(const InterpArgs<T, QT> &A, Ctx &ctx, T *sm, const LineGeom &lg, const LineTile &lt) {
+    const bool cubic = A.sh.cubic != 0;
+    const bool write2 = A.s >= 2;
+    for (int p = 0; p < 3; p++) {
+        const LinePass &P = lt.ps[p];
+        if (P.cu != 0 && P.cv != 0 && P.cD != 0) {
+            if (P.kind == 0) {
+                if (p < 2)
+                    line_items<T, QT, Ctx, false>(A, ctx, lg, P, sm, cubic, write2);
+                else
+                    line_items<T, QT, Ctx, true>(A, ctx, lg, P, sm, cubic, write2);
+            } else {
+                if (p < 2)
+                    row_items<T, QT, Ctx, false>(A, ctx, lg, P, sm, cubic, write2);
+                else
+                    row_items<T, QT, Ctx, true>(A, ctx, lg, P, sm, cubic, write2);
+            }
+        }
+        ctx.pass_end();
+        if (p < 2) ctx.sync();
+    }
+}
+
+}  // namespace sz3b

@@ -35,7 +35,7 @@ struct InterpPlan {
     uint64_t stride2[kMaxDim];
     uint64_t num2 = 0;
     bool tile = false;            // tile schedule (N == 3) or generic per-pass schedule
-    bool fast = false;            // tile schedule through the lean kernel (interp_fast.cuh)
+    int variant = 0;              // tile kernel: 0 = first generation, 1 = lean (interp_fast.cuh), 2 = line walker (interp_line.cuh)
     int interp_id = 1, direction = 0;
     double alpha = 1.25, beta = 2.0;
     double eb = 0;
@@ -121,8 +121,9 @@ inline const char *build_interp_plan(const sz3b_config &c, double eb, int schedu
     }
     pl.num2 = acc;
     pl.tile = (N == 3) && schedule != 1;
-    pl.fast = pl.tile && schedule != 2;
-    if ((schedule == 2 || schedule == 3) && N != 3) return "tile schedule needs N == 3";
+    pl.variant = schedule == 2 ? 0 : (schedule == 3 ? 1 : 2);
+    if (schedule >= 2 && schedule <= 4 && N != 3) return "tile schedule needs N == 3";
+    if (schedule < 0 || schedule > 4) return "unknown schedule";
 
     pl.levels.clear();
     pl.table.clear();

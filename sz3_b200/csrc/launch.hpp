@@ -19,6 +19,8 @@ void interp_launch_tiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t n
 template <class T, class QT>
 void interp_launch_ftiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st);
 template <class T, class QT>
+void interp_launch_ltiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st);
+template <class T, class QT>
 void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cudaStream_t st);
 
 // encode_kernels.cu

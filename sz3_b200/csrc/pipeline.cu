@@ -179,7 +179,9 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         for (int d = 0; d < kMaxDim; d++) A.nb[d] = L.nb[d];
         A.block_base = d_table + L.table_off;
         if (pl.tile) {
-            if (pl.fast)
+            if (pl.variant == 2)
+                interp_launch_ltiles<T, QT>(A, L.nblocks, nbatch, ws.st);
+            else if (pl.variant == 1)
                 interp_launch_ftiles<T, QT>(A, L.nblocks, nbatch, ws.st);
             else
                 interp_launch_tiles<T, QT>(A, L.nblocks, nbatch, ws.st);

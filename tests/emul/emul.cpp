@@ -10,6 +10,7 @@
 
 #include "../../sz3_b200/csrc/interp_body.cuh"
 #include "../../sz3_b200/csrc/interp_fast.cuh"
+#include "../../sz3_b200/csrc/interp_line.cuh"
 #include "../../sz3_b200/csrc/interp_plan.hpp"
 
 using namespace sz3b;
@@ -21,6 +22,7 @@ struct HostCtx {
     uint32_t tid() const { return t; }
     uint32_t nthreads() const { return nt; }
     void sync() { bar->arrive_and_wait(); }
+    void pass_end() {}
     void hist_add(int sym, bool active) {
         if (active) __atomic_fetch_add(&hist[sym], 1ull, __ATOMIC_RELAXED);
     }
@@ -91,7 +93,15 @@ static int run(const sz3b_config &c, double eb, const T *data, int schedule, int
             auto worker = [&](int t) {
                 HostCtx ctx{static_cast<uint32_t>(t), static_cast<uint32_t>(nthreads), &bar, hist.data()};
                 for (uint64_t tile = 0; tile < L.nblocks; tile++) {
-                    if (pl.fast) {
+                    if (pl.variant == 2) {
+                        static LineTile lt;   // shared by the worker threads like __shared__ memory
+                        LineGeom lg;
+                        line_geom(A, static_cast<uint32_t>(tile), 0, lg);
+                        if (t < 3) line_pass_setup(A, static_cast<uint32_t>(tile), 0, t, static_cast<uint32_t>(nthreads), lt.ps[t]);
+                        line_fill(A, ctx, lg, sm.data());
+                        ctx.sync();
+                        line_tile_passes(A, ctx, sm.data(), lg, lt);
+                    } else if (pl.variant == 1) {
                         FastTile ft;
                         fast_tile_setup(A, static_cast<uint32_t>(tile), 0, ft);
                         fast_tile_body(A, ctx, sm.data(), ft);

@@ -9,6 +9,6 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>/dev/null; cat gpurun_out/bench_ref_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_interp_ftile -s 30 -c 5 -o gpurun_out/prof_tile_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_interp_ltile -s 30 -c 5 -o gpurun_out/prof_tile_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out

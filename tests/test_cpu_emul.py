@@ -22,7 +22,7 @@ def emul(data, conf, eb, schedule, nthreads=4):
     return q, un[:nun.value]
 
 
-@pytest.mark.parametrize("schedule", [1, 2, 3])
+@pytest.mark.parametrize("schedule", [1, 2, 3, 4])
 @pytest.mark.parametrize("shape,dtype,kw", [
     ((40, 50, 70), np.float32, dict(interpAlgo=1, interpDirection=0)),
     ((33, 65, 97), np.float32, dict(interpAlgo=0, interpDirection=5)),
@@ -33,7 +33,7 @@ def test_emul_matches_reference_3d(shape, dtype, kw, schedule):
     data = field_nd(shape, dtype)
     conf = make_config(shape, cmprAlgo=ALGO_INTERP, interpAnchorStride=32, **kw)
     q_ref, blob_ref, _ = ref_interp(ref_lib(), data, conf, 1e-2)
-    q, un = emul(data, conf, 1e-2, schedule)
+    q, un = emul(data, conf, 1e-2, schedule, nthreads=32 if schedule == 4 else 4)
     assert np.array_equal(q, q_ref)
     _, un_ref = interp_blob_unpred(blob_ref, conf.N, dtype)
     assert np.array_equal(un, un_ref)
@@ -46,3 +46,24 @@ def test_emul_matches_reference_other_ranks(shape):
     q_ref, blob_ref, _ = ref_interp(ref_lib(), data, conf, 1e-3)
     q, un = emul(data, conf, 1e-3, 0)
     assert np.array_equal(q, q_ref)
+
+
+@pytest.mark.parametrize("shape,dtype,kw", [
+    ((64, 64, 64), np.float32, dict(interpAlgo=1, interpDirection=5)),
+    ((64, 64, 64), np.float32, dict(interpAlgo=0, interpDirection=0)),
+    ((100, 70, 130), np.float32, dict(interpAlgo=1, interpDirection=0)),
+    ((66, 35, 34), np.float32, dict(interpAlgo=0, interpDirection=5)),
+    ((2, 3, 200), np.float32, dict(interpAlgo=1, interpDirection=2)),
+    ((37, 41, 130), np.float64, dict(interpAlgo=0, interpDirection=1)),
+    ((45, 33, 36), np.float32, dict(interpAlgo=1, interpDirection=4)),
+])
+def test_emul_line_walker_shapes(shape, dtype, kw):
+    """Edge tiles (n = 32 / odd extents / degenerate dims), both interpolators, the non-tuner directions."""
+    data = field_nd(shape, dtype)
+    conf = make_config(shape, cmprAlgo=ALGO_INTERP, interpAnchorStride=32, **kw)
+    q_ref, blob_ref, _ = ref_interp(ref_lib(), data, conf, 1e-2)
+    for nthreads in (16, 48):
+        q, un = emul(data, conf, 1e-2, 4, nthreads=nthreads)
+        assert np.array_equal(q, q_ref)
+        _, un_ref = interp_blob_unpred(blob_ref, conf.N, dtype)
+        assert np.array_equal(un, un_ref)
