@@ -83,6 +83,11 @@ struct DevCtx2 {
             packed += 1ull << (k8 * 8u);
             return;
         }
+        hist_slow(shist, ghist, lo, sym);
+    }
+    // rare path (index outside the 8 register bins), out of line so the hot loops carry only a branch; static, so
+    // that the context itself never has its address taken (it must stay in registers)
+    static __device__ __noinline__ void hist_slow(unsigned *shist, unsigned long long *ghist, int lo, int sym) {
         const unsigned k = static_cast<unsigned>(sym - lo);
         if (k < static_cast<unsigned>(kHistWindow))
             atomicAdd(&shist[k], 1u);

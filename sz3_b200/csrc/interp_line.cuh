@@ -45,6 +45,12 @@ struct LineTile {
 
 SZ_HD uint32_t magic_u32_fast(uint32_t c) { return c <= 1 ? 0u : 0xffffffffu / c + 1u; }
 
+// rare path (an unpredictable point): kept out of line so that the hot loops carry a branch, not predicated stores
+template <class T>
+SZ_NOINLINE void store_unpred(T *ub, uint32_t pos, T orig) {
+    ub[pos] = orig;
+}
+
 // Tile geometry every thread keeps in registers (fill phase).
 struct LineGeom {
     uint32_t begin[3], n[3], E[3];
@@ -181,15 +187,20 @@ SZ_HD void line_pass_setup(const InterpArgs<T, QT> &A, uint32_t tile, uint32_t b
 // ---------------------------------------------------------------------------------------------------------------------
 // line items: the thread walks targets k0 <= k < k1 of one line along D
 // ---------------------------------------------------------------------------------------------------------------------
-template <class T, class QT, class Ctx, bool LAST>
-SZ_HD void line_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, const LinePass &P, T *sm, bool cubic,
-                      bool write2) {
+template <class T, class QT, class Ctx, bool LAST, bool WRITE2>
+SZ_HD void line_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, const LinePass &P, T *sm, bool cubic) {
     const uint32_t tid = ctx.tid(), nt = ctx.nthreads();
+    // pass constants -> registers (the table lives in shared memory)
     const uint32_t cu = P.cu, cv = P.cv, mgu = P.mgu, mgv = P.mgv, n = P.n, cD = P.cD, jmax = P.jmax;
     const uint32_t hS = P.hS, tS = P.tS, mD = P.mD, nseg = P.nseg, seglen = P.seglen;
     const uint32_t bnd0 = P.bnd[0], bnd1 = P.bnd[1], bb0 = P.bbase[0], bb1 = P.bbase[1], bb2 = P.bbase[2];
-    const uint32_t kfirst = P.kfirst;
-    const uint64_t base = P.base;
+    const uint32_t kfirst = P.kfirst, skipu = P.skipu, skipv = P.skipv;
+    const uint32_t gstep = static_cast<uint32_t>(2 * P.gD), hstep = static_cast<uint32_t>(2 * P.hD);
+    QT *const qb = A.q + P.base;
+    T *const ub = A.unpred_tmp + P.base;
+    const T *const gb = A.data + lg.gbase + P.gC + P.gD;
+    T *const hb = A.recon2 + lg.g2base + P.hC + P.hD;
+    const QuantParams qp = A.qp;
     const uint32_t nitems = nseg * cu * cv;
     for (uint32_t it = tid; it < nitems; it += nt) {
         const uint32_t t = fast_div(it, mgv);
@@ -198,21 +209,23 @@ SZ_HD void line_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, 
         const uint32_t iu = t - sg * cu;
         const uint32_t k0 = sg * seglen;
         const uint32_t k1 = sg + 1 == nseg ? cD : k0 + seglen;
-        const bool owned = iu >= P.skipu && iv >= P.skipv;
-        const uint32_t ru = iu - P.skipu, rv = iv - P.skipv;
+        const bool owned = iu >= skipu && iv >= skipv;
+        const uint32_t ru = iu - skipu, rv = iv - skipv;
         uint32_t pm = ru * P.mU + rv * P.mV + (k0 - kfirst) * mD;
         const uint32_t pb = ru * P.bU + rv * P.bV;
-        const T *gp = A.data + lg.gbase + iu * P.gU + iv * P.gV + P.gC + (2 * k0 + 1) * P.gD;
-        T *hp = A.recon2 + lg.g2base + iu * P.hU + iv * P.hV + P.hC + (2 * k0 + 1) * P.hD;
-        const uint64_t gstep = 2 * P.gD, hstep = 2 * P.hD;
+        uint32_t goff = iu * static_cast<uint32_t>(P.gU) + iv * static_cast<uint32_t>(P.gV) + k0 * gstep;
+        uint32_t hoff = iu * static_cast<uint32_t>(P.hU) + iv * static_cast<uint32_t>(P.hV) + k0 * hstep;
         T *nb = sm + (iu * P.sU + iv * P.sV + P.sC + k0 * hS);   // neighbour j = k (local index i-1)
         T w0 = 0, w1 = nb[0], w2 = 0, w3 = 0;
         if (k0 >= 1) w0 = nb[-static_cast<int>(hS)];
         if (k0 + 1 <= jmax) w2 = nb[hS];
         if (k0 + 2 <= jmax) w3 = nb[2 * hS];
         T prev_rec = 0;
+        T nxt = LAST ? gb[goff] : static_cast<T>(0);
         for (uint32_t k = k0; k < k1; k++) {
             const uint32_t i = 2 * k + 1;
+            const T orig = LAST ? nxt : nb[tS];
+            if (LAST && k + 1 < k1) nxt = gb[goff + gstep];
             T pred;
             bool in_main;
             if (cubic) {
@@ -237,13 +250,16 @@ SZ_HD void line_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, 
                     pred = n < 3 ? w1 : interp_linear1<T>(prev_rec, w1);
                 }
             }
-            const T orig = LAST ? *gp : nb[tS];
             T rec;
-            const int qv = quantize<T>(orig, pred, A.qp, rec);
+            const int qv = quantize<T>(orig, pred, qp, rec);
             if (!LAST) nb[tS] = rec;
             const uint32_t pos = in_main ? pm : pb + (i == bnd0 ? bb0 : (i == bnd1 ? bb1 : bb2));
-            emit(A, ctx, base + pos, qv, orig, owned);
-            if (write2 && owned) *hp = rec;
+            if (owned) {
+                qb[pos] = static_cast<QT>(qv);
+                if (qv == 0) store_unpred(ub, pos, orig);
+                if (WRITE2) hb[hoff] = rec;
+            }
+            ctx.hist_add(qv, owned);
             prev_rec = rec;
             pm += mD;
             w0 = w1;
@@ -251,27 +267,29 @@ SZ_HD void line_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, 
             w2 = w3;
             nb += hS;
             w3 = k + 3 <= jmax ? nb[2 * hS] : static_cast<T>(0);
-            gp += gstep;
-            hp += hstep;
+            goff += gstep;
+            hoff += hstep;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// row items (D == 2): 16 lanes on the targets of one row, the thread walks over rows
+// row items (D == 2): 16 lanes on the targets of one row, the thread walks over rows.
+// SIMPLE: n odd (no double-precision linear1 lane, no merged linear tail) and the rows a thread visits keep the same
+// iv (the stride over rows is a multiple of cv): everything advances by constants, no wrap test.
 // ---------------------------------------------------------------------------------------------------------------------
-template <class T, class QT, class Ctx, bool LAST>
-SZ_HD void row_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, const LinePass &P, T *sm, bool cubic,
-                     bool write2) {
+template <class T, class QT, class Ctx, bool LAST, bool WRITE2, bool SIMPLE>
+SZ_HD void row_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, const LinePass &P, T *sm, bool cubic) {
     const uint32_t tid = ctx.tid(), nt = ctx.nthreads();
     const uint32_t cu = P.cu, cv = P.cv, n = P.n, cD = P.cD;
-    const uint32_t hS = P.hS, tS = P.tS;
+    constexpr uint32_t hS = LAST ? 1u : 2u;   // D == 2: sst[D] == 1
+    constexpr uint32_t tS = LAST ? 0u : 1u;
     const uint32_t k = tid & 15u, slot = tid >> 4, nslots = nt >> 4;
     const uint32_t i = 2 * k + 1;
-    const bool merge_tail = !cubic && !(n & 1u) && n >= 4;   // linear mode: target n-1 is done by the lane of n-3
-    bool act = k < cD && !(merge_tail && k + 1 == cD);
-    // stencil of this lane as a 4-tap filter over (l-3, l-1, l+1, l+3); coefficients of unused taps are 0 and the
-    // taps themselves are not loaded (an infinite neighbour times 0 would poison the sum)
+    const bool merge_tail = !SIMPLE && !cubic && !(n & 1u) && n >= 4;   // linear: target n-1 is done by the lane of n-3
+    const bool act = k < cD && !(merge_tail && k + 1 == cD);
+    // stencil of this lane as a 4-tap filter over (l-3, l-1, l+1, l+3); unused taps have coefficient 0 and are not
+    // loaded (an infinite neighbour times 0 would poison the sum)
     T c0 = 0, c1 = 0, c2 = 0, c3 = 0, sc = 1;
     bool use_l1 = false, in_main = false;
     if (cubic) {
@@ -301,57 +319,113 @@ SZ_HD void row_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, c
             c1 = 1;   // n < 3 (n >= 4 is the merged tail)
         }
     }
+    if (SIMPLE) use_l1 = false;
     const bool ld0 = c0 != 0 || use_l1, ld2 = c2 != 0, ld3 = c3 != 0;
     const uint32_t bsel = i == P.bnd[0] ? P.bbase[0] : (i == P.bnd[1] ? P.bbase[1] : P.bbase[2]);
     const uint32_t posk = in_main ? (k - P.kfirst) * P.mD : bsel;
     const uint32_t pU = in_main ? P.mU : P.bU, pV = in_main ? P.mV : P.bV;
-    const uint64_t base = P.base;
+    const uint32_t skipu = P.skipu, skipv = P.skipv;
+    const uint32_t sU = P.sU, sV = P.sV;
+    const uint32_t gU = static_cast<uint32_t>(P.gU), gV = static_cast<uint32_t>(P.gV);
+    const uint32_t hU = static_cast<uint32_t>(P.hU), hV = static_cast<uint32_t>(P.hV);
+    const uint32_t gD2 = static_cast<uint32_t>(2 * P.gD), hD2 = static_cast<uint32_t>(2 * P.hD);
+    const uint32_t tail_pos = P.bbase[0], bU = P.bU, bV = P.bV;
+    QT *const qb = A.q + P.base;
+    T *const ub = A.unpred_tmp + P.base;
+    const T *const gb = A.data + lg.gbase + P.gC + static_cast<uint64_t>(i) * P.gD;
+    T *const hb = A.recon2 + lg.g2base + P.hC + static_cast<uint64_t>(i) * P.hD;
+    T *const sb = sm + P.sC + k * hS;
+    const QuantParams qp = A.qp;
     const uint32_t nrows = cu * cv;
     const uint32_t dU = cv ? nslots / cv : 0, dV = cv ? nslots % cv : 0;
     uint32_t iu = fast_div(slot, P.mgv), iv = slot - iu * cv;
-    const uint32_t soff_k = P.sC + k * hS;
-    const uint64_t goff_k = lg.gbase + P.gC + static_cast<uint64_t>(i) * P.gD;
-    const uint64_t hoff_k = lg.g2base + P.hC + static_cast<uint64_t>(i) * P.hD;
     const bool do_tail = merge_tail && k + 2 == cD;
-    for (uint32_t row = slot; row < nrows; row += nslots) {
-        int qv = 0;
-        uint64_t pos = 0;
-        T orig = 0;
-        bool owned = false;
-        if (act) {
-            const T *nb = sm + (iu * P.sU + iv * P.sV + soff_k);
+    if (!act) return;
+    if (SIMPLE) {
+        // dV == 0: the thread stays on one iv; every offset advances by a constant per visited row
+        if (slot >= nrows) return;
+        const uint32_t rows = (nrows - slot + nslots - 1) / nslots;
+        const bool v_owned = LAST || iv >= skipv;
+        // every address is a pointer advanced by a constant
+        T *nb = sb + (iu * sU + iv * sV);
+        const T *gp = gb + (iu * gU + iv * gV);
+        T *hp = hb + (iu * hU + iv * hV);
+        const uint32_t pos0 = (iu - skipu) * pU + (iv - skipv) * pV + posk;
+        QT *qp_ = qb + pos0;
+        T *up = ub + pos0;
+        const uint32_t so_inc = dU * sU, go_inc = dU * gU, ho_inc = dU * hU, pos_inc = dU * pU;
+        T nxt = LAST ? *gp : static_cast<T>(0);
+        for (uint32_t r = rows; r > 0; r--) {
+            const T orig = LAST ? nxt : nb[tS];
+            gp += go_inc;
+            if (LAST && r > 1) nxt = *gp;
             const T w1 = nb[0];
             const T w0 = ld0 ? nb[-static_cast<int>(hS)] : static_cast<T>(0);
             const T w2 = ld2 ? nb[hS] : static_cast<T>(0);
             const T w3 = ld3 ? nb[2 * hS] : static_cast<T>(0);
-            const T pred = use_l1 ? interp_linear1<T>(w0, w1) : (((c0 * w0 + c1 * w1) + c2 * w2) + c3 * w3) * sc;
-            const uint64_t goff = goff_k + iu * P.gU + iv * P.gV;
-            const uint64_t hoff = hoff_k + iu * P.hU + iv * P.hV;
-            orig = LAST ? A.data[goff] : nb[tS];
+            const T pred = (((c0 * w0 + c1 * w1) + c2 * w2) + c3 * w3) * sc;
             T rec;
-            qv = quantize<T>(orig, pred, A.qp, rec);
-            if (!LAST) const_cast<T *>(nb)[tS] = rec;
-            owned = iu >= P.skipu && iv >= P.skipv;
-            const uint32_t ru = iu - P.skipu, rv = iv - P.skipv;
-            pos = base + (ru * pU + rv * pV + posk);
-            if (write2 && owned) A.recon2[hoff] = rec;
-            if (do_tail) {
-                // flush this target, then the linear tail i+2 = n-1: linear1(recon(i), value(i+1))
-                emit(A, ctx, pos, qv, orig, owned);
-                const T pred2 = interp_linear1<T>(rec, w2);
-                orig = LAST ? A.data[goff + 2 * P.gD] : nb[tS + hS];
-                qv = quantize<T>(orig, pred2, A.qp, rec);
-                if (!LAST) const_cast<T *>(nb)[tS + hS] = rec;
-                pos = base + (ru * P.bU + rv * P.bV + P.bbase[0]);
-                if (write2 && owned) A.recon2[hoff + 2 * P.hD] = rec;
+            const int qv = quantize<T>(orig, pred, qp, rec);
+            if (!LAST) nb[tS] = rec;
+            const bool owned = LAST || (v_owned && iu >= skipu);
+            if (owned) {
+                *qp_ = static_cast<QT>(qv);
+                if (qv == 0) store_unpred(up, 0u, orig);
+                if (WRITE2) *hp = rec;
             }
+            ctx.hist_add(qv, owned);
+            nb += so_inc;
+            hp += ho_inc;
+            qp_ += pos_inc;
+            up += pos_inc;
+            iu += dU;
         }
-        emit(A, ctx, pos, qv, orig, act && owned);
+        return;
+    }
+    T nxt = LAST && slot < nrows ? gb[iu * gU + iv * gV] : static_cast<T>(0);
+    for (uint32_t row = slot; row < nrows; row += nslots) {
+        const uint32_t cu_ = iu, cv_ = iv;   // this row
         iv += dV;
         iu += dU;
         if (iv >= cv) {
             iv -= cv;
             iu++;
+        }
+        T *const nb = sb + (cu_ * sU + cv_ * sV);
+        T orig = LAST ? nxt : nb[tS];
+        if (LAST && row + nslots < nrows) nxt = gb[iu * gU + iv * gV];
+        const T w1 = nb[0];
+        const T w0 = ld0 ? nb[-static_cast<int>(hS)] : static_cast<T>(0);
+        const T w2 = ld2 ? nb[hS] : static_cast<T>(0);
+        const T w3 = ld3 ? nb[2 * hS] : static_cast<T>(0);
+        T pred = (((c0 * w0 + c1 * w1) + c2 * w2) + c3 * w3) * sc;
+        if (use_l1) pred = interp_linear1<T>(w0, w1);
+        T rec;
+        int qv = quantize<T>(orig, pred, qp, rec);
+        if (!LAST) nb[tS] = rec;
+        const bool owned = LAST || (cu_ >= skipu && cv_ >= skipv);
+        const uint32_t ru = cu_ - skipu, rv = cv_ - skipv;
+        uint32_t pos = ru * pU + rv * pV + posk;
+        const uint32_t hoff = cu_ * hU + cv_ * hV;
+        if (owned) {
+            qb[pos] = static_cast<QT>(qv);
+            if (qv == 0) store_unpred(ub, pos, orig);
+            if (WRITE2) hb[hoff] = rec;
+        }
+        ctx.hist_add(qv, owned);
+        if (do_tail) {
+            // the linear tail i+2 = n-1: linear1(recon(i), value(i+1))
+            const T pred2 = interp_linear1<T>(rec, w2);
+            orig = LAST ? gb[cu_ * gU + cv_ * gV + gD2] : nb[tS + hS];
+            qv = quantize<T>(orig, pred2, qp, rec);
+            if (!LAST) nb[tS + hS] = rec;
+            pos = ru * bU + rv * bV + tail_pos;
+            if (owned) {
+                qb[pos] = static_cast<QT>(qv);
+                if (qv == 0) store_unpred(ub, pos, orig);
+                if (WRITE2) hb[hoff + hD2] = rec;
+            }
+            ctx.hist_add(qv, owned);
         }
     }
 }
@@ -363,26 +437,55 @@ SZ_HD void row_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, c
 template <class T, class QT, class Ctx>
 SZ_HD void line_fill(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, T *sm) {
     const uint32_t tid = ctx.tid(), nt = ctx.nthreads();
-    const uint32_t E1 = lg.E[1], E2 = lg.E[2];
-    const uint32_t total = lg.E[0] * E1 * E2;
-    const uint32_t mg1 = magic_u32_fast(E1), mg2 = magic_u32_fast(E2);
     const uint32_t s = A.s;
     const uint32_t m0 = lg.last == 0 ? 2u : 1u, m1 = lg.last == 1 ? 2u : 1u, m2 = lg.last == 2 ? 2u : 1u;
-    const uint64_t g0 = m0 * s * A.sh.stride[0], g1 = m1 * s * A.sh.stride[1], g2 = static_cast<uint64_t>(m2) * s;
-    // recon2 offset of local index l (even): (begin + l*s)/2 = begin/2 + (l/2)*s
-    const uint64_t h0 = s * A.stride2[0], h1 = s * A.stride2[1], h2 = s;
-    const T *dat = A.data + lg.gbase;
-    const T *rc2 = A.recon2 + lg.g2base;
-    for (uint32_t it = tid; it < total; it += nt) {
-        const uint32_t r = fast_div(it, mg2);
-        const uint32_t e2 = it - r * E2;
-        const uint32_t e0 = fast_div(r, mg1);
-        const uint32_t e1 = r - e0 * E1;
-        const uint32_t l0 = e0 * m0, l1 = e1 * m1, l2 = e2 * m2;
-        const bool coarse = !((l0 | l1 | l2) & 1u);
-        const T *src = coarse ? rc2 + ((l0 >> 1) * h0 + (l1 >> 1) * h1 + (l2 >> 1) * h2)
-                              : dat + (e0 * g0 + e1 * g1 + e2 * g2);
-        sm[it] = *src;
+    {   // (1) every element of the sub-lattice from the input
+        const uint32_t E1 = lg.E[1], E2 = lg.E[2];
+        const uint32_t total = lg.E[0] * E1 * E2;
+        const uint32_t mg1 = magic_u32_fast(E1), mg2 = magic_u32_fast(E2);
+        const uint32_t g0 = m0 * s * static_cast<uint32_t>(A.sh.stride[0]), g1 = m1 * s * static_cast<uint32_t>(A.sh.stride[1]),
+                       g2 = m2 * s;
+        const T *dat = A.data + lg.gbase;
+        for (uint32_t it = tid; it < total; it += nt) {
+            const uint32_t r = fast_div(it, mg2);
+            const uint32_t e2 = it - r * E2;
+            const uint32_t e0 = fast_div(r, mg1);
+            const uint32_t e1 = r - e0 * E1;
+            sm[it] = dat[e0 * g0 + e1 * g1 + e2 * g2];
+        }
+    }
+    ctx.sync();
+    {   // (2) coarse points (all local indices even) are overwritten with their reconstruction from recon2:
+        //     local index 2c of dim d sits at smem coordinate 2c (d != last) or c (d == last) and at recon2 offset
+        //     (begin + 2c*s)/2 = begin/2 + c*s
+        const uint32_t C0 = (lg.n[0] + 1) / 2, C1 = (lg.n[1] + 1) / 2, C2 = (lg.n[2] + 1) / 2;
+        const uint32_t total = C0 * C1 * C2;
+        const uint32_t mg1 = magic_u32_fast(C1), mg2 = magic_u32_fast(C2);
+        const uint32_t h0 = s * static_cast<uint32_t>(A.stride2[0]), h1 = s * static_cast<uint32_t>(A.stride2[1]), h2 = s;
+        const uint32_t t2 = 2u / m2, t1 = (2u / m1) * lg.E[2], t0 = (2u / m0) * lg.E[2] * lg.E[1];
+        const T *rc2 = A.recon2 + lg.g2base;
+        for (uint32_t it = tid; it < total; it += nt) {
+            const uint32_t r = fast_div(it, mg2);
+            const uint32_t c2 = it - r * C2;
+            const uint32_t c0 = fast_div(r, mg1);
+            const uint32_t c1 = r - c0 * C1;
+            sm[c0 * t0 + c1 * t1 + c2 * t2] = rc2[c0 * h0 + c1 * h1 + c2 * h2];
+        }
+    }
+}
+
+template <class T, class QT, class Ctx, bool LAST, bool WRITE2>
+SZ_HD void line_pass_run(const InterpArgs<T, QT> &A, Ctx &ctx, T *sm, const LineGeom &lg, const LinePass &P,
+                         bool cubic) {
+    if (P.kind == 0) {
+        line_items<T, QT, Ctx, LAST, WRITE2>(A, ctx, lg, P, sm, cubic);
+    } else {
+        const uint32_t nslots = ctx.nthreads() >> 4;
+        const bool simple = (P.n & 1u) && P.cv != 0 && nslots % P.cv == 0;
+        if (simple)
+            row_items<T, QT, Ctx, LAST, WRITE2, true>(A, ctx, lg, P, sm, cubic);
+        else
+            row_items<T, QT, Ctx, LAST, WRITE2, false>(A, ctx, lg, P, sm, cubic);
     }
 }
 
@@ -393,16 +496,16 @@ SZ_HD void line_tile_passes(const InterpArgs<T, QT> &A, Ctx &ctx, T *sm, const L
     for (int p = 0; p < 3; p++) {
         const LinePass &P = lt.ps[p];
         if (P.cu != 0 && P.cv != 0 && P.cD != 0) {
-            if (P.kind == 0) {
-                if (p < 2)
-                    line_items<T, QT, Ctx, false>(A, ctx, lg, P, sm, cubic, write2);
+            if (p < 2) {
+                if (write2)
+                    line_pass_run<T, QT, Ctx, false, true>(A, ctx, sm, lg, P, cubic);
                 else
-                    line_items<T, QT, Ctx, true>(A, ctx, lg, P, sm, cubic, write2);
+                    line_pass_run<T, QT, Ctx, false, false>(A, ctx, sm, lg, P, cubic);
             } else {
-                if (p < 2)
-                    row_items<T, QT, Ctx, false>(A, ctx, lg, P, sm, cubic, write2);
+                if (write2)
+                    line_pass_run<T, QT, Ctx, true, true>(A, ctx, sm, lg, P, cubic);
                 else
-                    row_items<T, QT, Ctx, true>(A, ctx, lg, P, sm, cubic, write2);
+                    line_pass_run<T, QT, Ctx, true, false>(A, ctx, sm, lg, P, cubic);
             }
         }
         ctx.pass_end();

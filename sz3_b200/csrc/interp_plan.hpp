@@ -122,6 +122,11 @@ inline const char *build_interp_plan(const sz3b_config &c, double eb, int schedu
     pl.num2 = acc;
     pl.tile = (N == 3) && schedule != 1;
     pl.variant = schedule == 2 ? 0 : (schedule == 3 ? 1 : 2);
+    // the line walker keeps tile-relative element offsets in 32 bits
+    if (pl.variant == 2 && pl.num >= (1ull << 32)) {
+        if (schedule == 4) return "line-walker schedule needs fewer than 2^32 elements";
+        pl.variant = 1;
+    }
     if (schedule >= 2 && schedule <= 4 && N != 3) return "tile schedule needs N == 3";
     if (schedule < 0 || schedule > 4) return "unknown schedule";
 

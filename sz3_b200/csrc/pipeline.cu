@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -263,9 +264,30 @@ static void encode_indices(Workspace &ws, const QT *d_q, uint64_t n, const unsig
 
 // D2H of the packed bits / unpredictables into an assembled (pinned) buffer laid out as SZGenericCompressor does:
 //   decomposition.save | encoder.save | size_t n | size_t outSize | bits          (SZGenericCompressor.hpp:51-56)
+// The bits stream in as pieces of kD2HPiece bytes, each followed by an event, so that the host zstd workers start on
+// the first chunks while the rest is still crossing PCIe (ArrivalGate).
+constexpr size_t kD2HPiece = static_cast<size_t>(4) << 20;
+
+struct ArrivalGate : ZstdReady {
+    std::vector<size_t> upto;          // buffer bytes [0, upto[j]) are valid once ev[j] has completed
+    std::vector<cudaEvent_t> ev;
+    std::atomic<size_t> done{0};       // pieces known to have arrived
+    void wait(size_t need) override {
+        size_t j = done.load(std::memory_order_acquire);
+        while (j < upto.size() && (j == 0 ? 0 : upto[j - 1]) < need) {
+            cudaEventSynchronize(ev[j]);
+            j++;
+        }
+        size_t cur = done.load(std::memory_order_relaxed);
+        while (cur < j && !done.compare_exchange_weak(cur, j, std::memory_order_release)) {
+        }
+    }
+};
+
 template <class T>
 static size_t assemble_stream(Workspace &ws, const uint8_t *decomp_hdr, size_t decomp_hdr_len, const EncodeLayout &lay,
-                              const HuffmanBook &book, uint64_t n, PinBuf &dstbuf, uint8_t **dst_out) {
+                              const HuffmanBook &book, uint64_t n, PinBuf &dstbuf, uint8_t **dst_out,
+                              ArrivalGate &gate) {
     const size_t total = decomp_hdr_len + lay.n_unpred * sizeof(T) + lay.tree_len + 16 + lay.out_size;
     uint8_t *dst = static_cast<uint8_t *>(dstbuf.ensure(total + 16));
     uint8_t *p = dst;
@@ -279,20 +301,39 @@ static size_t assemble_stream(Workspace &ws, const uint8_t *decomp_hdr, size_t d
     p += lay.tree_len;
     put<uint64_t>(p, n);
     put<uint64_t>(p, lay.out_size);
-    if (lay.out_size) ws.d2h(p, ws.out_words.p, lay.out_size);
-    p += lay.out_size;
+    const size_t bits_off = static_cast<size_t>(p - dst);
+    const uint8_t *d_bits = static_cast<const uint8_t *>(ws.out_words.p);
+    size_t off = 0;
+    while (off < lay.out_size) {
+        // pieces end on multiples of kD2HPiece of the assembled buffer
+        size_t end_abs = ((bits_off + off) / kD2HPiece + 1) * kD2HPiece;
+        size_t len = std::min(lay.out_size - off, end_abs - (bits_off + off));
+        ws.d2h(p + off, d_bits + off, len);
+        off += len;
+        cudaEvent_t e = ws.event();
+        SZ3B_CUDA(cudaEventRecord(e, ws.st));
+        gate.ev.push_back(e);
+        gate.upto.push_back(bits_off + off);
+    }
+    if (gate.ev.empty() || gate.upto.back() < total) {
+        cudaEvent_t e = ws.event();
+        SZ3B_CUDA(cudaEventRecord(e, ws.st));
+        gate.ev.push_back(e);
+        gate.upto.push_back(total);
+    }
     ws.stage_end(h, 0);
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
     *dst_out = dst;
     return total;
 }
 
 struct TooSmall {};   // stands in for std::length_error(SZ3_ERROR_COMP_BUFFER_NOT_LARGE_ENOUGH)
 
-static size_t zstd_stage(Workspace &ws, const uint8_t *src, size_t len, uint8_t *dst, size_t cap, int threads) {
+static size_t zstd_stage(Workspace &ws, const uint8_t *src, size_t len, uint8_t *dst, size_t cap, int threads,
+                         ZstdReady *gate) {
     double t0 = now_ms();
     bool small = false;
-    size_t r = zstd_compress_framed(src, len, dst, cap, threads, &small);
+    size_t r = zstd_compress_framed(src, len, dst, cap, threads, &small, gate, &ws.zscratch);
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
     ws.host_stage("zstd_host", now_ms() - t0);
     if (small) throw TooSmall{};
     if (r == 0) fail(SZ3B_E_RUNTIME, "zstd compression failed");
@@ -329,8 +370,9 @@ static size_t interp_compress_t(Workspace &ws, const sz3b_config &conf, const T 
     uint8_t hdr[128];
     size_t hdr_len = interp_save_header<T>(pl, radius, lay.n_unpred, hdr);
     uint8_t *buf = nullptr;
-    size_t len = assemble_stream<T>(ws, hdr, hdr_len, lay, book, n, tuner ? ws.stage2 : ws.stage, &buf);
-    return zstd_stage(ws, buf, len, dst, cap, zstd_threads);
+    ArrivalGate gate;
+    size_t len = assemble_stream<T>(ws, hdr, hdr_len, lay, book, n, tuner ? ws.stage2 : ws.stage, &buf, gate);
+    return zstd_stage(ws, buf, len, dst, cap, zstd_threads, &gate);
 }
 
 template <class T>
@@ -527,7 +569,7 @@ static size_t lossless_compress(Workspace &ws, const sz3b_config &conf, const T 
         src = h;
     }
     try {
-        return zstd_stage(ws, src, bytes, dst, cap, host_threads());
+        return zstd_stage(ws, src, bytes, dst, cap, host_threads(), nullptr);
     } catch (TooSmall &) {
         fail(SZ3B_E_RUNTIME, "compressed buffer not large enough");   // std::length_error escapes in the reference
     }

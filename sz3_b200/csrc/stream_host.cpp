@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 namespace sz3b {
@@ -123,8 +125,125 @@ bool config_load(sz3b_config &c, const uint8_t *in, size_t len) {
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// persistent worker pool
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct HostPool {
+    std::mutex run_mu;            // one parallel region at a time (concurrent callers queue up here)
+    std::mutex mu;
+    std::condition_variable cv_start, cv_done;
+    std::vector<std::thread> threads;
+    uint64_t generation = 0;
+    int active = 0;               // workers (beyond the caller) taking part in the current region
+    int pending = 0;
+    void (*fn)(void *, int) = nullptr;
+    void *arg = nullptr;
+    bool stop = false;
+
+    void worker_main(int idx) {
+        uint64_t seen = 0;
+        for (;;) {
+            void (*f)(void *, int);
+            void *a;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_start.wait(lk, [&] { return stop || (generation != seen && idx <= active); });
+                if (stop) return;
+                seen = generation;
+                f = fn;
+                a = arg;
+            }
+            f(a, idx);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    void run(int nworkers, void (*f)(void *, int), void *a) {
+        std::lock_guard<std::mutex> rl(run_mu);
+        if (nworkers < 1) nworkers = 1;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            while (static_cast<int>(threads.size()) < nworkers - 1) {
+                int idx = static_cast<int>(threads.size()) + 1;
+                threads.emplace_back([this, idx] { worker_main(idx); });
+            }
+            fn = f;
+            arg = a;
+            active = nworkers - 1;
+            pending = nworkers - 1;
+            generation++;
+        }
+        cv_start.notify_all();
+        f(a, 0);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        active = 0;
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_start.notify_all();
+        for (auto &t : threads) t.join();
+    }
+};
+HostPool &pool() {
+    static HostPool *p = new HostPool();   // intentionally leaked: worker threads must not be joined at exit
+    return *p;
+}
+}  // namespace
+
+void host_parallel(int nworkers, void (*fn)(void *arg, int worker), void *arg) { pool().run(nworkers, fn, arg); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct ZJob {
+    const uint8_t *src;
+    size_t src_len, chunk, nchunks, slot;
+    uint8_t *scratch;
+    uint8_t *dst;
+    std::vector<size_t> sizes, offs;
+    std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
+    ZstdReady *ready;
+    int phase = 0;
+};
+thread_local ZSTD_CCtx *t_cctx = nullptr;
+
+void zjob_worker(void *arg, int) {
+    ZJob &j = *static_cast<ZJob *>(arg);
+    if (j.phase == 0) {
+        if (!t_cctx) t_cctx = ZSTD_createCCtx();
+        for (;;) {
+            size_t k = j.next.fetch_add(1);
+            if (k >= j.nchunks) break;
+            size_t off = k * j.chunk;
+            size_t len = std::min(j.chunk, j.src_len - off);
+            if (j.ready) j.ready->wait(off + len);
+            size_t r = t_cctx ? ZSTD_compressCCtx(t_cctx, j.scratch + k * j.slot, j.slot, j.src + off, len, 3)
+                              : ZSTD_compress(j.scratch + k * j.slot, j.slot, j.src + off, len, 3);
+            if (ZSTD_isError(r)) {
+                j.failed = true;
+                break;
+            }
+            j.sizes[k] = r;
+        }
+    } else {
+        for (;;) {
+            size_t k = j.next.fetch_add(1);
+            if (k >= j.nchunks) break;
+            memcpy(j.dst + j.offs[k], j.scratch + k * j.slot, j.sizes[k]);
+        }
+    }
+}
+}  // namespace
+
 size_t zstd_compress_framed(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, int threads,
-                            bool *too_small) {
+                            bool *too_small, ZstdReady *ready, std::vector<uint8_t> *scratch) {
     *too_small = false;
     if (dst_cap < sizeof(uint64_t) || dst_cap - sizeof(uint64_t) < ZSTD_compressBound(src_len)) {
         *too_small = true;
@@ -132,54 +251,43 @@ size_t zstd_compress_framed(const uint8_t *src, size_t src_len, uint8_t *dst, si
     }
     uint8_t *p = dst;
     put<uint64_t>(p, static_cast<uint64_t>(src_len));
-    const size_t kMinChunk = static_cast<size_t>(4) << 20;
-    size_t nchunks = 1;
-    if (threads > 1 && src_len >= 2 * kMinChunk) {
-        nchunks = std::min<size_t>(static_cast<size_t>(threads) * 2, src_len / kMinChunk);
-        if (nchunks < 1) nchunks = 1;
-    }
-    if (nchunks == 1) {
+    const size_t kChunk = static_cast<size_t>(1) << 20;
+    if (threads <= 1 || src_len < 2 * kChunk) {
+        if (ready) ready->wait(src_len);
         size_t r = ZSTD_compress(p, dst_cap - 8, src, src_len, 3);
         if (ZSTD_isError(r)) return 0;
         return r + 8;
     }
-    const size_t chunk = (src_len + nchunks - 1) / nchunks;
-    std::vector<std::vector<uint8_t>> bufs(nchunks);
-    std::vector<size_t> sizes(nchunks, 0);
-    std::atomic<size_t> next{0};
-    std::atomic<bool> failed{false};
-    auto worker = [&]() {
-        for (;;) {
-            size_t k = next.fetch_add(1);
-            if (k >= nchunks) break;
-            size_t off = k * chunk;
-            size_t len = std::min(chunk, src_len - off);
-            bufs[k].resize(ZSTD_compressBound(len));
-            size_t r = ZSTD_compress(bufs[k].data(), bufs[k].size(), src + off, len, 3);
-            if (ZSTD_isError(r)) {
-                failed = true;
-                break;
-            }
-            sizes[k] = r;
-        }
-    };
-    int nt = static_cast<int>(std::min<size_t>(threads, nchunks));
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nt; t++) pool.emplace_back(worker);
-    worker();
-    for (auto &t : pool) t.join();
-    if (failed) return 0;
+    ZJob j;
+    j.src = src;
+    j.src_len = src_len;
+    j.chunk = kChunk;
+    j.nchunks = (src_len + kChunk - 1) / kChunk;
+    j.slot = ZSTD_compressBound(kChunk);
+    std::vector<uint8_t> local;
+    std::vector<uint8_t> &sc = scratch ? *scratch : local;
+    if (sc.size() < j.nchunks * j.slot) sc.resize(j.nchunks * j.slot);
+    j.scratch = sc.data();
+    j.dst = p;
+    j.sizes.assign(j.nchunks, 0);
+    j.offs.assign(j.nchunks, 0);
+    j.ready = ready;
+    const int nt = static_cast<int>(std::min<size_t>(threads, j.nchunks));
+    host_parallel(nt, zjob_worker, &j);
+    if (j.failed) return 0;
     size_t total = 0;
-    for (size_t k = 0; k < nchunks; k++) total += sizes[k];
+    for (size_t k = 0; k < j.nchunks; k++) {
+        j.offs[k] = total;
+        total += j.sizes[k];
+    }
     if (total > dst_cap - 8) {
         *too_small = true;
         return 0;
     }
-    for (size_t k = 0; k < nchunks; k++) {
-        memcpy(p, bufs[k].data(), sizes[k]);
-        p += sizes[k];
-    }
-    return static_cast<size_t>(p - dst);
+    j.phase = 1;
+    j.next = 0;
+    host_parallel(nt, zjob_worker, &j);
+    return total + 8;
 }
 
 bool zstd_decompress_framed(const uint8_t *src, size_t src_len, std::vector<uint8_t> &out) {

@@ -43,8 +43,18 @@ bool config_load(sz3b_config &c, const uint8_t *in, size_t len);
 // Returns the bytes written, or 0 with *too_small = true when dstCap - 8 < ZSTD_compressBound(srcLen) (the reference
 // throws std::length_error there).  With threads > 1 the source is cut into chunks compressed concurrently and the
 // frames are concatenated; ZSTD_decompress (what the reference decoder calls) accepts concatenated frames.
+// `ready`, if given, is called by a worker before it touches src[0, upto): it blocks until those bytes have arrived
+// (the packed stream is still streaming in from the GPU while the first chunks are already being compressed).
+// `scratch` holds the per-chunk frames before they are concatenated; it only grows, so callers keep it across calls.
+struct ZstdReady {
+    virtual void wait(size_t upto) = 0;
+    virtual ~ZstdReady() {}
+};
 size_t zstd_compress_framed(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, int threads,
-                            bool *too_small);
+                            bool *too_small, ZstdReady *ready = nullptr, std::vector<uint8_t> *scratch = nullptr);
+
+// Persistent host worker threads of the host tail (zstd chunks, frame concatenation).
+void host_parallel(int nworkers, void (*fn)(void *arg, int worker), void *arg);
 // Lossless_zstd::decompress (:39-45).  Returns false on a zstd error.
 bool zstd_decompress_framed(const uint8_t *src, size_t src_len, std::vector<uint8_t> &out);
 bool zstd_decompress_into(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *dst_len);

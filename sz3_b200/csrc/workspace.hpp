@@ -93,6 +93,7 @@ struct Workspace {
     DevBuf coef, coef_q, side_q, misc;
     // pinned staging
     PinBuf stage, stage2, hist_host;
+    std::vector<uint8_t> zscratch;   // per-chunk zstd frames before concatenation (host tail)
     // profiling
     std::vector<StageRecord> prof;
     std::vector<cudaEvent_t> ev_pool;

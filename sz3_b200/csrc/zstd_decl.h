@@ -13,6 +13,11 @@ size_t ZSTD_compressBound(size_t srcSize);
 size_t ZSTD_compress(void *dst, size_t dstCapacity, const void *src, size_t srcSize, int compressionLevel);
 size_t ZSTD_decompress(void *dst, size_t dstCapacity, const void *src, size_t compressedSize);
 unsigned ZSTD_isError(size_t code);
+typedef struct ZSTD_CCtx_s ZSTD_CCtx;
+ZSTD_CCtx *ZSTD_createCCtx(void);
+size_t ZSTD_freeCCtx(ZSTD_CCtx *cctx);
+size_t ZSTD_compressCCtx(ZSTD_CCtx *cctx, void *dst, size_t dstCapacity, const void *src, size_t srcSize,
+                         int compressionLevel);
 const char *ZSTD_getErrorName(size_t code);
 unsigned ZSTD_versionNumber(void);
 #ifdef __cplusplus
