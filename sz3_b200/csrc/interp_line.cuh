@@ -350,7 +350,8 @@ SZ_HD void row_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, c
         T *nb = sb + (iu * sU + iv * sV);
         const T *gp = gb + (iu * gU + iv * gV);
         T *hp = hb + (iu * hU + iv * hV);
-        const uint32_t pos0 = (iu - skipu) * pU + (iv - skipv) * pV + posk;
+        // signed: rows on a low face this tile does not own start "before" the pass (never stored)
+        const int32_t pos0 = static_cast<int32_t>((iu - skipu) * pU + (iv - skipv) * pV + posk);
         QT *qp_ = qb + pos0;
         T *up = ub + pos0;
         const uint32_t so_inc = dU * sU, go_inc = dU * gU, ho_inc = dU * hU, pos_inc = dU * pU;

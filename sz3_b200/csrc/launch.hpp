@@ -36,6 +36,19 @@ void launch_pack(const QT *q, uint64_t n, int sym_min, int zero_sym, const uint8
                  unsigned long long *bit_off, unsigned long long *zero_off, unsigned *out_words, const T *unpred_tmp,
                  T *unpred_out, cudaStream_t st, cudaEvent_t after_scan);
 
+// blockwise.cu
+struct BlockShape;
+struct QuantParams;
+template <class T>
+void launch_reg_fit(const T *data, const BlockShape &bs, T *c_fit, uint8_t *valid, cudaStream_t st);
+template <class T>
+void launch_reg_chain(const T *c_fit, const uint8_t *sel, uint64_t nblocks, int N, const QuantParams &q_liner,
+                      const QuantParams &q_indep, int32_t *coef_q, T *c_rec, unsigned long long *counters,
+                      unsigned long long *unpred_pos, T *unpred_val, cudaStream_t st);
+template <class T, class QT>
+void launch_reg_predict(const T *data, const BlockShape &bs, const T *c_rec, const QuantParams &qp, QT *q, T *unpred_tmp,
+                        unsigned long long *hist, cudaStream_t st);
+
 // misc_kernels.cu
 template <class T>
 void launch_minmax(const T *data, uint64_t n, T *mm /* device: [min, max] */, cudaStream_t st);

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <vector>
 
+#include "blockwise.cuh"
 #include "huffman_host.hpp"
 #include "interp_body.cuh"
 #include "interp_plan.hpp"
@@ -555,6 +556,182 @@ void tune_stage(Workspace &ws, sz3b_config &conf, const T *data, int loc) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// BlockwiseDecomposition on the device (SZAlgoLorenzoReg.hpp:22-64, BlockwiseDecomposition.hpp:28-46,69-73).
+// Built so far: the single-predictor RegressionPredictor stack (config "Lorenzo=No, Regression=Yes").
+// ---------------------------------------------------------------------------------------------------------------------
+void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vector<uint8_t> &out, size_t *tree_len);
+
+// LinearQuantizer::save (LinearQuantizer.hpp:95-104)
+template <class T>
+static void quantizer_save(std::vector<uint8_t> &out, double eb, int radius, const std::vector<T> &unpred) {
+    uint8_t tmp[32];
+    uint8_t *p = tmp;
+    put<uint8_t>(p, 2);
+    put<double>(p, eb);
+    put<int32_t>(p, radius);
+    put<uint64_t>(p, unpred.size());
+    out.insert(out.end(), tmp, p);
+    const uint8_t *v = reinterpret_cast<const uint8_t *>(unpred.data());
+    out.insert(out.end(), v, v + unpred.size() * sizeof(T));
+}
+
+template <class T, class QT>
+static void run_blockwise(Workspace &ws, const sz3b_config &conf, double eb, const T *d_data, QT *d_q, T *d_unpred_tmp,
+                          unsigned long long *d_hist, int nbins, std::vector<uint8_t> &pred_blob, int *launches) {
+    const int N = conf.N;
+    const int method_cnt = (conf.lorenzo != 0) + (conf.lorenzo2 != 0) + (conf.regression != 0);
+    if (method_cnt == 0) fail(SZ3B_E_INVALID_ARGUMENT, "All lorenzo and regression methods are disabled.");
+    if (conf.lorenzo || conf.lorenzo2)
+        fail(SZ3B_E_UNSUPPORTED,
+             "ALGO_LORENZO_REG with a Lorenzo predictor is not on the GPU path yet (regression-only is; DESIGN.md)");
+    if (conf.blockSize < 1) fail(SZ3B_E_INVALID_ARGUMENT, "blockSize must be positive");
+    BlockShape bs;
+    block_shape_init(bs, N, conf.dims, static_cast<uint32_t>(conf.blockSize));
+    for (int d = 0; d < N; d++)
+        if (bs.dims[d] % bs.B == 1)
+            fail(SZ3B_E_UNSUPPORTED,
+                 "regression-only with a block of extent 1: the reference falls back to an unpadded Lorenzo predictor "
+                 "that reads outside the array; not reproduced");
+    const int nc = N + 1;
+    const int kCoefRadius = 32768;   // LinearQuantizer default (LinearQuantizer.hpp:21)
+    const double eb_indep = eb / nc;
+    const double eb_liner = eb / nc / static_cast<unsigned>(conf.blockSize);
+    T *c_fit = ws.coef.as<T>(bs.nblocks * nc);
+    T *c_rec = ws.coef2.as<T>(bs.nblocks * nc);
+    uint8_t *valid = ws.flags.as<uint8_t>(bs.nblocks);
+    int32_t *coef_q = ws.coef_q.as<int32_t>(bs.nblocks * nc);
+    unsigned long long *counters = ws.counters.as<unsigned long long>(2);
+    unsigned long long *upos = ws.cpos.as<unsigned long long>(bs.nblocks * nc);
+    T *uval = ws.cval.as<T>(bs.nblocks * nc);
+    size_t h = ws.stage_begin("regression_fit");
+    launch_reg_fit<T>(d_data, bs, c_fit, valid, ws.st);
+    ws.stage_end(h, 1);
+    h = ws.stage_begin("regression_coef_chain");
+    SZ3B_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ws.st));
+    launch_reg_chain<T>(c_fit, valid, bs.nblocks, N, make_quant(eb_liner, kCoefRadius), make_quant(eb_indep, kCoefRadius),
+                        coef_q, c_rec, counters, upos, uval, ws.st);
+    ws.stage_end(h, 1);
+    unsigned long long hc[2];
+    ws.d2h(hc, counters, sizeof(hc));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(cudaGetLastError());
+    *launches += 2;
+    const uint64_t n_coef = hc[0] * nc;
+    // unpredictable coefficients, back in chain order, split by quantizer
+    std::vector<T> un_liner, un_indep;
+    if (hc[1]) {
+        std::vector<unsigned long long> pos(hc[1]);
+        std::vector<T> val(hc[1]);
+        ws.d2h(pos.data(), upos, hc[1] * sizeof(unsigned long long));
+        ws.d2h(val.data(), uval, hc[1] * sizeof(T));
+        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        std::vector<size_t> order(hc[1]);
+        for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pos[a] < pos[b]; });
+        for (size_t i : order) (pos[i] % nc == static_cast<unsigned>(N) ? un_indep : un_liner).push_back(val[i]);
+    }
+    // RegressionPredictor::save (RegressionPredictor.hpp:94-107)
+    pred_blob.clear();
+    {
+        uint8_t tmp[8];
+        uint8_t *p = tmp;
+        put<uint64_t>(p, n_coef);
+        pred_blob.insert(pred_blob.end(), tmp, p);
+    }
+    if (n_coef) {
+        quantizer_save<T>(pred_blob, eb_indep, kCoefRadius, un_indep);
+        quantizer_save<T>(pred_blob, eb_liner, kCoefRadius, un_liner);
+        std::vector<uint8_t> side;
+        huffman_encode_device(ws, coef_q, n_coef, side, nullptr);
+        pred_blob.insert(pred_blob.end(), side.begin(), side.end());
+    }
+    h = ws.stage_begin("predict_quantize");
+    SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
+    launch_reg_predict<T, QT>(d_data, bs, c_rec, make_quant(eb, conf.quantbinCnt / 2), d_q, d_unpred_tmp, d_hist, ws.st);
+    ws.stage_end(h, 1);
+    SZ3B_CUDA(cudaGetLastError());
+    *launches += 1;
+}
+
+template <class T>
+static size_t quantizer_header(double eb, int radius, uint64_t n_unpred, uint8_t *out) {
+    uint8_t *p = out;
+    put<uint8_t>(p, 2);
+    put<double>(p, eb);
+    put<int32_t>(p, radius);
+    put<uint64_t>(p, n_unpred);
+    return static_cast<size_t>(p - out);
+}
+
+template <class T, class QT>
+static size_t blockwise_compress_t(Workspace &ws, const sz3b_config &conf, const T *d_data, uint8_t *dst, size_t cap,
+                                   int zstd_threads) {
+    const int radius = conf.quantbinCnt / 2;
+    const int nbins = 2 * radius;
+    const uint64_t n = config_num(conf);
+    QT *d_q = ws.q.as<QT>(n);
+    T *d_unpred_tmp = ws.unpred_tmp.as<T>(n);
+    unsigned long long *d_hist = ws.hist2.as<unsigned long long>(nbins);
+    std::vector<uint8_t> hdr;
+    int launches = 0;
+    run_blockwise<T, QT>(ws, conf, conf.absErrorBound, d_data, d_q, d_unpred_tmp, d_hist, nbins, hdr, &launches);
+    HuffmanBook book;
+    EncodeLayout lay;
+    encode_indices<QT, T>(ws, d_q, n, d_hist, nbins, 0, true, d_unpred_tmp, book, lay);
+    uint8_t qh[32];
+    size_t qh_len = quantizer_header<T>(conf.absErrorBound, radius, lay.n_unpred, qh);
+    hdr.insert(hdr.end(), qh, qh + qh_len);
+    uint8_t *buf = nullptr;
+    ArrivalGate gate;
+    size_t len = assemble_stream<T>(ws, hdr.data(), hdr.size(), lay, book, n, ws.stage, &buf, gate);
+    return zstd_stage(ws, buf, len, dst, cap, zstd_threads, &gate);
+}
+
+template <class T>
+static size_t blockwise_compress(Workspace &ws, const sz3b_config &conf, const T *d_data, uint8_t *dst, size_t cap,
+                                 int zstd_threads) {
+    if (conf.quantbinCnt < 2) fail(SZ3B_E_INVALID_ARGUMENT, "quantbinCnt must be >= 2");
+    if (conf.quantbinCnt / 2 <= 32768) return blockwise_compress_t<T, uint16_t>(ws, conf, d_data, dst, cap, zstd_threads);
+    return blockwise_compress_t<T, uint32_t>(ws, conf, d_data, dst, cap, zstd_threads);
+}
+
+template <class T, class QT>
+static void blockwise_decompose_t(Workspace &ws, const sz3b_config &conf, double eb, const T *d_data,
+                                  int32_t *quant_out, std::vector<uint8_t> &blob) {
+    const int radius = conf.quantbinCnt / 2;
+    const int nbins = 2 * radius;
+    const uint64_t n = config_num(conf);
+    QT *d_q = ws.q.as<QT>(n);
+    T *d_unpred_tmp = ws.unpred_tmp.as<T>(n);
+    unsigned long long *d_hist = ws.hist2.as<unsigned long long>(nbins);
+    int launches = 0;
+    run_blockwise<T, QT>(ws, conf, eb, d_data, d_q, d_unpred_tmp, d_hist, nbins, blob, &launches);
+    int32_t *d_wide = ws.side_q.as<int32_t>(n);
+    launch_widen<QT>(d_q, n, d_wide, ws.st);
+    ws.d2h(quant_out, d_wide, n * sizeof(int32_t));
+    HuffmanBook book;
+    EncodeLayout lay;
+    encode_indices<QT, T>(ws, d_q, n, d_hist, nbins, 0, true, d_unpred_tmp, book, lay);
+    uint8_t qh[32];
+    size_t qh_len = quantizer_header<T>(eb, radius, lay.n_unpred, qh);
+    blob.insert(blob.end(), qh, qh + qh_len);
+    const size_t at = blob.size();
+    blob.resize(at + lay.n_unpred * sizeof(T));
+    if (lay.n_unpred) ws.d2h(blob.data() + at, ws.unpred_out.p, lay.n_unpred * sizeof(T));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+}
+
+template <class T>
+void blockwise_decompose_stage(Workspace &ws, const sz3b_config &conf, double eb, const T *data, int loc,
+                               int32_t *quant_out, std::vector<uint8_t> &blob) {
+    const T *d = to_device(ws, data, loc, config_num(conf));
+    if (conf.quantbinCnt / 2 <= 32768)
+        blockwise_decompose_t<T, uint16_t>(ws, conf, eb, d, quant_out, blob);
+    else
+        blockwise_decompose_t<T, uint32_t>(ws, conf, eb, d, quant_out, blob);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // lossless path (SZDispatcher.hpp:54-59): size_t | zstd(raw bytes)
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T>
@@ -578,10 +755,6 @@ static size_t lossless_compress(Workspace &ws, const sz3b_config &conf, const T 
 // ---------------------------------------------------------------------------------------------------------------------
 // SZ_compress_dispatcher (SZDispatcher.hpp:13-76).  `range` > 0: precomputed value range (OMP slabs).
 // ---------------------------------------------------------------------------------------------------------------------
-template <class T>
-size_t blockwise_compress(Workspace &ws, const sz3b_config &conf, const T *d_data, uint8_t *dst, size_t cap,
-                          int zstd_threads);   // blockwise.cu
-
 template <class T>
 static size_t dispatch_compress(Workspace &ws, sz3b_config &conf, const T *data, int loc, uint8_t *dst, size_t cap,
                                 T range) {
@@ -786,7 +959,9 @@ void huffman_encode_stage(Workspace &ws, const int32_t *q, size_t n, int loc, st
     template void tune_stage<T>(Workspace &, sz3b_config &, const T *, int);                                         \
     template double abs_eb_stage<T>(Workspace &, const sz3b_config &, const T *, int);                               \
     template void minmax_stage<T>(Workspace &, const T *, int, size_t, double *, double *);                          \
-    template size_t compress_slab<T>(Workspace &, sz3b_config &, const T *, int, double, uint8_t *, size_t);
+    template size_t compress_slab<T>(Workspace &, sz3b_config &, const T *, int, double, uint8_t *, size_t);      \
+    template void blockwise_decompose_stage<T>(Workspace &, const sz3b_config &, double, const T *, int, int32_t *,  \
+                                               std::vector<uint8_t> &);
 SZ3B_INST_PIPE(float)
 SZ3B_INST_PIPE(double)
 

@@ -90,7 +90,7 @@ struct Workspace {
     // tuner
     DevBuf cubes, cube_q, cube_unpred, cube_recon, flags, starts;
     // side streams / blockwise
-    DevBuf coef, coef_q, side_q, misc;
+    DevBuf coef, coef2, coef_q, side_q, misc, counters, cpos, cval, hist2;
     // pinned staging
     PinBuf stage, stage2, hist_host;
     std::vector<uint8_t> zscratch;   // per-chunk zstd frames before concatenation (host tail)

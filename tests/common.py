@@ -96,7 +96,7 @@ def port_lib():
 def emul_lib():
     src = os.path.join(ROOT, "tests", "emul", "emul.cpp")
     out = os.path.join(ROOT, "tests", "emul", "_build", "libemul.so")
-    deps = [src] + [os.path.join(ROOT, "sz3_b200", "csrc", f) for f in ("core.cuh", "interp_body.cuh", "interp_fast.cuh", "interp_line.cuh", "interp_plan.hpp")]
+    deps = [src] + [os.path.join(ROOT, "sz3_b200", "csrc", f) for f in ("core.cuh", "interp_body.cuh", "interp_fast.cuh", "interp_line.cuh", "interp_plan.hpp", "blockwise.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-shared", "-pthread", src, "-o", out],
@@ -169,6 +169,20 @@ def ref_interp(lib, data, conf, eb, prefix="ref"):
            blob.ctypes.data_as(C.c_void_p), C.byref(blen))
     assert r == n, r
     return q, bytes(blob[:blen.value]), work
+
+
+def ref_blockwise(lib, data, conf, eb, prefix="ref"):
+    """BlockwiseDecomposition::compress + save of the checker: (indices, blob)."""
+    work = data.copy()
+    n = data.size
+    q = np.empty(n, dtype=np.int32)
+    blob = np.empty(2 * n * data.itemsize + (1 << 20), dtype=np.uint8)
+    blen = C.c_size_t(0)
+    fn = getattr(lib, prefix + "_blockwise_decompose")
+    r = fn(dtype_code(data), C.byref(conf), C.c_double(eb), work.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p),
+           blob.ctypes.data_as(C.c_void_p), C.byref(blen))
+    assert r == n, r
+    return q, bytes(blob[:blen.value])
 
 
 def interp_blob_unpred(blob, N, dtype):

@@ -157,3 +157,59 @@ extern "C" int emul_interp_decompose(int dtype, const sz3b_config *c, double eb,
     return run<double, uint16_t>(cc, eb, static_cast<const double *>(data), schedule, nthreads, quant_out,
                                  static_cast<double *>(unpred_out), n_unpred, hist_out);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Regression-only BlockwiseDecomposition: the per-thread bodies of sz3_b200/csrc/blockwise.cuh driven serially
+// (fit per block -> coefficient chain -> predict+quantize per element).  Outputs: data indices in traversal order,
+// coefficient indices, unpredictable data values in traversal order.
+// ---------------------------------------------------------------------------------------------------------------------
+#include "../../sz3_b200/csrc/blockwise.cuh"
+
+template <class T>
+static int run_reg(const sz3b_config &c, double eb, const T *data, int32_t *quant_out, int32_t *coef_q_out,
+                   size_t *n_coef, T *unpred_out, size_t *n_unpred) {
+    BlockShape bs;
+    block_shape_init(bs, c.N, c.dims, static_cast<uint32_t>(c.blockSize));
+    const int nc = c.N + 1;
+    std::vector<T> c_rec(bs.nblocks * nc, 0);
+    QuantParams ql = make_quant(eb / nc / static_cast<unsigned>(c.blockSize), 32768), qi = make_quant(eb / nc, 32768);
+    T prev[kMaxDim + 1] = {0, 0, 0, 0, 0};
+    size_t k = 0;
+    for (uint64_t b = 0; b < bs.nblocks; b++) {
+        T coef[kMaxDim + 1];
+        if (!reg_fit_block<T>(data, bs, b, coef)) return -2;
+        for (int d = 0; d < nc; d++) {
+            T rec;
+            coef_q_out[k++] = quantize<T>(coef[d], prev[d], d < c.N ? ql : qi, rec);
+            prev[d] = rec;
+            c_rec[b * nc + d] = rec;
+        }
+    }
+    *n_coef = k;
+    QuantParams qp = make_quant(eb, c.quantbinCnt / 2);
+    std::vector<T> un(bs.num);
+    for (uint64_t gid = 0; gid < bs.num; gid++) {
+        uint64_t blin, pos;
+        uint32_t li[kMaxDim];
+        reg_locate(bs, gid, &blin, li, &pos);
+        T pred = reg_predict<T>(bs.N, c_rec.data() + blin * nc, li);
+        T rec;
+        quant_out[pos] = quantize<T>(data[gid], pred, qp, rec);
+        un[pos] = data[gid];
+    }
+    size_t nu = 0;
+    for (uint64_t i = 0; i < bs.num; i++)
+        if (quant_out[i] == 0) unpred_out[nu++] = un[i];
+    *n_unpred = nu;
+    return 0;
+}
+
+extern "C" int emul_regression_decompose(int dtype, const sz3b_config *c, double eb, const void *data,
+                                         int32_t *quant_out, int32_t *coef_q_out, size_t *n_coef, void *unpred_out,
+                                         size_t *n_unpred) {
+    if (dtype == 0)
+        return run_reg<float>(*c, eb, static_cast<const float *>(data), quant_out, coef_q_out, n_coef,
+                              static_cast<float *>(unpred_out), n_unpred);
+    return run_reg<double>(*c, eb, static_cast<const double *>(data), quant_out, coef_q_out, n_coef,
+                           static_cast<double *>(unpred_out), n_unpred);
+}

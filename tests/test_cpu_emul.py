@@ -6,7 +6,8 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import ALGO_INTERP, dtype_code, emul_lib, field_nd, interp_blob_unpred, make_config, ref_interp, ref_lib
+from common import (ALGO_INTERP, ALGO_LORENZO_REG, dtype_code, emul_lib, field_nd, interp_blob_unpred, make_config,
+                    ref_blockwise, ref_interp, ref_lib)
 
 pytestmark = pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref not built")
 
@@ -67,3 +68,48 @@ def test_emul_line_walker_shapes(shape, dtype, kw):
         assert np.array_equal(q, q_ref)
         _, un_ref = interp_blob_unpred(blob_ref, conf.N, dtype)
         assert np.array_equal(un, un_ref)
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((64, 64, 64), dict(interpAlgo=0, interpDirection=5)),
+    ((64, 64, 64), dict(interpAlgo=1, interpDirection=0)),
+    ((40, 70, 66), dict(interpAlgo=1, interpDirection=5)),
+])
+def test_emul_line_walker_full_cta(shape, kw):
+    """512 emulated threads, as on the device: exercises the constant-increment row walk (needs 32 row slots)."""
+    data = field_nd(shape, np.float32)
+    conf = make_config(shape, cmprAlgo=ALGO_INTERP, interpAnchorStride=32, **kw)
+    q_ref, blob_ref, _ = ref_interp(ref_lib(), data, conf, 1e-2)
+    q, un = emul(data, conf, 1e-2, 4, nthreads=512)
+    assert np.array_equal(q, q_ref)
+    _, un_ref = interp_blob_unpred(blob_ref, conf.N, np.float32)
+    assert np.array_equal(un, un_ref)
+
+
+@pytest.mark.parametrize("shape,dtype,eb,bsz", [
+    ((24, 30, 36), np.float64, 1e-3, 6),
+    ((24, 30, 36), np.float32, 1e-3, 6),
+    ((20, 33, 47), np.float32, 1e-2, 6),      # clipped blocks (extents 2, 3, 5)
+    ((40, 45), np.float32, 1e-3, 16),
+    ((8, 10, 12, 14), np.float64, 1e-3, 6),
+    ((300,), np.float32, 1e-4, 128),
+])
+def test_emul_regression_matches_reference(shape, dtype, eb, bsz):
+    """Regression-only BlockwiseDecomposition: fit, coefficient chain and predict+quantize bodies (blockwise.cuh)."""
+    data = field_nd(shape, dtype)
+    conf = make_config(shape, cmprAlgo=ALGO_LORENZO_REG, lorenzo=0, lorenzo2=0, regression=1, blockSize=bsz)
+    q_ref, blob_ref = ref_blockwise(ref_lib(), data, conf, eb)
+    E = emul_lib()
+    q = np.empty(data.size, np.int32)
+    cq = np.empty(data.size * 2 + 64, np.int32)
+    un = np.empty(data.size, dtype)
+    ncoef, nun = C.c_size_t(0), C.c_size_t(0)
+    rc = E.emul_regression_decompose(dtype_code(data), C.byref(conf), C.c_double(eb), data.ctypes.data_as(C.c_void_p),
+                                     q.ctypes.data_as(C.c_void_p), cq.ctypes.data_as(C.c_void_p), C.byref(ncoef),
+                                     un.ctypes.data_as(C.c_void_p), C.byref(nun))
+    assert rc == 0
+    assert np.array_equal(q, q_ref), f"{int((q != q_ref).sum())} of {q.size} indices differ"
+    assert int(np.frombuffer(blob_ref[:8], np.uint64)[0]) == ncoef.value
+    if nun.value:
+        tail = np.frombuffer(blob_ref[len(blob_ref) - nun.value * data.itemsize:], dtype)
+        assert np.array_equal(tail, un[:nun.value])

@@ -1,0 +1,102 @@
+"""GPU parity of the BlockwiseDecomposition path (ALGO_LORENZO_REG) against the reference.
+
+Bar: bit-identical quantization indices, byte-identical decomposition blob (coefficient side stream included) and
+whole stream; every stream decodes with the unmodified reference decoder within the bound.
+Built so far on the GPU: the regression-only predictor stack (BASELINE.json config #3)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import (ALGO_LORENZO_REG, EB_REL, Config, dtype_code, field_g3, field_nd, make_config, product_lib, ref_blockwise,
+                    ref_lib)
+from test_gpu_compress import gpu_compress, ref_compress, ref_decompress
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref/libsz3ref.so not built")]
+
+REG_ONLY = dict(cmprAlgo=ALGO_LORENZO_REG, lorenzo=0, lorenzo2=0, regression=1)
+
+
+def gpu_blockwise(data, conf, eb):
+    L = product_lib()
+    n = data.size
+    q = np.empty(n, dtype=np.int32)
+    blob = np.empty(2 * n * data.itemsize + (1 << 20), dtype=np.uint8)
+    blen = C.c_size_t(0)
+    rc = L.sz3b_blockwise_decompose(dtype_code(data), C.byref(conf), C.c_double(eb), data.ctypes.data_as(C.c_void_p), 0,
+                                    q.ctypes.data_as(C.c_void_p), blob.ctypes.data_as(C.c_void_p), C.c_size_t(blob.size),
+                                    C.byref(blen))
+    assert rc == 0, L.sz3b_last_error()
+    return q, bytes(blob[:blen.value])
+
+
+@pytest.mark.parametrize("shape,dtype,eb,bsz", [
+    ((24, 30, 36), np.float64, 1e-3, 6),
+    ((24, 30, 36), np.float32, 1e-3, 6),
+    ((20, 33, 47), np.float32, 1e-2, 6),
+    ((66, 70, 130), np.float64, 1e-4, 6),
+    ((40, 45), np.float32, 1e-3, 16),
+    ((8, 10, 12, 14), np.float64, 1e-3, 6),
+    ((3000,), np.float32, 1e-4, 128),
+    ((48, 48, 48), np.float32, 1e-7, 6),          # eb far below the noise: many unpredictable points / coefficients
+    ((30, 30, 30), np.float32, 1e-3, 10),         # non-default block size
+])
+def test_regression_decomposition_identical(shape, dtype, eb, bsz):
+    data = field_nd(shape, dtype)
+    conf = make_config(shape, blockSize=bsz, **REG_ONLY)
+    q_ref, blob_ref = ref_blockwise(ref_lib(), data, conf, eb)
+    q, blob = gpu_blockwise(data, conf, eb)
+    assert np.array_equal(q, q_ref), f"{int((q != q_ref).sum())} of {q.size} indices differ"
+    assert blob == blob_ref, (len(blob), len(blob_ref))
+
+
+def test_regression_special_values():
+    data = field_nd((24, 24, 24), np.float32)
+    data[3, 4, 5] = np.nan
+    data[10, 11, 12] = np.inf
+    data[20, 2, 7] = -np.inf
+    conf = make_config(data.shape, **REG_ONLY)
+    q_ref, blob_ref = ref_blockwise(ref_lib(), data, conf, 1e-3)
+    q, blob = gpu_blockwise(data, conf, 1e-3)
+    assert np.array_equal(q, q_ref)
+    assert blob == blob_ref
+
+
+@pytest.mark.parametrize("shape,dtype,kw", [
+    ((60, 66, 72), np.float64, dict(errorBoundMode=EB_REL, relErrorBound=1e-4)),     # config #3 in small
+    ((60, 66, 72), np.float32, dict(absErrorBound=1e-3)),
+    ((96, 96), np.float32, dict(absErrorBound=1e-3)),
+])
+def test_regression_stream_identical_and_bounded(shape, dtype, kw):
+    data = field_g3(shape, dtype) if len(shape) == 3 else field_nd(shape, dtype)
+    conf = make_config(shape, **REG_ONLY, **kw)
+    ours, used = gpu_compress(data, conf)
+    theirs = ref_compress(data, conf)
+    assert ours.size == theirs.size and np.array_equal(ours, theirs), (ours.size, theirs.size)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.max(np.abs(dec.astype(np.float64) - data.astype(np.float64))) <= dconf.absErrorBound
+
+
+def test_composed_predictors_say_unsupported():
+    """Lorenzo stacks are not on the GPU path yet: the library must say so instead of producing a different stream."""
+    L = product_lib()
+    data = field_nd((20, 20, 20), np.float32)
+    conf = make_config(data.shape, cmprAlgo=ALGO_LORENZO_REG)
+    cap = L.sz3b_compress_bound(0, C.byref(conf))
+    out = np.empty(cap, dtype=np.uint8)
+    size = C.c_size_t(0)
+    rc = L.sz3b_compress(0, C.byref(conf), data.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_char_p), C.c_size_t(cap),
+                         C.byref(size), None)
+    assert rc == -4, L.sz3b_last_error()
+
+
+def test_config3_half_size_ratio_and_bound():
+    """BASELINE.json config #3 at 192^3 (float64, regression only, REL 1e-4): ratio equals the reference's."""
+    data = field_g3((192, 192, 192), np.float64)
+    conf = make_config(data.shape, errorBoundMode=EB_REL, relErrorBound=1e-4, **REG_ONLY)
+    ours, used = gpu_compress(data, conf)
+    theirs = ref_compress(data, conf)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.max(np.abs(dec - data)) <= dconf.absErrorBound
+    r_ours, r_ref = data.nbytes / ours.size, data.nbytes / theirs.size
+    assert abs(r_ours - r_ref) / r_ref < 0.01, (r_ours, r_ref)
