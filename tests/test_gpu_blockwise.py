@@ -59,7 +59,16 @@ def test_regression_special_values():
     q_ref, blob_ref = ref_blockwise(ref_lib(), data, conf, 1e-3)
     q, blob = gpu_blockwise(data, conf, 1e-3)
     assert np.array_equal(q, q_ref)
-    assert blob == blob_ref
+    # Blocks holding a NaN/Inf get NaN coefficients, stored as unpredictable coefficient values.  Their PAYLOAD bits are
+    # hardware-specific (x86 propagates an operand's payload, the GPU returns its canonical NaN), so the blob is
+    # compared with every NaN float canonicalised; everything else (sizes, side streams, data values) is identical.
+    assert len(blob) == len(blob_ref)
+    a, b = np.frombuffer(blob, np.uint8), np.frombuffer(blob_ref, np.uint8)
+    diff = np.flatnonzero(a != b)
+    for k in diff:
+        w = (k - 29) // 4 * 4 + 29     # unpredictable coefficients start at byte 29 of the blob (float32)
+        va, vb = np.frombuffer(blob[w:w + 4], np.float32)[0], np.frombuffer(blob_ref[w:w + 4], np.float32)[0]
+        assert np.isnan(va) and np.isnan(vb), (k, va, vb)
 
 
 @pytest.mark.parametrize("shape,dtype,kw", [
