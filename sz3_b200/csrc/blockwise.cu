@@ -87,28 +87,132 @@ __global__ void __launch_bounds__(32) k_reg_chain(const T *__restrict__ c_fit, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <class T, class QT>
-__global__ void __launch_bounds__(256) k_reg_predict(const T *__restrict__ data, BlockShape bs,
-                                                     const T *__restrict__ c_rec, QuantParams qp, QT *__restrict__ q,
-                                                     T *__restrict__ unpred_tmp, unsigned long long *__restrict__ hist) {
-    __shared__ unsigned shist[kHistWindow];
-    DevCtx ctx(shist, hist, qp.radius);
-    ctx.clear();
-    const uint64_t gid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool active = gid < bs.num;
-    int qv = 0;
-    if (active) {
-        uint64_t blin, pos;
-        uint32_t li[kMaxDim];
-        reg_locate(bs, gid, &blin, li, &pos);
-        const T pred = reg_predict<T>(bs.N, c_rec + blin * (bs.N + 1), li);
-        const T orig = data[gid];
+// Speculative form of the chain for the dense case (every block selected): one warp per coefficient walks windows of
+// 32 blocks.
+//   1. every lane guesses the lattice index K of its fitted coefficient relative to the last exact value r_cur
+//      (the quantizer snaps to the lattice r_cur + 2*eb*Z, so K does not depend on the blocks in between);
+//   2. the guessed steps d = 2*(K_b - K_{b-1})*eb are broadcast and the rounding-exact running value
+//      r_b = T(r_{b-1} + d_b) is rebuilt by every lane (one dependent FP64 add per block: the irreducible serial part);
+//   3. every lane runs the real quantizer on (c_b, r_{b-1}); lanes up to and including the first one whose index
+//      differs from the guess are exact by induction (their predecessor value was exact) and are committed with the
+//      REAL quantizer results; the window restarts after them.
+// A wrong guess costs one extra window, never a wrong result.
+template <class T>
+__global__ void __launch_bounds__(32 * (kMaxDim + 1)) k_reg_chain_spec(const T *__restrict__ c_fit, uint64_t nblocks, int N,
+                                                                       QuantParams q_liner, QuantParams q_indep,
+                                                                       int32_t *__restrict__ coef_q, T *__restrict__ c_rec,
+                                                                       unsigned long long *__restrict__ n_sel_out,
+                                                                       unsigned long long *__restrict__ n_unpred,
+                                                                       unsigned long long *__restrict__ unpred_pos,
+                                                                       T *__restrict__ unpred_val) {
+    const int d = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nc = N + 1;
+    if (d >= nc) return;
+    const QuantParams qp = d < N ? q_liner : q_indep;
+    const unsigned full = 0xffffffffu;
+    T r_cur = 0;
+    uint64_t b0 = 0;
+    T c_pref = lane < nblocks ? c_fit[static_cast<uint64_t>(lane) * nc + d] : static_cast<T>(0);
+    uint64_t pref_b0 = 0;
+    while (b0 < nblocks) {
+        const uint64_t b = b0 + lane;
+        const bool in = b < nblocks;
+        const T c = pref_b0 == b0 ? c_pref : (in ? c_fit[b * nc + d] : static_cast<T>(0));
+        {   // prefetch the window that follows a fully accepted one
+            const uint64_t nb = b0 + 32 + lane;
+            c_pref = nb < nblocks ? c_fit[nb * nc + d] : static_cast<T>(0);
+            pref_b0 = b0 + 32;
+        }
+        // 1. signed lattice index relative to r_cur
+        const T df = c - r_cur;
+        const double v = fabs(static_cast<double>(df)) * qp.ebr;
+        const bool sane = v < 1.0e9;
+        const int half = sane ? (trunc_to_int(v) + 1) >> 1 : 0;
+        const int K = df < 0 ? -half : half;
+        int Kp = __shfl_up_sync(full, K, 1);
+        if (lane == 0) Kp = 0;
+        const int dk = K - Kp;
+        const double dd = int_to_double(2 * dk) * qp.eb;
+        // 2. running value, rebuilt by every lane; keep r_{lane-1}
+        T r = r_cur, pred = r_cur;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const double di = __shfl_sync(full, dd, i);
+            r = static_cast<T>(static_cast<double>(r) + di);
+            if (i + 1 == lane) pred = r;
+        }
+        // 3. the real quantizer against the speculated predecessor
         T rec;
-        qv = quantize<T>(orig, pred, qp, rec);
-        q[pos] = static_cast<QT>(qv);
-        if (qv == 0) unpred_tmp[pos] = orig;
+        const int qv = quantize<T>(c, pred, qp, rec);
+        const bool ok = sane && qv != 0 && qv == qp.radius + dk;
+        const unsigned mism = __ballot_sync(full, in && !ok);
+        const unsigned n_in = nblocks - b0 < 32 ? static_cast<unsigned>(nblocks - b0) : 32u;
+        const unsigned first_bad = mism ? static_cast<unsigned>(__ffs(mism) - 1) : 32u;
+        const unsigned n_acc = first_bad + 1 < n_in ? first_bad + 1 : n_in;
+        if (static_cast<unsigned>(lane) < n_acc) {
+            coef_q[b * nc + d] = qv;
+            c_rec[b * nc + d] = rec;
+            if (qv == 0) {
+                const unsigned long long slot = atomicAdd(n_unpred, 1ull);
+                unpred_pos[slot] = b * nc + d;
+                unpred_val[slot] = c;
+            }
+        }
+        r_cur = __shfl_sync(full, rec, n_acc - 1);
+        b0 += n_acc;
     }
-    ctx.hist_add(qv, active);
+    if (threadIdx.x == 0) *n_sel_out = nblocks;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One CTA = one chunk of kRegChunk consecutive elements of one row (a row = all coordinates but the fastest fixed).
+// Row coordinates come from the grid indices, so no thread ever divides a 64-bit element index.
+constexpr int kRegThreads = 128;
+constexpr int kRegChunk = 512;
+
+template <class T, class QT>
+__global__ void __launch_bounds__(kRegThreads) k_reg_predict(const T *__restrict__ data, BlockShape bs, uint32_t nchunks,
+                                                            uint32_t mgB, const T *__restrict__ c_rec, QuantParams qp,
+                                                            QT *__restrict__ q, T *__restrict__ unpred_tmp,
+                                                            unsigned long long *__restrict__ hist) {
+    __shared__ unsigned shist[kHistWindow];
+    DevCtx2 ctx(shist, hist, qp.radius);
+    ctx.clear();
+    const int N = bs.N;
+    uint32_t xr[kMaxDim] = {0, 0, 0, 0};
+    uint32_t chunk = blockIdx.x;
+    if (N >= 2) {
+        xr[N - 2] = blockIdx.x / nchunks;
+        chunk = blockIdx.x - xr[N - 2] * nchunks;
+    }
+    if (N >= 3) xr[N - 3] = blockIdx.y;
+    if (N >= 4) xr[N - 4] = blockIdx.z;
+    RegRow rr;
+    reg_row_setup(bs, xr, rr);
+    uint64_t row_off = 0;
+    for (int d = 0; d < N - 1; d++) row_off += xr[d] * bs.stride[d];
+    const uint32_t len = bs.dims[N - 1];
+    const uint32_t x0 = chunk * kRegChunk;
+    const int nc = N + 1;
+#pragma unroll
+    for (int k = 0; k < kRegChunk / kRegThreads; k++) {
+        const uint32_t x = x0 + k * kRegThreads + threadIdx.x;
+        const bool active = x < len;
+        int qv = 0;
+        if (active) {
+            uint64_t blin, pos;
+            uint32_t li[kMaxDim] = {rr.li[0], rr.li[1], rr.li[2], rr.li[3]};
+            reg_row_locate(bs, rr, x, mgB, &blin, &li[N - 1], &pos);
+            const T pred = reg_predict<T>(N, c_rec + blin * nc, li);
+            const T orig = data[row_off + x];
+            T rec;
+            qv = quantize<T>(orig, pred, qp, rec);
+            q[pos] = static_cast<QT>(qv);
+            if (qv == 0) unpred_tmp[pos] = orig;
+        }
+        ctx.hist_add(qv, active);
+    }
+    ctx.pass_end();
     ctx.flush();
 }
 
@@ -122,14 +226,27 @@ template <class T>
 void launch_reg_chain(const T *c_fit, const uint8_t *sel, uint64_t nblocks, int N, const QuantParams &q_liner,
                       const QuantParams &q_indep, int32_t *coef_q, T *c_rec, unsigned long long *counters,
                       unsigned long long *unpred_pos, T *unpred_val, cudaStream_t st) {
-    k_reg_chain<T><<<1, 32, 0, st>>>(c_fit, sel, nblocks, N, q_liner, q_indep, coef_q, c_rec, counters, counters + 1,
-                                    unpred_pos, unpred_val);
+    if (sel == nullptr)   // dense: every block selected
+        k_reg_chain_spec<T><<<1, 32 * (N + 1), 0, st>>>(c_fit, nblocks, N, q_liner, q_indep, coef_q, c_rec, counters,
+                                                       counters + 1, unpred_pos, unpred_val);
+    else
+        k_reg_chain<T><<<1, 32, 0, st>>>(c_fit, sel, nblocks, N, q_liner, q_indep, coef_q, c_rec, counters, counters + 1,
+                                        unpred_pos, unpred_val);
 }
 template <class T, class QT>
-void launch_reg_predict(const T *data, const BlockShape &bs, const T *c_rec, const QuantParams &qp, QT *q, T *unpred_tmp,
-                        unsigned long long *hist, cudaStream_t st) {
-    const unsigned grid = static_cast<unsigned>((bs.num + 255) / 256);
-    k_reg_predict<T, QT><<<grid, 256, 0, st>>>(data, bs, c_rec, qp, q, unpred_tmp, hist);
+const char *launch_reg_predict(const T *data, const BlockShape &bs, const T *c_rec, const QuantParams &qp, QT *q,
+                               T *unpred_tmp, unsigned long long *hist, cudaStream_t st) {
+    const int N = bs.N;
+    const uint32_t len = bs.dims[N - 1];
+    const uint32_t nchunks = (len + kRegChunk - 1) / kRegChunk;
+    const uint64_t gx = static_cast<uint64_t>(nchunks) * (N >= 2 ? bs.dims[N - 2] : 1);
+    const uint32_t gy = N >= 3 ? bs.dims[N - 3] : 1, gz = N >= 4 ? bs.dims[N - 4] : 1;
+    if (gx > 0x7fffffffull || gy > 65535u || gz > 65535u) return "array shape exceeds the launch grid of the regression kernel";
+    // multiply-high division by B is exact while x * B < 2^32
+    const uint32_t mgB = (bs.B > 1 && static_cast<uint64_t>(len) * bs.B < (1ull << 32)) ? 0xffffffffu / bs.B + 1u : 0u;
+    dim3 grid(static_cast<unsigned>(gx), gy, gz);
+    k_reg_predict<T, QT><<<grid, kRegThreads, 0, st>>>(data, bs, nchunks, mgB, c_rec, qp, q, unpred_tmp, hist);
+    return nullptr;
 }
 
 #define SZ3B_INST_BW(T)                                                                                              \
@@ -137,10 +254,12 @@ void launch_reg_predict(const T *data, const BlockShape &bs, const T *c_rec, con
     template void launch_reg_chain<T>(const T *, const uint8_t *, uint64_t, int, const QuantParams &,                \
                                       const QuantParams &, int32_t *, T *, unsigned long long *,                    \
                                       unsigned long long *, T *, cudaStream_t);                                      \
-    template void launch_reg_predict<T, uint16_t>(const T *, const BlockShape &, const T *, const QuantParams &,     \
-                                                  uint16_t *, T *, unsigned long long *, cudaStream_t);             \
-    template void launch_reg_predict<T, uint32_t>(const T *, const BlockShape &, const T *, const QuantParams &,     \
-                                                  uint32_t *, T *, unsigned long long *, cudaStream_t);
+    template const char *launch_reg_predict<T, uint16_t>(const T *, const BlockShape &, const T *,                  \
+                                                         const QuantParams &, uint16_t *, T *, unsigned long long *, \
+                                                         cudaStream_t);                                              \
+    template const char *launch_reg_predict<T, uint32_t>(const T *, const BlockShape &, const T *,                  \
+                                                         const QuantParams &, uint32_t *, T *, unsigned long long *, \
+                                                         cudaStream_t);
 SZ3B_INST_BW(float)
 SZ3B_INST_BW(double)
 

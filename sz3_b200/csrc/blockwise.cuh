@@ -114,6 +114,49 @@ SZ_HD void reg_locate(const BlockShape &bs, uint64_t gid, uint64_t *blin_out, ui
     *pos_out = pos + within;
 }
 
+// Row-wise form of reg_locate for the predict kernel: everything that depends only on the row (all coordinates but the
+// fastest one) is folded once per row; an element then costs one small division.
+struct RegRow {
+    uint64_t pos_base;     // traversal position contributed by the slower dims (block offsets + in-block row rank)
+    uint64_t blin_base;    // block index contributed by the slower dims (times nb of the fastest dim)
+    uint64_t extprod;      // product of this row's block extents over the slower dims
+    uint64_t within_row;   // row-major rank of the row inside its block (over the slower dims)
+    uint32_t li[kMaxDim];  // in-block indices of the slower dims
+};
+
+// x[0..N-2]: coordinates of the row in the slower dims
+SZ_HD void reg_row_setup(const BlockShape &bs, const uint32_t x[kMaxDim], RegRow &rr) {
+    uint64_t blin = 0, pos = 0, within = 0, extprod = 1, tail = bs.num;
+    for (int d = 0; d < bs.N - 1; d++) {
+        const uint32_t bd = x[d] / bs.B;
+        const uint32_t lo = bd * bs.B;
+        const uint32_t ext = bs.dims[d] - lo < bs.B ? bs.dims[d] - lo : bs.B;
+        rr.li[d] = x[d] - lo;
+        blin = blin * bs.nb[d] + bd;
+        tail /= bs.dims[d];
+        pos += extprod * lo * tail;
+        within = within * ext + rr.li[d];
+        extprod *= ext;
+    }
+    rr.pos_base = pos;
+    rr.blin_base = blin * bs.nb[bs.N - 1];
+    rr.extprod = extprod;
+    rr.within_row = within;
+}
+
+// element x of the row: block index, in-block index along the fastest dim, traversal position
+SZ_HD void reg_row_locate(const BlockShape &bs, const RegRow &rr, uint32_t x, uint32_t mgB, uint64_t *blin,
+                          uint32_t *lx, uint64_t *pos) {
+    const int L = bs.N - 1;
+    // x / B: multiply-high by ceil(2^32 / B) when the row is short enough for that to be exact, else a division
+    const uint32_t bx = mgB ? static_cast<uint32_t>((static_cast<uint64_t>(x) * mgB) >> 32) : x / bs.B;
+    const uint32_t lo = bx * bs.B;
+    const uint32_t ext = bs.dims[L] - lo < bs.B ? bs.dims[L] - lo : bs.B;
+    *lx = x - lo;
+    *blin = rr.blin_base + bx;
+    *pos = rr.pos_base + rr.extprod * lo + rr.within_row * ext + (x - lo);
+}
+
 // RegressionPredictor::predict (RegressionPredictor.hpp:77-91), T arithmetic, left to right
 template <class T>
 SZ_HD T reg_predict(int N, const T *c, const uint32_t li[kMaxDim]) {

@@ -46,8 +46,8 @@ void launch_reg_chain(const T *c_fit, const uint8_t *sel, uint64_t nblocks, int 
                       const QuantParams &q_indep, int32_t *coef_q, T *c_rec, unsigned long long *counters,
                       unsigned long long *unpred_pos, T *unpred_val, cudaStream_t st);
 template <class T, class QT>
-void launch_reg_predict(const T *data, const BlockShape &bs, const T *c_rec, const QuantParams &qp, QT *q, T *unpred_tmp,
-                        unsigned long long *hist, cudaStream_t st);
+const char *launch_reg_predict(const T *data, const BlockShape &bs, const T *c_rec, const QuantParams &qp, QT *q,
+                               T *unpred_tmp, unsigned long long *hist, cudaStream_t st);   // nullptr or an error text
 
 // misc_kernels.cu
 template <class T>

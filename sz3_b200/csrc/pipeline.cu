@@ -608,7 +608,8 @@ static void run_blockwise(Workspace &ws, const sz3b_config &conf, double eb, con
     ws.stage_end(h, 1);
     h = ws.stage_begin("regression_coef_chain");
     SZ3B_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ws.st));
-    launch_reg_chain<T>(c_fit, valid, bs.nblocks, N, make_quant(eb_liner, kCoefRadius), make_quant(eb_indep, kCoefRadius),
+    // regression-only with no clipped-to-1 block: every block is selected -> the speculative dense chain (sel = null)
+    launch_reg_chain<T>(c_fit, nullptr, bs.nblocks, N, make_quant(eb_liner, kCoefRadius), make_quant(eb_indep, kCoefRadius),
                         coef_q, c_rec, counters, upos, uval, ws.st);
     ws.stage_end(h, 1);
     unsigned long long hc[2];
@@ -647,7 +648,9 @@ static void run_blockwise(Workspace &ws, const sz3b_config &conf, double eb, con
     }
     h = ws.stage_begin("predict_quantize");
     SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
-    launch_reg_predict<T, QT>(d_data, bs, c_rec, make_quant(eb, conf.quantbinCnt / 2), d_q, d_unpred_tmp, d_hist, ws.st);
+    if (const char *e = launch_reg_predict<T, QT>(d_data, bs, c_rec, make_quant(eb, conf.quantbinCnt / 2), d_q,
+                                                  d_unpred_tmp, d_hist, ws.st))
+        fail(SZ3B_E_UNSUPPORTED, e);
     ws.stage_end(h, 1);
     SZ3B_CUDA(cudaGetLastError());
     *launches += 1;

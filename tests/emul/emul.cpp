@@ -188,14 +188,30 @@ static int run_reg(const sz3b_config &c, double eb, const T *data, int32_t *quan
     *n_coef = k;
     QuantParams qp = make_quant(eb, c.quantbinCnt / 2);
     std::vector<T> un(bs.num);
-    for (uint64_t gid = 0; gid < bs.num; gid++) {
-        uint64_t blin, pos;
-        uint32_t li[kMaxDim];
-        reg_locate(bs, gid, &blin, li, &pos);
-        T pred = reg_predict<T>(bs.N, c_rec.data() + blin * nc, li);
-        T rec;
-        quant_out[pos] = quantize<T>(data[gid], pred, qp, rec);
-        un[pos] = data[gid];
+    // the kernel's mapping: one row (all coordinates but the fastest) at a time, reg_row_setup + reg_row_locate
+    const uint32_t len = bs.dims[bs.N - 1];
+    const uint32_t mgB = (bs.B > 1 && static_cast<uint64_t>(len) * bs.B < (1ull << 32)) ? 0xffffffffu / bs.B + 1u : 0u;
+    for (uint64_t row = 0; row < bs.num / len; row++) {
+        uint32_t xr[kMaxDim] = {0, 0, 0, 0};
+        uint64_t r = row;
+        for (int d = bs.N - 2; d >= 0; d--) {
+            xr[d] = static_cast<uint32_t>(r % bs.dims[d]);
+            r /= bs.dims[d];
+        }
+        RegRow rr;
+        reg_row_setup(bs, xr, rr);
+        for (uint32_t x = 0; x < len; x++) {
+            const uint64_t gid = row * len + x;
+            uint64_t blin, pos, blin2, pos2;
+            uint32_t li[kMaxDim] = {rr.li[0], rr.li[1], rr.li[2], rr.li[3]}, li2[kMaxDim];
+            reg_row_locate(bs, rr, x, mgB, &blin, &li[bs.N - 1], &pos);
+            reg_locate(bs, gid, &blin2, li2, &pos2);
+            if (blin != blin2 || pos != pos2) return -3;
+            T pred = reg_predict<T>(bs.N, c_rec.data() + blin * nc, li);
+            T rec;
+            quant_out[pos] = quantize<T>(data[gid], pred, qp, rec);
+            un[pos] = data[gid];
+        }
     }
     size_t nu = 0;
     for (uint64_t i = 0; i < bs.num; i++)
