@@ -327,6 +327,11 @@ void launch_minmax_int(const QT *q, uint64_t n, int *mm, cudaStream_t st) {
     k_minmax_int<QT><<<static_cast<unsigned>(blocks), 256, 0, st>>>(q, n, mm);
 }
 
+void launch_scan_chunks(const unsigned *chunk_bits, const unsigned *chunk_zeros, uint64_t nchunks, unsigned long long *bit_off,
+                        unsigned long long *zero_off, cudaStream_t st) {
+    k_pack_scan<<<1, 1024, 0, st>>>(chunk_bits, chunk_zeros, nchunks, bit_off, zero_off);
+}
+
 uint64_t pack_num_chunks(uint64_t n) { return (n + kPackChunk - 1) / kPackChunk; }
 
 template <class QT, class T>

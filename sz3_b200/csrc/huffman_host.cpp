@@ -252,4 +252,122 @@ bool huffman_decode(const uint8_t *&pos, size_t &remaining, size_t n, std::vecto
     return true;
 }
 
+bool HuffmanDecoder::load(const uint8_t *&pos, size_t &remaining, const char **err) {
+    auto fail = [&](const char *m) {
+        if (err) *err = m;
+        return false;
+    };
+    if (remaining < 13) return fail("huffman: truncated header");
+    memcpy(&offset, pos, 4);
+    nc = get_be32(pos + 4);
+    const uint8_t *p = pos + 13;
+    const size_t lw = nc <= 256 ? 1 : (nc <= 65536 ? 2 : 4);
+    const size_t body = 2 * static_cast<size_t>(nc) * lw + static_cast<size_t>(nc) * 5;
+    if (nc == 0 || remaining < 13 + body) return fail("huffman: truncated tree");
+    L.assign(nc, 0);
+    R.assign(nc, 0);
+    for (uint32_t i = 0; i < nc; i++) {
+        uint32_t l = 0, r = 0;
+        memcpy(&l, p + i * lw, lw);
+        memcpy(&r, p + (nc + static_cast<size_t>(i)) * lw, lw);
+        if (l >= nc || r >= nc) return fail("huffman: bad tree link");
+        L[i] = l;
+        R[i] = r;
+    }
+    const uint8_t *pc = p + 2 * static_cast<size_t>(nc) * lw;
+    C.resize(nc);
+    memcpy(C.data(), pc, static_cast<size_t>(nc) * 4);
+    leaf.assign(pc + static_cast<size_t>(nc) * 4, pc + static_cast<size_t>(nc) * 5);
+    p = pc + static_cast<size_t>(nc) * 5;
+    remaining -= static_cast<size_t>(p - pos);
+    pos = p;
+    // first-level table: walk the tree along every kLutBits-bit prefix
+    lut.assign(1u << kLutBits, 0);
+    if (!leaf[0]) {
+        for (uint32_t pre = 0; pre < (1u << kLutBits); pre++) {
+            uint32_t node = 0;
+            uint32_t e = 0;
+            for (int b = 0; b < kLutBits; b++) {
+                node = ((pre >> (kLutBits - 1 - b)) & 1u) ? R[node] : L[node];
+                if (node == 0) break;   // link to the root = absent child (malformed path): leave unresolved at root
+                if (leaf[node]) {
+                    e = (static_cast<uint32_t>(b + 1) << 24) | node;
+                    break;
+                }
+            }
+            lut[pre] = e ? e : node;   // len == 0: continue walking from `node` after kLutBits bits
+        }
+    }
+    return true;
+}
+
+template <class Out>
+bool HuffmanDecoder::decode(const uint8_t *&pos, size_t &remaining, size_t n, Out *out, const char **err) const {
+    auto fail = [&](const char *m) {
+        if (err) *err = m;
+        return false;
+    };
+    if (remaining < 8) return fail("huffman: truncated bitstream header");
+    uint64_t enc_len;
+    memcpy(&enc_len, pos, 8);
+    const uint8_t *p = pos + 8;
+    if (remaining - 8 < enc_len) return fail("huffman: truncated bitstream");
+    if (leaf[0]) {   // single-symbol tree (:233-237)
+        const Out v = static_cast<Out>(C[0] + offset);
+        for (size_t i = 0; i < n; i++) out[i] = v;
+    } else {
+        const uint64_t nbits = enc_len * 8;
+        uint64_t bitpos = 0;       // bits consumed
+        uint64_t acc = 0;          // next bits, left-aligned
+        int have = 0;              // valid bits in acc
+        size_t next_byte = 0;
+        auto refill = [&]() {
+            while (have <= 56 && next_byte < enc_len) {
+                acc |= static_cast<uint64_t>(p[next_byte++]) << (56 - have);
+                have += 8;
+            }
+        };
+        for (size_t cnt = 0; cnt < n; cnt++) {
+            refill();
+            uint32_t e = lut[acc >> (64 - kLutBits)];
+            uint32_t len = e >> 24, node = e & 0xffffffu;
+            if (len == 0) {   // long code: keep walking bit by bit
+                uint64_t a = acc << kLutBits;
+                int used = kLutBits;
+                if (used > have) return fail("huffman: bitstream exhausted");
+                for (;;) {
+                    if (used >= have) {   // need more bits than buffered: consume what we have and refill
+                        acc = used >= 64 ? 0 : acc << used;
+                        have -= used;
+                        bitpos += used;
+                        used = 0;
+                        refill();
+                        a = acc;
+                        if (have == 0) return fail("huffman: bitstream exhausted");
+                    }
+                    node = (a >> 63) ? R[node] : L[node];
+                    a <<= 1;
+                    used++;
+                    if (node == 0) return fail("huffman: bad tree link");
+                    if (leaf[node]) break;
+                }
+                len = static_cast<uint32_t>(used);
+            }
+            if (static_cast<int>(len) > have || bitpos + len > nbits) return fail("huffman: bitstream exhausted");
+            out[cnt] = static_cast<Out>(C[node] + offset);
+            acc <<= len;
+            have -= static_cast<int>(len);
+            bitpos += len;
+        }
+    }
+    p += enc_len;
+    remaining -= static_cast<size_t>(p - pos);
+    pos = p;
+    return true;
+}
+
+template bool HuffmanDecoder::decode<uint16_t>(const uint8_t *&, size_t &, size_t, uint16_t *, const char **) const;
+template bool HuffmanDecoder::decode<uint32_t>(const uint8_t *&, size_t &, size_t, uint32_t *, const char **) const;
+template bool HuffmanDecoder::decode<int32_t>(const uint8_t *&, size_t &, size_t, int32_t *, const char **) const;
+
 }  // namespace sz3b

@@ -32,4 +32,20 @@ bool huffman_build(const unsigned long long *hist, size_t nbins, int sym_base, H
 // laid out as `size_t outSize | bits`.  Advances *pos past everything it consumed.  Returns false on malformed input.
 bool huffman_decode(const uint8_t *&pos, size_t &remaining, size_t n, std::vector<int> &out, const char **err);
 
+// Table-driven decoder for the main index stream: `load` parses the tree blob of HuffmanEncoder::save (:108-125,
+// :261-279) and builds a kLutBits-wide first-level table (most codes of a skewed index distribution resolve in one
+// lookup), `decode` reads `size_t outSize | bits` (HuffmanEncoder::decode :225-255) and writes n symbols.
+struct HuffmanDecoder {
+    static constexpr int kLutBits = 12;
+    int offset = 0;
+    uint32_t nc = 0;
+    std::vector<uint32_t> L, R;
+    std::vector<int> C;
+    std::vector<uint8_t> leaf;
+    std::vector<uint32_t> lut;   // (len << 24) | node: len > 0 -> leaf `node` reached after len bits; len == 0 -> continue at `node`
+    bool load(const uint8_t *&pos, size_t &remaining, const char **err);
+    template <class Out>
+    bool decode(const uint8_t *&pos, size_t &remaining, size_t n, Out *out, const char **err) const;
+};
+
 }  // namespace sz3b

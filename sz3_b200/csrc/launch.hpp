@@ -49,6 +49,26 @@ template <class T, class QT>
 const char *launch_reg_predict(const T *data, const BlockShape &bs, const T *c_rec, const QuantParams &qp, QT *q,
                                T *unpred_tmp, unsigned long long *hist, cudaStream_t st);   // nullptr or an error text
 
+// decompress.cu
+uint64_t zero_num_chunks(uint64_t n);
+template <class QT>
+void launch_zero_count(const QT *q, uint64_t n, unsigned *chunk_zeros, unsigned *chunk_bits, cudaStream_t st);
+template <class QT, class T>
+void launch_zero_scatter(const QT *q, uint64_t n, const unsigned long long *zero_off, const T *unpred, uint64_t n_unpred,
+                         T *unpred_tmp, cudaStream_t st);
+template <class T, class QT>
+void launch_interp_recover(const InterpShape &sh, T *out, const QT *q, const T *unpred_tmp, const QuantParams &qp, uint32_t s,
+                           const uint32_t nb[kMaxDim], const uint64_t *block_base, int pass, uint32_t anchor_stride,
+                           uint64_t n_anchor, cudaStream_t st);
+template <class T>
+void launch_reg_chain_recover(const int32_t *coef_q, const T *coef_unp, uint64_t nblocks, int N, const QuantParams &q_liner,
+                              const QuantParams &q_indep, T *c_rec, cudaStream_t st);
+template <class T, class QT>
+const char *launch_reg_recover(T *out, const BlockShape &bs, const T *c_rec, const QuantParams &qp, const QT *q,
+                               const T *unpred_tmp, cudaStream_t st);
+void launch_scan_chunks(const unsigned *chunk_bits, const unsigned *chunk_zeros, uint64_t nchunks, unsigned long long *bit_off,
+                        unsigned long long *zero_off, cudaStream_t st);   // encode_kernels.cu (k_pack_scan)
+
 // misc_kernels.cu
 template <class T>
 void launch_minmax(const T *data, uint64_t n, T *mm /* device: [min, max] */, cudaStream_t st);

@@ -867,6 +867,272 @@ size_t compress_any(Workspace &ws, sz3b_config &conf, const T *data, int loc, ui
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// SZ_decompress_dispatcher / SZGenericCompressor::decompress / SZ_decompress_OMP
+// (api/impl/SZDispatcher.hpp:79-107, compressor/SZGenericCompressor.hpp:65-84, api/impl/SZImplOMP.hpp:120-186).
+// zstd and the (bit-serial, restart-free) Huffman decode run on the host; index expansion, unpredictable-value
+// placement and every `recover` loop run on the GPU.
+// ---------------------------------------------------------------------------------------------------------------------
+struct Cursor {
+    const uint8_t *p;
+    size_t rem;
+    template <class V>
+    V get() {
+        if (rem < sizeof(V)) fail(SZ3B_E_INVALID_ARGUMENT, "truncated stream");
+        V v;
+        memcpy(&v, p, sizeof(V));
+        p += sizeof(V);
+        rem -= sizeof(V);
+        return v;
+    }
+    const uint8_t *take(size_t n) {
+        if (rem < n) fail(SZ3B_E_INVALID_ARGUMENT, "truncated stream");
+        const uint8_t *q = p;
+        p += n;
+        rem -= n;
+        return q;
+    }
+};
+
+// LinearQuantizer::load (LinearQuantizer.hpp:106-120)
+template <class T>
+static void quantizer_load(Cursor &c, double *eb, int *radius, const T **unpred, uint64_t *n_unpred) {
+    (void)c.get<uint8_t>();   // uid
+    *eb = c.get<double>();
+    *radius = c.get<int32_t>();
+    *n_unpred = c.get<uint64_t>();
+    if (*n_unpred > c.rem / sizeof(T)) fail(SZ3B_E_INVALID_ARGUMENT, "truncated stream (unpredictable values)");
+    *unpred = reinterpret_cast<const T *>(c.take(*n_unpred * sizeof(T)));
+}
+
+// encoder.load | size_t n | size_t outSize | bits  ->  indices as QT in pinned memory, then on the device
+template <class QT>
+static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
+    HuffmanDecoder dec;
+    const char *err = nullptr;
+    double t0 = now_ms();
+    if (!dec.load(c.p, c.rem, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+    const uint64_t n = c.get<uint64_t>();
+    if (n != expect_n) fail(SZ3B_E_INVALID_ARGUMENT, "index count does not match the array size");
+    QT *h_q = static_cast<QT *>(ws.stage2.ensure(n * sizeof(QT)));
+    if (!dec.decode<QT>(c.p, c.rem, n, h_q, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+    ws.host_stage("huffman_decode_host", now_ms() - t0);
+    QT *d_q = ws.q.as<QT>(n);
+    size_t h = ws.stage_begin("h2d_indices");
+    ws.h2d(d_q, h_q, n * sizeof(QT));
+    ws.stage_end(h, 0);
+    return d_q;
+}
+
+// position-indexed unpredictable values on the device
+template <class T, class QT>
+static T *place_unpred(Workspace &ws, const QT *d_q, uint64_t n, const T *h_unpred, uint64_t n_unpred, int *launches) {
+    T *d_tmp = ws.unpred_tmp.as<T>(n);
+    if (n_unpred == 0) return d_tmp;
+    T *d_un = ws.unpred_out.as<T>(n_unpred);
+    ws.h2d(d_un, h_unpred, n_unpred * sizeof(T));
+    const uint64_t nch = zero_num_chunks(n);
+    unsigned *cz = ws.chunk_zeros.as<unsigned>(nch + 1);
+    unsigned *cb = ws.chunk_bits.as<unsigned>(nch + 1);
+    unsigned long long *zo = ws.zero_off.as<unsigned long long>(nch + 2);
+    unsigned long long *bo = ws.bit_off.as<unsigned long long>(nch + 2);
+    launch_zero_count<QT>(d_q, n, cz, cb, ws.st);
+    launch_scan_chunks(cb, cz, nch, bo, zo, ws.st);
+    launch_zero_scatter<QT, T>(d_q, n, zo, d_un, n_unpred, d_tmp, ws.st);
+    *launches += 3;
+    return d_tmp;
+}
+
+template <class T, class QT>
+static void interp_decompress_t(Workspace &ws, const sz3b_config &conf, Cursor &c, T *d_out, int radius_hint) {
+    // InterpolationDecomposition::load (:161-174)
+    sz3b_config ic = conf;
+    for (int d = 0; d < conf.N; d++) {
+        const uint64_t dim = c.get<uint64_t>();
+        if (dim != conf.dims[d]) fail(SZ3B_E_INVALID_ARGUMENT, "decomposition dims do not match the Config");
+    }
+    const uint32_t blocksize = c.get<uint32_t>();
+    if (blocksize != static_cast<uint32_t>(kInterpBlock)) fail(SZ3B_E_UNSUPPORTED, "interpolation block size other than 32");
+    ic.interpAlgo = c.get<int32_t>();
+    ic.interpDirection = c.get<int32_t>();
+    ic.interpAnchorStride = static_cast<int32_t>(c.get<uint64_t>());
+    ic.interpAlpha = c.get<double>();
+    ic.interpBeta = c.get<double>();
+    double eb;
+    int radius;
+    const T *h_unpred;
+    uint64_t n_unpred;
+    quantizer_load<T>(c, &eb, &radius, &h_unpred, &n_unpred);
+    if ((radius <= 32768) != (sizeof(QT) == 2)) fail(SZ3B_E_INVALID_ARGUMENT, "quantizer radius does not match Config.quantbinCnt");
+    (void)radius_hint;
+    InterpPlan pl;
+    if (const char *e = build_interp_plan(ic, eb, 1, pl)) fail(SZ3B_E_INVALID_ARGUMENT, e);
+    QT *d_q = decode_indices<QT>(ws, c, pl.num);
+    int launches = 0;
+    size_t h = ws.stage_begin("recover");
+    T *d_tmp = place_unpred<T, QT>(ws, d_q, pl.num, h_unpred, n_unpred, &launches);
+    uint64_t *d_table = ws.tables.as<uint64_t>(pl.table.size() + 1);
+    if (!pl.table.empty()) ws.h2d(d_table, pl.table.data(), pl.table.size() * sizeof(uint64_t));
+    launch_interp_recover<T, QT>(pl.sh, d_out, d_q, d_tmp, make_quant(pl.eb, radius), 0, nullptr, nullptr, -1,
+                                 pl.anchor_stride, pl.n_first, ws.st);
+    launches++;
+    for (const LevelPlan &L : pl.levels) {
+        for (int p = 0; p < pl.sh.N; p++) {
+            launch_interp_recover<T, QT>(pl.sh, d_out, d_q, d_tmp, make_quant(L.eb, radius), L.s, L.nb, d_table + L.table_off,
+                                         p, 0, 0, ws.st);
+            launches++;
+        }
+    }
+    ws.stage_end(h, launches);
+    SZ3B_CUDA(cudaGetLastError());
+}
+
+template <class T, class QT>
+static void blockwise_decompress_t(Workspace &ws, const sz3b_config &conf, Cursor &c, T *d_out) {
+    const int N = conf.N;
+    if (conf.lorenzo || conf.lorenzo2)
+        fail(SZ3B_E_UNSUPPORTED, "ALGO_LORENZO_REG streams with a Lorenzo predictor are not on the GPU path yet");
+    if (!conf.regression) fail(SZ3B_E_INVALID_ARGUMENT, "All lorenzo and regression methods are disabled.");
+    BlockShape bs;
+    block_shape_init(bs, N, conf.dims, static_cast<uint32_t>(conf.blockSize));
+    const int nc = N + 1;
+    // RegressionPredictor::load (RegressionPredictor.hpp:109-123)
+    const uint64_t n_coef = c.get<uint64_t>();
+    if (n_coef != bs.nblocks * nc) fail(SZ3B_E_UNSUPPORTED, "regression stream with fallback blocks (extent-1 blocks)");
+    double eb_i, eb_l;
+    int rad_i, rad_l;
+    const T *un_i, *un_l;
+    uint64_t nun_i, nun_l;
+    quantizer_load<T>(c, &eb_i, &rad_i, &un_i, &nun_i);
+    quantizer_load<T>(c, &eb_l, &rad_l, &un_l, &nun_l);
+    std::vector<int32_t> cq(n_coef);
+    {
+        HuffmanDecoder dec;
+        const char *err = nullptr;
+        if (!dec.load(c.p, c.rem, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+        if (!dec.decode<int32_t>(c.p, c.rem, n_coef, cq.data(), &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+    }
+    // stored exact coefficients, by position (both quantizers consume their lists in block order)
+    std::vector<T> cun(n_coef, 0);
+    {
+        uint64_t ki = 0, kl = 0;
+        for (uint64_t pos = 0; pos < n_coef; pos++)
+            if (cq[pos] == 0) {
+                if (pos % nc == static_cast<unsigned>(N)) {
+                    if (ki >= nun_i) fail(SZ3B_E_INVALID_ARGUMENT, "truncated stream (coefficients)");
+                    cun[pos] = un_i[ki++];
+                } else {
+                    if (kl >= nun_l) fail(SZ3B_E_INVALID_ARGUMENT, "truncated stream (coefficients)");
+                    cun[pos] = un_l[kl++];
+                }
+            }
+    }
+    double eb;
+    int radius;
+    const T *h_unpred;
+    uint64_t n_unpred;
+    quantizer_load<T>(c, &eb, &radius, &h_unpred, &n_unpred);
+    if ((radius <= 32768) != (sizeof(QT) == 2)) fail(SZ3B_E_INVALID_ARGUMENT, "quantizer radius does not match Config.quantbinCnt");
+    QT *d_q = decode_indices<QT>(ws, c, bs.num);
+    int launches = 0;
+    size_t h = ws.stage_begin("recover");
+    int32_t *d_cq = ws.coef_q.as<int32_t>(n_coef);
+    T *d_cun = ws.coef.as<T>(n_coef);
+    T *d_crec = ws.coef2.as<T>(n_coef);
+    ws.h2d(d_cq, cq.data(), n_coef * sizeof(int32_t));
+    ws.h2d(d_cun, cun.data(), n_coef * sizeof(T));
+    launch_reg_chain_recover<T>(d_cq, d_cun, bs.nblocks, N, make_quant(eb_l, rad_l), make_quant(eb_i, rad_i), d_crec, ws.st);
+    T *d_tmp = place_unpred<T, QT>(ws, d_q, bs.num, h_unpred, n_unpred, &launches);
+    if (const char *e = launch_reg_recover<T, QT>(d_out, bs, d_crec, make_quant(eb, radius), d_q, d_tmp, ws.st))
+        fail(SZ3B_E_UNSUPPORTED, e);
+    ws.stage_end(h, launches + 2);
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // cq / cun are host vectors
+    SZ3B_CUDA(cudaGetLastError());
+}
+
+// one non-OMP payload -> `out` (host or device pointer to config_num(conf) elements)
+template <class T>
+static void decompress_one(Workspace &ws, const sz3b_config &conf, const uint8_t *cmp, size_t cmp_size, T *out, int loc) {
+    const uint64_t num = config_num(conf);
+    const size_t bytes = num * sizeof(T);
+    if (conf.cmprAlgo == SZ3B_ALGO_LOSSLESS) {
+        // SZDispatcher.hpp:83-88: zstd(raw array)
+        uint8_t *dst = loc == SZ3B_HOST ? reinterpret_cast<uint8_t *>(out) : static_cast<uint8_t *>(ws.stage.ensure(bytes));
+        size_t raw = 0;
+        double t0 = now_ms();
+        if (!zstd_decompress_parallel(cmp, cmp_size, dst, bytes, &raw, host_threads()) || raw != bytes)
+            fail(SZ3B_E_RUNTIME, "lossless decompression failed (size mismatch)");
+        ws.host_stage("zstd_host", now_ms() - t0);
+        if (loc == SZ3B_DEVICE) {
+            ws.h2d(out, dst, bytes);
+            SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        }
+        return;
+    }
+    if (conf.cmprAlgo != SZ3B_ALGO_INTERP && conf.cmprAlgo != SZ3B_ALGO_LORENZO_REG) {
+        if (conf.cmprAlgo == SZ3B_ALGO_INTERP_LORENZO || conf.cmprAlgo == SZ3B_ALGO_NOPRED || conf.cmprAlgo == 5 || conf.cmprAlgo == 6)
+            fail(SZ3B_E_UNSUPPORTED, "stream algorithm outside the GPU hot path");
+        fail(SZ3B_E_INVALID_ARGUMENT, "Unknown compression algorithm");
+    }
+    const size_t raw_len = zstd_framed_raw_len(cmp, cmp_size);
+    if (raw_len == 0 || raw_len > (bytes + (static_cast<size_t>(1) << 20)) * 4) fail(SZ3B_E_INVALID_ARGUMENT, "implausible stream length");
+    uint8_t *raw = static_cast<uint8_t *>(ws.stage.ensure(raw_len + 16));
+    {
+        size_t got = 0;
+        double t0 = now_ms();
+        if (!zstd_decompress_parallel(cmp, cmp_size, raw, raw_len, &got, host_threads())) fail(SZ3B_E_RUNTIME, "zstd decompression failed");
+        ws.host_stage("zstd_host", now_ms() - t0);
+    }
+    Cursor c{raw, raw_len};
+    T *d_out = loc == SZ3B_DEVICE ? out : ws.data.as<T>(num);
+    const bool narrow = conf.quantbinCnt / 2 <= 32768;
+    if (conf.cmprAlgo == SZ3B_ALGO_INTERP) {
+        if (narrow)
+            interp_decompress_t<T, uint16_t>(ws, conf, c, d_out, 0);
+        else
+            interp_decompress_t<T, uint32_t>(ws, conf, c, d_out, 0);
+    } else {
+        if (narrow)
+            blockwise_decompress_t<T, uint16_t>(ws, conf, c, d_out);
+        else
+            blockwise_decompress_t<T, uint32_t>(ws, conf, c, d_out);
+    }
+    if (loc == SZ3B_HOST) {
+        size_t h = ws.stage_begin("d2h_output");
+        ws.d2h(out, d_out, bytes);
+        ws.stage_end(h, 0);
+    }
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+}
+
+template <class T>
+void decompress_any(Workspace &ws, sz3b_config &conf, const uint8_t *cmp, size_t cmp_size, T *out, int loc) {
+    if (!conf.openmp) {
+        decompress_one<T>(ws, conf, cmp, cmp_size, out, loc);
+        return;
+    }
+    // SZ_decompress_OMP (SZImplOMP.hpp:120-186): int nThreads | Config x n | size_t x n | payloads
+    Cursor c{cmp, cmp_size};
+    const int n = c.get<int32_t>();
+    if (n < 1 || static_cast<uint64_t>(n) > conf.dims[0]) fail(SZ3B_E_INVALID_ARGUMENT, "bad slab count in the OpenMP container");
+    std::vector<sz3b_config> confs(n, conf);
+    for (int t = 0; t < n; t++) {
+        if (c.rem < 1) fail(SZ3B_E_INVALID_ARGUMENT, "truncated stream");
+        const size_t len = c.p[0];
+        confs[t].openmp = 0;
+        if (!config_load(confs[t], c.take(len), len)) fail(SZ3B_E_INVALID_ARGUMENT, "malformed slab Config");
+        confs[t].openmp = 0;
+    }
+    std::vector<uint64_t> sizes(n);
+    for (int t = 0; t < n; t++) sizes[t] = c.get<uint64_t>();
+    const uint64_t row = config_num(conf) / conf.dims[0];
+    for (int t = 0; t < n; t++) {
+        const uint64_t lo = static_cast<uint64_t>(t) * conf.dims[0] / n, hi = static_cast<uint64_t>(t + 1) * conf.dims[0] / n;
+        if (config_num(confs[t]) != (hi - lo) * row) fail(SZ3B_E_INVALID_ARGUMENT, "slab Config does not match the container");
+        decompress_one<T>(ws, confs[t], c.take(sizes[t]), sizes[t], out + lo * row, loc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // stage-level entry points
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T, class QT>
@@ -963,6 +1229,7 @@ void huffman_encode_stage(Workspace &ws, const int32_t *q, size_t n, int loc, st
     template double abs_eb_stage<T>(Workspace &, const sz3b_config &, const T *, int);                               \
     template void minmax_stage<T>(Workspace &, const T *, int, size_t, double *, double *);                          \
     template size_t compress_slab<T>(Workspace &, sz3b_config &, const T *, int, double, uint8_t *, size_t);      \
+    template void decompress_any<T>(Workspace &, sz3b_config &, const uint8_t *, size_t, T *, int);                  \
     template void blockwise_decompose_stage<T>(Workspace &, const sz3b_config &, double, const T *, int, int32_t *,  \
                                                std::vector<uint8_t> &);
 SZ3B_INST_PIPE(float)

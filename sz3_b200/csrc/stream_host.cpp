@@ -309,4 +309,69 @@ bool zstd_decompress_into(const uint8_t *src, size_t src_len, uint8_t *dst, size
     return !ZSTD_isError(r) && r == n;
 }
 
+size_t zstd_framed_raw_len(const uint8_t *src, size_t src_len) {
+    if (src_len < 8) return 0;
+    uint64_t n;
+    memcpy(&n, src, 8);
+    return static_cast<size_t>(n);
+}
+
+namespace {
+struct DFrame {
+    const uint8_t *src;
+    size_t csize, off, dsize;
+};
+struct DJob {
+    std::vector<DFrame> frames;
+    uint8_t *dst;
+    std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
+};
+void djob_worker(void *arg, int) {
+    DJob &j = *static_cast<DJob *>(arg);
+    for (;;) {
+        size_t k = j.next.fetch_add(1);
+        if (k >= j.frames.size()) break;
+        const DFrame &f = j.frames[k];
+        size_t r = ZSTD_decompress(j.dst + f.off, f.dsize, f.src, f.csize);
+        if (ZSTD_isError(r) || r != f.dsize) j.failed = true;
+    }
+}
+}  // namespace
+
+bool zstd_decompress_parallel(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *raw_len, int threads) {
+    if (src_len < 8) return false;
+    const size_t n = zstd_framed_raw_len(src, src_len);
+    *raw_len = n;
+    if (n > dst_cap) return false;
+    const uint8_t *p = src + 8;
+    size_t rem = src_len - 8;
+    DJob j;
+    j.dst = dst;
+    size_t off = 0;
+    bool splittable = true;
+    while (rem > 0) {
+        size_t cs = ZSTD_findFrameCompressedSize(p, rem);
+        if (ZSTD_isError(cs) || cs == 0 || cs > rem) {
+            splittable = false;
+            break;
+        }
+        unsigned long long ds = ZSTD_getFrameContentSize(p, cs);
+        if (ds >= 0xfffffffffffffffeull) {   // unknown / error
+            splittable = false;
+            break;
+        }
+        j.frames.push_back({p, cs, off, static_cast<size_t>(ds)});
+        off += static_cast<size_t>(ds);
+        p += cs;
+        rem -= cs;
+    }
+    if (!splittable || off != n || j.frames.size() < 2 || threads < 2) {
+        size_t r = ZSTD_decompress(dst, n, src + 8, src_len - 8);
+        return !ZSTD_isError(r) && r == n;
+    }
+    host_parallel(static_cast<int>(std::min<size_t>(threads, j.frames.size())), djob_worker, &j);
+    return !j.failed;
+}
+
 }  // namespace sz3b

@@ -58,6 +58,10 @@ void host_parallel(int nworkers, void (*fn)(void *arg, int worker), void *arg);
 // Lossless_zstd::decompress (:39-45).  Returns false on a zstd error.
 bool zstd_decompress_framed(const uint8_t *src, size_t src_len, std::vector<uint8_t> &out);
 bool zstd_decompress_into(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *dst_len);
+// Same stream, frames decompressed concurrently when every frame states its content size (the frames this library
+// writes do); falls back to one ZSTD_decompress call otherwise.  *raw_len = the size_t prefix.
+bool zstd_decompress_parallel(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *raw_len, int threads);
+size_t zstd_framed_raw_len(const uint8_t *src, size_t src_len);
 
 int host_threads();
 void set_host_threads(int n);

@@ -13,6 +13,8 @@ size_t ZSTD_compressBound(size_t srcSize);
 size_t ZSTD_compress(void *dst, size_t dstCapacity, const void *src, size_t srcSize, int compressionLevel);
 size_t ZSTD_decompress(void *dst, size_t dstCapacity, const void *src, size_t compressedSize);
 unsigned ZSTD_isError(size_t code);
+size_t ZSTD_findFrameCompressedSize(const void *src, size_t srcSize);
+unsigned long long ZSTD_getFrameContentSize(const void *src, size_t srcSize);
 typedef struct ZSTD_CCtx_s ZSTD_CCtx;
 ZSTD_CCtx *ZSTD_createCCtx(void);
 size_t ZSTD_freeCCtx(ZSTD_CCtx *cctx);

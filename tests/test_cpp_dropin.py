@@ -1,0 +1,90 @@
+"""The drop-in C++ surface: a program written against the reference's own API (SZ3/api/sz.hpp, SZ3::Config, sz3c.h)
+must compile unchanged against include/ and link against sz3_b200/lib.  CPU part: compile + link + the Config-only
+behaviour (no GPU needed).  GPU part: run the round trip."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = r'''
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "SZ3/api/sz.hpp"
+#include "sz3c.h"
+int main(int argc, char **argv) {
+    SZ3::Config conf(40, 50, 60);
+    if (conf.N != 3 || conf.num != 40u * 50u * 60u || conf.blockSize != 6 || conf.cmprAlgo != SZ3::ALGO_INTERP_LORENZO) return 10;
+    conf.load_ini("[GlobalSettings]\nCmprAlgo = ALGO_INTERP\nErrorBoundMode = REL\nRelErrorBound = 1e-3\n[AlgoSettings]\nInterpolationAlgo = INTERP_ALGO_LINEAR\n");
+    if (conf.cmprAlgo != SZ3::ALGO_INTERP || conf.errorBoundMode != SZ3::EB_REL || conf.interpAlgo != SZ3::INTERP_ALGO_LINEAR) return 11;
+    unsigned char blob[256];
+    unsigned char *p = blob;
+    size_t n = conf.save(p);
+    SZ3::Config back;
+    const unsigned char *q = blob;
+    back.load(q);
+    if (n == 0 || back.N != 3 || back.dims != conf.dims || back.relErrorBound != 1e-3 || back.cmprAlgo != SZ3::ALGO_INTERP) return 12;
+    SZ3::Config one(1, 7, 1);
+    if (one.N != 1 || one.dims[0] != 7) return 13;
+    if (argc < 2 || strcmp(argv[1], "gpu")) { printf("config ok\n"); return 0; }
+    // round trip through SZ_compress / SZ_decompress and the C shim
+    SZ3::Config c2(40, 50, 60);
+    c2.absErrorBound = 1e-3;
+    std::vector<float> data(c2.num);
+    for (size_t i = 0; i < data.size(); i++) data[i] = std::sin(0.01f * i) + 0.001f * (i % 7);
+    size_t cmpSize = 0;
+    char *cmp = SZ_compress<float>(c2, data.data(), cmpSize);
+    SZ3::Config dc;
+    float *dec = nullptr;
+    SZ_decompress<float>(dc, cmp, cmpSize, dec);
+    if (dc.num != c2.num || dc.N != 3) return 20;
+    double worst = 0;
+    for (size_t i = 0; i < data.size(); i++) worst = std::fmax(worst, std::fabs((double)dec[i] - data[i]));
+    if (!(worst <= 1e-3)) return 21;
+    delete[] dec;
+    delete[] cmp;
+    try {
+        char small[8];
+        SZ_compress<float>(c2, data.data(), small, sizeof small);
+        return 22;
+    } catch (const std::invalid_argument &) {}
+    size_t outSize = 0;
+    unsigned char *c = SZ_compress_args(SZ_FLOAT, data.data(), &outSize, ABS, 1e-3, 0, 0, 0, 0, 40, 50, 60);
+    float *d2 = (float *)SZ_decompress(SZ_FLOAT, c, outSize, 0, 0, 40, 50, 60);
+    worst = 0;
+    for (size_t i = 0; i < data.size(); i++) worst = std::fmax(worst, std::fabs((double)d2[i] - data[i]));
+    free_buf(c);
+    free_buf(d2);
+    if (!(worst <= 1e-3)) return 23;
+    printf("roundtrip ok ratio %.2f\n", data.size() * 4.0 / cmpSize);
+    return 0;
+}
+'''
+
+
+def _build(tmp_path):
+    src = tmp_path / "dropin.cpp"
+    src.write_text(SRC)
+    exe = tmp_path / "dropin"
+    lib = os.path.join(ROOT, "sz3_b200", "lib")
+    subprocess.run(["g++", "-std=c++17", "-O1", str(src), "-I", os.path.join(ROOT, "include"), "-L", lib, "-lSZ3c", "-lsz3b200",
+                    f"-Wl,-rpath,{lib}", "-o", str(exe)], check=True)
+    return str(exe)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "sz3_b200", "lib", "libSZ3c.so")), reason="libraries not built")
+def test_dropin_headers_compile_and_config_roundtrip(tmp_path):
+    exe = _build(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_dropin_roundtrip_on_gpu(tmp_path):
+    exe = _build(tmp_path)
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "roundtrip ok" in r.stdout

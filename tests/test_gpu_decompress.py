@@ -1,0 +1,123 @@
+"""GPU parity of the SZ_decompress half (sz3b_decompress) against the reference decoder.
+
+Bar: the reconstructed array is BIT-IDENTICAL to what the unmodified reference decoder produces from the same stream
+(recover() is deterministic arithmetic), for streams written by either implementation, and honours the bound."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import (ALGO_INTERP, ALGO_INTERP_LORENZO, ALGO_LORENZO_REG, EB_REL, Config, dtype_code, field_g3, field_nd,
+                    make_config, product_lib, ref_lib)
+from test_gpu_compress import gpu_compress, ref_compress, ref_decompress
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref/libsz3ref.so not built")]
+
+
+def gpu_decompress(cmp, like, device=False):
+    L = product_lib()
+    conf = Config()
+    cmp = np.ascontiguousarray(cmp)
+    if device:
+        import torch
+        out_t = torch.empty(like.shape, dtype=torch.float32 if like.dtype == np.float32 else torch.float64, device="cuda")
+        rc = L.sz3b_decompress(dtype_code(like), cmp.ctypes.data_as(C.c_char_p), C.c_size_t(cmp.size), C.c_void_p(out_t.data_ptr()), 1, C.byref(conf))
+        assert rc == 0, L.sz3b_last_error()
+        return out_t.cpu().numpy(), conf
+    out = np.empty_like(like)
+    rc = L.sz3b_decompress(dtype_code(like), cmp.ctypes.data_as(C.c_char_p), C.c_size_t(cmp.size), out.ctypes.data_as(C.c_void_p), 0, C.byref(conf))
+    assert rc == 0, L.sz3b_last_error()
+    return out, conf
+
+
+def same_bits(a, b):
+    return np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+@pytest.mark.parametrize("writer", ["gpu", "ref"])
+@pytest.mark.parametrize("shape,dtype,kw", [
+    ((100, 70, 130), np.float32, dict(cmprAlgo=ALGO_INTERP_LORENZO, absErrorBound=1e-3)),
+    ((64, 80, 96), np.float64, dict(cmprAlgo=ALGO_INTERP, absErrorBound=1e-5, interpAlgo=0, interpDirection=5)),
+    ((33, 65, 97), np.float32, dict(cmprAlgo=ALGO_INTERP, absErrorBound=1e-2, interpAlgo=0, interpDirection=2)),
+    ((64, 64, 64), np.float32, dict(cmprAlgo=ALGO_INTERP, absErrorBound=1e-2, interpAlgo=1, interpDirection=3)),
+    ((12, 40, 40, 40), np.float32, dict(cmprAlgo=ALGO_INTERP_LORENZO, absErrorBound=1e-2)),
+    ((300, 500), np.float32, dict(cmprAlgo=ALGO_INTERP_LORENZO, absErrorBound=1e-3)),
+    ((5000,), np.float32, dict(cmprAlgo=ALGO_INTERP, absErrorBound=1e-3)),
+    ((8, 8, 128), np.float32, dict(cmprAlgo=ALGO_INTERP, absErrorBound=1e-3, interpAnchorStride=0)),
+    ((37, 41, 130), np.float32, dict(cmprAlgo=ALGO_INTERP, absErrorBound=1e-6, quantbinCnt=16)),
+    ((60, 66, 72), np.float64, dict(cmprAlgo=ALGO_LORENZO_REG, lorenzo=0, regression=1, errorBoundMode=EB_REL, relErrorBound=1e-4)),
+    ((40, 45), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, lorenzo=0, regression=1, absErrorBound=1e-3)),
+    ((48, 48, 48), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, lorenzo=0, regression=1, absErrorBound=1e-7)),
+])
+def test_decompress_bit_identical(shape, dtype, kw, writer):
+    data = field_nd(shape, dtype)
+    conf = make_config(shape, **kw)
+    cmp = gpu_compress(data, conf)[0] if writer == "gpu" else ref_compress(data, conf)
+    want, wconf = ref_decompress(cmp, data)
+    got, gconf = gpu_decompress(cmp, data)
+    assert same_bits(got, want), f"{int((got != want).sum())} elements differ"
+    assert np.max(np.abs(got.astype(np.float64) - data.astype(np.float64))) <= wconf.absErrorBound
+    assert gconf.cmprAlgo == wconf.cmprAlgo and gconf.absErrorBound == wconf.absErrorBound
+
+
+def test_decompress_to_device_pointer():
+    data = field_g3((96, 96, 96))
+    conf = make_config(data.shape, absErrorBound=1e-3)
+    cmp, _ = gpu_compress(data, conf)
+    want, _ = ref_decompress(cmp, data)
+    got, _ = gpu_decompress(cmp, data, device=True)
+    assert same_bits(got, want)
+
+
+def test_decompress_lossless_and_noise():
+    rng = np.random.default_rng(3)
+    data = rng.standard_normal((64, 64, 64)).astype(np.float32)
+    conf = make_config(data.shape, absErrorBound=1e-7)     # falls back to ALGO_LOSSLESS
+    for cmp in (gpu_compress(data, conf)[0], ref_compress(data, conf)):
+        got, gconf = gpu_decompress(cmp, data)
+        assert np.array_equal(got, data)
+
+
+@pytest.mark.parametrize("writer", ["gpu", "ref"])
+def test_decompress_omp_container(writer):
+    data = field_g3((100, 64, 64))
+    conf = make_config(data.shape, absErrorBound=1e-3, openmp=4 if writer == "gpu" else 1)
+    cmp = gpu_compress(data, conf)[0] if writer == "gpu" else ref_compress(data, conf)
+    want, _ = ref_decompress(cmp, data)
+    got, gconf = gpu_decompress(cmp, data)
+    assert same_bits(got, want)
+    assert np.max(np.abs(got - data)) <= 1e-3
+
+
+def test_decompress_special_values():
+    data = field_nd((40, 50, 70), np.float32)
+    data[3, 4, 5] = np.nan
+    data[10, 11, 12] = np.inf
+    data[20, 2, 7] = -np.inf
+    conf = make_config(data.shape, cmprAlgo=ALGO_INTERP, absErrorBound=1e-3)
+    cmp, _ = gpu_compress(data, conf)
+    want, _ = ref_decompress(cmp, data)
+    got, _ = gpu_decompress(cmp, data)
+    assert same_bits(got, want)
+
+
+def test_decompress_rejects_garbage():
+    L = product_lib()
+    junk = np.zeros(64, dtype=np.uint8)
+    out = np.empty(8, dtype=np.float32)
+    conf = Config()
+    rc = L.sz3b_decompress(0, junk.ctypes.data_as(C.c_char_p), C.c_size_t(junk.size), out.ctypes.data_as(C.c_void_p), 0, C.byref(conf))
+    assert rc == -1     # std::invalid_argument: magic number mismatch (sz.hpp:123-125)
+
+
+def test_g3_256_roundtrip_through_python_binding():
+    import sz3_b200
+    from sz3_b200 import sz, szConfig
+    data = field_g3((256, 256, 256))
+    conf = szConfig(*data.shape)
+    conf.absErrorBound = 1e-3
+    cmp, ratio = sz.compress(data, conf)
+    dec, dconf = sz.decompress(cmp, np.float32, data.shape)
+    assert np.max(np.abs(dec - data)) <= 1e-3
+    want, _ = ref_decompress(np.ascontiguousarray(cmp), data)
+    assert same_bits(dec, want)
