@@ -355,11 +355,14 @@ SZ_HD void row_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, c
         QT *qp_ = qb + pos0;
         T *up = ub + pos0;
         const uint32_t so_inc = dU * sU, go_inc = dU * gU, ho_inc = dU * hU, pos_inc = dU * pU;
+        // last pass: the original values stream in from global memory two rows ahead of their use
         T nxt = LAST ? *gp : static_cast<T>(0);
+        T nxt2 = LAST && rows > 1 ? gp[go_inc] : static_cast<T>(0);
         for (uint32_t r = rows; r > 0; r--) {
             const T orig = LAST ? nxt : nb[tS];
+            nxt = nxt2;
+            if (LAST && r > 2) nxt2 = gp[2 * go_inc];
             gp += go_inc;
-            if (LAST && r > 1) nxt = *gp;
             const T w1 = nb[0];
             const T w0 = ld0 ? nb[-static_cast<int>(hS)] : static_cast<T>(0);
             const T w2 = ld2 ? nb[hS] : static_cast<T>(0);
@@ -447,12 +450,25 @@ SZ_HD void line_fill(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, T
         const uint32_t g0 = m0 * s * static_cast<uint32_t>(A.sh.stride[0]), g1 = m1 * s * static_cast<uint32_t>(A.sh.stride[1]),
                        g2 = m2 * s;
         const T *dat = A.data + lg.gbase;
-        for (uint32_t it = tid; it < total; it += nt) {
-            const uint32_t r = fast_div(it, mg2);
-            const uint32_t e2 = it - r * E2;
-            const uint32_t e0 = fast_div(r, mg1);
-            const uint32_t e1 = r - e0 * E1;
-            sm[it] = dat[e0 * g0 + e1 * g1 + e2 * g2];
+        // four independent loads in flight per thread before the first shared-memory store
+        for (uint32_t it0 = tid; it0 < total; it0 += 4 * nt) {
+            T v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t it = it0 + k * nt;
+                if (it < total) {
+                    const uint32_t r = fast_div(it, mg2);
+                    const uint32_t e2 = it - r * E2;
+                    const uint32_t e0 = fast_div(r, mg1);
+                    const uint32_t e1 = r - e0 * E1;
+                    v[k] = dat[e0 * g0 + e1 * g1 + e2 * g2];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t it = it0 + k * nt;
+                if (it < total) sm[it] = v[k];
+            }
         }
     }
     ctx.sync();
@@ -465,12 +481,24 @@ SZ_HD void line_fill(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, T
         const uint32_t h0 = s * static_cast<uint32_t>(A.stride2[0]), h1 = s * static_cast<uint32_t>(A.stride2[1]), h2 = s;
         const uint32_t t2 = 2u / m2, t1 = (2u / m1) * lg.E[2], t0 = (2u / m0) * lg.E[2] * lg.E[1];
         const T *rc2 = A.recon2 + lg.g2base;
-        for (uint32_t it = tid; it < total; it += nt) {
-            const uint32_t r = fast_div(it, mg2);
-            const uint32_t c2 = it - r * C2;
-            const uint32_t c0 = fast_div(r, mg1);
-            const uint32_t c1 = r - c0 * C1;
-            sm[c0 * t0 + c1 * t1 + c2 * t2] = rc2[c0 * h0 + c1 * h1 + c2 * h2];
+        for (uint32_t it0 = tid; it0 < total; it0 += 4 * nt) {
+            T v[4];
+            uint32_t so[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t it = it0 + k * nt;
+                if (it < total) {
+                    const uint32_t r = fast_div(it, mg2);
+                    const uint32_t c2 = it - r * C2;
+                    const uint32_t c0 = fast_div(r, mg1);
+                    const uint32_t c1 = r - c0 * C1;
+                    so[k] = c0 * t0 + c1 * t1 + c2 * t2;
+                    v[k] = rc2[c0 * h0 + c1 * h1 + c2 * h2];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (it0 + k * nt < total) sm[so[k]] = v[k];
         }
     }
 }
