@@ -51,10 +51,16 @@ Workspace *workspace_acquire() {
     Workspace *ws = new Workspace();
     ws->device = dev;
     SZ3B_CUDA(cudaStreamCreateWithFlags(&ws->st, cudaStreamNonBlocking));
+    SZ3B_CUDA(cudaStreamCreateWithFlags(&ws->st_copy, cudaStreamNonBlocking));
+    SZ3B_CUDA(cudaEventCreateWithFlags(&ws->ev_copy, cudaEventDisableTiming));
     return ws;
 }
 
 void workspace_release(Workspace *ws) {
+    // a call that failed half-way may still have its background copy / kernels in flight on this workspace's buffers
+    if (ws->st_copy) cudaStreamSynchronize(ws->st_copy);
+    if (ws->st) cudaStreamSynchronize(ws->st);
+    cudaGetLastError();
     std::lock_guard<std::mutex> lk(g_pool_mu);
     g_pool.push_back(ws);
 }
@@ -71,6 +77,28 @@ static const T *to_device(Workspace &ws, const T *data, int loc, size_t num) {
     ws.stage_end(h, 0);
     return d;
 }
+
+// Pinned (page-locked, device-mapped) host input: returns the device alias of `data`, or nullptr.
+static const void *mapped_alias(const void *data) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, data) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) return nullptr;
+    return attr.devicePointer;
+}
+
+// Starts the H2D of the whole input on the copy stream and returns at once; ws.st waits for it via join_copy().
+template <class T>
+static const T *to_device_background(Workspace &ws, const T *data, size_t num) {
+    T *d = ws.data.as<T>(num);
+    SZ3B_CUDA(cudaMemcpyAsync(d, data, num * sizeof(T), cudaMemcpyHostToDevice, ws.st_copy));
+    ws.h2d_bytes += num * sizeof(T);
+    SZ3B_CUDA(cudaEventRecord(ws.ev_copy, ws.st_copy));
+    return d;
+}
+static void join_copy(Workspace &ws) { SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.ev_copy, 0)); }
 
 template <class T>
 void minmax_stage(Workspace &ws, const T *data, int loc, size_t num, double *mn, double *mx) {
@@ -774,7 +802,18 @@ static size_t dispatch_compress(Workspace &ws, sz3b_config &conf, const T *data,
     if (conf.cmprAlgo != SZ3B_ALGO_LOSSLESS) {
         try {
             if (conf.cmprAlgo == SZ3B_ALGO_INTERP_LORENZO) {
-                tune_interp<T>(ws, conf, dev());   // rewrites cmprAlgo to ALGO_INTERP (N >= 2)
+                const T *alias = (loc == SZ3B_HOST && !d_data) ? static_cast<const T *>(mapped_alias(data)) : nullptr;
+                if (alias) {
+                    // pinned host input: the tuner samples ~0.5 % of the array straight from host memory while the
+                    // bulk copy runs on its own stream
+                    double t0 = now_ms();
+                    d_data = to_device_background<T>(ws, data, num);
+                    tune_interp<T>(ws, conf, alias);
+                    join_copy(ws);
+                    ws.host_stage("tune_overlapped_with_h2d", now_ms() - t0);
+                } else {
+                    tune_interp<T>(ws, conf, dev());   // rewrites cmprAlgo to ALGO_INTERP (N >= 2)
+                }
             }
             if (conf.cmprAlgo == SZ3B_ALGO_INTERP) {
                 set_default_anchor(conf);

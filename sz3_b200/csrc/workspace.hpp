@@ -83,6 +83,8 @@ struct StageRecord {
 struct Workspace {
     int device = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st_copy = nullptr;   // bulk H2D of the input, so that sampling/tuning can overlap it
+    cudaEvent_t ev_copy = nullptr;
     // inputs / index stream
     DevBuf data, q, unpred_tmp, recon, hist, tables;
     // encoder
