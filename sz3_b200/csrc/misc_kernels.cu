@@ -210,4 +210,20 @@ template void launch_gather_cubes<double>(const double *, int, const uint32_t *,
 template void launch_widen<uint16_t>(const uint16_t *, uint64_t, int32_t *, cudaStream_t);
 template void launch_widen<uint32_t>(const uint32_t *, uint64_t, int32_t *, cudaStream_t);
 
+// Small upload without the copy engine: the source is pinned (device-mapped) host memory read by the SMs.  Used while
+// the bulk input copy owns the H2D engine, where a cudaMemcpyAsync would queue behind it.
+__global__ void __launch_bounds__(256) k_upload_bytes(unsigned char *__restrict__ dst, const unsigned char *__restrict__ src,
+                                                      size_t bytes) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t nvec = bytes / 16;
+    if (i < nvec) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    if (i < bytes - nvec * 16) dst[nvec * 16 + i] = src[nvec * 16 + i];
+}
+void launch_upload_bytes(void *dst, const void *src_mapped, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return;
+    const size_t n = bytes / 16 > 16 ? bytes / 16 : 16;
+    k_upload_bytes<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(static_cast<unsigned char *>(dst),
+                                                                          static_cast<const unsigned char *>(src_mapped), bytes);
+}
+
 }  // namespace sz3b

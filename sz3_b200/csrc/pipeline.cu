@@ -93,12 +93,20 @@ static const void *mapped_alias(const void *data) {
 template <class T>
 static const T *to_device_background(Workspace &ws, const T *data, size_t num) {
     T *d = ws.data.as<T>(num);
-    SZ3B_CUDA(cudaMemcpyAsync(d, data, num * sizeof(T), cudaMemcpyHostToDevice, ws.st_copy));
-    ws.h2d_bytes += num * sizeof(T);
+    // in pieces: the tuner's own small uploads share the H2D copy engine and can only slip in between commands
+    const size_t bytes = num * sizeof(T), piece = static_cast<size_t>(8) << 20;
+    for (size_t off = 0; off < bytes; off += piece)
+        SZ3B_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(d) + off, reinterpret_cast<const uint8_t *>(data) + off,
+                                  std::min(piece, bytes - off), cudaMemcpyHostToDevice, ws.st_copy));
+    ws.h2d_bytes += bytes;
     SZ3B_CUDA(cudaEventRecord(ws.ev_copy, ws.st_copy));
+    ws.bulk_copy_in_flight = true;
     return d;
 }
-static void join_copy(Workspace &ws) { SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.ev_copy, 0)); }
+static void join_copy(Workspace &ws) {
+    SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.ev_copy, 0));
+    ws.bulk_copy_in_flight = false;
+}
 
 template <class T>
 void minmax_stage(Workspace &ws, const T *data, int loc, size_t num, double *mn, double *mx) {

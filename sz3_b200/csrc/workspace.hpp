@@ -8,11 +8,15 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <string.h>
+
 #include <chrono>
 #include <string>
 #include <vector>
 
 namespace sz3b {
+
+void launch_upload_bytes(void *dst, const void *src_mapped, size_t bytes, cudaStream_t st);   // misc_kernels.cu
 
 struct CudaError {
     cudaError_t code;
@@ -116,9 +120,26 @@ struct Workspace {
     }
     // bytes moved across PCIe by the current call (reported by sz3b_last_transfer)
     size_t h2d_bytes = 0, d2h_bytes = 0;
+    // While the bulk input copy owns the H2D copy engine (bulk_copy_in_flight), small uploads go through a pinned
+    // staging arena read by an SM copy kernel instead of queueing behind it.
+    bool bulk_copy_in_flight = false;
+    PinBuf upload_arena;
+    size_t upload_used = 0;
+    static constexpr size_t kUploadArena = static_cast<size_t>(16) << 20;
     void h2d(void *dst, const void *src, size_t bytes) {
-        SZ3B_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
         h2d_bytes += bytes;
+        if (bulk_copy_in_flight && bytes <= (static_cast<size_t>(2) << 20)) {
+            const size_t need = (bytes + 255) & ~static_cast<size_t>(255);
+            unsigned char *arena = static_cast<unsigned char *>(upload_arena.ensure(kUploadArena));
+            if (upload_used + need <= kUploadArena && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                unsigned char *slot = arena + upload_used;
+                upload_used += need;
+                memcpy(slot, src, bytes);
+                launch_upload_bytes(dst, slot, bytes, st);
+                return;
+            }
+        }
+        SZ3B_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
     }
     void d2h(void *dst, const void *src, size_t bytes) {
         SZ3B_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
@@ -126,6 +147,8 @@ struct Workspace {
     }
     void prof_reset() {
         h2d_bytes = d2h_bytes = 0;
+        upload_used = 0;
+        bulk_copy_in_flight = false;
         prof.clear();
         pending.clear();
         ev_used = 0;
