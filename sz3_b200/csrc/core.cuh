@@ -54,7 +54,7 @@ SZ_HD int trunc_to_int(double v) {   // 0 <= v < 2^31
 #if defined(__CUDA_ARCH__)
     return __double2loint(__dadd_rz(v, 4503599627370496.0));   // 2^52: the integer part lands in the low word
 #else
-    return static_cast<int>(v);
+    return v < 2147483647.0 ? static_cast<int>(v) : 0;   // out of range / NaN: value unused by the caller
 #endif
 }
 SZ_HD double int_to_double(int q) {
@@ -69,33 +69,27 @@ SZ_HD double int_to_double(int q) {
 // leaves in the working array (the reconstruction, or the untouched original when unpredictable).
 template <class T>
 SZ_HD int quantize(T data, T pred, const QuantParams &qp, T &recon) {
-    T diff = data - pred;
-    double v = fabs(static_cast<double>(diff)) * qp.ebr;
-    if (v < qp.vmax) {  // NaN compares false -> unpredictable, as in the reference
-        int qi = trunc_to_int(v) + 1;
-        int half = qi >> 1;
-        int q2 = half << 1;
-        int shifted;
-        if (diff < 0) {
-            q2 = -q2;
-            shifted = qp.radius - half;
-        } else {
-            shifted = qp.radius + half;
-        }
-        T dec = static_cast<T>(static_cast<double>(pred) + int_to_double(q2) * qp.eb);
-        T err = static_cast<T>(fabs(dec - data));
-        bool ok;
-        if (sizeof(T) == 4)
-            ok = static_cast<float>(err) <= qp.ebf;
-        else
-            ok = static_cast<double>(err) <= qp.eb;
-        if (ok) {
-            recon = dec;
-            return shifted;
-        }
-    }
-    recon = data;
-    return 0;
+    // Straight-line form (selects instead of the reference's nested ifs): unpredictable points are rare, so nothing
+    // is wasted, and the hot loops keep no divergent region.  NaN / overflow make `inrange` false (comparisons with
+    // NaN are false) and whatever the arithmetic below produced is discarded.
+    const T diff = data - pred;
+    const double v = fabs(static_cast<double>(diff)) * qp.ebr;
+    const bool inrange = v < qp.vmax;
+    const int qi = trunc_to_int(v) + 1;   // garbage when !inrange (discarded)
+    const int half = qi >> 1;
+    const bool neg = diff < 0;
+    const int q2 = neg ? -(half << 1) : (half << 1);
+    const int shifted = neg ? qp.radius - half : qp.radius + half;
+    const T dec = static_cast<T>(static_cast<double>(pred) + int_to_double(q2) * qp.eb);
+    const T err = static_cast<T>(fabs(dec - data));
+    bool ok;
+    if (sizeof(T) == 4)
+        ok = static_cast<float>(err) <= qp.ebf;
+    else
+        ok = static_cast<double>(err) <= qp.eb;
+    ok = ok && inrange;
+    recon = ok ? dec : data;
+    return ok ? shifted : 0;
 }
 
 // recover (LinearQuantizer.hpp:74-86) for a predictable index.

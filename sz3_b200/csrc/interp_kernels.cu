@@ -86,7 +86,21 @@ __global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 2 : 1) k_interp
 // line-walker tile schedule (interp_line.cuh): two CTAs per SM; three lanes build the pass tables while the
 // rest of the CTA already fills shared memory
 template <class T, class QT>
+__device__ __forceinline__ void ltile_body(const InterpArgs<T, QT> &A);
+
+// Levels with fewer tiles than SMs (the coarsest ones) are pure latency: one CTA of 1024 threads per tile halves it.
+template <class T, class QT>
+__global__ void __launch_bounds__(1024, 1) k_interp_ltile_wide(InterpArgs<T, QT> A) {
+    ltile_body<T, QT>(A);
+}
+
+template <class T, class QT>
 __global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 2 : 1) k_interp_ltile(InterpArgs<T, QT> A) {
+    ltile_body<T, QT>(A);
+}
+
+template <class T, class QT>
+__device__ __forceinline__ void ltile_body(const InterpArgs<T, QT> &A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sm = reinterpret_cast<T *>(smem_raw);
     unsigned *shist = reinterpret_cast<unsigned *>(smem_raw + sizeof(T) * kTileSmemElems);
@@ -156,10 +170,14 @@ void interp_launch_ltiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t 
     const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
     if (!attr_set) {
         cudaFuncSetAttribute(k_interp_ltile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaFuncSetAttribute(k_interp_ltile_wide<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         attr_set = true;
     }
     dim3 grid(static_cast<unsigned>(ntiles), nbatch);
-    k_interp_ltile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
+    if (ntiles * nbatch <= 148 && sizeof(T) == 4)
+        k_interp_ltile_wide<T, QT><<<grid, 1024, smem, st>>>(A);
+    else
+        k_interp_ltile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
 }
 
 template <class T, class QT>

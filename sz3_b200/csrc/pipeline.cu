@@ -533,7 +533,9 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
         if (trial_out.size() < need) trial_out.resize(need);
     }
     auto trial = [&](const sz3b_config &tc) -> double {
+        ws.stage_prefix = "tune_";
         size_t sz = interp_compress<T>(ws, tc, d_cubes, ncubes, trial_out.data(), trial_out.size(), 1, true);
+        ws.stage_prefix.clear();
         return per_block * static_cast<double>(ncubes) * sizeof(T) * 1.0 / sz;
     };
     double best_interp = 0, best_lorenzo = 0, ratio;

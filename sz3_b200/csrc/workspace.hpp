@@ -149,14 +149,16 @@ struct Workspace {
         h2d_bytes = d2h_bytes = 0;
         upload_used = 0;
         bulk_copy_in_flight = false;
+        stage_prefix.clear();
         prof.clear();
         pending.clear();
         ev_used = 0;
     }
     // device stage: records events around the enclosed launches
+    std::string stage_prefix;   // "tune_" while the auto-tuner's trial compressions run
     size_t stage_begin(const char *name) {
         StageRecord r;
-        r.name = name;
+        r.name = stage_prefix.empty() || !strncmp(name, "tune_", 5) ? std::string(name) : stage_prefix + name;
         prof.push_back(r);
         Pending pd;
         pd.rec = prof.size() - 1;
@@ -172,7 +174,7 @@ struct Workspace {
     }
     void host_stage(const char *name, double ms) {
         StageRecord r;
-        r.name = name;
+        r.name = stage_prefix.empty() || !strncmp(name, "tune_", 5) ? std::string(name) : stage_prefix + name;
         r.ms = ms;
         r.host = true;
         prof.push_back(r);
