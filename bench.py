@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--edge", type=int, default=EDGE, help="cube edge (default 512 = the metric's configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lossless-policy", type=int, default=None, help="0 = zstd on every chunk, 1 = adaptive (library default)")
     return ap.parse_args()
 
 
@@ -226,6 +227,8 @@ def run_ours(args):
     if L is None:
         raise SystemExit("bench.py: sz3_b200/lib/libsz3b200.so missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
     L.sz3b_last_error.restype = C.c_char_p
+    if args.lossless_policy is not None:
+        L.sz3b_set_lossless_policy(args.lossless_policy)
     edge = args.edge
     nbytes = edge ** 3 * 4
     host = slab_field(rank, edge)
@@ -326,12 +329,13 @@ def run_ours(args):
             "config": {"workload": f"3D float32 {edge}x{edge}x{edge} per GPU, ALGO_INTERP_LORENZO abs-eb 1e-3"
                                    + (f", slab-sharded over {world} GPUs (OpenMP container)" if world > 1 else ""),
                        "field": "G3 (SURVEY.md 8d), seeded", "l2": "input 512 MiB per step > 126 MB L2 (no explicit flush)",
+                       "lossless_policy": {0: "zstd-3 on every chunk", 1: "adaptive: zstd-3 probes, raw zstd frames where zstd gains < 1 % (include/sz3b.h)"}[L.sz3b_get_lossless_policy()],
                        "value_path": "sz3b_compress, device-resident input, stream delivered to host",
                        "e2e_path": "sz3b_compress, pinned host input (H2D + D2H inside the timed region)"},
             "e2e": {"value": e2e, "unit": "GB/s", "h2d_bytes_per_step": h2d.value, "d2h_bytes_per_step": d2h.value,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "predict_quantize (k_interp_anchor + k_interp_tile x levels)",
+            "roofline": {"bound": "hbm", "kernel": "predict_quantize (k_interp_anchor + k_interp_ltile x 5 levels)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "algorithmic_bytes": alg_bytes,
                          "ms_per_step": pq_avg_ms},

@@ -95,6 +95,8 @@ int sz3b_device_count(void) {
 }
 
 void sz3b_set_host_threads(int n) { set_host_threads(n); }
+void sz3b_set_lossless_policy(int policy) { set_lossless_policy(policy); }
+int sz3b_get_lossless_policy(void) { return lossless_policy(); }
 
 int sz3b_config_init(sz3b_config *c, int ndims, const size_t *dims) {
     return guarded([&] {

@@ -369,7 +369,8 @@ static size_t zstd_stage(Workspace &ws, const uint8_t *src, size_t len, uint8_t 
                          ZstdReady *gate) {
     double t0 = now_ms();
     bool small = false;
-    size_t r = zstd_compress_framed(src, len, dst, cap, threads, &small, gate, &ws.zscratch);
+    // gate != nullptr <=> the source is a packed (Huffman-coded) stream, not raw data
+    size_t r = zstd_compress_framed(src, len, dst, cap, threads, &small, gate, &ws.zscratch, gate != nullptr);
     SZ3B_CUDA(cudaStreamSynchronize(ws.st));
     ws.host_stage("zstd_host", now_ms() - t0);
     if (small) throw TooSmall{};

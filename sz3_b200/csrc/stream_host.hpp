@@ -50,8 +50,13 @@ struct ZstdReady {
     virtual void wait(size_t upto) = 0;
     virtual ~ZstdReady() {}
 };
+// `allow_raw`: the stream is entropy-coded already (post-Huffman), so the adaptive policy may store chunks as raw
+// zstd frames when zstd gains < 1 % on sampled chunks (lossless_policy() == 1, the default; 0 = always compress).
 size_t zstd_compress_framed(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, int threads,
-                            bool *too_small, ZstdReady *ready = nullptr, std::vector<uint8_t> *scratch = nullptr);
+                            bool *too_small, ZstdReady *ready = nullptr, std::vector<uint8_t> *scratch = nullptr,
+                            bool allow_raw = false);
+void set_lossless_policy(int p);
+int lossless_policy();
 
 // Persistent host worker threads of the host tail (zstd chunks, frame concatenation).
 void host_parallel(int nworkers, void (*fn)(void *arg, int worker), void *arg);

@@ -128,3 +128,28 @@ def test_capacity_check():
     size = C.c_size_t(0)
     rc = L.sz3b_compress(0, C.byref(conf), data.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_char_p), C.c_size_t(64), C.byref(size), None)
     assert rc == -1  # std::invalid_argument in the reference (sz.hpp:47-49)
+
+
+@needs_ref
+def test_lossless_policy_adaptive_vs_full():
+    """Adaptive raw-frame policy of the host tail (include/sz3b.h: sz3b_set_lossless_policy): both policies give streams
+    the unmodified reference decoder reads, identical reconstructions, and ratios within 1 % of each other and of
+    the reference."""
+    L = product_lib()
+    data = field_g3((384, 384, 384))
+    conf = make_config(data.shape, absErrorBound=1e-3)
+    theirs = ref_compress(data, conf)
+    out = {}
+    try:
+        for pol in (0, 1):
+            L.sz3b_set_lossless_policy(pol)
+            out[pol], _ = gpu_compress(data, conf)
+    finally:
+        L.sz3b_set_lossless_policy(1)
+    dec0, _ = ref_decompress(out[0], data)
+    dec1, _ = ref_decompress(out[1], data)
+    assert np.array_equal(dec0, dec1)
+    assert np.max(np.abs(dec1 - data)) <= 1e-3
+    r_ref, r0, r1 = (data.nbytes / x.size for x in (theirs, out[0], out[1]))
+    assert abs(r0 - r_ref) / r_ref < 0.01 and abs(r1 - r_ref) / r_ref < 0.01, (r_ref, r0, r1)
+    assert out[1].size >= out[0].size
