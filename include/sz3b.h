@@ -138,11 +138,11 @@ void sz3b_last_transfer(size_t *h2d_bytes, size_t *d2h_bytes);
 /* zstd worker threads for the host tail (0 = hardware concurrency). */
 void sz3b_set_host_threads(int n);
 /* Lossless stage over the packed (Huffman-coded) stream, lossless/Lossless_zstd.hpp:29-37.
- *   0 = every chunk through zstd level 3 (the reference's behaviour, frame by frame);
- *   1 = adaptive (default): every 8th 1-MiB chunk is compressed as a probe; if zstd gains < 1 % on the probes, the other
- *       chunks are stored as raw zstd frames.  Costs at most 0.875 % of ratio, saves 7/8 of the host time on
- *       entropy-coded streams of noisy data.  Either way the result is a concatenation of standard zstd frames that
- *       the unmodified reference decoder (one ZSTD_decompress call) reads. */
+ *   0 = (default) every chunk through zstd level 3 (the reference's behaviour, frame by frame);
+ *   1 = adaptive: every 8th 1-MiB chunk is compressed as a probe; if zstd gains < 1 % on the probes, the other chunks
+ *       are stored as raw zstd frames (at most 0.875 % of ratio for 7/8 of the host time; pays off on entropy-coded
+ *       streams of very noisy data -- on BASELINE's 512^3 case zstd gains 1.1 %, so the probes keep zstd on).
+ *   Either way the result is a concatenation of standard zstd frames that the unmodified reference decoder reads. */
 void sz3b_set_lossless_policy(int policy);
 int sz3b_get_lossless_policy(void);
 

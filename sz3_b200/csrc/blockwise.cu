@@ -165,10 +165,113 @@ __global__ void __launch_bounds__(32 * (kMaxDim + 1)) k_reg_chain_spec(const T *
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Same speculation over super-windows of kSW blocks, so that the only serial work per block is the one dependent add:
+// lanes own interleaved blocks (i = j*32 + lane), guess all lattice indices, one lane rebuilds the running values
+// from shared memory back to back, then all lanes verify their blocks and the prefix up to the first disagreement is
+// committed with the real quantizer results.
+constexpr int kSW = 512;
+constexpr int kSWPer = kSW / 32;
+
+template <class T>
+__global__ void __launch_bounds__(32 * (kMaxDim + 1)) k_reg_chain_spec2(const T *__restrict__ c_fit, uint64_t nblocks, int N,
+                                                                        QuantParams q_liner, QuantParams q_indep,
+                                                                        int32_t *__restrict__ coef_q, T *__restrict__ c_rec,
+                                                                        unsigned long long *__restrict__ n_sel_out,
+                                                                        unsigned long long *__restrict__ n_unpred,
+                                                                        unsigned long long *__restrict__ unpred_pos,
+                                                                        T *__restrict__ unpred_val) {
+    __shared__ double s_d[kMaxDim + 1][kSW];
+    __shared__ T s_r[kMaxDim + 1][kSW + 1];
+    __shared__ T s_last[kMaxDim + 1];
+    const int d = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nc = N + 1;
+    if (d >= nc) return;
+    const QuantParams qp = d < N ? q_liner : q_indep;
+    const unsigned full = 0xffffffffu;
+    double *sd = s_d[d];
+    T *sr = s_r[d];
+    T r_cur = 0;
+    uint64_t b0 = 0;
+    while (b0 < nblocks) {
+        const unsigned n_in = nblocks - b0 < kSW ? static_cast<unsigned>(nblocks - b0) : kSW;
+        T c[kSWPer];
+        int dk[kSWPer];
+        bool sane_all = true;
+        // 1. lattice indices relative to r_cur, steps between consecutive blocks
+        int Kprev_row = 0;   // K of block (j-1)*32 + 31
+#pragma unroll
+        for (int j = 0; j < kSWPer; j++) {
+            const unsigned i = j * 32 + lane;
+            c[j] = i < n_in ? c_fit[(b0 + i) * nc + d] : static_cast<T>(0);
+            const T df = c[j] - r_cur;
+            const double v = fabs(static_cast<double>(df)) * qp.ebr;
+            const bool sane = v < 1.0e9;
+            sane_all = sane_all && (sane || i >= n_in);
+            const int half = sane ? (trunc_to_int(v) + 1) >> 1 : 0;
+            const int K = df < 0 ? -half : half;
+            const int up = __shfl_up_sync(full, K, 1);
+            const int Kp = lane ? up : Kprev_row;
+            Kprev_row = __shfl_sync(full, K, 31);
+            dk[j] = K - Kp;
+            sd[i] = int_to_double(2 * dk[j]) * qp.eb;
+        }
+        __syncwarp();
+        // 2. the serial part: one dependent add per block
+        if (lane == 0) {
+            T r = r_cur;
+            sr[0] = r;
+            for (unsigned i = 0; i < n_in; i++) {
+                r = static_cast<T>(static_cast<double>(r) + sd[i]);
+                sr[i + 1] = r;
+            }
+        }
+        __syncwarp();
+        // 3. verify every block against its speculated predecessor
+        unsigned first_bad = kSW;
+        int qv[kSWPer];
+        T rec[kSWPer];
+#pragma unroll
+        for (int j = 0; j < kSWPer; j++) {
+            const unsigned i = j * 32 + lane;
+            qv[j] = 0;
+            rec[j] = 0;
+            if (i < n_in) {
+                qv[j] = quantize<T>(c[j], sr[i], qp, rec[j]);
+                const bool ok = sane_all && qv[j] != 0 && qv[j] == qp.radius + dk[j];
+                if (!ok && i < first_bad) first_bad = i;
+            }
+        }
+        first_bad = __reduce_min_sync(full, first_bad);
+        const unsigned n_acc = first_bad + 1 < n_in ? first_bad + 1 : n_in;
+#pragma unroll
+        for (int j = 0; j < kSWPer; j++) {
+            const unsigned i = j * 32 + lane;
+            if (i < n_acc) {
+                const uint64_t pos = (b0 + i) * nc + d;
+                coef_q[pos] = qv[j];
+                c_rec[pos] = rec[j];
+                if (qv[j] == 0) {
+                    const unsigned long long slot = atomicAdd(n_unpred, 1ull);
+                    unpred_pos[slot] = pos;
+                    unpred_val[slot] = c[j];
+                }
+                if (i + 1 == n_acc) s_last[d] = rec[j];
+            }
+        }
+        __syncwarp();
+        r_cur = s_last[d];
+        b0 += n_acc;
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) *n_sel_out = nblocks;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // One CTA = one chunk of kRegChunk consecutive elements of one row (a row = all coordinates but the fastest fixed).
 // Row coordinates come from the grid indices, so no thread ever divides a 64-bit element index.
 constexpr int kRegThreads = 128;
 constexpr int kRegChunk = 512;
+constexpr int kRegRows = 16;   // consecutive rows (along the second-fastest dim) per CTA: amortises the histogram window
 
 template <class T, class QT>
 __global__ void __launch_bounds__(kRegThreads) k_reg_predict(const T *__restrict__ data, BlockShape bs, uint32_t nchunks,
@@ -180,39 +283,44 @@ __global__ void __launch_bounds__(kRegThreads) k_reg_predict(const T *__restrict
     ctx.clear();
     const int N = bs.N;
     uint32_t xr[kMaxDim] = {0, 0, 0, 0};
-    uint32_t chunk = blockIdx.x;
+    uint32_t chunk = blockIdx.x, row0 = 0, nrows = 1;
     if (N >= 2) {
-        xr[N - 2] = blockIdx.x / nchunks;
-        chunk = blockIdx.x - xr[N - 2] * nchunks;
+        const uint32_t rg = blockIdx.x / nchunks;
+        chunk = blockIdx.x - rg * nchunks;
+        row0 = rg * kRegRows;
+        nrows = bs.dims[N - 2] - row0 < static_cast<uint32_t>(kRegRows) ? bs.dims[N - 2] - row0 : kRegRows;
     }
     if (N >= 3) xr[N - 3] = blockIdx.y;
     if (N >= 4) xr[N - 4] = blockIdx.z;
-    RegRow rr;
-    reg_row_setup(bs, xr, rr);
-    uint64_t row_off = 0;
-    for (int d = 0; d < N - 1; d++) row_off += xr[d] * bs.stride[d];
     const uint32_t len = bs.dims[N - 1];
     const uint32_t x0 = chunk * kRegChunk;
     const int nc = N + 1;
+    for (uint32_t r = 0; r < nrows; r++) {
+        if (N >= 2) xr[N - 2] = row0 + r;
+        RegRow rr;
+        reg_row_setup(bs, xr, rr);
+        uint64_t row_off = 0;
+        for (int d = 0; d < N - 1; d++) row_off += xr[d] * bs.stride[d];
 #pragma unroll
-    for (int k = 0; k < kRegChunk / kRegThreads; k++) {
-        const uint32_t x = x0 + k * kRegThreads + threadIdx.x;
-        const bool active = x < len;
-        int qv = 0;
-        if (active) {
-            uint64_t blin, pos;
-            uint32_t li[kMaxDim] = {rr.li[0], rr.li[1], rr.li[2], rr.li[3]};
-            reg_row_locate(bs, rr, x, mgB, &blin, &li[N - 1], &pos);
-            const T pred = reg_predict<T>(N, c_rec + blin * nc, li);
-            const T orig = data[row_off + x];
-            T rec;
-            qv = quantize<T>(orig, pred, qp, rec);
-            q[pos] = static_cast<QT>(qv);
-            if (qv == 0) unpred_tmp[pos] = orig;
+        for (int k = 0; k < kRegChunk / kRegThreads; k++) {
+            const uint32_t x = x0 + k * kRegThreads + threadIdx.x;
+            const bool active = x < len;
+            int qv = 0;
+            if (active) {
+                uint64_t blin, pos;
+                uint32_t li[kMaxDim] = {rr.li[0], rr.li[1], rr.li[2], rr.li[3]};
+                reg_row_locate(bs, rr, x, mgB, &blin, &li[N - 1], &pos);
+                const T pred = reg_predict<T>(N, c_rec + blin * nc, li);
+                const T orig = data[row_off + x];
+                T rec;
+                qv = quantize<T>(orig, pred, qp, rec);
+                q[pos] = static_cast<QT>(qv);
+                if (qv == 0) unpred_tmp[pos] = orig;
+            }
+            ctx.hist_add(qv, active);
         }
-        ctx.hist_add(qv, active);
     }
-    ctx.pass_end();
+    ctx.pass_end();   // at most kRegRows * kRegChunk / kRegThreads = 64 points per thread: the 8-bit counters hold
     ctx.flush();
 }
 
@@ -227,8 +335,8 @@ void launch_reg_chain(const T *c_fit, const uint8_t *sel, uint64_t nblocks, int 
                       const QuantParams &q_indep, int32_t *coef_q, T *c_rec, unsigned long long *counters,
                       unsigned long long *unpred_pos, T *unpred_val, cudaStream_t st) {
     if (sel == nullptr)   // dense: every block selected
-        k_reg_chain_spec<T><<<1, 32 * (N + 1), 0, st>>>(c_fit, nblocks, N, q_liner, q_indep, coef_q, c_rec, counters,
-                                                       counters + 1, unpred_pos, unpred_val);
+        k_reg_chain_spec2<T><<<1, 32 * (N + 1), 0, st>>>(c_fit, nblocks, N, q_liner, q_indep, coef_q, c_rec, counters,
+                                                        counters + 1, unpred_pos, unpred_val);
     else
         k_reg_chain<T><<<1, 32, 0, st>>>(c_fit, sel, nblocks, N, q_liner, q_indep, coef_q, c_rec, counters, counters + 1,
                                         unpred_pos, unpred_val);
@@ -239,7 +347,7 @@ const char *launch_reg_predict(const T *data, const BlockShape &bs, const T *c_r
     const int N = bs.N;
     const uint32_t len = bs.dims[N - 1];
     const uint32_t nchunks = (len + kRegChunk - 1) / kRegChunk;
-    const uint64_t gx = static_cast<uint64_t>(nchunks) * (N >= 2 ? bs.dims[N - 2] : 1);
+    const uint64_t gx = static_cast<uint64_t>(nchunks) * (N >= 2 ? (bs.dims[N - 2] + kRegRows - 1) / kRegRows : 1);
     const uint32_t gy = N >= 3 ? bs.dims[N - 3] : 1, gz = N >= 4 ? bs.dims[N - 4] : 1;
     if (gx > 0x7fffffffull || gy > 65535u || gz > 65535u) return "array shape exceeds the launch grid of the regression kernel";
     // multiply-high division by B is exact while x * B < 2^32

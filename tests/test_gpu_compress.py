@@ -145,7 +145,7 @@ def test_lossless_policy_adaptive_vs_full():
             L.sz3b_set_lossless_policy(pol)
             out[pol], _ = gpu_compress(data, conf)
     finally:
-        L.sz3b_set_lossless_policy(1)
+        L.sz3b_set_lossless_policy(0)
     dec0, _ = ref_decompress(out[0], data)
     dec1, _ = ref_decompress(out[1], data)
     assert np.array_equal(dec0, dec1)
