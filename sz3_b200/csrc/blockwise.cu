@@ -220,9 +220,17 @@ __global__ void __launch_bounds__(32 * (kMaxDim + 1)) k_reg_chain_spec2(const T 
         if (lane == 0) {
             T r = r_cur;
             sr[0] = r;
-            for (unsigned i = 0; i < n_in; i++) {
-                r = static_cast<T>(static_cast<double>(r) + sd[i]);
-                sr[i + 1] = r;
+            // batches of 8: the shared-memory loads of a batch are issued together, so the loop runs at the
+            // latency of the dependent adds (entries beyond n_in are unused garbage)
+            for (unsigned i0 = 0; i0 < n_in; i0 += 8) {
+                double dv[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) dv[k] = sd[i0 + k];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    r = static_cast<T>(static_cast<double>(r) + dv[k]);
+                    sr[i0 + k + 1] = r;
+                }
             }
         }
         __syncwarp();

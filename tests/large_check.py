@@ -1,0 +1,71 @@
+"""Manual large-shape check (not collected by pytest): one slab of BASELINE config #5 (256 x 2048 x 2048 float32, 4 GiB,
+generated on the device), compressed with a device pointer, decompressed by this library on the GPU, bound checked on
+the GPU; optionally (--ref) the stream is also decoded by the unmodified reference and compared bit for bit.
+usage: python tests/large_check.py [--ref] [d0 d1 d2]"""
+import ctypes as C
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, "tests")
+sys.path.insert(0, ".")
+from common import Config, make_config, product_lib, ref_lib  # noqa: E402
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+shape = tuple(int(a) for a in args) if args else (256, 2048, 2048)
+use_ref = "--ref" in sys.argv
+dev = torch.device("cuda")
+z = torch.arange(shape[0], device=dev, dtype=torch.float32)[:, None, None]
+y = torch.arange(shape[1], device=dev, dtype=torch.float32)[None, :, None]
+x = torch.arange(shape[2], device=dev, dtype=torch.float32)[None, None, :]
+tp = 2 * np.pi
+data = torch.sin(tp * x / 64) * torch.cos(tp * y / 96) + 0.5 * torch.sin(tp * z / 128 + 0.3) + 0.25 * torch.sin(tp * (x + y + z) / 37)
+gen = torch.Generator(device=dev)
+gen.manual_seed(1234)
+data += 0.002 * torch.randn(shape, device=dev, generator=gen)
+data = data.contiguous()
+torch.cuda.synchronize()
+L = product_lib()
+L.sz3b_last_error.restype = C.c_char_p
+conf = make_config(shape, absErrorBound=1e-3)
+cap = L.sz3b_compress_bound(0, C.byref(conf))
+out = torch.empty(cap, dtype=torch.uint8).pin_memory().numpy()
+size = C.c_size_t(0)
+used = Config()
+for it in range(2):
+    t0 = time.perf_counter()
+    rc = L.sz3b_compress(0, C.byref(conf), C.c_void_p(data.data_ptr()), 1, out.ctypes.data_as(C.c_char_p), C.c_size_t(cap), C.byref(size), C.byref(used))
+    dt = time.perf_counter() - t0
+    assert rc == 0, L.sz3b_last_error()
+nbytes = data.numel() * 4
+print(f"compress {shape}: {dt*1e3:.1f} ms, {nbytes/dt/1e9:.1f} GB/s device-resident, ratio {nbytes/size.value:.3f}, algo {used.cmprAlgo}, "
+      f"interp {used.interpAlgo} dir {used.interpDirection} alpha {used.interpAlpha}", flush=True)
+names, ms, launches = (C.c_char_p * 64)(), (C.c_double * 64)(), (C.c_int * 64)()
+n = L.sz3b_last_profile(names, ms, launches, 64)
+acc = {}
+for i in range(n):
+    acc[names[i].decode()] = acc.get(names[i].decode(), 0) + ms[i]
+print({k: round(v, 2) for k, v in acc.items()}, flush=True)
+dec = torch.empty_like(data)
+dconf = Config()
+t0 = time.perf_counter()
+rc = L.sz3b_decompress(0, out.ctypes.data_as(C.c_char_p), C.c_size_t(size.value), C.c_void_p(dec.data_ptr()), 1, C.byref(dconf))
+dt = time.perf_counter() - t0
+assert rc == 0, L.sz3b_last_error()
+err = float((dec.double() - data.double()).abs().max())
+print(f"decompress: {dt*1e3:.1f} ms, max abs error {err:.3e} (bound 1e-3)", flush=True)
+assert err <= 1e-3
+if use_ref:
+    R = ref_lib()
+    host = np.empty(shape, np.float32)
+    rconf = Config()
+    t0 = time.perf_counter()
+    rc = R.ref_decompress(0, out.ctypes.data_as(C.c_char_p), C.c_size_t(size.value), host.ctypes.data_as(C.c_void_p), C.byref(rconf))
+    print(f"reference decoder: rc {rc}, {time.perf_counter()-t0:.1f} s", flush=True)
+    assert rc == 0
+    same = np.array_equal(host.view(np.uint32), dec.cpu().numpy().view(np.uint32))
+    print("bit-identical to the reference decoder:", same)
+    assert same
+print("ok")
