@@ -1,0 +1,165 @@
+// sz3_b200/csrc/huffman_decode.cu -- GPU decoder for the reference's Huffman bitstream (HuffmanEncoder::decode,
+// reference include/SZ3/encoder/HuffmanEncoder.hpp:225-255): MSB-first concatenated codes, no restart markers.
+//
+// The stream is cut into subsequences of kSubBits bits, one thread each.  Where a subsequence's first codeword starts
+// is unknown, but prefix codes self-synchronise: a decoder started at a wrong bit offset falls onto true codeword
+// boundaries after a few symbols.  So (after Weissenberger & Schmidt, ICPP 2018, restated for this format):
+//
+//   k_hd_sync   thread i decodes from (i*kSubBits + over_in[i-1]) to the first codeword boundary at or past
+//               (i+1)*kSubBits and publishes that overshoot and its symbol count.  Iterated with ping-pong overshoot
+//               arrays until no overshoot changes: then every start is the true boundary (thread 0's start is exact,
+//               and a thread whose start is exact publishes an exact overshoot -- induction over i; the loop ends
+//               only at a fixed point, which is therefore the true one).  2-3 iterations in practice.
+//   (scan)      exclusive prefix sum of the symbol counts -> output offsets (encode_kernels.cu: k_pack_scan)
+//   k_hd_write  same decode, symbols written at their offsets, clipped to the stream's symbol count.
+//
+// Codes are resolved with a first-level table of kLutBits bits in shared memory (entry = length << 24 | node); longer
+// codes continue down the tree arrays in global memory.
+#include <cuda_runtime.h>
+
+#include "launch.hpp"
+
+namespace sz3b {
+
+constexpr int kSubBits = 1024;
+constexpr int kHdThreads = 256;
+constexpr int kHdLutBits = 12;
+
+struct HdTables {
+    const uint32_t *lut;     // 1 << kHdLutBits entries
+    const uint32_t *L, *R;   // tree links (node count entries)
+    const int *C;            // symbol (state) per node
+    const uint8_t *leaf;
+    int offset;              // HuffmanEncoder::offset
+};
+
+// MSB-first bit reader over big-endian 32-bit words (the stream is copied to a 4-byte aligned, zero-padded buffer)
+struct BitReader {
+    const uint32_t *words;
+    uint64_t acc;      // next bits, left aligned
+    int have;          // valid bits in acc
+    uint64_t next_w;   // next word index to load
+    __device__ __forceinline__ void init(const uint32_t *w, uint64_t bitpos) {
+        words = w;
+        next_w = bitpos >> 5;
+        const unsigned sh = static_cast<unsigned>(bitpos & 31);
+        const uint64_t w0 = __byte_perm(words[next_w], 0, 0x0123), w1 = __byte_perm(words[next_w + 1], 0, 0x0123);
+        acc = ((w0 << 32) | w1) << sh;
+        have = 64 - static_cast<int>(sh);
+        next_w += 2;
+    }
+    __device__ __forceinline__ void refill() {
+        if (have <= 32) {
+            const uint64_t w = __byte_perm(words[next_w++], 0, 0x0123);
+            acc |= w << (32 - have);
+            have += 32;
+        }
+    }
+    __device__ __forceinline__ void skip(int n) {
+        acc <<= n;
+        have -= n;
+    }
+};
+
+// decodes one symbol; returns its node (leaf) and advances the reader; *len_out = code length
+__device__ __forceinline__ uint32_t hd_symbol(BitReader &br, const uint32_t *slut, const HdTables &t, int *len_out) {
+    br.refill();
+    const uint32_t e = slut[br.acc >> (64 - kHdLutBits)];
+    uint32_t len = e >> 24, node = e & 0xffffffu;
+    if (len) {
+        br.skip(static_cast<int>(len));
+    } else {   // code longer than the table: walk on bit by bit
+        br.skip(kHdLutBits);
+        len = kHdLutBits;
+        for (;;) {
+            br.refill();
+            node = (br.acc >> 63) ? t.R[node] : t.L[node];
+            br.skip(1);
+            len++;
+            if (t.leaf[node] || len >= 96) break;
+        }
+    }
+    *len_out = static_cast<int>(len);
+    return node;
+}
+
+__global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restrict__ words, uint64_t total_bits, uint64_t nsub,
+                                                       HdTables t, const uint8_t *__restrict__ over_in,
+                                                       uint8_t *__restrict__ over_out, unsigned *__restrict__ counts,
+                                                       unsigned *__restrict__ changed) {
+    __shared__ uint32_t slut[1 << kHdLutBits];
+    for (int k = threadIdx.x; k < (1 << kHdLutBits); k += blockDim.x) slut[k] = t.lut[k];
+    __syncthreads();
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nsub) return;
+    uint64_t pos = i * kSubBits + (i ? over_in[i - 1] : 0);
+    uint64_t limit = (i + 1) * kSubBits;
+    if (limit > total_bits) limit = total_bits;
+    unsigned cnt = 0;
+    if (pos < limit) {
+        BitReader br;
+        br.init(words, pos);
+        while (pos < limit) {
+            int len;
+            hd_symbol(br, slut, t, &len);
+            pos += len;
+            cnt++;
+        }
+    }
+    const uint64_t over = pos > (i + 1) * kSubBits ? pos - (i + 1) * kSubBits : 0;
+    const uint8_t o = static_cast<uint8_t>(over > 255 ? 255 : over);
+    counts[i] = cnt;
+    over_out[i] = o;
+    if (o != over_in[i]) *changed = 1u;   // thread i+1 started from over_in[i] in this round
+}
+
+template <class QT>
+__global__ void __launch_bounds__(kHdThreads) k_hd_write(const uint32_t *__restrict__ words, uint64_t total_bits, uint64_t nsub,
+                                                        HdTables t, const uint8_t *__restrict__ over,
+                                                        const unsigned long long *__restrict__ offs, uint64_t n,
+                                                        QT *__restrict__ out) {
+    __shared__ uint32_t slut[1 << kHdLutBits];
+    for (int k = threadIdx.x; k < (1 << kHdLutBits); k += blockDim.x) slut[k] = t.lut[k];
+    __syncthreads();
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nsub) return;
+    uint64_t pos = i * kSubBits + (i ? over[i - 1] : 0);
+    uint64_t limit = (i + 1) * kSubBits;
+    if (limit > total_bits) limit = total_bits;
+    uint64_t o = offs[i];
+    if (pos >= limit) return;
+    BitReader br;
+    br.init(words, pos);
+    while (pos < limit && o < n) {
+        int len;
+        const uint32_t node = hd_symbol(br, slut, t, &len);
+        out[o++] = static_cast<QT>(t.C[node] + t.offset);
+        pos += len;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+uint64_t hd_num_sub(uint64_t total_bits) { return (total_bits + kSubBits - 1) / kSubBits; }
+
+void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over_in,
+                    uint8_t *over_out, unsigned *counts, unsigned *changed, cudaStream_t st) {
+    const uint64_t nsub = hd_num_sub(total_bits);
+    HdTables t{tb.lut, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
+    k_hd_sync<<<static_cast<unsigned>((nsub + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, total_bits, nsub, t, over_in,
+                                                                                             over_out, counts, changed);
+}
+
+template <class QT>
+void launch_hd_write(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over,
+                     const unsigned long long *offs, uint64_t n, QT *out, cudaStream_t st) {
+    const uint64_t nsub = hd_num_sub(total_bits);
+    HdTables t{tb.lut, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
+    k_hd_write<QT><<<static_cast<unsigned>((nsub + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, total_bits, nsub, t, over,
+                                                                                                  offs, n, out);
+}
+template void launch_hd_write<uint16_t>(const uint32_t *, uint64_t, const HdDeviceTables &, const uint8_t *,
+                                        const unsigned long long *, uint64_t, uint16_t *, cudaStream_t);
+template void launch_hd_write<uint32_t>(const uint32_t *, uint64_t, const HdDeviceTables &, const uint8_t *,
+                                        const unsigned long long *, uint64_t, uint32_t *, cudaStream_t);
+
+}  // namespace sz3b

@@ -69,6 +69,21 @@ const char *launch_reg_recover(T *out, const BlockShape &bs, const T *c_rec, con
 void launch_scan_chunks(const unsigned *chunk_bits, const unsigned *chunk_zeros, uint64_t nchunks, unsigned long long *bit_off,
                         unsigned long long *zero_off, cudaStream_t st);   // encode_kernels.cu (k_pack_scan)
 
+// huffman_decode.cu
+struct HdDeviceTables {
+    const uint32_t *lut;
+    const uint32_t *L, *R;
+    const int *C;
+    const uint8_t *leaf;
+    int offset;
+};
+uint64_t hd_num_sub(uint64_t total_bits);
+void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over_in,
+                    uint8_t *over_out, unsigned *counts, unsigned *changed, cudaStream_t st);
+template <class QT>
+void launch_hd_write(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over,
+                     const unsigned long long *offs, uint64_t n, QT *out, cudaStream_t st);
+
 // misc_kernels.cu
 template <class T>
 void launch_minmax(const T *data, uint64_t n, T *mm /* device: [min, max] */, cudaStream_t st);

@@ -954,22 +954,76 @@ static void quantizer_load(Cursor &c, double *eb, int *radius, const T **unpred,
     *unpred = reinterpret_cast<const T *>(c.take(*n_unpred * sizeof(T)));
 }
 
-// encoder.load | size_t n | size_t outSize | bits  ->  indices as QT in pinned memory, then on the device
+// encoder.load | size_t n | size_t outSize | bits  ->  indices as QT on the device.
+// The tree is parsed on the host (a few thousand nodes); the bitstream is decoded on the GPU by the self-synchronising
+// decoder of huffman_decode.cu.  The host table decoder remains only for the degenerate one-symbol tree.
 template <class QT>
 static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     HuffmanDecoder dec;
     const char *err = nullptr;
-    double t0 = now_ms();
     if (!dec.load(c.p, c.rem, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
     const uint64_t n = c.get<uint64_t>();
     if (n != expect_n) fail(SZ3B_E_INVALID_ARGUMENT, "index count does not match the array size");
-    QT *h_q = static_cast<QT *>(ws.stage2.ensure(n * sizeof(QT)));
-    if (!dec.decode<QT>(c.p, c.rem, n, h_q, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
-    ws.host_stage("huffman_decode_host", now_ms() - t0);
     QT *d_q = ws.q.as<QT>(n);
-    size_t h = ws.stage_begin("h2d_indices");
-    ws.h2d(d_q, h_q, n * sizeof(QT));
-    ws.stage_end(h, 0);
+    if (dec.leaf[0]) {   // every index identical: no bits in the stream (HuffmanEncoder.hpp:233-237)
+        QT *h_q = static_cast<QT *>(ws.stage2.ensure(n * sizeof(QT)));
+        if (!dec.decode<QT>(c.p, c.rem, n, h_q, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+        ws.h2d(d_q, h_q, n * sizeof(QT));
+        return d_q;
+    }
+    const uint64_t enc_len = c.get<uint64_t>();
+    const uint8_t *bits = c.take(enc_len);
+    const uint64_t total_bits = enc_len * 8;
+    size_t h = ws.stage_begin("huffman_decode");
+    // tables: lut | L | R | C | leaf
+    const uint32_t nc = dec.nc;
+    const size_t lut_n = dec.lut.size();
+    const size_t tab_bytes = (lut_n + 3 * static_cast<size_t>(nc)) * 4 + nc + 64;
+    uint8_t *d_tab = ws.hd_tab.as<uint8_t>(tab_bytes);
+    uint32_t *d_lut = reinterpret_cast<uint32_t *>(d_tab);
+    uint32_t *d_L = d_lut + lut_n, *d_R = d_L + nc;
+    int *d_C = reinterpret_cast<int *>(d_R + nc);
+    uint8_t *d_leaf = reinterpret_cast<uint8_t *>(d_C + nc);
+    ws.h2d(d_lut, dec.lut.data(), lut_n * 4);
+    ws.h2d(d_L, dec.L.data(), nc * 4);
+    ws.h2d(d_R, dec.R.data(), nc * 4);
+    ws.h2d(d_C, dec.C.data(), nc * 4);
+    ws.h2d(d_leaf, dec.leaf.data(), nc);
+    // bitstream, 4-byte aligned and zero padded
+    const size_t padded = (enc_len + 3) / 4 * 4 + 64;
+    uint8_t *d_bits = ws.hd_bits.as<uint8_t>(padded);
+    SZ3B_CUDA(cudaMemsetAsync(d_bits + enc_len / 4 * 4, 0, padded - enc_len / 4 * 4, ws.st));
+    ws.h2d(d_bits, bits, enc_len);
+    const uint64_t nsub = hd_num_sub(total_bits);
+    uint8_t *d_over = ws.hd_over.as<uint8_t>(2 * nsub + 16);
+    unsigned *d_counts = ws.hd_counts.as<unsigned>(nsub + 2);
+    unsigned long long *d_offs = ws.hd_offs.as<unsigned long long>(2 * (nsub + 2));
+    unsigned *d_changed = reinterpret_cast<unsigned *>(ws.counters.as<unsigned long long>(2));
+    SZ3B_CUDA(cudaMemsetAsync(d_over, 0, 2 * nsub + 16, ws.st));
+    HdDeviceTables tb{d_lut, d_L, d_R, d_C, d_leaf, dec.offset};
+    uint8_t *in = d_over, *out = d_over + nsub + 8;
+    int launches = 0;
+    bool converged = false;
+    for (int it = 0; it < 64 && !converged; it++) {
+        SZ3B_CUDA(cudaMemsetAsync(d_changed, 0, sizeof(unsigned), ws.st));
+        launch_hd_sync(reinterpret_cast<const uint32_t *>(d_bits), total_bits, tb, in, out, d_counts, d_changed, ws.st);
+        launches++;
+        unsigned changed = 0;
+        ws.d2h(&changed, d_changed, sizeof(unsigned));
+        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        converged = changed == 0;
+        std::swap(in, out);   // the overshoots just written are the next round's starts (and the final ones)
+    }
+    if (!converged) fail(SZ3B_E_RUNTIME, "Huffman stream did not self-synchronise (malformed stream?)");
+    // `in` now holds the fixed point, d_counts the matching symbol counts
+    launch_scan_chunks(d_counts, d_counts, nsub, d_offs, d_offs + nsub + 2, ws.st);
+    unsigned long long total = 0;
+    ws.d2h(&total, d_offs + nsub, sizeof(total));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    if (total < n) fail(SZ3B_E_INVALID_ARGUMENT, "huffman: bitstream exhausted");
+    launch_hd_write<QT>(reinterpret_cast<const uint32_t *>(d_bits), total_bits, tb, in, d_offs, n, d_q, ws.st);
+    ws.stage_end(h, launches + 2);
+    SZ3B_CUDA(cudaGetLastError());
     return d_q;
 }
 

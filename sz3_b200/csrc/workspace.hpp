@@ -97,6 +97,8 @@ struct Workspace {
     DevBuf cubes, cube_q, cube_unpred, cube_recon, flags, starts;
     // side streams / blockwise
     DevBuf coef, coef2, coef_q, side_q, misc, counters, cpos, cval, hist2;
+    // Huffman decode
+    DevBuf hd_bits, hd_tab, hd_over, hd_counts, hd_offs;
     // pinned staging
     PinBuf stage, stage2, hist_host;
     std::vector<uint8_t> zscratch;   // per-chunk zstd frames before concatenation (host tail)
