@@ -135,14 +135,27 @@ __global__ void __launch_bounds__(256) k_interp_recover_pass(RecoverArgs<T, QT> 
         step[d] = qd < p ? s : 2 * s;
         ext[d] = qd == p ? ((sh.dims[d] - 1) / s + 1) / 2 : (sh.dims[d] - 1) / step[d] + 1;
     }
-    uint64_t r = gid, off = 0, blin = 0;
+    uint64_t off = 0, blin = 0;
     const uint32_t B = kInterpBlock * s;
-    for (int d = sh.N - 1; d >= 0; d--) {
-        const uint32_t idx = static_cast<uint32_t>(r % ext[d]);
-        r /= ext[d];
-        x[d] = d == D ? (2 * idx + 1) * s : idx * step[d];
-        bidx[d] = d == D ? x[d] / B : (x[d] ? (x[d] - 1) / B : 0);
-        off += x[d] * sh.stride[d];
+    if (total <= 0xffffffffull) {   // 32-bit index arithmetic
+        uint32_t r = static_cast<uint32_t>(gid);
+        for (int d = sh.N - 1; d >= 0; d--) {
+            const uint32_t qd = r / ext[d];
+            const uint32_t idx = r - qd * ext[d];
+            r = qd;
+            x[d] = d == D ? (2 * idx + 1) * s : idx * step[d];
+            bidx[d] = d == D ? x[d] / B : (x[d] ? (x[d] - 1) / B : 0);
+            off += x[d] * sh.stride[d];
+        }
+    } else {
+        uint64_t r = gid;
+        for (int d = sh.N - 1; d >= 0; d--) {
+            const uint32_t idx = static_cast<uint32_t>(r % ext[d]);
+            r /= ext[d];
+            x[d] = d == D ? (2 * idx + 1) * s : idx * step[d];
+            bidx[d] = d == D ? x[d] / B : (x[d] ? (x[d] - 1) / B : 0);
+            off += x[d] * sh.stride[d];
+        }
     }
     for (int d = 0; d < sh.N; d++) blin = blin * A.nb[d] + bidx[d];
     BlockGeom g;
