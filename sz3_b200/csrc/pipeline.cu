@@ -14,7 +14,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <exception>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "blockwise.cuh"
@@ -533,13 +535,46 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
         size_t need = ZSTD_compressBound(sizeof(T) * sampling_num + 65536 * 16) + 64;
         if (trial_out.size() < need) trial_out.resize(need);
     }
-    auto trial = [&](const sz3b_config &tc) -> double {
-        ws.stage_prefix = "tune_";
-        size_t sz = interp_compress<T>(ws, tc, d_cubes, ncubes, trial_out.data(), trial_out.size(), 1, true);
-        ws.stage_prefix.clear();
-        return per_block * static_cast<double>(ncubes) * sizeof(T) * 1.0 / sz;
+    // Trial compressions that do not depend on each other's outcome run concurrently: the first on this call's
+    // workspace, the others on host threads with workspaces of their own (own stream, own buffers; the sampled cubes
+    // are shared read-only).  The decisions below are then taken in the reference's order.
+    const size_t trial_cap = trial_out.size();
+    auto run_trials = [&](const std::vector<sz3b_config> &tcs) -> std::vector<double> {
+        std::vector<double> ratios(tcs.size(), 0.0);
+        std::vector<std::exception_ptr> errs(tcs.size());
+        auto one = [&](Workspace &w, size_t k, uint8_t *out) {
+            w.stage_prefix = "tune_";
+            size_t sz = interp_compress<T>(w, tcs[k], d_cubes, ncubes, out, trial_cap, 1, true);
+            w.stage_prefix.clear();
+            ratios[k] = per_block * static_cast<double>(ncubes) * sizeof(T) * 1.0 / sz;
+        };
+        std::vector<std::thread> th;
+        const int device = ws.device;
+        const bool bulk = ws.bulk_copy_in_flight;
+        for (size_t k = 1; k < tcs.size(); k++)
+            th.emplace_back([&, k] {
+                try {
+                    SZ3B_CUDA(cudaSetDevice(device));
+                    WorkspaceLease w2;
+                    w2->bulk_copy_in_flight = bulk;
+                    std::vector<uint8_t> out(trial_cap);
+                    one(*w2, k, out.data());
+                    w2->bulk_copy_in_flight = false;
+                } catch (...) {
+                    errs[k] = std::current_exception();
+                }
+            });
+        try {
+            one(ws, 0, trial_out.data());
+        } catch (...) {
+            errs[0] = std::current_exception();
+        }
+        for (auto &t : th) t.join();
+        for (auto &e : errs)
+            if (e) std::rethrow_exception(e);
+        return ratios;
     };
-    double best_interp = 0, best_lorenzo = 0, ratio;
+    double best_interp = 0, best_lorenzo = 0;
     conf.interpDirection = 0;
     conf.interpAlpha = 1.25;
     conf.interpBeta = 2.0;
@@ -549,34 +584,46 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
         for (int d = 0; d < N; d++) cd[d] = sbs + 1;
         config_set_dims(tc, N, cd);
     }
-    for (int op : {SZ3B_INTERP_LINEAR, SZ3B_INTERP_CUBIC}) {
-        tc.interpAlgo = op;
-        ratio = trial(tc);
-        if (ratio > best_interp) {
-            best_interp = ratio;
-            conf.interpAlgo = op;
-        }
+    {   // interpolator (SZAlgoInterp.hpp:176-184)
+        std::vector<sz3b_config> tcs(2, tc);
+        tcs[0].interpAlgo = SZ3B_INTERP_LINEAR;
+        tcs[1].interpAlgo = SZ3B_INTERP_CUBIC;
+        const std::vector<double> r = run_trials(tcs);
+        for (int k = 0; k < 2; k++)
+            if (r[k] > best_interp) {
+                best_interp = r[k];
+                conf.interpAlgo = tcs[k].interpAlgo;
+            }
     }
     tc.interpAlgo = conf.interpAlgo;
     int fact = 1;
     for (int i = 2; i <= N; i++) fact *= i;
-    tc.interpDirection = fact - 1;
-    ratio = trial(tc);
-    if (ratio > best_interp * 1.02) {
-        best_interp = ratio;
-        conf.interpDirection = tc.interpDirection;
+    // direction (:186-197) and the three (alpha, beta) candidates (:199-224) all compare against the running best,
+    // but an (alpha, beta) trial needs the chosen direction: the direction trial runs first, alone
+    {
+        std::vector<sz3b_config> tcs(1, tc);
+        tcs[0].interpDirection = fact - 1;
+        const std::vector<double> r = run_trials(tcs);
+        if (r[0] > best_interp * 1.02) {
+            best_interp = r[0];
+            conf.interpDirection = fact - 1;
+        }
     }
     tc.interpDirection = conf.interpDirection;
-    const double alphas[3] = {1.0, 1.5, 2.0}, betas[3] = {1.0, 2.5, 3.0};
-    for (int i = 0; i < 3; i++) {
-        tc.interpAlpha = alphas[i];
-        tc.interpBeta = betas[i];
-        ratio = trial(tc);
-        if (ratio > best_interp * 1.02) {
-            best_interp = ratio;
-            conf.interpAlpha = alphas[i];
-            conf.interpBeta = betas[i];
+    {
+        const double alphas[3] = {1.0, 1.5, 2.0}, betas[3] = {1.0, 2.5, 3.0};
+        std::vector<sz3b_config> tcs(3, tc);
+        for (int i = 0; i < 3; i++) {
+            tcs[i].interpAlpha = alphas[i];
+            tcs[i].interpBeta = betas[i];
         }
+        const std::vector<double> r = run_trials(tcs);
+        for (int i = 0; i < 3; i++)
+            if (r[i] > best_interp * 1.02) {
+                best_interp = r[i];
+                conf.interpAlpha = alphas[i];
+                conf.interpBeta = betas[i];
+            }
     }
     if (N == 1 && best_interp < 50) {
         // the reference additionally tries Lorenzo(1st+2nd order) on 1-D data (:227-241); that predictor stack is

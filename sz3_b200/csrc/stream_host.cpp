@@ -300,9 +300,16 @@ size_t zstd_compress_framed(const uint8_t *src, size_t src_len, uint8_t *dst, si
     ZJob j;
     j.src = src;
     j.src_len = src_len;
-    j.chunk = kChunk;
-    j.nchunks = (src_len + kChunk - 1) / kChunk;
-    j.slot = ZSTD_compressBound(kChunk);
+    // about 1 MiB per frame, but a whole number of rounds over the worker threads (46 frames on 16 threads would leave
+    // the third round two-thirds empty)
+    {
+        const size_t rounds = (src_len + kChunk * threads - 1) / (kChunk * static_cast<size_t>(threads));
+        const size_t want = rounds * static_cast<size_t>(threads);
+        j.chunk = std::max<size_t>((src_len + want - 1) / want, static_cast<size_t>(256) << 10);
+        j.chunk = (j.chunk + 4095) & ~static_cast<size_t>(4095);
+    }
+    j.nchunks = (src_len + j.chunk - 1) / j.chunk;
+    j.slot = ZSTD_compressBound(j.chunk);
     std::vector<uint8_t> local;
     std::vector<uint8_t> &sc = scratch ? *scratch : local;
     if (sc.size() < j.nchunks * j.slot) sc.resize(j.nchunks * j.slot);
@@ -316,7 +323,7 @@ size_t zstd_compress_framed(const uint8_t *src, size_t src_len, uint8_t *dst, si
     // Adaptive policy (post-Huffman streams only): every 8th chunk is a probe.  When zstd gains less than 1 % on the
     // probes -- entropy-coded indices of noisy data -- the other chunks are stored as raw frames: at most 0.875 % of
     // compression ratio traded for 7/8 of the host time.  The stream stays a plain concatenation of zstd frames.
-    const bool adaptive = allow_raw && g_lossless_policy.load() == 1 && j.nchunks >= 16;
+    const bool adaptive = allow_raw && g_lossless_policy.load() == 1 && j.nchunks >= 16 && j.chunk <= 0xfffffff0u;
     j.probe_stride = adaptive ? 8 : 1;
     j.phase = 0;
     host_parallel(nt, zjob_worker, &j);
