@@ -530,9 +530,10 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
         ws.stage_end(h, 1);
         SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // `starts` must outlive the copy
     }
-    std::vector<uint8_t> trial_out(sizeof(T) * sampling_num + (1u << 20));
+    std::vector<uint8_t> &trial_out = ws.trial_out;   // kept across calls (zero-filling megabytes per call costs a trial)
     {
-        size_t need = ZSTD_compressBound(sizeof(T) * sampling_num + 65536 * 16) + 64;
+        size_t need = std::max<size_t>(sizeof(T) * sampling_num + (1u << 20),
+                                       ZSTD_compressBound(sizeof(T) * sampling_num + 65536 * 16) + 64);
         if (trial_out.size() < need) trial_out.resize(need);
     }
     // Trial compressions that do not depend on each other's outcome run concurrently: the first on this call's
@@ -548,28 +549,37 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
             w.stage_prefix.clear();
             ratios[k] = per_block * static_cast<double>(ncubes) * sizeof(T) * 1.0 / sz;
         };
-        std::vector<std::thread> th;
-        const int device = ws.device;
-        const bool bulk = ws.bulk_copy_in_flight;
-        for (size_t k = 1; k < tcs.size(); k++)
-            th.emplace_back([&, k] {
-                try {
-                    SZ3B_CUDA(cudaSetDevice(device));
+        // persistent pool threads (stream_host.cpp): creating threads per call costs more than a trial
+        struct Ctx {
+            decltype(one) *fn;
+            Workspace *main_ws;
+            uint8_t *main_out;
+            size_t cap;
+            int device;
+            bool bulk;
+            std::vector<std::exception_ptr> *errs;
+            size_t n;
+        } cx{&one, &ws, trial_out.data(), trial_cap, ws.device, ws.bulk_copy_in_flight, &errs, tcs.size()};
+        auto task = [](void *arg, int worker) {
+            Ctx &c = *static_cast<Ctx *>(arg);
+            const size_t k = static_cast<size_t>(worker);
+            if (k >= c.n) return;
+            try {
+                if (k == 0) {
+                    (*c.fn)(*c.main_ws, 0, c.main_out);
+                } else {
+                    SZ3B_CUDA(cudaSetDevice(c.device));
                     WorkspaceLease w2;
-                    w2->bulk_copy_in_flight = bulk;
-                    std::vector<uint8_t> out(trial_cap);
-                    one(*w2, k, out.data());
+                    w2->bulk_copy_in_flight = c.bulk;
+                    if (w2->trial_out.size() < c.cap) w2->trial_out.resize(c.cap);
+                    (*c.fn)(*w2, k, w2->trial_out.data());
                     w2->bulk_copy_in_flight = false;
-                } catch (...) {
-                    errs[k] = std::current_exception();
                 }
-            });
-        try {
-            one(ws, 0, trial_out.data());
-        } catch (...) {
-            errs[0] = std::current_exception();
-        }
-        for (auto &t : th) t.join();
+            } catch (...) {
+                (*c.errs)[k] = std::current_exception();
+            }
+        };
+        host_parallel(static_cast<int>(tcs.size()), task, &cx);
         for (auto &e : errs)
             if (e) std::rethrow_exception(e);
         return ratios;

@@ -102,6 +102,7 @@ struct Workspace {
     // pinned staging
     PinBuf stage, stage2, hist_host;
     std::vector<uint8_t> zscratch;   // per-chunk zstd frames before concatenation (host tail)
+    std::vector<uint8_t> trial_out;  // compressed output of a tuner trial run on this workspace
     // profiling
     std::vector<StageRecord> prof;
     std::vector<cudaEvent_t> ev_pool;
