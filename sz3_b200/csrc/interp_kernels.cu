@@ -6,6 +6,7 @@
 #include "interp_body.cuh"
 #include "interp_fast.cuh"
 #include "interp_line.cuh"
+#include "interp_lean.cuh"
 #include "launch.hpp"
 
 namespace sz3b {
@@ -130,9 +131,56 @@ __global__ void __launch_bounds__(256) k_interp_pass(InterpArgs<T, QT> A, int p,
     ctx.flush();
 }
 
+// row-mapped per-pass schedule (interp_lean.cuh), N >= 3; RECOVER = decompression side
+template <class T, class QT, bool RECOVER>
+__global__ void __launch_bounds__(kLeanThreads) k_interp_lean(LeanArgs<T, QT> P) {
+    __shared__ LeanShared S;
+    __shared__ unsigned shist[kHistWindow];
+    DevCtx2 ctx(shist, P.A.hist, P.A.qp.radius);
+    if (!RECOVER) {
+        for (int i = threadIdx.x; i < kHistWindow; i += blockDim.x) shist[i] = 0;
+    }
+    lean_cta<T, QT, DevCtx2, RECOVER>(P, ctx, S, blockIdx.x, blockIdx.y, blockIdx.z);
+    if (!RECOVER) {
+        ctx.pass_end();
+        ctx.flush();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------------
+template <class T, class QT>
+bool interp_launch_lean(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, bool write_work, bool recover, const T *unpred_in,
+                        cudaStream_t st) {
+    const InterpShape &sh = A.sh;
+    const int L = sh.N - 1;
+    if (A.nb[L] > static_cast<uint32_t>(kLeanMaxBlocks)) return false;
+    LeanArgs<T, QT> P;
+    P.A = A;
+    P.p = p;
+    P.write_work = write_work ? 1u : 0u;
+    P.unpred_in = unpred_in;
+    P.lg_s = 0;
+    while ((1u << P.lg_s) < A.s) P.lg_s++;
+    const uint32_t row_len = lean_row_len(A, p);
+    if (row_len == 0) return true;
+    const uint32_t max_rows = lean_max_rows(A, p);
+    P.chunks_per_brow = (max_rows + kLeanRows - 1) / kLeanRows;
+    uint64_t nbrows = 1;
+    for (int d = 0; d < L; d++) nbrows *= A.nb[d];
+    const uint64_t gx = nbrows * P.chunks_per_brow;
+    const uint32_t gy = (row_len + kLeanThreads - 1) / kLeanThreads;
+    P.nchunks_L = gy;
+    if (gx > 0x7fffffffull || gy > 65535u || nbatch > 65535u) return false;
+    dim3 grid(static_cast<unsigned>(gx), gy, nbatch);
+    if (recover)
+        k_interp_lean<T, QT, true><<<grid, kLeanThreads, 0, st>>>(P);
+    else
+        k_interp_lean<T, QT, false><<<grid, kLeanThreads, 0, st>>>(P);
+    return true;
+}
+
 template <class T, class QT>
 void interp_launch_anchors(const InterpArgs<T, QT> &A, uint32_t anchor_stride, uint64_t n_anchor, uint32_t nbatch,
                            cudaStream_t st) {
@@ -194,7 +242,9 @@ void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cuda
     template void interp_launch_tiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);      \
     template void interp_launch_ftiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);     \
     template void interp_launch_ltiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);     \
-    template void interp_launch_pass<T, QT>(const InterpArgs<T, QT> &, int, uint32_t, cudaStream_t);
+    template void interp_launch_pass<T, QT>(const InterpArgs<T, QT> &, int, uint32_t, cudaStream_t);          \
+    template bool interp_launch_lean<T, QT>(const InterpArgs<T, QT> &, int, uint32_t, bool, bool, const T *,  \
+                                            cudaStream_t);
 SZ3B_INST(float, uint16_t)
 SZ3B_INST(float, uint32_t)
 SZ3B_INST(double, uint16_t)

@@ -35,6 +35,7 @@ struct InterpPlan {
     uint64_t stride2[kMaxDim];
     uint64_t num2 = 0;
     bool tile = false;            // tile schedule (N == 3) or generic per-pass schedule
+    bool lean = false;            // per-pass schedule through the row-mapped kernel (interp_lean.cuh, N >= 3)
     int variant = 0;              // tile kernel: 0 = first generation, 1 = lean (interp_fast.cuh), 2 = line walker (interp_line.cuh)
     int interp_id = 1, direction = 0;
     double alpha = 1.25, beta = 2.0;
@@ -120,7 +121,8 @@ inline const char *build_interp_plan(const sz3b_config &c, double eb, int schedu
         if (d < N) acc *= pl.dims2[d];
     }
     pl.num2 = acc;
-    pl.tile = (N == 3) && schedule != 1;
+    pl.tile = (N == 3) && schedule != 1 && schedule != 5;
+    pl.lean = N >= 3 && (schedule == 5 || (schedule == 0 && !pl.tile));
     pl.variant = schedule == 2 ? 0 : (schedule == 3 ? 1 : 2);
     // the line walker keeps tile-relative element offsets in 32 bits
     if (pl.variant == 2 && pl.num >= (1ull << 32)) {
@@ -128,7 +130,8 @@ inline const char *build_interp_plan(const sz3b_config &c, double eb, int schedu
         pl.variant = 1;
     }
     if (schedule >= 2 && schedule <= 4 && N != 3) return "tile schedule needs N == 3";
-    if (schedule < 0 || schedule > 4) return "unknown schedule";
+    if (schedule == 5 && N < 3) return "row-mapped per-pass schedule needs N >= 3";
+    if (schedule < 0 || schedule > 5) return "unknown schedule";
 
     pl.levels.clear();
     pl.table.clear();

@@ -22,6 +22,10 @@ template <class T, class QT>
 void interp_launch_ltiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st);
 template <class T, class QT>
 void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cudaStream_t st);
+// row-mapped per-pass kernel (N >= 3); returns false when the shape does not fit its table / grid (caller falls back)
+template <class T, class QT>
+bool interp_launch_lean(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, bool write_work, bool recover, const T *unpred_in,
+                        cudaStream_t st);
 
 // encode_kernels.cu
 template <class QT>

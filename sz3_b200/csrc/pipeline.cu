@@ -10,6 +10,7 @@
 // lays out the byte stream and runs zstd.  There is no CPU implementation of the kernels to fall back to.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -229,7 +230,10 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         } else {
             for (int p = 0; p < pl.sh.N; p++) {
                 if (pass_points(A, p) == 0) continue;
-                interp_launch_pass<T, QT>(A, p, nbatch, ws.st);
+                // the last pass of the finest level is read by nobody: its reconstructions need not be stored
+                const bool write_work = !(L.s == 1 && p == pl.sh.N - 1);
+                if (!(pl.lean && interp_launch_lean<T, QT>(A, p, nbatch, write_work, false, nullptr, ws.st)))
+                    interp_launch_pass<T, QT>(A, p, nbatch, ws.st);
                 (*launches)++;
             }
         }
@@ -388,7 +392,13 @@ template <class T, class QT>
 static size_t interp_compress_t(Workspace &ws, const sz3b_config &conf, const T *d_data, uint32_t nbatch, uint8_t *dst,
                                 size_t cap, int zstd_threads, bool tuner) {
     InterpPlan pl;
-    if (const char *e = build_interp_plan(conf, conf.absErrorBound, 0, pl)) fail(SZ3B_E_INVALID_ARGUMENT, e);
+    // SZ3B_SCHEDULE (diagnostics): force one of the schedules of sz3b_interp_decompose for whole compressions
+    static const int forced = [] {
+        const char *e = getenv("SZ3B_SCHEDULE");
+        return e ? atoi(e) : 0;
+    }();
+    const int schedule = (forced == 1 || (forced >= 2 && forced <= 4 && conf.N == 3) || (forced == 5 && conf.N >= 3)) ? forced : 0;
+    if (const char *e = build_interp_plan(conf, conf.absErrorBound, schedule, pl)) fail(SZ3B_E_INVALID_ARGUMENT, e);
     const int radius = conf.quantbinCnt / 2;
     const int nbins = 2 * radius;
     const uint64_t n = pl.num * nbatch;
@@ -1137,9 +1147,21 @@ static void interp_decompress_t(Workspace &ws, const sz3b_config &conf, Cursor &
                                  pl.anchor_stride, pl.n_first, ws.st);
     launches++;
     for (const LevelPlan &L : pl.levels) {
+        InterpArgs<T, QT> A;
+        memset(&A, 0, sizeof(A));
+        A.sh = pl.sh;
+        A.work = d_out;
+        A.q = d_q;
+        A.data_bstride = A.q_bstride = pl.num;
+        A.qp = make_quant(L.eb, radius);
+        A.s = L.s;
+        for (int d = 0; d < kMaxDim; d++) A.nb[d] = L.nb[d];
+        A.block_base = d_table + L.table_off;
         for (int p = 0; p < pl.sh.N; p++) {
-            launch_interp_recover<T, QT>(pl.sh, d_out, d_q, d_tmp, make_quant(L.eb, radius), L.s, L.nb, d_table + L.table_off,
-                                         p, 0, 0, ws.st);
+            if (pass_points(A, p) == 0) continue;
+            if (!(pl.sh.N >= 3 && interp_launch_lean<T, QT>(A, p, 1, true, true, d_tmp, ws.st)))
+                launch_interp_recover<T, QT>(pl.sh, d_out, d_q, d_tmp, make_quant(L.eb, radius), L.s, L.nb,
+                                             d_table + L.table_off, p, 0, 0, ws.st);
             launches++;
         }
     }

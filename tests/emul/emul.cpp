@@ -11,6 +11,7 @@
 #include "../../sz3_b200/csrc/interp_body.cuh"
 #include "../../sz3_b200/csrc/interp_fast.cuh"
 #include "../../sz3_b200/csrc/interp_line.cuh"
+#include "../../sz3_b200/csrc/interp_lean.cuh"
 #include "../../sz3_b200/csrc/interp_plan.hpp"
 
 using namespace sz3b;
@@ -117,6 +118,37 @@ static int run(const sz3b_config &c, double eb, const T *data, int schedule, int
             for (int t = 1; t < nthreads; t++) th.emplace_back(worker, t);
             worker(0);
             for (auto &x : th) x.join();
+        } else if (pl.lean) {
+            // row-mapped per-pass schedule: every CTA of the launch grid, one after the other, with host threads
+            static LeanShared S;
+            for (int p = 0; p < pl.sh.N; p++) {
+                if (pass_points(A, p) == 0) continue;
+                LeanArgs<T, QT> P;
+                P.A = A;
+                P.p = p;
+                P.write_work = !(L.s == 1 && p == pl.sh.N - 1);
+                P.unpred_in = nullptr;
+                P.lg_s = 0;
+                while ((1u << P.lg_s) < A.s) P.lg_s++;
+                P.chunks_per_brow = (lean_max_rows(A, p) + kLeanRows - 1) / kLeanRows;
+                uint64_t nbrows = 1;
+                for (int d = 0; d < pl.sh.N - 1; d++) nbrows *= A.nb[d];
+                const uint32_t row_len = lean_row_len(A, p);
+                const uint32_t gy = (row_len + nthreads - 1) / nthreads;
+                P.nchunks_L = gy;
+                auto worker = [&](int t) {
+                    HostCtx ctx{static_cast<uint32_t>(t), static_cast<uint32_t>(nthreads), &bar, hist.data()};
+                    for (uint64_t cx = 0; cx < nbrows * P.chunks_per_brow; cx++)
+                        for (uint32_t cy = 0; cy < gy; cy++) {
+                            lean_cta<T, QT, HostCtx, false>(P, ctx, S, static_cast<uint32_t>(cx), cy, 0);
+                            ctx.sync();
+                        }
+                };
+                std::vector<std::thread> th;
+                for (int t = 1; t < nthreads; t++) th.emplace_back(worker, t);
+                worker(0);
+                for (auto &x : th) x.join();
+            }
         } else {
             for (int p = 0; p < pl.sh.N; p++) {
                 uint64_t total = pass_points(A, p);

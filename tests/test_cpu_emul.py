@@ -113,3 +113,26 @@ def test_emul_regression_matches_reference(shape, dtype, eb, bsz):
     if nun.value:
         tail = np.frombuffer(blob_ref[len(blob_ref) - nun.value * data.itemsize:], dtype)
         assert np.array_equal(tail, un[:nun.value])
+
+
+@pytest.mark.parametrize("shape,dtype,kw", [
+    ((40, 50, 70), np.float32, dict(interpAlgo=1, interpDirection=0)),
+    ((33, 65, 97), np.float32, dict(interpAlgo=0, interpDirection=5)),
+    ((20, 37, 66), np.float64, dict(interpAlgo=1, interpDirection=3, interpAlpha=2.0, interpBeta=3.0)),
+    ((64, 64, 64), np.float32, dict(interpAlgo=0, interpDirection=2)),
+    ((66, 35, 34), np.float32, dict(interpAlgo=0, interpDirection=5)),
+    ((2, 3, 200), np.float32, dict(interpAlgo=1, interpDirection=4)),
+    ((9, 12, 20, 18), np.float32, dict(interpAlgo=1, interpDirection=0, interpAnchorStride=16)),
+    ((7, 18, 34, 21), np.float32, dict(interpAlgo=0, interpDirection=23, interpAnchorStride=16)),
+    ((10, 17, 19, 36), np.float64, dict(interpAlgo=1, interpDirection=9, interpAnchorStride=8)),
+])
+def test_emul_lean_per_pass_matches_reference(shape, dtype, kw):
+    """Row-mapped per-pass schedule (interp_lean.cuh): block tables, row descriptors, traversal positions, N = 3 and 4."""
+    data = field_nd(shape, dtype)
+    kw.setdefault("interpAnchorStride", 32)
+    conf = make_config(shape, cmprAlgo=ALGO_INTERP, **kw)
+    q_ref, blob_ref, _ = ref_interp(ref_lib(), data, conf, 1e-2)
+    q, un = emul(data, conf, 1e-2, 5, nthreads=32)
+    assert np.array_equal(q, q_ref), f"{int((q != q_ref).sum())} of {q.size} indices differ"
+    _, un_ref = interp_blob_unpred(blob_ref, conf.N, dtype)
+    assert np.array_equal(un, un_ref)

@@ -72,5 +72,27 @@ def full(path):
         print()
 
 
+def traffic(path):
+    """profiles/traffic.json for bench.py: DRAM bytes of one predict+quantize step = sum over the level launches of one
+    step in an `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+
+    def to_bytes(v, u):
+        m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        return float(v) * m.get(u, 1)
+
+    per = []
+    for r in rows[2:]:
+        rd = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
+        wr = to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+        per.append({"kernel": r[idx["Kernel Name"]].split("(")[0], "grid": r[idx["Grid Size"]], "dram_read": rd, "dram_write": wr,
+                    "time_us": float(r[idx["gpu__time_duration.sum"]]) * {"us": 1, "ms": 1e3, "ns": 1e-3}.get(units[idx["gpu__time_duration.sum"]], 1)})
+    print(json.dumps({"source": path, "predict_quantize_dram_bytes": sum(p["dram_read"] + p["dram_write"] for p in per), "launches": per}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
