@@ -21,7 +21,7 @@
 namespace sz3b {
 
 constexpr int kLeanThreads = 256;
-constexpr int kLeanRows = 16;        // lattice rows of one block-row per CTA
+constexpr int kLeanRows = 64;        // lattice rows of one block-row per CTA
 constexpr int kLeanMaxBlocks = 256;  // table entries (blocks along the fastest dim): fastest extent up to 8192 at stride 1
 
 struct LeanEntry {          // per block index along L
@@ -86,8 +86,11 @@ SZ_HD uint32_t lean_max_rows(const InterpArgs<T, QT> &A, int p) {
     for (int q = 0; q < sh.N; q++) {
         const int d = sh.perm[q];
         if (d == L) continue;
-        if (d == D) rows *= 16;                     // n <= 33 -> at most 16 odd local indices
-        else rows *= q < p ? 33u : 17u;             // owned points at step s / 2s (first block owns its low face)
+        // block bound (n <= 33: 16 odd local indices; 33 / 17 owned points at step s / 2s) and array bound
+        const uint32_t npts = (sh.dims[d] - 1) / A.s + 1;
+        if (d == D) rows *= npts / 2 < 16u ? npts / 2 : 16u;
+        else if (q < p) rows *= npts < 33u ? npts : 33u;
+        else rows *= (npts + 1) / 2 < 17u ? (npts + 1) / 2 : 17u;
     }
     return rows;
 }
@@ -322,7 +325,7 @@ SZ_HD void lean_cta(const LeanArgs<T, QT> &P, Ctx &ctx, LeanShared &S, uint32_t 
     if (S.row0 < S.nrows) {   // uniform: this chunk has rows
         for (uint32_t b = tid; b < A.nb[L]; b += nt) lean_entry_setup(P, brow, b, S, S.tab[b]);
         // the row descriptors are built by the LAST threads so that they overlap with the table entries
-        if (tid >= nt - kLeanRows) lean_row_setup(P, tid - (nt - kLeanRows), S, S.rows[tid - (nt - kLeanRows)]);
+        for (uint32_t r = nt - 1 - tid; r < static_cast<uint32_t>(kLeanRows); r += nt) lean_row_setup(P, r, S, S.rows[r]);
     }
     ctx.sync();
     if (S.row0 >= S.nrows) return;

@@ -232,7 +232,9 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
                 if (pass_points(A, p) == 0) continue;
                 // the last pass of the finest level is read by nobody: its reconstructions need not be stored
                 const bool write_work = !(L.s == 1 && p == pl.sh.N - 1);
-                if (!(pl.lean && interp_launch_lean<T, QT>(A, p, nbatch, write_work, false, nullptr, ws.st)))
+                // (tuner batches of small cubes stay on the point-mapped kernel: a CTA of the row-mapped one would
+                //  spend its time on the block table)
+                if (!(pl.lean && nbatch == 1 && interp_launch_lean<T, QT>(A, p, nbatch, write_work, false, nullptr, ws.st)))
                     interp_launch_pass<T, QT>(A, p, nbatch, ws.st);
                 (*launches)++;
             }
@@ -1159,7 +1161,8 @@ static void interp_decompress_t(Workspace &ws, const sz3b_config &conf, Cursor &
         A.block_base = d_table + L.table_off;
         for (int p = 0; p < pl.sh.N; p++) {
             if (pass_points(A, p) == 0) continue;
-            if (!(pl.sh.N >= 3 && interp_launch_lean<T, QT>(A, p, 1, true, true, d_tmp, ws.st)))
+            static const bool old_recover = getenv("SZ3B_RECOVER_OLD") != nullptr;   // diagnostics
+            if (!(pl.sh.N >= 3 && !old_recover && interp_launch_lean<T, QT>(A, p, 1, true, true, d_tmp, ws.st)))
                 launch_interp_recover<T, QT>(pl.sh, d_out, d_q, d_tmp, make_quant(L.eb, radius), L.s, L.nb,
                                              d_table + L.table_off, p, 0, 0, ws.st);
             launches++;

@@ -56,6 +56,12 @@ dt = time.perf_counter() - t0
 assert rc == 0, L.sz3b_last_error()
 err = float((dec.double() - data.double()).abs().max())
 print(f"decompress: {dt*1e3:.1f} ms, max abs error {err:.3e} (bound 1e-3)", flush=True)
+for it in range(2):
+    t0 = time.perf_counter()
+    rc = L.sz3b_decompress(0, out.ctypes.data_as(C.c_char_p), C.c_size_t(size.value), C.c_void_p(dec.data_ptr()), 1, C.byref(dconf))
+    dt = time.perf_counter() - t0
+n = L.sz3b_last_profile(names, ms, launches, 64)
+print(f"decompress (warm): {dt*1e3:.1f} ms, {nbytes/dt/1e9:.1f} GB/s", {names[i].decode(): round(ms[i], 2) for i in range(n)}, flush=True)
 assert err <= 1e-3
 if use_ref:
     R = ref_lib()
