@@ -1,0 +1,254 @@
+// sz3_b200/csrc/lorenzo.cu -- kernels of the BlockwiseDecomposition path with a Lorenzo predictor in the stack
+// (single Lorenzo, Lorenzo 1+2, Lorenzo + regression; reference include/SZ3/api/impl/SZAlgoLorenzoReg.hpp:22-64).
+//
+//   k_bw_pad         the reference's zero-padded working copy (BlockwiseIterator.hpp:205-222,246-281)
+//   k_bw_front       one front of the block wavefront: one warp per block, body in lorenzo.cuh
+//   k_bw_spec_coef   lattice guess of the reconstructed regression coefficients (selection guess pass)
+//   k_bw_rank        dense rank of the regression-selected blocks (single-CTA scan) + their count
+//   k_bw_gather_fit  fitted coefficients of the selected blocks, dense, in row-major block order (chain input)
+//
+// Compiled with -fmad=false like every kernel that reproduces reference arithmetic.
+#include <cuda_runtime.h>
+
+#include "launch.hpp"
+#include "lorenzo.cuh"
+
+namespace sz3b {
+
+template <class T>
+__global__ void __launch_bounds__(256) k_bw_pad(const T *__restrict__ data, BlockShape bs, uint64_t ps0, uint64_t ps1,
+                                                uint64_t ps2, uint64_t ps3, T *__restrict__ W, uint64_t b_lo) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    const uint64_t ps[kMaxDim] = {ps0, ps1, ps2, ps3};
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < bs.num; i += stride) {
+        uint64_t r = i, w = 0, b = 0, bmul = 1;
+        for (int d = bs.N - 1; d >= 0; d--) {
+            const uint64_t x = r % bs.dims[d];
+            r /= bs.dims[d];
+            w += (x + kBwPad) * ps[d];
+            b += (x / bs.B) * bmul;
+            bmul *= bs.nb[d];
+        }
+        if (b >= b_lo) W[w] = data[i];   // b_lo > 0: restore the originals of the blocks that are not final yet
+    }
+}
+
+// Row-major walk of the blocks [b_lo, nblocks) by one warp, the coefficient chain inline: the exact sequential
+// semantics of the reference, used to finish when the selection iteration keeps being invalidated (lorenzo.cuh).
+template <class T, class QT>
+__global__ void __launch_bounds__(32) k_bw_serial(BwArgs<T, QT> A, uint64_t b_lo, const T *__restrict__ chain_init,
+                                                  unsigned long long nsel0, unsigned long long *__restrict__ nsel_out,
+                                                  uint32_t tile_cap) {
+    extern __shared__ __align__(16) unsigned char bw_smem[];
+    __shared__ BwSerial<T> st;
+    T *tile = reinterpret_cast<T *>(bw_smem);
+    T *est = tile + tile_cap;
+    const int N = A.bs.N;
+    if (threadIdx.x == 0) {
+        for (int d = 0; d <= N; d++) st.prev[d] = chain_init ? chain_init[d] : static_cast<T>(0);
+        st.nsel = nsel0;
+    }
+    __syncwarp();
+    for (uint64_t b = b_lo; b < A.bs.nblocks; b++) {
+        uint32_t bi[kMaxDim] = {0, 0, 0, 0};
+        uint64_t r = b;
+        for (int d = N - 1; d >= 0; d--) {
+            bi[d] = static_cast<uint32_t>(r % A.bs.nb[d]);
+            r /= A.bs.nb[d];
+        }
+        bw_process_block<T, QT>(A, bi, tile, est, threadIdx.x, 32, &st);
+        __threadfence_block();
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) *nsel_out = st.nsel;
+}
+
+// One CTA (one warp) per tuple of leading block coordinates; the last block coordinate follows from the front.
+// N == 1 has a single CTA that walks all fronts (the 1-D Lorenzo recurrence is serial).
+template <class T, class QT>
+__global__ void __launch_bounds__(32) k_bw_front(BwArgs<T, QT> A, uint32_t f0, uint32_t f1, uint32_t tile_cap) {
+    extern __shared__ __align__(16) unsigned char bw_smem[];
+    T *tile = reinterpret_cast<T *>(bw_smem);
+    T *est = tile + tile_cap;
+    const int N = A.bs.N;
+    uint32_t bi[kMaxDim] = {0, 0, 0, 0};
+    uint32_t r = blockIdx.x, s = 0;
+    for (int d = N - 2; d >= 0; d--) {
+        bi[d] = r % A.bs.nb[d];
+        r /= A.bs.nb[d];
+        s += bi[d];
+    }
+    for (uint32_t f = f0; f < f1; f++) {
+        if (f < s) continue;
+        const uint32_t last = f - s;
+        if (last >= A.bs.nb[N - 1]) break;
+        bi[N - 1] = last;
+        bw_process_block<T, QT>(A, bi, tile, est, threadIdx.x, 32);
+        __threadfence_block();
+        __syncwarp();
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) k_bw_spec_coef(const T *__restrict__ c_fit, const uint8_t *__restrict__ valid,
+                                                      uint64_t nblocks, int N, QuantParams q_liner, QuantParams q_indep,
+                                                      T *__restrict__ c_spec) {
+    const int nc = N + 1;
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nblocks * nc) return;
+    const uint64_t b = i / nc;
+    const int d = static_cast<int>(i - b * nc);
+    c_spec[i] = valid[b] ? coef_lattice_guess<T>(c_fit[i], d < N ? q_liner : q_indep) : static_cast<T>(0);
+}
+
+__global__ void __launch_bounds__(1024) k_bw_rank(const uint8_t *__restrict__ sel, uint64_t nblocks, int reg_sid,
+                                                  uint32_t *__restrict__ rank, unsigned long long *__restrict__ count) {
+    __shared__ unsigned warp_sum[32];
+    __shared__ unsigned carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < nblocks; base += 1024) {
+        const uint64_t b = base + threadIdx.x;
+        const unsigned v = b < nblocks && sel[b] == reg_sid ? 1u : 0u;
+        unsigned x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned w = warp_sum[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sum[lane] = w;   // inclusive
+        }
+        __syncthreads();
+        const unsigned carry = carry_s;
+        const unsigned before = carry + (wid ? warp_sum[wid - 1] : 0u) + x - v;
+        if (b < nblocks) rank[b] = before;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_sum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = carry_s;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) k_bw_gather_fit(const T *__restrict__ c_fit, const uint8_t *__restrict__ sel,
+                                                       int reg_sid, const uint32_t *__restrict__ rank, uint64_t nblocks,
+                                                       int nc, T *__restrict__ c_dense) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nblocks * nc) return;
+    const uint64_t b = i / nc;
+    if (sel[b] != reg_sid) return;
+    c_dense[static_cast<uint64_t>(rank[b]) * nc + (i - b * nc)] = c_fit[i];
+}
+
+__global__ void __launch_bounds__(256) k_widen_u8(const uint8_t *__restrict__ in, uint64_t n, int32_t *__restrict__ out) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <class T>
+void launch_bw_pad(const T *data, const BlockShape &bs, const uint64_t *pstride, T *W, uint64_t b_lo, cudaStream_t st) {
+    uint64_t blocks = (bs.num + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    k_bw_pad<T><<<static_cast<unsigned>(blocks), 256, 0, st>>>(data, bs, pstride[0], pstride[1], pstride[2], pstride[3], W, b_lo);
+}
+
+static size_t bw_tile_cap(const BlockShape &bs) {
+    size_t tile_cap = 1;
+    for (int d = 0; d < bs.N; d++) tile_cap *= (bs.dims[d] < bs.B ? bs.dims[d] : bs.B) + kBwPad;
+    return tile_cap;
+}
+
+template <class T, class QT>
+const char *launch_bw_serial(const BwArgs<T, QT> &A, uint64_t b_lo, const T *chain_init, unsigned long long nsel0,
+                             unsigned long long *nsel_out, cudaStream_t st) {
+    const size_t smem = bw_scratch_elems(A.bs, A.nk) * sizeof(T);
+    if (smem > 200 * 1024) return "blockSize too large for the shared-memory tile of the Lorenzo kernel";
+    static thread_local size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        if (cudaFuncSetAttribute(k_bw_serial<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return "cannot raise the dynamic shared memory limit";
+        attr_set = 200 * 1024;
+    }
+    k_bw_serial<T, QT><<<1, 32, smem, st>>>(A, b_lo, chain_init, nsel0, nsel_out, static_cast<uint32_t>(bw_tile_cap(A.bs)));
+    return nullptr;
+}
+
+template <class T, class QT>
+const char *launch_bw_fronts(const BwArgs<T, QT> &A, cudaStream_t st, int *launches) {
+    const BlockShape &bs = A.bs;
+    const int N = bs.N;
+    uint64_t grid = 1;
+    for (int d = 0; d < N - 1; d++) grid *= bs.nb[d];
+    if (grid > 0x7fffffffull) return "block grid exceeds the launch grid of the Lorenzo kernel";
+    const size_t elems = bw_scratch_elems(bs, A.nk);
+    size_t tile_cap = 1;
+    for (int d = 0; d < N; d++) tile_cap *= (bs.dims[d] < bs.B ? bs.dims[d] : bs.B) + kBwPad;
+    const size_t smem = elems * sizeof(T);
+    if (smem > 200 * 1024) return "blockSize too large for the shared-memory tile of the Lorenzo kernel";
+    static thread_local size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        if (cudaFuncSetAttribute(k_bw_front<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return "cannot raise the dynamic shared memory limit";
+        attr_set = 200 * 1024;
+    }
+    const uint32_t nfronts = bw_num_fronts(bs);
+    if (N == 1) {
+        k_bw_front<T, QT><<<1, 32, smem, st>>>(A, 0, nfronts, static_cast<uint32_t>(tile_cap));
+        *launches += 1;
+    } else {
+        for (uint32_t f = 0; f < nfronts; f++)
+            k_bw_front<T, QT><<<static_cast<unsigned>(grid), 32, smem, st>>>(A, f, f + 1, static_cast<uint32_t>(tile_cap));
+        *launches += static_cast<int>(nfronts);
+    }
+    return nullptr;
+}
+
+template <class T>
+void launch_bw_spec_coef(const T *c_fit, const uint8_t *valid, uint64_t nblocks, int N, const QuantParams &q_liner,
+                         const QuantParams &q_indep, T *c_spec, cudaStream_t st) {
+    const uint64_t n = nblocks * (N + 1);
+    k_bw_spec_coef<T><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(c_fit, valid, nblocks, N, q_liner, q_indep, c_spec);
+}
+
+void launch_bw_rank(const uint8_t *sel, uint64_t nblocks, int reg_sid, uint32_t *rank, unsigned long long *count,
+                    cudaStream_t st) {
+    k_bw_rank<<<1, 1024, 0, st>>>(sel, nblocks, reg_sid, rank, count);
+}
+
+template <class T>
+void launch_bw_gather_fit(const T *c_fit, const uint8_t *sel, int reg_sid, const uint32_t *rank, uint64_t nblocks, int nc,
+                          T *c_dense, cudaStream_t st) {
+    const uint64_t n = nblocks * nc;
+    k_bw_gather_fit<T><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(c_fit, sel, reg_sid, rank, nblocks, nc, c_dense);
+}
+
+void launch_widen_u8(const uint8_t *in, uint64_t n, int32_t *out, cudaStream_t st) {
+    if (n == 0) return;
+    k_widen_u8<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(in, n, out);
+}
+
+#define SZ3B_INST_LZ(T)                                                                                              \
+    template void launch_bw_pad<T>(const T *, const BlockShape &, const uint64_t *, T *, uint64_t, cudaStream_t);    \
+    template const char *launch_bw_serial<T, uint16_t>(const BwArgs<T, uint16_t> &, uint64_t, const T *,             \
+                                                       unsigned long long, unsigned long long *, cudaStream_t);      \
+    template const char *launch_bw_serial<T, uint32_t>(const BwArgs<T, uint32_t> &, uint64_t, const T *,             \
+                                                       unsigned long long, unsigned long long *, cudaStream_t);      \
+    template const char *launch_bw_fronts<T, uint16_t>(const BwArgs<T, uint16_t> &, cudaStream_t, int *);            \
+    template const char *launch_bw_fronts<T, uint32_t>(const BwArgs<T, uint32_t> &, cudaStream_t, int *);            \
+    template void launch_bw_spec_coef<T>(const T *, const uint8_t *, uint64_t, int, const QuantParams &,             \
+                                         const QuantParams &, T *, cudaStream_t);                                    \
+    template void launch_bw_gather_fit<T>(const T *, const uint8_t *, int, const uint32_t *, uint64_t, int, T *,     \
+                                          cudaStream_t);
+SZ3B_INST_LZ(float)
+SZ3B_INST_LZ(double)
+
+}  // namespace sz3b

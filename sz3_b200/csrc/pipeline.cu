@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "blockwise.cuh"
+#include "lorenzo.cuh"
 #include "huffman_host.hpp"
 #include "interp_body.cuh"
 #include "interp_plan.hpp"
@@ -683,15 +684,246 @@ static void quantizer_save(std::vector<uint8_t> &out, double eb, int radius, con
     out.insert(out.end(), v, v + unpred.size() * sizeof(T));
 }
 
+// RegressionPredictor::save (RegressionPredictor.hpp:94-107) from the device-side chain results: `nsel` selected
+// blocks, `n_unp` unpredictable coefficients listed (unordered) as (dense position, value); entries at positions
+// >= nsel * (N+1) are leftovers of a discarded speculation and are dropped.
+template <class T>
+static void regression_save(Workspace &ws, int N, unsigned long long nsel, unsigned long long n_unp,
+                            const unsigned long long *upos, const T *uval, const int32_t *coef_q, double eb_indep,
+                            double eb_liner, std::vector<uint8_t> &pred_blob) {
+    const int nc = N + 1;
+    const int kCoefRadius = 32768;
+    const uint64_t n_coef = nsel * nc;
+    // unpredictable coefficients, back in chain order, split by quantizer
+    std::vector<T> un_liner, un_indep;
+    if (n_unp) {
+        std::vector<unsigned long long> pos(n_unp);
+        std::vector<T> val(n_unp);
+        ws.d2h(pos.data(), upos, n_unp * sizeof(unsigned long long));
+        ws.d2h(val.data(), uval, n_unp * sizeof(T));
+        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        std::vector<size_t> order(n_unp);
+        for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pos[a] < pos[b]; });
+        for (size_t i : order) {
+            if (pos[i] >= n_coef) continue;
+            (pos[i] % nc == static_cast<unsigned>(N) ? un_indep : un_liner).push_back(val[i]);
+        }
+    }
+    pred_blob.clear();
+    {
+        uint8_t tmp[8];
+        uint8_t *p = tmp;
+        put<uint64_t>(p, n_coef);
+        pred_blob.insert(pred_blob.end(), tmp, p);
+    }
+    if (n_coef) {
+        quantizer_save<T>(pred_blob, eb_indep, kCoefRadius, un_indep);
+        quantizer_save<T>(pred_blob, eb_liner, kCoefRadius, un_liner);
+        std::vector<uint8_t> side;
+        huffman_encode_device(ws, coef_q, n_coef, side, nullptr);
+        pred_blob.insert(pred_blob.end(), side.begin(), side.end());
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BlockwiseDecomposition with a Lorenzo predictor in the stack (lorenzo.cuh / lorenzo.cu).
+//   Lorenzo only (1st, 2nd, or both composed): one exact wavefront pass.
+//   Lorenzo + regression: selection guess pass, then  exact chain over the guess -> exact wavefront pass  until the
+//   selection reproduces itself; after kBwMaxPasses invalidated guesses the row-major walk (k_bw_serial) finishes
+//   from the first wrong block with the reference's sequential semantics.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kBwMaxPasses = 4;
+
+template <class T, class QT>
+static uint64_t bw_args_init(BwArgs<T, QT> &A, const sz3b_config &conf, const BlockShape &bs, double eb) {
+    memset(&A, 0, sizeof(A));
+    A.bs = bs;
+    uint64_t np = 1;
+    for (int d = bs.N - 1; d >= 0; d--) {
+        A.pstride[d] = np;
+        np *= static_cast<uint64_t>(bs.dims[d]) + kBwPad;
+    }
+    A.qp = make_quant(eb, conf.quantbinCnt / 2);
+    A.noise[0] = lorenzo_noise<T>(bs.N, 1, eb);
+    A.noise[1] = lorenzo_noise<T>(bs.N, 2, eb);
+    if (conf.lorenzo) A.kinds[A.nk++] = PK_LORENZO1;
+    if (conf.lorenzo2) A.kinds[A.nk++] = PK_LORENZO2;
+    if (conf.regression) A.kinds[A.nk++] = PK_REG;
+    const int nc = bs.N + 1;
+    A.q_liner = make_quant(eb / nc / static_cast<unsigned>(conf.blockSize), 32768);
+    A.q_indep = make_quant(eb / nc, 32768);
+    return np;
+}
+
+template <class T, class QT>
+static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double eb, const T *d_data, QT *d_q,
+                                  T *d_unpred_tmp, unsigned long long *d_hist, int nbins, std::vector<uint8_t> &pred_blob,
+                                  int *launches) {
+    const int N = conf.N, nc = N + 1;
+    if (conf.blockSize < 1) fail(SZ3B_E_INVALID_ARGUMENT, "blockSize must be positive");
+    BlockShape bs;
+    block_shape_init(bs, N, conf.dims, static_cast<uint32_t>(conf.blockSize));
+    if (bs.nblocks >= 0xfffffff0ull) fail(SZ3B_E_UNSUPPORTED, "more than 2^32 blocks");
+    BwArgs<T, QT> A;
+    const uint64_t np = bw_args_init<T, QT>(A, conf, bs, eb);
+    const bool has_reg = conf.regression != 0;
+    const int reg_sid = A.nk - 1;   // the regression predictor is always the last of the stack
+    T *W = ws.padded.as<T>(np);
+    A.W = W;
+    A.q = d_q;
+    A.unpred_tmp = d_unpred_tmp;
+    uint8_t *selA = ws.bsel.as<uint8_t>(bs.nblocks), *selB = ws.bsel2.as<uint8_t>(bs.nblocks);
+    uint8_t *sel_final = selA;
+    unsigned *d_mm = ws.misc.as<unsigned>(4);
+    auto pad = [&](uint64_t b_lo) {
+        if (b_lo == 0) SZ3B_CUDA(cudaMemsetAsync(W, 0, np * sizeof(T), ws.st));
+        launch_bw_pad<T>(d_data, bs, A.pstride, W, b_lo, ws.st);
+        *launches += 1;
+    };
+    auto fronts = [&](int mode) {
+        A.mode = mode;
+        if (const char *e = launch_bw_fronts<T, QT>(A, ws.st, launches)) fail(SZ3B_E_UNSUPPORTED, e);
+    };
+    size_t h = ws.stage_begin("predict_quantize");
+    const int l0 = *launches;
+    unsigned long long nsel = 0, n_unp = 0;
+    int32_t *coef_q = nullptr;
+    unsigned long long *upos = nullptr;
+    T *uval = nullptr;
+    if (!has_reg) {
+        pad(0);
+        A.sel_out = selA;
+        fronts(BW_EXACT);
+    } else {
+        T *c_fit = ws.coef.as<T>(bs.nblocks * nc);
+        T *c_rec = ws.coef2.as<T>(bs.nblocks * nc);
+        T *c_spec = ws.cspec.as<T>(bs.nblocks * nc);
+        T *c_dense = ws.cdense.as<T>(bs.nblocks * nc);
+        uint8_t *valid = ws.flags.as<uint8_t>(bs.nblocks);
+        uint32_t *rank = ws.brank.as<uint32_t>(bs.nblocks + 1);
+        coef_q = ws.coef_q.as<int32_t>(bs.nblocks * nc);
+        unsigned long long *counters = ws.counters.as<unsigned long long>(4);
+        upos = ws.cpos.as<unsigned long long>(2 * bs.nblocks * nc + 16);
+        uval = ws.cval.as<T>(2 * bs.nblocks * nc + 16);
+        launch_reg_fit<T>(d_data, bs, c_fit, valid, ws.st);
+        launch_bw_spec_coef<T>(c_fit, valid, bs.nblocks, N, A.q_liner, A.q_indep, c_spec, ws.st);
+        *launches += 2;
+        A.c_fit = c_fit;
+        A.fit_valid = valid;
+        A.c_spec = c_spec;
+        A.c_rec = c_rec;
+        A.rank = rank;
+        A.mismatch = d_mm;
+        pad(0);
+        A.sel_out = selA;
+        fronts(BW_SPEC);
+        for (int pass = 1;; pass++) {
+            launch_bw_rank(selA, bs.nblocks, reg_sid, rank, counters + 2, ws.st);
+            launch_bw_gather_fit<T>(c_fit, selA, reg_sid, rank, bs.nblocks, nc, c_dense, ws.st);
+            *launches += 2;
+            ws.d2h(&nsel, counters + 2, sizeof(nsel));
+            SZ3B_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ws.st));
+            SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+            if (nsel) {
+                launch_reg_chain<T>(c_dense, nullptr, nsel, N, A.q_liner, A.q_indep, coef_q, c_rec, counters, upos, uval, ws.st);
+                *launches += 1;
+            }
+            pad(0);
+            const unsigned mm_init[2] = {0u, ~0u};
+            ws.h2d(d_mm, mm_init, sizeof(mm_init));
+            A.sel_in = selA;
+            A.sel_out = selB;
+            fronts(BW_EXACT);
+            unsigned mm[2];
+            ws.d2h(mm, d_mm, sizeof(mm));
+            ws.d2h(&n_unp, counters + 1, sizeof(n_unp));
+            SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+            SZ3B_CUDA(cudaGetLastError());
+            if (mm[0] == 0) {
+                sel_final = selA;
+                break;
+            }
+            if (pass >= kBwMaxPasses) {
+                const uint64_t b_lo = mm[1];
+                uint32_t nsel0 = 0;
+                ws.d2h(&nsel0, rank + b_lo, sizeof(nsel0));
+                SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+                if (n_unp) {   // keep only the stored coefficients of the final prefix
+                    std::vector<unsigned long long> pos(n_unp);
+                    std::vector<T> val(n_unp);
+                    ws.d2h(pos.data(), upos, n_unp * sizeof(unsigned long long));
+                    ws.d2h(val.data(), uval, n_unp * sizeof(T));
+                    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+                    unsigned long long kept = 0;
+                    for (unsigned long long i = 0; i < n_unp; i++)
+                        if (pos[i] < static_cast<unsigned long long>(nsel0) * nc) {
+                            pos[kept] = pos[i];
+                            val[kept] = val[i];
+                            kept++;
+                        }
+                    if (kept) {
+                        ws.h2d(upos, pos.data(), kept * sizeof(unsigned long long));
+                        ws.h2d(uval, val.data(), kept * sizeof(T));
+                    }
+                    ws.h2d(counters + 1, &kept, sizeof(kept));
+                    SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // pos / val are locals
+                }
+                pad(b_lo);
+                A.mode = BW_SERIAL;
+                A.sel_in = nullptr;
+                A.coef_q = coef_q;
+                A.n_unpred_coef = counters + 1;
+                A.unpred_pos = upos;
+                A.unpred_val = uval;
+                if (const char *e = launch_bw_serial<T, QT>(A, b_lo, nsel0 ? c_rec + static_cast<uint64_t>(nsel0 - 1) * nc : nullptr,
+                                                            nsel0, counters + 2, ws.st))
+                    fail(SZ3B_E_UNSUPPORTED, e);
+                *launches += 1;
+                ws.d2h(&n_unp, counters + 1, sizeof(n_unp));
+                ws.d2h(&nsel, counters + 2, sizeof(nsel));
+                SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+                SZ3B_CUDA(cudaGetLastError());
+                sel_final = selB;
+                break;
+            }
+            std::swap(selA, selB);
+        }
+    }
+    SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
+    launch_histogram<QT>(d_q, bs.num, 0, nbins, conf.quantbinCnt / 2, d_hist, ws.st);
+    *launches += 1;
+    ws.stage_end(h, *launches - l0);
+    SZ3B_CUDA(cudaGetLastError());
+    // ComposedPredictor::save (ComposedPredictor.hpp:52-64): predictors in order (only regression stores anything),
+    // then the per-block selection, Huffman coded
+    pred_blob.clear();
+    if (has_reg)
+        regression_save<T>(ws, N, nsel, n_unp, upos, uval, coef_q, eb / nc, eb / nc / static_cast<unsigned>(conf.blockSize),
+                           pred_blob);
+    if (A.nk > 1) {
+        uint8_t tmp[8];
+        uint8_t *p = tmp;
+        put<uint64_t>(p, bs.nblocks);
+        pred_blob.insert(pred_blob.end(), tmp, p);
+        int32_t *d_sel32 = ws.side_q.as<int32_t>(bs.nblocks);
+        launch_widen_u8(sel_final, bs.nblocks, d_sel32, ws.st);
+        std::vector<uint8_t> side;
+        huffman_encode_device(ws, d_sel32, bs.nblocks, side, nullptr);
+        pred_blob.insert(pred_blob.end(), side.begin(), side.end());
+    }
+}
+
 template <class T, class QT>
 static void run_blockwise(Workspace &ws, const sz3b_config &conf, double eb, const T *d_data, QT *d_q, T *d_unpred_tmp,
                           unsigned long long *d_hist, int nbins, std::vector<uint8_t> &pred_blob, int *launches) {
     const int N = conf.N;
     const int method_cnt = (conf.lorenzo != 0) + (conf.lorenzo2 != 0) + (conf.regression != 0);
     if (method_cnt == 0) fail(SZ3B_E_INVALID_ARGUMENT, "All lorenzo and regression methods are disabled.");
-    if (conf.lorenzo || conf.lorenzo2)
-        fail(SZ3B_E_UNSUPPORTED,
-             "ALGO_LORENZO_REG with a Lorenzo predictor is not on the GPU path yet (regression-only is; DESIGN.md)");
+    if (conf.lorenzo || conf.lorenzo2) {
+        run_blockwise_lorenzo<T, QT>(ws, conf, eb, d_data, d_q, d_unpred_tmp, d_hist, nbins, pred_blob, launches);
+        return;
+    }
     if (conf.blockSize < 1) fail(SZ3B_E_INVALID_ARGUMENT, "blockSize must be positive");
     BlockShape bs;
     block_shape_init(bs, N, conf.dims, static_cast<uint32_t>(conf.blockSize));
@@ -725,35 +957,7 @@ static void run_blockwise(Workspace &ws, const sz3b_config &conf, double eb, con
     SZ3B_CUDA(cudaStreamSynchronize(ws.st));
     SZ3B_CUDA(cudaGetLastError());
     *launches += 2;
-    const uint64_t n_coef = hc[0] * nc;
-    // unpredictable coefficients, back in chain order, split by quantizer
-    std::vector<T> un_liner, un_indep;
-    if (hc[1]) {
-        std::vector<unsigned long long> pos(hc[1]);
-        std::vector<T> val(hc[1]);
-        ws.d2h(pos.data(), upos, hc[1] * sizeof(unsigned long long));
-        ws.d2h(val.data(), uval, hc[1] * sizeof(T));
-        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-        std::vector<size_t> order(hc[1]);
-        for (size_t i = 0; i < order.size(); i++) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pos[a] < pos[b]; });
-        for (size_t i : order) (pos[i] % nc == static_cast<unsigned>(N) ? un_indep : un_liner).push_back(val[i]);
-    }
-    // RegressionPredictor::save (RegressionPredictor.hpp:94-107)
-    pred_blob.clear();
-    {
-        uint8_t tmp[8];
-        uint8_t *p = tmp;
-        put<uint64_t>(p, n_coef);
-        pred_blob.insert(pred_blob.end(), tmp, p);
-    }
-    if (n_coef) {
-        quantizer_save<T>(pred_blob, eb_indep, kCoefRadius, un_indep);
-        quantizer_save<T>(pred_blob, eb_liner, kCoefRadius, un_liner);
-        std::vector<uint8_t> side;
-        huffman_encode_device(ws, coef_q, n_coef, side, nullptr);
-        pred_blob.insert(pred_blob.end(), side.begin(), side.end());
-    }
+    regression_save<T>(ws, N, hc[0], hc[1], upos, uval, coef_q, eb_indep, eb_liner, pred_blob);
     h = ws.stage_begin("predict_quantize");
     SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
     if (const char *e = launch_reg_predict<T, QT>(d_data, bs, c_rec, make_quant(eb, conf.quantbinCnt / 2), d_q,
@@ -1172,11 +1376,123 @@ static void interp_decompress_t(Workspace &ws, const sz3b_config &conf, Cursor &
     SZ3B_CUDA(cudaGetLastError());
 }
 
+// BlockwiseDecomposition::decompress with a Lorenzo predictor in the stack (BlockwiseDecomposition.hpp:48-67,75-79;
+// ComposedPredictor::load :66-78; RegressionPredictor::load :109-123): the selection and the coefficient indices come
+// from the stream, so one wavefront pass in recover mode suffices.
+template <class T, class QT>
+static void blockwise_decompress_lorenzo(Workspace &ws, const sz3b_config &conf, Cursor &c, T *d_out) {
+    const int N = conf.N, nc = N + 1;
+    if (conf.blockSize < 1) fail(SZ3B_E_INVALID_ARGUMENT, "blockSize must be positive");
+    BlockShape bs;
+    block_shape_init(bs, N, conf.dims, static_cast<uint32_t>(conf.blockSize));
+    if (bs.nblocks >= 0xfffffff0ull) fail(SZ3B_E_UNSUPPORTED, "more than 2^32 blocks");
+    BwArgs<T, QT> A;
+    const uint64_t np = bw_args_init<T, QT>(A, conf, bs, 1.0);
+    const bool has_reg = conf.regression != 0;
+    const int reg_sid = A.nk - 1;
+    // predictors in stack order: only the regression predictor stores anything
+    uint64_t n_coef = 0;
+    double eb_i = 0, eb_l = 0;
+    int rad_i = 0, rad_l = 0;
+    std::vector<int32_t> cq;
+    std::vector<T> cun;
+    if (has_reg) {
+        n_coef = c.get<uint64_t>();
+        if (n_coef % nc || n_coef / nc > bs.nblocks) fail(SZ3B_E_INVALID_ARGUMENT, "coefficient count does not match the block grid");
+        if (n_coef) {
+            const T *un_i, *un_l;
+            uint64_t nun_i, nun_l;
+            quantizer_load<T>(c, &eb_i, &rad_i, &un_i, &nun_i);
+            quantizer_load<T>(c, &eb_l, &rad_l, &un_l, &nun_l);
+            cq.resize(n_coef);
+            HuffmanDecoder dec;
+            const char *err = nullptr;
+            if (!dec.load(c.p, c.rem, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+            if (!dec.decode<int32_t>(c.p, c.rem, n_coef, cq.data(), &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+            cun.assign(n_coef, 0);
+            uint64_t ki = 0, kl = 0;
+            for (uint64_t pos = 0; pos < n_coef; pos++)
+                if (cq[pos] == 0) {
+                    if (pos % nc == static_cast<unsigned>(N)) {
+                        if (ki >= nun_i) fail(SZ3B_E_INVALID_ARGUMENT, "truncated stream (coefficients)");
+                        cun[pos] = un_i[ki++];
+                    } else {
+                        if (kl >= nun_l) fail(SZ3B_E_INVALID_ARGUMENT, "truncated stream (coefficients)");
+                        cun[pos] = un_l[kl++];
+                    }
+                }
+        }
+    }
+    std::vector<uint8_t> sel8;
+    if (A.nk > 1) {
+        const uint64_t n_sel = c.get<uint64_t>();
+        if (n_sel != bs.nblocks) fail(SZ3B_E_INVALID_ARGUMENT, "selection count does not match the block grid");
+        std::vector<int32_t> sel(n_sel);
+        HuffmanDecoder dec;
+        const char *err = nullptr;
+        if (!dec.load(c.p, c.rem, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+        if (!dec.decode<int32_t>(c.p, c.rem, n_sel, sel.data(), &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+        sel8.resize(n_sel);
+        uint64_t n_reg = 0;
+        for (uint64_t b = 0; b < n_sel; b++) {
+            if (sel[b] < 0 || sel[b] >= A.nk) fail(SZ3B_E_INVALID_ARGUMENT, "predictor selection out of range");
+            sel8[b] = static_cast<uint8_t>(sel[b]);
+            n_reg += has_reg && sel[b] == reg_sid;
+        }
+        if (has_reg && n_reg * nc != n_coef) fail(SZ3B_E_INVALID_ARGUMENT, "coefficient count does not match the selection");
+    }
+    double eb;
+    int radius;
+    const T *h_unpred;
+    uint64_t n_unpred;
+    quantizer_load<T>(c, &eb, &radius, &h_unpred, &n_unpred);
+    if ((radius <= 32768) != (sizeof(QT) == 2)) fail(SZ3B_E_INVALID_ARGUMENT, "quantizer radius does not match Config.quantbinCnt");
+    A.qp = make_quant(eb, radius);
+    QT *d_q = decode_indices<QT>(ws, c, bs.num);
+    int launches = 0;
+    size_t h = ws.stage_begin("recover");
+    if (A.nk > 1) {
+        uint8_t *d_sel = ws.bsel.as<uint8_t>(bs.nblocks);
+        ws.h2d(d_sel, sel8.data(), bs.nblocks);
+        A.sel_in = d_sel;
+        if (has_reg) {
+            uint32_t *rank = ws.brank.as<uint32_t>(bs.nblocks + 1);
+            unsigned long long *counters = ws.counters.as<unsigned long long>(4);
+            launch_bw_rank(d_sel, bs.nblocks, reg_sid, rank, counters + 2, ws.st);
+            launches++;
+            A.rank = rank;
+            if (n_coef) {
+                int32_t *d_cq = ws.coef_q.as<int32_t>(n_coef);
+                T *d_cun = ws.coef.as<T>(n_coef);
+                T *d_crec = ws.coef2.as<T>(n_coef);
+                ws.h2d(d_cq, cq.data(), n_coef * sizeof(int32_t));
+                ws.h2d(d_cun, cun.data(), n_coef * sizeof(T));
+                launch_reg_chain_recover<T>(d_cq, d_cun, n_coef / nc, N, make_quant(eb_l, rad_l), make_quant(eb_i, rad_i), d_crec,
+                                            ws.st);
+                launches++;
+                A.c_rec = d_crec;
+            }
+        }
+    }
+    A.unpred_tmp = place_unpred<T, QT>(ws, d_q, bs.num, h_unpred, n_unpred, &launches);
+    A.q = d_q;
+    A.out = d_out;
+    A.W = ws.padded.as<T>(np);
+    SZ3B_CUDA(cudaMemsetAsync(A.W, 0, np * sizeof(T), ws.st));
+    A.mode = BW_DECODE;
+    if (const char *e = launch_bw_fronts<T, QT>(A, ws.st, &launches)) fail(SZ3B_E_UNSUPPORTED, e);
+    ws.stage_end(h, launches);
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // cq / cun / sel8 are host vectors
+    SZ3B_CUDA(cudaGetLastError());
+}
+
 template <class T, class QT>
 static void blockwise_decompress_t(Workspace &ws, const sz3b_config &conf, Cursor &c, T *d_out) {
     const int N = conf.N;
-    if (conf.lorenzo || conf.lorenzo2)
-        fail(SZ3B_E_UNSUPPORTED, "ALGO_LORENZO_REG streams with a Lorenzo predictor are not on the GPU path yet");
+    if (conf.lorenzo || conf.lorenzo2) {
+        blockwise_decompress_lorenzo<T, QT>(ws, conf, c, d_out);
+        return;
+    }
     if (!conf.regression) fail(SZ3B_E_INVALID_ARGUMENT, "All lorenzo and regression methods are disabled.");
     BlockShape bs;
     block_shape_init(bs, N, conf.dims, static_cast<uint32_t>(conf.blockSize));

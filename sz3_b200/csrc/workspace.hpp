@@ -97,6 +97,8 @@ struct Workspace {
     DevBuf cubes, cube_q, cube_unpred, cube_recon, flags, starts;
     // side streams / blockwise
     DevBuf coef, coef2, coef_q, side_q, misc, counters, cpos, cval, hist2;
+    // Lorenzo stacks (lorenzo.cu): padded working array, block selections, dense ranks, coefficient guesses
+    DevBuf padded, bsel, bsel2, brank, cspec, cdense;
     // Huffman decode
     DevBuf hd_bits, hd_tab, hd_over, hd_counts, hd_offs;
     // pinned staging

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <barrier>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -260,4 +261,229 @@ extern "C" int emul_regression_decompose(int dtype, const sz3b_config *c, double
                               static_cast<float *>(unpred_out), n_unpred);
     return run_reg<double>(*c, eb, static_cast<const double *>(data), quant_out, coef_q_out, n_coef,
                            static_cast<double *>(unpred_out), n_unpred);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BlockwiseDecomposition with a Lorenzo predictor in the stack (lorenzo.cuh): the block wavefront in front order, the
+// selection-guess / exact-chain / exact-pass iteration of pipeline.cu, then (optionally) the decode pass.
+// Returns the number of exact passes that were needed (>= 1), negative on error.
+// ---------------------------------------------------------------------------------------------------------------------
+#include "../../sz3_b200/csrc/lorenzo.cuh"
+
+template <class T>
+static void emul_fronts(const BwArgs<T, uint32_t> &A) {
+    const BlockShape &bs = A.bs;
+    const int N = bs.N;
+    std::vector<T> scratch(bw_scratch_elems(bs, A.nk));
+    size_t tile_cap = 1;
+    for (int d = 0; d < N; d++) tile_cap *= (bs.dims[d] < bs.B ? bs.dims[d] : bs.B) + kBwPad;
+    uint64_t grid = 1;
+    for (int d = 0; d < N - 1; d++) grid *= bs.nb[d];
+    const uint32_t nfronts = bw_num_fronts(bs);
+    for (uint32_t f = 0; f < nfronts; f++)
+        for (uint64_t cta = grid; cta-- > 0;) {   // reverse order inside a front: blocks of a front are independent
+            uint32_t bi[kMaxDim] = {0, 0, 0, 0};
+            uint64_t r = cta;
+            uint32_t s = 0;
+            for (int d = N - 2; d >= 0; d--) {
+                bi[d] = static_cast<uint32_t>(r % bs.nb[d]);
+                r /= bs.nb[d];
+                s += bi[d];
+            }
+            if (f < s || f - s >= bs.nb[N - 1]) continue;
+            bi[N - 1] = f - s;
+            bw_process_block<T, uint32_t>(A, bi, scratch.data(), scratch.data() + tile_cap, 0, 1);
+        }
+}
+
+template <class T>
+static int run_lorenzo(const sz3b_config &c, double eb, const T *data, int32_t *quant_out, uint8_t *sel_out,
+                       int32_t *coef_q_out, size_t *n_coef, T *unpred_out, size_t *n_unpred, T *decoded) {
+    BlockShape bs;
+    block_shape_init(bs, c.N, c.dims, static_cast<uint32_t>(c.blockSize));
+    const int N = c.N, nc = N + 1;
+    BwArgs<T, uint32_t> A;
+    memset(&A, 0, sizeof(A));
+    A.bs = bs;
+    uint64_t np = 1;
+    for (int d = N - 1; d >= 0; d--) {
+        A.pstride[d] = np;
+        np *= bs.dims[d] + kBwPad;
+    }
+    A.qp = make_quant(eb, c.quantbinCnt / 2);
+    A.noise[0] = lorenzo_noise<T>(N, 1, eb);
+    A.noise[1] = lorenzo_noise<T>(N, 2, eb);
+    if (c.lorenzo) A.kinds[A.nk++] = PK_LORENZO1;
+    if (c.lorenzo2) A.kinds[A.nk++] = PK_LORENZO2;
+    if (c.regression) A.kinds[A.nk++] = PK_REG;
+    const bool has_reg = c.regression != 0 && A.nk > 1;
+    int reg_sid = -1;
+    for (int k = 0; k < A.nk; k++)
+        if (A.kinds[k] == PK_REG) reg_sid = k;
+    std::vector<T> W(np), c_fit(bs.nblocks * nc, 0), c_spec(bs.nblocks * nc, 0), c_rec(bs.nblocks * nc, 0), un(bs.num, 0);
+    std::vector<uint8_t> valid(bs.nblocks, 0), selA(bs.nblocks, 0), selB(bs.nblocks, 0);
+    std::vector<uint32_t> rank(bs.nblocks, 0), q(bs.num, 0);
+    QuantParams ql = make_quant(eb / nc / static_cast<unsigned>(c.blockSize), 32768), qi = make_quant(eb / nc, 32768);
+    auto pad = [&]() {
+        std::fill(W.begin(), W.end(), static_cast<T>(0));
+        for (uint64_t i = 0; i < bs.num; i++) {
+            uint64_t r = i, w = 0;
+            for (int d = N - 1; d >= 0; d--) {
+                w += (r % bs.dims[d] + kBwPad) * A.pstride[d];
+                r /= bs.dims[d];
+            }
+            W[w] = data[i];
+        }
+    };
+    A.W = W.data();
+    A.q = q.data();
+    A.unpred_tmp = un.data();
+    unsigned mm[2] = {0, ~0u};
+    A.mismatch = mm;
+    int passes = 0;
+    *n_coef = 0;
+    const char *kmax_env = getenv("EMUL_KMAX");
+    const int kmax = kmax_env ? atoi(kmax_env) : 3;   // exact wavefront passes before the row-major walk takes over
+    std::vector<uint8_t> *final_sel = &selA;
+    if (has_reg) {
+        for (uint64_t b = 0; b < bs.nblocks; b++) {
+            T coef[kMaxDim + 1];
+            valid[b] = reg_fit_block<T>(data, bs, b, coef) ? 1 : 0;
+            if (valid[b])
+                for (int d = 0; d < nc; d++) {
+                    c_fit[b * nc + d] = coef[d];
+                    c_spec[b * nc + d] = coef_lattice_guess<T>(coef[d], d < N ? ql : qi);
+                }
+        }
+        A.c_fit = c_fit.data();
+        A.fit_valid = valid.data();
+        A.c_spec = c_spec.data();
+        A.c_rec = c_rec.data();
+        A.rank = rank.data();
+        A.q_liner = ql;
+        A.q_indep = qi;
+        pad();
+        A.mode = BW_SPEC;
+        A.sel_out = selA.data();
+        emul_fronts(A);
+        for (;;) {
+            // exact chain over the guessed selection (dense)
+            T prev[kMaxDim + 1] = {0, 0, 0, 0, 0};
+            size_t k = 0;
+            uint32_t nsel = 0;
+            for (uint64_t b = 0; b < bs.nblocks; b++) {
+                rank[b] = nsel;
+                if (selA[b] != reg_sid) continue;
+                for (int d = 0; d < nc; d++) {
+                    T rec;
+                    coef_q_out[k++] = quantize<T>(c_fit[b * nc + d], prev[d], d < N ? ql : qi, rec);
+                    prev[d] = rec;
+                    c_rec[static_cast<size_t>(nsel) * nc + d] = rec;
+                }
+                nsel++;
+            }
+            *n_coef = k;
+            pad();
+            mm[0] = 0;
+            mm[1] = ~0u;
+            A.mode = BW_EXACT;
+            A.sel_in = selA.data();
+            A.sel_out = selB.data();
+            emul_fronts(A);
+            passes++;
+            if (getenv("EMUL_VERBOSE"))
+                fprintf(stderr, "pass %d: %u mismatches, first at block %u of %llu, nsel %u\n", passes, mm[0], mm[1],
+                        (unsigned long long)bs.nblocks, nsel);
+            if (mm[0] == 0) break;
+            if (passes >= kmax) {
+                // row-major walk from the first wrong guess (k_bw_serial)
+                const uint64_t b_lo = mm[1];
+                BwSerial<T> st;
+                st.nsel = rank[b_lo];
+                for (int d = 0; d < nc; d++) st.prev[d] = st.nsel ? c_rec[(st.nsel - 1) * nc + d] : static_cast<T>(0);
+                for (uint64_t i = 0; i < bs.num; i++) {   // k_bw_pad with b_lo
+                    uint64_t r = i, w = 0, b = 0, bmul = 1;
+                    for (int d = N - 1; d >= 0; d--) {
+                        const uint64_t x = r % bs.dims[d];
+                        r /= bs.dims[d];
+                        w += (x + kBwPad) * A.pstride[d];
+                        b += (x / bs.B) * bmul;
+                        bmul *= bs.nb[d];
+                    }
+                    if (b >= b_lo) W[w] = data[i];
+                }
+                std::vector<T> scratch(bw_scratch_elems(bs, A.nk));
+                size_t tile_cap = 1;
+                for (int d = 0; d < N; d++) tile_cap *= (bs.dims[d] < bs.B ? bs.dims[d] : bs.B) + kBwPad;
+                std::vector<unsigned long long> upos(bs.nblocks * nc + 1);
+                std::vector<T> uval(bs.nblocks * nc + 1);
+                unsigned long long nuc = 0;
+                A.mode = BW_SERIAL;
+                A.coef_q = coef_q_out;
+                A.n_unpred_coef = &nuc;
+                A.unpred_pos = upos.data();
+                A.unpred_val = uval.data();
+                for (uint64_t b = b_lo; b < bs.nblocks; b++) {
+                    uint32_t bi[kMaxDim] = {0, 0, 0, 0};
+                    uint64_t r = b;
+                    for (int d = N - 1; d >= 0; d--) {
+                        bi[d] = static_cast<uint32_t>(r % bs.nb[d]);
+                        r /= bs.nb[d];
+                    }
+                    bw_process_block<T, uint32_t>(A, bi, scratch.data(), scratch.data() + tile_cap, 0, 1, &st);
+                }
+                *n_coef = st.nsel * nc;
+                final_sel = &selB;
+                passes = -passes;   // reported as negative: finished by the walk
+                break;
+            }
+            selA.swap(selB);
+        }
+    } else {
+        pad();
+        A.mode = BW_EXACT;
+        A.sel_in = nullptr;
+        A.sel_out = selA.data();
+        emul_fronts(A);
+        passes = 1;
+    }
+    for (uint64_t i = 0; i < bs.num; i++) quant_out[i] = static_cast<int32_t>(q[i]);
+    memcpy(sel_out, final_sel->data(), bs.nblocks);
+    size_t nu = 0;
+    for (uint64_t i = 0; i < bs.num; i++)
+        if (q[i] == 0) unpred_out[nu++] = un[i];
+    *n_unpred = nu;
+    if (decoded) {
+        std::fill(W.begin(), W.end(), static_cast<T>(0));
+        A.mode = BW_DECODE;
+        A.sel_in = final_sel->data();
+        if (has_reg) {   // dense chain recover over the final selection (k_reg_chain_recover + k_bw_rank)
+            T cur[kMaxDim + 1] = {0, 0, 0, 0, 0};
+            uint32_t nsel = 0;
+            size_t k = 0;
+            for (uint64_t b = 0; b < bs.nblocks; b++) {
+                rank[b] = nsel;
+                if ((*final_sel)[b] != reg_sid) continue;
+                for (int d = 0; d < nc; d++) {
+                    const int qv = coef_q_out[k++];
+                    cur[d] = qv ? recover_pred<T>(cur[d], qv, d < N ? ql : qi) : c_fit[b * nc + d];   // 0: stored exactly
+                    c_rec[static_cast<size_t>(nsel) * nc + d] = cur[d];
+                }
+                nsel++;
+            }
+        }
+        A.out = decoded;
+        emul_fronts(A);
+    }
+    return passes;
+}
+
+extern "C" int emul_lorenzo_decompose(int dtype, const sz3b_config *c, double eb, const void *data, int32_t *quant_out,
+                                      uint8_t *sel_out, int32_t *coef_q_out, size_t *n_coef, void *unpred_out,
+                                      size_t *n_unpred, void *decoded) {
+    if (dtype == 0)
+        return run_lorenzo<float>(*c, eb, static_cast<const float *>(data), quant_out, sel_out, coef_q_out, n_coef,
+                                  static_cast<float *>(unpred_out), n_unpred, static_cast<float *>(decoded));
+    return run_lorenzo<double>(*c, eb, static_cast<const double *>(data), quant_out, sel_out, coef_q_out, n_coef,
+                               static_cast<double *>(unpred_out), n_unpred, static_cast<double *>(decoded));
 }

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import (ALGO_INTERP, ALGO_LORENZO_REG, dtype_code, emul_lib, field_nd, interp_blob_unpred, make_config,
+from common import (ALGO_INTERP, ALGO_LORENZO_REG, dtype_code, emul_lib, field_g3, field_nd, interp_blob_unpred, make_config,
                     ref_blockwise, ref_interp, ref_lib)
 
 pytestmark = pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref not built")
@@ -136,3 +136,58 @@ def test_emul_lean_per_pass_matches_reference(shape, dtype, kw):
     assert np.array_equal(q, q_ref), f"{int((q != q_ref).sum())} of {q.size} indices differ"
     _, un_ref = interp_blob_unpred(blob_ref, conf.N, dtype)
     assert np.array_equal(un, un_ref)
+
+
+@pytest.mark.parametrize("shape,dtype,eb,kw", [
+    ((24, 30, 36), np.float32, 1e-3, dict(lorenzo=1, regression=0)),
+    ((20, 33, 47), np.float32, 1e-3, dict(lorenzo=1, regression=1)),
+    ((30, 31, 32), np.float64, 1e-4, dict(lorenzo=1, lorenzo2=1, regression=1)),
+    ((30, 31, 32), np.float32, 1e-2, dict(lorenzo=0, lorenzo2=1, regression=1)),
+    ((40, 45), np.float32, 1e-3, dict(lorenzo=1, regression=1, blockSize=16)),
+    ((3000,), np.float32, 1e-3, dict(lorenzo=1, lorenzo2=1, regression=0, blockSize=128)),
+    ((9, 12, 13, 7), np.float64, 1e-3, dict(lorenzo=1, lorenzo2=1, regression=1, blockSize=4)),
+    ((61, 67, 73), np.float32, 1e-4, dict(lorenzo=1, lorenzo2=1, regression=1)),
+    ((25, 31, 37), np.float32, 1e-3, dict(lorenzo=1, regression=1, quantbinCnt=16)),
+])
+@pytest.mark.parametrize("kmax", [1, 50])
+def test_emul_lorenzo_stacks_match_reference(shape, dtype, eb, kw, kmax, monkeypatch):
+    """Block wavefront + selection iteration of lorenzo.cuh (kmax = 50) and the row-major walk that takes over after
+    kmax invalidated guesses (kmax = 1), both against the reference's sequential BlockwiseDecomposition."""
+    monkeypatch.setenv("EMUL_KMAX", str(kmax))
+    data = field_nd(shape, dtype)
+    conf = make_config(shape, cmprAlgo=ALGO_LORENZO_REG, **kw)
+    q_ref, blob_ref = ref_blockwise(ref_lib(), data, conf, eb)
+    E = emul_lib()
+    q = np.empty(data.size, np.int32)
+    sel = np.empty(data.size, np.uint8)
+    cq = np.empty(data.size * 2 + 64, np.int32)
+    un = np.empty(data.size, dtype)
+    dec = np.empty(data.size, dtype)
+    ncoef, nun = C.c_size_t(0), C.c_size_t(0)
+    rc = E.emul_lorenzo_decompose(dtype_code(data), C.byref(conf), C.c_double(eb), data.ctypes.data_as(C.c_void_p),
+                                  q.ctypes.data_as(C.c_void_p), sel.ctypes.data_as(C.c_void_p), cq.ctypes.data_as(C.c_void_p),
+                                  C.byref(ncoef), un.ctypes.data_as(C.c_void_p), C.byref(nun), dec.ctypes.data_as(C.c_void_p))
+    assert rc != 0 and rc > -60
+    assert np.array_equal(q, q_ref), f"{int((q != q_ref).sum())} of {q.size} indices differ"
+    if nun.value:
+        tail = np.frombuffer(blob_ref[len(blob_ref) - nun.value * data.itemsize:], dtype)
+        assert np.array_equal(tail, un[:nun.value])
+    assert np.max(np.abs(dec.reshape(shape).astype(np.float64) - data)) <= eb
+
+
+def test_emul_lorenzo_noisy_field_walk():
+    """Regression-heavy selection (G3 noise, eb 1e-2): several exact passes, finished by the walk."""
+    data = field_g3((100, 100, 100))
+    conf = make_config(data.shape, cmprAlgo=ALGO_LORENZO_REG)
+    q_ref, _ = ref_blockwise(ref_lib(), data, conf, 1e-2)
+    E = emul_lib()
+    q = np.empty(data.size, np.int32)
+    sel = np.empty(data.size, np.uint8)
+    cq = np.empty(data.size * 2 + 64, np.int32)
+    un = np.empty(data.size, np.float32)
+    ncoef, nun = C.c_size_t(0), C.c_size_t(0)
+    rc = E.emul_lorenzo_decompose(0, C.byref(conf), C.c_double(1e-2), data.ctypes.data_as(C.c_void_p),
+                                  q.ctypes.data_as(C.c_void_p), sel.ctypes.data_as(C.c_void_p), cq.ctypes.data_as(C.c_void_p),
+                                  C.byref(ncoef), un.ctypes.data_as(C.c_void_p), C.byref(nun), None)
+    assert rc == -3, rc
+    assert np.array_equal(q, q_ref)

@@ -2,7 +2,7 @@
 
 Bar: bit-identical quantization indices, byte-identical decomposition blob (coefficient side stream included) and
 whole stream; every stream decodes with the unmodified reference decoder within the bound.
-Built so far on the GPU: the regression-only predictor stack (BASELINE.json config #3)."""
+Covers the regression-only stack (BASELINE.json config #3) and every stack with a Lorenzo predictor."""
 import ctypes as C
 
 import numpy as np
@@ -89,17 +89,72 @@ def test_regression_stream_identical_and_bounded(shape, dtype, kw):
     assert np.max(np.abs(dec.astype(np.float64) - data.astype(np.float64))) <= dconf.absErrorBound
 
 
-def test_composed_predictors_say_unsupported():
-    """Lorenzo stacks are not on the GPU path yet: the library must say so instead of producing a different stream."""
+LORENZO_STACKS = [
+    ((24, 30, 36), np.float32, 1e-3, dict(lorenzo=1, regression=0)),
+    ((24, 30, 36), np.float64, 1e-4, dict(lorenzo=0, lorenzo2=1, regression=0)),
+    ((20, 33, 47), np.float32, 1e-3, dict(lorenzo=1, regression=1)),                      # the default stack
+    ((30, 31, 32), np.float64, 1e-4, dict(lorenzo=1, lorenzo2=1, regression=1)),
+    ((30, 31, 32), np.float32, 1e-2, dict(lorenzo=0, lorenzo2=1, regression=1)),
+    ((31, 37, 25), np.float32, 1e-3, dict(lorenzo=1, lorenzo2=1, regression=0)),
+    ((40, 45), np.float32, 1e-3, dict(lorenzo=1, regression=1, blockSize=16)),
+    ((130, 77), np.float64, 1e-3, dict(lorenzo=1, lorenzo2=1, regression=1, blockSize=16)),
+    ((3000,), np.float32, 1e-3, dict(lorenzo=1, lorenzo2=1, regression=0, blockSize=128)),
+    ((3000,), np.float32, 1e-3, dict(lorenzo=1, regression=1, blockSize=128)),
+    ((9, 12, 20, 18), np.float32, 1e-3, dict(lorenzo=1, regression=1)),
+    ((9, 12, 13, 7), np.float64, 1e-3, dict(lorenzo=1, lorenzo2=1, regression=1, blockSize=4)),
+    ((61, 67, 73), np.float32, 1e-4, dict(lorenzo=1, lorenzo2=1, regression=1)),
+    ((25, 31, 37), np.float32, 1e-3, dict(lorenzo=1, regression=1, quantbinCnt=16)),     # mostly unpredictable
+    ((30, 30, 30), np.float32, 1e-3, dict(lorenzo=1, regression=1, blockSize=10)),
+    ((19, 19, 19), np.float32, 1e-3, dict(lorenzo=1, regression=1)),                      # clipped blocks of extent 1
+]
+
+
+@pytest.mark.parametrize("shape,dtype,eb,kw", LORENZO_STACKS)
+def test_lorenzo_stack_decomposition_identical(shape, dtype, eb, kw):
+    """Lorenzo / composed stacks (block wavefront, lorenzo.cu): indices, selection and coefficient side streams."""
+    data = field_nd(shape, dtype)
+    conf = make_config(shape, cmprAlgo=ALGO_LORENZO_REG, **kw)
+    q_ref, blob_ref = ref_blockwise(ref_lib(), data, conf, eb)
+    q, blob = gpu_blockwise(data, conf, eb)
+    assert np.array_equal(q, q_ref), f"{int((q != q_ref).sum())} of {q.size} indices differ"
+    assert blob == blob_ref, (len(blob), len(blob_ref))
+
+
+@pytest.mark.parametrize("n,eb", [(128, 1e-3), (100, 1e-2), (200, 1e-2)])
+def test_lorenzo_regression_noisy_field(n, eb):
+    """G3 with its noise term makes the regression predictor win often: the selection iteration needs several exact
+    passes and, at 200^3, is finished by the row-major walk; the stream must still be the reference's, byte for byte."""
+    data = field_g3((n, n, n))
+    conf = make_config(data.shape, cmprAlgo=ALGO_LORENZO_REG, absErrorBound=eb)
+    ours, used = gpu_compress(data, conf)
+    theirs = ref_compress(data, conf)
+    assert ours.size == theirs.size and np.array_equal(ours, theirs), (ours.size, theirs.size)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.max(np.abs(dec.astype(np.float64) - data.astype(np.float64))) <= eb
+
+
+def test_lorenzo_special_values():
+    data = field_nd((24, 24, 24), np.float32)
+    data[3, 4, 5] = np.nan
+    data[10, 11, 12] = np.inf
+    data[20, 2, 7] = -np.inf
+    conf = make_config(data.shape, cmprAlgo=ALGO_LORENZO_REG, lorenzo=1, regression=0)
+    q_ref, blob_ref = ref_blockwise(ref_lib(), data, conf, 1e-3)
+    q, blob = gpu_blockwise(data, conf, 1e-3)
+    assert np.array_equal(q, q_ref)
+    assert len(blob) == len(blob_ref)
+
+
+def test_all_predictors_disabled_is_invalid():
     L = product_lib()
     data = field_nd((20, 20, 20), np.float32)
-    conf = make_config(data.shape, cmprAlgo=ALGO_LORENZO_REG)
+    conf = make_config(data.shape, cmprAlgo=ALGO_LORENZO_REG, lorenzo=0, lorenzo2=0, regression=0)
     cap = L.sz3b_compress_bound(0, C.byref(conf))
     out = np.empty(cap, dtype=np.uint8)
     size = C.c_size_t(0)
     rc = L.sz3b_compress(0, C.byref(conf), data.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_char_p), C.c_size_t(cap),
                          C.byref(size), None)
-    assert rc == -4, L.sz3b_last_error()
+    assert rc != 0 and b"disabled" in L.sz3b_last_error()
 
 
 def test_config3_half_size_ratio_and_bound():

@@ -48,6 +48,14 @@ def same_bits(a, b):
     ((60, 66, 72), np.float64, dict(cmprAlgo=ALGO_LORENZO_REG, lorenzo=0, regression=1, errorBoundMode=EB_REL, relErrorBound=1e-4)),
     ((40, 45), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, lorenzo=0, regression=1, absErrorBound=1e-3)),
     ((48, 48, 48), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, lorenzo=0, regression=1, absErrorBound=1e-7)),
+    ((50, 43, 61), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1e-3)),                     # Lorenzo + regression
+    ((30, 31, 32), np.float64, dict(cmprAlgo=ALGO_LORENZO_REG, lorenzo2=1, absErrorBound=1e-4)),         # all three
+    ((24, 30, 36), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, regression=0, absErrorBound=1e-3)),       # Lorenzo alone
+    ((31, 37, 25), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, lorenzo2=1, regression=0, absErrorBound=1e-3)),
+    ((130, 77), np.float64, dict(cmprAlgo=ALGO_LORENZO_REG, lorenzo2=1, blockSize=16, absErrorBound=1e-3)),
+    ((3000,), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, blockSize=128, absErrorBound=1e-3)),
+    ((9, 12, 20, 18), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1e-3)),
+    ((25, 31, 37), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1e-3, quantbinCnt=16)),
 ])
 def test_decompress_bit_identical(shape, dtype, kw, writer):
     data = field_nd(shape, dtype)
