@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(32 * (kMaxDim + 1)) k_reg_chain_spec2(const T 
                                                                         unsigned long long *__restrict__ n_sel_out,
                                                                         unsigned long long *__restrict__ n_unpred,
                                                                         unsigned long long *__restrict__ unpred_pos,
-                                                                        T *__restrict__ unpred_val) {
+                                                                        T *__restrict__ unpred_val, const T *__restrict__ init,
+                                                                        unsigned long long pos_base) {
     __shared__ double s_d[kMaxDim + 1][kSW];
     __shared__ T s_r[kMaxDim + 1][kSW + 1];
     __shared__ T s_last[kMaxDim + 1];
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(32 * (kMaxDim + 1)) k_reg_chain_spec2(const T 
     const unsigned full = 0xffffffffu;
     double *sd = s_d[d];
     T *sr = s_r[d];
-    T r_cur = 0;
+    T r_cur = init ? init[d] : static_cast<T>(0);   // chain continued from an earlier launch
     uint64_t b0 = 0;
     while (b0 < nblocks) {
         const unsigned n_in = nblocks - b0 < kSW ? static_cast<unsigned>(nblocks - b0) : kSW;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(32 * (kMaxDim + 1)) k_reg_chain_spec2(const T 
                 c_rec[pos] = rec[j];
                 if (qv[j] == 0) {
                     const unsigned long long slot = atomicAdd(n_unpred, 1ull);
-                    unpred_pos[slot] = pos;
+                    unpred_pos[slot] = pos_base + pos;
                     unpred_val[slot] = c[j];
                 }
                 if (i + 1 == n_acc) s_last[d] = rec[j];
@@ -341,10 +342,11 @@ void launch_reg_fit(const T *data, const BlockShape &bs, T *c_fit, uint8_t *vali
 template <class T>
 void launch_reg_chain(const T *c_fit, const uint8_t *sel, uint64_t nblocks, int N, const QuantParams &q_liner,
                       const QuantParams &q_indep, int32_t *coef_q, T *c_rec, unsigned long long *counters,
-                      unsigned long long *unpred_pos, T *unpred_val, cudaStream_t st) {
+                      unsigned long long *unpred_pos, T *unpred_val, cudaStream_t st, const T *init,
+                      unsigned long long pos_base) {
     if (sel == nullptr)   // dense: every block selected
         k_reg_chain_spec2<T><<<1, 32 * (N + 1), 0, st>>>(c_fit, nblocks, N, q_liner, q_indep, coef_q, c_rec, counters,
-                                                        counters + 1, unpred_pos, unpred_val);
+                                                        counters + 1, unpred_pos, unpred_val, init, pos_base);
     else
         k_reg_chain<T><<<1, 32, 0, st>>>(c_fit, sel, nblocks, N, q_liner, q_indep, coef_q, c_rec, counters, counters + 1,
                                         unpred_pos, unpred_val);
@@ -369,7 +371,7 @@ const char *launch_reg_predict(const T *data, const BlockShape &bs, const T *c_r
     template void launch_reg_fit<T>(const T *, const BlockShape &, T *, uint8_t *, cudaStream_t);                    \
     template void launch_reg_chain<T>(const T *, const uint8_t *, uint64_t, int, const QuantParams &,                \
                                       const QuantParams &, int32_t *, T *, unsigned long long *,                    \
-                                      unsigned long long *, T *, cudaStream_t);                                      \
+                                      unsigned long long *, T *, cudaStream_t, const T *, unsigned long long);       \
     template const char *launch_reg_predict<T, uint16_t>(const T *, const BlockShape &, const T *,                  \
                                                          const QuantParams &, uint16_t *, T *, unsigned long long *, \
                                                          cudaStream_t);                                              \

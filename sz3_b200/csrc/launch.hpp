@@ -48,7 +48,8 @@ void launch_reg_fit(const T *data, const BlockShape &bs, T *c_fit, uint8_t *vali
 template <class T>
 void launch_reg_chain(const T *c_fit, const uint8_t *sel, uint64_t nblocks, int N, const QuantParams &q_liner,
                       const QuantParams &q_indep, int32_t *coef_q, T *c_rec, unsigned long long *counters,
-                      unsigned long long *unpred_pos, T *unpred_val, cudaStream_t st);
+                      unsigned long long *unpred_pos, T *unpred_val, cudaStream_t st, const T *init = nullptr,
+                      unsigned long long pos_base = 0);   // init / pos_base: dense chain continued from an earlier launch
 template <class T, class QT>
 const char *launch_reg_predict(const T *data, const BlockShape &bs, const T *c_rec, const QuantParams &qp, QT *q,
                                T *unpred_tmp, unsigned long long *hist, cudaStream_t st);   // nullptr or an error text
@@ -57,20 +58,21 @@ const char *launch_reg_predict(const T *data, const BlockShape &bs, const T *c_r
 template <class T, class QT>
 struct BwArgs;
 template <class T>
-void launch_bw_pad(const T *data, const BlockShape &bs, const uint64_t *pstride, T *W, uint64_t b_lo, cudaStream_t st);
+void launch_bw_pad(const T *data, const BlockShape &bs, const uint64_t *pstride, T *W, uint64_t b_lo, uint64_t b_hi,
+                   cudaStream_t st);
 template <class T, class QT>
-const char *launch_bw_serial(const BwArgs<T, QT> &A, uint64_t b_lo, const T *chain_init, unsigned long long nsel0,
-                             unsigned long long *nsel_out, cudaStream_t st);
+const char *launch_bw_serial(const BwArgs<T, QT> &A, uint64_t b_lo, uint64_t b_hi, const T *chain_init,
+                             unsigned long long nsel0, unsigned long long *nsel_out, cudaStream_t st);
 template <class T, class QT>
 const char *launch_bw_fronts(const BwArgs<T, QT> &A, cudaStream_t st, int *launches);   // nullptr or an error text
 template <class T>
 void launch_bw_spec_coef(const T *c_fit, const uint8_t *valid, uint64_t nblocks, int N, const QuantParams &q_liner,
                          const QuantParams &q_indep, T *c_spec, cudaStream_t st);
-void launch_bw_rank(const uint8_t *sel, uint64_t nblocks, int reg_sid, uint32_t *rank, unsigned long long *count,
-                    cudaStream_t st);
+void launch_bw_rank(const uint8_t *sel, uint64_t b_lo, uint64_t b_hi, int reg_sid, uint32_t base, uint32_t *rank,
+                    unsigned long long *count, cudaStream_t st);
 template <class T>
-void launch_bw_gather_fit(const T *c_fit, const uint8_t *sel, int reg_sid, const uint32_t *rank, uint64_t nblocks, int nc,
-                          T *c_dense, cudaStream_t st);
+void launch_bw_gather_fit(const T *c_fit, const uint8_t *sel, int reg_sid, const uint32_t *rank, uint64_t b_lo, uint64_t b_hi,
+                          int nc, T *c_dense, cudaStream_t st);
 void launch_widen_u8(const uint8_t *in, uint64_t n, int32_t *out, cudaStream_t st);
 
 // decompress.cu

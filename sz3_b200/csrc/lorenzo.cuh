@@ -55,9 +55,11 @@ struct BwArgs {
                                  //           [1] the first such block in row-major order (atomicMin; init ~0u)
     QT *q;                       // quantization indices, block-major (written by BW_EXACT, read by BW_DECODE)
     T *unpred_tmp;               // position-indexed unpredictable values (same direction as q)
+    uint64_t b_lo, b_hi;         // window of row-major block indices processed by a front launch
     // BW_SERIAL (row-major walk with the coefficient chain inline): chain outputs, dense over the selected blocks
     QuantParams q_liner, q_indep;
     int32_t *coef_q;
+    T *c_rec_out;                // reconstructed coefficients (same dense array the exact passes read as c_rec)
     unsigned long long *n_unpred_coef, *unpred_pos;   // unpredictable coefficients: count, dense position
     T *unpred_val;
 };
@@ -276,6 +278,7 @@ SZ_HD void bw_process_block(const BwArgs<T, QT> &A, const uint32_t bi[kMaxDim], 
                 const int qv = quantize<T>(c, chain->prev[d], d < N ? A.q_liner : A.q_indep, cf[d]);
                 if (lane == 0) {
                     A.coef_q[at + d] = qv;
+                    A.c_rec_out[at + d] = cf[d];
                     if (qv == 0) {
 #if defined(__CUDA_ARCH__)
                         const unsigned long long slot = atomicAdd(A.n_unpred_coef, 1ull);

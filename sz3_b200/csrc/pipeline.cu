@@ -684,32 +684,35 @@ static void quantizer_save(std::vector<uint8_t> &out, double eb, int radius, con
     out.insert(out.end(), v, v + unpred.size() * sizeof(T));
 }
 
-// RegressionPredictor::save (RegressionPredictor.hpp:94-107) from the device-side chain results: `nsel` selected
-// blocks, `n_unp` unpredictable coefficients listed (unordered) as (dense position, value); entries at positions
-// >= nsel * (N+1) are leftovers of a discarded speculation and are dropped.
+// Unpredictable coefficients listed by the chain kernels as (dense position, value), unordered: fetch the entries
+// below `limit` (entries at or above it are leftovers of a discarded speculation).
 template <class T>
-static void regression_save(Workspace &ws, int N, unsigned long long nsel, unsigned long long n_unp,
-                            const unsigned long long *upos, const T *uval, const int32_t *coef_q, double eb_indep,
-                            double eb_liner, std::vector<uint8_t> &pred_blob) {
+static void fetch_coef_unpred(Workspace &ws, unsigned long long n_unp, const unsigned long long *upos, const T *uval,
+                              unsigned long long limit, std::vector<std::pair<unsigned long long, T>> &out) {
+    if (!n_unp) return;
+    std::vector<unsigned long long> pos(n_unp);
+    std::vector<T> val(n_unp);
+    ws.d2h(pos.data(), upos, n_unp * sizeof(unsigned long long));
+    ws.d2h(val.data(), uval, n_unp * sizeof(T));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    for (unsigned long long i = 0; i < n_unp; i++)
+        if (pos[i] < limit) out.emplace_back(pos[i], val[i]);
+}
+
+// RegressionPredictor::save (RegressionPredictor.hpp:94-107): `nsel` selected blocks, their coefficient indices on the
+// device (dense), the stored exact coefficients as (dense position, value).
+template <class T>
+static void regression_save(Workspace &ws, int N, unsigned long long nsel, std::vector<std::pair<unsigned long long, T>> &unp,
+                            const int32_t *coef_q, double eb_indep, double eb_liner, std::vector<uint8_t> &pred_blob) {
     const int nc = N + 1;
     const int kCoefRadius = 32768;
     const uint64_t n_coef = nsel * nc;
-    // unpredictable coefficients, back in chain order, split by quantizer
+    // back in chain order, split by quantizer
+    std::sort(unp.begin(), unp.end(), [](const std::pair<unsigned long long, T> &a, const std::pair<unsigned long long, T> &b) {
+        return a.first < b.first;
+    });
     std::vector<T> un_liner, un_indep;
-    if (n_unp) {
-        std::vector<unsigned long long> pos(n_unp);
-        std::vector<T> val(n_unp);
-        ws.d2h(pos.data(), upos, n_unp * sizeof(unsigned long long));
-        ws.d2h(val.data(), uval, n_unp * sizeof(T));
-        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-        std::vector<size_t> order(n_unp);
-        for (size_t i = 0; i < order.size(); i++) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return pos[a] < pos[b]; });
-        for (size_t i : order) {
-            if (pos[i] >= n_coef) continue;
-            (pos[i] % nc == static_cast<unsigned>(N) ? un_indep : un_liner).push_back(val[i]);
-        }
-    }
+    for (const auto &e : unp) (e.first % nc == static_cast<unsigned>(N) ? un_indep : un_liner).push_back(e.second);
     pred_blob.clear();
     {
         uint8_t tmp[8];
@@ -733,7 +736,9 @@ static void regression_save(Workspace &ws, int N, unsigned long long nsel, unsig
 //   selection reproduces itself; after kBwMaxPasses invalidated guesses the row-major walk (k_bw_serial) finishes
 //   from the first wrong block with the reference's sequential semantics.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kBwMaxPasses = 4;
+constexpr uint64_t kBwMinWindow = 4096;   // blocks per window of the selection iteration (grows with the advance)
+constexpr uint64_t kBwWalkBelow = 24;     // an advance below this many blocks per pass hands the next stretch to the walk
+constexpr uint64_t kBwWalkLen = 512;
 
 template <class T, class QT>
 static uint64_t bw_args_init(BwArgs<T, QT> &A, const sz3b_config &conf, const BlockShape &bs, double eb) {
@@ -753,9 +758,17 @@ static uint64_t bw_args_init(BwArgs<T, QT> &A, const sz3b_config &conf, const Bl
     const int nc = bs.N + 1;
     A.q_liner = make_quant(eb / nc / static_cast<unsigned>(conf.blockSize), 32768);
     A.q_indep = make_quant(eb / nc, 32768);
+    A.b_lo = 0;
+    A.b_hi = bs.nblocks;
     return np;
 }
 
+// Lorenzo only (1st, 2nd, or both composed): one exact wavefront pass over all blocks.
+// Lorenzo + regression: a selection guess pass, then windows of consecutive blocks [b_lo, b_hi): exact chain over the
+// guessed selection of the window (continued from the last final block) -> exact wavefront pass over the window that
+// re-derives the selection.  Everything before the first block whose guess was wrong is final; the next window
+// starts there with the corrected guess.  The window follows the advance; when the advance collapses the row-major
+// walk (k_bw_serial, the reference's sequential semantics) does the next stretch.
 template <class T, class QT>
 static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double eb, const T *d_data, QT *d_q,
                                   T *d_unpred_tmp, unsigned long long *d_hist, int nbins, std::vector<uint8_t> &pred_blob,
@@ -774,27 +787,29 @@ static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double
     A.q = d_q;
     A.unpred_tmp = d_unpred_tmp;
     uint8_t *selA = ws.bsel.as<uint8_t>(bs.nblocks), *selB = ws.bsel2.as<uint8_t>(bs.nblocks);
-    uint8_t *sel_final = selA;
     unsigned *d_mm = ws.misc.as<unsigned>(4);
-    auto pad = [&](uint64_t b_lo) {
-        if (b_lo == 0) SZ3B_CUDA(cudaMemsetAsync(W, 0, np * sizeof(T), ws.st));
-        launch_bw_pad<T>(d_data, bs, A.pstride, W, b_lo, ws.st);
+    auto pad = [&](uint64_t b_lo, uint64_t b_hi) {
+        if (b_lo == 0 && b_hi == bs.nblocks) SZ3B_CUDA(cudaMemsetAsync(W, 0, np * sizeof(T), ws.st));
+        launch_bw_pad<T>(d_data, bs, A.pstride, W, b_lo, b_hi, ws.st);
         *launches += 1;
     };
-    auto fronts = [&](int mode) {
+    auto fronts = [&](int mode, uint64_t b_lo, uint64_t b_hi) {
         A.mode = mode;
+        A.b_lo = b_lo;
+        A.b_hi = b_hi;
         if (const char *e = launch_bw_fronts<T, QT>(A, ws.st, launches)) fail(SZ3B_E_UNSUPPORTED, e);
     };
     size_t h = ws.stage_begin("predict_quantize");
     const int l0 = *launches;
-    unsigned long long nsel = 0, n_unp = 0;
+    uint32_t nsel_lo = 0;   // regression-selected blocks among the final ones
     int32_t *coef_q = nullptr;
-    unsigned long long *upos = nullptr;
-    T *uval = nullptr;
+    std::vector<std::pair<unsigned long long, T>> unp;
+    int n_pass = 0, n_walk = 0;
     if (!has_reg) {
-        pad(0);
+        pad(0, bs.nblocks);
         A.sel_out = selA;
-        fronts(BW_EXACT);
+        fronts(BW_EXACT, 0, bs.nblocks);
+        n_pass = 1;
     } else {
         T *c_fit = ws.coef.as<T>(bs.nblocks * nc);
         T *c_rec = ws.coef2.as<T>(bs.nblocks * nc);
@@ -804,8 +819,8 @@ static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double
         uint32_t *rank = ws.brank.as<uint32_t>(bs.nblocks + 1);
         coef_q = ws.coef_q.as<int32_t>(bs.nblocks * nc);
         unsigned long long *counters = ws.counters.as<unsigned long long>(4);
-        upos = ws.cpos.as<unsigned long long>(2 * bs.nblocks * nc + 16);
-        uval = ws.cval.as<T>(2 * bs.nblocks * nc + 16);
+        unsigned long long *upos = ws.cpos.as<unsigned long long>(bs.nblocks * nc + 16);
+        T *uval = ws.cval.as<T>(bs.nblocks * nc + 16);
         launch_reg_fit<T>(d_data, bs, c_fit, valid, ws.st);
         launch_bw_spec_coef<T>(c_fit, valid, bs.nblocks, N, A.q_liner, A.q_indep, c_spec, ws.st);
         *launches += 2;
@@ -815,79 +830,78 @@ static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double
         A.c_rec = c_rec;
         A.rank = rank;
         A.mismatch = d_mm;
-        pad(0);
+        A.coef_q = coef_q;
+        A.c_rec_out = c_rec;
+        A.n_unpred_coef = counters + 1;
+        A.unpred_pos = upos;
+        A.unpred_val = uval;
+        pad(0, bs.nblocks);
         A.sel_out = selA;
-        fronts(BW_SPEC);
-        for (int pass = 1;; pass++) {
-            launch_bw_rank(selA, bs.nblocks, reg_sid, rank, counters + 2, ws.st);
-            launch_bw_gather_fit<T>(c_fit, selA, reg_sid, rank, bs.nblocks, nc, c_dense, ws.st);
+        fronts(BW_SPEC, 0, bs.nblocks);
+        uint64_t b_lo = 0, win = bs.nblocks, last_adv = bs.nblocks;
+        while (b_lo < bs.nblocks) {
+            const T *init = nsel_lo ? c_rec + static_cast<uint64_t>(nsel_lo - 1) * nc : nullptr;
+            unsigned long long n_unp = 0, cnt = 0;
+            if (last_adv < kBwWalkBelow) {
+                const uint64_t b_hi = std::min<uint64_t>(bs.nblocks, b_lo + kBwWalkLen);
+                pad(b_lo, b_hi);
+                SZ3B_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ws.st));
+                A.mode = BW_SERIAL;
+                A.sel_in = nullptr;
+                A.sel_out = selA;
+                if (const char *e = launch_bw_serial<T, QT>(A, b_lo, b_hi, init, nsel_lo, counters + 2, ws.st))
+                    fail(SZ3B_E_UNSUPPORTED, e);
+                *launches += 1;
+                ws.d2h(&n_unp, counters + 1, sizeof(n_unp));
+                ws.d2h(&cnt, counters + 2, sizeof(cnt));
+                SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+                SZ3B_CUDA(cudaGetLastError());
+                fetch_coef_unpred<T>(ws, n_unp, upos, uval, cnt * nc, unp);
+                nsel_lo = static_cast<uint32_t>(cnt);
+                b_lo = b_hi;
+                last_adv = kBwWalkBelow;   // try a window again
+                win = kBwMinWindow;
+                n_walk++;
+                continue;
+            }
+            const uint64_t b_hi = std::min<uint64_t>(bs.nblocks, b_lo + win);
+            launch_bw_rank(selA, b_lo, b_hi, reg_sid, nsel_lo, rank, counters + 2, ws.st);
+            launch_bw_gather_fit<T>(c_fit, selA, reg_sid, rank, b_lo, b_hi, nc, c_dense, ws.st);
             *launches += 2;
-            ws.d2h(&nsel, counters + 2, sizeof(nsel));
+            ws.d2h(&cnt, counters + 2, sizeof(cnt));
             SZ3B_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ws.st));
             SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-            if (nsel) {
-                launch_reg_chain<T>(c_dense, nullptr, nsel, N, A.q_liner, A.q_indep, coef_q, c_rec, counters, upos, uval, ws.st);
+            const uint64_t at = static_cast<uint64_t>(nsel_lo) * nc;
+            if (cnt) {
+                launch_reg_chain<T>(c_dense + at, nullptr, cnt, N, A.q_liner, A.q_indep, coef_q + at, c_rec + at, counters, upos,
+                                    uval, ws.st, init, at);
                 *launches += 1;
             }
-            pad(0);
+            pad(b_lo, b_hi);
             const unsigned mm_init[2] = {0u, ~0u};
             ws.h2d(d_mm, mm_init, sizeof(mm_init));
             A.sel_in = selA;
             A.sel_out = selB;
-            fronts(BW_EXACT);
+            fronts(BW_EXACT, b_lo, b_hi);
             unsigned mm[2];
             ws.d2h(mm, d_mm, sizeof(mm));
             ws.d2h(&n_unp, counters + 1, sizeof(n_unp));
             SZ3B_CUDA(cudaStreamSynchronize(ws.st));
             SZ3B_CUDA(cudaGetLastError());
-            if (mm[0] == 0) {
-                sel_final = selA;
-                break;
-            }
-            if (pass >= kBwMaxPasses) {
-                const uint64_t b_lo = mm[1];
-                uint32_t nsel0 = 0;
-                ws.d2h(&nsel0, rank + b_lo, sizeof(nsel0));
+            n_pass++;
+            uint64_t boundary = b_hi;
+            uint32_t nsel_after = nsel_lo + static_cast<uint32_t>(cnt);
+            if (mm[0]) {
+                boundary = mm[1];
+                ws.d2h(&nsel_after, rank + boundary, sizeof(nsel_after));
+                SZ3B_CUDA(cudaMemcpyAsync(selA + boundary, selB + boundary, b_hi - boundary, cudaMemcpyDeviceToDevice, ws.st));
                 SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-                if (n_unp) {   // keep only the stored coefficients of the final prefix
-                    std::vector<unsigned long long> pos(n_unp);
-                    std::vector<T> val(n_unp);
-                    ws.d2h(pos.data(), upos, n_unp * sizeof(unsigned long long));
-                    ws.d2h(val.data(), uval, n_unp * sizeof(T));
-                    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-                    unsigned long long kept = 0;
-                    for (unsigned long long i = 0; i < n_unp; i++)
-                        if (pos[i] < static_cast<unsigned long long>(nsel0) * nc) {
-                            pos[kept] = pos[i];
-                            val[kept] = val[i];
-                            kept++;
-                        }
-                    if (kept) {
-                        ws.h2d(upos, pos.data(), kept * sizeof(unsigned long long));
-                        ws.h2d(uval, val.data(), kept * sizeof(T));
-                    }
-                    ws.h2d(counters + 1, &kept, sizeof(kept));
-                    SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // pos / val are locals
-                }
-                pad(b_lo);
-                A.mode = BW_SERIAL;
-                A.sel_in = nullptr;
-                A.coef_q = coef_q;
-                A.n_unpred_coef = counters + 1;
-                A.unpred_pos = upos;
-                A.unpred_val = uval;
-                if (const char *e = launch_bw_serial<T, QT>(A, b_lo, nsel0 ? c_rec + static_cast<uint64_t>(nsel0 - 1) * nc : nullptr,
-                                                            nsel0, counters + 2, ws.st))
-                    fail(SZ3B_E_UNSUPPORTED, e);
-                *launches += 1;
-                ws.d2h(&n_unp, counters + 1, sizeof(n_unp));
-                ws.d2h(&nsel, counters + 2, sizeof(nsel));
-                SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-                SZ3B_CUDA(cudaGetLastError());
-                sel_final = selB;
-                break;
             }
-            std::swap(selA, selB);
+            fetch_coef_unpred<T>(ws, n_unp, upos, uval, static_cast<unsigned long long>(nsel_after) * nc, unp);
+            last_adv = boundary - b_lo;
+            b_lo = boundary;
+            nsel_lo = nsel_after;
+            win = std::max<uint64_t>(kBwMinWindow, 4 * last_adv);
         }
     }
     SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
@@ -895,19 +909,19 @@ static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double
     *launches += 1;
     ws.stage_end(h, *launches - l0);
     SZ3B_CUDA(cudaGetLastError());
+    if (getenv("SZ3B_VERBOSE")) fprintf(stderr, "[sz3b] lorenzo stack: %d exact passes, %d walks\n", n_pass, n_walk);
     // ComposedPredictor::save (ComposedPredictor.hpp:52-64): predictors in order (only regression stores anything),
     // then the per-block selection, Huffman coded
     pred_blob.clear();
     if (has_reg)
-        regression_save<T>(ws, N, nsel, n_unp, upos, uval, coef_q, eb / nc, eb / nc / static_cast<unsigned>(conf.blockSize),
-                           pred_blob);
+        regression_save<T>(ws, N, nsel_lo, unp, coef_q, eb / nc, eb / nc / static_cast<unsigned>(conf.blockSize), pred_blob);
     if (A.nk > 1) {
         uint8_t tmp[8];
         uint8_t *p = tmp;
         put<uint64_t>(p, bs.nblocks);
         pred_blob.insert(pred_blob.end(), tmp, p);
         int32_t *d_sel32 = ws.side_q.as<int32_t>(bs.nblocks);
-        launch_widen_u8(sel_final, bs.nblocks, d_sel32, ws.st);
+        launch_widen_u8(selA, bs.nblocks, d_sel32, ws.st);
         std::vector<uint8_t> side;
         huffman_encode_device(ws, d_sel32, bs.nblocks, side, nullptr);
         pred_blob.insert(pred_blob.end(), side.begin(), side.end());
@@ -957,7 +971,9 @@ static void run_blockwise(Workspace &ws, const sz3b_config &conf, double eb, con
     SZ3B_CUDA(cudaStreamSynchronize(ws.st));
     SZ3B_CUDA(cudaGetLastError());
     *launches += 2;
-    regression_save<T>(ws, N, hc[0], hc[1], upos, uval, coef_q, eb_indep, eb_liner, pred_blob);
+    std::vector<std::pair<unsigned long long, T>> unp;
+    fetch_coef_unpred<T>(ws, hc[1], upos, uval, hc[0] * nc, unp);
+    regression_save<T>(ws, N, hc[0], unp, coef_q, eb_indep, eb_liner, pred_blob);
     h = ws.stage_begin("predict_quantize");
     SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
     if (const char *e = launch_reg_predict<T, QT>(d_data, bs, c_rec, make_quant(eb, conf.quantbinCnt / 2), d_q,
@@ -1458,7 +1474,7 @@ static void blockwise_decompress_lorenzo(Workspace &ws, const sz3b_config &conf,
         if (has_reg) {
             uint32_t *rank = ws.brank.as<uint32_t>(bs.nblocks + 1);
             unsigned long long *counters = ws.counters.as<unsigned long long>(4);
-            launch_bw_rank(d_sel, bs.nblocks, reg_sid, rank, counters + 2, ws.st);
+            launch_bw_rank(d_sel, 0, bs.nblocks, reg_sid, 0, rank, counters + 2, ws.st);
             launches++;
             A.rank = rank;
             if (n_coef) {

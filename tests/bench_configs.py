@@ -81,3 +81,12 @@ if "c2d" in which:  # config #2 with the other tuner direction forced
     from common import ALGO_INTERP
     d = field_g3((512, 512, 512))
     run("C2 512^3 f32 ALGO_INTERP dir 5", d, make_config(d.shape, cmprAlgo=ALGO_INTERP, absErrorBound=1e-3, interpDirection=5), ref=False)
+if "lz" in which:   # ALGO_LORENZO_REG stacks with a Lorenzo predictor (block wavefront, lorenzo.cu)
+    d = field_g3((256, 256, 256))
+    run("LZ 256^3 f32 lorenzo ABS 1e-3", d, make_config(d.shape, cmprAlgo=ALGO_LORENZO_REG, regression=0, absErrorBound=1e-3))
+    run("LZ 256^3 f32 lorenzo+regression ABS 1e-3", d, make_config(d.shape, cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1e-3))
+    run("LZ 256^3 f32 lorenzo+regression ABS 1e-2", d, make_config(d.shape, cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1e-2))
+if "lz512" in which:
+    d = field_g3((512, 512, 512))
+    run("LZ 512^3 f32 lorenzo ABS 1e-3", d, make_config(d.shape, cmprAlgo=ALGO_LORENZO_REG, regression=0, absErrorBound=1e-3))
+    run("LZ 512^3 f32 lorenzo+regression ABS 1e-3", d, make_config(d.shape, cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1e-3), reps=1)

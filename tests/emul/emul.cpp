@@ -1,6 +1,7 @@
 // tests/emul/emul.cpp -- TEST INFRASTRUCTURE: runs the kernel *bodies* of sz3_b200/csrc/interp_body.cuh with host
 // threads so that the traversal/indexing logic can be checked against the reference on a machine without a GPU.
 // Never linked into the product library (which has no CPU path); built by tests/conftest.py into tests/emul/_build/.
+#include <algorithm>
 #include <atomic>
 #include <barrier>
 #include <cstdio>
@@ -292,10 +293,18 @@ static void emul_fronts(const BwArgs<T, uint32_t> &A) {
             }
             if (f < s || f - s >= bs.nb[N - 1]) continue;
             bi[N - 1] = f - s;
+            const uint64_t b = cta * bs.nb[N - 1] + bi[N - 1];
+            if (b < A.b_lo || b >= A.b_hi) continue;
             bw_process_block<T, uint32_t>(A, bi, scratch.data(), scratch.data() + tile_cap, 0, 1);
         }
 }
 
+static uint64_t env_u64(const char *name, uint64_t dflt) {
+    const char *v = getenv(name);
+    return v ? strtoull(v, nullptr, 10) : dflt;
+}
+
+// Mirrors run_blockwise_lorenzo (pipeline.cu): returns the number of exact passes + 1000 * walks, negative on error.
 template <class T>
 static int run_lorenzo(const sz3b_config &c, double eb, const T *data, int32_t *quant_out, uint8_t *sel_out,
                        int32_t *coef_q_out, size_t *n_coef, T *unpred_out, size_t *n_unpred, T *decoded) {
@@ -316,23 +325,26 @@ static int run_lorenzo(const sz3b_config &c, double eb, const T *data, int32_t *
     if (c.lorenzo) A.kinds[A.nk++] = PK_LORENZO1;
     if (c.lorenzo2) A.kinds[A.nk++] = PK_LORENZO2;
     if (c.regression) A.kinds[A.nk++] = PK_REG;
+    A.b_lo = 0;
+    A.b_hi = bs.nblocks;
     const bool has_reg = c.regression != 0 && A.nk > 1;
-    int reg_sid = -1;
-    for (int k = 0; k < A.nk; k++)
-        if (A.kinds[k] == PK_REG) reg_sid = k;
+    const int reg_sid = A.nk - 1;
     std::vector<T> W(np), c_fit(bs.nblocks * nc, 0), c_spec(bs.nblocks * nc, 0), c_rec(bs.nblocks * nc, 0), un(bs.num, 0);
     std::vector<uint8_t> valid(bs.nblocks, 0), selA(bs.nblocks, 0), selB(bs.nblocks, 0);
-    std::vector<uint32_t> rank(bs.nblocks, 0), q(bs.num, 0);
+    std::vector<uint32_t> rank(bs.nblocks + 1, 0), q(bs.num, 0);
     QuantParams ql = make_quant(eb / nc / static_cast<unsigned>(c.blockSize), 32768), qi = make_quant(eb / nc, 32768);
-    auto pad = [&]() {
-        std::fill(W.begin(), W.end(), static_cast<T>(0));
+    auto pad = [&](uint64_t b_lo, uint64_t b_hi) {   // k_bw_pad
+        if (b_lo == 0 && b_hi == bs.nblocks) std::fill(W.begin(), W.end(), static_cast<T>(0));
         for (uint64_t i = 0; i < bs.num; i++) {
-            uint64_t r = i, w = 0;
+            uint64_t r = i, w = 0, b = 0, bmul = 1;
             for (int d = N - 1; d >= 0; d--) {
-                w += (r % bs.dims[d] + kBwPad) * A.pstride[d];
+                const uint64_t x = r % bs.dims[d];
                 r /= bs.dims[d];
+                w += (x + kBwPad) * A.pstride[d];
+                b += (x / bs.B) * bmul;
+                bmul *= bs.nb[d];
             }
-            W[w] = data[i];
+            if (b >= b_lo && b < b_hi) W[w] = data[i];
         }
     };
     A.W = W.data();
@@ -340,11 +352,10 @@ static int run_lorenzo(const sz3b_config &c, double eb, const T *data, int32_t *
     A.unpred_tmp = un.data();
     unsigned mm[2] = {0, ~0u};
     A.mismatch = mm;
-    int passes = 0;
-    *n_coef = 0;
-    const char *kmax_env = getenv("EMUL_KMAX");
-    const int kmax = kmax_env ? atoi(kmax_env) : 3;   // exact wavefront passes before the row-major walk takes over
-    std::vector<uint8_t> *final_sel = &selA;
+    int passes = 0, walks = 0;
+    uint32_t nsel_lo = 0;
+    const uint64_t min_win = env_u64("EMUL_MINWIN", 4096), walk_below = env_u64("EMUL_WALKBELOW", 24),
+                   walk_len = env_u64("EMUL_WALKLEN", 512);
     if (has_reg) {
         for (uint64_t b = 0; b < bs.nblocks; b++) {
             T coef[kMaxDim + 1];
@@ -355,75 +366,40 @@ static int run_lorenzo(const sz3b_config &c, double eb, const T *data, int32_t *
                     c_spec[b * nc + d] = coef_lattice_guess<T>(coef[d], d < N ? ql : qi);
                 }
         }
+        std::vector<unsigned long long> upos(bs.nblocks * nc + 1);
+        std::vector<T> uval(bs.nblocks * nc + 1);
+        unsigned long long nuc = 0;
         A.c_fit = c_fit.data();
         A.fit_valid = valid.data();
         A.c_spec = c_spec.data();
         A.c_rec = c_rec.data();
+        A.c_rec_out = c_rec.data();
         A.rank = rank.data();
         A.q_liner = ql;
         A.q_indep = qi;
-        pad();
+        A.coef_q = coef_q_out;
+        A.n_unpred_coef = &nuc;
+        A.unpred_pos = upos.data();
+        A.unpred_val = uval.data();
+        pad(0, bs.nblocks);
         A.mode = BW_SPEC;
         A.sel_out = selA.data();
         emul_fronts(A);
-        for (;;) {
-            // exact chain over the guessed selection (dense)
-            T prev[kMaxDim + 1] = {0, 0, 0, 0, 0};
-            size_t k = 0;
-            uint32_t nsel = 0;
-            for (uint64_t b = 0; b < bs.nblocks; b++) {
-                rank[b] = nsel;
-                if (selA[b] != reg_sid) continue;
-                for (int d = 0; d < nc; d++) {
-                    T rec;
-                    coef_q_out[k++] = quantize<T>(c_fit[b * nc + d], prev[d], d < N ? ql : qi, rec);
-                    prev[d] = rec;
-                    c_rec[static_cast<size_t>(nsel) * nc + d] = rec;
-                }
-                nsel++;
-            }
-            *n_coef = k;
-            pad();
-            mm[0] = 0;
-            mm[1] = ~0u;
-            A.mode = BW_EXACT;
-            A.sel_in = selA.data();
-            A.sel_out = selB.data();
-            emul_fronts(A);
-            passes++;
-            if (getenv("EMUL_VERBOSE"))
-                fprintf(stderr, "pass %d: %u mismatches, first at block %u of %llu, nsel %u\n", passes, mm[0], mm[1],
-                        (unsigned long long)bs.nblocks, nsel);
-            if (mm[0] == 0) break;
-            if (passes >= kmax) {
-                // row-major walk from the first wrong guess (k_bw_serial)
-                const uint64_t b_lo = mm[1];
+        uint64_t b_lo = 0, win = bs.nblocks, last_adv = bs.nblocks;
+        while (b_lo < bs.nblocks) {
+            if (last_adv < walk_below) {   // k_bw_serial over the next stretch
+                const uint64_t b_hi = std::min<uint64_t>(bs.nblocks, b_lo + walk_len);
+                pad(b_lo, b_hi);
                 BwSerial<T> st;
-                st.nsel = rank[b_lo];
-                for (int d = 0; d < nc; d++) st.prev[d] = st.nsel ? c_rec[(st.nsel - 1) * nc + d] : static_cast<T>(0);
-                for (uint64_t i = 0; i < bs.num; i++) {   // k_bw_pad with b_lo
-                    uint64_t r = i, w = 0, b = 0, bmul = 1;
-                    for (int d = N - 1; d >= 0; d--) {
-                        const uint64_t x = r % bs.dims[d];
-                        r /= bs.dims[d];
-                        w += (x + kBwPad) * A.pstride[d];
-                        b += (x / bs.B) * bmul;
-                        bmul *= bs.nb[d];
-                    }
-                    if (b >= b_lo) W[w] = data[i];
-                }
+                st.nsel = nsel_lo;
+                for (int d = 0; d < nc; d++) st.prev[d] = nsel_lo ? c_rec[static_cast<size_t>(nsel_lo - 1) * nc + d] : static_cast<T>(0);
                 std::vector<T> scratch(bw_scratch_elems(bs, A.nk));
                 size_t tile_cap = 1;
                 for (int d = 0; d < N; d++) tile_cap *= (bs.dims[d] < bs.B ? bs.dims[d] : bs.B) + kBwPad;
-                std::vector<unsigned long long> upos(bs.nblocks * nc + 1);
-                std::vector<T> uval(bs.nblocks * nc + 1);
-                unsigned long long nuc = 0;
                 A.mode = BW_SERIAL;
-                A.coef_q = coef_q_out;
-                A.n_unpred_coef = &nuc;
-                A.unpred_pos = upos.data();
-                A.unpred_val = uval.data();
-                for (uint64_t b = b_lo; b < bs.nblocks; b++) {
+                A.sel_in = nullptr;
+                A.sel_out = selA.data();
+                for (uint64_t b = b_lo; b < b_hi; b++) {
                     uint32_t bi[kMaxDim] = {0, 0, 0, 0};
                     uint64_t r = b;
                     for (int d = N - 1; d >= 0; d--) {
@@ -432,23 +408,68 @@ static int run_lorenzo(const sz3b_config &c, double eb, const T *data, int32_t *
                     }
                     bw_process_block<T, uint32_t>(A, bi, scratch.data(), scratch.data() + tile_cap, 0, 1, &st);
                 }
-                *n_coef = st.nsel * nc;
-                final_sel = &selB;
-                passes = -passes;   // reported as negative: finished by the walk
-                break;
+                nsel_lo = static_cast<uint32_t>(st.nsel);
+                b_lo = b_hi;
+                last_adv = walk_below;
+                win = min_win;
+                walks++;
+                continue;
             }
-            selA.swap(selB);
+            const uint64_t b_hi = std::min<uint64_t>(bs.nblocks, b_lo + win);
+            // k_bw_rank + k_bw_gather_fit + k_reg_chain_spec2 (continued chain) over the window's guessed selection
+            T prev[kMaxDim + 1];
+            for (int d = 0; d < nc; d++) prev[d] = nsel_lo ? c_rec[static_cast<size_t>(nsel_lo - 1) * nc + d] : static_cast<T>(0);
+            uint32_t nsel = nsel_lo;
+            for (uint64_t b = b_lo; b < b_hi; b++) {
+                rank[b] = nsel;
+                if (selA[b] != reg_sid) continue;
+                for (int d = 0; d < nc; d++) {
+                    T rec;
+                    coef_q_out[static_cast<size_t>(nsel) * nc + d] = quantize<T>(c_fit[b * nc + d], prev[d], d < N ? ql : qi, rec);
+                    prev[d] = rec;
+                    c_rec[static_cast<size_t>(nsel) * nc + d] = rec;
+                }
+                nsel++;
+            }
+            pad(b_lo, b_hi);
+            mm[0] = 0;
+            mm[1] = ~0u;
+            A.mode = BW_EXACT;
+            A.b_lo = b_lo;
+            A.b_hi = b_hi;
+            A.sel_in = selA.data();
+            A.sel_out = selB.data();
+            emul_fronts(A);
+            passes++;
+            uint64_t boundary = b_hi;
+            uint32_t nsel_after = nsel;
+            if (mm[0]) {
+                boundary = mm[1];
+                nsel_after = rank[boundary];
+                for (uint64_t b = boundary; b < b_hi; b++) selA[b] = selB[b];
+            }
+            if (getenv("EMUL_VERBOSE"))
+                fprintf(stderr, "pass %d: window [%llu, %llu) %u mismatches, final up to %llu of %llu\n", passes,
+                        (unsigned long long)b_lo, (unsigned long long)b_hi, mm[0], (unsigned long long)boundary,
+                        (unsigned long long)bs.nblocks);
+            last_adv = boundary - b_lo;
+            b_lo = boundary;
+            nsel_lo = nsel_after;
+            win = std::max<uint64_t>(min_win, 4 * last_adv);
         }
+        A.b_lo = 0;
+        A.b_hi = bs.nblocks;
     } else {
-        pad();
+        pad(0, bs.nblocks);
         A.mode = BW_EXACT;
         A.sel_in = nullptr;
         A.sel_out = selA.data();
         emul_fronts(A);
         passes = 1;
     }
+    *n_coef = static_cast<size_t>(nsel_lo) * nc;
     for (uint64_t i = 0; i < bs.num; i++) quant_out[i] = static_cast<int32_t>(q[i]);
-    memcpy(sel_out, final_sel->data(), bs.nblocks);
+    memcpy(sel_out, selA.data(), bs.nblocks);
     size_t nu = 0;
     for (uint64_t i = 0; i < bs.num; i++)
         if (q[i] == 0) unpred_out[nu++] = un[i];
@@ -456,14 +477,14 @@ static int run_lorenzo(const sz3b_config &c, double eb, const T *data, int32_t *
     if (decoded) {
         std::fill(W.begin(), W.end(), static_cast<T>(0));
         A.mode = BW_DECODE;
-        A.sel_in = final_sel->data();
+        A.sel_in = selA.data();
         if (has_reg) {   // dense chain recover over the final selection (k_reg_chain_recover + k_bw_rank)
             T cur[kMaxDim + 1] = {0, 0, 0, 0, 0};
             uint32_t nsel = 0;
             size_t k = 0;
             for (uint64_t b = 0; b < bs.nblocks; b++) {
                 rank[b] = nsel;
-                if ((*final_sel)[b] != reg_sid) continue;
+                if (selA[b] != reg_sid) continue;
                 for (int d = 0; d < nc; d++) {
                     const int qv = coef_q_out[k++];
                     cur[d] = qv ? recover_pred<T>(cur[d], qv, d < N ? ql : qi) : c_fit[b * nc + d];   // 0: stored exactly
@@ -475,7 +496,7 @@ static int run_lorenzo(const sz3b_config &c, double eb, const T *data, int32_t *
         A.out = decoded;
         emul_fronts(A);
     }
-    return passes;
+    return passes + 1000 * walks;
 }
 
 extern "C" int emul_lorenzo_decompose(int dtype, const sz3b_config *c, double eb, const void *data, int32_t *quant_out,
