@@ -108,6 +108,11 @@ int sz3b_blockwise_decompose(int dtype, const sz3b_config *c, double abs_eb, con
 int sz3b_huffman_encode(const int32_t *q, size_t n, int q_loc, unsigned char *out, size_t out_cap, size_t *out_len,
                         size_t *tree_len);
 
+/* Lossless_zstd::compress (lossless/Lossless_zstd.hpp:29-37) by the GPU lossless stage of policy 2: src (host or
+ * device, src_loc) -> out (host) = size_t srcLen | standard zstd frames of Huffman-only literal blocks. */
+int sz3b_lossless_compress(const unsigned char *src, size_t src_len, int src_loc, unsigned char *out, size_t out_cap,
+                           size_t *out_len);
+
 /* The auto-tuner inside SZ_compress_Interp_lorenzo (api/impl/SZAlgoInterp.hpp:122-286): fills in cmprAlgo,
  * interpAlgo, interpDirection, interpAlpha, interpBeta (and absErrorBound) exactly as the reference would choose. */
 int sz3b_tune(int dtype, sz3b_config *c, const void *data, int data_loc);
@@ -139,11 +144,14 @@ void sz3b_last_transfer(size_t *h2d_bytes, size_t *d2h_bytes);
 /* zstd worker threads for the host tail (0 = hardware concurrency). */
 void sz3b_set_host_threads(int n);
 /* Lossless stage over the packed (Huffman-coded) stream, lossless/Lossless_zstd.hpp:29-37.
- *   0 = (default) every chunk through zstd level 3 (the reference's behaviour, frame by frame);
- *   1 = adaptive: every 8th 1-MiB chunk is compressed as a probe; if zstd gains < 1 % on the probes, the other chunks
- *       are stored as raw zstd frames (at most 0.875 % of ratio for 7/8 of the host time; pays off on entropy-coded
- *       streams of very noisy data -- on BASELINE's 512^3 case zstd gains 1.1 %, so the probes keep zstd on).
- *   Either way the result is a concatenation of standard zstd frames that the unmodified reference decoder reads. */
+ *   0 = every chunk through zstd level 3 on the host (the reference's call, frame by frame);
+ *   1 = adaptive host zstd: every 8th 1-MiB chunk is compressed as a probe; if zstd gains < 1 % on the probes, the
+ *       other chunks are stored as raw zstd frames;
+ *   2 = (default) streams of 4 MiB and more are coded on the GPU into standard zstd frames whose blocks hold
+ *       Huffman-only literals with one table per 128 KiB block (sz3_b200/csrc/zhuf.cuh): zstd finds no matches in an
+ *       entropy-coded stream, its gain there IS the literal coding; only the compressed frames cross PCIe.
+ *       Shorter streams take the host zstd call of policy 0 and stay byte-identical to the reference's.
+ *   In every case the result is a concatenation of standard zstd frames that the unmodified reference decoder reads. */
 void sz3b_set_lossless_policy(int policy);
 int sz3b_get_lossless_policy(void);
 

@@ -289,6 +289,16 @@ int sz3b_huffman_encode(const int32_t *q, size_t n, int q_loc, unsigned char *ou
     });
 }
 
+int sz3b_lossless_compress(const unsigned char *src, size_t src_len, int src_loc, unsigned char *out, size_t out_cap,
+                           size_t *out_len) {
+    return guarded([&] {
+        WorkspaceLease ws;
+        const size_t n = lossless_gpu_stage(*ws, src, src_len, src_loc, out, out_cap);
+        finish_profile(*ws);
+        if (out_len) *out_len = n;
+    });
+}
+
 int sz3b_tune(int dtype, sz3b_config *c, const void *data, int data_loc) {
     return guarded([&] {
         check_dtype(dtype);

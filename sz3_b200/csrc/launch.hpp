@@ -95,6 +95,11 @@ const char *launch_reg_recover(T *out, const BlockShape &bs, const T *c_rec, con
 void launch_scan_chunks(const unsigned *chunk_bits, const unsigned *chunk_zeros, uint64_t nchunks, unsigned long long *bit_off,
                         unsigned long long *zero_off, cudaStream_t st);   // encode_kernels.cu (k_pack_scan)
 
+// zhuf_kernels.cu: the GPU lossless stage (zstd frames of Huffman-only literal blocks, zhuf.cuh)
+struct ZhufBlockInfo;
+void launch_zhuf(const uint8_t *src, uint64_t len, ZhufBlockInfo *infos, uint8_t *out, unsigned long long *total,
+                 cudaStream_t st);
+
 // huffman_decode.cu
 struct HdDeviceTables {
     const uint32_t *lut;

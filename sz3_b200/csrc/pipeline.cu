@@ -22,6 +22,7 @@
 
 #include "blockwise.cuh"
 #include "lorenzo.cuh"
+#include "zhuf.cuh"
 #include "huffman_host.hpp"
 #include "interp_body.cuh"
 #include "interp_plan.hpp"
@@ -388,6 +389,130 @@ static size_t zstd_stage(Workspace &ws, const uint8_t *src, size_t len, uint8_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Lossless stage on the GPU (lossless policy 2, zhuf.cuh): the stream SZGenericCompressor hands to Lossless_zstd
+// (SZGenericCompressor.hpp:51-60) is assembled in device memory, coded into zstd frames of Huffman-only literal blocks
+// by zhuf_kernels.cu, and only the compressed frames cross PCIe.  Same layout as Lossless_zstd::compress
+// (Lossless_zstd.hpp:29-37): size_t srcLen | zstd frames.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr size_t kZhufMinStream = static_cast<size_t>(4) << 20;   // shorter streams keep the reference's own zstd call
+
+template <class T>
+static size_t stream_len(size_t decomp_hdr_len, const EncodeLayout &lay) {
+    return decomp_hdr_len + lay.n_unpred * sizeof(T) + lay.tree_len + 16 + lay.out_size;
+}
+
+struct CopyJob {
+    uint8_t *dst;
+    const uint8_t *src;
+    size_t len;
+    int parts;
+};
+static void copy_part(void *arg, int worker) {
+    CopyJob &j = *static_cast<CopyJob *>(arg);
+    const size_t per = (j.len + j.parts - 1) / j.parts;
+    const size_t a = std::min(j.len, per * worker), b = std::min(j.len, a + per);
+    if (b > a) memcpy(j.dst + a, j.src + a, b - a);
+}
+
+// device -> caller memory: straight into pinned / registered memory, through the pinned staging buffer and the host
+// worker pool otherwise (a pageable cudaMemcpy would run at a fraction of the link rate)
+static void deliver_d2h(Workspace &ws, uint8_t *dst, const uint8_t *d_src, size_t bytes) {
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();   // an unregistered pointer may leave an error behind on old drivers
+    if (pinned) {
+        ws.d2h(dst, d_src, bytes);
+        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        return;
+    }
+    uint8_t *stage = static_cast<uint8_t *>(ws.stage.ensure(bytes + 16));
+    ws.d2h(stage, d_src, bytes);
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    CopyJob j{dst, stage, bytes, std::max(1, std::min(host_threads(), 8))};
+    if (bytes < (1u << 20))
+        memcpy(dst, stage, bytes);
+    else
+        host_parallel(j.parts, copy_part, &j);
+}
+
+// stage-level entry (sz3b_lossless_compress): any byte buffer through the GPU lossless stage
+size_t lossless_gpu_stage(Workspace &ws, const uint8_t *src, size_t len, int loc, uint8_t *out, size_t cap) {
+    if (cap < sizeof(uint64_t) + zhuf_bound(len)) fail(SZ3B_E_INVALID_ARGUMENT, "output buffer too small");
+    const uint8_t *d_src = src;
+    if (loc == SZ3B_HOST) {
+        uint8_t *d = ws.zsrc.as<uint8_t>(len + 64);
+        if (len) SZ3B_CUDA(cudaMemcpyAsync(d, src, len, cudaMemcpyHostToDevice, ws.st));
+        ws.h2d_bytes += len;
+        d_src = d;
+    }
+    const uint64_t nblocks = zhuf_num_blocks(len);
+    ZhufBlockInfo *d_info = ws.zinfo.as<ZhufBlockInfo>(nblocks + 1);
+    uint8_t *d_out = ws.zdst.as<uint8_t>(zhuf_bound(len));
+    unsigned long long *d_total = ws.counters.as<unsigned long long>(4) + 3;
+    size_t h = ws.stage_begin("lossless_gpu");
+    launch_zhuf(d_src, len, d_info, d_out, d_total, ws.st);
+    ws.stage_end(h, 3);
+    unsigned long long csize = 0;
+    ws.d2h(&csize, d_total, sizeof(csize));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(cudaGetLastError());
+    if (csize > zhuf_bound(len)) fail(SZ3B_E_RUNTIME, "GPU lossless stage produced an invalid size");
+    uint8_t *p = out;
+    put<uint64_t>(p, static_cast<uint64_t>(len));
+    if (csize) deliver_d2h(ws, p, d_out, csize);
+    return sizeof(uint64_t) + csize;
+}
+
+template <class T>
+static size_t zhuf_stage(Workspace &ws, const uint8_t *decomp_hdr, size_t decomp_hdr_len, const EncodeLayout &lay,
+                         const HuffmanBook &book, uint64_t n, uint8_t *dst, size_t cap) {
+    const size_t total = stream_len<T>(decomp_hdr_len, lay);
+    // the reference's capacity rule (Lossless_zstd.hpp:30-33 -> std::length_error), independent of the policy
+    if (cap < sizeof(uint64_t) || cap - sizeof(uint64_t) < ZSTD_compressBound(total)) throw TooSmall{};
+    size_t h = ws.stage_begin("lossless_gpu");
+    uint8_t *d_src = ws.zsrc.as<uint8_t>(total + 64);
+    // small host-built pieces go up, the bulk (unpredictable values, packed bits) is already on the device
+    size_t off = 0;
+    ws.h2d(d_src, decomp_hdr, decomp_hdr_len);
+    off += decomp_hdr_len;
+    if (lay.n_unpred)
+        SZ3B_CUDA(cudaMemcpyAsync(d_src + off, ws.unpred_out.p, lay.n_unpred * sizeof(T), cudaMemcpyDeviceToDevice, ws.st));
+    off += lay.n_unpred * sizeof(T);
+    std::vector<uint8_t> mid(lay.tree_len + 16);
+    memcpy(mid.data(), book.tree_blob.data(), lay.tree_len);
+    {
+        uint8_t *p = mid.data() + lay.tree_len;
+        put<uint64_t>(p, n);
+        put<uint64_t>(p, lay.out_size);
+    }
+    uint8_t *mid_pin = static_cast<uint8_t *>(ws.stage2.ensure(mid.size() + 16));
+    memcpy(mid_pin, mid.data(), mid.size());
+    SZ3B_CUDA(cudaMemcpyAsync(d_src + off, mid_pin, mid.size(), cudaMemcpyHostToDevice, ws.st));
+    ws.h2d_bytes += mid.size();
+    off += mid.size();
+    if (lay.out_size)
+        SZ3B_CUDA(cudaMemcpyAsync(d_src + off, ws.out_words.p, lay.out_size, cudaMemcpyDeviceToDevice, ws.st));
+    const uint64_t nblocks = zhuf_num_blocks(total);
+    ZhufBlockInfo *d_info = ws.zinfo.as<ZhufBlockInfo>(nblocks + 1);
+    uint8_t *d_out = ws.zdst.as<uint8_t>(zhuf_bound(total));
+    unsigned long long *d_total = ws.counters.as<unsigned long long>(4) + 3;
+    launch_zhuf(d_src, total, d_info, d_out, d_total, ws.st);
+    ws.stage_end(h, 3);
+    unsigned long long csize = 0;
+    ws.d2h(&csize, d_total, sizeof(csize));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(cudaGetLastError());
+    if (csize == 0 || csize > zhuf_bound(total)) fail(SZ3B_E_RUNTIME, "GPU lossless stage produced an invalid size");
+    if (sizeof(uint64_t) + csize > cap) throw TooSmall{};
+    double t0 = now_ms();
+    uint8_t *p = dst;
+    put<uint64_t>(p, static_cast<uint64_t>(total));
+    deliver_d2h(ws, p, d_out, csize);
+    ws.host_stage("d2h_compressed", now_ms() - t0);
+    return sizeof(uint64_t) + csize;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // SZ_compress_Interp (SZAlgoInterp.hpp:17-30) for `nbatch` arrays of identical shape (nbatch > 1 only in the tuner,
 // where the index streams of all sampled cubes are merged before encoding, :50-56).
 // ---------------------------------------------------------------------------------------------------------------------
@@ -422,6 +547,8 @@ static size_t interp_compress_t(Workspace &ws, const sz3b_config &conf, const T 
     encode_indices<QT, T>(ws, d_q, n, d_hist, nbins, 0, true, d_unpred_tmp, book, lay);
     uint8_t hdr[128];
     size_t hdr_len = interp_save_header<T>(pl, radius, lay.n_unpred, hdr);
+    if (!tuner && lossless_policy() == 2 && stream_len<T>(hdr_len, lay) >= kZhufMinStream)
+        return zhuf_stage<T>(ws, hdr, hdr_len, lay, book, n, dst, cap);
     uint8_t *buf = nullptr;
     ArrivalGate gate;
     size_t len = assemble_stream<T>(ws, hdr, hdr_len, lay, book, n, tuner ? ws.stage2 : ws.stage, &buf, gate);
@@ -1012,6 +1139,8 @@ static size_t blockwise_compress_t(Workspace &ws, const sz3b_config &conf, const
     uint8_t qh[32];
     size_t qh_len = quantizer_header<T>(conf.absErrorBound, radius, lay.n_unpred, qh);
     hdr.insert(hdr.end(), qh, qh + qh_len);
+    if (lossless_policy() == 2 && stream_len<T>(hdr.size(), lay) >= kZhufMinStream)
+        return zhuf_stage<T>(ws, hdr.data(), hdr.size(), lay, book, n, dst, cap);
     uint8_t *buf = nullptr;
     ArrivalGate gate;
     size_t len = assemble_stream<T>(ws, hdr.data(), hdr.size(), lay, book, n, ws.stage, &buf, gate);

@@ -275,7 +275,7 @@ void zjob_worker(void *arg, int) {
     }
 }
 
-std::atomic<int> g_lossless_policy{0};
+std::atomic<int> g_lossless_policy{2};
 }  // namespace
 
 void set_lossless_policy(int p) { g_lossless_policy.store(p); }

@@ -99,6 +99,8 @@ struct Workspace {
     DevBuf coef, coef2, coef_q, side_q, misc, counters, cpos, cval, hist2;
     // Lorenzo stacks (lorenzo.cu): padded working array, block selections, dense ranks, coefficient guesses
     DevBuf padded, bsel, bsel2, brank, cspec, cdense;
+    // GPU lossless stage (zhuf_kernels.cu): assembled stream, per-block tables, compressed frames
+    DevBuf zsrc, zinfo, zdst;
     // Huffman decode
     DevBuf hd_bits, hd_tab, hd_over, hd_counts, hd_offs;
     // pinned staging

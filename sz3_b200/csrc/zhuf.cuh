@@ -1,0 +1,358 @@
+// sz3_b200/csrc/zhuf.cuh -- the GPU lossless stage ("zhuf"): standard zstd frames whose blocks hold only
+// Huffman-coded literals (no sequences), so that the unmodified reference decoder (Lossless_zstd::decompress ->
+// ZSTD_decompress, reference include/SZ3/lossless/Lossless_zstd.hpp:39-45) reads them like any other zstd stream.
+//
+// Why: the bytes that reach the lossless stage are the output of HuffmanEncoder.  zstd finds no matches in them; its
+// whole gain (about 1 %) is the order-0 entropy coding of the literals, and that costs 7 ms of host time per 46 MB at
+// level 3 on 16 cores.  Here every 128 KiB block gets its own byte histogram, length-limited Huffman code, tree
+// description and 4-stream bit packing on the GPU; the host only learns the total size.  Per-block tables follow the
+// local statistics of the index stream (coarse levels first, then the fine level), which gains more than zstd -3 does.
+//
+// Format facts used (zstd compression format, sections Frame_Header, Block_Header, Literals_Section,
+// Huffman_Tree_Description, FSE_Table_Description), checked against libzstd's decoder by tests/test_zhuf.py:
+//   * frame   = magic 0xFD2FB528 | FHD 0xA0 (single segment, 4-byte content size) | content size | blocks
+//   * block   = 3-byte header (last | type << 1 | size << 3) | payload;  type 0 raw, 2 compressed
+//   * literals-only compressed block = literals section | 0x00 (zero sequences)
+//   * literals section (type 2, 4 streams, size format 3) = 5-byte header | tree description | 6-byte jump table |
+//     4 streams; a stream holds its symbols LAST symbol first, codes appended LSB-first, closed by a single 1 bit
+//   * tree description = FSE-compressed weights (accuracy log 6, two interleaved states) or 4-bit direct weights;
+//     weight = max_bits + 1 - length, the last present symbol's weight is implied
+//   * code of a symbol: canonical, longest codes first, symbols ascending inside a length
+//
+// Plain inline code shared by the kernels (zhuf_kernels.cu) and the test-only sequential encoder (tests/emul).
+#pragma once
+#include "core.cuh"
+
+namespace sz3b {
+
+constexpr int kZhufMaxBits = 11;               // Huffman literals: Max_Number_of_Bits
+constexpr uint32_t kZhufBlock = 128u << 10;    // Block_Maximum_Size
+constexpr uint32_t kZhufFrame = 1u << 20;      // source bytes per frame (8 blocks): frames decode in parallel
+constexpr uint32_t kZhufBlocksPerFrame = kZhufFrame / kZhufBlock;
+constexpr uint32_t kZhufMinCoded = 1024;       // shorter blocks are stored raw
+constexpr uint32_t kZhufFrameHeader = 9;
+constexpr uint32_t kZhufDescCap = 136;
+
+struct ZhufBlockInfo {
+    uint32_t sym[256];          // len << 16 | code, 0 for absent symbols
+    uint8_t desc[kZhufDescCap]; // Huffman_Tree_Description
+    uint32_t desc_len;
+    uint32_t ok;                // a usable code exists
+    uint32_t sb[4];             // bytes of the 4 streams (closing bit included)
+    uint32_t coded;             // decided by the scan: 1 = compressed block, 0 = raw block
+    uint32_t pad_;
+    unsigned long long off;     // offset of the block header in the output
+};
+
+// worst-case output size for `len` source bytes (every block raw + headers)
+SZ_HD size_t zhuf_bound(size_t len) {
+    const size_t frames = (len + kZhufFrame - 1) / kZhufFrame + 1;
+    const size_t blocks = (len + kZhufBlock - 1) / kZhufBlock + frames;
+    return len + frames * kZhufFrameHeader + blocks * 3 + 64;
+}
+SZ_HD uint64_t zhuf_num_blocks(uint64_t len) { return (len + kZhufBlock - 1) / kZhufBlock; }
+SZ_HD uint32_t zhuf_block_len(uint64_t len, uint64_t g) {
+    const uint64_t a = g * kZhufBlock;
+    return static_cast<uint32_t>(len - a < kZhufBlock ? len - a : kZhufBlock);
+}
+// source range of stream s (0..3) of block g
+SZ_HD void zhuf_stream_range(uint64_t len, uint64_t g, int s, uint64_t *a, uint64_t *b) {
+    const uint32_t bl = zhuf_block_len(len, g);
+    const uint32_t seg = (bl + 3) / 4;
+    const uint32_t lo = static_cast<uint32_t>(s) * seg < bl ? static_cast<uint32_t>(s) * seg : bl;
+    const uint32_t hi = s == 3 ? bl : (lo + seg < bl ? lo + seg : bl);
+    *a = g * kZhufBlock + lo;
+    *b = g * kZhufBlock + hi;
+}
+// payload bytes of block g and whether it is worth coding
+SZ_HD uint32_t zhuf_block_payload(uint32_t bl, const ZhufBlockInfo &bi, bool *coded) {
+    const uint64_t lit = static_cast<uint64_t>(bi.desc_len) + 6 + bi.sb[0] + bi.sb[1] + bi.sb[2] + bi.sb[3];
+    const uint64_t payload = 5 + lit + 1;
+    *coded = bi.ok && bl >= kZhufMinCoded && payload < bl && lit < (1u << 18);
+    return *coded ? static_cast<uint32_t>(payload) : bl;
+}
+
+SZ_HD void zhuf_put_le(uint8_t *p, uint64_t v, int nbytes) {
+    for (int i = 0; i < nbytes; i++) p[i] = static_cast<uint8_t>(v >> (8 * i));
+}
+
+// Headers of block g (block header at out + bi.off): frame header (first block of a frame), block header, literals
+// header, tree description, jump table, closing "0 sequences" byte.  Returns the offset of stream 0 / the raw bytes.
+SZ_HD uint64_t zhuf_write_headers(uint8_t *out, uint64_t len, uint64_t g, const ZhufBlockInfo &bi) {
+    const uint64_t nblocks = zhuf_num_blocks(len);
+    const uint64_t f = g / kZhufBlocksPerFrame, g0 = f * kZhufBlocksPerFrame;
+    const bool last = g + 1 == nblocks || g + 1 == g0 + kZhufBlocksPerFrame;
+    const uint32_t bl = zhuf_block_len(len, g);
+    const uint64_t bo = bi.off;
+    if (g == g0) {
+        const uint64_t fa = f * kZhufFrame;
+        const uint64_t flen = len - fa < kZhufFrame ? len - fa : kZhufFrame;
+        uint8_t *h = out + bo - kZhufFrameHeader;
+        zhuf_put_le(h, 0xFD2FB528u, 4);
+        h[4] = 0xA0;   // Frame_Content_Size_flag 2 (4 bytes), Single_Segment_flag
+        zhuf_put_le(h + 5, flen, 4);
+    }
+    if (!bi.coded) {
+        zhuf_put_le(out + bo, (last ? 1u : 0u) | (0u << 1) | (static_cast<uint64_t>(bl) << 3), 3);
+        return bo + 3;
+    }
+    const uint64_t lit = static_cast<uint64_t>(bi.desc_len) + 6 + bi.sb[0] + bi.sb[1] + bi.sb[2] + bi.sb[3];
+    const uint64_t payload = 5 + lit + 1;
+    zhuf_put_le(out + bo, (last ? 1u : 0u) | (2u << 1) | (payload << 3), 3);
+    uint8_t *p = out + bo + 3;
+    // Literals_Section_Header, size format 3: type(2) | 3(2) | regenerated size(18) | compressed size(18)
+    zhuf_put_le(p, 2u | (3u << 2) | (static_cast<uint64_t>(bl) << 4) | (lit << 22), 5);
+    p += 5;
+    for (uint32_t i = 0; i < bi.desc_len; i++) p[i] = bi.desc[i];
+    p += bi.desc_len;
+    zhuf_put_le(p, bi.sb[0], 2);
+    zhuf_put_le(p + 2, bi.sb[1], 2);
+    zhuf_put_le(p + 4, bi.sb[2], 2);
+    out[bo + 3 + payload - 1] = 0;   // Sequences_Section: 0 sequences
+    return bo + 3 + 5 + bi.desc_len + 6;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Huffman code construction (one block = at most 131072 symbols over 256 byte values)
+// ---------------------------------------------------------------------------------------------------------------------
+// In-place minimum-redundancy code lengths (Moffat & Katajainen): A[0..n) ascending frequencies in, code lengths out
+// (A[0] = the rarest symbol's = the longest).
+SZ_HD void zhuf_mk_lengths(uint32_t *A, int n) {
+    if (n == 1) {
+        A[0] = 0;
+        return;
+    }
+    A[0] += A[1];
+    int root = 0, leaf = 2;
+    for (int next = 1; next < n - 1; next++) {
+        if (leaf >= n || A[root] < A[leaf]) {
+            A[next] = A[root];
+            A[root++] = static_cast<uint32_t>(next);
+        } else {
+            A[next] = A[leaf++];
+        }
+        if (leaf >= n || (root < next && A[root] < A[leaf])) {
+            A[next] += A[root];
+            A[root++] = static_cast<uint32_t>(next);
+        } else {
+            A[next] += A[leaf++];
+        }
+    }
+    A[n - 2] = 0;
+    for (int next = n - 3; next >= 0; next--) A[next] = A[A[next]] + 1;
+    int avbl = 1, used = 0, dpth = 0, r = n - 2, nx = n - 1;
+    while (avbl > 0) {
+        while (r >= 0 && static_cast<int>(A[r]) == dpth) {
+            used++;
+            r--;
+        }
+        while (avbl > used) {
+            A[nx--] = static_cast<uint32_t>(dpth);
+            avbl--;
+        }
+        avbl = 2 * used;
+        dpth++;
+        used = 0;
+    }
+}
+
+struct ZhufBits {   // forward bit writer, LSB first, into a zeroed byte buffer
+    uint8_t *p;
+    uint32_t cap, bits;
+    bool overflow;
+};
+SZ_HD void zhuf_bits_init(ZhufBits &w, uint8_t *buf, uint32_t cap) {
+    w.p = buf;
+    w.cap = cap;
+    w.bits = 0;
+    w.overflow = false;
+    for (uint32_t i = 0; i < cap; i++) buf[i] = 0;
+}
+SZ_HD void zhuf_bits_put(ZhufBits &w, uint32_t v, int n) {
+    for (int i = 0; i < n; i++, w.bits++) {
+        if ((w.bits >> 3) >= w.cap) {
+            w.overflow = true;
+            return;
+        }
+        if ((v >> i) & 1u) w.p[w.bits >> 3] |= static_cast<uint8_t>(1u << (w.bits & 7));
+    }
+}
+
+// FSE-compressed weights: FSE_Table_Description (normalized counts, accuracy log 6) followed by the two-state backward
+// bitstream.  Returns the number of bytes written, 0 when this representation is not possible.
+SZ_HD uint32_t zhuf_fse_weights(const uint8_t *w, int n, uint8_t *out, uint32_t cap) {
+    constexpr int kLog = 6, kSize = 1 << kLog;
+    if (n < 2) return 0;
+    int count[16], norm[16];
+    for (int s = 0; s < 16; s++) count[s] = norm[s] = 0;
+    int max_sym = 0;
+    for (int i = 0; i < n; i++) {
+        count[w[i]]++;
+        max_sym = w[i] > max_sym ? w[i] : max_sym;
+    }
+    // normalized counts: every present symbol at least 1, total kSize, no symbol owning the whole table
+    int total = 0, present = 0;
+    for (int s = 0; s <= max_sym; s++)
+        if (count[s]) {
+            const int v = (count[s] * kSize + n / 2) / n;
+            norm[s] = v < 1 ? 1 : v;
+            total += norm[s];
+            present++;
+        }
+    if (present < 2) return 0;   // one repeated weight has no FSE form
+    while (total != kSize) {
+        int best = -1;
+        for (int s = 0; s <= max_sym; s++)
+            if (norm[s] > (total > kSize ? 1 : 0) && (best < 0 || norm[s] > norm[best])) best = s;
+        if (best < 0) return 0;
+        if (total > kSize) {
+            norm[best]--;
+            total--;
+        } else {
+            norm[best]++;
+            total++;
+        }
+    }
+    for (int s = 0; s <= max_sym; s++)
+        if (norm[s] >= kSize) return 0;
+    // ---- FSE_Table_Description
+    ZhufBits hw;
+    zhuf_bits_init(hw, out, cap);
+    zhuf_bits_put(hw, kLog - 5, 4);
+    {
+        int remaining = kSize + 1, threshold = kSize, nbits = kLog + 1;
+        int s = 0;
+        while (remaining > 1 && s <= max_sym) {
+            const int c = norm[s++];
+            const int max = (2 * threshold - 1) - remaining;
+            remaining -= c;
+            int v = c + 1;
+            if (v >= threshold) v += max;
+            zhuf_bits_put(hw, static_cast<uint32_t>(v), nbits - (v < max ? 1 : 0));
+            if (c == 0) {   // further zero-probability symbols: 2-bit repeat codes, 3 = "three more and continue"
+                int run = 0;
+                while (s <= max_sym && norm[s] == 0) {
+                    run++;
+                    s++;
+                }
+                while (run >= 3) {
+                    zhuf_bits_put(hw, 3, 2);
+                    run -= 3;
+                }
+                zhuf_bits_put(hw, static_cast<uint32_t>(run), 2);
+            }
+            while (remaining < threshold) {
+                nbits--;
+                threshold >>= 1;
+            }
+        }
+        if (remaining != 1) return 0;
+    }
+    if (hw.overflow) return 0;
+    const uint32_t hdr = (hw.bits + 7) >> 3;
+    // ---- the decoder's table: symbols spread with step (size/2 + size/8 + 3), states numbered per symbol in table
+    //      order; the encoder needs the inverse map (symbol, k-th occurrence) -> table index
+    uint8_t table_sym[kSize];
+    {
+        const int step = (kSize >> 1) + (kSize >> 3) + 3;
+        int pos = 0;
+        for (int s = 0; s <= max_sym; s++)
+            for (int i = 0; i < norm[s]; i++) {
+                table_sym[pos] = static_cast<uint8_t>(s);
+                pos = (pos + step) & (kSize - 1);
+            }
+        if (pos != 0) return 0;
+    }
+    uint8_t first_of[16];    // table index range of a symbol's states, as a start into state_of
+    uint8_t state_of[kSize]; // table indices grouped by symbol, in table order
+    {
+        int at = 0;
+        for (int s = 0; s <= max_sym; s++) {
+            first_of[s] = static_cast<uint8_t>(at);
+            at += norm[s];
+        }
+        int seen[16];
+        for (int s = 0; s < 16; s++) seen[s] = 0;
+        for (int u = 0; u < kSize; u++) {
+            const int s = table_sym[u];
+            state_of[first_of[s] + seen[s]++] = static_cast<uint8_t>(u);
+        }
+    }
+    // ---- two interleaved states, symbols taken from the last to the first; even positions use state 0.  A state
+    //      starts on the smallest sub-state of its symbol: the decoder then reads the most bits for it (at least one,
+    //      as no count reaches the table size), which is how it detects the end of the stream on the last two symbols.
+    ZhufBits bw;
+    zhuf_bits_init(bw, out + hdr, cap - hdr);
+    int X[2] = {0, 0};
+    bool init[2] = {false, false};
+    for (int i = n - 1; i >= 0; i--) {
+        const int k = i & 1, s = w[i], c = norm[s];
+        if (!init[k]) {
+            X[k] = kSize + state_of[first_of[s]];
+            init[k] = true;
+            continue;
+        }
+        int nb = 0;
+        while ((X[k] >> nb) >= 2 * c) nb++;
+        zhuf_bits_put(bw, static_cast<uint32_t>(X[k]) & ((1u << nb) - 1u), nb);
+        X[k] = kSize + state_of[first_of[s] + (X[k] >> nb) - c];
+    }
+    zhuf_bits_put(bw, static_cast<uint32_t>(X[1] - kSize), kLog);
+    zhuf_bits_put(bw, static_cast<uint32_t>(X[0] - kSize), kLog);
+    zhuf_bits_put(bw, 1, 1);
+    if (bw.overflow) return 0;
+    return hdr + ((bw.bits + 7) >> 3);
+}
+
+// Table of one block from its byte histogram.  sorted_sym / sorted_freq: the present symbols in ascending (frequency,
+// symbol) order (n of them) -- produced by the caller (rank sort across the lanes of a warp on the device).
+// work: n words of scratch.
+SZ_HD void zhuf_build_table(const uint8_t *sorted_sym, uint32_t *sorted_freq, int n, uint32_t *work, ZhufBlockInfo &t) {
+    for (int s = 0; s < 256; s++) t.sym[s] = 0;
+    t.desc_len = 0;
+    t.ok = 0;
+    if (n < 2) return;
+    int longest;
+    for (;;) {
+        for (int i = 0; i < n; i++) work[i] = sorted_freq[i];
+        zhuf_mk_lengths(work, n);
+        longest = static_cast<int>(work[0]);
+        if (longest <= kZhufMaxBits) break;
+        // flatten the histogram until the code fits; halving keeps the order, the result stays a complete Huffman code
+        for (int i = 0; i < n; i++) sorted_freq[i] = (sorted_freq[i] + 1) / 2;
+    }
+    uint8_t len[256], w[256];
+    for (int s = 0; s < 256; s++) len[s] = 0;
+    for (int i = 0; i < n; i++) len[sorted_sym[i]] = static_cast<uint8_t>(work[i]);
+    int last = 255;
+    while (last >= 0 && len[last] == 0) last--;
+    if (last < 1) return;
+    for (int s = 0; s < last; s++) w[s] = len[s] ? static_cast<uint8_t>(longest + 1 - len[s]) : 0;
+    const int nw = last;   // explicit weights; the last present symbol's weight is implied
+    const uint32_t fse = zhuf_fse_weights(w, nw, t.desc + 1, kZhufDescCap - 1);
+    if (fse > 0 && fse < 128) {
+        t.desc[0] = static_cast<uint8_t>(fse);
+        t.desc_len = fse + 1;
+    } else if (nw <= 128) {   // direct representation: 4 bits per weight
+        t.desc[0] = static_cast<uint8_t>(127 + nw);
+        for (int i = 0; i < nw; i += 2) t.desc[1 + i / 2] = static_cast<uint8_t>((w[i] << 4) | (i + 1 < nw ? w[i + 1] : 0));
+        t.desc_len = static_cast<uint32_t>(1 + (nw + 1) / 2);
+    } else {
+        return;
+    }
+    // canonical codes: longest codes first, symbols ascending inside a length
+    uint32_t per_rank[kZhufMaxBits + 2], val[kZhufMaxBits + 2];
+    for (int b = 0; b < kZhufMaxBits + 2; b++) per_rank[b] = val[b] = 0;
+    for (int s = 0; s < 256; s++)
+        if (len[s]) per_rank[len[s]]++;
+    uint32_t min = 0;
+    for (int b = longest; b >= 1; b--) {
+        val[b] = min;
+        min = (min + per_rank[b]) >> 1;
+    }
+    for (int s = 0; s < 256; s++)
+        if (len[s]) t.sym[s] = (static_cast<uint32_t>(len[s]) << 16) | val[len[s]]++;
+    t.ok = 1;
+}
+
+}  // namespace sz3b

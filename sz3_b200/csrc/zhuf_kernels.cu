@@ -1,0 +1,230 @@
+// sz3_b200/csrc/zhuf_kernels.cu -- the GPU lossless stage: zstd frames of Huffman-only literal blocks (zhuf.cuh).
+//
+//   k_zhuf_build    one CTA per 128 KiB block: byte histogram (shared-memory atomics), rank sort of the 256 counters,
+//                   Huffman code + zstd tree description (one thread; a few thousand serial steps), bytes of the 4 streams
+//   k_zhuf_scan     one CTA: coded / raw decision per block, output offsets (frame and block headers included), total
+//   k_zhuf_encode   one CTA per stream: per-thread chunk bit counts, suffix scan, codes OR-ed into a shared-memory bit
+//                   buffer (last symbol first, LSB-first), closing bit, byte copy to the stream's place; stream 0's CTA
+//                   also writes the block's headers
+//
+// HBM-bound byte work: the source is read three times (histogram, sizes, encode; the second and third hit L2 for the
+// block sizes involved) and the output written once.
+#include <cuda_runtime.h>
+
+#include "launch.hpp"
+#include "zhuf.cuh"
+
+namespace sz3b {
+
+constexpr int kZhufThreads = 256;
+
+__global__ void __launch_bounds__(kZhufThreads) k_zhuf_build(const uint8_t *__restrict__ src, uint64_t len,
+                                                             ZhufBlockInfo *__restrict__ infos) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint8_t ss[256];
+    __shared__ uint32_t sf[256], work[256];
+    __shared__ ZhufBlockInfo info;
+    __shared__ unsigned long long bits[4];
+    const uint64_t g = blockIdx.x;
+    const uint32_t bl = zhuf_block_len(len, g);
+    const uint8_t *p = src + g * kZhufBlock;
+    const int tid = threadIdx.x;
+    hist[tid] = 0;
+    if (tid < 4) bits[tid] = 0;
+    __syncthreads();
+    const uint32_t nvec = bl / 16;   // blocks start 16-byte aligned (the stream buffer is, and 128 KiB divides evenly)
+    const uint4 *pv = reinterpret_cast<const uint4 *>(p);
+    for (uint32_t i = tid; i < nvec; i += kZhufThreads) {
+        const uint4 v = pv[i];
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            atomicAdd(&hist[wv[k] & 0xff], 1u);
+            atomicAdd(&hist[(wv[k] >> 8) & 0xff], 1u);
+            atomicAdd(&hist[(wv[k] >> 16) & 0xff], 1u);
+            atomicAdd(&hist[wv[k] >> 24], 1u);
+        }
+    }
+    for (uint32_t i = nvec * 16 + tid; i < bl; i += kZhufThreads) atomicAdd(&hist[p[i]], 1u);
+    __syncthreads();
+    // rank sort by (count, symbol): thread s places symbol s
+    const uint32_t mine = hist[tid];
+    int rank = 0;
+    for (int j = 0; j < 256; j++) {
+        const uint32_t h = hist[j];
+        rank += (h != 0 && (h < mine || (h == mine && j < tid))) ? 1 : 0;
+    }
+    if (mine) {
+        ss[rank] = static_cast<uint8_t>(tid);
+        sf[rank] = mine;
+    }
+    const int n = __syncthreads_count(mine != 0);
+    if (tid == 0) zhuf_build_table(ss, sf, n, work, info);
+    __syncthreads();
+    // bytes of the four streams under this code
+    const uint32_t seg = (bl + 3) / 4;
+    unsigned long long acc[4] = {0, 0, 0, 0};
+    for (uint32_t i = tid; i < nvec; i += kZhufThreads) {
+        const uint4 v = pv[i];
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t at = i * 16;
+        uint32_t s = at / seg;   // a 16-byte group lies in one stream whenever seg is a multiple of 16 (full blocks)
+        if (s > 3) s = 3;
+        const bool whole = (at + 15) / seg == at / seg || s == 3;
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t l = info.sym[(wv[k] >> (8 * b)) & 0xff] >> 16;
+                if (whole) {
+                    sum += l;
+                } else {
+                    uint32_t sj = (at + 4 * k + b) / seg;
+                    acc[sj > 3 ? 3 : sj] += l;
+                }
+            }
+        }
+        acc[s] += sum;
+    }
+    for (uint32_t i = nvec * 16 + tid; i < bl; i += kZhufThreads) {
+        uint32_t sj = i / seg;
+        acc[sj > 3 ? 3 : sj] += info.sym[p[i]] >> 16;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        unsigned long long v = acc[s];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0 && v) atomicAdd(&bits[s], v);
+    }
+    __syncthreads();
+    if (tid < 4) info.sb[tid] = static_cast<uint32_t>(bits[tid] / 8 + 1);
+    __syncthreads();
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&infos[g]);
+    const uint32_t *sp = reinterpret_cast<const uint32_t *>(&info);
+    for (uint32_t i = tid; i < sizeof(ZhufBlockInfo) / 4; i += kZhufThreads) dst[i] = sp[i];
+}
+
+__global__ void __launch_bounds__(1024) k_zhuf_scan(ZhufBlockInfo *__restrict__ infos, uint64_t len, uint64_t nblocks,
+                                                    unsigned long long *__restrict__ total_out) {
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint64_t start = 0; start < nblocks; start += 1024) {
+        const uint64_t g = start + threadIdx.x;
+        unsigned long long v = 0, pre = 0;
+        bool coded = false;
+        if (g < nblocks) {
+            const uint32_t payload = zhuf_block_payload(zhuf_block_len(len, g), infos[g], &coded);
+            pre = g % kZhufBlocksPerFrame == 0 ? kZhufFrameHeader : 0;
+            v = pre + 3 + payload;
+        }
+        unsigned long long x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long w = warp_sum[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sum[lane] = w;
+        }
+        __syncthreads();
+        const unsigned long long carry = carry_s;
+        const unsigned long long before = carry + (wid ? warp_sum[wid - 1] : 0ull) + x - v;
+        if (g < nblocks) {
+            infos[g].coded = coded ? 1u : 0u;
+            infos[g].off = before + pre;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_sum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+constexpr uint32_t kZhufBufWords = (kZhufBlock / 4 * kZhufMaxBits + 31) / 32 + 2;   // bits of one stream + closing bit
+
+__global__ void __launch_bounds__(kZhufThreads) k_zhuf_encode(const uint8_t *__restrict__ src, uint64_t len,
+                                                              const ZhufBlockInfo *__restrict__ infos,
+                                                              uint8_t *__restrict__ out) {
+    __shared__ uint32_t sym_s[256];
+    __shared__ uint32_t buf[kZhufBufWords];
+    __shared__ uint32_t warp_sum[kZhufThreads / 32];
+    const uint64_t g = blockIdx.x >> 2;
+    const int s = blockIdx.x & 3;
+    const int tid = threadIdx.x;
+    const ZhufBlockInfo &bi = infos[g];
+    if (s == 0 && tid == 0) zhuf_write_headers(out, len, g, bi);
+    uint64_t a, b;
+    zhuf_stream_range(len, g, s, &a, &b);
+    const uint32_t n = static_cast<uint32_t>(b - a);
+    if (!bi.coded) {
+        uint8_t *dst = out + bi.off + 3 + (a - g * kZhufBlock);
+        for (uint32_t i = tid; i < n; i += kZhufThreads) dst[i] = src[a + i];
+        return;
+    }
+    const uint32_t sb = bi.sb[s];
+    uint64_t p = bi.off + 3 + 5 + bi.desc_len + 6;
+    for (int k = 0; k < s; k++) p += bi.sb[k];
+    sym_s[tid] = bi.sym[tid];
+    for (uint32_t i = tid; i < (sb + 3) / 4 + 1 && i < kZhufBufWords; i += kZhufThreads) buf[i] = 0;
+    __syncthreads();
+    // chunk of this thread, bit count
+    const uint32_t per = (n + kZhufThreads - 1) / kZhufThreads;
+    const uint32_t c0 = tid * per < n ? tid * per : n, c1 = c0 + per < n ? c0 + per : n;
+    const uint8_t *sp = src + a;
+    uint32_t mybits = 0;
+    for (uint32_t i = c0; i < c1; i++) mybits += sym_s[sp[i]] >> 16;
+    // bits written before this chunk = bits of all LATER chunks (the last symbol goes first)
+    uint32_t x = mybits;
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[wid] = x;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kZhufThreads / 32; w++) {
+        if (w < wid) before += warp_sum[w];
+        total += warp_sum[w];
+    }
+    uint32_t o = total - (before + x);
+    for (uint32_t i = c1; i-- > c0;) {
+        const uint32_t e = sym_s[sp[i]];
+        const uint32_t nb = e >> 16, code = e & 0xffffu;
+        const uint32_t w = o >> 5, sh = o & 31;
+        atomicOr(&buf[w], code << sh);
+        if (sh + nb > 32) atomicOr(&buf[w + 1], code >> (32 - sh));
+        o += nb;
+    }
+    if (tid == 0) atomicOr(&buf[total >> 5], 1u << (total & 31));   // closing bit
+    __syncthreads();
+    const uint8_t *bb = reinterpret_cast<const uint8_t *>(buf);
+    uint8_t *dst = out + p;
+    for (uint32_t i = tid; i < sb; i += kZhufThreads) dst[i] = bb[i];
+}
+
+// Compresses src[0, len) (device) into out (device, zhuf_bound(len) bytes); *total (device) receives the size.
+void launch_zhuf(const uint8_t *src, uint64_t len, ZhufBlockInfo *infos, uint8_t *out, unsigned long long *total,
+                 cudaStream_t st) {
+    const uint64_t nblocks = zhuf_num_blocks(len);
+    if (nblocks == 0) {
+        cudaMemsetAsync(total, 0, sizeof(unsigned long long), st);
+        return;
+    }
+    k_zhuf_build<<<static_cast<unsigned>(nblocks), kZhufThreads, 0, st>>>(src, len, infos);
+    k_zhuf_scan<<<1, 1024, 0, st>>>(infos, len, nblocks, total);
+    k_zhuf_encode<<<static_cast<unsigned>(nblocks * 4), kZhufThreads, 0, st>>>(src, len, infos, out);
+}
+
+}  // namespace sz3b

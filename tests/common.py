@@ -104,6 +104,67 @@ def emul_lib():
     return C.CDLL(out)
 
 
+def zhuf_emul_lib():
+    """Sequential encoder of the GPU lossless stage's frames (tests/emul/zhuf_emul.cpp; test infrastructure)."""
+    src = os.path.join(ROOT, "tests", "emul", "zhuf_emul.cpp")
+    out = os.path.join(ROOT, "tests", "emul", "_build", "libzhuf_emul.so")
+    deps = [src, os.path.join(ROOT, "sz3_b200", "csrc", "zhuf.cuh"), os.path.join(ROOT, "sz3_b200", "csrc", "core.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", src, "-o", out], check=True)
+    lib = C.CDLL(out)
+    lib.zhuf_emul_compress.restype = C.c_longlong
+    lib.zhuf_emul_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    return lib
+
+
+def zstd_lib():
+    """The image's libzstd runtime: its decoder is the checker of every zstd frame this repo writes."""
+    z = C.CDLL("libzstd.so.1")
+    z.ZSTD_decompress.restype = C.c_size_t
+    z.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    z.ZSTD_compress.restype = C.c_size_t
+    z.ZSTD_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    z.ZSTD_compressBound.restype = C.c_size_t
+    z.ZSTD_compressBound.argtypes = [C.c_size_t]
+    z.ZSTD_isError.argtypes = [C.c_size_t]
+    z.ZSTD_getErrorName.restype = C.c_char_p
+    z.ZSTD_getErrorName.argtypes = [C.c_size_t]
+    return z
+
+
+def zhuf_cases():
+    """Byte buffers for the lossless-stage tests: (name, uint8 array)."""
+    rng = np.random.default_rng(1)
+    cases = []
+    # a Huffman-coded index stream like the one the stage sees: geometric symbols through a canonical-ish bit packing
+    sym = np.minimum(rng.geometric(0.35, size=3_000_000), 15).astype(np.uint8)
+    bits = np.unpackbits(((1 << sym.astype(np.uint16)) - 2).astype(">u2").view(np.uint8).reshape(-1, 2), axis=1)
+    keep = np.arange(16)[None, :] >= (16 - sym[:, None])
+    cases.append(("huffman-coded stream", np.packbits(bits[keep])))
+    p = np.exp(-np.arange(256) / 20.0)
+    cases.append(("geometric over 256 symbols", rng.choice(256, size=2_500_000, p=p / p.sum()).astype(np.uint8)))
+    p = np.exp(-np.arange(256) / 4.0)
+    cases.append(("steep (length-limited code)", rng.choice(256, size=1_200_000, p=p / p.sum()).astype(np.uint8)))
+    cases.append(("40 symbols uniform", rng.choice(40, size=900_000).astype(np.uint8)))
+    cases.append(("3 symbols", rng.choice(3, size=600_000, p=[0.9, 0.09, 0.01]).astype(np.uint8)))
+    cases.append(("two symbols", rng.choice([7, 200], size=300_000).astype(np.uint8)))
+    cases.append(("uniform random (raw blocks)", rng.integers(0, 256, size=1_500_000).astype(np.uint8)))
+    cases.append(("all zero (raw blocks)", np.zeros(400_000, np.uint8)))
+    cases.append(("mixed", np.concatenate([rng.choice(256, size=1 << 20, p=p / p.sum()), rng.integers(0, 256, size=1 << 20)]).astype(np.uint8)))
+    cases.append(("one block + short tail", rng.choice(256, size=131072 + 500, p=p / p.sum()).astype(np.uint8)))
+    cases.append(("5000 bytes", rng.choice(30, size=5000).astype(np.uint8)))
+    cases.append(("100 bytes", rng.choice(30, size=100).astype(np.uint8)))
+    cases.append(("1 byte", np.array([42], np.uint8)))
+    for k in range(12):
+        n = int(rng.integers(1, 400000))
+        a = float(rng.uniform(0.5, 60))
+        m = int(rng.integers(2, 257))
+        pp = np.exp(-np.arange(m) / a)
+        cases.append((f"random alphabet m={m} a={a:.1f} n={n}", rng.permutation(256)[:m][rng.choice(m, size=n, p=pp / pp.sum())].astype(np.uint8)))
+    return cases
+
+
 def product_lib():
     lib = _load(os.path.join(ROOT, "sz3_b200", "lib", "libsz3b200.so"))
     if lib is None:

@@ -132,7 +132,7 @@ def test_capacity_check():
 
 @needs_ref
 def test_lossless_policy_adaptive_vs_full():
-    """Adaptive raw-frame policy of the host tail (include/sz3b.h: sz3b_set_lossless_policy): both policies give streams
+    """Lossless policies (include/sz3b.h: sz3b_set_lossless_policy; 2 = GPU stage, the default): all give streams
     the unmodified reference decoder reads, identical reconstructions, and ratios within 1 % of each other and of
     the reference."""
     L = product_lib()
@@ -141,15 +141,17 @@ def test_lossless_policy_adaptive_vs_full():
     theirs = ref_compress(data, conf)
     out = {}
     try:
-        for pol in (0, 1):
+        for pol in (0, 1, 2):
             L.sz3b_set_lossless_policy(pol)
             out[pol], _ = gpu_compress(data, conf)
     finally:
-        L.sz3b_set_lossless_policy(0)
+        L.sz3b_set_lossless_policy(2)
     dec0, _ = ref_decompress(out[0], data)
     dec1, _ = ref_decompress(out[1], data)
     assert np.array_equal(dec0, dec1)
     assert np.max(np.abs(dec1 - data)) <= 1e-3
-    r_ref, r0, r1 = (data.nbytes / x.size for x in (theirs, out[0], out[1]))
-    assert abs(r0 - r_ref) / r_ref < 0.01 and abs(r1 - r_ref) / r_ref < 0.01, (r_ref, r0, r1)
+    dec2, _ = ref_decompress(out[2], data)
+    assert np.array_equal(dec0, dec2)
+    r_ref, r0, r1, r2 = (data.nbytes / x.size for x in (theirs, out[0], out[1], out[2]))
+    assert abs(r0 - r_ref) / r_ref < 0.01 and abs(r1 - r_ref) / r_ref < 0.01 and abs(r2 - r_ref) / r_ref < 0.01, (r_ref, r0, r1, r2)
     assert out[1].size >= out[0].size

@@ -1,0 +1,113 @@
+"""The GPU lossless stage ("zhuf", sz3_b200/csrc/zhuf.cuh): zstd frames of Huffman-only literal blocks.
+
+CPU half: the sequential encoder built from the SAME table builder and layout code the kernels use (tests/emul) must
+produce frames that libzstd's own decoder -- what the reference's Lossless_zstd::decompress calls -- turns back into the
+input, for every shape of byte histogram (codes that need length limiting, alphabets that need the FSE or the direct
+tree description, incompressible and constant data that must fall back to raw blocks, ragged sizes).
+GPU half: the kernels produce byte-identical frames to the sequential encoder, and whole compressions under the
+default policy decode with the unmodified reference with a ratio within 1 % of the reference's."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import (Config, dtype_code, field_g3, make_config, product_lib, ref_lib, zhuf_cases, zhuf_emul_lib, zstd_lib)
+
+CASES = zhuf_cases()
+
+
+def emul_compress(src):
+    E = zhuf_emul_lib()
+    out = np.zeros(src.size + src.size // 8 + 4096, np.uint8)
+    coded = C.c_int(0)
+    n = E.zhuf_emul_compress(src.ctypes.data, src.size, out.ctypes.data, out.size, C.byref(coded))
+    assert n > 0, n
+    return out[:n], coded.value
+
+
+def zstd_decode(frames, expect):
+    z = zstd_lib()
+    dec = np.zeros(expect + 64, np.uint8)
+    r = z.ZSTD_decompress(dec.ctypes.data, dec.size, frames.ctypes.data, frames.size)
+    assert not z.ZSTD_isError(r), z.ZSTD_getErrorName(r)
+    return dec[:r]
+
+
+@pytest.mark.parametrize("name,src", CASES, ids=[c[0] for c in CASES])
+def test_frames_decode_with_libzstd(name, src):
+    src = np.ascontiguousarray(src)
+    frames, coded = emul_compress(src)
+    assert np.array_equal(zstd_decode(frames, src.size), src)
+    nblocks = (src.size + (128 << 10) - 1) // (128 << 10)
+    if name.startswith(("uniform random", "all zero", "100 bytes", "1 byte")):
+        assert coded == 0            # nothing to gain: raw blocks
+    elif name.startswith(("geometric", "steep", "40 symbols", "3 symbols", "two symbols", "huffman-coded")):
+        assert coded == nblocks and frames.size < src.size
+
+
+def test_gain_on_index_stream_matches_zstd():
+    """On an entropy-coded stream zstd's whole gain is literal coding: per-block Huffman tables do at least as well."""
+    z = zstd_lib()
+    src = np.ascontiguousarray(CASES[0][1])
+    frames, _ = emul_compress(src)
+    ref = np.zeros(z.ZSTD_compressBound(src.size), np.uint8)
+    r = z.ZSTD_compress(ref.ctypes.data, ref.size, src.ctypes.data, src.size, 3)
+    assert not z.ZSTD_isError(r)
+    assert frames.size <= r * 1.005, (frames.size, r)
+
+
+# ---- GPU half ----------------------------------------------------------------------------------------------------------
+def gpu_lossless(src, device=False):
+    L = product_lib()
+    L.sz3b_lossless_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    out = np.zeros(src.size + src.size // 8 + 8192, np.uint8)
+    n = C.c_size_t(0)
+    if device:
+        import torch
+        t = torch.from_numpy(src).cuda()
+        rc = L.sz3b_lossless_compress(t.data_ptr(), src.size, 1, out.ctypes.data, out.size, C.byref(n))
+    else:
+        rc = L.sz3b_lossless_compress(src.ctypes.data, src.size, 0, out.ctypes.data, out.size, C.byref(n))
+    assert rc == 0, L.sz3b_last_error()
+    assert int(np.frombuffer(out[:8], np.uint64)[0]) == src.size
+    return out[8:n.value]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,src", CASES, ids=[c[0] for c in CASES])
+def test_gpu_frames_identical_to_sequential_encoder(name, src):
+    src = np.ascontiguousarray(src)
+    frames = gpu_lossless(src, device=(len(name) % 2 == 0))
+    want, _ = emul_compress(src)
+    assert frames.size == want.size and np.array_equal(frames, want)
+    assert np.array_equal(zstd_decode(frames, src.size), src)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref/libsz3ref.so not built")
+@pytest.mark.parametrize("dtype,eb", [(np.float32, 1e-3), (np.float64, 1e-4)])
+def test_gpu_lossless_policy_whole_compression(dtype, eb):
+    """256^3 under the default policy: the stream is above 4 MiB, so the frames come from the GPU stage.  The unmodified
+    reference decodes it, both decoders agree bit for bit, and the ratio is within 1 % of the reference's."""
+    from test_gpu_compress import gpu_compress, ref_compress, ref_decompress
+    from test_gpu_decompress import gpu_decompress, same_bits
+    L = product_lib()
+    assert L.sz3b_get_lossless_policy() == 2
+    data = field_g3((256, 256, 256), dtype)
+    conf = make_config(data.shape, absErrorBound=eb)
+    ours, _ = gpu_compress(data, conf)
+    theirs = ref_compress(data, conf)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.max(np.abs(dec.astype(np.float64) - data.astype(np.float64))) <= eb
+    got, _ = gpu_decompress(ours, data)
+    assert same_bits(got, dec)
+    r_ours, r_ref = data.nbytes / ours.size, data.nbytes / theirs.size
+    assert abs(r_ours - r_ref) / r_ref < 0.01, (r_ours, r_ref)
+    # the host-zstd policies still give the reference's own stream size to within the frame overhead
+    try:
+        L.sz3b_set_lossless_policy(0)
+        host, _ = gpu_compress(data, conf)
+    finally:
+        L.sz3b_set_lossless_policy(2)
+    assert abs(host.size - theirs.size) / theirs.size < 0.002
+    assert same_bits(ref_decompress(host, data)[0], dec)
