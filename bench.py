@@ -294,13 +294,24 @@ def run_ours(args):
             ms_total = float(t.item())
         return ms_total, pq_ms, launches, csize
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         step(dev.data_ptr(), 1)
+    # untimed settling beyond W: the first calls still grow per-workspace buffers and the SM clock is still ramping
+    # (the first three 512^3 steps run 30-50 % slower than the steady state); wait until two steps in a row agree
+    prev = None
+    for _ in range(40):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step(dev.data_ptr(), 1)
+        dt = time.perf_counter() - t0
+        if prev is not None and abs(dt - prev) < 0.03 * prev:
+            break
+        prev = dt
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_dev, pq_ms, launches, csize = timed(dev.data_ptr(), 1, args.steps, True)
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(max(args.warmup, 3)):
         step(pinned.data_ptr(), 0)
     ms_e2e, _, _, _ = timed(pinned.data_ptr(), 0, args.steps, False)
     h2d, d2h = C.c_size_t(0), C.c_size_t(0)
@@ -312,9 +323,11 @@ def run_ours(args):
     host_zstd = None
     if policy == 2:
         L.sz3b_set_lossless_policy(0)
-        step(dev.data_ptr(), 1)
+        for _ in range(4):
+            step(dev.data_ptr(), 1)
         ms_dev0, _, _, csize0 = timed(dev.data_ptr(), 1, args.steps, False)
-        step(pinned.data_ptr(), 0)
+        for _ in range(2):
+            step(pinned.data_ptr(), 0)
         ms_e2e0, _, _, _ = timed(pinned.data_ptr(), 0, args.steps, False)
         L.sz3b_set_lossless_policy(2)
         host_zstd = (ms_dev0, ms_e2e0, csize0)

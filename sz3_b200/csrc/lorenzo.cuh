@@ -56,6 +56,10 @@ struct BwArgs {
     QT *q;                       // quantization indices, block-major (written by BW_EXACT, read by BW_DECODE)
     T *unpred_tmp;               // position-indexed unpredictable values (same direction as q)
     uint64_t b_lo, b_hi;         // window of row-major block indices processed by a front launch
+    // points of a FULL block (every extent == B) ordered by index sum: entry = tile offset (relative to the block's
+    // first point) << 16 | row-major rank inside the block; diag_start[d] .. diag_start[d + 1] = diagonal d
+    const uint32_t *diag_tab;
+    const uint16_t *diag_start;
     // BW_SERIAL (row-major walk with the coefficient chain inline): chain outputs, dense over the selected blocks
     QuantParams q_liner, q_indep;
     int32_t *coef_q;
@@ -187,17 +191,30 @@ SZ_HD void bw_process_block(const BwArgs<T, QT> &A, const uint32_t bi[kMaxDim], 
     const int N = bs.N, nc = N + 1;
     BwGeom g;
     bw_geometry(A, bi, g);
-    // ---- 1. tile = halo (finished reconstruction of the lower neighbour blocks, or the zero padding) + the block
-    for (uint32_t e = lane; e < g.tile_size; e += nl) {
-        uint32_t r = e;
-        uint64_t w = g.wbase;
-        for (int d = N - 1; d >= 0; d--) {
-            const uint32_t te = g.ext[d] + kBwPad;
-            const uint32_t t = r % te;
-            r /= te;
-            w += static_cast<uint64_t>(t) * A.pstride[d];
+    // ---- 1. tile = halo (finished reconstruction of the lower neighbour blocks, or the zero padding) + the block;
+    //         row by row, four independent loads in flight per lane
+    {
+        const uint32_t rowlen = g.ext[N - 1] + kBwPad, nrows = g.tile_size / rowlen;
+        for (uint32_t row = lane; row < nrows; row += nl) {
+            uint32_t r = row;
+            uint64_t w = g.wbase;
+            for (int d = N - 2; d >= 0; d--) {
+                const uint32_t te = g.ext[d] + kBwPad;
+                w += static_cast<uint64_t>(r % te) * A.pstride[d];
+                r /= te;
+            }
+            const T *src = A.W + w;
+            T *dst = tile + row * rowlen;
+            uint32_t x = 0;
+            for (; x + 4 <= rowlen; x += 4) {
+                const T v0 = src[x], v1 = src[x + 1], v2 = src[x + 2], v3 = src[x + 3];
+                dst[x] = v0;
+                dst[x + 1] = v1;
+                dst[x + 2] = v2;
+                dst[x + 3] = v3;
+            }
+            for (; x < rowlen; x++) dst[x] = src[x];
         }
-        tile[e] = A.W[w];
     }
     SZ_WARP_SYNC();
     // offset of in-block point (0,..,0) inside the tile
@@ -331,23 +348,33 @@ SZ_HD void bw_process_block(const BwArgs<T, QT> &A, const uint32_t bi[kMaxDim], 
         }
     } else {
         const int L = use + 1;
-        const uint32_t nlead = g.npts / extL;   // index tuples over the dimensions before the last
+        bool full = A.diag_tab != nullptr;
+        for (int d = 0; d < N; d++) full = full && g.ext[d] == bs.B;
         uint32_t ndiag = 1;
         for (int d = 0; d < N; d++) ndiag += g.ext[d] - 1;
+        const uint32_t nlead = g.npts / extL;   // index tuples over the dimensions before the last
         for (uint32_t diag = 0; diag < ndiag; diag++) {
-            for (uint32_t item = lane; item < nlead; item += nl) {
-                uint32_t r = item, s = 0, off = t00, within = 0;
-                for (int d = N - 2; d >= 0; d--) {
-                    const uint32_t i = r % g.ext[d];
-                    r /= g.ext[d];
-                    s += i;
-                    off += i * g.ts[d];
+            const uint32_t i0 = full ? A.diag_start[diag] : 0u, i1 = full ? A.diag_start[diag + 1] : nlead;
+            for (uint32_t item = i0 + lane; item < i1; item += nl) {
+                uint32_t off, within;
+                if (full) {
+                    const uint32_t e = A.diag_tab[item];
+                    off = t00 + (e >> 16);
+                    within = e & 0xffffu;
+                } else {
+                    uint32_t r = item, s = 0;
+                    off = t00;
+                    for (int d = N - 2; d >= 0; d--) {
+                        const uint32_t i = r % g.ext[d];
+                        r /= g.ext[d];
+                        s += i;
+                        off += i * g.ts[d];
+                    }
+                    if (diag < s || diag - s >= extL) continue;
+                    const uint32_t last = diag - s;
+                    off += last;
+                    within = item * extL + last;
                 }
-                within = item * extL;
-                if (diag < s || diag - s >= extL) continue;
-                const uint32_t last = diag - s;
-                off += last;
-                within += last;
                 const T pred = lorenzo_predict_tile<T>(tile + off, N, L, g.ts);
                 if (A.mode == BW_DECODE) {
                     const int qv = static_cast<int>(A.q[g.pos0 + within]);
@@ -383,6 +410,40 @@ SZ_HD void bw_process_block(const BwArgs<T, QT> &A, const uint32_t bi[kMaxDim], 
         if (A.mode == BW_DECODE) A.out[o] = v;
     }
     SZ_WARP_SYNC();
+}
+
+// Diagonal table of a full block (see BwArgs::diag_tab).  tab: B^N entries, start: N * (B - 1) + 2 entries.  Returns
+// false when the offsets do not fit the 16-bit fields (the generic enumeration is used then).
+SZ_HD bool bw_build_diag_table(int N, uint32_t B, uint32_t *tab, uint16_t *start) {
+    uint64_t npts = 1, tile = 1;
+    for (int d = 0; d < N; d++) {
+        npts *= B;
+        tile *= B + kBwPad;
+    }
+    if (npts > 0xffffu || tile > 0xffffu) return false;
+    uint32_t ts[kMaxDim] = {0, 0, 0, 0};
+    uint32_t acc = 1;
+    for (int d = N - 1; d >= 0; d--) {
+        ts[d] = acc;
+        acc *= B + kBwPad;
+    }
+    const uint32_t ndiag = static_cast<uint32_t>(N) * (B - 1) + 1;
+    uint32_t at = 0;
+    for (uint32_t diag = 0; diag < ndiag; diag++) {
+        start[diag] = static_cast<uint16_t>(at);
+        for (uint32_t e = 0; e < npts; e++) {   // row-major order inside a diagonal
+            uint32_t r = e, s = 0, off = 0;
+            for (int d = N - 1; d >= 0; d--) {
+                const uint32_t i = r % B;
+                r /= B;
+                s += i;
+                off += i * ts[d];
+            }
+            if (s == diag) tab[at++] = (off << 16) | e;
+        }
+    }
+    start[ndiag] = static_cast<uint16_t>(at);
+    return true;
 }
 
 // number of block fronts (hyperplanes of constant block-coordinate sum)

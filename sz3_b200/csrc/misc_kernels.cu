@@ -100,11 +100,15 @@ struct Dims4 {
     uint32_t d[4];
 };
 
+// One warp per sampled block: the lanes share the block's (bs / pstride + 1)^N probe points, min / max by shuffles.
+// Every lane starts from the block's first point like the reference's loop does, so a NaN there poisons the result
+// the same way; NaNs elsewhere are skipped by both (all comparisons false).
 template <class T>
 __global__ void __launch_bounds__(128) k_profile_blocks(const T *__restrict__ data, int N, Dims4 dims, uint32_t bs,
                                                         uint32_t pstride, double abs_eb, uint8_t *__restrict__ flags,
                                                         uint64_t nblocks) {
-    const uint64_t b = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t b = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (b >= nblocks) return;
     uint32_t cb[4] = {1, 1, 1, 1}, start[4] = {0, 0, 0, 0};
     uint64_t stride[4] = {0, 0, 0, 0};
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(128) k_profile_blocks(const T *__restrict__ da
         r /= cb[d];
         base += start[d] * stride[d];
     }
-    T mn = data[base], mx = data[base];
+    T mn = data[base], mx = mn;
     const uint32_t np = bs / pstride + 1;  // ii = 0, pstride, ... <= bs
     uint32_t cnt[4] = {1, 1, 1, 1};
     uint32_t total = 1;
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(128) k_profile_blocks(const T *__restrict__ da
         cnt[d] = np;
         total *= np;
     }
-    for (uint32_t it = 0; it < total; it++) {
+    for (uint32_t it = lane; it < total; it += 32) {
         uint32_t rr = it;
         uint64_t off = base;
         for (int d = N - 1; d >= 0; d--) {
@@ -141,7 +145,12 @@ __global__ void __launch_bounds__(128) k_profile_blocks(const T *__restrict__ da
         else if (v > mx)
             mx = v;
     }
-    flags[b] = static_cast<double>(static_cast<T>(mx - mn)) > abs_eb ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+        const T omn = __shfl_xor_sync(0xffffffffu, mn, o), omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        if (omn < mn) mn = omn;
+        if (omx > mx) mx = omx;
+    }
+    if (lane == 0) flags[b] = static_cast<double>(static_cast<T>(mx - mn)) > abs_eb ? 1 : 0;
 }
 
 template <class T>
@@ -150,8 +159,8 @@ void launch_profile_blocks(const T *data, int N, const uint32_t *dims, uint32_t 
     if (nblocks == 0) return;
     Dims4 d4;
     for (int i = 0; i < 4; i++) d4.d[i] = i < N ? dims[i] : 1;
-    k_profile_blocks<T><<<static_cast<unsigned>((nblocks + 127) / 128), 128, 0, st>>>(data, N, d4, block, pstride,
-                                                                                      abs_eb, flags, nblocks);
+    k_profile_blocks<T><<<static_cast<unsigned>((nblocks + 3) / 4), 128, 0, st>>>(data, N, d4, block, pstride, abs_eb, flags,
+                                                                                  nblocks);
 }
 
 template <class T>

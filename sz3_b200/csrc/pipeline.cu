@@ -890,6 +890,26 @@ static uint64_t bw_args_init(BwArgs<T, QT> &A, const sz3b_config &conf, const Bl
     return np;
 }
 
+// diagonal table of a full block (BwArgs::diag_tab), uploaded per call (a few hundred entries)
+template <class T, class QT>
+static void bw_upload_diag_table(Workspace &ws, BwArgs<T, QT> &A) {
+    const int N = A.bs.N;
+    const uint32_t B = A.bs.B;
+    uint64_t npts = 1;
+    for (int d = 0; d < N; d++) npts *= B;
+    if (npts > 0xffffu) return;
+    const uint32_t nstart = static_cast<uint32_t>(N) * (B - 1) + 2;
+    std::vector<uint32_t> tab(npts);
+    std::vector<uint16_t> start(nstart + 1);
+    if (!bw_build_diag_table(N, B, tab.data(), start.data())) return;
+    uint8_t *d = ws.tables.as<uint8_t>(npts * 4 + nstart * 2 + 64);
+    ws.h2d(d, tab.data(), npts * 4);
+    ws.h2d(d + npts * 4, start.data(), nstart * 2);
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // tab / start are locals
+    A.diag_tab = reinterpret_cast<const uint32_t *>(d);
+    A.diag_start = reinterpret_cast<const uint16_t *>(d + npts * 4);
+}
+
 // Lorenzo only (1st, 2nd, or both composed): one exact wavefront pass over all blocks.
 // Lorenzo + regression: a selection guess pass, then windows of consecutive blocks [b_lo, b_hi): exact chain over the
 // guessed selection of the window (continued from the last final block) -> exact wavefront pass over the window that
@@ -907,6 +927,7 @@ static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double
     if (bs.nblocks >= 0xfffffff0ull) fail(SZ3B_E_UNSUPPORTED, "more than 2^32 blocks");
     BwArgs<T, QT> A;
     const uint64_t np = bw_args_init<T, QT>(A, conf, bs, eb);
+    bw_upload_diag_table<T, QT>(ws, A);
     const bool has_reg = conf.regression != 0;
     const int reg_sid = A.nk - 1;   // the regression predictor is always the last of the stack
     T *W = ws.padded.as<T>(np);
@@ -1533,6 +1554,7 @@ static void blockwise_decompress_lorenzo(Workspace &ws, const sz3b_config &conf,
     if (bs.nblocks >= 0xfffffff0ull) fail(SZ3B_E_UNSUPPORTED, "more than 2^32 blocks");
     BwArgs<T, QT> A;
     const uint64_t np = bw_args_init<T, QT>(A, conf, bs, 1.0);
+    bw_upload_diag_table<T, QT>(ws, A);
     const bool has_reg = conf.regression != 0;
     const int reg_sid = A.nk - 1;
     // predictors in stack order: only the regression predictor stores anything

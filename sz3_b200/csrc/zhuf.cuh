@@ -156,26 +156,44 @@ SZ_HD void zhuf_mk_lengths(uint32_t *A, int n) {
     }
 }
 
-struct ZhufBits {   // forward bit writer, LSB first, into a zeroed byte buffer
+struct ZhufBits {   // forward bit writer, LSB first
     uint8_t *p;
-    uint32_t cap, bits;
+    uint32_t cap, nbytes;
+    unsigned long long acc;
+    int nacc;
     bool overflow;
 };
 SZ_HD void zhuf_bits_init(ZhufBits &w, uint8_t *buf, uint32_t cap) {
     w.p = buf;
     w.cap = cap;
-    w.bits = 0;
+    w.nbytes = 0;
+    w.acc = 0;
+    w.nacc = 0;
     w.overflow = false;
-    for (uint32_t i = 0; i < cap; i++) buf[i] = 0;
 }
 SZ_HD void zhuf_bits_put(ZhufBits &w, uint32_t v, int n) {
-    for (int i = 0; i < n; i++, w.bits++) {
-        if ((w.bits >> 3) >= w.cap) {
+    w.acc |= static_cast<unsigned long long>(v & ((1u << n) - 1u)) << w.nacc;
+    w.nacc += n;
+    while (w.nacc >= 8) {
+        if (w.nbytes < w.cap)
+            w.p[w.nbytes++] = static_cast<uint8_t>(w.acc);
+        else
             w.overflow = true;
-            return;
-        }
-        if ((v >> i) & 1u) w.p[w.bits >> 3] |= static_cast<uint8_t>(1u << (w.bits & 7));
+        w.acc >>= 8;
+        w.nacc -= 8;
     }
+}
+// bytes written once the last partial byte is flushed (zero padded)
+SZ_HD uint32_t zhuf_bits_close(ZhufBits &w) {
+    if (w.nacc > 0) {
+        if (w.nbytes < w.cap)
+            w.p[w.nbytes++] = static_cast<uint8_t>(w.acc);
+        else
+            w.overflow = true;
+        w.acc = 0;
+        w.nacc = 0;
+    }
+    return w.nbytes;
 }
 
 // FSE-compressed weights: FSE_Table_Description (normalized counts, accuracy log 6) followed by the two-state backward
@@ -248,8 +266,8 @@ SZ_HD uint32_t zhuf_fse_weights(const uint8_t *w, int n, uint8_t *out, uint32_t 
         }
         if (remaining != 1) return 0;
     }
+    const uint32_t hdr = zhuf_bits_close(hw);
     if (hw.overflow) return 0;
-    const uint32_t hdr = (hw.bits + 7) >> 3;
     // ---- the decoder's table: symbols spread with step (size/2 + size/8 + 3), states numbered per symbol in table
     //      order; the encoder needs the inverse map (symbol, k-th occurrence) -> table index
     uint8_t table_sym[kSize];
@@ -300,59 +318,101 @@ SZ_HD uint32_t zhuf_fse_weights(const uint8_t *w, int n, uint8_t *out, uint32_t 
     zhuf_bits_put(bw, static_cast<uint32_t>(X[1] - kSize), kLog);
     zhuf_bits_put(bw, static_cast<uint32_t>(X[0] - kSize), kLog);
     zhuf_bits_put(bw, 1, 1);
+    const uint32_t body = zhuf_bits_close(bw);
     if (bw.overflow) return 0;
-    return hdr + ((bw.bits + 7) >> 3);
+    return hdr + body;
 }
 
-// Table of one block from its byte histogram.  sorted_sym / sorted_freq: the present symbols in ascending (frequency,
-// symbol) order (n of them) -- produced by the caller (rank sort across the lanes of a warp on the device).
-// work: n words of scratch.
-SZ_HD void zhuf_build_table(const uint8_t *sorted_sym, uint32_t *sorted_freq, int n, uint32_t *work, ZhufBlockInfo &t) {
-    for (int s = 0; s < 256; s++) t.sym[s] = 0;
-    t.desc_len = 0;
-    t.ok = 0;
-    if (n < 2) return;
-    int longest;
-    for (;;) {
-        for (int i = 0; i < n; i++) work[i] = sorted_freq[i];
-        zhuf_mk_lengths(work, n);
-        longest = static_cast<int>(work[0]);
-        if (longest <= kZhufMaxBits) break;
-        // flatten the histogram until the code fits; halving keeps the order, the result stays a complete Huffman code
-        for (int i = 0; i < n; i++) sorted_freq[i] = (sorted_freq[i] + 1) / 2;
-    }
+#if defined(__CUDA_ARCH__)
+#define SZ_CTA_SYNC() __syncthreads()
+#define SZ_SMEM_INC(p) atomicAdd((p), 1u)
+#else
+#define SZ_CTA_SYNC() ((void)0)
+#define SZ_SMEM_INC(p) (++*(p))
+#endif
+
+struct ZhufScratch {   // shared memory of the building CTA
+    uint32_t work[256];
     uint8_t len[256], w[256];
-    for (int s = 0; s < 256; s++) len[s] = 0;
-    for (int i = 0; i < n; i++) len[sorted_sym[i]] = static_cast<uint8_t>(work[i]);
-    int last = 255;
-    while (last >= 0 && len[last] == 0) last--;
-    if (last < 1) return;
-    for (int s = 0; s < last; s++) w[s] = len[s] ? static_cast<uint8_t>(longest + 1 - len[s]) : 0;
-    const int nw = last;   // explicit weights; the last present symbol's weight is implied
-    const uint32_t fse = zhuf_fse_weights(w, nw, t.desc + 1, kZhufDescCap - 1);
-    if (fse > 0 && fse < 128) {
-        t.desc[0] = static_cast<uint8_t>(fse);
-        t.desc_len = fse + 1;
-    } else if (nw <= 128) {   // direct representation: 4 bits per weight
-        t.desc[0] = static_cast<uint8_t>(127 + nw);
-        for (int i = 0; i < nw; i += 2) t.desc[1 + i / 2] = static_cast<uint8_t>((w[i] << 4) | (i + 1 < nw ? w[i + 1] : 0));
-        t.desc_len = static_cast<uint32_t>(1 + (nw + 1) / 2);
-    } else {
-        return;
-    }
-    // canonical codes: longest codes first, symbols ascending inside a length
     uint32_t per_rank[kZhufMaxBits + 2], val[kZhufMaxBits + 2];
-    for (int b = 0; b < kZhufMaxBits + 2; b++) per_rank[b] = val[b] = 0;
-    for (int s = 0; s < 256; s++)
-        if (len[s]) per_rank[len[s]]++;
-    uint32_t min = 0;
-    for (int b = longest; b >= 1; b--) {
-        val[b] = min;
-        min = (min + per_rank[b]) >> 1;
+    int longest, last, desc_ok;
+};
+
+// Table of one block from its byte histogram, by the tid-th of nt threads of one CTA (all of them call this; the
+// tests' sequential twin runs it with nt = 1).  sorted_sym / sorted_freq: the present symbols in ascending
+// (frequency, symbol) order, n of them.  The two inherently serial pieces -- the Moffat-Katajainen length computation
+// and the FSE state chain over the weights -- run on thread 0; the per-symbol loops are spread over the CTA.
+SZ_HD void zhuf_build_table(const uint8_t *sorted_sym, uint32_t *sorted_freq, int n, ZhufScratch &S, ZhufBlockInfo &t, int tid,
+                            int nt) {
+    for (int s = tid; s < 256; s += nt) {
+        t.sym[s] = 0;
+        S.len[s] = 0;
     }
-    for (int s = 0; s < 256; s++)
-        if (len[s]) t.sym[s] = (static_cast<uint32_t>(len[s]) << 16) | val[len[s]]++;
-    t.ok = 1;
+    for (int b = tid; b < kZhufMaxBits + 2; b += nt) S.per_rank[b] = 0;
+    if (tid == 0) {
+        t.desc_len = 0;
+        t.ok = 0;
+        S.desc_ok = 0;
+    }
+    SZ_CTA_SYNC();
+    if (n < 2) return;
+    if (tid == 0) {
+        for (;;) {
+            for (int i = 0; i < n; i++) S.work[i] = sorted_freq[i];
+            zhuf_mk_lengths(S.work, n);
+            S.longest = static_cast<int>(S.work[0]);
+            if (S.longest <= kZhufMaxBits) break;
+            // flatten the histogram until the code fits; halving keeps the order, the result stays a complete code
+            for (int i = 0; i < n; i++) sorted_freq[i] = (sorted_freq[i] + 1) / 2;
+        }
+    }
+    SZ_CTA_SYNC();
+    for (int i = tid; i < n; i += nt) S.len[sorted_sym[i]] = static_cast<uint8_t>(S.work[i]);
+    SZ_CTA_SYNC();
+    if (tid == 0) {
+        int last = 255;
+        while (last >= 0 && S.len[last] == 0) last--;
+        S.last = last;
+    }
+    SZ_CTA_SYNC();
+    const int last = S.last, longest = S.longest;
+    if (last < 1) return;
+    for (int s = tid; s < last; s += nt) S.w[s] = S.len[s] ? static_cast<uint8_t>(longest + 1 - S.len[s]) : 0;
+    for (int s = tid; s < 256; s += nt)
+        if (S.len[s]) SZ_SMEM_INC(&S.per_rank[S.len[s]]);
+    SZ_CTA_SYNC();
+    if (tid == 0) {
+        const int nw = last;   // explicit weights
+        const uint32_t fse = zhuf_fse_weights(S.w, nw, t.desc + 1, kZhufDescCap - 1);
+        if (fse > 0 && fse < 128) {
+            t.desc[0] = static_cast<uint8_t>(fse);
+            t.desc_len = fse + 1;
+            S.desc_ok = 1;
+        } else if (nw <= 128) {   // direct representation: 4 bits per weight
+            t.desc[0] = static_cast<uint8_t>(127 + nw);
+            for (int i = 0; i < nw; i += 2)
+                t.desc[1 + i / 2] = static_cast<uint8_t>((S.w[i] << 4) | (i + 1 < nw ? S.w[i + 1] : 0));
+            t.desc_len = static_cast<uint32_t>(1 + (nw + 1) / 2);
+            S.desc_ok = 1;
+        }
+        // canonical codes: longest codes first, symbols ascending inside a length
+        uint32_t min = 0;
+        for (int b = longest; b >= 1; b--) {
+            S.val[b] = min;
+            min = (min + S.per_rank[b]) >> 1;
+        }
+    }
+    SZ_CTA_SYNC();
+    if (!S.desc_ok) return;
+    for (int s = tid; s < 256; s += nt) {
+        const uint32_t l = S.len[s];
+        if (!l) continue;
+        uint32_t before = 0;   // symbols of the same length below s
+        for (int j = 0; j < s; j++) before += S.len[j] == l ? 1u : 0u;
+        t.sym[s] = (l << 16) | (S.val[l] + before);
+    }
+    if (tid == 0) t.ok = 1;
+    SZ_CTA_SYNC();
 }
 
 }  // namespace sz3b

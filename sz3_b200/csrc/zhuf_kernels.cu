@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_build(const uint8_t *__re
                                                              ZhufBlockInfo *__restrict__ infos) {
     __shared__ uint32_t hist[256];
     __shared__ uint8_t ss[256];
-    __shared__ uint32_t sf[256], work[256];
+    __shared__ uint32_t sf[256];
+    __shared__ ZhufScratch scratch;
     __shared__ ZhufBlockInfo info;
     __shared__ unsigned long long bits[4];
     const uint64_t g = blockIdx.x;
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_build(const uint8_t *__re
         sf[rank] = mine;
     }
     const int n = __syncthreads_count(mine != 0);
-    if (tid == 0) zhuf_build_table(ss, sf, n, work, info);
+    zhuf_build_table(ss, sf, n, scratch, info, tid, kZhufThreads);
     __syncthreads();
     // bytes of the four streams under this code
     const uint32_t seg = (bl + 3) / 4;
@@ -177,12 +178,29 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_encode(const uint8_t *__r
     sym_s[tid] = bi.sym[tid];
     for (uint32_t i = tid; i < (sb + 3) / 4 + 1 && i < kZhufBufWords; i += kZhufThreads) buf[i] = 0;
     __syncthreads();
-    // chunk of this thread, bit count
+    // chunk of this thread, bit count.  Full streams (32768 symbols, 128 per thread, 16-byte aligned) keep their bytes
+    // in registers between the two passes.
     const uint32_t per = (n + kZhufThreads - 1) / kZhufThreads;
     const uint32_t c0 = tid * per < n ? tid * per : n, c1 = c0 + per < n ? c0 + per : n;
     const uint8_t *sp = src + a;
+    const bool vec = per == 128 && n == 128 * kZhufThreads && ((a & 15) == 0);
+    uint4 v[8];
     uint32_t mybits = 0;
-    for (uint32_t i = c0; i < c1; i++) mybits += sym_s[sp[i]] >> 16;
+    if (vec) {
+        const uint4 *pv = reinterpret_cast<const uint4 *>(sp + c0);
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = pv[k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t wv[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                mybits += (sym_s[wv[j] & 0xff] >> 16) + (sym_s[(wv[j] >> 8) & 0xff] >> 16) + (sym_s[(wv[j] >> 16) & 0xff] >> 16) +
+                          (sym_s[wv[j] >> 24] >> 16);
+        }
+    } else {
+        for (uint32_t i = c0; i < c1; i++) mybits += sym_s[sp[i]] >> 16;
+    }
     // bits written before this chunk = bits of all LATER chunks (the last symbol goes first)
     uint32_t x = mybits;
     const int lane = tid & 31, wid = tid >> 5;
@@ -198,20 +216,55 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_encode(const uint8_t *__r
         if (w < wid) before += warp_sum[w];
         total += warp_sum[w];
     }
-    uint32_t o = total - (before + x);
-    for (uint32_t i = c1; i-- > c0;) {
-        const uint32_t e = sym_s[sp[i]];
-        const uint32_t nb = e >> 16, code = e & 0xffffu;
-        const uint32_t w = o >> 5, sh = o & 31;
-        atomicOr(&buf[w], code << sh);
-        if (sh + nb > 32) atomicOr(&buf[w + 1], code >> (32 - sh));
-        o += nb;
+    // Codes are gathered in a 64-bit register and leave as whole words.  The words strictly inside the chunk's bit
+    // range belong to this thread alone (plain stores); the first and the last one are shared with the neighbours.
+    const uint32_t o0 = total - (before + x);
+    unsigned long long acc = 0;
+    uint32_t nacc = o0 & 31, w = o0 >> 5;
+    bool first = true;
+    auto emit = [&](uint32_t byte) {
+        const uint32_t e = sym_s[byte];
+        acc |= static_cast<unsigned long long>(e & 0xffffu) << nacc;
+        nacc += e >> 16;
+        if (nacc >= 32) {
+            if (first)
+                atomicOr(&buf[w], static_cast<uint32_t>(acc));
+            else
+                buf[w] = static_cast<uint32_t>(acc);
+            first = false;
+            acc >>= 32;
+            nacc -= 32;
+            w++;
+        }
+    };
+    if (vec) {
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            const uint32_t wv[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int j = 3; j >= 0; j--) {
+                emit(wv[j] >> 24);
+                emit((wv[j] >> 16) & 0xff);
+                emit((wv[j] >> 8) & 0xff);
+                emit(wv[j] & 0xff);
+            }
+        }
+    } else {
+        for (uint32_t i = c1; i-- > c0;) emit(sp[i]);
     }
+    if (nacc && acc) atomicOr(&buf[w], static_cast<uint32_t>(acc));
     if (tid == 0) atomicOr(&buf[total >> 5], 1u << (total & 31));   // closing bit
     __syncthreads();
+    // copy out: bytes up to the first 4-byte boundary of the destination, aligned words, tail bytes
     const uint8_t *bb = reinterpret_cast<const uint8_t *>(buf);
     uint8_t *dst = out + p;
-    for (uint32_t i = tid; i < sb; i += kZhufThreads) dst[i] = bb[i];
+    const uint32_t head = static_cast<uint32_t>((4 - (p & 3)) & 3) < sb ? static_cast<uint32_t>((4 - (p & 3)) & 3) : sb;
+    if (tid < static_cast<int>(head)) dst[tid] = bb[tid];
+    const uint32_t nwords = (sb - head) / 4;
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+    for (uint32_t i = tid; i < nwords; i += kZhufThreads)
+        dw[i] = head ? __funnelshift_r(buf[i], buf[i + 1], 8 * head) : buf[i];
+    for (uint32_t i = head + nwords * 4 + tid; i < sb; i += kZhufThreads) dst[i] = bb[i];
 }
 
 // Compresses src[0, len) (device) into out (device, zhuf_bound(len) bytes); *total (device) receives the size.

@@ -18,7 +18,8 @@ extern "C" long long zhuf_emul_compress(const uint8_t *src, size_t len, uint8_t 
         uint32_t hist[256] = {0};
         for (uint32_t i = 0; i < bl; i++) hist[src[g * kZhufBlock + i]]++;
         uint8_t ss[256];
-        uint32_t sf[256], work[256];
+        uint32_t sf[256];
+        ZhufScratch scratch;
         int n = 0;
         for (int s = 0; s < 256; s++) {   // rank sort, as the warp does it
             if (!hist[s]) continue;
@@ -29,7 +30,7 @@ extern "C" long long zhuf_emul_compress(const uint8_t *src, size_t len, uint8_t 
             sf[rank] = hist[s];
             n++;
         }
-        zhuf_build_table(ss, sf, n, work, info[g]);
+        zhuf_build_table(ss, sf, n, scratch, info[g], 0, 1);
         for (int s = 0; s < 4; s++) {
             uint64_t a, b, bits = 0;
             zhuf_stream_range(len, g, s, &a, &b);
