@@ -59,7 +59,7 @@ template <class T, class QT>
 struct BwArgs;
 template <class T>
 void launch_bw_pad(const T *data, const BlockShape &bs, const uint64_t *pstride, T *W, uint64_t b_lo, uint64_t b_hi,
-                   cudaStream_t st);
+                   cudaStream_t st, uint32_t nbatch = 1, uint64_t w_bstride = 0);
 template <class T, class QT>
 const char *launch_bw_serial(const BwArgs<T, QT> &A, uint64_t b_lo, uint64_t b_hi, const T *chain_init,
                              unsigned long long nsel0, unsigned long long *nsel_out, cudaStream_t st);

@@ -18,7 +18,9 @@ namespace sz3b {
 template <class T>
 __global__ void __launch_bounds__(256) k_bw_pad(const T *__restrict__ data, BlockShape bs, uint64_t ps0, uint64_t ps1,
                                                 uint64_t ps2, uint64_t ps3, T *__restrict__ W, uint64_t b_lo, uint64_t b_hi, uint64_t e_lo,
-                                                uint64_t e_hi) {
+                                                uint64_t e_hi, uint64_t w_bstride) {
+    data += static_cast<uint64_t>(blockIdx.y) * bs.num;   // batch member (the tuner's sampled blocks)
+    W += static_cast<uint64_t>(blockIdx.y) * w_bstride;
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     const uint64_t ps[kMaxDim] = {ps0, ps1, ps2, ps3};
     for (uint64_t i = e_lo + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < e_hi; i += stride) {
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(32) k_bw_serial(BwArgs<T, QT> A, uint64_t b_lo
             bi[d] = static_cast<uint32_t>(r % A.bs.nb[d]);
             r /= A.bs.nb[d];
         }
-        bw_process_block<T, QT>(A, bi, tile, est, threadIdx.x, 32, &st);
+        bw_process_block<T, QT>(A, bi, tile, est, threadIdx.x, blockDim.x, &st);
         __threadfence_block();
         __syncwarp();
     }
@@ -73,6 +75,13 @@ __global__ void __launch_bounds__(32) k_bw_front(BwArgs<T, QT> A, uint32_t f0, u
     T *tile = reinterpret_cast<T *>(bw_smem);
     T *est = tile + tile_cap;
     const int N = A.bs.N;
+    if (blockIdx.y) {   // batch member: same shape, own working array / index range / selection
+        A.W += static_cast<uint64_t>(blockIdx.y) * A.w_bstride;
+        A.q += static_cast<uint64_t>(blockIdx.y) * A.q_bstride;
+        A.unpred_tmp += static_cast<uint64_t>(blockIdx.y) * A.q_bstride;
+        if (A.sel_out) A.sel_out += static_cast<uint64_t>(blockIdx.y) * A.sel_bstride;
+        if (A.sel_in) A.sel_in += static_cast<uint64_t>(blockIdx.y) * A.sel_bstride;
+    }
     uint32_t bi[kMaxDim] = {0, 0, 0, 0};
     const uint32_t lead = blockIdx.x + lead_lo;
     uint32_t r = lead, s = 0;
@@ -89,7 +98,7 @@ __global__ void __launch_bounds__(32) k_bw_front(BwArgs<T, QT> A, uint32_t f0, u
         const uint64_t b = row_base + last;
         if (b < A.b_lo || b >= A.b_hi) continue;
         bi[N - 1] = last;
-        bw_process_block<T, QT>(A, bi, tile, est, threadIdx.x, 32);
+        bw_process_block<T, QT>(A, bi, tile, est, threadIdx.x, blockDim.x);
         __threadfence_block();
         __syncwarp();
     }
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(256) k_widen_u8(const uint8_t *__restrict__ in
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T>
 void launch_bw_pad(const T *data, const BlockShape &bs, const uint64_t *pstride, T *W, uint64_t b_lo, uint64_t b_hi,
-                   cudaStream_t st) {
+                   cudaStream_t st, uint32_t nbatch, uint64_t w_bstride) {
     if (b_lo >= b_hi) return;
     // elements of the outermost-dimension slabs the block range touches
     const uint64_t per_plane = bs.nblocks / bs.nb[0];
@@ -172,8 +181,8 @@ void launch_bw_pad(const T *data, const BlockShape &bs, const uint64_t *pstride,
     const uint64_t e_lo = i_lo * bs.B * bs.stride[0], e_hi = x_hi * bs.stride[0];
     uint64_t blocks = (e_hi - e_lo + 255) / 256;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    k_bw_pad<T><<<static_cast<unsigned>(blocks), 256, 0, st>>>(data, bs, pstride[0], pstride[1], pstride[2], pstride[3], W, b_lo,
-                                                               b_hi, e_lo, e_hi);
+    k_bw_pad<T><<<dim3(static_cast<unsigned>(blocks), nbatch), 256, 0, st>>>(data, bs, pstride[0], pstride[1], pstride[2],
+                                                                             pstride[3], W, b_lo, b_hi, e_lo, e_hi, w_bstride);
 }
 
 static size_t bw_tile_cap(const BlockShape &bs) {
@@ -193,7 +202,8 @@ const char *launch_bw_serial(const BwArgs<T, QT> &A, uint64_t b_lo, uint64_t b_h
             return "cannot raise the dynamic shared memory limit";
         attr_set = 200 * 1024;
     }
-    k_bw_serial<T, QT><<<1, 32, smem, st>>>(A, b_lo, b_hi, chain_init, nsel0, nsel_out, static_cast<uint32_t>(bw_tile_cap(A.bs)));
+    k_bw_serial<T, QT><<<1, A.bs.N == 1 ? 1 : 32, smem, st>>>(A, b_lo, b_hi, chain_init, nsel0, nsel_out,
+                                                                 static_cast<uint32_t>(bw_tile_cap(A.bs)));
     return nullptr;
 }
 
@@ -237,12 +247,15 @@ const char *launch_bw_fronts(const BwArgs<T, QT> &A, cudaStream_t st, int *launc
         }
     }
     const unsigned grid = static_cast<unsigned>(lead_hi - lead_lo + 1);
+    const unsigned nbatch = A.nbatch ? A.nbatch : 1u;
     if (N == 1) {
-        k_bw_front<T, QT><<<1, 32, smem, st>>>(A, f_min, f_max + 1, 0, static_cast<uint32_t>(tile_cap));
+        // the 1-D recurrence is serial point by point: one thread walks the blocks (a warp would only add barriers)
+        k_bw_front<T, QT><<<dim3(1, nbatch), 1, smem, st>>>(A, f_min, f_max + 1, 0, static_cast<uint32_t>(tile_cap));
         *launches += 1;
     } else {
         for (uint32_t f = f_min; f <= f_max; f++)
-            k_bw_front<T, QT><<<grid, 32, smem, st>>>(A, f, f + 1, static_cast<uint32_t>(lead_lo), static_cast<uint32_t>(tile_cap));
+            k_bw_front<T, QT><<<dim3(grid, nbatch), 32, smem, st>>>(A, f, f + 1, static_cast<uint32_t>(lead_lo),
+                                                                    static_cast<uint32_t>(tile_cap));
         *launches += static_cast<int>(f_max - f_min + 1);
     }
     return nullptr;
@@ -275,7 +288,7 @@ void launch_widen_u8(const uint8_t *in, uint64_t n, int32_t *out, cudaStream_t s
 
 #define SZ3B_INST_LZ(T)                                                                                              \
     template void launch_bw_pad<T>(const T *, const BlockShape &, const uint64_t *, T *, uint64_t, uint64_t,         \
-                                   cudaStream_t);                                                                    \
+                                   cudaStream_t, uint32_t, uint64_t);                                                \
     template const char *launch_bw_serial<T, uint16_t>(const BwArgs<T, uint16_t> &, uint64_t, uint64_t, const T *,   \
                                                        unsigned long long, unsigned long long *, cudaStream_t);      \
     template const char *launch_bw_serial<T, uint32_t>(const BwArgs<T, uint32_t> &, uint64_t, uint64_t, const T *,   \

@@ -56,6 +56,9 @@ struct BwArgs {
     QT *q;                       // quantization indices, block-major (written by BW_EXACT, read by BW_DECODE)
     T *unpred_tmp;               // position-indexed unpredictable values (same direction as q)
     uint64_t b_lo, b_hi;         // window of row-major block indices processed by a front launch
+    // batch of independent arrays of identical shape (the tuner's sampled blocks): strides between batch members
+    uint32_t nbatch;
+    uint64_t w_bstride, q_bstride, sel_bstride;
     // points of a FULL block (every extent == B) ordered by index sum: entry = tile offset (relative to the block's
     // first point) << 16 | row-major rank inside the block; diag_start[d] .. diag_start[d + 1] = diagonal d
     const uint32_t *diag_tab;

@@ -576,10 +576,19 @@ static void set_default_anchor(sz3b_config &conf) {
 // ALGO_LORENZO_REG); all trial compressions run through the same GPU kernels on the sampled cubes.
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T>
+static size_t quantizer_header(double eb, int radius, uint64_t n_unpred, uint8_t *out);
+
+// lorenzo_compress_test (SZAlgoInterp.hpp:78-119), defined with the Lorenzo stack further down
+template <class T>
+static double lorenzo_trial(Workspace &ws, const sz3b_config &lc, const T *d_cubes, uint32_t ncubes, size_t per_block,
+                            uint8_t *out, size_t cap);
+
+template <class T>
 static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
     const int N = conf.N;
     const uint64_t num = config_num(conf);
     set_default_anchor(conf);
+    const sz3b_config conf_entry = conf;   // `Config lorenzo_config = conf;` (:182) is taken before the interp tuning
     const double sampleRate = 0.005;
     static const size_t sbs_def[4] = {4096, 128, 32, 16};
     size_t sbs = sbs_def[N - 1];
@@ -775,13 +784,39 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
                 conf.interpBeta = betas[i];
             }
     }
-    if (N == 1 && best_interp < 50) {
-        // the reference additionally tries Lorenzo(1st+2nd order) on 1-D data (:227-241); that predictor stack is
-        // not on the GPU path yet, so say so instead of silently choosing differently.
-        fail(SZ3B_E_UNSUPPORTED, "1-D ALGO_INTERP_LORENZO needs the Lorenzo trial (not on the GPU path yet); use ALGO_INTERP");
+    sz3b_config lc = conf_entry;
+    if (N == 1 && best_interp < 50) {   // only test lorenzo for 1D (:226-242)
+        lc.cmprAlgo = SZ3B_ALGO_LORENZO_REG;
+        uint64_t cd[4] = {sbs + 1, 0, 0, 0};
+        config_set_dims(lc, N, cd);
+        lc.lorenzo = 1;
+        lc.lorenzo2 = 1;
+        lc.regression = 0;
+        lc.regression2 = 0;
+        lc.openmp = 0;
+        lc.blockSize = 5;
+        ws.stage_prefix = "tune_";
+        best_lorenzo = lorenzo_trial<T>(ws, lc, d_cubes, ncubes, per_block, trial_out.data(), trial_cap);
+        ws.stage_prefix.clear();
     }
-    (void)best_lorenzo;
-    conf.cmprAlgo = SZ3B_ALGO_INTERP;
+    const bool use_interp = !(best_lorenzo >= best_interp * 1.1 && best_lorenzo < 50 && best_interp < 50);   // :244-245
+    if (use_interp) {
+        conf.cmprAlgo = SZ3B_ALGO_INTERP;
+        return;
+    }
+    if (conf.relErrorBound < 1.01e-6 && best_lorenzo > 5 && lc.quantbinCnt != 16384) {   // :268-277
+        const int quant_num = lc.quantbinCnt;
+        lc.quantbinCnt = 16384;
+        ws.stage_prefix = "tune_";
+        const double ratio = lorenzo_trial<T>(ws, lc, d_cubes, ncubes, per_block, trial_out.data(), trial_cap);
+        ws.stage_prefix.clear();
+        if (ratio > best_lorenzo * 1.02)
+            best_lorenzo = ratio;
+        else
+            lc.quantbinCnt = quant_num;
+    }
+    config_set_dims(lc, N, conf.dims);   // :278 -- resets blockSize to the default of the rank
+    conf = lc;                           // :279; SZ_compress_LorenzoReg follows in the dispatcher
 }
 
 template <class T>
@@ -908,6 +943,80 @@ static void bw_upload_diag_table(Workspace &ws, BwArgs<T, QT> &A) {
     SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // tab / start are locals
     A.diag_tab = reinterpret_cast<const uint32_t *>(d);
     A.diag_start = reinterpret_cast<const uint16_t *>(d + npts * 4);
+}
+
+// lorenzo_compress_test (SZAlgoInterp.hpp:78-119): every sampled block through BlockwiseDecomposition with the composed
+// Lorenzo(1st) + Lorenzo(2nd) predictor (one decomposition object: the selections and the unpredictable values of all
+// sampled blocks end up in one save()), the merged index stream through Huffman and zstd; returns the ratio.
+template <class T, class QT>
+static double lorenzo_trial_t(Workspace &ws, const sz3b_config &lc, const T *d_cubes, uint32_t ncubes, size_t per_block,
+                              uint8_t *out, size_t cap) {
+    sz3b_config c2 = lc;
+    c2.lorenzo = 1;
+    c2.lorenzo2 = 1;
+    c2.regression = 0;
+    BlockShape bs;
+    block_shape_init(bs, c2.N, c2.dims, static_cast<uint32_t>(c2.blockSize));
+    if (bs.num != per_block) fail(SZ3B_E_RUNTIME, "tuner: sampled block shape mismatch");
+    BwArgs<T, QT> A;
+    const uint64_t np = bw_args_init<T, QT>(A, c2, bs, c2.absErrorBound);
+    bw_upload_diag_table<T, QT>(ws, A);
+    const int radius = c2.quantbinCnt / 2, nbins = 2 * radius;
+    const uint64_t n = static_cast<uint64_t>(per_block) * ncubes;
+    QT *d_q = ws.cube_q.as<QT>(n);
+    T *d_un = ws.cube_unpred.as<T>(n);
+    unsigned long long *d_hist = ws.hist2.as<unsigned long long>(nbins);
+    T *W = ws.padded.as<T>(np * ncubes);
+    uint8_t *d_sel = ws.bsel.as<uint8_t>(bs.nblocks * ncubes);
+    A.W = W;
+    A.q = d_q;
+    A.unpred_tmp = d_un;
+    A.sel_out = d_sel;
+    A.nbatch = ncubes;
+    A.w_bstride = np;
+    A.q_bstride = per_block;
+    A.sel_bstride = bs.nblocks;
+    A.mode = BW_EXACT;
+    int launches = 0;
+    size_t h = ws.stage_begin("predict_quantize");
+    SZ3B_CUDA(cudaMemsetAsync(W, 0, np * ncubes * sizeof(T), ws.st));
+    launch_bw_pad<T>(d_cubes, bs, A.pstride, W, 0, bs.nblocks, ws.st, ncubes, np);
+    if (const char *e = launch_bw_fronts<T, QT>(A, ws.st, &launches)) fail(SZ3B_E_UNSUPPORTED, e);
+    SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
+    launch_histogram<QT>(d_q, n, 0, nbins, radius, d_hist, ws.st);
+    ws.stage_end(h, launches + 2);
+    SZ3B_CUDA(cudaGetLastError());
+    std::vector<uint8_t> hdr;
+    {
+        const uint64_t nsel = bs.nblocks * ncubes;
+        uint8_t tmp[8];
+        uint8_t *p = tmp;
+        put<uint64_t>(p, nsel);
+        hdr.insert(hdr.end(), tmp, p);
+        int32_t *d_sel32 = ws.side_q.as<int32_t>(nsel);
+        launch_widen_u8(d_sel, nsel, d_sel32, ws.st);
+        std::vector<uint8_t> side;
+        huffman_encode_device(ws, d_sel32, nsel, side, nullptr);
+        hdr.insert(hdr.end(), side.begin(), side.end());
+    }
+    HuffmanBook book;
+    EncodeLayout lay;
+    encode_indices<QT, T>(ws, d_q, n, d_hist, nbins, 0, true, d_un, book, lay);
+    uint8_t qh[32];
+    const size_t qh_len = quantizer_header<T>(c2.absErrorBound, radius, lay.n_unpred, qh);
+    hdr.insert(hdr.end(), qh, qh + qh_len);
+    uint8_t *buf = nullptr;
+    ArrivalGate gate;
+    const size_t len = assemble_stream<T>(ws, hdr.data(), hdr.size(), lay, book, n, ws.stage2, &buf, gate);
+    const size_t size = zstd_stage(ws, buf, len, out, cap, 1, &gate);
+    return static_cast<double>(per_block) * ncubes * sizeof(T) * 1.0 / size;
+}
+
+template <class T>
+static double lorenzo_trial(Workspace &ws, const sz3b_config &lc, const T *d_cubes, uint32_t ncubes, size_t per_block,
+                            uint8_t *out, size_t cap) {
+    if (lc.quantbinCnt / 2 <= 32768) return lorenzo_trial_t<T, uint16_t>(ws, lc, d_cubes, ncubes, per_block, out, cap);
+    return lorenzo_trial_t<T, uint32_t>(ws, lc, d_cubes, ncubes, per_block, out, cap);
 }
 
 // Lorenzo only (1st, 2nd, or both composed): one exact wavefront pass over all blocks.

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import (ALGO_INTERP, ALGO_INTERP_LORENZO, ALGO_LOSSLESS, EB_ABS, EB_PSNR, EB_REL, Config, dtype_code, field_g3,
+from common import (field_g1, ALGO_INTERP, ALGO_INTERP_LORENZO, ALGO_LOSSLESS, EB_ABS, EB_PSNR, EB_REL, Config, dtype_code, field_g3,
                     field_g4, field_nd, make_config, product_lib, ref_lib)
 
 pytestmark = pytest.mark.gpu
@@ -155,3 +155,26 @@ def test_lossless_policy_adaptive_vs_full():
     r_ref, r0, r1, r2 = (data.nbytes / x.size for x in (theirs, out[0], out[1], out[2]))
     assert abs(r0 - r_ref) / r_ref < 0.01 and abs(r1 - r_ref) / r_ref < 0.01 and abs(r2 - r_ref) / r_ref < 0.01, (r_ref, r0, r1, r2)
     assert out[1].size >= out[0].size
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,n,eb", [("g1", 1 << 20, 1e-4), ("g1", 300000, 1e-3), ("noisy", 1 << 18, 1e-3), ("walk", 200000, 1e-2),
+                                       ("g1", 20000, 1e-4)])
+def test_one_dimensional_default_algorithm(kind, n, eb):
+    """1-D ALGO_INTERP_LORENZO (BASELINE.json config #1 is the 2^20 case): the tuner also tries the composed
+    Lorenzo(1st + 2nd order) stack on the sampled blocks (SZAlgoInterp.hpp:226-282) and may hand the whole array to
+    SZ_compress_LorenzoReg; either way the stream must be the reference's, byte for byte."""
+    rng = np.random.default_rng(5)
+    if kind == "g1":
+        data = field_g1(n)
+    elif kind == "noisy":
+        data = (np.sin(np.arange(n) / 50.0) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    else:
+        data = np.cumsum(rng.standard_normal(n)).astype(np.float32)
+    conf = make_config(data.shape, cmprAlgo=ALGO_INTERP_LORENZO, absErrorBound=eb)
+    ours, used = gpu_compress(data, conf)
+    theirs = ref_compress(data, conf)
+    dec, dconf = ref_decompress(ours, data)
+    assert used.cmprAlgo == dconf.cmprAlgo
+    assert ours.size == theirs.size and np.array_equal(ours, theirs), (ours.size, theirs.size, used.cmprAlgo)
+    assert np.max(np.abs(dec.astype(np.float64) - data.astype(np.float64))) <= eb
