@@ -196,43 +196,48 @@ SZ_HD uint32_t zhuf_bits_close(ZhufBits &w) {
     return w.nbytes;
 }
 
+struct ZhufFseScratch {   // tables of the weight coder (shared memory on the device: one thread uses them)
+    int count[16], norm[16];
+    int delta_nb[16], delta_find[16];   // FSE symbol transforms: nbBits = (state + delta_nb) >> 16, next = tab[(state >> nbBits) + delta_find]
+    uint8_t table_sym[64], state_tab[64];
+};
+
 // FSE-compressed weights: FSE_Table_Description (normalized counts, accuracy log 6) followed by the two-state backward
-// bitstream.  Returns the number of bytes written, 0 when this representation is not possible.
-SZ_HD uint32_t zhuf_fse_weights(const uint8_t *w, int n, uint8_t *out, uint32_t cap) {
+// bitstream.  F.count[] holds the histogram of the n weights on entry.  Returns the bytes written, 0 when this
+// representation is not possible.
+SZ_HD uint32_t zhuf_fse_weights(const uint8_t *w, int n, ZhufFseScratch &F, uint8_t *out, uint32_t cap) {
     constexpr int kLog = 6, kSize = 1 << kLog;
     if (n < 2) return 0;
-    int count[16], norm[16];
-    for (int s = 0; s < 16; s++) count[s] = norm[s] = 0;
     int max_sym = 0;
-    for (int i = 0; i < n; i++) {
-        count[w[i]]++;
-        max_sym = w[i] > max_sym ? w[i] : max_sym;
+    for (int s = 0; s < 16; s++) {
+        F.norm[s] = 0;
+        if (F.count[s]) max_sym = s;
     }
     // normalized counts: every present symbol at least 1, total kSize, no symbol owning the whole table
     int total = 0, present = 0;
     for (int s = 0; s <= max_sym; s++)
-        if (count[s]) {
-            const int v = (count[s] * kSize + n / 2) / n;
-            norm[s] = v < 1 ? 1 : v;
-            total += norm[s];
+        if (F.count[s]) {
+            const int v = (F.count[s] * kSize + n / 2) / n;
+            F.norm[s] = v < 1 ? 1 : v;
+            total += F.norm[s];
             present++;
         }
     if (present < 2) return 0;   // one repeated weight has no FSE form
     while (total != kSize) {
         int best = -1;
         for (int s = 0; s <= max_sym; s++)
-            if (norm[s] > (total > kSize ? 1 : 0) && (best < 0 || norm[s] > norm[best])) best = s;
+            if (F.norm[s] > (total > kSize ? 1 : 0) && (best < 0 || F.norm[s] > F.norm[best])) best = s;
         if (best < 0) return 0;
         if (total > kSize) {
-            norm[best]--;
+            F.norm[best]--;
             total--;
         } else {
-            norm[best]++;
+            F.norm[best]++;
             total++;
         }
     }
     for (int s = 0; s <= max_sym; s++)
-        if (norm[s] >= kSize) return 0;
+        if (F.norm[s] >= kSize) return 0;
     // ---- FSE_Table_Description
     ZhufBits hw;
     zhuf_bits_init(hw, out, cap);
@@ -241,7 +246,7 @@ SZ_HD uint32_t zhuf_fse_weights(const uint8_t *w, int n, uint8_t *out, uint32_t 
         int remaining = kSize + 1, threshold = kSize, nbits = kLog + 1;
         int s = 0;
         while (remaining > 1 && s <= max_sym) {
-            const int c = norm[s++];
+            const int c = F.norm[s++];
             const int max = (2 * threshold - 1) - remaining;
             remaining -= c;
             int v = c + 1;
@@ -249,7 +254,7 @@ SZ_HD uint32_t zhuf_fse_weights(const uint8_t *w, int n, uint8_t *out, uint32_t 
             zhuf_bits_put(hw, static_cast<uint32_t>(v), nbits - (v < max ? 1 : 0));
             if (c == 0) {   // further zero-probability symbols: 2-bit repeat codes, 3 = "three more and continue"
                 int run = 0;
-                while (s <= max_sym && norm[s] == 0) {
+                while (s <= max_sym && F.norm[s] == 0) {
                     run++;
                     s++;
                 }
@@ -268,55 +273,65 @@ SZ_HD uint32_t zhuf_fse_weights(const uint8_t *w, int n, uint8_t *out, uint32_t 
     }
     const uint32_t hdr = zhuf_bits_close(hw);
     if (hw.overflow) return 0;
-    // ---- the decoder's table: symbols spread with step (size/2 + size/8 + 3), states numbered per symbol in table
-    //      order; the encoder needs the inverse map (symbol, k-th occurrence) -> table index
-    uint8_t table_sym[kSize];
+    // ---- the decoder's table: symbols spread with step (size/2 + size/8 + 3); a symbol's k-th cell in table order is
+    //      its sub-state k (decoder: nextState = count + k).  The encoder needs the inverse: state_tab holds the table
+    //      indices grouped by symbol in that order, delta_find[s] = (start of the group) - count, so that the cell for
+    //      sub-state (state >> nbBits) is state_tab[(state >> nbBits) + delta_find[s]].
     {
         const int step = (kSize >> 1) + (kSize >> 3) + 3;
         int pos = 0;
         for (int s = 0; s <= max_sym; s++)
-            for (int i = 0; i < norm[s]; i++) {
-                table_sym[pos] = static_cast<uint8_t>(s);
+            for (int i = 0; i < F.norm[s]; i++) {
+                F.table_sym[pos] = static_cast<uint8_t>(s);
                 pos = (pos + step) & (kSize - 1);
             }
         if (pos != 0) return 0;
-    }
-    uint8_t first_of[16];    // table index range of a symbol's states, as a start into state_of
-    uint8_t state_of[kSize]; // table indices grouped by symbol, in table order
-    {
         int at = 0;
+        int fill[16];
         for (int s = 0; s <= max_sym; s++) {
-            first_of[s] = static_cast<uint8_t>(at);
-            at += norm[s];
+            const int c = F.norm[s];
+            fill[s] = at;
+            F.delta_find[s] = at - c;
+            if (c) {
+                int hb = 0;   // highbit(c - 1), 0 for c == 1
+                for (int v = c - 1; v > 1; v >>= 1) hb++;
+                const int max_bits = c == 1 ? kLog : kLog - hb;
+                F.delta_nb[s] = (max_bits << 16) - (c << max_bits);
+            }
+            at += c;
         }
-        int seen[16];
-        for (int s = 0; s < 16; s++) seen[s] = 0;
-        for (int u = 0; u < kSize; u++) {
-            const int s = table_sym[u];
-            state_of[first_of[s] + seen[s]++] = static_cast<uint8_t>(u);
-        }
+        for (int u = 0; u < kSize; u++) F.state_tab[fill[F.table_sym[u]]++] = static_cast<uint8_t>(u);
     }
     // ---- two interleaved states, symbols taken from the last to the first; even positions use state 0.  A state
     //      starts on the smallest sub-state of its symbol: the decoder then reads the most bits for it (at least one,
     //      as no count reaches the table size), which is how it detects the end of the stream on the last two symbols.
     ZhufBits bw;
     zhuf_bits_init(bw, out + hdr, cap - hdr);
-    int X[2] = {0, 0};
-    bool init[2] = {false, false};
-    for (int i = n - 1; i >= 0; i--) {
-        const int k = i & 1, s = w[i], c = norm[s];
-        if (!init[k]) {
-            X[k] = kSize + state_of[first_of[s]];
-            init[k] = true;
-            continue;
+    int X0 = 0, X1 = 0;   // states of the even / odd positions
+    {
+        const int sa = w[n - 1], sb = w[n - 2];
+        const int xa = kSize + F.state_tab[F.norm[sa] + F.delta_find[sa]], xb = kSize + F.state_tab[F.norm[sb] + F.delta_find[sb]];
+        if ((n - 1) & 1) {
+            X1 = xa;
+            X0 = xb;
+        } else {
+            X0 = xa;
+            X1 = xb;
         }
-        int nb = 0;
-        while ((X[k] >> nb) >= 2 * c) nb++;
-        zhuf_bits_put(bw, static_cast<uint32_t>(X[k]) & ((1u << nb) - 1u), nb);
-        X[k] = kSize + state_of[first_of[s] + (X[k] >> nb) - c];
     }
-    zhuf_bits_put(bw, static_cast<uint32_t>(X[1] - kSize), kLog);
-    zhuf_bits_put(bw, static_cast<uint32_t>(X[0] - kSize), kLog);
+    for (int i = n - 3; i >= 0; i--) {
+        const int s = w[i];
+        const int X = (i & 1) ? X1 : X0;
+        const int nb = (X + F.delta_nb[s]) >> 16;
+        zhuf_bits_put(bw, static_cast<uint32_t>(X), nb);
+        const int nx = kSize + F.state_tab[(X >> nb) + F.delta_find[s]];
+        if (i & 1)
+            X1 = nx;
+        else
+            X0 = nx;
+    }
+    zhuf_bits_put(bw, static_cast<uint32_t>(X1 - kSize), kLog);
+    zhuf_bits_put(bw, static_cast<uint32_t>(X0 - kSize), kLog);
     zhuf_bits_put(bw, 1, 1);
     const uint32_t body = zhuf_bits_close(bw);
     if (bw.overflow) return 0;
@@ -336,6 +351,7 @@ struct ZhufScratch {   // shared memory of the building CTA
     uint8_t len[256], w[256];
     uint32_t per_rank[kZhufMaxBits + 2], val[kZhufMaxBits + 2];
     int longest, last, desc_ok;
+    ZhufFseScratch fse;
 };
 
 // Table of one block from its byte histogram, by the tid-th of nt threads of one CTA (all of them call this; the
@@ -349,6 +365,7 @@ SZ_HD void zhuf_build_table(const uint8_t *sorted_sym, uint32_t *sorted_freq, in
         S.len[s] = 0;
     }
     for (int b = tid; b < kZhufMaxBits + 2; b += nt) S.per_rank[b] = 0;
+    for (int b = tid; b < 16; b += nt) S.fse.count[b] = 0;
     if (tid == 0) {
         t.desc_len = 0;
         t.ok = 0;
@@ -356,17 +373,19 @@ SZ_HD void zhuf_build_table(const uint8_t *sorted_sym, uint32_t *sorted_freq, in
     }
     SZ_CTA_SYNC();
     if (n < 2) return;
-    if (tid == 0) {
-        for (;;) {
-            for (int i = 0; i < n; i++) S.work[i] = sorted_freq[i];
+    for (;;) {
+        for (int i = tid; i < n; i += nt) S.work[i] = sorted_freq[i];
+        SZ_CTA_SYNC();
+        if (tid == 0) {
             zhuf_mk_lengths(S.work, n);
             S.longest = static_cast<int>(S.work[0]);
-            if (S.longest <= kZhufMaxBits) break;
-            // flatten the histogram until the code fits; halving keeps the order, the result stays a complete code
-            for (int i = 0; i < n; i++) sorted_freq[i] = (sorted_freq[i] + 1) / 2;
         }
+        SZ_CTA_SYNC();
+        if (S.longest <= kZhufMaxBits) break;
+        // flatten the histogram until the code fits; halving keeps the order, the result stays a complete code
+        for (int i = tid; i < n; i += nt) sorted_freq[i] = (sorted_freq[i] + 1) / 2;
+        SZ_CTA_SYNC();
     }
-    SZ_CTA_SYNC();
     for (int i = tid; i < n; i += nt) S.len[sorted_sym[i]] = static_cast<uint8_t>(S.work[i]);
     SZ_CTA_SYNC();
     if (tid == 0) {
@@ -377,13 +396,21 @@ SZ_HD void zhuf_build_table(const uint8_t *sorted_sym, uint32_t *sorted_freq, in
     SZ_CTA_SYNC();
     const int last = S.last, longest = S.longest;
     if (last < 1) return;
-    for (int s = tid; s < last; s += nt) S.w[s] = S.len[s] ? static_cast<uint8_t>(longest + 1 - S.len[s]) : 0;
+    for (int s = tid; s < last; s += nt) {
+        const uint8_t wv = S.len[s] ? static_cast<uint8_t>(longest + 1 - S.len[s]) : 0;
+        S.w[s] = wv;
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&S.fse.count[wv], 1);
+#else
+        S.fse.count[wv]++;
+#endif
+    }
     for (int s = tid; s < 256; s += nt)
         if (S.len[s]) SZ_SMEM_INC(&S.per_rank[S.len[s]]);
     SZ_CTA_SYNC();
     if (tid == 0) {
         const int nw = last;   // explicit weights
-        const uint32_t fse = zhuf_fse_weights(S.w, nw, t.desc + 1, kZhufDescCap - 1);
+        const uint32_t fse = zhuf_fse_weights(S.w, nw, S.fse, t.desc + 1, kZhufDescCap - 1);
         if (fse > 0 && fse < 128) {
             t.desc[0] = static_cast<uint8_t>(fse);
             t.desc_len = fse + 1;
