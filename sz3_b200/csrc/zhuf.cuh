@@ -112,48 +112,103 @@ SZ_HD uint64_t zhuf_write_headers(uint8_t *out, uint64_t len, uint64_t g, const 
     return bo + 3 + 5 + bi.desc_len + 6;
 }
 
+#if defined(__CUDA_ARCH__)
+#define SZ_CTA_SYNC() __syncthreads()
+#define SZ_SMEM_INC(p) atomicAdd((p), 1u)
+#else
+#define SZ_CTA_SYNC() ((void)0)
+#define SZ_SMEM_INC(p) (++*(p))
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Huffman code construction (one block = at most 131072 symbols over 256 byte values)
 // ---------------------------------------------------------------------------------------------------------------------
-// In-place minimum-redundancy code lengths (Moffat & Katajainen): A[0..n) ascending frequencies in, code lengths out
-// (A[0] = the rarest symbol's = the longest).
-SZ_HD void zhuf_mk_lengths(uint32_t *A, int n) {
-    if (n == 1) {
-        A[0] = 0;
-        return;
+struct ZhufMkScratch {   // shared memory of the cooperative length computation
+    uint16_t p[2][256], d[2][256];
+    uint32_t cnt[256], cum[256];
+    int maxdep;
+};
+
+// Minimum-redundancy code lengths (Moffat & Katajainen, in place): A[0..n) ascending frequencies in, code lengths out
+// (A[0] = the rarest symbol's = the longest), n >= 2.  Called by all nt threads of the CTA.
+//   phase 1 (thread 0): the two-queue merge; the heads of both queues are kept in registers, so an iteration costs
+//            one or two shared-memory loads instead of four.  Leaves A[i], i < n - 2, then hold parent indices.
+//   phase 2 (all): depth of every internal node by pointer jumping (8 rounds cover any tree over 256 leaves).
+//   phase 3 (all): internal nodes per depth -> leaves per depth (the deepest leaves go to the rarest symbols).
+SZ_HD void zhuf_mk_lengths(uint32_t *A, int n, ZhufMkScratch &M, int tid, int nt) {
+    if (tid == 0) {
+        A[0] += A[1];
+        int root = 0, leaf = 2;
+        uint32_t vroot = A[0], vleaf = n > 2 ? A[2] : 0u;   // heads of the internal-node and the leaf queue
+        for (int next = 1; next < n - 1; next++) {
+            uint32_t sum;
+            // first item of the pair
+            if (leaf >= n || vroot < vleaf) {
+                sum = vroot;
+                A[root++] = static_cast<uint32_t>(next);
+                vroot = A[root];   // nodes root..next-1 hold weights (next itself is written below, root < next here
+                                   // unless the queue is empty, in which case the value is not used before it is set)
+            } else {
+                sum = vleaf;
+                leaf++;
+                vleaf = leaf < n ? A[leaf] : 0u;
+            }
+            // second item
+            if (leaf >= n || (root < next && vroot < vleaf)) {
+                sum += vroot;
+                A[root++] = static_cast<uint32_t>(next);
+                vroot = root < next ? A[root] : 0u;
+            } else {
+                sum += vleaf;
+                leaf++;
+                vleaf = leaf < n ? A[leaf] : 0u;
+            }
+            A[next] = sum;
+            if (root == next) vroot = sum;   // the queue of internal nodes was empty: the new node is its head
+        }
     }
-    A[0] += A[1];
-    int root = 0, leaf = 2;
-    for (int next = 1; next < n - 1; next++) {
-        if (leaf >= n || A[root] < A[leaf]) {
-            A[next] = A[root];
-            A[root++] = static_cast<uint32_t>(next);
-        } else {
-            A[next] = A[leaf++];
-        }
-        if (leaf >= n || (root < next && A[root] < A[leaf])) {
-            A[next] += A[root];
-            A[root++] = static_cast<uint32_t>(next);
-        } else {
-            A[next] += A[leaf++];
-        }
+    SZ_CTA_SYNC();
+    // internal nodes 0 .. n-2, root = n-2
+    const int ni = n - 1;
+    for (int i = tid; i < ni; i += nt) {
+        const bool is_root = i == ni - 1;
+        M.p[0][i] = static_cast<uint16_t>(is_root ? i : A[i]);
+        M.d[0][i] = is_root ? 0 : 1;
     }
-    A[n - 2] = 0;
-    for (int next = n - 3; next >= 0; next--) A[next] = A[A[next]] + 1;
-    int avbl = 1, used = 0, dpth = 0, r = n - 2, nx = n - 1;
-    while (avbl > 0) {
-        while (r >= 0 && static_cast<int>(A[r]) == dpth) {
-            used++;
-            r--;
+    for (int i = tid; i < 256; i += nt) M.cnt[i] = 0;
+    SZ_CTA_SYNC();
+    int cur = 0;
+    for (int r = 0; r < 8; r++) {
+        for (int i = tid; i < ni; i += nt) {
+            const int pi = M.p[cur][i];
+            M.d[cur ^ 1][i] = static_cast<uint16_t>(M.d[cur][i] + M.d[cur][pi]);
+            M.p[cur ^ 1][i] = M.p[cur][pi];
         }
-        while (avbl > used) {
-            A[nx--] = static_cast<uint32_t>(dpth);
-            avbl--;
-        }
-        avbl = 2 * used;
-        dpth++;
-        used = 0;
+        cur ^= 1;
+        SZ_CTA_SYNC();
     }
+    for (int i = tid; i < ni; i += nt) SZ_SMEM_INC(&M.cnt[M.d[cur][i]]);
+    SZ_CTA_SYNC();
+    if (tid == 0) {
+        uint32_t avbl = 1, cum = 0;
+        int dep = 0;
+        for (; dep < 256; dep++) {
+            const uint32_t used = M.cnt[dep];
+            cum += avbl - used;   // leaves at this depth
+            M.cum[dep] = cum;
+            avbl = 2 * used;
+            if (avbl == 0) break;
+        }
+        M.maxdep = dep < 256 ? dep : 255;
+    }
+    SZ_CTA_SYNC();
+    for (int i = tid; i < n; i += nt) {
+        const uint32_t pos = static_cast<uint32_t>(n - 1 - i);   // rank from the most frequent leaf
+        int dep = 0;
+        while (dep < M.maxdep && M.cum[dep] <= pos) dep++;
+        A[i] = static_cast<uint32_t>(dep);
+    }
+    SZ_CTA_SYNC();
 }
 
 struct ZhufBits {   // forward bit writer, LSB first
@@ -338,20 +393,13 @@ SZ_HD uint32_t zhuf_fse_weights(const uint8_t *w, int n, ZhufFseScratch &F, uint
     return hdr + body;
 }
 
-#if defined(__CUDA_ARCH__)
-#define SZ_CTA_SYNC() __syncthreads()
-#define SZ_SMEM_INC(p) atomicAdd((p), 1u)
-#else
-#define SZ_CTA_SYNC() ((void)0)
-#define SZ_SMEM_INC(p) (++*(p))
-#endif
-
 struct ZhufScratch {   // shared memory of the building CTA
     uint32_t work[256];
     uint8_t len[256], w[256];
     uint32_t per_rank[kZhufMaxBits + 2], val[kZhufMaxBits + 2];
     int longest, last, desc_ok;
     ZhufFseScratch fse;
+    ZhufMkScratch mk;
 };
 
 // Table of one block from its byte histogram, by the tid-th of nt threads of one CTA (all of them call this; the
@@ -376,10 +424,8 @@ SZ_HD void zhuf_build_table(const uint8_t *sorted_sym, uint32_t *sorted_freq, in
     for (;;) {
         for (int i = tid; i < n; i += nt) S.work[i] = sorted_freq[i];
         SZ_CTA_SYNC();
-        if (tid == 0) {
-            zhuf_mk_lengths(S.work, n);
-            S.longest = static_cast<int>(S.work[0]);
-        }
+        zhuf_mk_lengths(S.work, n, S.mk, tid, nt);
+        if (tid == 0) S.longest = static_cast<int>(S.work[0]);
         SZ_CTA_SYNC();
         if (S.longest <= kZhufMaxBits) break;
         // flatten the histogram until the code fits; halving keeps the order, the result stays a complete code
