@@ -108,6 +108,10 @@ int sz3b_blockwise_decompose(int dtype, const sz3b_config *c, double abs_eb, con
 int sz3b_huffman_encode(const int32_t *q, size_t n, int q_loc, unsigned char *out, size_t out_cap, size_t *out_len,
                         size_t *tree_len);
 
+/* HuffmanEncoder<int>::load + decode (encoder/HuffmanEncoder.hpp:225-279) on the GPU (self-synchronising decoder):
+ * in = tree blob | size_t outSize | bits, tree_len as reported by sz3b_huffman_encode; out = n host int32. */
+int sz3b_huffman_decode(const unsigned char *in, size_t in_len, size_t tree_len, size_t n, int32_t *out);
+
 /* Lossless_zstd::compress (lossless/Lossless_zstd.hpp:29-37) by the GPU lossless stage of policy 2: src (host or
  * device, src_loc) -> out (host) = size_t srcLen | standard zstd frames of Huffman-only literal blocks. */
 int sz3b_lossless_compress(const unsigned char *src, size_t src_len, int src_loc, unsigned char *out, size_t out_cap,

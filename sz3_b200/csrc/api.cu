@@ -289,6 +289,14 @@ int sz3b_huffman_encode(const int32_t *q, size_t n, int q_loc, unsigned char *ou
     });
 }
 
+int sz3b_huffman_decode(const unsigned char *in, size_t in_len, size_t tree_len, size_t n, int32_t *out) {
+    return guarded([&] {
+        WorkspaceLease ws;
+        huffman_decode_stage(*ws, in, in_len, tree_len, n, out);
+        finish_profile(*ws);
+    });
+}
+
 int sz3b_lossless_compress(const unsigned char *src, size_t src_len, int src_loc, unsigned char *out, size_t out_cap,
                            size_t *out_len) {
     return guarded([&] {

@@ -1999,6 +1999,21 @@ void huffman_encode_stage(Workspace &ws, const int32_t *q, size_t n, int loc, st
     huffman_encode_device(ws, d_q, n, out, tree_len);
 }
 
+// HuffmanEncoder::load + decode (HuffmanEncoder.hpp:225-279) of `in` = tree blob | size_t outSize | bits (what
+// sz3b_huffman_encode and the reference's save() + encode() write) through the GPU decoder; `tree_len` as reported there.
+void huffman_decode_stage(Workspace &ws, const uint8_t *in, size_t in_len, size_t tree_len, size_t n, int32_t *out) {
+    if (tree_len > in_len) fail(SZ3B_E_INVALID_ARGUMENT, "tree length exceeds the input");
+    std::vector<uint8_t> buf(in_len + 8);
+    memcpy(buf.data(), in, tree_len);
+    uint8_t *p = buf.data() + tree_len;
+    put<uint64_t>(p, static_cast<uint64_t>(n));
+    memcpy(p, in + tree_len, in_len - tree_len);
+    Cursor c{buf.data(), buf.size()};
+    uint32_t *d_q = decode_indices<uint32_t>(ws, c, n);
+    ws.d2h(out, d_q, n * sizeof(uint32_t));
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+}
+
 #define SZ3B_INST_PIPE(T)                                                                                             \
     template size_t compress_any<T>(Workspace &, sz3b_config &, const T *, int, uint8_t *, size_t);                  \
     template void interp_decompose_stage<T>(Workspace &, const sz3b_config &, double, const T *, int, int, int32_t *, \

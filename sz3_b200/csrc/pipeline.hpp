@@ -32,6 +32,7 @@ void blockwise_decompose_stage(Workspace &ws, const sz3b_config &conf, double eb
                                int32_t *quant_out, std::vector<uint8_t> &blob);
 void huffman_encode_stage(Workspace &ws, const int32_t *q, size_t n, int loc, std::vector<uint8_t> &out,
                           size_t *tree_len);
+void huffman_decode_stage(Workspace &ws, const uint8_t *in, size_t in_len, size_t tree_len, size_t n, int32_t *out);
 size_t lossless_gpu_stage(Workspace &ws, const uint8_t *src, size_t len, int loc, uint8_t *out, size_t cap);
 template <class T>
 void tune_stage(Workspace &ws, sz3b_config &conf, const T *data, int loc);

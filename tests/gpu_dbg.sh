@@ -1,5 +1,5 @@
-# GPU-box script (diagnostics): where does the 2^31-element decompression fail?
+# GPU-box script (diagnostics): where does the 2^31-element 4-D case fail?
 cd $GRAFT_REPO_ROOT
-echo "== A: 4-D 2^30 elements, policy 2"; timeout 600 python tests/large_check.py --c4 16 256 512 512 2>&1 | tail -4 | cut -c1-300
-echo "== B: 4-D 2^31 elements, policy 0"; SZ3B_POLICY=0 timeout 900 python tests/large_check.py --c4 32 256 512 512 2>&1 | tail -4 | cut -c1-300
-echo "== C: 3-D 2^31 elements, policy 2"; timeout 900 python tests/large_check.py 512 2048 2048 2>&1 | tail -4 | cut -c1-300
+free -g | head -2
+echo "== 4-D 31x256x512x512 (just below 2^31)"; timeout 600 python tests/large_check.py --c4 31 256 512 512 2>&1 | tail -3 | cut -c1-200
+echo "== 4-D 32x256x512x512 with the reference decoder"; timeout 1500 python tests/large_check.py --c4 --ref 32 256 512 512 2>&1 | tail -6 | cut -c1-200

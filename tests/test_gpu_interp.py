@@ -137,3 +137,42 @@ def test_schedules_agree_512():
     assert np.array_equal(q1, q2) and b1 == b2
     hist = np.bincount(q1, minlength=65536)
     assert hist.sum() == data.size and hist[0] >= 4096  # anchors are stored as unpredictables
+
+
+def _huffman_both(q):
+    """(ours, reference) = tree blob | size_t outSize | bits for the int32 array q, plus tree lengths."""
+    L, R = product_lib(), ref_lib()
+    L.sz3b_huffman_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    R.ref_huffman_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    cap = q.size * 8 + (1 << 22)
+    ours, theirs = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
+    n1, t1, t2 = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    rc = L.sz3b_huffman_encode(q.ctypes.data, q.size, 0, ours.ctypes.data, cap, C.byref(n1), C.byref(t1))
+    assert rc == 0, L.sz3b_last_error()
+    n2 = R.ref_huffman_encode(q.ctypes.data, q.size, theirs.ctypes.data, C.byref(t2))
+    assert n2 > 0
+    return ours[:n1.value], t1.value, theirs[:n2], t2.value
+
+
+@pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref/libsz3ref.so not built")
+@pytest.mark.parametrize("nsym", [20, 36, 40])
+def test_huffman_long_codes(nsym):
+    """Fibonacci symbol counts give a maximally skewed tree: code lengths up to nsym - 1 bits (beyond the 12-bit first
+    level table of the decoder, and beyond 32 bits for nsym = 36 and 40 -- the case a 2^31-element array reaches on
+    its rarest symbols).  Encoder against the reference byte for byte, GPU decoder on both streams."""
+    fib = [1, 1]
+    while len(fib) < nsym:
+        fib.append(fib[-1] + fib[-2])
+    scale = max(1, fib[-1] // 30_000_000)          # keep the array below ~80 M symbols
+    counts = [max(1, f // scale) for f in fib]
+    rng = np.random.default_rng(nsym)
+    q = np.repeat(np.arange(nsym, dtype=np.int32) * 3 + 1000, counts)
+    rng.shuffle(q)
+    ours, t1, theirs, t2 = _huffman_both(q)
+    assert t1 == t2 and ours.size == theirs.size and np.array_equal(ours, theirs)
+    L = product_lib()
+    L.sz3b_huffman_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    back = np.empty(q.size, np.int32)
+    rc = L.sz3b_huffman_decode(theirs.ctypes.data, theirs.size, t2, q.size, back.ctypes.data)
+    assert rc == 0, L.sz3b_last_error()
+    assert np.array_equal(back, q)
