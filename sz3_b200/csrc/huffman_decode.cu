@@ -9,7 +9,10 @@
 //               (i+1)*kSubBits and publishes that overshoot and its symbol count.  Iterated with ping-pong overshoot
 //               arrays until no overshoot changes: then every start is the true boundary (thread 0's start is exact,
 //               and a thread whose start is exact publishes an exact overshoot -- induction over i; the loop ends
-//               only at a fixed point, which is therefore the true one).  2-3 iterations in practice.
+//               only at a fixed point, which is therefore the true one).  2-3 iterations in practice; a stretch where
+//               the wrong phase happens to decode consistently (e.g. a run of one 2-bit codeword whose shifted reading
+//               is another codeword) needs one round per subsequence of the stretch, so after the first round only the
+//               subsequences whose start moved are decoded again and the loop runs until nothing moves.
 //   (scan)      exclusive prefix sum of the symbol counts -> output offsets (encode_kernels.cu: k_pack_scan)
 //   k_hd_write  same decode, symbols written at their offsets, clipped to the stream's symbol count.
 //
@@ -85,13 +88,29 @@ __device__ __forceinline__ uint32_t hd_symbol(BitReader &br, const uint32_t *slu
 
 __global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restrict__ words, uint64_t total_bits, uint64_t nsub,
                                                        HdTables t, const uint8_t *__restrict__ over_in,
-                                                       uint8_t *__restrict__ over_out, unsigned *__restrict__ counts,
-                                                       unsigned *__restrict__ changed) {
+                                                       uint8_t *__restrict__ over_out, const uint8_t *__restrict__ dirty_in,
+                                                       uint8_t *__restrict__ dirty_out, int first_round,
+                                                       unsigned *__restrict__ counts, unsigned *__restrict__ changed) {
     __shared__ uint32_t slut[1 << kHdLutBits];
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    // a subsequence is decoded again only when its start moved in the last round (the overshoot of its predecessor
+    // changed); CTAs without such a subsequence skip the table load as well
+    const bool need = i < nsub && (first_round || (i > 0 && dirty_in[i - 1]));
+    if (!__syncthreads_or(need ? 1 : 0)) {
+        if (i < nsub) {
+            over_out[i] = over_in[i];
+            dirty_out[i] = 0;
+        }
+        return;
+    }
     for (int k = threadIdx.x; k < (1 << kHdLutBits); k += blockDim.x) slut[k] = t.lut[k];
     __syncthreads();
-    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= nsub) return;
+    if (!need) {
+        over_out[i] = over_in[i];
+        dirty_out[i] = 0;
+        return;
+    }
     uint64_t pos = i * kSubBits + (i ? over_in[i - 1] : 0);
     uint64_t limit = (i + 1) * kSubBits;
     if (limit > total_bits) limit = total_bits;
@@ -110,7 +129,9 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restri
     const uint8_t o = static_cast<uint8_t>(over > 255 ? 255 : over);
     counts[i] = cnt;
     over_out[i] = o;
-    if (o != over_in[i]) *changed = 1u;   // thread i+1 started from over_in[i] in this round
+    const bool moved = o != over_in[i];   // thread i+1 started from over_in[i] in this round
+    dirty_out[i] = moved ? 1 : 0;
+    if (moved) *changed = 1u;
 }
 
 template <class QT>
@@ -142,11 +163,12 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_write(const uint32_t *__restr
 uint64_t hd_num_sub(uint64_t total_bits) { return (total_bits + kSubBits - 1) / kSubBits; }
 
 void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over_in,
-                    uint8_t *over_out, unsigned *counts, unsigned *changed, cudaStream_t st) {
+                    uint8_t *over_out, const uint8_t *dirty_in, uint8_t *dirty_out, bool first_round, unsigned *counts,
+                    unsigned *changed, cudaStream_t st) {
     const uint64_t nsub = hd_num_sub(total_bits);
     HdTables t{tb.lut, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
-    k_hd_sync<<<static_cast<unsigned>((nsub + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, total_bits, nsub, t, over_in,
-                                                                                             over_out, counts, changed);
+    k_hd_sync<<<static_cast<unsigned>((nsub + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(
+        words, total_bits, nsub, t, over_in, over_out, dirty_in, dirty_out, first_round ? 1 : 0, counts, changed);
 }
 
 template <class QT>

@@ -110,7 +110,8 @@ struct HdDeviceTables {
 };
 uint64_t hd_num_sub(uint64_t total_bits);
 void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over_in,
-                    uint8_t *over_out, unsigned *counts, unsigned *changed, cudaStream_t st);
+                    uint8_t *over_out, const uint8_t *dirty_in, uint8_t *dirty_out, bool first_round, unsigned *counts,
+                    unsigned *changed, cudaStream_t st);
 template <class QT>
 void launch_hd_write(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over,
                      const unsigned long long *offs, uint64_t n, QT *out, cudaStream_t st);
