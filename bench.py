@@ -304,7 +304,12 @@ def run_ours(args):
         t0 = time.perf_counter()
         step(dev.data_ptr(), 1)
         dt = time.perf_counter() - t0
-        if prev is not None and abs(dt - prev) < 0.03 * prev:
+        settled = prev is not None and abs(dt - prev) < 0.03 * prev
+        if world > 1:   # every rank must leave the loop in the same iteration (step() holds a collective)
+            flag = torch.tensor([1 if settled else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            settled = bool(flag.item())
+        if settled:
             break
         prev = dt
     sampler = ClockSampler(local)

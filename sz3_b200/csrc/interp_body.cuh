@@ -41,6 +41,7 @@ struct InterpArgs {
     uint32_t s;             // level stride
     uint32_t nb[kMaxDim];   // blocks per dimension at this level
     const uint64_t *block_base;  // position (inside one array) of the first index each block emits
+    uint32_t tile0;         // tile kernels: index of the first tile of this launch (partial launches of one level)
 };
 
 template <class T, class QT, class Ctx>

@@ -109,9 +109,10 @@ __device__ __forceinline__ void ltile_body(const InterpArgs<T, QT> &A) {
     DevCtx2 ctx(shist, A.hist, A.qp.radius);
     for (int i = threadIdx.x; i < kHistWindow; i += blockDim.x) shist[i] = 0;
     LineGeom lg;
-    line_geom(A, blockIdx.x, blockIdx.y, lg);
+    const uint32_t tile = blockIdx.x + A.tile0;
+    line_geom(A, tile, blockIdx.y, lg);
     if ((threadIdx.x & 31u) == 0 && (threadIdx.x >> 5) < 3)
-        line_pass_setup(A, blockIdx.x, blockIdx.y, static_cast<int>(threadIdx.x >> 5), blockDim.x, lt.ps[threadIdx.x >> 5]);
+        line_pass_setup(A, tile, blockIdx.y, static_cast<int>(threadIdx.x >> 5), blockDim.x, lt.ps[threadIdx.x >> 5]);
     line_fill(A, ctx, lg, sm);
     __syncthreads();
     line_tile_passes(A, ctx, sm, lg, lt);

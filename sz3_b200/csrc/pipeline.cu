@@ -111,6 +111,48 @@ static const T *to_device_background(Workspace &ws, const T *data, size_t num) {
 static void join_copy(Workspace &ws) {
     SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.ev_copy, 0));
     ws.bulk_copy_in_flight = false;
+    ws.copy_plan.active = false;
+}
+
+// Same, for a 3-D array that the interpolation tile path will consume: planes of the outermost dimension in the
+// order the levels need them (Workspace::CopyPlan).  Coarse levels (stride >= 2) only touch even coordinates, so they
+// can run once the even planes are there; the level-1 tiles of block-row b read planes [32 b, 32 b + 32].
+template <class T>
+static const T *to_device_planes(Workspace &ws, const T *data, const sz3b_config &conf) {
+    const size_t num = config_num(conf);
+    T *d = ws.data.as<T>(num);
+    const size_t nz = conf.dims[0], plane = num / nz * sizeof(T);
+    uint8_t *dst = reinterpret_cast<uint8_t *>(d);
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(data);
+    // even planes, a few at a time so that other traffic can slip in between commands
+    const size_t n_even = (nz + 1) / 2;
+    for (size_t k = 0; k < n_even; k += 8) {
+        const size_t cnt = std::min<size_t>(8, n_even - k);
+        SZ3B_CUDA(cudaMemcpy2DAsync(dst + 2 * k * plane, 2 * plane, src + 2 * k * plane, 2 * plane, plane, cnt,
+                                    cudaMemcpyHostToDevice, ws.st_copy));
+    }
+    ws.copy_plan.ev_even = ws.event();
+    SZ3B_CUDA(cudaEventRecord(ws.copy_plan.ev_even, ws.st_copy));
+    // odd planes, one group per block-row of the finest level (blocks of 32, the last one closed at nz - 1)
+    const size_t nrows = (nz - 1 + kInterpBlock - 1) / kInterpBlock;
+    ws.copy_plan.ev_row.clear();
+    for (size_t b = 0; b < nrows; b++) {
+        const size_t z0 = b * kInterpBlock + 1;
+        const size_t z_end = std::min<size_t>((b + 1) * kInterpBlock, nz - 1);   // last plane the block-row reads
+        if (z0 <= z_end) {
+            const size_t cnt = (z_end - z0) / 2 + 1;
+            SZ3B_CUDA(cudaMemcpy2DAsync(dst + z0 * plane, 2 * plane, src + z0 * plane, 2 * plane, plane, cnt,
+                                        cudaMemcpyHostToDevice, ws.st_copy));
+        }
+        cudaEvent_t e = ws.event();
+        SZ3B_CUDA(cudaEventRecord(e, ws.st_copy));
+        ws.copy_plan.ev_row.push_back(e);
+    }
+    ws.h2d_bytes += num * sizeof(T);
+    SZ3B_CUDA(cudaEventRecord(ws.ev_copy, ws.st_copy));
+    ws.bulk_copy_in_flight = true;
+    ws.copy_plan.active = true;
+    return d;
 }
 
 template <class T>
@@ -214,6 +256,15 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         ws.h2d(d_table, pl.table.data(), pl.table.size() * sizeof(uint64_t));
     A.qp = make_quant(pl.eb, radius);
     A.s = 0;
+    // input still arriving in plane order (to_device_planes): the line-walker tile path follows the copy, anything
+    // else waits for all of it
+    bool planes = ws.copy_plan.active && d_data == ws.data.p && nbatch == 1;
+    if (planes && !(pl.tile && pl.variant == 2 && !pl.levels.empty() && pl.levels.back().s == 1 &&
+                    pl.levels.back().nb[0] == ws.copy_plan.ev_row.size())) {
+        join_copy(ws);
+        planes = false;
+    }
+    if (planes) SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.copy_plan.ev_even, 0));
     interp_launch_anchors<T, QT>(A, pl.anchor_stride, pl.n_first, nbatch, ws.st);
     (*launches)++;
     for (const LevelPlan &L : pl.levels) {
@@ -221,6 +272,19 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         A.s = L.s;
         for (int d = 0; d < kMaxDim; d++) A.nb[d] = L.nb[d];
         A.block_base = d_table + L.table_off;
+        if (planes && L.s == 1) {
+            // the finest level, block-row by block-row as the odd planes arrive
+            const uint64_t per_row = static_cast<uint64_t>(L.nb[1]) * L.nb[2];
+            for (uint32_t b = 0; b < L.nb[0]; b++) {
+                SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.copy_plan.ev_row[b], 0));
+                A.tile0 = static_cast<uint32_t>(b * per_row);
+                interp_launch_ltiles<T, QT>(A, per_row, nbatch, ws.st);
+                (*launches)++;
+            }
+            A.tile0 = 0;
+            join_copy(ws);
+            continue;
+        }
         if (pl.tile) {
             if (pl.variant == 2)
                 interp_launch_ltiles<T, QT>(A, L.nblocks, nbatch, ws.st);
@@ -1366,9 +1430,13 @@ static size_t dispatch_compress(Workspace &ws, sz3b_config &conf, const T *data,
                     // pinned host input: the tuner samples ~0.5 % of the array straight from host memory while the
                     // bulk copy runs on its own stream
                     double t0 = now_ms();
-                    d_data = to_device_background<T>(ws, data, num);
+                    // 3-D arrays with an absolute bound go up in plane order, and predict+quantize follows the copy
+                    // (run_interp); everything else waits for the whole array after tuning
+                    const bool planes = conf.N == 3 && conf.dims[0] >= 64 && num < (1ull << 32) &&
+                                        num / conf.dims[0] * sizeof(T) >= (64u << 10);
+                    d_data = planes ? to_device_planes<T>(ws, data, conf) : to_device_background<T>(ws, data, num);
                     tune_interp<T>(ws, conf, alias);
-                    join_copy(ws);
+                    if (!(planes && conf.cmprAlgo == SZ3B_ALGO_INTERP)) join_copy(ws);
                     ws.host_stage("tune_overlapped_with_h2d", now_ms() - t0);
                 } else {
                     tune_interp<T>(ws, conf, dev());   // rewrites cmprAlgo to ALGO_INTERP (N >= 2)

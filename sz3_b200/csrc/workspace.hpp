@@ -130,6 +130,14 @@ struct Workspace {
     // While the bulk input copy owns the H2D copy engine (bulk_copy_in_flight), small uploads go through a pinned
     // staging arena read by an SM copy kernel instead of queueing behind it.
     bool bulk_copy_in_flight = false;
+    // Plane-ordered bulk copy of a 3-D input (pipeline.cu: to_device_planes): the even planes of the outermost
+    // dimension go first (everything the interpolation levels with stride >= 2 read), then the odd planes, one
+    // group per block-row of the finest level, so that level-1 tiles start while later planes are still in flight.
+    struct CopyPlan {
+        bool active = false;
+        cudaEvent_t ev_even = nullptr;
+        std::vector<cudaEvent_t> ev_row;   // ev_row[b]: every plane the level-1 tiles of block-row b read has arrived
+    } copy_plan;
     PinBuf upload_arena;
     size_t upload_used = 0;
     static constexpr size_t kUploadArena = static_cast<size_t>(16) << 20;
@@ -156,6 +164,8 @@ struct Workspace {
         h2d_bytes = d2h_bytes = 0;
         upload_used = 0;
         bulk_copy_in_flight = false;
+        copy_plan.active = false;
+        copy_plan.ev_row.clear();
         stage_prefix.clear();
         prof.clear();
         pending.clear();

@@ -178,3 +178,32 @@ def test_one_dimensional_default_algorithm(kind, n, eb):
     assert used.cmprAlgo == dconf.cmprAlgo
     assert ours.size == theirs.size and np.array_equal(ours, theirs), (ours.size, theirs.size, used.cmprAlgo)
     assert np.max(np.abs(dec.astype(np.float64) - data.astype(np.float64))) <= eb
+
+
+@needs_ref
+@pytest.mark.parametrize("shape,dtype,algo", [
+    ((96, 160, 128), np.float32, ALGO_INTERP_LORENZO),     # plane-ordered copy: 3 block-rows, even nz
+    ((97, 160, 128), np.float32, ALGO_INTERP_LORENZO),     # odd nz: the last block-row is closed by an even plane
+    ((65, 129, 130), np.float64, ALGO_INTERP_LORENZO),     # two block-rows, the second a single plane pair
+    ((64, 256, 96), np.float32, ALGO_INTERP_LORENZO),
+    ((130, 100, 70), np.float32, ALGO_INTERP_LORENZO),     # planes below 64 KiB: plain background copy
+    ((40, 40, 40, 24), np.float32, ALGO_INTERP_LORENZO),   # 4-D: plain background copy
+])
+def test_pinned_host_input_stream_identical(shape, dtype, algo):
+    """Pinned host input takes the overlapped path: the tuner samples host memory while the array goes up, and for 3-D
+    arrays the copy runs in plane order with predict+quantize following it (level 1 block-row by block-row).  The
+    stream must not depend on how the input arrived."""
+    import torch
+    data = field_nd(shape, dtype)
+    conf = make_config(shape, cmprAlgo=algo, absErrorBound=1e-3)
+    pinned = torch.from_numpy(data).pin_memory()
+    L = product_lib()
+    cap = L.sz3b_compress_bound(dtype_code(data), C.byref(conf))
+    out = np.empty(cap, dtype=np.uint8)
+    size = C.c_size_t(0)
+    theirs = ref_compress(data, conf)
+    for _ in range(2):   # the second call reuses warm buffers and events
+        rc = L.sz3b_compress(dtype_code(data), C.byref(conf), C.c_void_p(pinned.data_ptr()), 0, out.ctypes.data_as(C.c_char_p),
+                             C.c_size_t(cap), C.byref(size), None)
+        assert rc == 0, L.sz3b_last_error()
+        assert size.value == theirs.size and np.array_equal(out[:size.value], theirs)
