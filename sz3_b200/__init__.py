@@ -223,5 +223,15 @@ class sz:
         n = L.sz3b_last_profile(names, ms, launches, cap)
         return [(names[i].decode(), ms[i], launches[i]) for i in range(min(n, cap))]
 
+    @staticmethod
+    def set_lossless_policy(policy):
+        """Where the lossless stage over the packed stream runs (include/sz3b.h): 2 = on the GPU as standard zstd frames
+        of Huffman-only literal blocks (default), 0 = zstd level 3 on the host like the reference, 1 = adaptive host."""
+        lib().sz3b_set_lossless_policy(int(policy))
+
+    @staticmethod
+    def get_lossless_policy():
+        return int(lib().sz3b_get_lossless_policy())
+
 
 __all__ = ["sz", "szConfig", "szErrorBoundMode", "szAlgorithm", "SZ3BError", "lib"]
