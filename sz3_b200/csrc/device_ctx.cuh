@@ -94,13 +94,20 @@ struct DevCtx2 {
         else
             atomicAdd(&ghist[sym], 1ull);
     }
-    // all threads of the CTA, converged
+    // all threads of the CTA, converged.  The eight 8-bit counters are widened to 16-bit fields (even / odd bytes of
+    // the two halves: a warp's sum of a field is at most 32 * 255), four warp reductions add them up, and lane b
+    // (b < 8) adds bin b to the shared window.
     __device__ __forceinline__ void pass_end() {
-#pragma unroll
-        for (int b = 0; b < 8; b++) {
-            unsigned v = static_cast<unsigned>(packed >> (8 * b)) & 0xffu;
-            v = __reduce_add_sync(0xffffffffu, v);
-            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&shist[lo8 - lo + b], v);
+        const unsigned plo = static_cast<unsigned>(packed), phi = static_cast<unsigned>(packed >> 32);
+        const unsigned e_lo = __reduce_add_sync(0xffffffffu, plo & 0x00ff00ffu);          // bins 0, 2
+        const unsigned o_lo = __reduce_add_sync(0xffffffffu, (plo >> 8) & 0x00ff00ffu);   // bins 1, 3
+        const unsigned e_hi = __reduce_add_sync(0xffffffffu, phi & 0x00ff00ffu);          // bins 4, 6
+        const unsigned o_hi = __reduce_add_sync(0xffffffffu, (phi >> 8) & 0x00ff00ffu);   // bins 5, 7
+        const unsigned lane = threadIdx.x & 31u;
+        if (lane < 8u) {
+            const unsigned word = (lane & 4u) ? ((lane & 1u) ? o_hi : e_hi) : ((lane & 1u) ? o_lo : e_lo);
+            const unsigned v = (lane & 2u) ? word >> 16 : word & 0xffffu;
+            if (v) atomicAdd(&shist[lo8 - lo + static_cast<int>(lane)], v);
         }
         packed = 0;
     }

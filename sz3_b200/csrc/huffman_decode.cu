@@ -5,14 +5,15 @@
 // is unknown, but prefix codes self-synchronise: a decoder started at a wrong bit offset falls onto true codeword
 // boundaries after a few symbols.  So (after Weissenberger & Schmidt, ICPP 2018, restated for this format):
 //
-//   k_hd_sync   thread i decodes from (i*kSubBits + over_in[i-1]) to the first codeword boundary at or past
-//               (i+1)*kSubBits and publishes that overshoot and its symbol count.  Iterated with ping-pong overshoot
-//               arrays until no overshoot changes: then every start is the true boundary (thread 0's start is exact,
+//   k_hd_sync   thread i decodes from (i*kSubBits + over[i-1]) to the first codeword boundary at or past
+//               (i+1)*kSubBits and publishes that overshoot and its symbol count.  Iterated until no overshoot
+//               changes: then every start is the true boundary (thread 0's start is exact,
 //               and a thread whose start is exact publishes an exact overshoot -- induction over i; the loop ends
 //               only at a fixed point, which is therefore the true one).  2-3 iterations in practice; a stretch where
 //               the wrong phase happens to decode consistently (e.g. a run of one 2-bit codeword whose shifted reading
 //               is another codeword) needs one round per subsequence of the stretch, so after the first round only the
-//               subsequences whose start moved are decoded again and the loop runs until nothing moves.
+//               subsequences whose start moved are decoded again (the launch covers just their index range) and the
+//               loop runs until nothing moves.
 //   (scan)      exclusive prefix sum of the symbol counts -> output offsets (encode_kernels.cu: k_pack_scan)
 //   k_hd_write  same decode, symbols written at their offsets, clipped to the stream's symbol count.
 //
@@ -86,32 +87,26 @@ __device__ __forceinline__ uint32_t hd_symbol(BitReader &br, const uint32_t *slu
     return node;
 }
 
+// One synchronisation round over the subsequences [base, base + count).  `over` is updated in place and `stamp[i]`
+// remembers (mod 256) the round in which over[i] last moved: subsequence i is decoded again in round r only if its
+// start moved in round r - 1.  A reader may see its predecessor's overshoot of this or of the previous round; either
+// way the predecessor's stamp makes it run again in the next round, so the loop can only stop at the fixed point.  The
+// host restricts the next round to the successors of the subsequences that moved (moved[1..2] = their index range).
 __global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restrict__ words, uint64_t total_bits, uint64_t nsub,
-                                                       HdTables t, const uint8_t *__restrict__ over_in,
-                                                       uint8_t *__restrict__ over_out, const uint8_t *__restrict__ dirty_in,
-                                                       uint8_t *__restrict__ dirty_out, int first_round,
-                                                       unsigned *__restrict__ counts, unsigned *__restrict__ changed) {
+                                                       HdTables t, uint8_t *over, uint8_t *stamp, int round, uint64_t base,
+                                                       uint64_t count, unsigned *__restrict__ counts,
+                                                       unsigned long long *__restrict__ moved) {
     __shared__ uint32_t slut[1 << kHdLutBits];
-    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    // a subsequence is decoded again only when its start moved in the last round (the overshoot of its predecessor
-    // changed); CTAs without such a subsequence skip the table load as well
-    const bool need = i < nsub && (first_round || (i > 0 && dirty_in[i - 1]));
-    if (!__syncthreads_or(need ? 1 : 0)) {
-        if (i < nsub) {
-            over_out[i] = over_in[i];
-            dirty_out[i] = 0;
-        }
-        return;
-    }
-    for (int k = threadIdx.x; k < (1 << kHdLutBits); k += blockDim.x) slut[k] = t.lut[k];
+    const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t i = base + k;
+    const bool in = k < count && i < nsub;
+    const uint8_t prev_round = static_cast<uint8_t>((round - 1) & 0xff);
+    const bool need = in && (round == 1 || (i > 0 && stamp[i - 1] == prev_round));
+    if (!__syncthreads_or(need ? 1 : 0)) return;   // nothing to decode in this CTA: skip the table load as well
+    for (int j = threadIdx.x; j < (1 << kHdLutBits); j += blockDim.x) slut[j] = t.lut[j];
     __syncthreads();
-    if (i >= nsub) return;
-    if (!need) {
-        over_out[i] = over_in[i];
-        dirty_out[i] = 0;
-        return;
-    }
-    uint64_t pos = i * kSubBits + (i ? over_in[i - 1] : 0);
+    if (!need) return;
+    uint64_t pos = i * kSubBits + (i ? over[i - 1] : 0);
     uint64_t limit = (i + 1) * kSubBits;
     if (limit > total_bits) limit = total_bits;
     unsigned cnt = 0;
@@ -125,13 +120,16 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restri
             cnt++;
         }
     }
-    const uint64_t over = pos > (i + 1) * kSubBits ? pos - (i + 1) * kSubBits : 0;
-    const uint8_t o = static_cast<uint8_t>(over > 255 ? 255 : over);
+    const uint64_t ov = pos > (i + 1) * kSubBits ? pos - (i + 1) * kSubBits : 0;
+    const uint8_t o = static_cast<uint8_t>(ov > 255 ? 255 : ov);
     counts[i] = cnt;
-    over_out[i] = o;
-    const bool moved = o != over_in[i];   // thread i+1 started from over_in[i] in this round
-    dirty_out[i] = moved ? 1 : 0;
-    if (moved) *changed = 1u;
+    if (o != over[i]) {
+        over[i] = o;
+        stamp[i] = static_cast<uint8_t>(round & 0xff);
+        moved[0] = 1ull;
+        atomicMin(&moved[1], static_cast<unsigned long long>(i));
+        atomicMax(&moved[2], static_cast<unsigned long long>(i));
+    }
 }
 
 template <class QT>
@@ -162,13 +160,13 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_write(const uint32_t *__restr
 // ---------------------------------------------------------------------------------------------------------------------
 uint64_t hd_num_sub(uint64_t total_bits) { return (total_bits + kSubBits - 1) / kSubBits; }
 
-void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over_in,
-                    uint8_t *over_out, const uint8_t *dirty_in, uint8_t *dirty_out, bool first_round, unsigned *counts,
-                    unsigned *changed, cudaStream_t st) {
+void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, uint8_t *over, uint8_t *stamp, int round,
+                    uint64_t base, uint64_t count, unsigned *counts, unsigned long long *moved, cudaStream_t st) {
     const uint64_t nsub = hd_num_sub(total_bits);
+    if (count == 0) return;
     HdTables t{tb.lut, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
-    k_hd_sync<<<static_cast<unsigned>((nsub + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(
-        words, total_bits, nsub, t, over_in, over_out, dirty_in, dirty_out, first_round ? 1 : 0, counts, changed);
+    k_hd_sync<<<static_cast<unsigned>((count + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, total_bits, nsub, t, over,
+                                                                                              stamp, round, base, count, counts, moved);
 }
 
 template <class QT>

@@ -109,9 +109,8 @@ struct HdDeviceTables {
     int offset;
 };
 uint64_t hd_num_sub(uint64_t total_bits);
-void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over_in,
-                    uint8_t *over_out, const uint8_t *dirty_in, uint8_t *dirty_out, bool first_round, unsigned *counts,
-                    unsigned *changed, cudaStream_t st);
+void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, uint8_t *over, uint8_t *stamp, int round,
+                    uint64_t base, uint64_t count, unsigned *counts, unsigned long long *moved, cudaStream_t st);
 template <class QT>
 void launch_hd_write(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over,
                      const unsigned long long *offs, uint64_t n, QT *out, cudaStream_t st);

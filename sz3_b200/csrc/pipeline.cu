@@ -1611,28 +1611,34 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     SZ3B_CUDA(cudaMemsetAsync(d_bits + enc_len / 4 * 4, 0, padded - enc_len / 4 * 4, ws.st));
     ws.h2d(d_bits, bits, enc_len);
     const uint64_t nsub = hd_num_sub(total_bits);
-    uint8_t *d_over = ws.hd_over.as<uint8_t>(4 * (nsub + 8));   // overshoots and "start moved" flags, ping-pong
+    uint8_t *d_over = ws.hd_over.as<uint8_t>(2 * (nsub + 8));   // overshoots, and the round each one last moved in
     unsigned *d_counts = ws.hd_counts.as<unsigned>(nsub + 2);
     unsigned long long *d_offs = ws.hd_offs.as<unsigned long long>(2 * (nsub + 2));
-    unsigned *d_changed = reinterpret_cast<unsigned *>(ws.counters.as<unsigned long long>(2));
-    SZ3B_CUDA(cudaMemsetAsync(d_over, 0, 4 * (nsub + 8), ws.st));
+    unsigned long long *d_moved = ws.counters.as<unsigned long long>(4);
+    SZ3B_CUDA(cudaMemsetAsync(d_over, 0, 2 * (nsub + 8), ws.st));
     HdDeviceTables tb{d_lut, d_L, d_R, d_C, d_leaf, dec.offset};
-    uint8_t *in = d_over, *out = d_over + (nsub + 8);
-    uint8_t *dirty_in = d_over + 2 * (nsub + 8), *dirty_out = d_over + 3 * (nsub + 8);
+    uint8_t *in = d_over, *stamp = d_over + (nsub + 8);
     int launches = 0;
     bool converged = false;
+    uint64_t base = 0, count = nsub;
     // every round makes at least the first not yet exact subsequence exact, so nsub rounds always suffice
-    for (uint64_t it = 0; it <= nsub + 1 && !converged; it++) {
-        SZ3B_CUDA(cudaMemsetAsync(d_changed, 0, sizeof(unsigned), ws.st));
-        launch_hd_sync(reinterpret_cast<const uint32_t *>(d_bits), total_bits, tb, in, out, dirty_in, dirty_out, it == 0, d_counts,
-                       d_changed, ws.st);
+    for (uint64_t round = 1; round <= nsub + 1 && !converged; round++) {
+        // {flag, lowest index, highest index} of what moves in this round; read back through pinned memory (a
+        // pageable readback costs more than the round itself once the rounds get small)
+        SZ3B_CUDA(cudaMemsetAsync(d_moved, 0, 3 * sizeof(unsigned long long), ws.st));
+        SZ3B_CUDA(cudaMemsetAsync(d_moved + 1, 0xff, sizeof(unsigned long long), ws.st));
+        launch_hd_sync(reinterpret_cast<const uint32_t *>(d_bits), total_bits, tb, in, stamp, static_cast<int>(round & 0x7fffffff), base,
+                       count, d_counts, d_moved, ws.st);
         launches++;
-        unsigned changed = 0;
-        ws.d2h(&changed, d_changed, sizeof(unsigned));
+        unsigned long long *moved = static_cast<unsigned long long *>(ws.hist_host.ensure(64));
+        ws.d2h(moved, d_moved, 3 * sizeof(unsigned long long));
         SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-        converged = changed == 0;
-        std::swap(in, out);   // the overshoots just written are the next round's starts (and the final ones)
-        std::swap(dirty_in, dirty_out);
+        converged = moved[0] == 0;
+        if (!converged) {   // next round: the successors of what moved
+            base = moved[1] + 1;
+            count = std::min<uint64_t>(moved[2] - moved[1] + 1, nsub > base ? nsub - base : 0);
+            if (count == 0) converged = true;   // only the last subsequence moved: nobody starts after it
+        }
     }
     if (!converged) fail(SZ3B_E_RUNTIME, "Huffman stream did not self-synchronise (malformed stream?)");
     if (getenv("SZ3B_VERBOSE")) fprintf(stderr, "[sz3b] huffman decode: %d synchronisation rounds over %llu subsequences\n", launches,
