@@ -63,6 +63,7 @@ struct BwArgs {
     // first point) << 16 | row-major rank inside the block; diag_start[d] .. diag_start[d + 1] = diagonal d
     const uint32_t *diag_tab;
     const uint16_t *diag_start;
+    const uint32_t *diag_idx;    // same order: the point's in-block index, 8 bits per dimension (dimension d at bits 8d)
     // BW_SERIAL (row-major walk with the coefficient chain inline): chain outputs, dense over the selected blocks
     QuantParams q_liner, q_indep;
     int32_t *coef_q;
@@ -157,7 +158,7 @@ template <class T, class QT>
 SZ_HD void bw_geometry(const BwArgs<T, QT> &A, const uint32_t bi[kMaxDim], BwGeom &g) {
     const BlockShape &bs = A.bs;
     const int N = bs.N;
-    uint64_t extprod = 1, tail = bs.num;
+    uint64_t extprod = 1;
     g.b = 0;
     g.pos0 = 0;
     g.wbase = 0;
@@ -171,8 +172,7 @@ SZ_HD void bw_geometry(const BwArgs<T, QT> &A, const uint32_t bi[kMaxDim], BwGeo
         g.lo[d] = bi[d] * bs.B;
         g.ext[d] = bs.dims[d] - g.lo[d] < bs.B ? bs.dims[d] - g.lo[d] : bs.B;
         g.b = g.b * bs.nb[d] + bi[d];
-        tail /= bs.dims[d];
-        g.pos0 += extprod * g.lo[d] * tail;   // same closed form as reg_locate (blockwise.cuh)
+        g.pos0 += extprod * g.lo[d] * bs.stride[d];   // closed form of reg_locate (blockwise.cuh); stride = trailing extent product
         extprod *= g.ext[d];
         g.wbase += static_cast<uint64_t>(g.lo[d]) * A.pstride[d];
         g.obase += static_cast<uint64_t>(g.lo[d]) * bs.stride[d];
@@ -326,13 +326,23 @@ SZ_HD void bw_process_block(const BwArgs<T, QT> &A, const uint32_t bi[kMaxDim], 
                 coef = A.c_rec + static_cast<uint64_t>(A.rank[g.b]) * nc;
             for (int d = 0; d < nc; d++) cf[d] = coef[d];
         }
-        for (uint32_t e = lane; e < g.npts; e += nl) {
+        bool fullr = A.diag_tab != nullptr;
+        for (int d = 0; d < N; d++) fullr = fullr && g.ext[d] == bs.B;
+        for (uint32_t it = lane; it < g.npts; it += nl) {
             uint32_t idx[kMaxDim] = {0, 0, 0, 0};
-            uint32_t r = e, off = t00;
-            for (int d = N - 1; d >= 0; d--) {
-                idx[d] = r % g.ext[d];
-                r /= g.ext[d];
-                off += idx[d] * g.ts[d];
+            uint32_t e = it, off = t00;
+            if (fullr) {   // table order (any order is fine here: the points of a regression block are independent)
+                const uint32_t te = A.diag_tab[it], pk = A.diag_idx[it];
+                off += te >> 16;
+                e = te & 0xffffu;
+                for (int d = 0; d < N; d++) idx[d] = (pk >> (8 * d)) & 0xffu;
+            } else {
+                uint32_t r = it;
+                for (int d = N - 1; d >= 0; d--) {
+                    idx[d] = r % g.ext[d];
+                    r /= g.ext[d];
+                    off += idx[d] * g.ts[d];
+                }
             }
             const T pred = reg_predict<T>(N, cf, idx);
             if (A.mode == BW_DECODE) {
@@ -398,15 +408,28 @@ SZ_HD void bw_process_block(const BwArgs<T, QT> &A, const uint32_t bi[kMaxDim], 
     }
     SZ_WARP_SYNC();
     // ---- 4. the block's reconstruction goes back to the working array (halo of the blocks of later fronts)
+    bool fullw = A.diag_tab != nullptr;
+    for (int d = 0; d < N; d++) fullw = fullw && g.ext[d] == bs.B;
     for (uint32_t e = lane; e < g.npts; e += nl) {
-        uint32_t r = e, off = t00;
+        uint32_t off = t00;
         uint64_t w = g.wbase, o = g.obase;
-        for (int d = N - 1; d >= 0; d--) {
-            const uint32_t i = r % g.ext[d];
-            r /= g.ext[d];
-            off += i * g.ts[d];
-            w += static_cast<uint64_t>(i + kBwPad) * A.pstride[d];
-            o += static_cast<uint64_t>(i) * bs.stride[d];
+        if (fullw) {
+            const uint32_t pk = A.diag_idx[e];
+            off += A.diag_tab[e] >> 16;
+            for (int d = 0; d < N; d++) {
+                const uint32_t i = (pk >> (8 * d)) & 0xffu;
+                w += static_cast<uint64_t>(i + kBwPad) * A.pstride[d];
+                o += static_cast<uint64_t>(i) * bs.stride[d];
+            }
+        } else {
+            uint32_t r = e;
+            for (int d = N - 1; d >= 0; d--) {
+                const uint32_t i = r % g.ext[d];
+                r /= g.ext[d];
+                off += i * g.ts[d];
+                w += static_cast<uint64_t>(i + kBwPad) * A.pstride[d];
+                o += static_cast<uint64_t>(i) * bs.stride[d];
+            }
         }
         const T v = tile[off];
         A.W[w] = v;
@@ -417,13 +440,13 @@ SZ_HD void bw_process_block(const BwArgs<T, QT> &A, const uint32_t bi[kMaxDim], 
 
 // Diagonal table of a full block (see BwArgs::diag_tab).  tab: B^N entries, start: N * (B - 1) + 2 entries.  Returns
 // false when the offsets do not fit the 16-bit fields (the generic enumeration is used then).
-SZ_HD bool bw_build_diag_table(int N, uint32_t B, uint32_t *tab, uint16_t *start) {
+SZ_HD bool bw_build_diag_table(int N, uint32_t B, uint32_t *tab, uint16_t *start, uint32_t *idx_tab) {
     uint64_t npts = 1, tile = 1;
     for (int d = 0; d < N; d++) {
         npts *= B;
         tile *= B + kBwPad;
     }
-    if (npts > 0xffffu || tile > 0xffffu) return false;
+    if (npts > 0xffffu || tile > 0xffffu || B > 255u) return false;
     uint32_t ts[kMaxDim] = {0, 0, 0, 0};
     uint32_t acc = 1;
     for (int d = N - 1; d >= 0; d--) {
@@ -435,14 +458,18 @@ SZ_HD bool bw_build_diag_table(int N, uint32_t B, uint32_t *tab, uint16_t *start
     for (uint32_t diag = 0; diag < ndiag; diag++) {
         start[diag] = static_cast<uint16_t>(at);
         for (uint32_t e = 0; e < npts; e++) {   // row-major order inside a diagonal
-            uint32_t r = e, s = 0, off = 0;
+            uint32_t r = e, s = 0, off = 0, packed = 0;
             for (int d = N - 1; d >= 0; d--) {
                 const uint32_t i = r % B;
                 r /= B;
                 s += i;
                 off += i * ts[d];
+                packed |= i << (8 * d);
             }
-            if (s == diag) tab[at++] = (off << 16) | e;
+            if (s == diag) {
+                idx_tab[at] = packed;
+                tab[at++] = (off << 16) | e;
+            }
         }
     }
     start[ndiag] = static_cast<uint16_t>(at);

@@ -998,15 +998,17 @@ static void bw_upload_diag_table(Workspace &ws, BwArgs<T, QT> &A) {
     for (int d = 0; d < N; d++) npts *= B;
     if (npts > 0xffffu) return;
     const uint32_t nstart = static_cast<uint32_t>(N) * (B - 1) + 2;
-    std::vector<uint32_t> tab(npts);
+    std::vector<uint32_t> tab(npts), idx(npts);
     std::vector<uint16_t> start(nstart + 1);
-    if (!bw_build_diag_table(N, B, tab.data(), start.data())) return;
-    uint8_t *d = ws.tables.as<uint8_t>(npts * 4 + nstart * 2 + 64);
+    if (!bw_build_diag_table(N, B, tab.data(), start.data(), idx.data())) return;
+    uint8_t *d = ws.tables.as<uint8_t>(npts * 8 + nstart * 2 + 64);
     ws.h2d(d, tab.data(), npts * 4);
-    ws.h2d(d + npts * 4, start.data(), nstart * 2);
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // tab / start are locals
+    ws.h2d(d + npts * 4, idx.data(), npts * 4);
+    ws.h2d(d + npts * 8, start.data(), nstart * 2);
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // tab / idx / start are locals
     A.diag_tab = reinterpret_cast<const uint32_t *>(d);
-    A.diag_start = reinterpret_cast<const uint16_t *>(d + npts * 4);
+    A.diag_idx = reinterpret_cast<const uint32_t *>(d + npts * 4);
+    A.diag_start = reinterpret_cast<const uint16_t *>(d + npts * 8);
 }
 
 // lorenzo_compress_test (SZAlgoInterp.hpp:78-119): every sampled block through BlockwiseDecomposition with the composed

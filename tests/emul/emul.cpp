@@ -327,11 +327,12 @@ static int run_lorenzo(const sz3b_config &c, double eb, const T *data, int32_t *
     if (c.regression) A.kinds[A.nk++] = PK_REG;
     A.b_lo = 0;
     A.b_hi = bs.nblocks;
-    std::vector<uint32_t> dtab(65536);
+    std::vector<uint32_t> dtab(65536), didx(65536);
     std::vector<uint16_t> dstart(N * (bs.B - 1) + 2);
-    if (!getenv("EMUL_NO_DIAGTAB") && bw_build_diag_table(N, bs.B, dtab.data(), dstart.data())) {
+    if (!getenv("EMUL_NO_DIAGTAB") && bw_build_diag_table(N, bs.B, dtab.data(), dstart.data(), didx.data())) {
         A.diag_tab = dtab.data();
         A.diag_start = dstart.data();
+        A.diag_idx = didx.data();
     }
     const bool has_reg = c.regression != 0 && A.nk > 1;
     const int reg_sid = A.nk - 1;
