@@ -12,8 +12,8 @@
 //               only at a fixed point, which is therefore the true one).  2-3 iterations in practice; a stretch where
 //               the wrong phase happens to decode consistently (e.g. a run of one 2-bit codeword whose shifted reading
 //               is another codeword) needs one round per subsequence of the stretch, so after the first round only the
-//               subsequences whose start moved are decoded again (the launch covers just their index range) and the
-//               loop runs until nothing moves.
+//               subsequences whose start moved are decoded again (a work list: the launch has one thread per moved
+//               predecessor) and the loop runs until nothing moves.
 //   (scan)      exclusive prefix sum of the symbol counts -> output offsets (encode_kernels.cu: k_pack_scan)
 //   k_hd_write  same decode, symbols written at their offsets, clipped to the stream's symbol count.
 //
@@ -87,25 +87,26 @@ __device__ __forceinline__ uint32_t hd_symbol(BitReader &br, const uint32_t *slu
     return node;
 }
 
-// One synchronisation round over the subsequences [base, base + count).  `over` is updated in place and `stamp[i]`
-// remembers (mod 256) the round in which over[i] last moved: subsequence i is decoded again in round r only if its
-// start moved in round r - 1.  A reader may see its predecessor's overshoot of this or of the previous round; either
-// way the predecessor's stamp makes it run again in the next round, so the loop can only stop at the fixed point.  The
-// host restricts the next round to the successors of the subsequences that moved (moved[1..2] = their index range).
+// One synchronisation round.  Round 1 (list_in == nullptr) decodes every subsequence; later rounds decode the
+// successors of the subsequences whose overshoot moved in the previous round (list_in, n_in entries).  `over` is updated
+// in place: a reader may see its predecessor's overshoot of this or of the previous round, but a predecessor that moves
+// is listed, so its successor runs again in the next round and the loop can only stop at the fixed point.
 __global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restrict__ words, uint64_t total_bits, uint64_t nsub,
-                                                       HdTables t, uint8_t *over, uint8_t *stamp, int round, uint64_t base,
-                                                       uint64_t count, unsigned *__restrict__ counts,
-                                                       unsigned long long *__restrict__ moved) {
+                                                       HdTables t, uint8_t *over, const uint32_t *__restrict__ list_in,
+                                                       uint64_t n_in, uint32_t *__restrict__ list_out,
+                                                       unsigned *__restrict__ counts, unsigned long long *__restrict__ n_out) {
     __shared__ uint32_t slut[1 << kHdLutBits];
-    const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const uint64_t i = base + k;
-    const bool in = k < count && i < nsub;
-    const uint8_t prev_round = static_cast<uint8_t>((round - 1) & 0xff);
-    const bool need = in && (round == 1 || (i > 0 && stamp[i - 1] == prev_round));
-    if (!__syncthreads_or(need ? 1 : 0)) return;   // nothing to decode in this CTA: skip the table load as well
     for (int j = threadIdx.x; j < (1 << kHdLutBits); j += blockDim.x) slut[j] = t.lut[j];
     __syncthreads();
-    if (!need) return;
+    const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint64_t i;
+    if (list_in) {
+        if (k >= n_in) return;
+        i = static_cast<uint64_t>(list_in[k]) + 1;
+    } else {
+        i = k;
+    }
+    if (i >= nsub) return;
     uint64_t pos = i * kSubBits + (i ? over[i - 1] : 0);
     uint64_t limit = (i + 1) * kSubBits;
     if (limit > total_bits) limit = total_bits;
@@ -125,10 +126,7 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restri
     counts[i] = cnt;
     if (o != over[i]) {
         over[i] = o;
-        stamp[i] = static_cast<uint8_t>(round & 0xff);
-        moved[0] = 1ull;
-        atomicMin(&moved[1], static_cast<unsigned long long>(i));
-        atomicMax(&moved[2], static_cast<unsigned long long>(i));
+        list_out[atomicAdd(n_out, 1ull)] = static_cast<uint32_t>(i);
     }
 }
 
@@ -160,13 +158,14 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_write(const uint32_t *__restr
 // ---------------------------------------------------------------------------------------------------------------------
 uint64_t hd_num_sub(uint64_t total_bits) { return (total_bits + kSubBits - 1) / kSubBits; }
 
-void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, uint8_t *over, uint8_t *stamp, int round,
-                    uint64_t base, uint64_t count, unsigned *counts, unsigned long long *moved, cudaStream_t st) {
+void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, uint8_t *over, const uint32_t *list_in,
+                    uint64_t n_in, uint32_t *list_out, unsigned *counts, unsigned long long *n_out, cudaStream_t st) {
     const uint64_t nsub = hd_num_sub(total_bits);
-    if (count == 0) return;
+    const uint64_t nthreads = list_in ? n_in : nsub;
+    if (nthreads == 0) return;
     HdTables t{tb.lut, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
-    k_hd_sync<<<static_cast<unsigned>((count + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, total_bits, nsub, t, over,
-                                                                                              stamp, round, base, count, counts, moved);
+    k_hd_sync<<<static_cast<unsigned>((nthreads + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, total_bits, nsub, t, over,
+                                                                                                 list_in, n_in, list_out, counts, n_out);
 }
 
 template <class QT>

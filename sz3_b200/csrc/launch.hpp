@@ -109,8 +109,8 @@ struct HdDeviceTables {
     int offset;
 };
 uint64_t hd_num_sub(uint64_t total_bits);
-void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, uint8_t *over, uint8_t *stamp, int round,
-                    uint64_t base, uint64_t count, unsigned *counts, unsigned long long *moved, cudaStream_t st);
+void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, uint8_t *over, const uint32_t *list_in,
+                    uint64_t n_in, uint32_t *list_out, unsigned *counts, unsigned long long *n_out, cudaStream_t st);
 template <class QT>
 void launch_hd_write(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over,
                      const unsigned long long *offs, uint64_t n, QT *out, cudaStream_t st);

@@ -70,8 +70,7 @@ __global__ void __launch_bounds__(32) k_bw_serial(BwArgs<T, QT> A, uint64_t b_lo
 // from the front.  Only blocks whose row-major index lies in [A.b_lo, A.b_hi) are processed (window of the selection
 // iteration).  N == 1 has a single CTA that walks all fronts (the 1-D Lorenzo recurrence is serial).
 template <class T, class QT>
-__global__ void __launch_bounds__(32) k_bw_front(BwArgs<T, QT> A, uint32_t f0, uint32_t f1, uint32_t lead_lo, uint32_t tile_cap,
-                                                 uint32_t tab_off) {
+__global__ void __launch_bounds__(32) k_bw_front(BwArgs<T, QT> A, uint32_t f0, uint32_t f1, uint32_t lead_lo, uint32_t tile_cap) {
     extern __shared__ __align__(16) unsigned char bw_smem[];
     T *tile = reinterpret_cast<T *>(bw_smem);
     T *est = tile + tile_cap;
@@ -87,24 +86,6 @@ __global__ void __launch_bounds__(32) k_bw_front(BwArgs<T, QT> A, uint32_t f0, u
     if (f1 == f0 + 1) {   // one front per launch: most CTAs of a launch have no block on it
         const uint64_t b = static_cast<uint64_t>(lead) * A.bs.nb[N - 1] + (f0 - s);
         if (f0 < s || f0 - s >= A.bs.nb[N - 1] || b < A.b_lo || b >= A.b_hi) return;
-    }
-    if (A.diag_tab) {
-        // the per-diagonal point table is read once per diagonal, each time on the block's critical path: keep it in
-        // shared memory (the copy overlaps the tile load of the first block)
-        uint32_t npts = 1;
-        for (int d = 0; d < N; d++) npts *= A.bs.B;
-        const uint32_t nstart = static_cast<uint32_t>(N) * (A.bs.B - 1) + 2;
-        uint32_t *s_tab = reinterpret_cast<uint32_t *>(bw_smem + tab_off);
-        uint32_t *s_idx = s_tab + npts;
-        uint16_t *s_start = reinterpret_cast<uint16_t *>(s_idx + npts);
-        for (uint32_t i = threadIdx.x; i < npts; i += blockDim.x) {
-            s_tab[i] = A.diag_tab[i];
-            s_idx[i] = A.diag_idx[i];
-        }
-        for (uint32_t i = threadIdx.x; i < nstart; i += blockDim.x) s_start[i] = A.diag_start[i];
-        A.diag_tab = s_tab;
-        A.diag_idx = s_idx;
-        A.diag_start = s_start;
     }
     if (blockIdx.y) {   // batch member: same shape, own working array / index range / selection
         A.W += static_cast<uint64_t>(blockIdx.y) * A.w_bstride;
@@ -238,14 +219,9 @@ const char *launch_bw_fronts(const BwArgs<T, QT> &A, cudaStream_t st, int *launc
     for (int d = 0; d < N - 1; d++) nlead *= bs.nb[d];
     if (nlead > 0x7fffffffull) return "block grid exceeds the launch grid of the Lorenzo kernel";
     const size_t tile_cap = bw_tile_cap(bs);
-    const size_t tab_off = (bw_scratch_elems(bs, A.nk) * sizeof(T) + 15) & ~static_cast<size_t>(15);
-    size_t tab_bytes = 0;
-    if (A.diag_tab) {
-        size_t npts = 1;
-        for (int d = 0; d < N; d++) npts *= bs.B;
-        tab_bytes = npts * 8 + (static_cast<size_t>(N) * (bs.B - 1) + 2) * 2 + 16;
-    }
-    const size_t smem = tab_off + tab_bytes;
+    // (the per-diagonal tables of BwArgs stay in global memory: a few hundred bytes shared by every block, L1 hits;
+    //  staging them per CTA costs more than it saves, one block per CTA)
+    const size_t smem = bw_scratch_elems(bs, A.nk) * sizeof(T);
     if (smem > 200 * 1024) return "blockSize too large for the shared-memory tile of the Lorenzo kernel";
     static thread_local size_t attr_set = 0;
     if (smem > 48 * 1024 && smem > attr_set) {
@@ -280,13 +256,12 @@ const char *launch_bw_fronts(const BwArgs<T, QT> &A, cudaStream_t st, int *launc
     const unsigned nbatch = A.nbatch ? A.nbatch : 1u;
     if (N == 1) {
         // the 1-D recurrence is serial point by point: one thread walks the blocks (a warp would only add barriers)
-        k_bw_front<T, QT><<<dim3(1, nbatch), 1, smem, st>>>(A, f_min, f_max + 1, 0, static_cast<uint32_t>(tile_cap),
-                                                            static_cast<uint32_t>(tab_off));
+        k_bw_front<T, QT><<<dim3(1, nbatch), 1, smem, st>>>(A, f_min, f_max + 1, 0, static_cast<uint32_t>(tile_cap));
         *launches += 1;
     } else {
         for (uint32_t f = f_min; f <= f_max; f++)
             k_bw_front<T, QT><<<dim3(grid, nbatch), 32, smem, st>>>(A, f, f + 1, static_cast<uint32_t>(lead_lo),
-                                                                    static_cast<uint32_t>(tile_cap), static_cast<uint32_t>(tab_off));
+                                                                    static_cast<uint32_t>(tile_cap));
         *launches += static_cast<int>(f_max - f_min + 1);
     }
     return nullptr;

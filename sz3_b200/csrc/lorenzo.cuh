@@ -257,14 +257,25 @@ SZ_HD void bw_process_block(const BwArgs<T, QT> &A, const uint32_t bi[kMaxDim], 
                 est[item] = e;
             }
             SZ_WARP_SYNC();
-            double best = 0;
-            for (int k = 0; k < A.nk; k++) {
+            // double sums in sample order (ComposedPredictor.hpp:31-33); with a warp, lane k sums predictor k
+            double best = 0, mine = 0;
+            const int k_lo = nl > 1 ? lane : 0, k_hi = nl > 1 ? lane + 1 : A.nk;
+            double errs[3] = {0, 0, 0};
+            for (int k = k_lo; k < k_hi && k < A.nk; k++) {
                 double err = 0;
                 if (A.kinds[k] == PK_REG && !reg_ok) {
                     err = DBL_MAX;
                 } else {
                     for (uint32_t p = 0; p < P; p++) err += static_cast<double>(est[k * P + p]);
                 }
+                errs[k < 3 ? k : 0] = err;
+                mine = err;
+            }
+            for (int k = 0; k < A.nk; k++) {
+                double err = errs[k];
+#if defined(__CUDA_ARCH__)
+                if (nl > 1) err = __shfl_sync(0xffffffffu, mine, k);
+#endif
                 if (k == 0 || err < best) {   // std::min_element: the first minimum wins
                     best = err;
                     sid = k;

@@ -1613,34 +1613,33 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     SZ3B_CUDA(cudaMemsetAsync(d_bits + enc_len / 4 * 4, 0, padded - enc_len / 4 * 4, ws.st));
     ws.h2d(d_bits, bits, enc_len);
     const uint64_t nsub = hd_num_sub(total_bits);
-    uint8_t *d_over = ws.hd_over.as<uint8_t>(2 * (nsub + 8));   // overshoots, and the round each one last moved in
+    if (nsub >= 0xfffffff0ull) fail(SZ3B_E_UNSUPPORTED, "Huffman stream above 2^42 bits");
+    // overshoots (1 byte each), then two work lists of subsequence indices (ping-pong)
+    const size_t over_bytes = (nsub + 8 + 15) & ~static_cast<size_t>(15);
+    uint8_t *d_over = ws.hd_over.as<uint8_t>(over_bytes + 2 * (nsub + 1) * sizeof(uint32_t));
+    uint32_t *list_a = reinterpret_cast<uint32_t *>(d_over + over_bytes), *list_b = list_a + nsub + 1;
     unsigned *d_counts = ws.hd_counts.as<unsigned>(nsub + 2);
     unsigned long long *d_offs = ws.hd_offs.as<unsigned long long>(2 * (nsub + 2));
     unsigned long long *d_moved = ws.counters.as<unsigned long long>(4);
-    SZ3B_CUDA(cudaMemsetAsync(d_over, 0, 2 * (nsub + 8), ws.st));
+    SZ3B_CUDA(cudaMemsetAsync(d_over, 0, over_bytes, ws.st));
     HdDeviceTables tb{d_lut, d_L, d_R, d_C, d_leaf, dec.offset};
-    uint8_t *in = d_over, *stamp = d_over + (nsub + 8);
+    uint8_t *in = d_over;
     int launches = 0;
     bool converged = false;
-    uint64_t base = 0, count = nsub;
+    unsigned long long n_in = 0;
     // every round makes at least the first not yet exact subsequence exact, so nsub rounds always suffice
     for (uint64_t round = 1; round <= nsub + 1 && !converged; round++) {
-        // {flag, lowest index, highest index} of what moves in this round; read back through pinned memory (a
-        // pageable readback costs more than the round itself once the rounds get small)
-        SZ3B_CUDA(cudaMemsetAsync(d_moved, 0, 3 * sizeof(unsigned long long), ws.st));
-        SZ3B_CUDA(cudaMemsetAsync(d_moved + 1, 0xff, sizeof(unsigned long long), ws.st));
-        launch_hd_sync(reinterpret_cast<const uint32_t *>(d_bits), total_bits, tb, in, stamp, static_cast<int>(round & 0x7fffffff), base,
-                       count, d_counts, d_moved, ws.st);
+        SZ3B_CUDA(cudaMemsetAsync(d_moved, 0, sizeof(unsigned long long), ws.st));
+        launch_hd_sync(reinterpret_cast<const uint32_t *>(d_bits), total_bits, tb, in, round == 1 ? nullptr : list_a, n_in, list_b,
+                       d_counts, d_moved, ws.st);
         launches++;
+        // read back through pinned memory (a pageable readback costs more than a late round itself)
         unsigned long long *moved = static_cast<unsigned long long *>(ws.hist_host.ensure(64));
-        ws.d2h(moved, d_moved, 3 * sizeof(unsigned long long));
+        ws.d2h(moved, d_moved, sizeof(unsigned long long));
         SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-        converged = moved[0] == 0;
-        if (!converged) {   // next round: the successors of what moved
-            base = moved[1] + 1;
-            count = std::min<uint64_t>(moved[2] - moved[1] + 1, nsub > base ? nsub - base : 0);
-            if (count == 0) converged = true;   // only the last subsequence moved: nobody starts after it
-        }
+        n_in = moved[0];
+        converged = n_in == 0;
+        std::swap(list_a, list_b);   // what moved in this round feeds the next one
     }
     if (!converged) fail(SZ3B_E_RUNTIME, "Huffman stream did not self-synchronise (malformed stream?)");
     if (getenv("SZ3B_VERBOSE")) fprintf(stderr, "[sz3b] huffman decode: %d synchronisation rounds over %llu subsequences\n", launches,
