@@ -69,11 +69,24 @@ __global__ void __launch_bounds__(32) k_bw_serial(BwArgs<T, QT> A, uint64_t b_lo
 // One CTA (one warp) per tuple of leading block coordinates (lead_lo + blockIdx.x); the last block coordinate follows
 // from the front.  Only blocks whose row-major index lies in [A.b_lo, A.b_hi) are processed (window of the selection
 // iteration).  N == 1 has a single CTA that walks all fronts (the 1-D Lorenzo recurrence is serial).
-template <class T, class QT>
-__global__ void __launch_bounds__(32) k_bw_front(BwArgs<T, QT> A, uint32_t f0, uint32_t f1, uint32_t lead_lo, uint32_t tile_cap) {
+// BATCH: the tuner's sampled blocks (blockIdx.y = batch member).  Kept out of the plain instantiation because offsetting
+// the pointers needs a writable copy of the argument block, which then lives in local memory instead of the constant bank.
+template <class T, class QT, bool BATCH>
+__global__ void __launch_bounds__(32) k_bw_front(const BwArgs<T, QT> A0, uint32_t f0, uint32_t f1, uint32_t lead_lo,
+                                                 uint32_t tile_cap) {
     extern __shared__ __align__(16) unsigned char bw_smem[];
     T *tile = reinterpret_cast<T *>(bw_smem);
     T *est = tile + tile_cap;
+    BwArgs<T, QT> Ab;
+    if (BATCH) {   // same shape, own working array / index range / selection
+        Ab = A0;
+        Ab.W += static_cast<uint64_t>(blockIdx.y) * Ab.w_bstride;
+        Ab.q += static_cast<uint64_t>(blockIdx.y) * Ab.q_bstride;
+        Ab.unpred_tmp += static_cast<uint64_t>(blockIdx.y) * Ab.q_bstride;
+        if (Ab.sel_out) Ab.sel_out += static_cast<uint64_t>(blockIdx.y) * Ab.sel_bstride;
+        if (Ab.sel_in) Ab.sel_in += static_cast<uint64_t>(blockIdx.y) * Ab.sel_bstride;
+    }
+    const BwArgs<T, QT> &A = BATCH ? Ab : A0;
     const int N = A.bs.N;
     uint32_t bi[kMaxDim] = {0, 0, 0, 0};
     const uint32_t lead = blockIdx.x + lead_lo;
@@ -86,13 +99,6 @@ __global__ void __launch_bounds__(32) k_bw_front(BwArgs<T, QT> A, uint32_t f0, u
     if (f1 == f0 + 1) {   // one front per launch: most CTAs of a launch have no block on it
         const uint64_t b = static_cast<uint64_t>(lead) * A.bs.nb[N - 1] + (f0 - s);
         if (f0 < s || f0 - s >= A.bs.nb[N - 1] || b < A.b_lo || b >= A.b_hi) return;
-    }
-    if (blockIdx.y) {   // batch member: same shape, own working array / index range / selection
-        A.W += static_cast<uint64_t>(blockIdx.y) * A.w_bstride;
-        A.q += static_cast<uint64_t>(blockIdx.y) * A.q_bstride;
-        A.unpred_tmp += static_cast<uint64_t>(blockIdx.y) * A.q_bstride;
-        if (A.sel_out) A.sel_out += static_cast<uint64_t>(blockIdx.y) * A.sel_bstride;
-        if (A.sel_in) A.sel_in += static_cast<uint64_t>(blockIdx.y) * A.sel_bstride;
     }
     const uint64_t row_base = static_cast<uint64_t>(lead) * A.bs.nb[N - 1];
     for (uint32_t f = f0; f < f1; f++) {
@@ -225,7 +231,8 @@ const char *launch_bw_fronts(const BwArgs<T, QT> &A, cudaStream_t st, int *launc
     if (smem > 200 * 1024) return "blockSize too large for the shared-memory tile of the Lorenzo kernel";
     static thread_local size_t attr_set = 0;
     if (smem > 48 * 1024 && smem > attr_set) {
-        if (cudaFuncSetAttribute(k_bw_front<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_bw_front<T, QT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(k_bw_front<T, QT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return "cannot raise the dynamic shared memory limit";
         attr_set = 200 * 1024;
     }
@@ -254,14 +261,21 @@ const char *launch_bw_fronts(const BwArgs<T, QT> &A, cudaStream_t st, int *launc
     }
     const unsigned grid = static_cast<unsigned>(lead_hi - lead_lo + 1);
     const unsigned nbatch = A.nbatch ? A.nbatch : 1u;
+    const uint32_t tc = static_cast<uint32_t>(tile_cap), ll = static_cast<uint32_t>(lead_lo);
     if (N == 1) {
         // the 1-D recurrence is serial point by point: one thread walks the blocks (a warp would only add barriers)
-        k_bw_front<T, QT><<<dim3(1, nbatch), 1, smem, st>>>(A, f_min, f_max + 1, 0, static_cast<uint32_t>(tile_cap));
+        if (nbatch > 1)
+            k_bw_front<T, QT, true><<<dim3(1, nbatch), 1, smem, st>>>(A, f_min, f_max + 1, 0, tc);
+        else
+            k_bw_front<T, QT, false><<<1, 1, smem, st>>>(A, f_min, f_max + 1, 0, tc);
         *launches += 1;
     } else {
-        for (uint32_t f = f_min; f <= f_max; f++)
-            k_bw_front<T, QT><<<dim3(grid, nbatch), 32, smem, st>>>(A, f, f + 1, static_cast<uint32_t>(lead_lo),
-                                                                    static_cast<uint32_t>(tile_cap));
+        for (uint32_t f = f_min; f <= f_max; f++) {
+            if (nbatch > 1)
+                k_bw_front<T, QT, true><<<dim3(grid, nbatch), 32, smem, st>>>(A, f, f + 1, ll, tc);
+            else
+                k_bw_front<T, QT, false><<<grid, 32, smem, st>>>(A, f, f + 1, ll, tc);
+        }
         *launches += static_cast<int>(f_max - f_min + 1);
     }
     return nullptr;
