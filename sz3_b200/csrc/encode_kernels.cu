@@ -139,9 +139,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_count(const QT *__restric
     }
 }
 
-// single CTA; off arrays get nchunks+1 entries (last = total).  Every thread owns kScanPer consecutive chunks per
-// sweep, so a sweep of the CTA covers 1024 * kScanPer chunks between barriers.
-constexpr int kScanPer = 8;
+// single CTA; off arrays get nchunks+1 entries (last = total)
 __global__ void __launch_bounds__(1024) k_pack_scan(const unsigned *__restrict__ chunk_bits,
                                                     const unsigned *__restrict__ chunk_zeros, uint64_t nchunks,
                                                     unsigned long long *__restrict__ bit_off,
@@ -151,17 +149,9 @@ __global__ void __launch_bounds__(1024) k_pack_scan(const unsigned *__restrict__
     if (threadIdx.x == 0) carry[0] = carry[1] = 0;
     __syncthreads();
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (uint64_t base = 0; base < nchunks; base += 1024 * kScanPer) {
-        const uint64_t i0 = base + static_cast<uint64_t>(threadIdx.x) * kScanPer;
-        unsigned vb[kScanPer], vz[kScanPer];
-        unsigned long long v[2] = {0, 0};
-#pragma unroll
-        for (int k = 0; k < kScanPer; k++) {
-            vb[k] = i0 + k < nchunks ? chunk_bits[i0 + k] : 0u;
-            vz[k] = i0 + k < nchunks ? chunk_zeros[i0 + k] : 0u;
-            v[0] += vb[k];
-            v[1] += vz[k];
-        }
+    for (uint64_t base = 0; base < nchunks; base += 1024) {
+        uint64_t i = base + threadIdx.x;
+        unsigned long long v[2] = {i < nchunks ? chunk_bits[i] : 0ull, i < nchunks ? chunk_zeros[i] : 0ull};
         unsigned long long inc[2] = {v[0], v[1]};
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long t0 = __shfl_up_sync(0xffffffffu, inc[0], o);
@@ -178,34 +168,29 @@ __global__ void __launch_bounds__(1024) k_pack_scan(const unsigned *__restrict__
         __syncthreads();
         if (wid == 0) {
             unsigned long long w0 = wsum[0][lane], w1 = wsum[1][lane];
-            unsigned long long s0 = w0, s1 = w1;
+            unsigned long long i0 = w0, i1 = w1;
             for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long t0 = __shfl_up_sync(0xffffffffu, s0, o);
-                unsigned long long t1 = __shfl_up_sync(0xffffffffu, s1, o);
+                unsigned long long t0 = __shfl_up_sync(0xffffffffu, i0, o);
+                unsigned long long t1 = __shfl_up_sync(0xffffffffu, i1, o);
                 if (lane >= static_cast<unsigned>(o)) {
-                    s0 += t0;
-                    s1 += t1;
+                    i0 += t0;
+                    i1 += t1;
                 }
             }
-            wsum[0][lane] = s0 - w0;
-            wsum[1][lane] = s1 - w1;
+            wsum[0][lane] = i0 - w0;
+            wsum[1][lane] = i1 - w1;
         }
         __syncthreads();
         unsigned long long e0 = carry[0] + wsum[0][wid] + inc[0] - v[0];
         unsigned long long e1 = carry[1] + wsum[1][wid] + inc[1] - v[1];
-#pragma unroll
-        for (int k = 0; k < kScanPer; k++) {
-            if (i0 + k < nchunks) {
-                bit_off[i0 + k] = e0;
-                zero_off[i0 + k] = e1;
-            }
-            e0 += vb[k];
-            e1 += vz[k];
+        if (i < nchunks) {
+            bit_off[i] = e0;
+            zero_off[i] = e1;
         }
         __syncthreads();
         if (threadIdx.x == 1023) {
-            carry[0] = e0;
-            carry[1] = e1;
+            carry[0] = e0 + v[0];
+            carry[1] = e1 + v[1];
         }
         __syncthreads();
     }
