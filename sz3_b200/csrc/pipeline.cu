@@ -124,10 +124,11 @@ static const T *to_device_planes(Workspace &ws, const T *data, const sz3b_config
     const size_t nz = conf.dims[0], plane = num / nz * sizeof(T);
     uint8_t *dst = reinterpret_cast<uint8_t *>(d);
     const uint8_t *src = reinterpret_cast<const uint8_t *>(data);
-    // even planes, a few at a time so that other traffic can slip in between commands
+    // even planes, 32 per command (measured: 2-D copies of 8 planes lose 1 % of the link rate, of 32 none; the
+    // tuner's small uploads do not queue behind them, they go through the SM copy path while this is in flight)
     const size_t n_even = (nz + 1) / 2;
-    for (size_t k = 0; k < n_even; k += 8) {
-        const size_t cnt = std::min<size_t>(8, n_even - k);
+    for (size_t k = 0; k < n_even; k += 32) {
+        const size_t cnt = std::min<size_t>(32, n_even - k);
         SZ3B_CUDA(cudaMemcpy2DAsync(dst + 2 * k * plane, 2 * plane, src + 2 * k * plane, 2 * plane, plane, cnt,
                                     cudaMemcpyHostToDevice, ws.st_copy));
     }
