@@ -500,6 +500,59 @@ static void deliver_d2h(Workspace &ws, uint8_t *dst, const uint8_t *d_src, size_
         host_parallel(j.parts, copy_part, &j);
 }
 
+// d_src[0, len) -> dst (host) as zhuf frames; returns their size.  The stream is coded in up to four slices of whole
+// frames: every slice's kernels are queued at once, and while slice j + 1 is being coded the frames of slice j cross
+// PCIe on the copy stream (straight into `dst` when it is pinned; otherwise one slice and a staged copy).
+static size_t zhuf_run(Workspace &ws, const uint8_t *d_src, size_t len, uint8_t *dst, size_t cap) {
+    const uint64_t nblocks = zhuf_num_blocks(len);
+    ZhufBlockInfo *d_info = ws.zinfo.as<ZhufBlockInfo>(nblocks + 1);
+    uint8_t *d_out = ws.zdst.as<uint8_t>(zhuf_bound(len));
+    unsigned long long *d_total = ws.counters.as<unsigned long long>(4) + 3;
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const uint64_t nframes = (nblocks + kZhufBlocksPerFrame - 1) / kZhufBlocksPerFrame;
+    const int nslices = pinned && nframes >= 16 ? 4 : 1;
+    unsigned long long *h_log = static_cast<unsigned long long *>(ws.hist_host.ensure(64));
+    cudaEvent_t ev[4];
+    size_t h = ws.stage_begin("lossless_gpu");
+    SZ3B_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), ws.st));
+    for (int j = 0; j < nslices; j++) {
+        const uint64_t f0 = nframes * j / nslices, f1 = nframes * (j + 1) / nslices;
+        const uint64_t g0 = f0 * kZhufBlocksPerFrame, g1 = std::min<uint64_t>(f1 * kZhufBlocksPerFrame, nblocks);
+        launch_zhuf(d_src, len, g0, g1, d_info, d_out, d_total, d_total - 1, ws.st);
+        SZ3B_CUDA(cudaMemcpyAsync(h_log + j, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ws.st));
+        ev[j] = ws.event();
+        SZ3B_CUDA(cudaEventRecord(ev[j], ws.st));
+    }
+    ws.stage_end(h, 3 * nslices);
+    ws.d2h_bytes += sizeof(unsigned long long) * nslices;
+    double t0 = now_ms();
+    unsigned long long done = 0;
+    bool small = false;
+    for (int j = 0; j < nslices; j++) {
+        SZ3B_CUDA(cudaEventSynchronize(ev[j]));
+        const unsigned long long end = h_log[j];
+        if (end > zhuf_bound(len) || end < done) fail(SZ3B_E_RUNTIME, "GPU lossless stage produced an invalid size");
+        if (end > cap) {
+            small = true;
+            break;
+        }
+        if (nslices > 1) {
+            SZ3B_CUDA(cudaMemcpyAsync(dst + done, d_out + done, end - done, cudaMemcpyDeviceToHost, ws.st_copy));
+            ws.d2h_bytes += end - done;
+        }
+        done = end;
+    }
+    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    if (nslices > 1) SZ3B_CUDA(cudaStreamSynchronize(ws.st_copy));
+    SZ3B_CUDA(cudaGetLastError());
+    if (small) throw TooSmall{};
+    if (nslices == 1 && done) deliver_d2h(ws, dst, d_out, done);
+    ws.host_stage("d2h_compressed", now_ms() - t0);
+    return done;
+}
+
 // stage-level entry (sz3b_lossless_compress): any byte buffer through the GPU lossless stage
 size_t lossless_gpu_stage(Workspace &ws, const uint8_t *src, size_t len, int loc, uint8_t *out, size_t cap) {
     if (cap < sizeof(uint64_t) + zhuf_bound(len)) fail(SZ3B_E_INVALID_ARGUMENT, "output buffer too small");
@@ -510,21 +563,14 @@ size_t lossless_gpu_stage(Workspace &ws, const uint8_t *src, size_t len, int loc
         ws.h2d_bytes += len;
         d_src = d;
     }
-    const uint64_t nblocks = zhuf_num_blocks(len);
-    ZhufBlockInfo *d_info = ws.zinfo.as<ZhufBlockInfo>(nblocks + 1);
-    uint8_t *d_out = ws.zdst.as<uint8_t>(zhuf_bound(len));
-    unsigned long long *d_total = ws.counters.as<unsigned long long>(4) + 3;
-    size_t h = ws.stage_begin("lossless_gpu");
-    launch_zhuf(d_src, len, d_info, d_out, d_total, ws.st);
-    ws.stage_end(h, 3);
-    unsigned long long csize = 0;
-    ws.d2h(&csize, d_total, sizeof(csize));
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-    SZ3B_CUDA(cudaGetLastError());
-    if (csize > zhuf_bound(len)) fail(SZ3B_E_RUNTIME, "GPU lossless stage produced an invalid size");
     uint8_t *p = out;
     put<uint64_t>(p, static_cast<uint64_t>(len));
-    if (csize) deliver_d2h(ws, p, d_out, csize);
+    size_t csize = 0;
+    try {
+        csize = zhuf_run(ws, d_src, len, p, cap - sizeof(uint64_t));
+    } catch (TooSmall &) {
+        fail(SZ3B_E_INVALID_ARGUMENT, "output buffer too small");
+    }
     return sizeof(uint64_t) + csize;
 }
 
@@ -534,7 +580,7 @@ static size_t zhuf_stage(Workspace &ws, const uint8_t *decomp_hdr, size_t decomp
     const size_t total = stream_len<T>(decomp_hdr_len, lay);
     // the reference's capacity rule (Lossless_zstd.hpp:30-33 -> std::length_error), independent of the policy
     if (cap < sizeof(uint64_t) || cap - sizeof(uint64_t) < ZSTD_compressBound(total)) throw TooSmall{};
-    size_t h = ws.stage_begin("lossless_gpu");
+    size_t h = ws.stage_begin("lossless_assemble");
     uint8_t *d_src = ws.zsrc.as<uint8_t>(total + 64);
     // small host-built pieces go up, the bulk (unpredictable values, packed bits) is already on the device
     size_t off = 0;
@@ -557,23 +603,11 @@ static size_t zhuf_stage(Workspace &ws, const uint8_t *decomp_hdr, size_t decomp
     off += mid.size();
     if (lay.out_size)
         SZ3B_CUDA(cudaMemcpyAsync(d_src + off, ws.out_words.p, lay.out_size, cudaMemcpyDeviceToDevice, ws.st));
-    const uint64_t nblocks = zhuf_num_blocks(total);
-    ZhufBlockInfo *d_info = ws.zinfo.as<ZhufBlockInfo>(nblocks + 1);
-    uint8_t *d_out = ws.zdst.as<uint8_t>(zhuf_bound(total));
-    unsigned long long *d_total = ws.counters.as<unsigned long long>(4) + 3;
-    launch_zhuf(d_src, total, d_info, d_out, d_total, ws.st);
-    ws.stage_end(h, 3);
-    unsigned long long csize = 0;
-    ws.d2h(&csize, d_total, sizeof(csize));
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-    SZ3B_CUDA(cudaGetLastError());
-    if (csize == 0 || csize > zhuf_bound(total)) fail(SZ3B_E_RUNTIME, "GPU lossless stage produced an invalid size");
-    if (sizeof(uint64_t) + csize > cap) throw TooSmall{};
-    double t0 = now_ms();
+    ws.stage_end(h, 0);
     uint8_t *p = dst;
     put<uint64_t>(p, static_cast<uint64_t>(total));
-    deliver_d2h(ws, p, d_out, csize);
-    ws.host_stage("d2h_compressed", now_ms() - t0);
+    const size_t csize = zhuf_run(ws, d_src, total, p, cap - sizeof(uint64_t));
+    if (csize == 0) fail(SZ3B_E_RUNTIME, "GPU lossless stage produced an invalid size");
     return sizeof(uint64_t) + csize;
 }
 

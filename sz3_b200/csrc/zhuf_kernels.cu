@@ -19,14 +19,14 @@ namespace sz3b {
 constexpr int kZhufThreads = 256;
 
 __global__ void __launch_bounds__(kZhufThreads) k_zhuf_build(const uint8_t *__restrict__ src, uint64_t len,
-                                                             ZhufBlockInfo *__restrict__ infos) {
+                                                             ZhufBlockInfo *__restrict__ infos, uint64_t g0) {
     __shared__ uint32_t hist[256];
     __shared__ uint8_t ss[256];
     __shared__ uint32_t sf[256];
     __shared__ ZhufScratch scratch;
     __shared__ ZhufBlockInfo info;
     __shared__ unsigned long long bits[4];
-    const uint64_t g = blockIdx.x;
+    const uint64_t g = g0 + blockIdx.x;
     const uint32_t bl = zhuf_block_len(len, g);
     const uint8_t *p = src + g * kZhufBlock;
     const int tid = threadIdx.x;
@@ -106,18 +106,21 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_build(const uint8_t *__re
     for (uint32_t i = tid; i < sizeof(ZhufBlockInfo) / 4; i += kZhufThreads) dst[i] = sp[i];
 }
 
-__global__ void __launch_bounds__(1024) k_zhuf_scan(ZhufBlockInfo *__restrict__ infos, uint64_t len, uint64_t nblocks,
-                                                    unsigned long long *__restrict__ total_out) {
+// Blocks [g0, g1): coded / raw decision and output offsets, continuing from *total (the bytes of the blocks before g0);
+// *total is advanced and a copy is left in total_log[0] for the host (which learns the byte range of this slice from it).
+__global__ void __launch_bounds__(1024) k_zhuf_scan(ZhufBlockInfo *__restrict__ infos, uint64_t len, uint64_t g0, uint64_t g1,
+                                                    unsigned long long *__restrict__ total,
+                                                    unsigned long long *__restrict__ total_log) {
     __shared__ unsigned long long warp_sum[32];
     __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
+    if (threadIdx.x == 0) carry_s = *total;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (uint64_t start = 0; start < nblocks; start += 1024) {
+    for (uint64_t start = g0; start < g1; start += 1024) {
         const uint64_t g = start + threadIdx.x;
         unsigned long long v = 0, pre = 0;
         bool coded = false;
-        if (g < nblocks) {
+        if (g < g1) {
             const uint32_t payload = zhuf_block_payload(zhuf_block_len(len, g), infos[g], &coded);
             pre = g % kZhufBlocksPerFrame == 0 ? kZhufFrameHeader : 0;
             v = pre + 3 + payload;
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(1024) k_zhuf_scan(ZhufBlockInfo *__restrict__ 
         __syncthreads();
         const unsigned long long carry = carry_s;
         const unsigned long long before = carry + (wid ? warp_sum[wid - 1] : 0ull) + x - v;
-        if (g < nblocks) {
+        if (g < g1) {
             infos[g].coded = coded ? 1u : 0u;
             infos[g].off = before + pre;
         }
@@ -148,18 +151,21 @@ __global__ void __launch_bounds__(1024) k_zhuf_scan(ZhufBlockInfo *__restrict__ 
         if (threadIdx.x == 0) carry_s = carry + warp_sum[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total_out = carry_s;
+    if (threadIdx.x == 0) {
+        *total = carry_s;
+        *total_log = carry_s;
+    }
 }
 
 constexpr uint32_t kZhufBufWords = (kZhufBlock / 4 * kZhufMaxBits + 31) / 32 + 2;   // bits of one stream + closing bit
 
 __global__ void __launch_bounds__(kZhufThreads) k_zhuf_encode(const uint8_t *__restrict__ src, uint64_t len,
                                                               const ZhufBlockInfo *__restrict__ infos,
-                                                              uint8_t *__restrict__ out) {
+                                                              uint8_t *__restrict__ out, uint64_t g0) {
     __shared__ uint32_t sym_s[256];
     __shared__ uint32_t buf[kZhufBufWords];
     __shared__ uint32_t warp_sum[kZhufThreads / 32];
-    const uint64_t g = blockIdx.x >> 2;
+    const uint64_t g = g0 + (blockIdx.x >> 2);
     const int s = blockIdx.x & 3;
     const int tid = threadIdx.x;
     const ZhufBlockInfo &bi = infos[g];
@@ -267,17 +273,16 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_encode(const uint8_t *__r
     for (uint32_t i = head + nwords * 4 + tid; i < sb; i += kZhufThreads) dst[i] = bb[i];
 }
 
-// Compresses src[0, len) (device) into out (device, zhuf_bound(len) bytes); *total (device) receives the size.
-void launch_zhuf(const uint8_t *src, uint64_t len, ZhufBlockInfo *infos, uint8_t *out, unsigned long long *total,
-                 cudaStream_t st) {
-    const uint64_t nblocks = zhuf_num_blocks(len);
-    if (nblocks == 0) {
-        cudaMemsetAsync(total, 0, sizeof(unsigned long long), st);
-        return;
-    }
-    k_zhuf_build<<<static_cast<unsigned>(nblocks), kZhufThreads, 0, st>>>(src, len, infos);
-    k_zhuf_scan<<<1, 1024, 0, st>>>(infos, len, nblocks, total);
-    k_zhuf_encode<<<static_cast<unsigned>(nblocks * 4), kZhufThreads, 0, st>>>(src, len, infos, out);
+// Compresses the blocks [g0, g1) of src[0, len) (device) into out (device, zhuf_bound(len) bytes).  *total (device)
+// must hold the bytes produced for the blocks before g0 (0 for the first slice) and receives the new running total,
+// which is also left in *total_log.  Slices must start on frame boundaries (multiples of kZhufBlocksPerFrame).
+void launch_zhuf(const uint8_t *src, uint64_t len, uint64_t g0, uint64_t g1, ZhufBlockInfo *infos, uint8_t *out,
+                 unsigned long long *total, unsigned long long *total_log, cudaStream_t st) {
+    if (g1 <= g0) return;
+    const uint64_t nb = g1 - g0;
+    k_zhuf_build<<<static_cast<unsigned>(nb), kZhufThreads, 0, st>>>(src, len, infos, g0);
+    k_zhuf_scan<<<1, 1024, 0, st>>>(infos, len, g0, g1, total, total_log);
+    k_zhuf_encode<<<static_cast<unsigned>(nb * 4), kZhufThreads, 0, st>>>(src, len, infos, out, g0);
 }
 
 }  // namespace sz3b
