@@ -97,8 +97,9 @@ void launch_scan_chunks(const unsigned *chunk_bits, const unsigned *chunk_zeros,
 
 // zhuf_kernels.cu: the GPU lossless stage (zstd frames of Huffman-only literal blocks, zhuf.cuh)
 struct ZhufBlockInfo;
-void launch_zhuf(const uint8_t *src, uint64_t len, uint64_t g0, uint64_t g1, ZhufBlockInfo *infos, uint8_t *out,
-                 unsigned long long *total, unsigned long long *total_log, cudaStream_t st);
+void launch_zhuf_build(const uint8_t *src, uint64_t len, ZhufBlockInfo *infos, cudaStream_t st);
+void launch_zhuf_emit(const uint8_t *src, uint64_t len, uint64_t g0, uint64_t g1, ZhufBlockInfo *infos, uint8_t *out,
+                      unsigned long long *total, unsigned long long *total_log, cudaStream_t st);
 
 // huffman_decode.cu
 struct HdDeviceTables {

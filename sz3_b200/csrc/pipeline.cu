@@ -500,9 +500,10 @@ static void deliver_d2h(Workspace &ws, uint8_t *dst, const uint8_t *d_src, size_
         host_parallel(j.parts, copy_part, &j);
 }
 
-// d_src[0, len) -> dst (host) as zhuf frames; returns their size.  The stream is coded in up to four slices of whole
-// frames: every slice's kernels are queued at once, and while slice j + 1 is being coded the frames of slice j cross
-// PCIe on the copy stream (straight into `dst` when it is pinned; otherwise one slice and a staged copy).
+// d_src[0, len) -> dst (host) as zhuf frames; returns their size.  The tables of all blocks are built by one launch
+// (its time is one block's latency); offsets and bit streams then follow in up to four slices of whole frames, all
+// queued at once, and while slice j + 1 is being written the frames of slice j cross PCIe on the copy stream (straight
+// into `dst` when it is pinned; otherwise one slice and a staged copy).
 static size_t zhuf_run(Workspace &ws, const uint8_t *d_src, size_t len, uint8_t *dst, size_t cap) {
     const uint64_t nblocks = zhuf_num_blocks(len);
     ZhufBlockInfo *d_info = ws.zinfo.as<ZhufBlockInfo>(nblocks + 1);
@@ -517,15 +518,16 @@ static size_t zhuf_run(Workspace &ws, const uint8_t *d_src, size_t len, uint8_t 
     cudaEvent_t ev[4];
     size_t h = ws.stage_begin("lossless_gpu");
     SZ3B_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), ws.st));
+    launch_zhuf_build(d_src, len, d_info, ws.st);
     for (int j = 0; j < nslices; j++) {
         const uint64_t f0 = nframes * j / nslices, f1 = nframes * (j + 1) / nslices;
         const uint64_t g0 = f0 * kZhufBlocksPerFrame, g1 = std::min<uint64_t>(f1 * kZhufBlocksPerFrame, nblocks);
-        launch_zhuf(d_src, len, g0, g1, d_info, d_out, d_total, d_total - 1, ws.st);
+        launch_zhuf_emit(d_src, len, g0, g1, d_info, d_out, d_total, d_total - 1, ws.st);
         SZ3B_CUDA(cudaMemcpyAsync(h_log + j, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ws.st));
         ev[j] = ws.event();
         SZ3B_CUDA(cudaEventRecord(ev[j], ws.st));
     }
-    ws.stage_end(h, 3 * nslices);
+    ws.stage_end(h, 1 + 2 * nslices);
     ws.d2h_bytes += sizeof(unsigned long long) * nslices;
     double t0 = now_ms();
     unsigned long long done = 0;

@@ -273,16 +273,21 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_encode(const uint8_t *__r
     for (uint32_t i = head + nwords * 4 + tid; i < sb; i += kZhufThreads) dst[i] = bb[i];
 }
 
-// Compresses the blocks [g0, g1) of src[0, len) (device) into out (device, zhuf_bound(len) bytes).  *total (device)
-// must hold the bytes produced for the blocks before g0 (0 for the first slice) and receives the new running total,
-// which is also left in *total_log.  Slices must start on frame boundaries (multiples of kZhufBlocksPerFrame).
-void launch_zhuf(const uint8_t *src, uint64_t len, uint64_t g0, uint64_t g1, ZhufBlockInfo *infos, uint8_t *out,
-                 unsigned long long *total, unsigned long long *total_log, cudaStream_t st) {
+// Tables and stream sizes of every block of src[0, len) (device).  One launch for the whole stream: the kernel's time
+// is the latency of one block's table construction, whatever the number of blocks.
+void launch_zhuf_build(const uint8_t *src, uint64_t len, ZhufBlockInfo *infos, cudaStream_t st) {
+    const uint64_t nblocks = zhuf_num_blocks(len);
+    if (nblocks) k_zhuf_build<<<static_cast<unsigned>(nblocks), kZhufThreads, 0, st>>>(src, len, infos, 0);
+}
+
+// Offsets and frames of the blocks [g0, g1) into out (device, zhuf_bound(len) bytes).  *total (device) must hold the
+// bytes produced for the blocks before g0 (0 for the first slice) and receives the new running total, which is also
+// left in *total_log.  Slices must start on frame boundaries (multiples of kZhufBlocksPerFrame).
+void launch_zhuf_emit(const uint8_t *src, uint64_t len, uint64_t g0, uint64_t g1, ZhufBlockInfo *infos, uint8_t *out,
+                      unsigned long long *total, unsigned long long *total_log, cudaStream_t st) {
     if (g1 <= g0) return;
-    const uint64_t nb = g1 - g0;
-    k_zhuf_build<<<static_cast<unsigned>(nb), kZhufThreads, 0, st>>>(src, len, infos, g0);
     k_zhuf_scan<<<1, 1024, 0, st>>>(infos, len, g0, g1, total, total_log);
-    k_zhuf_encode<<<static_cast<unsigned>(nb * 4), kZhufThreads, 0, st>>>(src, len, infos, out, g0);
+    k_zhuf_encode<<<static_cast<unsigned>((g1 - g0) * 4), kZhufThreads, 0, st>>>(src, len, infos, out, g0);
 }
 
 }  // namespace sz3b
