@@ -522,13 +522,13 @@ static size_t zhuf_run(Workspace &ws, const uint8_t *d_src, size_t len, uint8_t 
     for (int j = 0; j < nslices; j++) {
         const uint64_t f0 = nframes * j / nslices, f1 = nframes * (j + 1) / nslices;
         const uint64_t g0 = f0 * kZhufBlocksPerFrame, g1 = std::min<uint64_t>(f1 * kZhufBlocksPerFrame, nblocks);
-        launch_zhuf_emit(d_src, len, g0, g1, d_info, d_out, d_total, d_total - 1, ws.st);
-        SZ3B_CUDA(cudaMemcpyAsync(h_log + j, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ws.st));
+        // the running total goes straight into pinned (device-mapped) host memory: a copy command would queue behind
+        // the previous slice's frames on the D2H engine
+        launch_zhuf_emit(d_src, len, g0, g1, d_info, d_out, d_total, h_log + j, ws.st);
         ev[j] = ws.event();
         SZ3B_CUDA(cudaEventRecord(ev[j], ws.st));
     }
     ws.stage_end(h, 1 + 2 * nslices);
-    ws.d2h_bytes += sizeof(unsigned long long) * nslices;
     double t0 = now_ms();
     unsigned long long done = 0;
     bool small = false;

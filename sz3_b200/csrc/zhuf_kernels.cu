@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(1024) k_zhuf_scan(ZhufBlockInfo *__restrict__ 
     }
     if (threadIdx.x == 0) {
         *total = carry_s;
-        *total_log = carry_s;
+        *total_log = carry_s;   // may be mapped host memory: the host reads it after the event that follows the slice
+        __threadfence_system();
     }
 }
 
