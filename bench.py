@@ -404,7 +404,15 @@ def _merge(stages):
 
 if __name__ == "__main__":
     a = parse()
+    # The contract is ONE JSON line on stdout.  Libraries underneath also write there at the C level (NCCL prints its
+    # version line, the reference printf()s "OpenMP enabled for compression ..."): send file descriptor 1 to stderr for
+    # the duration of the run and give Python's stdout the original descriptor back, so that only print() reaches it.
+    sys.stdout.flush()
+    _real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real, "w", buffering=1)
     if a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
+    sys.stdout.flush()
