@@ -18,28 +18,32 @@ struct Node {
 // 1-indexed binary min-heap of node ids keyed by freq, with the reference's exact sift rules
 // (HuffmanEncoder.hpp:440-470): ties keep insertion-dependent order, which fixes the tree shape.
 struct Heap {
-    std::vector<int> a;
+    struct Item {
+        uint64_t f;   // the node's frequency, kept next to its id: the sift loops then touch one array only
+        int id;
+    };
+    std::vector<Item> a;
     const std::vector<Node> *nodes;
     explicit Heap(const std::vector<Node> *n, size_t cap) : a(cap + 2), nodes(n) {}
     int end = 1;
-    uint64_t f(int id) const { return (*nodes)[id].freq; }
     void push(int id) {
+        const uint64_t fid = (*nodes)[id].freq;
         int i = end++;
         for (int j; (j = i >> 1) != 0; i = j) {
-            if (f(a[j]) <= f(id)) break;
+            if (a[j].f <= fid) break;
             a[i] = a[j];
         }
-        a[i] = id;
+        a[i] = Item{fid, id};
     }
     int pop() {
         if (end < 2) return -1;
-        int top = a[1];
+        const int top = a[1].id;
         end--;
         a[1] = a[end];
         int i = 1, l;
         while ((l = i << 1) < end) {
-            if (l + 1 < end && f(a[l + 1]) < f(a[l])) l++;
-            if (f(a[i]) > f(a[l])) {
+            if (l + 1 < end && a[l + 1].f < a[l].f) l++;
+            if (a[i].f > a[l].f) {
                 std::swap(a[i], a[l]);
                 i = l;
             } else {
@@ -113,7 +117,7 @@ bool huffman_build(const unsigned long long *hist, size_t nbins, int sym_base, H
         nodes.push_back(nd);
         heap.push(static_cast<int>(nodes.size()) - 1);
     }
-    const int root = heap.a[1];
+    const int root = heap.a[1].id;
     book.node_count = static_cast<uint32_t>(2 * distinct - 1);
 
     // pre-order walk: assigns the serialisation ids of pad_tree and the codes of build_code in one pass
