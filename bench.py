@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--edge", type=int, default=EDGE, help="cube edge (default 512 = the metric's configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-threads", type=int, default=None, help="host threads per rank (default: this rank's share of the cores)")
+    ap.add_argument("--host-wait", type=int, default=None, help="0 = spin while waiting for the device, 1 = poll and yield")
     ap.add_argument("--lossless-policy", type=int, default=None, help="0 = zstd on every chunk, 1 = adaptive (library default)")
     return ap.parse_args()
 
@@ -229,6 +231,13 @@ def run_ours(args):
     L.sz3b_last_error.restype = C.c_char_p
     if args.lossless_policy is not None:
         L.sz3b_set_lossless_policy(args.lossless_policy)
+    # one rank per GPU on one host: every rank gets its share of the cores (16 pool threads per rank on 2 cores per
+    # rank cost half of e2e; tests/gpu_cores.sh).  Waiting threads keep spinning: yielding measured slower.
+    cores = len(os.sched_getaffinity(0))
+    host_threads = args.host_threads if args.host_threads is not None else (max(2, cores // world) if world > 1 else 0)
+    host_wait = args.host_wait if args.host_wait is not None else 0
+    L.sz3b_set_host_threads(host_threads)
+    L.sz3b_set_host_wait(host_wait)
     edge = args.edge
     nbytes = edge ** 3 * 4
     host = slab_field(rank, edge)
@@ -361,6 +370,7 @@ def run_ours(args):
                        "field": "G3 (SURVEY.md 8d), seeded", "l2": "input 512 MiB per step > 126 MB L2 (no explicit flush)",
                        "lossless_policy": {0: "host zstd-3 on every chunk", 1: "adaptive host zstd: probes, raw zstd frames where zstd gains < 1 % (include/sz3b.h)",
                                            2: "GPU lossless stage: zstd frames of Huffman-only literal blocks, one table per 128 KiB (sz3_b200/csrc/zhuf.cuh); decodes with the unmodified reference"}[policy],
+                       "host": {"cores": cores, "threads_per_rank": host_threads or cores, "device_wait": ["spin", "yield"][host_wait]},
                        "value_path": "sz3b_compress, device-resident input, stream delivered to host",
                        "e2e_path": "sz3b_compress, pinned host input (H2D + D2H inside the timed region)"},
             "e2e": {"value": e2e, "unit": "GB/s", "h2d_bytes_per_step": h2d.value, "d2h_bytes_per_step": d2h.value,

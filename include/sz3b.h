@@ -145,8 +145,13 @@ int sz3b_device_count(void);
 int sz3b_last_profile(const char **names, double *ms, int *launches, int cap);
 /* Bytes the calling thread's last call moved host->device and device->host (cudaMemcpyAsync on the call's stream). */
 void sz3b_last_transfer(size_t *h2d_bytes, size_t *d2h_bytes);
-/* zstd worker threads for the host tail (0 = hardware concurrency). */
+/* Host threads the library may use: zstd workers of the host tail and concurrent tuner trials (0 = hardware
+ * concurrency).  With one rank per GPU on a shared host, give each rank its share of the cores. */
 void sz3b_set_host_threads(int n);
+/* How host threads wait for the device: 0 = the driver's wait (spins; lowest latency when cores are plentiful),
+ * 1 = poll and yield the core between polls (for hosts with more waiting threads than cores).  No reference
+ * counterpart (the reference has no device); initial value from the environment variable SZ3B_HOST_WAIT. */
+void sz3b_set_host_wait(int mode);
 /* Lossless stage over the packed (Huffman-coded) stream, lossless/Lossless_zstd.hpp:29-37.
  *   0 = every chunk through zstd level 3 on the host (the reference's call, frame by frame);
  *   1 = adaptive host zstd: every 8th 1-MiB chunk is compressed as a probe; if zstd gains < 1 % on the probes, the

@@ -233,5 +233,15 @@ class sz:
     def get_lossless_policy():
         return int(lib().sz3b_get_lossless_policy())
 
+    @staticmethod
+    def set_host_threads(n):
+        """Host threads the library may use (zstd workers, concurrent tuner trials); 0 = hardware concurrency."""
+        lib().sz3b_set_host_threads(int(n))
+
+    @staticmethod
+    def set_host_wait(mode):
+        """0 = host threads spin while they wait for the device (default), 1 = they poll and yield the core."""
+        lib().sz3b_set_host_wait(int(mode))
+
 
 __all__ = ["sz", "szConfig", "szErrorBoundMode", "szAlgorithm", "SZ3BError", "lib"]

@@ -63,8 +63,8 @@ Workspace *workspace_acquire() {
 
 void workspace_release(Workspace *ws) {
     // a call that failed half-way may still have its background copy / kernels in flight on this workspace's buffers
-    if (ws->st_copy) cudaStreamSynchronize(ws->st_copy);
-    if (ws->st) cudaStreamSynchronize(ws->st);
+    if (ws->st_copy) stream_wait(ws->st_copy);
+    if (ws->st) stream_wait(ws->st);
     cudaGetLastError();
     std::lock_guard<std::mutex> lk(g_pool_mu);
     g_pool.push_back(ws);
@@ -165,7 +165,7 @@ void minmax_stage(Workspace &ws, const T *data, int loc, size_t num, double *mn,
     ws.stage_end(h, 2);
     T hmm[2];
     ws.d2h(hmm, mm, sizeof(hmm));
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
     *mn = static_cast<double>(hmm[0]);
     *mx = static_cast<double>(hmm[1]);
 }
@@ -343,7 +343,7 @@ static void encode_indices(Workspace &ws, const QT *d_q, uint64_t n, const unsig
                            int sym_base, bool has_unpred, const T *d_unpred_tmp, HuffmanBook &book, EncodeLayout &lay) {
     unsigned long long *h_hist = static_cast<unsigned long long *>(ws.hist_host.ensure(sizeof(unsigned long long) * nbins));
     ws.d2h(h_hist, d_hist, sizeof(unsigned long long) * nbins);
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
     double t0 = now_ms();
     const char *err = nullptr;
     if (!huffman_build(h_hist, nbins, sym_base, book, &err))
@@ -387,7 +387,7 @@ struct ArrivalGate : ZstdReady {
     void wait(size_t need) override {
         size_t j = done.load(std::memory_order_acquire);
         while (j < upto.size() && (j == 0 ? 0 : upto[j - 1]) < need) {
-            cudaEventSynchronize(ev[j]);
+            event_wait(ev[j]);
             j++;
         }
         size_t cur = done.load(std::memory_order_relaxed);
@@ -446,7 +446,7 @@ static size_t zstd_stage(Workspace &ws, const uint8_t *src, size_t len, uint8_t 
     bool small = false;
     // gate != nullptr <=> the source is a packed (Huffman-coded) stream, not raw data
     size_t r = zstd_compress_framed(src, len, dst, cap, threads, &small, gate, &ws.zscratch, gate != nullptr);
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
     ws.host_stage("zstd_host", now_ms() - t0);
     if (small) throw TooSmall{};
     if (r == 0) fail(SZ3B_E_RUNTIME, "zstd compression failed");
@@ -487,12 +487,12 @@ static void deliver_d2h(Workspace &ws, uint8_t *dst, const uint8_t *d_src, size_
     cudaGetLastError();   // an unregistered pointer may leave an error behind on old drivers
     if (pinned) {
         ws.d2h(dst, d_src, bytes);
-        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        SZ3B_CUDA(stream_wait(ws.st));
         return;
     }
     uint8_t *stage = static_cast<uint8_t *>(ws.stage.ensure(bytes + 16));
     ws.d2h(stage, d_src, bytes);
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
     CopyJob j{dst, stage, bytes, std::max(1, std::min(host_threads(), 8))};
     if (bytes < (1u << 20))
         memcpy(dst, stage, bytes);
@@ -533,7 +533,7 @@ static size_t zhuf_run(Workspace &ws, const uint8_t *d_src, size_t len, uint8_t 
     unsigned long long done = 0;
     bool small = false;
     for (int j = 0; j < nslices; j++) {
-        SZ3B_CUDA(cudaEventSynchronize(ev[j]));
+        SZ3B_CUDA(event_wait(ev[j]));
         const unsigned long long end = h_log[j];
         if (end > zhuf_bound(len) || end < done) fail(SZ3B_E_RUNTIME, "GPU lossless stage produced an invalid size");
         if (end > cap) {
@@ -546,8 +546,8 @@ static size_t zhuf_run(Workspace &ws, const uint8_t *d_src, size_t len, uint8_t 
         }
         done = end;
     }
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
-    if (nslices > 1) SZ3B_CUDA(cudaStreamSynchronize(ws.st_copy));
+    SZ3B_CUDA(stream_wait(ws.st));
+    if (nslices > 1) SZ3B_CUDA(stream_wait(ws.st_copy));
     SZ3B_CUDA(cudaGetLastError());
     if (small) throw TooSmall{};
     if (nslices == 1 && done) deliver_d2h(ws, dst, d_out, done);
@@ -743,7 +743,7 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
         ws.stage_end(h, 1);
         std::vector<uint8_t> flags(ncand);
         ws.d2h(flags.data(), d_flags, ncand);
-        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        SZ3B_CUDA(stream_wait(ws.st));
         for (uint64_t b = 0; b < ncand; b++)
             if (flags[b]) filtered.push_back(b);
     }
@@ -778,7 +778,7 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
         size_t h = ws.stage_begin("tune_gather");
         launch_gather_cubes<T>(d_data, N, dims32, static_cast<uint32_t>(sbs + 1), d_starts, ncubes, d_cubes, ws.st);
         ws.stage_end(h, 1);
-        SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // `starts` must outlive the copy
+        SZ3B_CUDA(stream_wait(ws.st));   // `starts` must outlive the copy
     }
     std::vector<uint8_t> &trial_out = ws.trial_out;   // kept across calls (zero-filling megabytes per call costs a trial)
     {
@@ -808,28 +808,29 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
             int device;
             bool bulk;
             std::vector<std::exception_ptr> *errs;
-            size_t n;
-        } cx{&one, &ws, trial_out.data(), trial_cap, ws.device, ws.bulk_copy_in_flight, &errs, tcs.size()};
+            size_t n, workers;
+        } cx{&one, &ws, trial_out.data(), trial_cap, ws.device, ws.bulk_copy_in_flight, &errs, tcs.size(),
+             std::min<size_t>(tcs.size(), static_cast<size_t>(std::max(1, host_threads())))};
         auto task = [](void *arg, int worker) {
             Ctx &c = *static_cast<Ctx *>(arg);
-            const size_t k = static_cast<size_t>(worker);
-            if (k >= c.n) return;
-            try {
-                if (k == 0) {
-                    (*c.fn)(*c.main_ws, 0, c.main_out);
-                } else {
-                    SZ3B_CUDA(cudaSetDevice(c.device));
-                    WorkspaceLease w2;
-                    w2->bulk_copy_in_flight = c.bulk;
-                    if (w2->trial_out.size() < c.cap) w2->trial_out.resize(c.cap);
-                    (*c.fn)(*w2, k, w2->trial_out.data());
-                    w2->bulk_copy_in_flight = false;
+            for (size_t k = static_cast<size_t>(worker); k < c.n; k += c.workers) {
+                try {
+                    if (k == 0) {
+                        (*c.fn)(*c.main_ws, 0, c.main_out);
+                    } else {
+                        SZ3B_CUDA(cudaSetDevice(c.device));
+                        WorkspaceLease w2;
+                        w2->bulk_copy_in_flight = c.bulk;
+                        if (w2->trial_out.size() < c.cap) w2->trial_out.resize(c.cap);
+                        (*c.fn)(*w2, k, w2->trial_out.data());
+                        w2->bulk_copy_in_flight = false;
+                    }
+                } catch (...) {
+                    (*c.errs)[k] = std::current_exception();
                 }
-            } catch (...) {
-                (*c.errs)[k] = std::current_exception();
             }
         };
-        host_parallel(static_cast<int>(tcs.size()), task, &cx);
+        host_parallel(static_cast<int>(cx.workers), task, &cx);
         for (auto &e : errs)
             if (e) std::rethrow_exception(e);
         return ratios;
@@ -957,7 +958,7 @@ static void fetch_coef_unpred(Workspace &ws, unsigned long long n_unp, const uns
     std::vector<T> val(n_unp);
     ws.d2h(pos.data(), upos, n_unp * sizeof(unsigned long long));
     ws.d2h(val.data(), uval, n_unp * sizeof(T));
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
     for (unsigned long long i = 0; i < n_unp; i++)
         if (pos[i] < limit) out.emplace_back(pos[i], val[i]);
 }
@@ -1042,7 +1043,7 @@ static void bw_upload_diag_table(Workspace &ws, BwArgs<T, QT> &A) {
     ws.h2d(d, tab.data(), npts * 4);
     ws.h2d(d + npts * 4, idx.data(), npts * 4);
     ws.h2d(d + npts * 8, start.data(), nstart * 2);
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // tab / idx / start are locals
+    SZ3B_CUDA(stream_wait(ws.st));   // tab / idx / start are locals
     A.diag_tab = reinterpret_cast<const uint32_t *>(d);
     A.diag_idx = reinterpret_cast<const uint32_t *>(d + npts * 4);
     A.diag_start = reinterpret_cast<const uint16_t *>(d + npts * 8);
@@ -1214,7 +1215,7 @@ static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double
                 *launches += 1;
                 ws.d2h(&n_unp, counters + 1, sizeof(n_unp));
                 ws.d2h(&cnt, counters + 2, sizeof(cnt));
-                SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+                SZ3B_CUDA(stream_wait(ws.st));
                 SZ3B_CUDA(cudaGetLastError());
                 fetch_coef_unpred<T>(ws, n_unp, upos, uval, cnt * nc, unp);
                 nsel_lo = static_cast<uint32_t>(cnt);
@@ -1230,7 +1231,7 @@ static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double
             *launches += 2;
             ws.d2h(&cnt, counters + 2, sizeof(cnt));
             SZ3B_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ws.st));
-            SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+            SZ3B_CUDA(stream_wait(ws.st));
             const uint64_t at = static_cast<uint64_t>(nsel_lo) * nc;
             if (cnt) {
                 launch_reg_chain<T>(c_dense + at, nullptr, cnt, N, A.q_liner, A.q_indep, coef_q + at, c_rec + at, counters, upos,
@@ -1246,7 +1247,7 @@ static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double
             unsigned mm[2];
             ws.d2h(mm, d_mm, sizeof(mm));
             ws.d2h(&n_unp, counters + 1, sizeof(n_unp));
-            SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+            SZ3B_CUDA(stream_wait(ws.st));
             SZ3B_CUDA(cudaGetLastError());
             n_pass++;
             uint64_t boundary = b_hi;
@@ -1255,7 +1256,7 @@ static void run_blockwise_lorenzo(Workspace &ws, const sz3b_config &conf, double
                 boundary = mm[1];
                 ws.d2h(&nsel_after, rank + boundary, sizeof(nsel_after));
                 SZ3B_CUDA(cudaMemcpyAsync(selA + boundary, selB + boundary, b_hi - boundary, cudaMemcpyDeviceToDevice, ws.st));
-                SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+                SZ3B_CUDA(stream_wait(ws.st));
             }
             fetch_coef_unpred<T>(ws, n_unp, upos, uval, static_cast<unsigned long long>(nsel_after) * nc, unp);
             last_adv = boundary - b_lo;
@@ -1328,7 +1329,7 @@ static void run_blockwise(Workspace &ws, const sz3b_config &conf, double eb, con
     ws.stage_end(h, 1);
     unsigned long long hc[2];
     ws.d2h(hc, counters, sizeof(hc));
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
     SZ3B_CUDA(cudaGetLastError());
     *launches += 2;
     std::vector<std::pair<unsigned long long, T>> unp;
@@ -1411,7 +1412,7 @@ static void blockwise_decompose_t(Workspace &ws, const sz3b_config &conf, double
     const size_t at = blob.size();
     blob.resize(at + lay.n_unpred * sizeof(T));
     if (lay.n_unpred) ws.d2h(blob.data() + at, ws.unpred_out.p, lay.n_unpred * sizeof(T));
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
 }
 
 template <class T>
@@ -1435,7 +1436,7 @@ static size_t lossless_compress(Workspace &ws, const sz3b_config &conf, const T 
     if (loc == SZ3B_DEVICE) {
         uint8_t *h = static_cast<uint8_t *>(ws.stage.ensure(bytes));
         ws.d2h(h, data, bytes);
-        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        SZ3B_CUDA(stream_wait(ws.st));
         src = h;
     }
     try {
@@ -1673,7 +1674,7 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
         // read back through pinned memory (a pageable readback costs more than a late round itself)
         unsigned long long *moved = static_cast<unsigned long long *>(ws.hist_host.ensure(64));
         ws.d2h(moved, d_moved, sizeof(unsigned long long));
-        SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+        SZ3B_CUDA(stream_wait(ws.st));
         n_in = moved[0];
         converged = n_in == 0;
         std::swap(list_a, list_b);   // what moved in this round feeds the next one
@@ -1685,7 +1686,7 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     launch_scan_chunks(d_counts, d_counts, nsub, d_offs, d_offs + nsub + 2, ws.st);
     unsigned long long total = 0;
     ws.d2h(&total, d_offs + nsub, sizeof(total));
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
     if (total < n) fail(SZ3B_E_INVALID_ARGUMENT, "huffman: bitstream exhausted");
     launch_hd_write<QT>(reinterpret_cast<const uint32_t *>(d_bits), total_bits, tb, in, d_offs, n, d_q, ws.st);
     ws.stage_end(h, launches + 2);
@@ -1876,7 +1877,7 @@ static void blockwise_decompress_lorenzo(Workspace &ws, const sz3b_config &conf,
     A.mode = BW_DECODE;
     if (const char *e = launch_bw_fronts<T, QT>(A, ws.st, &launches)) fail(SZ3B_E_UNSUPPORTED, e);
     ws.stage_end(h, launches);
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // cq / cun / sel8 are host vectors
+    SZ3B_CUDA(stream_wait(ws.st));   // cq / cun / sel8 are host vectors
     SZ3B_CUDA(cudaGetLastError());
 }
 
@@ -1941,7 +1942,7 @@ static void blockwise_decompress_t(Workspace &ws, const sz3b_config &conf, Curso
     if (const char *e = launch_reg_recover<T, QT>(d_out, bs, d_crec, make_quant(eb, radius), d_q, d_tmp, ws.st))
         fail(SZ3B_E_UNSUPPORTED, e);
     ws.stage_end(h, launches + 2);
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));   // cq / cun are host vectors
+    SZ3B_CUDA(stream_wait(ws.st));   // cq / cun are host vectors
     SZ3B_CUDA(cudaGetLastError());
 }
 
@@ -1960,7 +1961,7 @@ static void decompress_one(Workspace &ws, const sz3b_config &conf, const uint8_t
         ws.host_stage("zstd_host", now_ms() - t0);
         if (loc == SZ3B_DEVICE) {
             ws.h2d(out, dst, bytes);
-            SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+            SZ3B_CUDA(stream_wait(ws.st));
         }
         return;
     }
@@ -1997,7 +1998,7 @@ static void decompress_one(Workspace &ws, const sz3b_config &conf, const uint8_t
         ws.d2h(out, d_out, bytes);
         ws.stage_end(h, 0);
     }
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
 }
 
 template <class T>
@@ -2063,7 +2064,7 @@ static void interp_decompose_t(Workspace &ws, const sz3b_config &conf, double eb
     memcpy(blob.data(), hdr, hdr_len);
     if (lay.n_unpred)
         ws.d2h(blob.data() + hdr_len, ws.unpred_out.p, lay.n_unpred * sizeof(T));
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
 }
 
 template <class T>
@@ -2086,7 +2087,7 @@ void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vec
     launch_minmax_int<int32_t>(d_q, n, d_mm, ws.st);
     int mm[2];
     ws.d2h(mm, d_mm, sizeof(mm));
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
     const int64_t span = static_cast<int64_t>(mm[1]) - mm[0] + 1;
     if (span > (1 << 26)) fail(SZ3B_E_UNSUPPORTED, "Huffman symbol range above 2^26");
     const int nbins = static_cast<int>(span);
@@ -2102,7 +2103,7 @@ void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vec
     uint8_t *p = out.data() + lay.tree_len;
     put<uint64_t>(p, lay.out_size);
     if (lay.out_size) ws.d2h(p, ws.out_words.p, lay.out_size);
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
     if (tree_len) *tree_len = lay.tree_len;
 }
 
@@ -2129,7 +2130,7 @@ void huffman_decode_stage(Workspace &ws, const uint8_t *in, size_t in_len, size_
     Cursor c{buf.data(), buf.size()};
     uint32_t *d_q = decode_indices<uint32_t>(ws, c, n);
     ws.d2h(out, d_q, n * sizeof(uint32_t));
-    SZ3B_CUDA(cudaStreamSynchronize(ws.st));
+    SZ3B_CUDA(stream_wait(ws.st));
 }
 
 #define SZ3B_INST_PIPE(T)                                                                                             \

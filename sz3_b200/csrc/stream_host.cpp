@@ -1,6 +1,8 @@
 // sz3_b200/csrc/stream_host.cpp -- see stream_host.hpp.
 #include "stream_host.hpp"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -14,9 +16,18 @@ static std::atomic<int> g_host_threads{0};
 int host_threads() {
     int n = g_host_threads.load();
     if (n <= 0) {
-        n = static_cast<int>(std::thread::hardware_concurrency());
-        if (n <= 0) n = 1;
-        if (n > 64) n = 64;
+        // this process's share of the cores when a launcher says how many ranks share the host (torchrun, Open MPI):
+        // a full-size pool per rank oversubscribes the cores and halves the end-to-end rate (tests/gpu_cores.sh)
+        static const int share = [] {
+            int c = static_cast<int>(std::thread::hardware_concurrency());
+            if (c <= 0) c = 1;
+            if (c > 64) c = 64;
+            int ranks = 1;
+            for (const char *name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE"})
+                if (const char *e = getenv(name)) ranks = std::max(ranks, atoi(e));
+            return ranks > 1 ? std::max(2, c / ranks) : c;
+        }();
+        n = share;
     }
     return n;
 }

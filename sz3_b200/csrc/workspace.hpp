@@ -10,6 +10,10 @@
 
 #include <string.h>
 
+#include <sched.h>
+#include <stdlib.h>
+
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -30,6 +34,30 @@ struct CudaError {
         cudaError_t _e = (expr);                                                \
         if (_e != cudaSuccess) throw sz3b::CudaError{_e, #expr, __FILE__, __LINE__}; \
     } while (0)
+
+// How a host thread waits for the device.  0: the driver's own wait, which spins on a core -- lowest latency while
+// every waiting thread has a core to itself.  1: poll and give the core away between polls -- for hosts where the
+// waiting threads (one rank per GPU, each with concurrent tuner trials) outnumber the cores, so that a thread with
+// real work (Huffman tree, zstd trial) is not time-sliced against spinners.  sz3b_set_host_wait() / SZ3B_HOST_WAIT.
+inline std::atomic<int> &host_wait_mode() {
+    static std::atomic<int> m{[] {
+        const char *e = getenv("SZ3B_HOST_WAIT");
+        return e ? atoi(e) : 0;
+    }()};
+    return m;
+}
+inline cudaError_t stream_wait(cudaStream_t st) {
+    if (host_wait_mode().load(std::memory_order_relaxed) == 0) return cudaStreamSynchronize(st);
+    cudaError_t e;
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) sched_yield();
+    return e;
+}
+inline cudaError_t event_wait(cudaEvent_t ev) {
+    if (host_wait_mode().load(std::memory_order_relaxed) == 0) return cudaEventSynchronize(ev);
+    cudaError_t e;
+    while ((e = cudaEventQuery(ev)) == cudaErrorNotReady) sched_yield();
+    return e;
+}
 
 struct DevBuf {
     void *p = nullptr;
