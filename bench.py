@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--edge", type=int, default=EDGE, help="cube edge (default 512 = the metric's configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--diag", action="store_true", help="per-rank step times and host-link rate on stderr")
     ap.add_argument("--host-threads", type=int, default=None, help="host threads per rank (default: this rank's share of the cores)")
     ap.add_argument("--host-wait", type=int, default=None, help="0 = spin while waiting for the device, 1 = poll and yield")
     ap.add_argument("--lossless-policy", type=int, default=None, help="0 = zstd on every chunk, 1 = adaptive (library default)")
@@ -297,12 +298,14 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         ms_total = e0.elapsed_time(e1)
+        local_ms.append(ms_total / steps)
         if world > 1:
             t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_total = float(t.item())
         return ms_total, pq_ms, launches, csize
 
+    local_ms = []
     for _ in range(max(args.warmup, 3)):
         step(dev.data_ptr(), 1)
     # untimed settling beyond W: the first calls still grow per-workspace buffers and the SM clock is still ramping
@@ -330,6 +333,35 @@ def run_ours(args):
     ms_e2e, _, _, _ = timed(pinned.data_ptr(), 0, args.steps, False)
     h2d, d2h = C.c_size_t(0), C.c_size_t(0)
     L.sz3b_last_transfer(C.byref(h2d), C.byref(d2h))
+    if args.diag:   # per-rank view: this rank's own step times and its share of the host link with all ranks copying
+        if world > 1:
+            dist.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            dev.copy_(pinned, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_rate = 5 * nbytes / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        print(f"[diag] rank {rank} gpu {local}: value path {local_ms[0]:.2f} ms/step, e2e path {local_ms[1]:.2f} ms/step, "
+              f"plain H2D with all ranks copying {h2d_rate:.1f} GB/s, last e2e step: "
+              + " ".join(f"{n}={m:.2f}" for n, m, _ in profile()), file=sys.stderr, flush=True)
+        if world > 1:
+            dist.barrier()
+        for th, wt in [(cores, 0), (max(2, cores // world), 0), (2, 0), (cores, 1), (max(2, cores // world), 1)]:
+            L.sz3b_set_host_threads(th)
+            L.sz3b_set_host_wait(wt)
+            for _ in range(3):
+                step(dev.data_ptr(), 1)
+            a, _, _, _ = timed(dev.data_ptr(), 1, args.steps, False)
+            for _ in range(2):
+                step(pinned.data_ptr(), 0)
+            b, _, _, _ = timed(pinned.data_ptr(), 0, args.steps, False)
+            if rank == 0:
+                print(f"[diag] host threads {th}, wait {['spin', 'yield'][wt]}: value path {a / args.steps:.2f} ms/step, "
+                      f"e2e path {b / args.steps:.2f} ms/step (max over ranks)", file=sys.stderr, flush=True)
+        L.sz3b_set_host_threads(host_threads)
+        L.sz3b_set_host_wait(host_wait)
     clocks = sampler.stop() if rank == 0 else None
     # the same two measurements with the lossless stage on the host (zstd level 3 on every chunk, the reference's own
     # call), reported next to the headline so that the effect of the GPU lossless stage is visible
