@@ -76,11 +76,19 @@ void write_links(uint8_t *dst, const std::vector<uint32_t> &v) {
 }  // namespace
 
 bool huffman_build(const unsigned long long *hist, size_t nbins, int sym_base, HuffmanBook &book, const char **err) {
-    size_t lo = nbins, hi = 0;
-    for (size_t k = 0; k < nbins; k++) {
-        if (hist[k]) {
-            if (lo == nbins) lo = k;
-            hi = k;
+    // almost every bin of a 65536-bin histogram is empty: look at 16 bins per test
+    size_t lo = nbins, hi = 0, present = 0;
+    for (size_t k0 = 0; k0 < nbins; k0 += 16) {
+        const size_t k1 = k0 + 16 < nbins ? k0 + 16 : nbins;
+        unsigned long long any = 0;
+        for (size_t k = k0; k < k1; k++) any |= hist[k];
+        if (!any) continue;
+        for (size_t k = k0; k < k1; k++) {
+            if (hist[k]) {
+                if (lo == nbins) lo = k;
+                hi = k;
+                present++;
+            }
         }
     }
     if (lo == nbins) {
@@ -93,9 +101,10 @@ bool huffman_build(const unsigned long long *hist, size_t nbins, int sym_base, H
     book.code.assign(states, 0);
     book.len.assign(states, 0);
 
+    // sized by the symbols present, not by the symbol range: a few hundred nodes instead of megabytes of fresh pages
     std::vector<Node> nodes;
-    nodes.reserve(2 * states);
-    Heap heap(&nodes, 2 * states);
+    nodes.reserve(2 * present);
+    Heap heap(&nodes, 2 * present);
     size_t distinct = 0;
     for (size_t k = lo; k <= hi; k++) {
         if (!hist[k]) continue;

@@ -43,7 +43,26 @@ struct LineTile {
     LinePass ps[3];
 };
 
-SZ_HD uint32_t magic_u32_fast(uint32_t c) { return c <= 1 ? 0u : 0xffffffffu / c + 1u; }
+// Divisors inside a tile are its extents (<= 33): their magic numbers come from a table in constant memory.  Every
+// thread needs four of them before its first load of the fill; as integer divisions they were 1 % of the instructions
+// and 13 % of the stall samples of the level-1 launch (profiles/r1y_full_interp_ltile.md).
+struct MagicTab {
+    uint32_t v[65];
+};
+constexpr MagicTab make_magic_tab() {
+    MagicTab t{};
+    for (uint32_t c = 0; c <= 64; c++) t.v[c] = c <= 1 ? 0u : 0xffffffffu / c + 1u;
+    return t;
+}
+#ifdef __CUDACC__
+static __constant__ MagicTab kMagicTab = make_magic_tab();
+#endif
+SZ_HD uint32_t magic_u32_fast(uint32_t c) {
+#ifdef __CUDA_ARCH__
+    if (c <= 64u) return kMagicTab.v[c];
+#endif
+    return c <= 1 ? 0u : 0xffffffffu / c + 1u;
+}
 
 // rare path (an unpredictable point): kept out of line so that the hot loops carry a branch, not predicated stores
 template <class T>
@@ -436,14 +455,16 @@ SZ_HD void row_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, c
 
 // ---------------------------------------------------------------------------------------------------------------------
 // fill: the sub-lattice even along the last pass dimension; coarse points (all local indices even) from recon2,
-// everything else from the immutable input
+// everything else from the immutable input.  The two loops write disjoint shared-memory cells, so there is no barrier
+// between them and the loads of both are in flight together.
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T, class QT, class Ctx>
 SZ_HD void line_fill(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, T *sm) {
     const uint32_t tid = ctx.tid(), nt = ctx.nthreads();
     const uint32_t s = A.s;
     const uint32_t m0 = lg.last == 0 ? 2u : 1u, m1 = lg.last == 1 ? 2u : 1u, m2 = lg.last == 2 ? 2u : 1u;
-    {   // (1) every element of the sub-lattice from the input
+    {   // (1) every element of the sub-lattice that is not a coarse point, from the input
+        const uint32_t o0 = lg.last == 0 ? 0u : 1u, o1 = lg.last == 1 ? 0u : 1u, o2 = lg.last == 2 ? 0u : 1u;
         const uint32_t E1 = lg.E[1], E2 = lg.E[2];
         const uint32_t total = lg.E[0] * E1 * E2;
         const uint32_t mg1 = magic_u32_fast(E1), mg2 = magic_u32_fast(E2);
@@ -453,26 +474,26 @@ SZ_HD void line_fill(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, T
         // four independent loads in flight per thread before the first shared-memory store
         for (uint32_t it0 = tid; it0 < total; it0 += 4 * nt) {
             T v[4];
+            bool fine[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t it = it0 + k * nt;
+                fine[k] = false;
                 if (it < total) {
                     const uint32_t r = fast_div(it, mg2);
                     const uint32_t e2 = it - r * E2;
                     const uint32_t e0 = fast_div(r, mg1);
                     const uint32_t e1 = r - e0 * E1;
-                    v[k] = dat[e0 * g0 + e1 * g1 + e2 * g2];
+                    fine[k] = (((e0 & o0) | (e1 & o1) | (e2 & o2)) & 1u) != 0;
+                    if (fine[k]) v[k] = dat[e0 * g0 + e1 * g1 + e2 * g2];
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t it = it0 + k * nt;
-                if (it < total) sm[it] = v[k];
-            }
+            for (int k = 0; k < 4; k++)
+                if (fine[k]) sm[it0 + k * nt] = v[k];
         }
     }
-    ctx.sync();
-    {   // (2) coarse points (all local indices even) are overwritten with their reconstruction from recon2:
+    {   // (2) coarse points (all local indices even) come as their reconstruction from recon2:
         //     local index 2c of dim d sits at smem coordinate 2c (d != last) or c (d == last) and at recon2 offset
         //     (begin + 2c*s)/2 = begin/2 + c*s
         const uint32_t C0 = (lg.n[0] + 1) / 2, C1 = (lg.n[1] + 1) / 2, C2 = (lg.n[2] + 1) / 2;
