@@ -455,9 +455,30 @@ SZ_HD void row_items(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, c
 
 // ---------------------------------------------------------------------------------------------------------------------
 // fill: the sub-lattice even along the last pass dimension; coarse points (all local indices even) from recon2,
-// everything else from the immutable input.  The two loops write disjoint shared-memory cells, so there is no barrier
-// between them and the loads of both are in flight together.
+// everything else from the immutable input.  Elements go from global to shared memory as asynchronous copies
+// (cp.async, no register staging): a thread issues all of its ~46 copies back to back and waits once, instead of
+// paying a global-memory round trip per batch of four loads.  The two loops write disjoint cells, so they need no
+// barrier between them.
 // ---------------------------------------------------------------------------------------------------------------------
+template <class T>
+SZ_HD void fill_copy(T *smem_dst, const T *gsrc) {
+#ifdef __CUDA_ARCH__
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "cp.async element size");
+    const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    if (sizeof(T) == 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+#else
+    *smem_dst = *gsrc;
+#endif
+}
+SZ_HD void fill_copy_wait() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 template <class T, class QT, class Ctx>
 SZ_HD void line_fill(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, T *sm) {
     const uint32_t tid = ctx.tid(), nt = ctx.nthreads();
@@ -471,26 +492,13 @@ SZ_HD void line_fill(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, T
         const uint32_t g0 = m0 * s * static_cast<uint32_t>(A.sh.stride[0]), g1 = m1 * s * static_cast<uint32_t>(A.sh.stride[1]),
                        g2 = m2 * s;
         const T *dat = A.data + lg.gbase;
-        // four independent loads in flight per thread before the first shared-memory store
-        for (uint32_t it0 = tid; it0 < total; it0 += 4 * nt) {
-            T v[4];
-            bool fine[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t it = it0 + k * nt;
-                fine[k] = false;
-                if (it < total) {
-                    const uint32_t r = fast_div(it, mg2);
-                    const uint32_t e2 = it - r * E2;
-                    const uint32_t e0 = fast_div(r, mg1);
-                    const uint32_t e1 = r - e0 * E1;
-                    fine[k] = (((e0 & o0) | (e1 & o1) | (e2 & o2)) & 1u) != 0;
-                    if (fine[k]) v[k] = dat[e0 * g0 + e1 * g1 + e2 * g2];
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (fine[k]) sm[it0 + k * nt] = v[k];
+#pragma unroll 4
+        for (uint32_t it = tid; it < total; it += nt) {
+            const uint32_t r = fast_div(it, mg2);
+            const uint32_t e2 = it - r * E2;
+            const uint32_t e0 = fast_div(r, mg1);
+            const uint32_t e1 = r - e0 * E1;
+            if (((e0 & o0) | (e1 & o1) | (e2 & o2)) & 1u) fill_copy(sm + it, dat + (e0 * g0 + e1 * g1 + e2 * g2));
         }
     }
     {   // (2) coarse points (all local indices even) come as their reconstruction from recon2:
@@ -502,26 +510,16 @@ SZ_HD void line_fill(const InterpArgs<T, QT> &A, Ctx &ctx, const LineGeom &lg, T
         const uint32_t h0 = s * static_cast<uint32_t>(A.stride2[0]), h1 = s * static_cast<uint32_t>(A.stride2[1]), h2 = s;
         const uint32_t t2 = 2u / m2, t1 = (2u / m1) * lg.E[2], t0 = (2u / m0) * lg.E[2] * lg.E[1];
         const T *rc2 = A.recon2 + lg.g2base;
-        for (uint32_t it0 = tid; it0 < total; it0 += 4 * nt) {
-            T v[4];
-            uint32_t so[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t it = it0 + k * nt;
-                if (it < total) {
-                    const uint32_t r = fast_div(it, mg2);
-                    const uint32_t c2 = it - r * C2;
-                    const uint32_t c0 = fast_div(r, mg1);
-                    const uint32_t c1 = r - c0 * C1;
-                    so[k] = c0 * t0 + c1 * t1 + c2 * t2;
-                    v[k] = rc2[c0 * h0 + c1 * h1 + c2 * h2];
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (it0 + k * nt < total) sm[so[k]] = v[k];
+#pragma unroll 4
+        for (uint32_t it = tid; it < total; it += nt) {
+            const uint32_t r = fast_div(it, mg2);
+            const uint32_t c2 = it - r * C2;
+            const uint32_t c0 = fast_div(r, mg1);
+            const uint32_t c1 = r - c0 * C1;
+            fill_copy(sm + (c0 * t0 + c1 * t1 + c2 * t2), rc2 + (c0 * h0 + c1 * h1 + c2 * h2));
         }
     }
+    fill_copy_wait();   // the caller's barrier publishes the tile
 }
 
 template <class T, class QT, class Ctx, bool LAST, bool WRITE2>
