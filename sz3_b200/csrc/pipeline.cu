@@ -94,10 +94,44 @@ static const void *mapped_alias(const void *data) {
     return attr.devicePointer;
 }
 
+// Bulk uploads of concurrent callers go up one after the other instead of sharing the link command by command: the
+// caller whose array is complete then encodes and downloads while the next caller's array is still on its way (two
+// callers interleaved would both see their last plane after two upload times).
+namespace {
+struct UploadChain {
+    std::mutex mu;
+    cudaEvent_t ring[4] = {nullptr, nullptr, nullptr, nullptr};
+    int head = 0;
+    bool any = false;
+};
+UploadChain &upload_chain(int device) {
+    static UploadChain chains[64];
+    return chains[device >= 0 && device < 64 ? device : 0];
+}
+struct UploadTurn {   // holds the chain while one call enqueues its copies on its copy stream
+    UploadChain &c;
+    cudaStream_t st;
+    UploadTurn(Workspace &ws) : c(upload_chain(ws.device)), st(ws.st_copy) {
+        c.mu.lock();
+        if (c.any) cudaStreamWaitEvent(st, c.ring[c.head], 0);
+    }
+    ~UploadTurn() {
+        const int next = (c.head + 1) & 3;
+        if (!c.ring[next]) cudaEventCreateWithFlags(&c.ring[next], cudaEventDisableTiming);
+        if (c.ring[next] && cudaEventRecord(c.ring[next], st) == cudaSuccess) {
+            c.head = next;
+            c.any = true;
+        }
+        c.mu.unlock();
+    }
+};
+}  // namespace
+
 // Starts the H2D of the whole input on the copy stream and returns at once; ws.st waits for it via join_copy().
 template <class T>
 static const T *to_device_background(Workspace &ws, const T *data, size_t num) {
     T *d = ws.data.as<T>(num);
+    UploadTurn turn(ws);
     // in pieces: the tuner's own small uploads share the H2D copy engine and can only slip in between commands
     const size_t bytes = num * sizeof(T), piece = static_cast<size_t>(8) << 20;
     for (size_t off = 0; off < bytes; off += piece)
@@ -124,6 +158,7 @@ static const T *to_device_planes(Workspace &ws, const T *data, const sz3b_config
     const size_t nz = conf.dims[0], plane = num / nz * sizeof(T);
     uint8_t *dst = reinterpret_cast<uint8_t *>(d);
     const uint8_t *src = reinterpret_cast<const uint8_t *>(data);
+    UploadTurn turn(ws);
     // even planes, 32 per command (measured: 2-D copies of 8 planes lose 1 % of the link rate, of 32 none; the
     // tuner's small uploads do not queue behind them, they go through the SM copy path while this is in flight)
     const size_t n_even = (nz + 1) / 2;

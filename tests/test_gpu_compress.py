@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import (field_g1, ALGO_INTERP, ALGO_INTERP_LORENZO, ALGO_LOSSLESS, EB_ABS, EB_PSNR, EB_REL, Config, dtype_code, field_g3,
+from common import (field_g1, ALGO_INTERP, ALGO_INTERP_LORENZO, ALGO_LORENZO_REG, ALGO_LOSSLESS, EB_ABS, EB_PSNR, EB_REL, Config, dtype_code, field_g3,
                     field_g4, field_nd, make_config, product_lib, ref_lib)
 
 pytestmark = pytest.mark.gpu
@@ -207,3 +207,45 @@ def test_pinned_host_input_stream_identical(shape, dtype, algo):
                              C.c_size_t(cap), C.byref(size), None)
         assert rc == 0, L.sz3b_last_error()
         assert size.value == theirs.size and np.array_equal(out[:size.value], theirs)
+
+
+def test_concurrent_callers_streams_identical():
+    """The library is reentrant (every call borrows its own workspace and streams): three host threads compressing
+    different arrays at the same time -- pinned host input on the plane-ordered path, pageable host input, a blockwise
+    stack -- must each produce the stream a lone caller gets, call after call."""
+    import threading
+
+    import torch
+    L = product_lib()
+    L.sz3b_last_error.restype = C.c_char_p
+    a = field_nd((96, 160, 128), np.float32)
+    b = field_g3((80, 90, 100), np.float32)
+    c = field_nd((60, 66, 72), np.float64)
+    pinned = torch.from_numpy(a).pin_memory()
+    jobs = [
+        (a, make_config(a.shape, cmprAlgo=ALGO_INTERP_LORENZO, absErrorBound=1e-3), pinned.data_ptr()),
+        (b, make_config(b.shape, cmprAlgo=ALGO_INTERP_LORENZO, absErrorBound=1e-3), b.ctypes.data),
+        (c, make_config(c.shape, cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1e-4), c.ctypes.data),
+    ]
+    alone = [gpu_compress(d, conf)[0] for d, conf, _ in jobs]
+    failures = []
+
+    def caller(k):
+        d, conf, ptr = jobs[k]
+        cap = L.sz3b_compress_bound(dtype_code(d), C.byref(conf))
+        out = np.empty(cap, dtype=np.uint8)
+        size = C.c_size_t(0)
+        for it in range(4):
+            rc = L.sz3b_compress(dtype_code(d), C.byref(conf), C.c_void_p(ptr), 0, out.ctypes.data_as(C.c_char_p), C.c_size_t(cap),
+                                 C.byref(size), None)
+            if rc != 0:
+                failures.append((k, it, L.sz3b_last_error()))
+            elif size.value != alone[k].size or not np.array_equal(out[:size.value], alone[k]):
+                failures.append((k, it, "stream differs from the lone caller's", size.value, alone[k].size))
+
+    threads = [threading.Thread(target=caller, args=(k,)) for k in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not failures, failures
