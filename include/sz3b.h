@@ -148,6 +148,7 @@ void sz3b_last_transfer(size_t *h2d_bytes, size_t *d2h_bytes);
 /* Host threads the library may use: zstd workers of the host tail and concurrent tuner trials (0 = hardware
  * concurrency).  With one rank per GPU on a shared host, give each rank its share of the cores. */
 void sz3b_set_host_threads(int n);
+int sz3b_get_host_threads(void);   /* the value in force (after the defaults above) */
 /* How host threads wait for the device: 0 = the driver's wait (spins; lowest latency when cores are plentiful),
  * 1 = poll and yield the core between polls (for hosts with more waiting threads than cores).  No reference
  * counterpart (the reference has no device); initial value from the environment variable SZ3B_HOST_WAIT. */

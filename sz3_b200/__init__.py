@@ -239,6 +239,10 @@ class sz:
         lib().sz3b_set_host_threads(int(n))
 
     @staticmethod
+    def get_host_threads():
+        return int(lib().sz3b_get_host_threads())
+
+    @staticmethod
     def set_host_wait(mode):
         """0 = host threads spin while they wait for the device (default), 1 = they poll and yield the core."""
         lib().sz3b_set_host_wait(int(mode))

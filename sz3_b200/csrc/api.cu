@@ -95,6 +95,7 @@ int sz3b_device_count(void) {
 }
 
 void sz3b_set_host_threads(int n) { set_host_threads(n); }
+int sz3b_get_host_threads(void) { return host_threads(); }
 void sz3b_set_host_wait(int mode) { host_wait_mode().store(mode != 0); }
 void sz3b_set_lossless_policy(int policy) { set_lossless_policy(policy); }
 int sz3b_get_lossless_policy(void) { return lossless_policy(); }

@@ -81,3 +81,27 @@ def test_compute_fails_loudly_without_gpu():
                          C.byref(size), None)
     assert rc == -3, "no CPU fallback may exist: expected SZ3B_E_CUDA"
     assert b"CUDA" in L.sz3b_last_error() or b"cuda" in L.sz3b_last_error()
+
+
+def test_host_threads_default_is_the_ranks_share_of_the_cores():
+    """One rank per GPU on a shared host: the default pool is hardware concurrency / LOCAL_WORLD_SIZE (at least 2);
+    an explicit sz3b_set_host_threads wins.  Read in a fresh process (the default is computed once)."""
+    import subprocess
+    import sys
+    code = ("import ctypes as C, sys; sys.path.insert(0, 'tests'); from common import product_lib; L = product_lib(); "
+            "a = L.sz3b_get_host_threads(); L.sz3b_set_host_threads(3); b = L.sz3b_get_host_threads(); "
+            "L.sz3b_set_host_threads(0); print(a, b, L.sz3b_get_host_threads())")
+
+    def run(env_extra):
+        env = dict(os.environ)
+        for k in ("LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE"):
+            env.pop(k, None)
+        env.update(env_extra)
+        out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, check=True).stdout
+        return [int(x) for x in out.split()]
+
+    cores = min(64, os.cpu_count() or 1)
+    alone = run({})
+    assert alone[1] == 3 and alone[0] == alone[2] and 1 <= alone[0] <= cores
+    shared = run({"LOCAL_WORLD_SIZE": "4"})
+    assert shared[0] == (max(2, alone[0] // 4) if alone[0] // 4 >= 1 else 2) and shared[1] == 3 and shared[2] == shared[0]
