@@ -77,7 +77,9 @@ void write_links(uint8_t *dst, const std::vector<uint32_t> &v) {
 
 bool huffman_build(const unsigned long long *hist, size_t nbins, int sym_base, HuffmanBook &book, const char **err) {
     // almost every bin of a 65536-bin histogram is empty: look at 16 bins per test
-    size_t lo = nbins, hi = 0, present = 0;
+    size_t lo = nbins, hi = 0;
+    std::vector<uint32_t> used;   // bins that occur, ascending
+    used.reserve(1024);
     for (size_t k0 = 0; k0 < nbins; k0 += 16) {
         const size_t k1 = k0 + 16 < nbins ? k0 + 16 : nbins;
         unsigned long long any = 0;
@@ -87,10 +89,11 @@ bool huffman_build(const unsigned long long *hist, size_t nbins, int sym_base, H
             if (hist[k]) {
                 if (lo == nbins) lo = k;
                 hi = k;
-                present++;
+                used.push_back(static_cast<uint32_t>(k));
             }
         }
     }
+    const size_t present = used.size();
     if (lo == nbins) {
         if (err) *err = "Huffman bins should not be empty";
         return false;
@@ -106,8 +109,7 @@ bool huffman_build(const unsigned long long *hist, size_t nbins, int sym_base, H
     nodes.reserve(2 * present);
     Heap heap(&nodes, 2 * present);
     size_t distinct = 0;
-    for (size_t k = lo; k <= hi; k++) {
-        if (!hist[k]) continue;
+    for (const uint32_t k : used) {
         Node nd;
         nd.freq = hist[k];
         nd.sym = static_cast<int>(k - lo);

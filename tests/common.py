@@ -104,6 +104,21 @@ def emul_lib():
     return C.CDLL(out)
 
 
+def huffman_host_emul_lib():
+    """The product's host Huffman stage (tree, blob, code table) with sequential stand-ins for its two GPU kernels
+    (tests/emul/huffman_host_emul.cpp; test infrastructure)."""
+    src = os.path.join(ROOT, "tests", "emul", "huffman_host_emul.cpp")
+    out = os.path.join(ROOT, "tests", "emul", "_build", "libhuffman_host_emul.so")
+    deps = [src] + [os.path.join(ROOT, "sz3_b200", "csrc", f) for f in ("huffman_host.cpp", "huffman_host.hpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", src, "-o", out], check=True)
+    lib = C.CDLL(out)
+    lib.emul_huffman_encode.restype = C.c_longlong
+    lib.emul_huffman_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+    return lib
+
+
 def zhuf_emul_lib():
     """Sequential encoder of the GPU lossless stage's frames (tests/emul/zhuf_emul.cpp; test infrastructure)."""
     src = os.path.join(ROOT, "tests", "emul", "zhuf_emul.cpp")

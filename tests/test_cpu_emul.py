@@ -200,3 +200,36 @@ def test_emul_lorenzo_noisy_field(minwin, walkbelow, monkeypatch):
     assert rc > 1, rc
     assert np.array_equal(q, q_ref)
     assert int(np.frombuffer(blob_ref[:8], np.uint64)[0]) == ncoef.value
+
+
+def test_host_huffman_tree_and_codes_match_reference():
+    """The product builds the Huffman tree on the host (huffman_host.cpp); histogram and bit packing are CUDA kernels.
+    With sequential stand-ins for those two, tree blob, code table and bit stream must be the reference's own
+    (HuffmanEncoder::save + ::encode) -- ties in the heap included."""
+    from common import huffman_host_emul_lib, port_lib
+    E = huffman_host_emul_lib()
+    checker, pre = (ref_lib(), "ref") if ref_lib() is not None else (port_lib(), "orc")
+    rng = np.random.default_rng(11)
+    cases = [
+        rng.integers(32700, 32830, 20000).astype(np.int32),
+        np.full(1000, 7, np.int32),                                              # one symbol: zero-length code
+        np.array([5, 9] * 300, np.int32),                                        # two symbols, equal counts
+        (32768 + np.round(rng.standard_normal(50000) * 3)).astype(np.int32),     # the usual shape of an index stream
+        np.concatenate([np.zeros(40, np.int32), (32768 + np.round(rng.standard_normal(30000) * 40)).astype(np.int32)]),
+        rng.integers(0, 65536, 30000).astype(np.int32),                          # almost every symbol once: many ties
+        np.repeat(np.arange(100, 164, dtype=np.int32), 2 ** np.arange(64) % 7 + 1),
+    ]
+    for q in cases:
+        q = np.ascontiguousarray(q)
+        outs = []
+        for fn in (lambda b, tl: E.emul_huffman_encode(q.ctypes.data, q.size, 65536, b.ctypes.data, C.addressof(tl)),
+                   lambda b, tl: getattr(checker, pre + "_huffman_encode")(q.ctypes.data_as(C.c_void_p), C.c_size_t(q.size),
+                                                                           b.ctypes.data_as(C.c_void_p), C.byref(tl))):
+            buf = np.zeros(q.size * 8 + (1 << 20), np.uint8)
+            tl = C.c_size_t(0)
+            n = fn(buf, tl)
+            assert n > 0, n
+            outs.append((tl.value, bytes(buf[:n])))
+        assert outs[0][0] == outs[1][0], "tree blob length"
+        assert outs[0][1][:outs[0][0]] == outs[1][1][:outs[1][0]], "tree blob"
+        assert outs[0][1] == outs[1][1], "bit stream"
