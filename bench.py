@@ -14,6 +14,9 @@ per-slab byte counts (weak scaling: work per GPU is fixed).
   roofline  the fused predict+quantize launches (k_interp_*): algorithmic bytes N*(sizeof(T)+4) / their device time
             (CUDA events recorded by the library on its own stream), against MEASURED_PEAKS.json's HBM copy peak
   cpu_baseline  oracle/_ref (the unmodified reference, conf.openmp = true) on the box's host cores, same array
+  extras    host_zstd_policy (the same two measurements with the reference's own host zstd call), e2e_two_callers
+            (N = 1: the e2e call issued by two host threads at once), config.host (cores, threads per rank);
+            --diag prints per-rank step times, the host-link rate and an A/B of the host thread settings on stderr
 """
 import argparse
 import ctypes as C
