@@ -14,8 +14,11 @@
  *               framing         api/sz.hpp:43-82,117-157; api/impl/SZDispatcher.hpp:13-107;
  *                               compressor/SZGenericCompressor.hpp:38-84; lossless/Lossless_zstd.hpp:29-45
  *
- * Not restated: the auto-tuner of ALGO_INTERP_LORENZO (api/impl/SZAlgoInterp.hpp:122-286) and the OpenMP container --
- * orc_compress refuses those configurations (returns -1); the unmodified reference in oracle/_ref covers them.
+ *               auto-tuner      api/impl/SZAlgoInterp.hpp:43-119 (trial compressions), :122-286 (decisions);
+ *                               utils/Sample.hpp:9-127 (profiling_block), :202-289 (sampleBlocks)  [typed half]
+ *
+ * Not restated: the OpenMP container -- orc_compress refuses it (returns -1); the unmodified reference in
+ * oracle/_ref covers it.
  *
  * Pinning: tests/test_oracle_port.py diffs every entry point below against oracle/_ref (the reference itself compiled
  * in this container) on seeded inputs -- indices, blobs and whole streams byte for byte.  The reference's own tests
@@ -325,6 +328,8 @@ static int huff_read(const uint8_t **c, size_t n, int *out) {
 }
 
 /* ------------------------------------------------------------------ typed halves */
+static long long zwrap(const uint8_t *src, size_t len, uint8_t *dst, size_t cap);
+
 #define T float
 #define SUF f
 #include "sz3_oracle_t.inc"
@@ -605,6 +610,9 @@ long long orc_compress(int dtype, const orc_config *c0, const void *data, char *
     c.absErrorBound = orc_abs_eb(dtype, &c, data);
     c.errorBoundMode = ORC_EB_ABS;
     if (c.absErrorBound == 0) c.cmprAlgo = ORC_ALGO_LOSSLESS;
+    if (c.cmprAlgo == ORC_ALGO_INTERP_LORENZO) { /* SZ_compress_Interp_lorenzo: tune, then one of the two below */
+        if ((dtype == 0 ? tunef(&c, (const float *)data) : tuned(&c, (const double *)data)) != 0) return -1;
+    }
     if (c.cmprAlgo == ORC_ALGO_INTERP || c.cmprAlgo == ORC_ALGO_LORENZO_REG) {
         void *work = malloc(n * esz);
         memcpy(work, data, n * esz);
@@ -623,7 +631,7 @@ long long orc_compress(int dtype, const orc_config *c0, const void *data, char *
             free(tmp);
         }
     } else if (c.cmprAlgo != ORC_ALGO_LOSSLESS) {
-        return -1; /* tuner / NOPRED / BIOMD: not restated */
+        return -1; /* NOPRED / BIOMD: not restated */
     }
     if (c.cmprAlgo == ORC_ALGO_LOSSLESS && payload < 0) {
         payload = zwrap((const uint8_t *)data, n * esz, p, dcap);
@@ -754,8 +762,12 @@ int orc_decompress(int dtype, const char *cmp, size_t n, void *out, orc_config *
     return rc;
 }
 
-/* the tuner is not restated (see header) */
+/* the tuner inside SZ_compress_Interp_lorenzo (api/impl/SZAlgoInterp.hpp:122-286): resolves the bound like the
+ * dispatcher does, then rewrites *c to the configuration the reference goes on to compress with */
 int orc_tune(int dtype, orc_config *c, const void *data) {
-    (void)dtype; (void)c; (void)data;
-    return -1;
+    if (c->N < 1 || c->N > 4) return -1;
+    fix_conf(c);
+    c->absErrorBound = orc_abs_eb(dtype, c, data);
+    c->errorBoundMode = ORC_EB_ABS;
+    return dtype == 0 ? tunef(c, (const float *)data) : tuned(c, (const double *)data);
 }

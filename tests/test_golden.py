@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from common import ALGO_INTERP_LORENZO, ROOT, Config, dtype_code, make_config, port_lib, product_lib, ref_lib
+from common import ROOT, Config, dtype_code, make_config, port_lib, product_lib, ref_lib
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 with open(os.path.join(GOLDEN, "cases.json")) as _f:
@@ -42,11 +42,10 @@ def test_oracle_port_writes_and_decodes_golden(case):
     P = port_lib()
     data, stream = load(case)
     conf = make_config(data.shape, **case["config"])
-    if case["config"]["cmprAlgo"] != ALGO_INTERP_LORENZO:   # the restatement has no tuner
-        out = np.empty(stream.size + (1 << 20), np.uint8)
-        n = P.orc_compress(dtype_code(data), C.byref(conf), data.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_char_p),
-                           C.c_size_t(out.size))
-        assert n == stream.size and np.array_equal(out[:n], stream)
+    out = np.empty(stream.size + (1 << 20), np.uint8)   # tuned cases included: the restatement has the auto-tuner
+    n = P.orc_compress(dtype_code(data), C.byref(conf), data.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_char_p),
+                       C.c_size_t(out.size))
+    assert n == stream.size and np.array_equal(out[:n], stream)
     dec, dconf = np.empty_like(data), Config()
     assert P.orc_decompress(dtype_code(data), stream.ctypes.data_as(C.c_char_p), C.c_size_t(stream.size),
                             dec.ctypes.data_as(C.c_void_p), C.byref(dconf)) == 0

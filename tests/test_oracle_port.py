@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import (ALGO_INTERP, ALGO_LORENZO_REG, EB_REL, Config, dtype_code, field_nd, make_config, port_lib, ref_blockwise,
+from common import (ALGO_INTERP, ALGO_LORENZO_REG, EB_REL, Config, dtype_code, field_g1, field_g3, field_nd, make_config, port_lib, ref_blockwise,
                     ref_interp, ref_lib)
 
 pytestmark = pytest.mark.skipif(ref_lib() is None or port_lib() is None, reason="needs oracle/_ref and oracle/libsz3oracle.so")
@@ -86,3 +86,36 @@ def test_port_streams_match_reference_and_decode(shape, dtype, kw):
     assert R.ref_decompress(dtype_code(data), a.ctypes.data_as(C.c_char_p), C.c_size_t(na), dec_r.ctypes.data_as(C.c_void_p), C.byref(cr)) == 0
     assert P.orc_decompress(dtype_code(data), a.ctypes.data_as(C.c_char_p), C.c_size_t(na), dec_p.ctypes.data_as(C.c_void_p), C.byref(cp)) == 0
     assert np.array_equal(dec_r.view(np.uint8), dec_p.view(np.uint8))
+
+
+def _tuner_inputs():
+    rng = np.random.default_rng(5)
+    n = np.arange(1 << 16)
+    return [
+        (field_nd((8, 8, 128), np.float32), dict(absErrorBound=1.0)),                         # too small to tune
+        (field_nd((100, 70, 130), np.float32), dict(absErrorBound=1e-3)),                     # (alpha, beta) = (1, 1) wins
+        (field_nd((48, 60, 72), np.float64), dict(absErrorBound=1e-5)),
+        (field_nd((12, 40, 40, 40), np.float32), dict(absErrorBound=1e-2)),                   # 4-D, 16-cubes
+        (field_nd((300, 500), np.float32), dict(absErrorBound=1e-3)),
+        (field_g1(1 << 18), dict(absErrorBound=1e-4)),                                         # 1-D: the Lorenzo stack wins
+        ((np.sin(n / 50.0) + 0.05 * rng.standard_normal(n.size)).astype(np.float32), dict(absErrorBound=1e-3)),   # linear wins
+        (field_g1(100000), dict(errorBoundMode=EB_REL, relErrorBound=5e-7)),                   # tight relative bound
+        (field_g3((64, 64, 64)), dict(errorBoundMode=EB_REL, relErrorBound=1e-7)),             # tuned stream overflows the buffer -> lossless
+        (rng.standard_normal((40, 40, 40)).astype(np.float32), dict(absErrorBound=1e-3)),      # noise
+    ]
+
+
+@pytest.mark.parametrize("k", range(10))
+def test_port_tuner_matches_reference(k):
+    """ALGO_INTERP_LORENZO: profiling, sampling, the trial compressions and the decision sequence of
+    SZ_compress_Interp_lorenzo, restated in oracle/sz3_oracle_t.inc -- the stream (with the tuned Config at its end) is
+    the reference's, byte for byte, at the same buffer capacity (a length_error of the tuned run means lossless)."""
+    from common import ALGO_INTERP_LORENZO
+    data, kw = _tuner_inputs()[k]
+    conf = make_config(data.shape, cmprAlgo=ALGO_INTERP_LORENZO, **kw)
+    R, P = ref_lib(), port_lib()
+    cap = R.ref_size_bound(dtype_code(data), C.byref(conf)) + 8192
+    a, b = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
+    na = R.ref_compress(dtype_code(data), C.byref(conf), data.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_char_p), C.c_size_t(cap))
+    nb = P.orc_compress(dtype_code(data), C.byref(conf), data.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_char_p), C.c_size_t(cap))
+    assert na > 0 and na == nb and np.array_equal(a[:na], b[:nb])
