@@ -17,8 +17,8 @@
  *               auto-tuner      api/impl/SZAlgoInterp.hpp:43-119 (trial compressions), :122-286 (decisions);
  *                               utils/Sample.hpp:9-127 (profiling_block), :202-289 (sampleBlocks)  [typed half]
  *
- * Not restated: the OpenMP container -- orc_compress refuses it (returns -1); the unmodified reference in
- * oracle/_ref covers it.
+ *               OpenMP container api/impl/SZImplOMP.hpp:16-186 (slabs compressed one after the other; conf.openmp
+ *                               = number of slabs, where the reference takes omp_get_num_threads())
  *
  * Pinning: tests/test_oracle_port.py diffs every entry point below against oracle/_ref (the reference itself compiled
  * in this container) on seeded inputs -- indices, blobs and whole streams byte for byte.  The reference's own tests
@@ -588,35 +588,23 @@ static long long generic_compress(int dtype, orc_config *c, void *work, uint8_t 
     return r;
 }
 
-/* SZ_compress (api/sz.hpp:43-82) + SZ_compress_dispatcher (api/impl/SZDispatcher.hpp:13-76) */
-long long orc_compress(int dtype, const orc_config *c0, const void *data, char *out, size_t cap) {
-    orc_config c = *c0;
-    uint64_t n = conf_num(&c);
+/* SZ_compress_dispatcher (api/impl/SZDispatcher.hpp:13-76): payload of one array (or one OpenMP slab) into dst;
+ * *c leaves with what the reference's conf holds afterwards (resolved bound, tuned / fallback algorithm). */
+static long long dispatch_compress(int dtype, orc_config *c, const void *data, uint8_t *p, size_t dcap) {
+    uint64_t n = conf_num(c);
     size_t esz = dtype == 0 ? 4 : 8;
-    uint8_t *p = (uint8_t *)out, *size_pos;
-    uint8_t blob[256];
-    size_t conf_est, dcap;
     long long payload = -1;
-    uint32_t u;
-    if (c.openmp || c.N < 1 || c.N > 4) return -1;
-    fix_conf(&c);
-    if (cap < orc_size_bound(dtype, &c)) return -1;
-    u = ORC_MAGIC; wr(&p, &u, 4);
-    u = ORC_DATAVER; wr(&p, &u, 4);
-    size_pos = p;
-    p += 8;
-    conf_est = orc_config_save(&c, blob);
-    dcap = cap - 16 - 2 * conf_est;
-    c.absErrorBound = orc_abs_eb(dtype, &c, data);
-    c.errorBoundMode = ORC_EB_ABS;
-    if (c.absErrorBound == 0) c.cmprAlgo = ORC_ALGO_LOSSLESS;
-    if (c.cmprAlgo == ORC_ALGO_INTERP_LORENZO) { /* SZ_compress_Interp_lorenzo: tune, then one of the two below */
-        if ((dtype == 0 ? tunef(&c, (const float *)data) : tuned(&c, (const double *)data)) != 0) return -1;
+    fix_conf(c);
+    c->absErrorBound = orc_abs_eb(dtype, c, data);
+    c->errorBoundMode = ORC_EB_ABS;
+    if (c->absErrorBound == 0) c->cmprAlgo = ORC_ALGO_LOSSLESS;
+    if (c->cmprAlgo == ORC_ALGO_INTERP_LORENZO) { /* SZ_compress_Interp_lorenzo: tune, then one of the two below */
+        if ((dtype == 0 ? tunef(c, (const float *)data) : tuned(c, (const double *)data)) != 0) return -1;
     }
-    if (c.cmprAlgo == ORC_ALGO_INTERP || c.cmprAlgo == ORC_ALGO_LORENZO_REG) {
+    if (c->cmprAlgo == ORC_ALGO_INTERP || c->cmprAlgo == ORC_ALGO_LORENZO_REG) {
         void *work = malloc(n * esz);
         memcpy(work, data, n * esz);
-        payload = generic_compress(dtype, &c, work, p, dcap);
+        payload = generic_compress(dtype, c, work, p, dcap);
         free(work);
         if (payload == -1) return -1;
         if (payload >= 0 && (double)(n * esz) / (double)payload < 3) { /* :62-73 */
@@ -624,23 +612,113 @@ long long orc_compress(int dtype, const orc_config *c0, const void *data, char *
             uint8_t *tmp = (uint8_t *)malloc(zcap);
             long long z = zwrap((const uint8_t *)data, n * esz, tmp, zcap);
             if (z >= 0 && z < payload && (size_t)z <= dcap) {
-                c.cmprAlgo = ORC_ALGO_LOSSLESS;
+                c->cmprAlgo = ORC_ALGO_LOSSLESS;
                 memcpy(p, tmp, (size_t)z);
                 payload = z;
             }
             free(tmp);
         }
-    } else if (c.cmprAlgo != ORC_ALGO_LOSSLESS) {
+    } else if (c->cmprAlgo != ORC_ALGO_LOSSLESS) {
         return -1; /* NOPRED / BIOMD: not restated */
     }
-    if (c.cmprAlgo == ORC_ALGO_LOSSLESS && payload < 0) {
+    if (c->cmprAlgo == ORC_ALGO_LOSSLESS && payload < 0) {
         payload = zwrap((const uint8_t *)data, n * esz, p, dcap);
         if (payload < 0) return -1;
     } else if (payload == -2) {
-        c.cmprAlgo = ORC_ALGO_LOSSLESS;
+        c->cmprAlgo = ORC_ALGO_LOSSLESS;
         payload = zwrap((const uint8_t *)data, n * esz, p, dcap);
         if (payload < 0) return -1;
     }
+    return payload;
+}
+
+/* Config::setDims (utils/Config.hpp:154-177): unit dimensions dropped, rank-dependent defaults reset */
+static void conf_set_dims(orc_config *c, int nd, const uint64_t *dims) {
+    int i, k = 0;
+    uint64_t d[4] = {0, 0, 0, 0};
+    for (i = 0; i < nd && k < 4; i++)
+        if (dims[i] > 1) d[k++] = dims[i];
+    if (k == 0) d[k++] = 1;
+    memcpy(c->dims, d, sizeof(d));
+    c->N = k;
+    c->blockSize = k == 1 ? 128 : (k == 2 ? 16 : 6);
+}
+
+/* SZ_compress_OMP (api/impl/SZImplOMP.hpp:16-117) with c->openmp slabs along the outermost dimension, executed one
+ * after the other: int nThreads | Config of every slab (saved after its compression) | size_t sizes | payloads */
+static long long omp_compress(int dtype, orc_config *c, const void *data, uint8_t *dst, size_t cap) {
+    size_t esz = dtype == 0 ? 4 : 8;
+    int nslabs = c->openmp, t;
+    uint64_t row = conf_num(c) / c->dims[0];
+    uint8_t **parts;
+    uint64_t *sizes;
+    orc_config *confs;
+    uint8_t *p = dst;
+    size_t need = 4;
+    uint8_t blob[256];
+    if ((uint64_t)nslabs > c->dims[0]) nslabs = (int)c->dims[0];
+    if (c->errorBoundMode != ORC_EB_ABS) { /* per-thread min/max reduced to the global range (:57-68) */
+        c->absErrorBound = orc_abs_eb(dtype, c, data);
+        c->errorBoundMode = ORC_EB_ABS;
+    }
+    parts = (uint8_t **)calloc((size_t)nslabs, sizeof(*parts));
+    sizes = (uint64_t *)calloc((size_t)nslabs, sizeof(*sizes));
+    confs = (orc_config *)calloc((size_t)nslabs, sizeof(*confs));
+    for (t = 0; t < nslabs; t++) {
+        int lo = (int)((uint64_t)t * c->dims[0] / (uint64_t)nslabs), hi = (int)((uint64_t)(t + 1) * c->dims[0] / (uint64_t)nslabs);
+        uint64_t d[4];
+        size_t pcap;
+        long long r;
+        int i;
+        for (i = 0; i < c->N; i++) d[i] = c->dims[i];
+        d[0] = (uint64_t)(hi - lo);
+        confs[t] = *c;
+        conf_set_dims(&confs[t], c->N, d);
+        pcap = ZSTD_compressBound(conf_num(&confs[t]) * esz);
+        parts[t] = (uint8_t *)malloc(pcap);
+        r = dispatch_compress(dtype, &confs[t], (const uint8_t *)data + (uint64_t)lo * row * esz, parts[t], pcap);
+        if (r < 0) {
+            for (i = 0; i <= t; i++) free(parts[i]);
+            free(parts); free(sizes); free(confs);
+            return -1;
+        }
+        sizes[t] = (uint64_t)r;
+    }
+    for (t = 0; t < nslabs; t++) need += orc_config_save(&confs[t], blob) + 8 + sizes[t];
+    if (need <= cap) {
+        int32_t ns = nslabs;
+        wr(&p, &ns, 4);
+        for (t = 0; t < nslabs; t++) p += orc_config_save(&confs[t], p);
+        for (t = 0; t < nslabs; t++) wr(&p, &sizes[t], 8);
+        for (t = 0; t < nslabs; t++) {
+            memcpy(p, parts[t], sizes[t]);
+            p += sizes[t];
+        }
+    }
+    for (t = 0; t < nslabs; t++) free(parts[t]);
+    free(parts); free(sizes); free(confs);
+    return need <= cap ? (long long)(p - dst) : -1;
+}
+
+/* SZ_compress (api/sz.hpp:43-82): magic | data version | size_t payload size | payload | Config */
+long long orc_compress(int dtype, const orc_config *c0, const void *data, char *out, size_t cap) {
+    orc_config c = *c0;
+    uint8_t *p = (uint8_t *)out, *size_pos;
+    uint8_t blob[256];
+    size_t conf_est, dcap;
+    long long payload;
+    uint32_t u;
+    if (c.N < 1 || c.N > 4) return -1;
+    if (!c.openmp) fix_conf(&c);
+    if (cap < orc_size_bound(dtype, &c)) return -1;
+    u = ORC_MAGIC; wr(&p, &u, 4);
+    u = ORC_DATAVER; wr(&p, &u, 4);
+    size_pos = p;
+    p += 8;
+    conf_est = orc_config_save(&c, blob);
+    dcap = cap - 16 - 2 * conf_est;
+    payload = c.openmp ? omp_compress(dtype, &c, data, p, dcap) : dispatch_compress(dtype, &c, data, p, dcap);
+    if (payload < 0) return -1;
     {
         uint64_t ps = (uint64_t)payload;
         memcpy(size_pos, &ps, 8);
@@ -650,29 +728,20 @@ long long orc_compress(int dtype, const orc_config *c0, const void *data, char *
     return (long long)(p - (uint8_t *)out);
 }
 
-/* SZ_decompress (api/sz.hpp:117-157) + dispatcher (:79-107) + SZGenericCompressor::decompress (:65-84) */
-int orc_decompress(int dtype, const char *cmp, size_t n, void *out, orc_config *conf_out) {
-    const uint8_t *p = (const uint8_t *)cmp;
-    uint32_t magic, ver;
-    uint64_t payload, raw_len, num;
-    orc_config c;
+/* SZ_decompress_dispatcher (api/impl/SZDispatcher.hpp:79-107) + SZGenericCompressor::decompress (:65-84): one payload */
+static int dispatch_decompress(int dtype, orc_config *cp, const uint8_t *p, uint64_t payload, void *out) {
+    orc_config c = *cp;
+    uint64_t raw_len, num;
     size_t esz = dtype == 0 ? 4 : 8;
     uint8_t *raw;
     const uint8_t *q;
     int rc = -1;
-    if (n < 17) return -1;
-    rd(&p, &magic, 4);
-    rd(&p, &ver, 4);
-    rd(&p, &payload, 8);
-    if (magic != ORC_MAGIC || ver != ORC_DATAVER || payload > n - 16) return -1;
-    if (conf_load(&c, p + payload)) return -1;
-    if (c.openmp) return -1;
+    if (payload < 8) return -1;
     num = conf_num(&c);
     memcpy(&raw_len, p, 8);
     if (c.cmprAlgo == ORC_ALGO_LOSSLESS) {
         size_t r = ZSTD_decompress(out, num * esz, p + 8, payload - 8);
         if (ZSTD_isError(r) || r != num * esz) return -1;
-        if (conf_out) *conf_out = c;
         return 0;
     }
     raw = (uint8_t *)malloc(raw_len + 16);
@@ -758,6 +827,53 @@ int orc_decompress(int dtype, const char *cmp, size_t n, void *out, orc_config *
         free(quant);
     }
     free(raw);
+    return rc;
+}
+
+/* SZ_decompress (api/sz.hpp:117-157); the payload is one dispatcher stream or the container of SZ_decompress_OMP
+ * (api/impl/SZImplOMP.hpp:120-186) */
+int orc_decompress(int dtype, const char *cmp, size_t n, void *out, orc_config *conf_out) {
+    const uint8_t *p = (const uint8_t *)cmp;
+    uint32_t magic, ver;
+    uint64_t payload;
+    orc_config c;
+    size_t esz = dtype == 0 ? 4 : 8;
+    int rc;
+    if (n < 17) return -1;
+    rd(&p, &magic, 4);
+    rd(&p, &ver, 4);
+    rd(&p, &payload, 8);
+    if (magic != ORC_MAGIC || ver != ORC_DATAVER || payload > n - 16) return -1;
+    if (conf_load(&c, p + payload)) return -1;
+    if (!c.openmp) {
+        rc = dispatch_decompress(dtype, &c, p, payload, out);
+    } else {
+        const uint8_t *q = p, *end = p + payload;
+        int32_t nslabs, t;
+        uint64_t row = conf_num(&c) / c.dims[0], off = 0;
+        orc_config *confs;
+        uint64_t *sizes;
+        if (payload < 4) return -1;
+        rd(&q, &nslabs, 4);
+        if (nslabs < 1 || (uint64_t)nslabs > c.dims[0]) return -1;
+        confs = (orc_config *)calloc((size_t)nslabs, sizeof(*confs));
+        sizes = (uint64_t *)calloc((size_t)nslabs, sizeof(*sizes));
+        rc = 0;
+        for (t = 0; t < nslabs && rc == 0; t++) {
+            if (q >= end || q + q[0] > end || conf_load(&confs[t], q)) rc = -1;
+            else q += q[0];
+        }
+        if (rc == 0 && (size_t)(end - q) < (size_t)nslabs * 8) rc = -1;
+        for (t = 0; t < nslabs && rc == 0; t++) rd(&q, &sizes[t], 8);
+        for (t = 0; t < nslabs && rc == 0; t++) {
+            uint64_t lo = (uint64_t)t * c.dims[0] / (uint64_t)nslabs;
+            if (off + sizes[t] > (uint64_t)(end - q)) { rc = -1; break; }
+            rc = dispatch_decompress(dtype, &confs[t], q + off, sizes[t], (uint8_t *)out + lo * row * esz);
+            off += sizes[t];
+        }
+        free(confs);
+        free(sizes);
+    }
     if (rc == 0 && conf_out) *conf_out = c;
     return rc;
 }

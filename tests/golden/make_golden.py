@@ -36,6 +36,8 @@ CASES = [
     ("lorenzo_reg_4d_f32", field_nd((9, 12, 20, 18), np.float32), dict(cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1e-3), "decode"),
     ("regression_rel_3d_f64", field_nd((20, 24, 28), np.float64), dict(cmprAlgo=ALGO_LORENZO_REG, errorBoundMode=EB_REL, relErrorBound=1e-4, **REG_ONLY), "cpu"),
     ("lossless_2d_f32", field_nd((64, 64), np.float32), dict(cmprAlgo=ALGO_INTERP, absErrorBound=0.0), "cpu"),
+    # OpenMP container: the slab count is the generating box's thread count and is read back from the stream
+    ("omp_container_3d_f32", field_nd((24, 30, 36), np.float32), dict(cmprAlgo=ALGO_INTERP_LORENZO, absErrorBound=1e-3, openmp=1), "cpu"),
 ]
 
 

@@ -119,3 +119,31 @@ def test_port_tuner_matches_reference(k):
     na = R.ref_compress(dtype_code(data), C.byref(conf), data.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_char_p), C.c_size_t(cap))
     nb = P.orc_compress(dtype_code(data), C.byref(conf), data.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_char_p), C.c_size_t(cap))
     assert na > 0 and na == nb and np.array_equal(a[:na], b[:nb])
+
+
+@pytest.mark.parametrize("shape,dtype,kw", [
+    ((100, 64, 64), np.float32, dict(cmprAlgo=1, absErrorBound=1e-3)),                                  # tuned slabs
+    ((37, 40, 50), np.float64, dict(cmprAlgo=ALGO_LORENZO_REG, errorBoundMode=EB_REL, relErrorBound=1e-4)),   # global range
+    ((64, 300), np.float32, dict(cmprAlgo=ALGO_INTERP, errorBoundMode=2, psnrErrorBound=70.0)),
+    ((5, 40, 50), np.float32, dict(cmprAlgo=1, absErrorBound=1e-3)),      # fewer rows than threads: one-row slabs lose a dimension
+    ((200000,), np.float32, dict(cmprAlgo=1, absErrorBound=1e-4)),        # 1-D slabs: some go to the Lorenzo stack
+])
+def test_port_openmp_container_matches_reference(shape, dtype, kw):
+    """SZ_compress_OMP / SZ_decompress_OMP (api/impl/SZImplOMP.hpp): the restatement writes the reference's container
+    byte for byte when told the reference's thread count, and decodes it to the same bits."""
+    data = field_g1(shape[0]) if len(shape) == 1 else field_nd(shape, dtype)
+    R, P = ref_lib(), port_lib()
+    conf = make_config(shape, openmp=1, **kw)
+    cap = R.ref_size_bound(dtype_code(data), C.byref(conf)) + 8192
+    a, b = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
+    na = R.ref_compress(dtype_code(data), C.byref(conf), data.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_char_p), C.c_size_t(cap))
+    # the slab count the reference just used (it lowers the OpenMP thread count for good when rows < threads)
+    threads = C.CDLL("libgomp.so.1").omp_get_max_threads()
+    pconf = make_config(shape, openmp=min(threads, shape[0]), **kw)
+    nb = P.orc_compress(dtype_code(data), C.byref(pconf), data.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_char_p), C.c_size_t(cap))
+    assert na > 0 and na == nb and np.array_equal(a[:na], b[:nb])
+    dec_r, dec_p = np.empty_like(data), np.empty_like(data)
+    cr, cp = Config(), Config()
+    assert R.ref_decompress(dtype_code(data), a.ctypes.data_as(C.c_char_p), C.c_size_t(na), dec_r.ctypes.data_as(C.c_void_p), C.byref(cr)) == 0
+    assert P.orc_decompress(dtype_code(data), a.ctypes.data_as(C.c_char_p), C.c_size_t(na), dec_p.ctypes.data_as(C.c_void_p), C.byref(cp)) == 0
+    assert np.array_equal(dec_r.view(np.uint8), dec_p.view(np.uint8))
