@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--diag", action="store_true", help="per-rank step times and host-link rate on stderr")
     ap.add_argument("--host-threads", type=int, default=None, help="host threads per rank (default: this rank's share of the cores)")
     ap.add_argument("--host-wait", type=int, default=None, help="0 = spin while waiting for the device, 1 = poll and yield")
-    ap.add_argument("--lossless-policy", type=int, default=None, help="0 = zstd on every chunk, 1 = adaptive (library default)")
+    ap.add_argument("--lossless-policy", type=int, default=None, help="0 = host zstd on every chunk, 1 = adaptive host zstd, 2 = GPU lossless stage (library default)")
     return ap.parse_args()
 
 
