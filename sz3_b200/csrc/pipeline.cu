@@ -965,7 +965,8 @@ void tune_stage(Workspace &ws, sz3b_config &conf, const T *data, int loc) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // BlockwiseDecomposition on the device (SZAlgoLorenzoReg.hpp:22-64, BlockwiseDecomposition.hpp:28-46,69-73).
-// Built so far: the single-predictor RegressionPredictor stack (config "Lorenzo=No, Regression=Yes").
+// The regression-only stack runs on blockwise.cu (fit, speculative coefficient chain, fused predict+quantize); every
+// stack with a Lorenzo predictor on the block wavefront of lorenzo.cu (run_blockwise_lorenzo below).
 // ---------------------------------------------------------------------------------------------------------------------
 void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vector<uint8_t> &out, size_t *tree_len);
 
