@@ -8,7 +8,7 @@ SRC := sz3_b200/csrc
 OBJDIR := build/obj
 LIB := sz3_b200/lib/libsz3b200.so
 LIBC := sz3_b200/lib/libSZ3c.so
-CU := api.cu pipeline.cu interp_kernels.cu encode_kernels.cu misc_kernels.cu blockwise.cu lorenzo.cu decompress.cu huffman_decode.cu zhuf_kernels.cu
+CU := api.cu pipeline.cu interp_kernels.cu interp_box.cu encode_kernels.cu misc_kernels.cu blockwise.cu lorenzo.cu decompress.cu huffman_decode.cu zhuf_kernels.cu
 CPP := huffman_host.cpp stream_host.cpp
 OBJS := $(CU:%.cu=$(OBJDIR)/%.o) $(CPP:%.cpp=$(OBJDIR)/%.o)
 HDRS := $(wildcard $(SRC)/*.hpp $(SRC)/*.cuh $(SRC)/*.h) include/sz3b.h

@@ -120,4 +120,23 @@ struct DevCtx2 {
     }
 };
 
+// Same counting scheme as DevCtx2 with the rare path inline: a called function, however rarely taken, makes the
+// compiler give up every value it keeps in uniform registers across the call site (box schedule, interp_box.cu).
+struct DevCtxBox : DevCtx2 {
+    __device__ __forceinline__ DevCtxBox(unsigned *sh, unsigned long long *gh, int radius) : DevCtx2(sh, gh, radius) {}
+    __device__ __forceinline__ void hist_add(int sym, bool active) {
+        if (!active) return;
+        const unsigned k8 = static_cast<unsigned>(sym - lo8);
+        if (k8 < 8u) {
+            packed += 1ull << (k8 * 8u);
+            return;
+        }
+        const unsigned k = static_cast<unsigned>(sym - lo);
+        if (k < static_cast<unsigned>(kHistWindow))
+            atomicAdd(&shist[k], 1u);
+        else
+            atomicAdd(&ghist[sym], 1ull);
+    }
+};
+
 }  // namespace sz3b

@@ -1,0 +1,199 @@
+// sz3_b200/csrc/interp_box.cu -- __global__ wrapper + launcher of the box schedule (interp_box.cuh): the fused
+// interpolation-predict + LinearQuantizer kernel of the finest level for float data, pass order z, y, x.
+//
+// Staging: every raw z-plane of a tile (33 rows x 36 floats) comes in by one TMA box copy (cp.async.bulk.tensor.3d,
+// completion on the warp's mbarrier); the warp that owns the plane re-arms its slot for its next plane as soon as
+// the rows of the current plane sit in registers, so the copy runs under the pass-2 arithmetic.  Two CTAs of eight
+// warps per SM (88 KB of shared memory each) cover each other's phase-A latency.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "device_ctx.cuh"
+#include "interp_box.cuh"
+#include "launch.hpp"
+
+namespace sz3b {
+
+namespace {
+
+constexpr int kBoxEEPad = 9568;   // EE floats rounded up to a multiple of 32 (128 B)
+constexpr size_t kBoxSmem = sizeof(float) * (kBoxWarps * kBoxSlotStride + kBoxEEPad) + sizeof(uint16_t) * kBoxWarps * kBoxStageU16 +
+                            sizeof(unsigned) * kHistWindow + sizeof(uint64_t) * kBoxWarps;
+constexpr unsigned kBoxPlaneBytes = kBoxSlotElems * sizeof(float);   // what one TMA box delivers (zero fill included)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    const unsigned a = smem_u32(bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_plane(float *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
+template <bool CUBIC>
+__global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_constant__ CUtensorMap tmap, BoxArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *const slots = reinterpret_cast<float *>(smem_raw);
+    float *const EE = slots + kBoxWarps * kBoxSlotStride;
+    uint16_t *const stages = reinterpret_cast<uint16_t *>(EE + kBoxEEPad);
+    unsigned *const shist = reinterpret_cast<unsigned *>(stages + kBoxWarps * kBoxStageU16);
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(shist + kHistWindow);
+    __shared__ BoxTile T;
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t tile = blockIdx.x + A.tile0;
+    BoxOrigin o;
+    box_origin(A, tile, o);
+    float *const slot = slots + warp * kBoxSlotStride;
+    uint16_t *const stage = stages + warp * kBoxStageU16;
+    uint64_t *const bar = bars + warp;
+    const uint32_t nz = o.n[0];
+    uint32_t z = (o.begin[0] ? 1u : 0u) + warp;   // planes of this warp: z, z + 8, ...
+    const int x0 = static_cast<int>(o.begin[2]), y0 = static_cast<int>(o.begin[1]), z0 = static_cast<int>(o.begin[0]);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        if (z < nz) {   // the first plane travels while phase A runs
+            mbar_expect_tx(bar, kBoxPlaneBytes);
+            tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z));
+        }
+    }
+    DevCtxBox ctx(shist, A.hist, A.qp.radius);
+    for (int i = tid; i < kHistWindow; i += kBoxThreads) shist[i] = 0;
+    if (tid == 0) box_tile_setup<CUBIC>(A, tile, o, T);
+    // ---- phase A: EE, pass 0 ----------------------------------------------------------------------------------------
+    box_fill_column(A, o, tid, EE);
+    if (tid < 33) box_fill_column(A, o, 256 + tid, EE);
+    fill_copy_wait();
+    __syncthreads();
+    box_pass0_line<CUBIC>(A, ctx, T, tid, EE);
+    for (uint32_t e = tid; e < 33u * 16u; e += kBoxThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE);
+    __syncthreads();
+    // ---- phase B: the warp's planes -----------------------------------------------------------------------------------
+    const uint32_t lowy = T.low[1], c1y = T.c1[1];
+    unsigned parity = 0;
+    for (; z < nz; z += kBoxWarps) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        const float *const EEz = EE + z * kBoxEEPlane;
+        box_merge(T, lane, EEz, slot);
+        box_pass1_lane<CUBIC>(A, ctx, T, lane, z, EEz, slot);
+        box_pass1_left<CUBIC>(A, ctx, T, lane, z, EEz, slot);
+        __syncwarp();
+        float v[36];
+        if (lane < c1y) {
+            const float4 *row = reinterpret_cast<const float4 *>(slot + (lane + lowy) * kBoxPitch);
+#pragma unroll
+            for (int c = 0; c < 9; c++) {
+                const float4 f = row[c];
+                v[4 * c] = f.x;
+                v[4 * c + 1] = f.y;
+                v[4 * c + 2] = f.z;
+                v[4 * c + 3] = f.w;
+            }
+        }
+        box_pass2_left<CUBIC>(A, ctx, T, lane, z, slot, stage);
+        __syncwarp();
+        if (lane == 0 && z + kBoxWarps < nz) {   // slot free: the next plane comes in under the arithmetic of this one
+            fence_proxy_async();
+            mbar_expect_tx(bar, kBoxPlaneBytes);
+            tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z + kBoxWarps));
+        }
+        if (lane < c1y) box_pass2_row<CUBIC>(A, ctx, T, lane, z, v, stage);
+        __syncwarp();
+        box_copy_out(A, T, lane, z, stage);
+        __syncwarp();
+    }
+    ctx.pass_end();
+    ctx.flush();
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+}  // namespace
+
+// Can the level with stride A.s run on the box schedule?  (float / 16-bit indices by type; pass order z, y, x; every
+// tile 32 or 33 points wide; rows 16-byte aligned for the tensor map.)
+bool interp_box_applicable(const BoxArgs &A, uint64_t ntiles_level) {
+    if (A.s != 1 || A.sh.N != 3 || A.sh.perm[0] != 0 || A.sh.perm[1] != 1 || A.sh.perm[2] != 2) return false;
+    if ((reinterpret_cast<uintptr_t>(A.data) & 15u) || (A.sh.dims[2] & 3u)) return false;
+    if ((reinterpret_cast<uintptr_t>(A.q) & 15u)) return false;
+    for (int d = 0; d < 3; d++) {
+        // tiles are 33 points wide except the last one, which holds ((dims - 1) % 32) + 1
+        if (((A.sh.dims[d] - 1) % kInterpBlock) + 1 != 32) return false;
+    }
+    (void)ntiles_level;
+    return encode_tiled_fn() != nullptr;
+}
+
+// Launches tiles [A.tile0, A.tile0 + ntiles) of the level.  Returns false when the tensor map cannot be encoded
+// (the caller then takes the line-walker kernel).
+bool interp_launch_box(const BoxArgs &A, uint64_t ntiles, cudaStream_t st) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {A.sh.dims[2], A.sh.dims[1], A.sh.dims[0]};
+    const cuuint64_t gstr[2] = {A.sh.stride[1] * sizeof(float), A.sh.stride[0] * sizeof(float)};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(kBoxPitch), 33u, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(A.data), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_interp_box<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxSmem));
+        cudaFuncSetAttribute(k_interp_box<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxSmem));
+        attr_set = true;
+    }
+    const dim3 grid(static_cast<unsigned>(ntiles));
+    if (A.sh.cubic)
+        k_interp_box<true><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A);
+    else
+        k_interp_box<false><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A);
+    return true;
+}
+
+}  // namespace sz3b

@@ -1,0 +1,521 @@
+// sz3_b200/csrc/interp_box.cuh -- fifth-generation N == 3 tile schedule of the fused interpolation-predict +
+// LinearQuantizer kernel (InterpolationDecomposition::compress, reference
+// include/SZ3/decomposition/InterpolationDecomposition.hpp:99-143, :309-402; LinearQuantizer.hpp:43-71) for the
+// configuration the auto-tuner picks most often: float data, pass order z, y, x (interpDirection 0), tiles whose
+// three extents are 32 or 33 points (every tile of an array whose dims are multiples of 32, e.g. 512^3 / 2048^3).
+//
+// Same closed-tile mathematics as the earlier generations (a level block recomputed standalone
+// from {original values} U {final reconstruction of its coarse points} reproduces the reference bit for bit), but the
+// work is cut so that no thread ever decodes an index:
+//
+//   phase A (CTA)   EE = the sub-lattice even in y and x (33 x 17 x 17): coarse points from recon2, the rest from the
+//                   input; thread c owns the z-line c = y' * 17 + x': it fills the line, then predicts + quantizes its
+//                   16 targets from registers (pass 0, fully unrolled, stencil per target known at compile time).
+//   phase B (warp)  after pass 0 the z-planes are independent.  A warp owns planes z = low + w, + 8, ...; the raw plane
+//                   (33 rows x 36 floats) arrives in the warp's slot by ONE TMA box copy (cp.async.bulk.tensor), the
+//                   even-even points are overwritten with EE, pass 1 runs on lanes (x', half of the targets), pass 2
+//                   on lanes = rows: a lane reads its whole row with nine 16-byte shared-memory loads (row pitch of
+//                   nine 16-byte chunks: conflict-free) and walks its 16 targets from registers.
+//
+// Index positions are closed forms of (z, y, x) with per-tile multipliers (BoxTile); the 14 (or 13..16) main-phase
+// indices of a row are staged in shared memory so that a plane's run leaves as 16-byte stores.
+//
+// The per-lane phase functions below are plain inline code: tests/emul runs them lane by lane on the CPU (with a
+// host copy standing in for the TMA box) against the reference before any GPU time is spent.
+#pragma once
+#include "core.cuh"
+#include "interp_body.cuh"
+#include "interp_line.cuh"
+
+namespace sz3b {
+
+constexpr int kBoxWarps = 8;
+constexpr int kBoxThreads = kBoxWarps * 32;
+constexpr int kBoxPitch = 36;                    // floats per slot row: 144 B = nine 16-byte chunks
+constexpr int kBoxSlotElems = 33 * kBoxPitch;    // one raw plane
+constexpr int kBoxSlotStride = 1216;             // floats between the slots of two warps (4864 B, a multiple of 128 B)
+constexpr int kBoxEEPlane = 17 * 17;
+constexpr int kBoxEEElems = 33 * kBoxEEPlane;
+constexpr int kBoxStageU16 = 576;                // per warp: 8 (misalignment) + 33 rows * 16 indices, rounded up
+
+using BoxArgs = InterpArgs<float, uint16_t>;
+
+#ifdef __CUDACC__
+using BoxChunk = uint4;
+#else
+struct alignas(16) BoxChunk {
+    uint32_t w[4];
+};
+#endif
+
+// Per-tile constants (shared memory; written by one thread while the others fill EE).
+struct BoxTile {
+    uint32_t n[3];       // points per dim (32 or 33), natural order z, y, x
+    uint32_t low[3];     // 1 when the low face belongs to the previous tile (begin > 0)
+    uint32_t C[3];       // lattice points at step 2: (n + 1) / 2
+    uint32_t c1[3];      // owned points at step 1: n - low
+    uint32_t c2[3];      // owned lattice points at step 2: C - low
+    uint32_t mainc[3];   // targets of the main sub-phase along the dim
+    uint32_t pb[3];      // first index of each pass, relative to qbase
+    uint32_t other[3];   // lines of each pass (product of the owned counts of the two other dims)
+    uint64_t qbase;      // position of the tile's first index in the stream
+};
+
+// What every thread needs before BoxTile is ready (a few integer operations, recomputed per thread).
+struct BoxOrigin {
+    uint32_t begin[3], n[3];
+    uint64_t gbase, g2base;
+};
+
+SZ_HD void box_origin(const BoxArgs &A, uint32_t tile, BoxOrigin &o) {
+    uint32_t bidx[3];
+    uint32_t r = tile;
+    bidx[2] = r % A.nb[2];
+    r /= A.nb[2];
+    bidx[1] = r % A.nb[1];
+    bidx[0] = r / A.nb[1];
+    const uint32_t B = kInterpBlock * A.s;
+    o.gbase = 0;
+    o.g2base = 0;
+    for (int d = 0; d < 3; d++) {
+        const uint32_t b = bidx[d] * B;
+        uint32_t e = b + B;
+        if (e > A.sh.dims[d] - 1) e = A.sh.dims[d] - 1;
+        o.begin[d] = b;
+        o.n[d] = (e - b) / A.s + 1;
+        o.gbase += static_cast<uint64_t>(b) * A.sh.stride[d];
+        o.g2base += static_cast<uint64_t>(b >> 1) * A.stride2[d];
+    }
+}
+
+// Host + device: can this tile take the box schedule?
+SZ_HD bool box_tile_ok(const BoxOrigin &o) {
+    return (o.n[0] == 32 || o.n[0] == 33) && (o.n[1] == 32 || o.n[1] == 33) && (o.n[2] == 32 || o.n[2] == 33);
+}
+
+template <bool CUBIC>
+SZ_HD void box_tile_setup(const BoxArgs &A, uint32_t tile, const BoxOrigin &o, BoxTile &T) {
+    for (int d = 0; d < 3; d++) {
+        const uint32_t n = o.n[d], low = o.begin[d] ? 1u : 0u;
+        T.n[d] = n;
+        T.low[d] = low;
+        T.C[d] = (n + 1) / 2;
+        T.c1[d] = n - low;
+        T.c2[d] = (n + 1) / 2 - low;
+        T.mainc[d] = CUBIC ? (n - 7) / 2 + 1 : (n - 1) / 2;
+    }
+    // boundary sub-phases along a dim: cubic i = 1 and (n odd: n-2 | n even: n-3, n-1); linear n even: n-1
+    uint32_t nbnd[3];
+    for (int d = 0; d < 3; d++) nbnd[d] = CUBIC ? ((T.n[d] & 1u) ? 2u : 3u) : ((T.n[d] & 1u) ? 0u : 1u);
+    T.other[0] = T.c2[1] * T.c2[2];
+    T.other[1] = T.c1[0] * T.c2[2];
+    T.other[2] = T.c1[0] * T.c1[1];
+    T.pb[0] = 0;
+    T.pb[1] = (T.mainc[0] + nbnd[0]) * T.other[0];
+    T.pb[2] = T.pb[1] + (T.mainc[1] + nbnd[1]) * T.other[1];
+    T.qbase = A.block_base[tile];
+}
+
+// Sub-phase of target k (local index 2k + 1) on a line of n = 33 (n_odd) or 32 points: true = main sub-phase with
+// index idx inside it, false = boundary sub-phase number idx (reference order, InterpolationDecomposition.hpp:334-400).
+// With k a compile-time constant everything but the last two targets folds away.
+template <bool CUBIC>
+SZ_HD bool box_class(uint32_t k, bool n_odd, uint32_t &idx) {
+    if (CUBIC) {
+        if (k == 0) {
+            idx = 0;
+            return false;
+        }
+        if (k <= 13) {
+            idx = k - 1;
+            return true;
+        }
+        if (k == 14) {            // i = 29: main for n = 33, the n-3 boundary for n = 32
+            idx = n_odd ? 13u : 1u;
+            return n_odd;
+        }
+        idx = n_odd ? 1u : 2u;    // i = 31: n-2 (n = 33) or n-1 (n = 32)
+        return false;
+    }
+    if (k <= 14) {
+        idx = k;
+        return true;
+    }
+    idx = n_odd ? 15u : 0u;       // i = 31: main for n = 33, the tail for n = 32
+    return n_odd;
+}
+
+// Prediction of target k from the line's values v[local index] (n = 32 or 33 points); rec_prev = reconstruction of
+// target k - 1 (the linear tail of an even line needs it).  k is a compile-time constant after unrolling.
+template <bool CUBIC>
+SZ_HD float box_pred(const float *v, int k, bool n_odd, float rec_prev) {
+    if (CUBIC) {
+        if (k == 0) return interp_quad_1<float>(v[0], v[2], v[4]);
+        if (k <= 13) return interp_cubic<float>(v[2 * k - 2], v[2 * k], v[2 * k + 2], v[2 * k + 4]);
+        if (k == 14)
+            return n_odd ? interp_cubic<float>(v[26], v[28], v[30], v[32]) : interp_quad_2<float>(v[26], v[28], v[30]);
+        return n_odd ? interp_quad_2<float>(v[28], v[30], v[32]) : interp_linear1<float>(v[28], v[30]);
+    }
+    if (k <= 14) return interp_linear<float>(v[2 * k], v[2 * k + 2]);
+    return n_odd ? interp_linear<float>(v[30], v[32]) : interp_linear1<float>(rec_prev, v[30]);
+}
+
+// Where a line's indices go: the main sub-phase at qm[idx * main_mul], boundary sub-phase j at qm[bnd0 + j * other]
+// (element offsets relative to qm; everything a register after inlining).  ub is the same place in unpred_tmp.
+struct BoxEmit {
+    uint16_t *qm;
+    float *um;
+    uint32_t main_mul, bnd0, other;
+};
+template <bool CUBIC, class Ctx>
+SZ_HD void box_emit(const BoxEmit &E, Ctx &ctx, uint32_t k, bool n_odd, int qv, float orig, bool owned) {
+    uint32_t idx;
+    const bool in_main = box_class<CUBIC>(k, n_odd, idx);
+    const uint32_t off = in_main ? idx * E.main_mul : E.bnd0 + idx * E.other;
+    if (owned) {
+        E.qm[off] = static_cast<uint16_t>(qv);
+        if (qv == 0) E.um[off] = orig;
+    }
+    ctx.hist_add(qv, owned);
+}
+
+// One target through the reference's own line predictor (core.cuh: predict_line): the few lines / rows / columns
+// that do not fit the lane mappings (the 17th lattice column, a 33rd owned row, z-lines 256..288).
+// ld(l) = current value at local index l, st(l, v) stores a reconstruction, em(k, qv, orig) emits.
+template <bool CUBIC, class Ld, class St, class Em>
+SZ_HD void box_generic_target(uint32_t k, uint32_t n, const QuantParams &qp, Ld &&ld, St &&st, Em &&em) {
+    const bool tail_pair = !CUBIC && !(n & 1u);   // linear, even n: target n-1 needs the reconstruction of n-3
+    if (tail_pair && 2 * k + 1 == n - 1) return;  // done together with its predecessor
+    const uint32_t i = 2 * k + 1;
+    float pred = predict_line<float>(CUBIC ? 1 : 0, i, n, ld, 0.0f);
+    float orig = ld(i), rec;
+    int qv = quantize<float>(orig, pred, qp, rec);
+    st(i, rec);
+    em(k, qv, orig);
+    if (tail_pair && i + 2 == n - 1) {
+        pred = interp_linear1<float>(rec, ld(i + 1));
+        orig = ld(i + 2);
+        qv = quantize<float>(orig, pred, qp, rec);
+        st(i + 2, rec);
+        em(k + 1, qv, orig);
+    }
+}
+// runtime-k twin of box_emit for the generic targets
+template <bool CUBIC, class Ctx>
+SZ_HD void box_emit_rt(const BoxEmit &E, Ctx &ctx, uint32_t k, bool n_odd, int qv, float orig, bool owned) {
+    uint32_t idx = 0;
+    bool in_main = false;
+    if (CUBIC) {
+        if (k >= 1 && k <= 13) { in_main = true; idx = k - 1; }
+        else if (k == 0) idx = 0;
+        else if (k == 14) { in_main = n_odd; idx = n_odd ? 13u : 1u; }
+        else idx = n_odd ? 1u : 2u;
+    } else {
+        if (k <= 14) { in_main = true; idx = k; }
+        else { in_main = n_odd; idx = n_odd ? 15u : 0u; }
+    }
+    const uint32_t off = in_main ? idx * E.main_mul : E.bnd0 + idx * E.other;
+    if (owned) {
+        E.qm[off] = static_cast<uint16_t>(qv);
+        if (qv == 0) E.um[off] = orig;
+    }
+    ctx.hist_add(qv, owned);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// phase A: EE fill, thread c fills z-line c (c = y' * 17 + x'); asynchronous 4-byte copies, one wait at the end
+// ---------------------------------------------------------------------------------------------------------------------
+SZ_HD void box_fill_column(const BoxArgs &A, const BoxOrigin &o, uint32_t c, float *EE) {
+    const uint32_t yl = c / 17u, xl = c - yl * 17u;
+    if (yl >= (o.n[1] + 1) / 2 || xl >= (o.n[2] + 1) / 2) return;
+    const uint32_t s = A.s;
+    // coarse points (z even): recon2 offset of local (2a, 2b, 2c) is g2base + (a*stride2[0] + b*stride2[1] + c) * s
+    const float *rc = A.recon2 + o.g2base + static_cast<uint64_t>(yl) * s * A.stride2[1] + static_cast<uint64_t>(xl) * s;
+    const uint64_t rstep = static_cast<uint64_t>(s) * A.stride2[0];
+    // originals (z odd) at local (z, 2y', 2x')
+    const float *gp = A.data + o.gbase + static_cast<uint64_t>(2 * yl) * s * A.sh.stride[1] + static_cast<uint64_t>(2 * xl) * s;
+    const uint64_t gstep = static_cast<uint64_t>(s) * A.sh.stride[0];
+    float *dst = EE + c;
+    const uint32_t nz = o.n[0];
+    for (uint32_t z = 0; z < nz; z += 2) {
+        fill_copy(dst + z * kBoxEEPlane, rc + (z >> 1) * rstep);
+        if (z + 1 < nz) fill_copy(dst + (z + 1) * kBoxEEPlane, gp + (z + 1) * gstep);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pass 0 (along z), thread c < 256 on its own z-line; everything from registers
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool CUBIC, class Ctx>
+SZ_HD void box_pass0_line(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t c, float *EE) {
+    const uint32_t yl = c / 17u, xl = c - yl * 17u;
+    if (yl >= T.C[1] || xl >= T.C[2]) return;
+    const bool n_odd = T.n[0] & 1u;
+    const uint32_t lowy = T.low[1], lowx = T.low[2], c2x = T.c2[2], other = T.other[0], mainc = T.mainc[0];
+    const uint64_t base = T.qbase;   // pb[0] == 0
+    float v[33];
+#pragma unroll
+    for (int z = 0; z < 32; z++) v[z] = EE[z * kBoxEEPlane + c];
+    v[32] = n_odd ? EE[32 * kBoxEEPlane + c] : 0.0f;
+    const bool owned = yl >= lowy && xl >= lowx;
+    const uint32_t line_rank = (yl - lowy) * c2x + (xl - lowx);
+    BoxEmit E;
+    E.qm = A.q + base + line_rank;
+    E.um = A.unpred_tmp + base + line_rank;
+    E.main_mul = other;
+    E.bnd0 = mainc * other;
+    E.other = other;
+    const QuantParams qp = A.qp;
+    float *const col = EE + c;
+    float rec_prev = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const float pred = box_pred<CUBIC>(v, k, n_odd, rec_prev);
+        const float orig = v[2 * k + 1];
+        float rec;
+        const int qv = quantize<float>(orig, pred, qp, rec);
+        rec_prev = rec;
+        col[(2 * k + 1) * kBoxEEPlane] = rec;
+        box_emit<CUBIC>(E, ctx, k, n_odd, qv, orig, owned);
+    }
+}
+
+// z-lines 256..288 (the 17th lattice row / column spill-over of the 256-thread mapping): item e = (line, target)
+template <bool CUBIC, class Ctx>
+SZ_HD void box_pass0_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t e, float *EE) {
+    const uint32_t c = 256u + (e >> 4), k = e & 15u;
+    if (c >= static_cast<uint32_t>(kBoxEEPlane)) return;
+    const uint32_t yl = c / 17u, xl = c - yl * 17u;
+    if (yl >= T.C[1] || xl >= T.C[2]) return;
+    const uint32_t nz = T.n[0];
+    const bool owned = yl >= T.low[1] && xl >= T.low[2];
+    const uint32_t line_rank = (yl - T.low[1]) * T.c2[2] + (xl - T.low[2]);
+    BoxEmit E;
+    E.qm = A.q + T.qbase + line_rank;
+    E.um = A.unpred_tmp + T.qbase + line_rank;
+    E.main_mul = T.other[0];
+    E.bnd0 = T.mainc[0] * T.other[0];
+    E.other = T.other[0];
+    box_generic_target<CUBIC>(
+        k, nz, A.qp, [&](uint32_t l) { return EE[l * kBoxEEPlane + c]; },
+        [&](uint32_t l, float r) { EE[l * kBoxEEPlane + c] = r; },
+        [&](uint32_t kk, int qv, float orig) { box_emit_rt<CUBIC>(E, ctx, kk, nz & 1u, qv, orig, owned); });
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// phase B, per warp and plane z.  slot = the raw plane [33][36]; EEz = EE + z * 289.
+// ---------------------------------------------------------------------------------------------------------------------
+// even-even points of the plane take their current values (coarse points, pass-0 reconstructions)
+SZ_HD void box_merge(const BoxTile &T, uint32_t lane, const float *EEz, float *slot) {
+    const uint32_t xl = lane & 15u, h = lane >> 4;
+    const uint32_t Cy = T.C[1];
+    for (uint32_t yl = h; yl < Cy; yl += 2) slot[2 * yl * kBoxPitch + 2 * xl] = EEz[yl * 17 + xl];
+    if (T.C[2] == 17 && lane < Cy) slot[2 * lane * kBoxPitch + 32] = EEz[lane * 17 + 16];
+}
+
+// stencils of pass 1 whose kind depends on the lane: four taps with coefficients (unused taps are zero, never NaN)
+enum { BOX_ST_CUBIC = 0, BOX_ST_QUAD1 = 1, BOX_ST_QUAD2 = 2, BOX_ST_LINEAR1 = 3 };
+SZ_HD float box_stencil4(uint32_t kind, float w0, float w1, float w2, float w3) {
+    // (((c0*w0 + c1*w1) + c2*w2) + c3*w3) * sc evaluates cubic / quad_1 / quad_2 in the reference's operation order
+    const float c0 = kind == BOX_ST_QUAD1 ? 0.0f : -1.0f;
+    const float c1 = kind == BOX_ST_CUBIC ? 9.0f : (kind == BOX_ST_QUAD1 ? 3.0f : 6.0f);
+    const float c2 = kind == BOX_ST_CUBIC ? 9.0f : (kind == BOX_ST_QUAD1 ? 6.0f : 3.0f);
+    const float c3 = kind == BOX_ST_QUAD2 ? 0.0f : -1.0f;
+    const float sc = kind == BOX_ST_CUBIC ? 0.0625f : 0.125f;
+    const float p = (((c0 * w0 + c1 * w1) + c2 * w2) + c3 * w3) * sc;
+    return kind == BOX_ST_LINEAR1 ? interp_linear1<float>(w0, w1) : p;
+}
+
+// pass 1 (along y): lane = (x' = lane & 15, half h of the 16 targets); neighbours from EE (conflict-free), targets
+// read and overwritten in the slot
+template <bool CUBIC, class Ctx>
+SZ_HD void box_pass1_lane(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z, const float *EEz,
+                          float *slot) {
+    const uint32_t xl = lane & 15u, h = lane >> 4;
+    const bool n_odd = T.n[1] & 1u;
+    const int jmax = n_odd ? 16 : 15;             // last lattice index along y
+    const uint32_t lowx = T.low[2], c2x = T.c2[2], mainc = T.mainc[1], other = T.other[1];
+    const uint32_t rz = z - T.low[0];
+    const uint64_t base = T.qbase + T.pb[1];
+    // window w[m] = value at lattice index jb + m, jb = -1 (h = 0) or 7 (h = 1); target t (k = 8h + t) uses w[t .. t+3]
+    const int jb = h ? 7 : -1;
+    float w[11];
+#pragma unroll
+    for (int m = 0; m < 11; m++) {
+        const int j = jb + m;
+        w[m] = (j >= 0 && j <= jmax) ? EEz[j * 17 + static_cast<int>(xl)] : 0.0f;
+    }
+    const bool owned = xl >= lowx;
+    const uint32_t line_rank = rz * c2x + (xl - lowx);
+    // main: (rz * mainc + idx) * c2x + rx; boundary j: (mainc + j) * other + rz * c2x + rx
+    BoxEmit E;
+    const uint32_t m0 = rz * mainc * c2x + (xl - lowx);
+    E.qm = A.q + base + m0;
+    E.um = A.unpred_tmp + base + m0;
+    E.main_mul = c2x;
+    E.bnd0 = mainc * other + line_rank - m0;
+    E.other = other;
+    const QuantParams qp = A.qp;
+    float *const col = slot + 2 * xl + h * (16 * kBoxPitch);
+    float rec_prev = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        float pred;
+        if (CUBIC) {
+            if (t >= 1 && t <= 5) {
+                pred = interp_cubic<float>(w[t], w[t + 1], w[t + 2], w[t + 3]);
+            } else {
+                uint32_t kind = BOX_ST_CUBIC;
+                if (t == 0 && h == 0) kind = BOX_ST_QUAD1;
+                if (t == 6 && h == 1 && !n_odd) kind = BOX_ST_QUAD2;
+                if (t == 7 && h == 1) kind = n_odd ? BOX_ST_QUAD2 : BOX_ST_LINEAR1;
+                pred = box_stencil4(kind, w[t], w[t + 1], w[t + 2], w[t + 3]);
+            }
+        } else {
+            pred = interp_linear<float>(w[t + 1], w[t + 2]);
+            if (t == 7 && h == 1 && !n_odd) pred = interp_linear1<float>(rec_prev, w[t + 1]);
+        }
+        const float orig = col[(2 * t + 1) * kBoxPitch];
+        float rec;
+        const int qv = quantize<float>(orig, pred, qp, rec);
+        rec_prev = rec;
+        col[(2 * t + 1) * kBoxPitch] = rec;
+        // sub-phase of k = 8h + t: the lower half is compile-time, the upper half differs only for t = 6, 7
+        if (h == 0)
+            box_emit<CUBIC>(E, ctx, t, n_odd, qv, orig, owned);
+        else
+            box_emit<CUBIC>(E, ctx, 8 + t, n_odd, qv, orig, owned);
+    }
+}
+
+// the 17th lattice column (x = 32) of pass 1: lane = target
+template <bool CUBIC, class Ctx>
+SZ_HD void box_pass1_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z, const float *EEz,
+                          float *slot) {
+    if (T.C[2] != 17 || lane >= 16) return;
+    const uint32_t ny = T.n[1];
+    const uint32_t rz = z - T.low[0], rx = 16u - T.low[2];
+    const uint32_t line_rank = rz * T.c2[2] + rx;
+    const uint32_t m0 = rz * T.mainc[1] * T.c2[2] + rx;
+    const uint64_t base = T.qbase + T.pb[1];
+    BoxEmit E;
+    E.qm = A.q + base + m0;
+    E.um = A.unpred_tmp + base + m0;
+    E.main_mul = T.c2[2];
+    E.bnd0 = T.mainc[1] * T.other[1] + line_rank - m0;
+    E.other = T.other[1];
+    box_generic_target<CUBIC>(
+        lane, ny, A.qp,
+        [&](uint32_t l) { return (l & 1u) ? slot[l * kBoxPitch + 32] : EEz[(l >> 1) * 17 + 16]; },
+        [&](uint32_t l, float r) { slot[l * kBoxPitch + 32] = r; },
+        [&](uint32_t kk, int qv, float orig) { box_emit_rt<CUBIC>(E, ctx, kk, ny & 1u, qv, orig, true); });
+}
+
+// Position of a plane's main-phase run of pass 2 and its misalignment (in indices) against 16-byte chunks.
+SZ_HD uint64_t box_run_pos(const BoxTile &T, uint32_t z) {
+    return T.qbase + T.pb[2] + static_cast<uint64_t>((z - T.low[0]) * T.c1[1]) * T.mainc[2];
+}
+
+// pass 2 (along x), lane = row: `v` are the row's 36 floats (registers).  Main-phase indices go to the warp's
+// staging buffer at the row's place inside the plane's run; boundary sub-phases straight to global memory (lanes
+// sit on consecutive positions).
+struct BoxRowOut {
+    uint16_t *srow;      // staging: main sub-phase of this row
+    uint16_t *qb;        // global: boundary sub-phase 0 of this row
+    float *um, *ub;      // unpred_tmp at the same two places
+    uint32_t other;
+};
+template <class Ctx>
+SZ_HD void box_row_out(const BoxArgs &A, const BoxTile &T, uint32_t ry, uint32_t z, uint16_t *stage, BoxRowOut &R) {
+    const uint32_t mainc = T.mainc[2], c1y = T.c1[1];
+    const uint32_t line_rank = (z - T.low[0]) * c1y + ry;
+    const uint64_t base = T.qbase + T.pb[2];
+    const uint32_t mis = static_cast<uint32_t>(base + static_cast<uint64_t>((z - T.low[0]) * c1y) * mainc) & 7u;
+    R.srow = stage + mis + ry * mainc;
+    R.other = T.other[2];
+    R.qb = A.q + base + mainc * R.other + line_rank;
+    R.ub = A.unpred_tmp + base + mainc * R.other + line_rank;
+    R.um = A.unpred_tmp + base + line_rank * mainc;
+}
+template <bool CUBIC, class Ctx>
+SZ_HD void box_row_emit(const BoxRowOut &R, Ctx &ctx, bool in_main, uint32_t idx, int qv, float orig) {
+    if (in_main) {
+        R.srow[idx] = static_cast<uint16_t>(qv);
+        if (qv == 0) R.um[idx] = orig;
+    } else {
+        R.qb[idx * R.other] = static_cast<uint16_t>(qv);
+        if (qv == 0) R.ub[idx * R.other] = orig;
+    }
+    ctx.hist_add(qv, true);
+}
+
+template <bool CUBIC, class Ctx>
+SZ_HD void box_pass2_row(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t ry, uint32_t z, const float *v,
+                         uint16_t *stage) {
+    const bool n_odd = T.n[2] & 1u;
+    BoxRowOut R;
+    box_row_out<Ctx>(A, T, ry, z, stage, R);
+    const QuantParams qp = A.qp;
+    float rec_prev = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const float pred = box_pred<CUBIC>(v, k, n_odd, rec_prev);
+        const float orig = v[2 * k + 1];
+        float rec;
+        const int qv = quantize<float>(orig, pred, qp, rec);
+        rec_prev = rec;
+        uint32_t idx;
+        const bool in_main = box_class<CUBIC>(k, n_odd, idx);
+        box_row_emit<CUBIC>(R, ctx, in_main, idx, qv, orig);
+    }
+}
+
+// a 33rd owned row (tiles at y = 0 with 33 points): lane = target, values from the slot
+template <bool CUBIC, class Ctx>
+SZ_HD void box_pass2_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z, const float *slot,
+                          uint16_t *stage) {
+    if (T.c1[1] != 33 || lane >= 16) return;
+    const uint32_t nx = T.n[2];
+    BoxRowOut R;
+    box_row_out<Ctx>(A, T, 32u, z, stage, R);   // low == 0 here: row 32 is local y = 32
+    const float *row = slot + 32 * kBoxPitch;
+    box_generic_target<CUBIC>(
+        lane, nx, A.qp, [&](uint32_t l) { return row[l]; }, [&](uint32_t, float) {},
+        [&](uint32_t kk, int qv, float orig) {
+            // runtime twin of box_class
+            const bool n_odd = nx & 1u;
+            uint32_t idx = 0;
+            bool in_main = false;
+            if (CUBIC) {
+                if (kk >= 1 && kk <= 13) { in_main = true; idx = kk - 1; }
+                else if (kk == 0) idx = 0;
+                else if (kk == 14) { in_main = n_odd; idx = n_odd ? 13u : 1u; }
+                else idx = n_odd ? 1u : 2u;
+            } else {
+                if (kk <= 14) { in_main = true; idx = kk; }
+                else { in_main = n_odd; idx = n_odd ? 15u : 0u; }
+            }
+            box_row_emit<CUBIC>(R, ctx, in_main, idx, qv, orig);
+        });
+}
+
+// staging buffer -> index stream: the plane's run [pos, pos + len) starts `mis` indices into a 16-byte chunk, and the
+// staging buffer is laid out with the same misalignment, so whole chunks move as 16-byte loads / stores
+SZ_HD void box_copy_out(const BoxArgs &A, const BoxTile &T, uint32_t lane, uint32_t z, const uint16_t *stage) {
+    const uint64_t pos = box_run_pos(T, z);
+    const uint32_t len = T.c1[1] * T.mainc[2];
+    const uint32_t mis = static_cast<uint32_t>(pos) & 7u;
+    uint16_t *const g0 = A.q + (pos - mis);     // 16-byte aligned (A.q is)
+    const uint32_t end = mis + len;
+    const uint32_t nchunks = (end + 7) / 8;
+    for (uint32_t c = lane; c < nchunks; c += 32) {
+        const uint32_t a = c * 8, b = a + 8;
+        if (a >= mis && b <= end) {
+            *reinterpret_cast<BoxChunk *>(g0 + a) = *reinterpret_cast<const BoxChunk *>(stage + a);
+        } else {
+            for (uint32_t e = a < mis ? mis : a; e < (b < end ? b : end); e++) g0[e] = stage[e];
+        }
+    }
+}
+
+}  // namespace sz3b

@@ -27,6 +27,10 @@ template <class T, class QT>
 bool interp_launch_lean(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, bool write_work, bool recover, const T *unpred_in,
                         cudaStream_t st);
 
+// interp_box.cu: box schedule of the finest level (float data, 16-bit indices, pass order z, y, x)
+bool interp_box_applicable(const InterpArgs<float, uint16_t> &A, uint64_t ntiles_level);
+bool interp_launch_box(const InterpArgs<float, uint16_t> &A, uint64_t ntiles, cudaStream_t st);
+
 // encode_kernels.cu
 template <class QT>
 void launch_histogram(const QT *q, uint64_t n, int sym_min, int nbins, int center, unsigned long long *ghist,

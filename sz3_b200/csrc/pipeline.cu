@@ -18,6 +18,7 @@
 #include <exception>
 #include <mutex>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "blockwise.cuh"
@@ -263,6 +264,23 @@ struct IndexStream {       // device-resident result of a decomposition
     bool wide = false;     // QT = uint32 (radius > 32768)
 };
 
+// Box schedule (interp_box.cu) for the tiles [A.tile0, A.tile0 + ntiles) of the finest level; false = not this type /
+// shape, the caller launches the line walker instead.
+template <class T, class QT>
+static bool box_applicable(const InterpArgs<T, QT> &A, uint64_t ntiles_level) {
+    if constexpr (std::is_same<T, float>::value && std::is_same<QT, uint16_t>::value)
+        return interp_box_applicable(A, ntiles_level);
+    else
+        return false;
+}
+template <class T, class QT>
+static bool launch_box(const InterpArgs<T, QT> &A, uint64_t ntiles, cudaStream_t st) {
+    if constexpr (std::is_same<T, float>::value && std::is_same<QT, uint16_t>::value)
+        return interp_launch_box(A, ntiles, st);
+    else
+        return false;
+}
+
 template <class T, class QT>
 static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uint32_t nbatch, int radius, QT *d_q,
                        T *d_unpred_tmp, unsigned long long *d_hist, DevBuf &recon_buf, int *launches) {
@@ -308,13 +326,15 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         A.s = L.s;
         for (int d = 0; d < kMaxDim; d++) A.nb[d] = L.nb[d];
         A.block_base = d_table + L.table_off;
+        const bool box = pl.box && pl.variant == 2 && nbatch == 1 && L.s == 1 && box_applicable<T, QT>(A, L.nblocks);
+        if (pl.box_required && L.s == 1 && !box) fail(SZ3B_E_UNSUPPORTED, "box schedule does not apply to this shape / type");
         if (planes && L.s == 1) {
             // the finest level, block-row by block-row as the odd planes arrive
             const uint64_t per_row = static_cast<uint64_t>(L.nb[1]) * L.nb[2];
             for (uint32_t b = 0; b < L.nb[0]; b++) {
                 SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.copy_plan.ev_row[b], 0));
                 A.tile0 = static_cast<uint32_t>(b * per_row);
-                interp_launch_ltiles<T, QT>(A, per_row, nbatch, ws.st);
+                if (!(box && launch_box<T, QT>(A, per_row, ws.st))) interp_launch_ltiles<T, QT>(A, per_row, nbatch, ws.st);
                 (*launches)++;
             }
             A.tile0 = 0;
@@ -322,7 +342,8 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
             continue;
         }
         if (pl.tile) {
-            if (pl.variant == 2)
+            if (box && launch_box<T, QT>(A, L.nblocks, ws.st)) {
+            } else if (pl.variant == 2)
                 interp_launch_ltiles<T, QT>(A, L.nblocks, nbatch, ws.st);
             else if (pl.variant == 1)
                 interp_launch_ftiles<T, QT>(A, L.nblocks, nbatch, ws.st);

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <thread>
 #include <vector>
 
@@ -14,6 +15,7 @@
 #include "../../sz3_b200/csrc/interp_fast.cuh"
 #include "../../sz3_b200/csrc/interp_line.cuh"
 #include "../../sz3_b200/csrc/interp_lean.cuh"
+#include "../../sz3_b200/csrc/interp_box.cuh"
 #include "../../sz3_b200/csrc/interp_plan.hpp"
 
 using namespace sz3b;
@@ -31,17 +33,73 @@ struct HostCtx {
     }
 };
 
+// Box schedule (interp_box.cuh): the per-lane phase functions run lane by lane, warp by warp, in the order the
+// kernel's barriers impose; a host copy with zero fill stands in for the TMA box (out-of-bounds elements read 0).
+struct SeqCtx {
+    unsigned long long *hist;
+    void hist_add(int sym, bool active) {
+        if (active) hist[sym]++;
+    }
+};
+
+template <bool CUBIC>
+static void box_tile_emul(const BoxArgs &A, uint32_t tile, unsigned long long *hist) {
+    static std::vector<float> EE(kBoxEEElems), slots(kBoxWarps * kBoxSlotStride);
+    static std::vector<uint16_t> stage(kBoxWarps * kBoxStageU16);
+    std::fill(EE.begin(), EE.end(), std::numeric_limits<float>::quiet_NaN());   // unfilled cells must never matter
+    SeqCtx ctx{hist};
+    BoxOrigin o;
+    box_origin(A, tile, o);
+    BoxTile T;
+    box_tile_setup<CUBIC>(A, tile, o, T);
+    for (uint32_t t = 0; t < kBoxThreads; t++) {
+        box_fill_column(A, o, t, EE.data());
+        if (t < 33) box_fill_column(A, o, 256 + t, EE.data());
+    }
+    for (uint32_t t = kBoxThreads; t-- > 0;) box_pass0_line<CUBIC>(A, ctx, T, t, EE.data());
+    for (uint32_t t = kBoxThreads; t-- > 0;)
+        for (uint32_t e = t; e < 33 * 16; e += kBoxThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE.data());
+    for (uint32_t w = kBoxWarps; w-- > 0;) {
+        float *slot = slots.data() + w * kBoxSlotStride;
+        uint16_t *stg = stage.data() + w * kBoxStageU16;
+        for (uint32_t z = T.low[0] + w; z < T.n[0]; z += kBoxWarps) {
+            // TMA box (36, 33, 1) at (x0, y0, z0 + z)
+            for (uint32_t y = 0; y < 33; y++)
+                for (uint32_t x = 0; x < 36; x++) {
+                    const uint64_t gz = o.begin[0] + z, gy = o.begin[1] + y, gx = o.begin[2] + x;
+                    const bool in = gz < A.sh.dims[0] && gy < A.sh.dims[1] && gx < A.sh.dims[2];
+                    slot[y * kBoxPitch + x] = in ? A.data[gz * A.sh.stride[0] + gy * A.sh.stride[1] + gx] : 0.0f;
+                }
+            const float *EEz = EE.data() + z * kBoxEEPlane;
+            for (uint32_t l = 32; l-- > 0;) box_merge(T, l, EEz, slot);
+            for (uint32_t l = 32; l-- > 0;) box_pass1_lane<CUBIC>(A, ctx, T, l, z, EEz, slot);
+            for (uint32_t l = 32; l-- > 0;) box_pass1_left<CUBIC>(A, ctx, T, l, z, EEz, slot);
+            std::fill(stg, stg + kBoxStageU16, static_cast<uint16_t>(0xdead));
+            for (uint32_t l = 32; l-- > 0;) box_pass2_left<CUBIC>(A, ctx, T, l, z, slot, stg);
+            for (uint32_t l = 32; l-- > 0;) {
+                if (l >= T.c1[1]) continue;
+                float v[36];
+                memcpy(v, slot + (l + T.low[1]) * kBoxPitch, sizeof(v));
+                box_pass2_row<CUBIC>(A, ctx, T, l, z, v, stg);
+            }
+            for (uint32_t l = 32; l-- > 0;) box_copy_out(A, T, l, z, stg);
+        }
+    }
+}
+
 template <class T, class QT>
 static int run(const sz3b_config &c, double eb, const T *data, int schedule, int nthreads, int32_t *quant_out,
                T *unpred_out, size_t *n_unpred, unsigned long long *hist_out) {
     InterpPlan pl;
+    const bool box_schedule = schedule == 6;
+    if (box_schedule) schedule = 4;
     if (const char *e = build_interp_plan(c, eb, schedule, pl)) {
         fprintf(stderr, "[emul] plan: %s\n", e);
         return -1;
     }
     const int radius = c.quantbinCnt / 2;
     const uint64_t n = pl.num;
-    std::vector<QT> q(n, static_cast<QT>(0xFFFF));
+    std::vector<QT> q(n + 8, static_cast<QT>(0xFFFF));
     std::vector<T> unpred_tmp(n);
     std::vector<T> recon(pl.tile ? pl.num2 : pl.num);
     std::vector<unsigned long long> hist(2 * radius, 0);
@@ -92,11 +150,27 @@ static int run(const sz3b_config &c, double eb, const T *data, int schedule, int
         for (int d = 0; d < kMaxDim; d++) A.nb[d] = L.nb[d];
         A.block_base = pl.table.data() + L.table_off;
         std::barrier<> bar(nthreads);
+        // box schedule (schedule 6 of the emulation): every level-1 tile must qualify, else the line walker runs
+        bool box_level = false;
+        if (box_schedule && pl.tile && L.s == 1 && sizeof(T) == 4 && sizeof(QT) == 2 && pl.sh.perm[0] == 0 && pl.sh.perm[1] == 1) {
+            box_level = true;
+            for (uint64_t tile = 0; tile < L.nblocks; tile++) {
+                BoxOrigin o;
+                box_origin(*reinterpret_cast<const BoxArgs *>(&A), static_cast<uint32_t>(tile), o);
+                if (!box_tile_ok(o)) box_level = false;
+            }
+            if (!box_level) return -7;
+        }
         if (pl.tile) {
             auto worker = [&](int t) {
                 HostCtx ctx{static_cast<uint32_t>(t), static_cast<uint32_t>(nthreads), &bar, hist.data()};
                 for (uint64_t tile = 0; tile < L.nblocks; tile++) {
-                    if (pl.variant == 2) {
+                    if (box_level) {
+                        if (t == 0) {
+                            if (pl.sh.cubic) box_tile_emul<true>(*reinterpret_cast<const BoxArgs *>(&A), static_cast<uint32_t>(tile), hist.data());
+                            else box_tile_emul<false>(*reinterpret_cast<const BoxArgs *>(&A), static_cast<uint32_t>(tile), hist.data());
+                        }
+                    } else if (pl.variant == 2) {
                         static LineTile lt;   // shared by the worker threads like __shared__ memory
                         LineGeom lg;
                         line_geom(A, static_cast<uint32_t>(tile), 0, lg);

@@ -233,3 +233,25 @@ def test_host_huffman_tree_and_codes_match_reference():
         assert outs[0][0] == outs[1][0], "tree blob length"
         assert outs[0][1][:outs[0][0]] == outs[1][1][:outs[1][0]], "tree blob"
         assert outs[0][1] == outs[1][1], "bit stream"
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((64, 64, 64), dict(interpAlgo=1)),
+    ((64, 96, 128), dict(interpAlgo=1)),
+    ((64, 64, 64), dict(interpAlgo=0)),
+    ((96, 64, 128), dict(interpAlgo=0)),
+    ((32, 64, 96), dict(interpAlgo=1)),
+])
+def test_emul_box_schedule(shape, kw):
+    """Box schedule (interp_box.cuh): per-lane phase functions run lane by lane with a host copy standing in for the
+    TMA box; tiles of 32 and 33 points, owned and foreign low faces, both interpolators."""
+    data = field_nd(shape, np.float32)
+    data[5, 6, 7] = np.nan
+    data[40 % shape[0], 33, 32] = np.inf
+    conf = make_config(shape, cmprAlgo=ALGO_INTERP, interpAnchorStride=32, interpDirection=0, **kw)
+    for eb in (1e-2, 1e-5):
+        q_ref, blob_ref, _ = ref_interp(ref_lib(), data, conf, eb)
+        q, un = emul(data, conf, eb, 6, nthreads=32)
+        assert np.array_equal(q, q_ref)
+        _, un_ref = interp_blob_unpred(blob_ref, conf.N, np.float32)
+        assert np.array_equal(un, un_ref, equal_nan=True)

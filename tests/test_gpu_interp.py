@@ -128,6 +128,61 @@ def test_interp3d_g3_256(schedule):
     check(data.shape, np.float32, 1e-3, schedule, data=data, interpAlgo=1)
 
 
+# ---- box schedule (interp_box.cu): finest level by TMA-staged planes; dims must be multiples of 32 -------------------------
+BOX_SHAPES = [(64, 64, 64), (32, 64, 96), (96, 64, 128), (128, 128, 160)]
+
+
+@pytest.mark.parametrize("schedule", [0, 6])
+@pytest.mark.parametrize("shape", BOX_SHAPES)
+@pytest.mark.parametrize("algo", [0, 1])
+def test_interp3d_box(shape, algo, schedule):
+    check(shape, np.float32, 1e-2, schedule, interpAlgo=algo, interpDirection=0)
+
+
+@pytest.mark.parametrize("kw", [dict(interpAlpha=-1.0), dict(interpAlpha=2.0, interpBeta=3.0), dict(interpAnchorStride=64),
+                                dict(quantbinCnt=64), dict(quantbinCnt=1024)])
+def test_interp3d_box_variants(kw):
+    check((64, 96, 64), np.float32, 1e-3, 6, interpAlgo=1, interpDirection=0, **kw)
+
+
+def test_interp3d_box_many_unpredictable():
+    check((64, 64, 96), np.float32, 1e-6, 6, interpAlgo=1, quantbinCnt=16)
+    check((64, 64, 96), np.float32, 1e-6, 6, interpAlgo=0, quantbinCnt=16)
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_interp3d_box_special_values(algo):
+    data = field_nd((64, 64, 64), np.float32)
+    data[3, 4, 5] = np.nan
+    data[10, 11, 12] = np.inf
+    data[20, 21, 22] = -np.inf
+    data[30, 31, 32] = 1e30
+    data[33, 32, 63] = np.nan
+    data[63, 63, 63] = -np.inf
+    check(data.shape, np.float32, 1e-3, 6, data=data, interpAlgo=algo, interpAnchorStride=32)
+
+
+def test_interp3d_box_rejects_other_shapes():
+    """Schedule 6 insists on the box kernel: a shape it does not cover is an error, not a silent fallback."""
+    L = product_lib()
+    data = field_nd((40, 50, 70), np.float32)
+    conf = make_config(data.shape, cmprAlgo=ALGO_INTERP, interpAnchorStride=32)
+    q = np.empty(data.size, dtype=np.int32)
+    blob = np.empty(data.nbytes + 4096, dtype=np.uint8)
+    blen = C.c_size_t(0)
+    rc = L.sz3b_interp_decompose(0, C.byref(conf), C.c_double(1e-3), data.ctypes.data_as(C.c_void_p), 0, 6,
+                                 q.ctypes.data_as(C.c_void_p), blob.ctypes.data_as(C.c_void_p), C.c_size_t(blob.size), C.byref(blen))
+    assert rc != 0
+
+
+@pytest.mark.parametrize("schedule", [0, 4, 6])
+def test_interp3d_g3_512_against_reference(schedule):
+    """The headline array (512^3 G3, abs 1e-3, what bench.py times) against the reference itself: every index and the
+    decomposition blob, for the automatic schedule, the line walker and the box kernel."""
+    data = field_g3((512, 512, 512))
+    check(data.shape, np.float32, 1e-3, schedule, data=data, interpAlgo=1, interpDirection=0, interpAlpha=1.0, interpBeta=1.0)
+
+
 def test_schedules_agree_512():
     """Full headline size: the two independent GPU schedules must produce identical streams (size-independent check)."""
     data = field_g3((512, 512, 512))
