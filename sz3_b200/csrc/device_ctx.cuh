@@ -120,17 +120,17 @@ struct DevCtx2 {
     }
 };
 
-// Same counting scheme as DevCtx2 with the rare path inline: a called function, however rarely taken, makes the
-// compiler give up every value it keeps in uniform registers across the call site (box schedule, interp_box.cu).
+// Same counting scheme as DevCtx2, split for straight-line hot loops (box schedule, interp_box.cuh: BoxHist):
+// hist_fast counts a symbol of the 8-bin register window and reports the others, hist_rare counts one of those.
 struct DevCtxBox : DevCtx2 {
     __device__ __forceinline__ DevCtxBox(unsigned *sh, unsigned long long *gh, int radius) : DevCtx2(sh, gh, radius) {}
-    __device__ __forceinline__ void hist_add(int sym, bool active) {
-        if (!active) return;
+    __device__ __forceinline__ bool hist_fast(int sym, bool active) {
         const unsigned k8 = static_cast<unsigned>(sym - lo8);
-        if (k8 < 8u) {
-            packed += 1ull << (k8 * 8u);
-            return;
-        }
+        const bool in = k8 < 8u;
+        if (active && in) packed += 1ull << (k8 * 8u);
+        return active && !in;
+    }
+    __device__ __forceinline__ void hist_rare(int sym) {
         const unsigned k = static_cast<unsigned>(sym - lo);
         if (k < static_cast<unsigned>(kHistWindow))
             atomicAdd(&shist[k], 1u);

@@ -59,6 +59,7 @@ struct BoxTile {
     uint32_t pb[3];      // first index of each pass, relative to qbase
     uint32_t other[3];   // lines of each pass (product of the owned counts of the two other dims)
     uint64_t qbase;      // position of the tile's first index in the stream
+    uint64_t gbase;      // element offset of the tile's origin in the input array
 };
 
 // What every thread needs before BoxTile is ready (a few integer operations, recomputed per thread).
@@ -114,6 +115,7 @@ SZ_HD void box_tile_setup(const BoxArgs &A, uint32_t tile, const BoxOrigin &o, B
     T.pb[1] = (T.mainc[0] + nbnd[0]) * T.other[0];
     T.pb[2] = T.pb[1] + (T.mainc[1] + nbnd[1]) * T.other[1];
     T.qbase = A.block_base[tile];
+    T.gbase = o.gbase;
 }
 
 // Sub-phase of target k (local index 2k + 1) on a line of n = 33 (n_odd) or 32 points: true = main sub-phase with
@@ -161,65 +163,107 @@ SZ_HD float box_pred(const float *v, int k, bool n_odd, float rec_prev) {
 }
 
 // Where a line's indices go: the main sub-phase at qm[idx * main_mul], boundary sub-phase j at qm[bnd0 + j * other]
-// (element offsets relative to qm; everything a register after inlining).  ub is the same place in unpred_tmp.
+// (element offsets relative to qm; everything a register after inlining).  um is the same place in unpred_tmp.
 struct BoxEmit {
     uint16_t *qm;
     float *um;
     uint32_t main_mul, bnd0, other;
 };
-template <bool CUBIC, class Ctx>
-SZ_HD void box_emit(const BoxEmit &E, Ctx &ctx, uint32_t k, bool n_odd, int qv, float orig, bool owned) {
-    uint32_t idx;
-    const bool in_main = box_class<CUBIC>(k, n_odd, idx);
-    const uint32_t off = in_main ? idx * E.main_mul : E.bnd0 + idx * E.other;
+SZ_HD uint32_t box_off(const BoxEmit &E, bool in_main, uint32_t idx) {
+    return in_main ? idx * E.main_mul : E.bnd0 + idx * E.other;
+}
+SZ_HD void box_store(const BoxEmit &E, bool in_main, uint32_t idx, int qv, float orig, bool owned) {
+    const uint32_t off = box_off(E, in_main, idx);
     if (owned) {
         E.qm[off] = static_cast<uint16_t>(qv);
         if (qv == 0) E.um[off] = orig;
     }
-    ctx.hist_add(qv, owned);
+}
+// runtime-k twin of box_class (leftover lines: lane = target)
+template <bool CUBIC>
+SZ_HD bool box_class_rt(uint32_t k, bool n_odd, uint32_t &idx) {
+    if (CUBIC) {
+        const bool in_main = (k >= 1 && k <= 13) || (k == 14 && n_odd);
+        idx = in_main ? k - 1 : (k == 0 ? 0u : (k == 14 ? 1u : (n_odd ? 1u : 2u)));
+        return in_main;
+    }
+    const bool in_main = k <= 14 || n_odd;
+    idx = in_main ? k : 0u;
+    return in_main;
 }
 
-// One target through the reference's own line predictor (core.cuh: predict_line): the few lines / rows / columns
-// that do not fit the lane mappings (the 17th lattice column, a 33rd owned row, z-lines 256..288).
-// ld(l) = current value at local index l, st(l, v) stores a reconstruction, em(k, qv, orig) emits.
-template <bool CUBIC, class Ld, class St, class Em>
-SZ_HD void box_generic_target(uint32_t k, uint32_t n, const QuantParams &qp, Ld &&ld, St &&st, Em &&em) {
-    const bool tail_pair = !CUBIC && !(n & 1u);   // linear, even n: target n-1 needs the reconstruction of n-3
-    if (tail_pair && 2 * k + 1 == n - 1) return;  // done together with its predecessor
-    const uint32_t i = 2 * k + 1;
-    float pred = predict_line<float>(CUBIC ? 1 : 0, i, n, ld, 0.0f);
-    float orig = ld(i), rec;
-    int qv = quantize<float>(orig, pred, qp, rec);
-    st(i, rec);
-    em(k, qv, orig);
-    if (tail_pair && i + 2 == n - 1) {
-        pred = interp_linear1<float>(rec, ld(i + 1));
-        orig = ld(i + 2);
-        qv = quantize<float>(orig, pred, qp, rec);
-        st(i + 2, rec);
-        em(k + 1, qv, orig);
+// Histogram bookkeeping of a run of up to 32 targets handled by one thread: symbols inside the context's register
+// window are counted on the spot (straight-line code, so that the compiler can interleave the arithmetic of
+// neighbouring targets); the rare others are remembered in a bit mask and counted after the run.
+// Index 0 (an unpredictable point) is always one of the rare ones: its original value is stored from the same place,
+// through `zero(k)` -- the caller re-reads the value from the input array, nothing stays in registers for it.
+template <class Ctx, int N>
+struct BoxHist {
+    int q[N];
+    uint32_t rare = 0;
+    SZ_HD void add(Ctx &ctx, int k, int qv, bool active) {
+        q[k] = qv;
+        if (ctx.hist_fast(qv, active)) rare |= 1u << k;
     }
+    template <class Zero>
+    SZ_HD void finish(Ctx &ctx, Zero &&zero) {
+        if (rare) {
+#pragma unroll
+            for (int k = 0; k < N; k++)
+                if ((rare >> k) & 1u) {
+                    ctx.hist_rare(q[k]);
+                    if (q[k] == 0) zero(k);
+                }
+        }
+    }
+};
+
+// stencils whose kind depends on the lane: four taps with coefficients (unused taps must be zero, never NaN)
+enum { BOX_ST_CUBIC = 0, BOX_ST_QUAD1 = 1, BOX_ST_QUAD2 = 2, BOX_ST_LINEAR1 = 3 };
+SZ_HD float box_stencil4(uint32_t kind, float w0, float w1, float w2, float w3) {
+    // (((c0*w0 + c1*w1) + c2*w2) + c3*w3) * sc evaluates cubic / quad_1 / quad_2 in the reference's operation order
+    const float c0 = kind == BOX_ST_QUAD1 ? 0.0f : -1.0f;
+    const float c1 = kind == BOX_ST_CUBIC ? 9.0f : (kind == BOX_ST_QUAD1 ? 3.0f : 6.0f);
+    const float c2 = kind == BOX_ST_CUBIC ? 9.0f : (kind == BOX_ST_QUAD1 ? 6.0f : 3.0f);
+    const float c3 = kind == BOX_ST_QUAD2 ? 0.0f : -1.0f;
+    const float sc = kind == BOX_ST_CUBIC ? 0.0625f : 0.125f;
+    const float p = (((c0 * w0 + c1 * w1) + c2 * w2) + c3 * w3) * sc;
+    return kind == BOX_ST_LINEAR1 ? interp_linear1<float>(w0, w1) : p;
 }
-// runtime-k twin of box_emit for the generic targets
-template <bool CUBIC, class Ctx>
-SZ_HD void box_emit_rt(const BoxEmit &E, Ctx &ctx, uint32_t k, bool n_odd, int qv, float orig, bool owned) {
-    uint32_t idx = 0;
-    bool in_main = false;
+
+// One target with a run-time k (lane = target) without divergent code: the few lines / rows / columns that do not
+// fit the lane mappings (the 17th lattice column, a 33rd owned row, z-lines 256..288).  ld(l) = current value at local
+// index l (only indices inside the line are requested), st(l, v) stores a reconstruction, em(k, qv, orig) emits.
+// Same arithmetic as box_pred: the stencil kinds of the reference (InterpolationDecomposition.hpp:334-400) for
+// n = 32 / 33, evaluated through box_stencil4.
+template <bool CUBIC, class Ld, class St, class Em>
+SZ_HD void box_target_rt(uint32_t k, bool n_odd, const QuantParams &qp, Ld &&ld, St &&st, Em &&em) {
+    const bool tail_pair = !CUBIC && !n_odd;      // linear, even n: target 15 needs the reconstruction of target 14
+    if (tail_pair && k == 15) return;             // done together with its predecessor
+    float pred;
     if (CUBIC) {
-        if (k >= 1 && k <= 13) { in_main = true; idx = k - 1; }
-        else if (k == 0) idx = 0;
-        else if (k == 14) { in_main = n_odd; idx = n_odd ? 13u : 1u; }
-        else idx = n_odd ? 1u : 2u;
+        const uint32_t kind = k == 0 ? BOX_ST_QUAD1
+                                     : (k <= 13 ? BOX_ST_CUBIC
+                                                : (k == 14 ? (n_odd ? BOX_ST_CUBIC : BOX_ST_QUAD2) : (n_odd ? BOX_ST_QUAD2 : BOX_ST_LINEAR1)));
+        const float w0 = k >= 1 ? ld(2 * k - 2) : 0.0f;
+        const float w1 = ld(2 * k);
+        const float w2 = kind != BOX_ST_LINEAR1 ? ld(2 * k + 2) : 0.0f;
+        const float w3 = (kind == BOX_ST_CUBIC || kind == BOX_ST_QUAD1) ? ld(2 * k + 4) : 0.0f;
+        pred = box_stencil4(kind, w0, w1, w2, w3);
     } else {
-        if (k <= 14) { in_main = true; idx = k; }
-        else { in_main = n_odd; idx = n_odd ? 15u : 0u; }
+        pred = interp_linear<float>(ld(2 * k), ld(2 * k + 2));
     }
-    const uint32_t off = in_main ? idx * E.main_mul : E.bnd0 + idx * E.other;
-    if (owned) {
-        E.qm[off] = static_cast<uint16_t>(qv);
-        if (qv == 0) E.um[off] = orig;
+    float orig = ld(2 * k + 1), rec;
+    int qv = quantize_f32(orig, pred, qp, rec);
+    st(2 * k + 1, rec);
+    em(k, qv, orig);
+    if (tail_pair && k == 14) {
+        pred = interp_linear1<float>(rec, ld(30));
+        orig = ld(31);
+        qv = quantize_f32(orig, pred, qp, rec);
+        st(31, rec);
+        em(15, qv, orig);
     }
-    ctx.hist_add(qv, owned);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -233,50 +277,75 @@ SZ_HD void box_fill_column(const BoxArgs &A, const BoxOrigin &o, uint32_t c, flo
     const float *rc = A.recon2 + o.g2base + static_cast<uint64_t>(yl) * s * A.stride2[1] + static_cast<uint64_t>(xl) * s;
     const uint64_t rstep = static_cast<uint64_t>(s) * A.stride2[0];
     // originals (z odd) at local (z, 2y', 2x')
-    const float *gp = A.data + o.gbase + static_cast<uint64_t>(2 * yl) * s * A.sh.stride[1] + static_cast<uint64_t>(2 * xl) * s;
     const uint64_t gstep = static_cast<uint64_t>(s) * A.sh.stride[0];
+    const float *gp = A.data + o.gbase + static_cast<uint64_t>(2 * yl) * s * A.sh.stride[1] + static_cast<uint64_t>(2 * xl) * s + gstep;
     float *dst = EE + c;
-    const uint32_t nz = o.n[0];
-    for (uint32_t z = 0; z < nz; z += 2) {
-        fill_copy(dst + z * kBoxEEPlane, rc + (z >> 1) * rstep);
-        if (z + 1 < nz) fill_copy(dst + (z + 1) * kBoxEEPlane, gp + (z + 1) * gstep);
+#pragma unroll
+    for (int z = 0; z < 32; z += 2) {
+        fill_copy(dst + z * kBoxEEPlane, rc);
+        fill_copy(dst + (z + 1) * kBoxEEPlane, gp);
+        rc += rstep;
+        gp += 2 * gstep;
     }
+    if (o.n[0] & 1u) fill_copy(dst + 32 * kBoxEEPlane, rc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // pass 0 (along z), thread c < 256 on its own z-line; everything from registers
 // ---------------------------------------------------------------------------------------------------------------------
+template <class Ctx>
+SZ_HD void box_pass0_emit(const BoxArgs &A, const BoxTile &T, uint32_t yl, uint32_t xl, BoxEmit &E, bool &owned) {
+    const uint32_t lowy = T.low[1], lowx = T.low[2], other = T.other[0];
+    owned = yl >= lowy && xl >= lowx;
+    const uint32_t line_rank = (yl - lowy) * T.c2[2] + (xl - lowx);
+    E.qm = A.q + T.qbase + line_rank;   // pb[0] == 0
+    E.um = A.unpred_tmp + T.qbase + line_rank;
+    E.main_mul = other;
+    E.bnd0 = T.mainc[0] * other;
+    E.other = other;
+}
+
 template <bool CUBIC, class Ctx>
 SZ_HD void box_pass0_line(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t c, float *EE) {
     const uint32_t yl = c / 17u, xl = c - yl * 17u;
     if (yl >= T.C[1] || xl >= T.C[2]) return;
     const bool n_odd = T.n[0] & 1u;
-    const uint32_t lowy = T.low[1], lowx = T.low[2], c2x = T.c2[2], other = T.other[0], mainc = T.mainc[0];
-    const uint64_t base = T.qbase;   // pb[0] == 0
     float v[33];
 #pragma unroll
     for (int z = 0; z < 32; z++) v[z] = EE[z * kBoxEEPlane + c];
     v[32] = n_odd ? EE[32 * kBoxEEPlane + c] : 0.0f;
-    const bool owned = yl >= lowy && xl >= lowx;
-    const uint32_t line_rank = (yl - lowy) * c2x + (xl - lowx);
     BoxEmit E;
-    E.qm = A.q + base + line_rank;
-    E.um = A.unpred_tmp + base + line_rank;
-    E.main_mul = other;
-    E.bnd0 = mainc * other;
-    E.other = other;
+    bool owned;
+    box_pass0_emit<Ctx>(A, T, yl, xl, E, owned);
     const QuantParams qp = A.qp;
     float *const col = EE + c;
+    // where the line's originals sit in the input (rare path: value of an unpredictable point)
+    const uint64_t gstep = static_cast<uint64_t>(A.s) * A.sh.stride[0];
+    const float *const gcol = A.data + T.gbase + (static_cast<uint64_t>(2 * yl) * A.sh.stride[1] + 2 * xl) * A.s;
     float rec_prev = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const float pred = box_pred<CUBIC>(v, k, n_odd, rec_prev);
-        const float orig = v[2 * k + 1];
-        float rec;
-        const int qv = quantize<float>(orig, pred, qp, rec);
-        rec_prev = rec;
-        col[(2 * k + 1) * kBoxEEPlane] = rec;
-        box_emit<CUBIC>(E, ctx, k, n_odd, qv, orig, owned);
+    for (int half = 0; half < 2; half++) {   // two runs of eight: bounds the indices kept for the rare histogram path
+        BoxHist<Ctx, 8> H;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const int k = 8 * half + t;
+            const float pred = box_pred<CUBIC>(v, k, n_odd, rec_prev);
+            const float orig = v[2 * k + 1];
+            float rec;
+            const int qv = quantize_f32(orig, pred, qp, rec);
+            rec_prev = rec;
+            col[(2 * k + 1) * kBoxEEPlane] = rec;
+            uint32_t idx;
+            const bool in_main = box_class<CUBIC>(k, n_odd, idx);
+            if (owned) E.qm[box_off(E, in_main, idx)] = static_cast<uint16_t>(qv);
+            H.add(ctx, t, qv, owned);
+        }
+        H.finish(ctx, [&](int t) {
+            const int k = 8 * half + t;
+            uint32_t idx;
+            const bool in_main = box_class<CUBIC>(k, n_odd, idx);
+            E.um[box_off(E, in_main, idx)] = gcol[static_cast<uint64_t>(2 * k + 1) * gstep];
+        });
     }
 }
 
@@ -287,19 +356,19 @@ SZ_HD void box_pass0_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
     if (c >= static_cast<uint32_t>(kBoxEEPlane)) return;
     const uint32_t yl = c / 17u, xl = c - yl * 17u;
     if (yl >= T.C[1] || xl >= T.C[2]) return;
-    const uint32_t nz = T.n[0];
-    const bool owned = yl >= T.low[1] && xl >= T.low[2];
-    const uint32_t line_rank = (yl - T.low[1]) * T.c2[2] + (xl - T.low[2]);
+    const bool n_odd = T.n[0] & 1u;
     BoxEmit E;
-    E.qm = A.q + T.qbase + line_rank;
-    E.um = A.unpred_tmp + T.qbase + line_rank;
-    E.main_mul = T.other[0];
-    E.bnd0 = T.mainc[0] * T.other[0];
-    E.other = T.other[0];
-    box_generic_target<CUBIC>(
-        k, nz, A.qp, [&](uint32_t l) { return EE[l * kBoxEEPlane + c]; },
-        [&](uint32_t l, float r) { EE[l * kBoxEEPlane + c] = r; },
-        [&](uint32_t kk, int qv, float orig) { box_emit_rt<CUBIC>(E, ctx, kk, nz & 1u, qv, orig, owned); });
+    bool owned;
+    box_pass0_emit<Ctx>(A, T, yl, xl, E, owned);
+    float *const col = EE + c;
+    box_target_rt<CUBIC>(
+        k, n_odd, A.qp, [&](uint32_t l) { return col[l * kBoxEEPlane]; }, [&](uint32_t l, float r) { col[l * kBoxEEPlane] = r; },
+        [&](uint32_t kk, int qv, float orig) {
+            uint32_t idx;
+            const bool in_main = box_class_rt<CUBIC>(kk, n_odd, idx);
+            box_store(E, in_main, idx, qv, orig, owned);
+            if (ctx.hist_fast(qv, owned)) ctx.hist_rare(qv);
+        });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -309,55 +378,70 @@ SZ_HD void box_pass0_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
 SZ_HD void box_merge(const BoxTile &T, uint32_t lane, const float *EEz, float *slot) {
     const uint32_t xl = lane & 15u, h = lane >> 4;
     const uint32_t Cy = T.C[1];
-    for (uint32_t yl = h; yl < Cy; yl += 2) slot[2 * yl * kBoxPitch + 2 * xl] = EEz[yl * 17 + xl];
+    const float *src = EEz + h * 17 + xl;
+    float *dst = slot + 2 * h * kBoxPitch + 2 * xl;
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[4 * i * kBoxPitch] = src[34 * i];    // y' = h + 2i <= 15
+    if (h == 0 && Cy == 17) dst[32 * kBoxPitch] = src[34 * 8];           // y' = 16
     if (T.C[2] == 17 && lane < Cy) slot[2 * lane * kBoxPitch + 32] = EEz[lane * 17 + 16];
-}
-
-// stencils of pass 1 whose kind depends on the lane: four taps with coefficients (unused taps are zero, never NaN)
-enum { BOX_ST_CUBIC = 0, BOX_ST_QUAD1 = 1, BOX_ST_QUAD2 = 2, BOX_ST_LINEAR1 = 3 };
-SZ_HD float box_stencil4(uint32_t kind, float w0, float w1, float w2, float w3) {
-    // (((c0*w0 + c1*w1) + c2*w2) + c3*w3) * sc evaluates cubic / quad_1 / quad_2 in the reference's operation order
-    const float c0 = kind == BOX_ST_QUAD1 ? 0.0f : -1.0f;
-    const float c1 = kind == BOX_ST_CUBIC ? 9.0f : (kind == BOX_ST_QUAD1 ? 3.0f : 6.0f);
-    const float c2 = kind == BOX_ST_CUBIC ? 9.0f : (kind == BOX_ST_QUAD1 ? 6.0f : 3.0f);
-    const float c3 = kind == BOX_ST_QUAD2 ? 0.0f : -1.0f;
-    const float sc = kind == BOX_ST_CUBIC ? 0.0625f : 0.125f;
-    const float p = (((c0 * w0 + c1 * w1) + c2 * w2) + c3 * w3) * sc;
-    return kind == BOX_ST_LINEAR1 ? interp_linear1<float>(w0, w1) : p;
 }
 
 // pass 1 (along y): lane = (x' = lane & 15, half h of the 16 targets); neighbours from EE (conflict-free), targets
 // read and overwritten in the slot
-template <bool CUBIC, class Ctx>
-SZ_HD void box_pass1_lane(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z, const float *EEz,
-                          float *slot) {
-    const uint32_t xl = lane & 15u, h = lane >> 4;
-    const bool n_odd = T.n[1] & 1u;
-    const int jmax = n_odd ? 16 : 15;             // last lattice index along y
+template <class Ctx>
+SZ_HD void box_pass1_emit(const BoxArgs &A, const BoxTile &T, uint32_t z, uint32_t xl, BoxEmit &E, bool &owned) {
     const uint32_t lowx = T.low[2], c2x = T.c2[2], mainc = T.mainc[1], other = T.other[1];
     const uint32_t rz = z - T.low[0];
     const uint64_t base = T.qbase + T.pb[1];
-    // window w[m] = value at lattice index jb + m, jb = -1 (h = 0) or 7 (h = 1); target t (k = 8h + t) uses w[t .. t+3]
-    const int jb = h ? 7 : -1;
-    float w[11];
-#pragma unroll
-    for (int m = 0; m < 11; m++) {
-        const int j = jb + m;
-        w[m] = (j >= 0 && j <= jmax) ? EEz[j * 17 + static_cast<int>(xl)] : 0.0f;
-    }
-    const bool owned = xl >= lowx;
-    const uint32_t line_rank = rz * c2x + (xl - lowx);
+    owned = xl >= lowx;
     // main: (rz * mainc + idx) * c2x + rx; boundary j: (mainc + j) * other + rz * c2x + rx
-    BoxEmit E;
+    const uint32_t line_rank = rz * c2x + (xl - lowx);
     const uint32_t m0 = rz * mainc * c2x + (xl - lowx);
     E.qm = A.q + base + m0;
     E.um = A.unpred_tmp + base + m0;
     E.main_mul = c2x;
     E.bnd0 = mainc * other + line_rank - m0;
     E.other = other;
+}
+
+template <bool CUBIC, class Ctx>
+SZ_HD void box_pass1_lane(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z, const float *EEz,
+                          float *slot) {
+    const uint32_t xl = lane & 15u, h = lane >> 4;
+    const bool n_odd = T.n[1] & 1u;
+    const int jmax = n_odd ? 16 : 15;             // last lattice index along y
+    // window w[m] = value at lattice index jb + m, jb = -1 (h = 0) or 7 (h = 1); target t (k = 8h + t) uses w[t .. t+3]
+    float w[11];
+    {
+        const float *src = EEz + xl + (h ? 7 * 17 : -17);
+        w[0] = h ? src[0] : 0.0f;
+#pragma unroll
+        for (int m = 1; m < 9; m++) w[m] = src[m * 17];                 // j = 0..7 | 8..15
+        w[9] = (h == 0 || jmax == 16) ? src[9 * 17] : 0.0f;              // j = 8 | 16
+        w[10] = h ? 0.0f : src[10 * 17];                                 // j = 9 | 17 (beyond the line)
+    }
+    BoxEmit E;
+    bool owned;
+    box_pass1_emit<Ctx>(A, T, z, xl, E, owned);
     const QuantParams qp = A.qp;
     float *const col = slot + 2 * xl + h * (16 * kBoxPitch);
+    // element offsets (relative to E.qm) of the lane's targets k = 8h + t: regular main-phase ones advance by c2x,
+    // the first / last two of a line sit in boundary sub-phases
+    const uint32_t c2x = E.main_mul, b1 = E.bnd0 + E.other, b2 = b1 + E.other;
+    const uint32_t base_off = (8u * h - (CUBIC ? 1u : 0u)) * c2x;
+    auto off_of = [&](int t) -> uint32_t {
+        const uint32_t reg = base_off + static_cast<uint32_t>(t) * c2x;
+        if (CUBIC) {
+            if (t == 0) return h ? reg : E.bnd0;
+            if (t == 6) return (h && !n_odd) ? b1 : reg;
+            if (t == 7) return h ? (n_odd ? b1 : b2) : reg;
+            return reg;
+        }
+        if (t == 7) return (h && !n_odd) ? E.bnd0 : reg;
+        return reg;
+    };
     float rec_prev = 0.0f;
+    BoxHist<Ctx, 8> H;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
         float pred;
@@ -377,15 +461,17 @@ SZ_HD void box_pass1_lane(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
         }
         const float orig = col[(2 * t + 1) * kBoxPitch];
         float rec;
-        const int qv = quantize<float>(orig, pred, qp, rec);
+        const int qv = quantize_f32(orig, pred, qp, rec);
         rec_prev = rec;
         col[(2 * t + 1) * kBoxPitch] = rec;
-        // sub-phase of k = 8h + t: the lower half is compile-time, the upper half differs only for t = 6, 7
-        if (h == 0)
-            box_emit<CUBIC>(E, ctx, t, n_odd, qv, orig, owned);
-        else
-            box_emit<CUBIC>(E, ctx, 8 + t, n_odd, qv, orig, owned);
+        if (owned) E.qm[off_of(t)] = static_cast<uint16_t>(qv);
+        H.add(ctx, t, qv, owned);
     }
+    H.finish(ctx, [&](int t) {
+        // rare: the original of an unpredictable point, re-read from the input at local (z, 2k + 1, 2x')
+        const uint64_t g = T.gbase + (static_cast<uint64_t>(z) * A.sh.stride[0] + static_cast<uint64_t>(16 * h + 2 * t + 1) * A.sh.stride[1] + 2 * xl) * A.s;
+        E.um[off_of(t)] = A.data[g];
+    });
 }
 
 // the 17th lattice column (x = 32) of pass 1: lane = target
@@ -393,22 +479,21 @@ template <bool CUBIC, class Ctx>
 SZ_HD void box_pass1_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z, const float *EEz,
                           float *slot) {
     if (T.C[2] != 17 || lane >= 16) return;
-    const uint32_t ny = T.n[1];
-    const uint32_t rz = z - T.low[0], rx = 16u - T.low[2];
-    const uint32_t line_rank = rz * T.c2[2] + rx;
-    const uint32_t m0 = rz * T.mainc[1] * T.c2[2] + rx;
-    const uint64_t base = T.qbase + T.pb[1];
+    const bool n_odd = T.n[1] & 1u;
     BoxEmit E;
-    E.qm = A.q + base + m0;
-    E.um = A.unpred_tmp + base + m0;
-    E.main_mul = T.c2[2];
-    E.bnd0 = T.mainc[1] * T.other[1] + line_rank - m0;
-    E.other = T.other[1];
-    box_generic_target<CUBIC>(
-        lane, ny, A.qp,
-        [&](uint32_t l) { return (l & 1u) ? slot[l * kBoxPitch + 32] : EEz[(l >> 1) * 17 + 16]; },
-        [&](uint32_t l, float r) { slot[l * kBoxPitch + 32] = r; },
-        [&](uint32_t kk, int qv, float orig) { box_emit_rt<CUBIC>(E, ctx, kk, ny & 1u, qv, orig, true); });
+    bool owned;
+    box_pass1_emit<Ctx>(A, T, z, 16u, E, owned);
+    const float *ecol = EEz + 16;
+    float *scol = slot + 32;
+    box_target_rt<CUBIC>(
+        lane, n_odd, A.qp, [&](uint32_t l) { return (l & 1u) ? scol[l * kBoxPitch] : ecol[(l >> 1) * 17]; },
+        [&](uint32_t l, float r) { scol[l * kBoxPitch] = r; },
+        [&](uint32_t kk, int qv, float orig) {
+            uint32_t idx;
+            const bool in_main = box_class_rt<CUBIC>(kk, n_odd, idx);
+            box_store(E, in_main, idx, qv, orig, true);
+            if (ctx.hist_fast(qv, true)) ctx.hist_rare(qv);
+        });
 }
 
 // Position of a plane's main-phase run of pass 2 and its misalignment (in indices) against 16-byte chunks.
@@ -425,20 +510,18 @@ struct BoxRowOut {
     float *um, *ub;      // unpred_tmp at the same two places
     uint32_t other;
 };
-template <class Ctx>
 SZ_HD void box_row_out(const BoxArgs &A, const BoxTile &T, uint32_t ry, uint32_t z, uint16_t *stage, BoxRowOut &R) {
     const uint32_t mainc = T.mainc[2], c1y = T.c1[1];
     const uint32_t line_rank = (z - T.low[0]) * c1y + ry;
     const uint64_t base = T.qbase + T.pb[2];
-    const uint32_t mis = static_cast<uint32_t>(base + static_cast<uint64_t>((z - T.low[0]) * c1y) * mainc) & 7u;
+    const uint32_t mis = static_cast<uint32_t>(box_run_pos(T, z)) & 7u;
     R.srow = stage + mis + ry * mainc;
     R.other = T.other[2];
     R.qb = A.q + base + mainc * R.other + line_rank;
     R.ub = A.unpred_tmp + base + mainc * R.other + line_rank;
     R.um = A.unpred_tmp + base + line_rank * mainc;
 }
-template <bool CUBIC, class Ctx>
-SZ_HD void box_row_emit(const BoxRowOut &R, Ctx &ctx, bool in_main, uint32_t idx, int qv, float orig) {
+SZ_HD void box_row_store(const BoxRowOut &R, bool in_main, uint32_t idx, int qv, float orig) {
     if (in_main) {
         R.srow[idx] = static_cast<uint16_t>(qv);
         if (qv == 0) R.um[idx] = orig;
@@ -446,7 +529,6 @@ SZ_HD void box_row_emit(const BoxRowOut &R, Ctx &ctx, bool in_main, uint32_t idx
         R.qb[idx * R.other] = static_cast<uint16_t>(qv);
         if (qv == 0) R.ub[idx * R.other] = orig;
     }
-    ctx.hist_add(qv, true);
 }
 
 template <bool CUBIC, class Ctx>
@@ -454,19 +536,37 @@ SZ_HD void box_pass2_row(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t 
                          uint16_t *stage) {
     const bool n_odd = T.n[2] & 1u;
     BoxRowOut R;
-    box_row_out<Ctx>(A, T, ry, z, stage, R);
+    box_row_out(A, T, ry, z, stage, R);
     const QuantParams qp = A.qp;
     float rec_prev = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const float pred = box_pred<CUBIC>(v, k, n_odd, rec_prev);
-        const float orig = v[2 * k + 1];
-        float rec;
-        const int qv = quantize<float>(orig, pred, qp, rec);
-        rec_prev = rec;
-        uint32_t idx;
-        const bool in_main = box_class<CUBIC>(k, n_odd, idx);
-        box_row_emit<CUBIC>(R, ctx, in_main, idx, qv, orig);
+    for (int half = 0; half < 2; half++) {
+        BoxHist<Ctx, 8> H;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const int k = 8 * half + t;
+            const float pred = box_pred<CUBIC>(v, k, n_odd, rec_prev);
+            const float orig = v[2 * k + 1];
+            float rec;
+            const int qv = quantize_f32(orig, pred, qp, rec);
+            rec_prev = rec;
+            uint32_t idx;
+            if (box_class<CUBIC>(k, n_odd, idx))
+                R.srow[idx] = static_cast<uint16_t>(qv);
+            else
+                R.qb[idx * R.other] = static_cast<uint16_t>(qv);
+            H.add(ctx, t, qv, true);
+        }
+        H.finish(ctx, [&](int t) {
+            // rare: the original of an unpredictable point, re-read from the input at local (z, y, 2k + 1)
+            const int k = 8 * half + t;
+            const uint64_t g = T.gbase + (static_cast<uint64_t>(z) * A.sh.stride[0] + static_cast<uint64_t>(ry + T.low[1]) * A.sh.stride[1] + (2 * k + 1)) * A.s;
+            uint32_t idx;
+            if (box_class<CUBIC>(k, n_odd, idx))
+                R.um[idx] = A.data[g];
+            else
+                R.ub[idx * R.other] = A.data[g];
+        });
     }
 }
 
@@ -475,27 +575,17 @@ template <bool CUBIC, class Ctx>
 SZ_HD void box_pass2_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z, const float *slot,
                           uint16_t *stage) {
     if (T.c1[1] != 33 || lane >= 16) return;
-    const uint32_t nx = T.n[2];
+    const bool n_odd = T.n[2] & 1u;
     BoxRowOut R;
-    box_row_out<Ctx>(A, T, 32u, z, stage, R);   // low == 0 here: row 32 is local y = 32
+    box_row_out(A, T, 32u, z, stage, R);   // low == 0 here: row 32 is local y = 32
     const float *row = slot + 32 * kBoxPitch;
-    box_generic_target<CUBIC>(
-        lane, nx, A.qp, [&](uint32_t l) { return row[l]; }, [&](uint32_t, float) {},
+    box_target_rt<CUBIC>(
+        lane, n_odd, A.qp, [&](uint32_t l) { return row[l]; }, [&](uint32_t, float) {},
         [&](uint32_t kk, int qv, float orig) {
-            // runtime twin of box_class
-            const bool n_odd = nx & 1u;
-            uint32_t idx = 0;
-            bool in_main = false;
-            if (CUBIC) {
-                if (kk >= 1 && kk <= 13) { in_main = true; idx = kk - 1; }
-                else if (kk == 0) idx = 0;
-                else if (kk == 14) { in_main = n_odd; idx = n_odd ? 13u : 1u; }
-                else idx = n_odd ? 1u : 2u;
-            } else {
-                if (kk <= 14) { in_main = true; idx = kk; }
-                else { in_main = n_odd; idx = n_odd ? 15u : 0u; }
-            }
-            box_row_emit<CUBIC>(R, ctx, in_main, idx, qv, orig);
+            uint32_t idx;
+            const bool in_main = box_class_rt<CUBIC>(kk, n_odd, idx);
+            box_row_store(R, in_main, idx, qv, orig);
+            if (ctx.hist_fast(qv, true)) ctx.hist_rare(qv);
         });
 }
 

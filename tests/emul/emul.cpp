@@ -37,9 +37,13 @@ struct HostCtx {
 // kernel's barriers impose; a host copy with zero fill stands in for the TMA box (out-of-bounds elements read 0).
 struct SeqCtx {
     unsigned long long *hist;
-    void hist_add(int sym, bool active) {
-        if (active) hist[sym]++;
+    int lo8;
+    bool hist_fast(int sym, bool active) {   // same split as DevCtxBox: an 8-bin window, the rest reported back
+        const unsigned k8 = static_cast<unsigned>(sym - lo8);
+        if (active && k8 < 8u) hist[sym]++;
+        return active && k8 >= 8u;
     }
+    void hist_rare(int sym) { hist[sym]++; }
 };
 
 template <bool CUBIC>
@@ -47,7 +51,7 @@ static void box_tile_emul(const BoxArgs &A, uint32_t tile, unsigned long long *h
     static std::vector<float> EE(kBoxEEElems), slots(kBoxWarps * kBoxSlotStride);
     static std::vector<uint16_t> stage(kBoxWarps * kBoxStageU16);
     std::fill(EE.begin(), EE.end(), std::numeric_limits<float>::quiet_NaN());   // unfilled cells must never matter
-    SeqCtx ctx{hist};
+    SeqCtx ctx{hist, A.qp.radius - 4};
     BoxOrigin o;
     box_origin(A, tile, o);
     BoxTile T;

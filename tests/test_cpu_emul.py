@@ -12,13 +12,14 @@ from common import (ALGO_INTERP, ALGO_LORENZO_REG, dtype_code, emul_lib, field_g
 pytestmark = pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref not built")
 
 
-def emul(data, conf, eb, schedule, nthreads=4):
+def emul(data, conf, eb, schedule, nthreads=4, hist=None):
     E = emul_lib()
     q = np.empty(data.size, np.int32)
     un = np.empty(data.size, data.dtype)
     nun = C.c_size_t(0)
     rc = E.emul_interp_decompose(dtype_code(data), C.byref(conf), C.c_double(eb), data.ctypes.data_as(C.c_void_p), schedule,
-                                 nthreads, q.ctypes.data_as(C.c_void_p), un.ctypes.data_as(C.c_void_p), C.byref(nun), None)
+                                 nthreads, q.ctypes.data_as(C.c_void_p), un.ctypes.data_as(C.c_void_p), C.byref(nun),
+                                 None if hist is None else hist.ctypes.data_as(C.c_void_p))
     assert rc == 0
     return q, un[:nun.value]
 
@@ -251,7 +252,9 @@ def test_emul_box_schedule(shape, kw):
     conf = make_config(shape, cmprAlgo=ALGO_INTERP, interpAnchorStride=32, interpDirection=0, **kw)
     for eb in (1e-2, 1e-5):
         q_ref, blob_ref, _ = ref_interp(ref_lib(), data, conf, eb)
-        q, un = emul(data, conf, eb, 6, nthreads=32)
+        hist = np.zeros(conf.quantbinCnt, np.uint64)
+        q, un = emul(data, conf, eb, 6, nthreads=32, hist=hist)
         assert np.array_equal(q, q_ref)
         _, un_ref = interp_blob_unpred(blob_ref, conf.N, np.float32)
         assert np.array_equal(un, un_ref, equal_nan=True)
+        assert np.array_equal(hist, np.bincount(q_ref, minlength=conf.quantbinCnt).astype(np.uint64))
