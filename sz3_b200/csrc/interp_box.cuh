@@ -266,6 +266,54 @@ SZ_HD void box_target_rt(uint32_t k, bool n_odd, const QuantParams &qp, Ld &&ld,
     }
 }
 
+// Eight consecutive targets k = 8h + t of a line of n = 32 | 33 points, the unit every pass is cut into (one compact
+// body instead of sixteen unrolled targets per pass: the kernel has to stay inside the instruction cache).
+//   nb[m]  value at lattice index 8h - 1 + m, i.e. local index 2 (8h - 1 + m); entries outside the line must be 0
+//   og[t]  original value of target t (local index 16h + 2t + 1)
+// Results: rc[t] reconstructions, H.q[t] indices (counted in the histogram when `owned`).
+template <bool CUBIC, class Ctx>
+SZ_HD void box_run8(const float (&nb)[11], const float (&og)[8], uint32_t h, bool n_odd, const QuantParams &qp, Ctx &ctx,
+                    bool owned, float (&rc)[8], BoxHist<Ctx, 8> &H) {
+    float rec_prev = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        float pred;
+        if (CUBIC) {
+            if (t >= 1 && t <= 5) {
+                pred = interp_cubic<float>(nb[t], nb[t + 1], nb[t + 2], nb[t + 3]);
+            } else {
+                uint32_t kind = BOX_ST_CUBIC;
+                if (t == 0 && h == 0) kind = BOX_ST_QUAD1;
+                if (t == 6 && h == 1 && !n_odd) kind = BOX_ST_QUAD2;
+                if (t == 7 && h == 1) kind = n_odd ? BOX_ST_QUAD2 : BOX_ST_LINEAR1;
+                pred = box_stencil4(kind, nb[t], nb[t + 1], nb[t + 2], nb[t + 3]);
+            }
+        } else {
+            pred = interp_linear<float>(nb[t + 1], nb[t + 2]);
+            if (t == 7 && h == 1 && !n_odd) pred = interp_linear1<float>(rec_prev, nb[t + 1]);
+        }
+        const int qv = quantize_f32(og[t], pred, qp, rc[t]);
+        rec_prev = rc[t];
+        H.add(ctx, t, qv, owned);
+    }
+}
+
+// Element offset (relative to E.qm) of target k = 8h + t: the regular main-phase ones advance by main_mul, the first
+// and the last two of a line sit in boundary sub-phases.
+template <bool CUBIC>
+SZ_HD uint32_t box_off8(const BoxEmit &E, uint32_t h, bool n_odd, int t) {
+    const uint32_t reg = (8u * h + static_cast<uint32_t>(t) - (CUBIC ? 1u : 0u)) * E.main_mul;
+    const uint32_t b1 = E.bnd0 + E.other, b2 = b1 + E.other;
+    if (CUBIC) {
+        if (t == 0) return h ? reg : E.bnd0;
+        if (t == 6) return (h && !n_odd) ? b1 : reg;
+        if (t == 7) return h ? (n_odd ? b1 : b2) : reg;
+        return reg;
+    }
+    if (t == 7) return (h && !n_odd) ? E.bnd0 : reg;
+    return reg;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // phase A: EE fill, thread c fills z-line c (c = y' * 17 + x'); asynchronous 4-byte copies, one wait at the end
 // ---------------------------------------------------------------------------------------------------------------------
@@ -310,42 +358,32 @@ SZ_HD void box_pass0_line(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
     const uint32_t yl = c / 17u, xl = c - yl * 17u;
     if (yl >= T.C[1] || xl >= T.C[2]) return;
     const bool n_odd = T.n[0] & 1u;
-    float v[33];
-#pragma unroll
-    for (int z = 0; z < 32; z++) v[z] = EE[z * kBoxEEPlane + c];
-    v[32] = n_odd ? EE[32 * kBoxEEPlane + c] : 0.0f;
     BoxEmit E;
     bool owned;
     box_pass0_emit<Ctx>(A, T, yl, xl, E, owned);
     const QuantParams qp = A.qp;
-    float *const col = EE + c;
     // where the line's originals sit in the input (rare path: value of an unpredictable point)
     const uint64_t gstep = static_cast<uint64_t>(A.s) * A.sh.stride[0];
     const float *const gcol = A.data + T.gbase + (static_cast<uint64_t>(2 * yl) * A.sh.stride[1] + 2 * xl) * A.s;
-    float rec_prev = 0.0f;
+#pragma unroll 1
+    for (uint32_t h = 0; h < 2; h++) {
+        float *const col = EE + c + h * (16 * kBoxEEPlane);   // local z = 16h
+        float nb[11], og[8], rc[8];
+        nb[0] = h ? col[-2 * kBoxEEPlane] : 0.0f;
 #pragma unroll
-    for (int half = 0; half < 2; half++) {   // two runs of eight: bounds the indices kept for the rare histogram path
+        for (int m = 1; m < 9; m++) nb[m] = col[(2 * m - 2) * kBoxEEPlane];
+        nb[9] = (h == 0 || n_odd) ? col[16 * kBoxEEPlane] : 0.0f;
+        nb[10] = h ? 0.0f : col[18 * kBoxEEPlane];
+#pragma unroll
+        for (int t = 0; t < 8; t++) og[t] = col[(2 * t + 1) * kBoxEEPlane];
         BoxHist<Ctx, 8> H;
+        box_run8<CUBIC>(nb, og, h, n_odd, qp, ctx, owned, rc, H);
 #pragma unroll
         for (int t = 0; t < 8; t++) {
-            const int k = 8 * half + t;
-            const float pred = box_pred<CUBIC>(v, k, n_odd, rec_prev);
-            const float orig = v[2 * k + 1];
-            float rec;
-            const int qv = quantize_f32(orig, pred, qp, rec);
-            rec_prev = rec;
-            col[(2 * k + 1) * kBoxEEPlane] = rec;
-            uint32_t idx;
-            const bool in_main = box_class<CUBIC>(k, n_odd, idx);
-            if (owned) E.qm[box_off(E, in_main, idx)] = static_cast<uint16_t>(qv);
-            H.add(ctx, t, qv, owned);
+            col[(2 * t + 1) * kBoxEEPlane] = rc[t];
+            if (owned) E.qm[box_off8<CUBIC>(E, h, n_odd, t)] = static_cast<uint16_t>(H.q[t]);
         }
-        H.finish(ctx, [&](int t) {
-            const int k = 8 * half + t;
-            uint32_t idx;
-            const bool in_main = box_class<CUBIC>(k, n_odd, idx);
-            E.um[box_off(E, in_main, idx)] = gcol[static_cast<uint64_t>(2 * k + 1) * gstep];
-        });
+        H.finish(ctx, [&](int t) { E.um[box_off8<CUBIC>(E, h, n_odd, t)] = gcol[static_cast<uint64_t>(16 * h + 2 * t + 1) * gstep]; });
     }
 }
 
@@ -409,68 +447,32 @@ SZ_HD void box_pass1_lane(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
                           float *slot) {
     const uint32_t xl = lane & 15u, h = lane >> 4;
     const bool n_odd = T.n[1] & 1u;
-    const int jmax = n_odd ? 16 : 15;             // last lattice index along y
-    // window w[m] = value at lattice index jb + m, jb = -1 (h = 0) or 7 (h = 1); target t (k = 8h + t) uses w[t .. t+3]
-    float w[11];
+    float nb[11], og[8], rc[8];
     {
-        const float *src = EEz + xl + (h ? 7 * 17 : -17);
-        w[0] = h ? src[0] : 0.0f;
+        const float *src = EEz + xl + (h ? 7 * 17 : -17);   // lattice index 8h - 1
+        nb[0] = h ? src[0] : 0.0f;
 #pragma unroll
-        for (int m = 1; m < 9; m++) w[m] = src[m * 17];                 // j = 0..7 | 8..15
-        w[9] = (h == 0 || jmax == 16) ? src[9 * 17] : 0.0f;              // j = 8 | 16
-        w[10] = h ? 0.0f : src[10 * 17];                                 // j = 9 | 17 (beyond the line)
+        for (int m = 1; m < 9; m++) nb[m] = src[m * 17];
+        nb[9] = (h == 0 || n_odd) ? src[9 * 17] : 0.0f;
+        nb[10] = h ? 0.0f : src[10 * 17];
     }
+    float *const col = slot + 2 * xl + h * (16 * kBoxPitch);
+#pragma unroll
+    for (int t = 0; t < 8; t++) og[t] = col[(2 * t + 1) * kBoxPitch];
     BoxEmit E;
     bool owned;
     box_pass1_emit<Ctx>(A, T, z, xl, E, owned);
-    const QuantParams qp = A.qp;
-    float *const col = slot + 2 * xl + h * (16 * kBoxPitch);
-    // element offsets (relative to E.qm) of the lane's targets k = 8h + t: regular main-phase ones advance by c2x,
-    // the first / last two of a line sit in boundary sub-phases
-    const uint32_t c2x = E.main_mul, b1 = E.bnd0 + E.other, b2 = b1 + E.other;
-    const uint32_t base_off = (8u * h - (CUBIC ? 1u : 0u)) * c2x;
-    auto off_of = [&](int t) -> uint32_t {
-        const uint32_t reg = base_off + static_cast<uint32_t>(t) * c2x;
-        if (CUBIC) {
-            if (t == 0) return h ? reg : E.bnd0;
-            if (t == 6) return (h && !n_odd) ? b1 : reg;
-            if (t == 7) return h ? (n_odd ? b1 : b2) : reg;
-            return reg;
-        }
-        if (t == 7) return (h && !n_odd) ? E.bnd0 : reg;
-        return reg;
-    };
-    float rec_prev = 0.0f;
     BoxHist<Ctx, 8> H;
+    box_run8<CUBIC>(nb, og, h, n_odd, A.qp, ctx, owned, rc, H);
 #pragma unroll
     for (int t = 0; t < 8; t++) {
-        float pred;
-        if (CUBIC) {
-            if (t >= 1 && t <= 5) {
-                pred = interp_cubic<float>(w[t], w[t + 1], w[t + 2], w[t + 3]);
-            } else {
-                uint32_t kind = BOX_ST_CUBIC;
-                if (t == 0 && h == 0) kind = BOX_ST_QUAD1;
-                if (t == 6 && h == 1 && !n_odd) kind = BOX_ST_QUAD2;
-                if (t == 7 && h == 1) kind = n_odd ? BOX_ST_QUAD2 : BOX_ST_LINEAR1;
-                pred = box_stencil4(kind, w[t], w[t + 1], w[t + 2], w[t + 3]);
-            }
-        } else {
-            pred = interp_linear<float>(w[t + 1], w[t + 2]);
-            if (t == 7 && h == 1 && !n_odd) pred = interp_linear1<float>(rec_prev, w[t + 1]);
-        }
-        const float orig = col[(2 * t + 1) * kBoxPitch];
-        float rec;
-        const int qv = quantize_f32(orig, pred, qp, rec);
-        rec_prev = rec;
-        col[(2 * t + 1) * kBoxPitch] = rec;
-        if (owned) E.qm[off_of(t)] = static_cast<uint16_t>(qv);
-        H.add(ctx, t, qv, owned);
+        col[(2 * t + 1) * kBoxPitch] = rc[t];
+        if (owned) E.qm[box_off8<CUBIC>(E, h, n_odd, t)] = static_cast<uint16_t>(H.q[t]);
     }
     H.finish(ctx, [&](int t) {
         // rare: the original of an unpredictable point, re-read from the input at local (z, 2k + 1, 2x')
         const uint64_t g = T.gbase + (static_cast<uint64_t>(z) * A.sh.stride[0] + static_cast<uint64_t>(16 * h + 2 * t + 1) * A.sh.stride[1] + 2 * xl) * A.s;
-        E.um[off_of(t)] = A.data[g];
+        E.um[box_off8<CUBIC>(E, h, n_odd, t)] = A.data[g];
     });
 }
 
@@ -538,31 +540,39 @@ SZ_HD void box_pass2_row(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t 
     BoxRowOut R;
     box_row_out(A, T, ry, z, stage, R);
     const QuantParams qp = A.qp;
-    float rec_prev = 0.0f;
+#pragma unroll 1
+    for (uint32_t h = 0; h < 2; h++) {
+        // the half's window out of the row registers: nb[m] = v[16h - 2 + 2m], og[t] = v[16h + 2t + 1]
+        float nb[11], og[8], rc[8];
+        nb[0] = h ? v[14] : 0.0f;
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+        for (int m = 1; m < 9; m++) nb[m] = h ? v[14 + 2 * m] : v[2 * m - 2];
+        nb[9] = h ? (n_odd ? v[32] : 0.0f) : v[16];
+        nb[10] = h ? 0.0f : v[18];
+#pragma unroll
+        for (int t = 0; t < 8; t++) og[t] = h ? v[17 + 2 * t] : v[2 * t + 1];
         BoxHist<Ctx, 8> H;
+        box_run8<CUBIC>(nb, og, h, n_odd, qp, ctx, true, rc, H);
+        uint16_t *const sm = R.srow + 8 * h - (CUBIC ? 1 : 0);   // regular main-phase target t at sm[t]
 #pragma unroll
         for (int t = 0; t < 8; t++) {
-            const int k = 8 * half + t;
-            const float pred = box_pred<CUBIC>(v, k, n_odd, rec_prev);
-            const float orig = v[2 * k + 1];
-            float rec;
-            const int qv = quantize_f32(orig, pred, qp, rec);
-            rec_prev = rec;
-            uint32_t idx;
-            if (box_class<CUBIC>(k, n_odd, idx))
-                R.srow[idx] = static_cast<uint16_t>(qv);
-            else
-                R.qb[idx * R.other] = static_cast<uint16_t>(qv);
-            H.add(ctx, t, qv, true);
+            uint32_t i0, i1;
+            const bool m0 = box_class<CUBIC>(t, n_odd, i0), m1 = box_class<CUBIC>(8 + t, n_odd, i1);
+            const bool in_main = h ? m1 : m0;
+            const uint32_t idx = h ? i1 : i0;
+            const uint16_t qv = static_cast<uint16_t>(H.q[t]);
+            if (m0 && m1) {
+                sm[t] = qv;
+            } else {
+                if (in_main) sm[t] = qv; else R.qb[idx * R.other] = qv;
+            }
         }
         H.finish(ctx, [&](int t) {
             // rare: the original of an unpredictable point, re-read from the input at local (z, y, 2k + 1)
-            const int k = 8 * half + t;
+            const uint32_t k = 8 * h + t;
             const uint64_t g = T.gbase + (static_cast<uint64_t>(z) * A.sh.stride[0] + static_cast<uint64_t>(ry + T.low[1]) * A.sh.stride[1] + (2 * k + 1)) * A.s;
             uint32_t idx;
-            if (box_class<CUBIC>(k, n_odd, idx))
+            if (box_class_rt<CUBIC>(k, n_odd, idx))
                 R.um[idx] = A.data[g];
             else
                 R.ub[idx * R.other] = A.data[g];
