@@ -7,6 +7,7 @@
 // warps per SM (88 KB of shared memory each) cover each other's phase-A latency.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "device_ctx.cuh"
 #include "interp_box.cuh"
@@ -56,8 +57,10 @@ __device__ __forceinline__ void tma_plane(float *dst, const CUtensorMap *map, ui
         : "memory");
 }
 
+__device__ __forceinline__ void gather_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <bool CUBIC>
-__global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_constant__ CUtensorMap tmap, BoxArgs A) {
+__global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_constant__ CUtensorMap tmap, BoxArgs A, BoxSrc S) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *const slots = reinterpret_cast<float *>(smem_raw);
     float *const EE = slots + kBoxWarps * kBoxSlotStride;
@@ -69,14 +72,16 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t tile = blockIdx.x + A.tile0;
     BoxOrigin o;
-    box_origin(A, tile, o);
+    box_origin(A, S, tile, o);
     float *const slot = slots + warp * kBoxSlotStride;
     uint16_t *const stage = stages + warp * kBoxStageU16;
     uint64_t *const bar = bars + warp;
     const uint32_t nz = o.n[0];
+    const bool tma = S.tma != 0, write2 = A.s >= 2;
     uint32_t z = (o.begin[0] ? 1u : 0u) + warp;   // planes of this warp: z, z + 8, ...
-    const int x0 = static_cast<int>(o.begin[2]), y0 = static_cast<int>(o.begin[1]), z0 = static_cast<int>(o.begin[0]);
-    if (lane == 0) {
+    const int x0 = static_cast<int>(o.begin[2] / S.odiv), y0 = static_cast<int>(o.begin[1] / S.odiv),
+              z0 = static_cast<int>(o.begin[0] / S.odiv);
+    if (tma && lane == 0) {
         mbar_init(bar, 1);
         fence_barrier_init();
         if (z < nz) {   // the first plane travels while phase A runs
@@ -88,27 +93,34 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
     for (int i = tid; i < kHistWindow; i += kBoxThreads) shist[i] = 0;
     if (tid == 0) box_tile_setup<CUBIC>(A, tile, o, T);
     // ---- phase A: EE, pass 0 ----------------------------------------------------------------------------------------
-    box_fill_column(A, o, tid, EE);
-    if (tid < 33) box_fill_column(A, o, 256 + tid, EE);
+    box_fill_column(A, S, o, tid, EE);
+    if (tid < 33) box_fill_column(A, S, o, 256 + tid, EE);
     fill_copy_wait();
     __syncthreads();
-    box_pass0_line<CUBIC>(A, ctx, T, tid, EE);
+    if (!tma && z < nz) box_gather_plane(S, T, lane, z, slot);   // (needs T: after the barrier)
+    box_pass0_line<CUBIC>(A, S, ctx, T, tid, EE);
     for (uint32_t e = tid; e < 33u * 16u; e += kBoxThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE);
     __syncthreads();
     // ---- phase B: the warp's planes -----------------------------------------------------------------------------------
     const uint32_t lowy = T.low[1], c1y = T.c1[1];
     unsigned parity = 0;
     for (; z < nz; z += kBoxWarps) {
-        mbar_wait(bar, parity);
-        parity ^= 1u;
+        if (tma) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            gather_wait();
+            __syncwarp();
+        }
         const float *const EEz = EE + z * kBoxEEPlane;
         box_merge(T, lane, EEz, slot);
-        box_pass1_lane<CUBIC>(A, ctx, T, lane, z, EEz, slot);
+        box_pass1_lane<CUBIC>(A, S, ctx, T, lane, z, EEz, slot);
         box_pass1_left<CUBIC>(A, ctx, T, lane, z, EEz, slot);
         __syncwarp();
         float v[36];
+        float *const my_row = slot + (lane + lowy) * kBoxPitch;
         if (lane < c1y) {
-            const float4 *row = reinterpret_cast<const float4 *>(slot + (lane + lowy) * kBoxPitch);
+            const float4 *row = reinterpret_cast<const float4 *>(my_row);
 #pragma unroll
             for (int c = 0; c < 9; c++) {
                 const float4 f = row[c];
@@ -118,20 +130,67 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
                 v[4 * c + 3] = f.w;
             }
         }
-        box_pass2_left<CUBIC>(A, ctx, T, lane, z, slot, stage);
-        __syncwarp();
-        if (lane == 0 && z + kBoxWarps < nz) {   // slot free: the next plane comes in under the arithmetic of this one
-            fence_proxy_async();
-            mbar_expect_tx(bar, kBoxPlaneBytes);
-            tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z + kBoxWarps));
+        box_pass2_left<CUBIC>(A, ctx, T, lane, z, slot, stage, write2);
+        const bool more = z + kBoxWarps < nz;
+        if (!write2) {   // slot free: the next plane comes in under the arithmetic of this one
+            __syncwarp();
+            if (more) {
+                if (tma) {
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(bar, kBoxPlaneBytes);
+                        tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z + kBoxWarps));
+                    }
+                } else {
+                    box_gather_plane(S, T, lane, z + kBoxWarps, slot);
+                }
+            }
         }
-        if (lane < c1y) box_pass2_row<CUBIC>(A, ctx, T, lane, z, v, stage);
+        if (lane < c1y) box_pass2_row<CUBIC>(A, S, ctx, T, lane, z, v, stage, write2 ? my_row : nullptr);
         __syncwarp();
         box_copy_out(A, T, lane, z, stage);
+        if (write2) {   // the plane's reconstructions feed the next finer level; the slot is re-armed after that
+            box_plane_out(A, T, lane, z, slot);
+            __syncwarp();
+            if (more) {
+                if (tma) {
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(bar, kBoxPlaneBytes);
+                        tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z + kBoxWarps));
+                    }
+                } else {
+                    box_gather_plane(S, T, lane, z + kBoxWarps, slot);
+                }
+            }
+        }
         __syncwarp();
     }
     ctx.pass_end();
     ctx.flush();
+}
+
+// Compact copies of the coarse lattices: dst_k[z][y][x] = src[z * s_k][y * s_k][x * s_k] for up to three strides
+// s_0 < s_1 < s_2 (each twice the previous).  A single tile of a coarse level would gather its ~36 k scattered sectors
+// with one SM (tens of microseconds of pure latency); here the whole GPU does it once, and the levels then read dense
+// arrays.  One thread per element of the finest of the compact lattices.
+struct CompactArgs {
+    const float *src;
+    uint64_t sstride[3];
+    uint32_t s0;
+    uint32_t cd[3][3];     // dims of compact array k
+    float *dst[3];
+    int n;
+};
+__global__ void __launch_bounds__(256) k_box_compact(CompactArgs C) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    if (x >= C.cd[0][2]) return;
+    const float v = C.src[(static_cast<uint64_t>(z) * C.sstride[0] + static_cast<uint64_t>(y) * C.sstride[1] + x) * C.s0];
+    C.dst[0][(static_cast<uint64_t>(z) * C.cd[0][1] + y) * C.cd[0][2] + x] = v;
+    if (C.n > 1 && !((x | y | z) & 1u))
+        C.dst[1][(static_cast<uint64_t>(z >> 1) * C.cd[1][1] + (y >> 1)) * C.cd[1][2] + (x >> 1)] = v;
+    if (C.n > 2 && !((x | y | z) & 3u))
+        C.dst[2][(static_cast<uint64_t>(z >> 2) * C.cd[2][1] + (y >> 2)) * C.cd[2][2] + (x >> 2)] = v;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -155,44 +214,67 @@ EncodeTiledFn encode_tiled_fn() {
 }  // namespace
 
 // Can the level with stride A.s run on the box schedule?  (float / 16-bit indices by type; pass order z, y, x; every
-// tile 32 or 33 points wide; rows 16-byte aligned for the tensor map.)
-bool interp_box_applicable(const BoxArgs &A, uint64_t ntiles_level) {
-    if (A.s != 1 || A.sh.N != 3 || A.sh.perm[0] != 0 || A.sh.perm[1] != 1 || A.sh.perm[2] != 2) return false;
-    if ((reinterpret_cast<uintptr_t>(A.data) & 15u) || (A.sh.dims[2] & 3u)) return false;
+// tile 32 or 33 points wide.)
+bool interp_box_applicable(const BoxArgs &A) {
+    if (A.sh.N != 3 || A.sh.perm[0] != 0 || A.sh.perm[1] != 1 || A.sh.perm[2] != 2) return false;
     if ((reinterpret_cast<uintptr_t>(A.q) & 15u)) return false;
     for (int d = 0; d < 3; d++) {
-        // tiles are 33 points wide except the last one, which holds ((dims - 1) % 32) + 1
-        if (((A.sh.dims[d] - 1) % kInterpBlock) + 1 != 32) return false;
+        // tiles are 33 points wide except the last one
+        const uint32_t B = kInterpBlock * A.s;
+        const uint32_t last_begin = ((A.sh.dims[d] - 1) / B) * B;
+        const uint32_t n_last = (A.sh.dims[d] - 1 - last_begin) / A.s + 1;
+        if (n_last != 32 && n_last != 33) return false;
     }
-    (void)ntiles_level;
-    return encode_tiled_fn() != nullptr;
+    return true;
 }
 
-// Launches tiles [A.tile0, A.tile0 + ntiles) of the level.  Returns false when the tensor map cannot be encoded
-// (the caller then takes the line-walker kernel).
-bool interp_launch_box(const BoxArgs &A, uint64_t ntiles, cudaStream_t st) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) return false;
+void interp_launch_compact(const float *src, const uint32_t dims[3], const uint64_t stride[3], uint32_t s0, int n, float *const dst[3],
+                           cudaStream_t st) {
+    CompactArgs C;
+    C.src = src;
+    C.s0 = s0;
+    C.n = n;
+    for (int d = 0; d < 3; d++) C.sstride[d] = stride[d];
+    for (int k = 0; k < 3; k++) {
+        for (int d = 0; d < 3; d++) C.cd[k][d] = k < n ? (dims[d] - 1) / (s0 << k) + 1 : 1;
+        C.dst[k] = k < n ? dst[k] : nullptr;
+    }
+    const dim3 grid((C.cd[0][2] + 255) / 256, C.cd[0][1], C.cd[0][0]);
+    k_box_compact<<<grid, 256, 0, st>>>(C);
+}
+
+// Launches tiles [A.tile0, A.tile0 + ntiles) of the level.  `S` says where the level's values come from; with S.tma
+// the planes arrive by TMA box copies through a tensor map over S.p (dims `sdims`, dense rows).  Returns false when
+// the tensor map cannot be encoded (the caller then takes the gather fill or the line-walker kernel).
+bool interp_launch_box(const BoxArgs &A, const BoxSrc &S, const uint32_t sdims[3], uint64_t ntiles, cudaStream_t st) {
     CUtensorMap map;
-    const cuuint64_t gdim[3] = {A.sh.dims[2], A.sh.dims[1], A.sh.dims[0]};
-    const cuuint64_t gstr[2] = {A.sh.stride[1] * sizeof(float), A.sh.stride[0] * sizeof(float)};
-    const cuuint32_t box[3] = {static_cast<cuuint32_t>(kBoxPitch), 33u, 1u};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(A.data), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return false;
-    static bool attr_set = false;
-    if (!attr_set) {
+    memset(&map, 0, sizeof(map));
+    if (S.tma) {
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) return false;
+        if ((reinterpret_cast<uintptr_t>(S.p) & 15u) || (sdims[2] & 3u) || S.st[2] != 1) return false;
+        const cuuint64_t gdim[3] = {sdims[2], sdims[1], sdims[0]};
+        const cuuint64_t gstr[2] = {S.st[1] * sizeof(float), S.st[0] * sizeof(float)};
+        const cuuint32_t box[3] = {static_cast<cuuint32_t>(kBoxPitch), 33u, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(S.p), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {false};
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         cudaFuncSetAttribute(k_interp_box<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxSmem));
         cudaFuncSetAttribute(k_interp_box<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxSmem));
-        attr_set = true;
+        attr_set[dev] = true;
     }
     const dim3 grid(static_cast<unsigned>(ntiles));
     if (A.sh.cubic)
-        k_interp_box<true><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A);
+        k_interp_box<true><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A, S);
     else
-        k_interp_box<false><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A);
+        k_interp_box<false><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A, S);
     return true;
 }
 

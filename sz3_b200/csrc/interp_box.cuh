@@ -48,6 +48,18 @@ struct alignas(16) BoxChunk {
 };
 #endif
 
+// Where a level's input values come from: the input array itself (one lattice step = s elements per dim) or a compact
+// copy of the level's lattice (interp_box.cu: k_box_compact; unit steps, so that coarse levels read dense memory and
+// can use the TMA path).  Lattice point (l0, l1, l2) of the tile with origin `begin` is
+// p[sum_d (begin[d] / odiv) * ost[d] + l[d] * st[d]].
+struct BoxSrc {
+    const float *p;
+    uint64_t ost[3];   // stride of the tile origin (per unit of begin / odiv)
+    uint64_t st[3];    // one lattice step
+    uint32_t odiv;
+    uint32_t tma;      // planes arrive by TMA box copies (unit x step, 16-byte aligned rows) or by per-element copies
+};
+
 // Per-tile constants (shared memory; written by one thread while the others fill EE).
 struct BoxTile {
     uint32_t n[3];       // points per dim (32 or 33), natural order z, y, x
@@ -59,16 +71,17 @@ struct BoxTile {
     uint32_t pb[3];      // first index of each pass, relative to qbase
     uint32_t other[3];   // lines of each pass (product of the owned counts of the two other dims)
     uint64_t qbase;      // position of the tile's first index in the stream
-    uint64_t gbase;      // element offset of the tile's origin in the input array
+    uint64_t sbase;      // element offset of the tile's origin in the source array (BoxSrc)
+    uint64_t g2base;     // ... and in recon2
 };
 
 // What every thread needs before BoxTile is ready (a few integer operations, recomputed per thread).
 struct BoxOrigin {
     uint32_t begin[3], n[3];
-    uint64_t gbase, g2base;
+    uint64_t sbase, g2base;
 };
 
-SZ_HD void box_origin(const BoxArgs &A, uint32_t tile, BoxOrigin &o) {
+SZ_HD void box_origin(const BoxArgs &A, const BoxSrc &S, uint32_t tile, BoxOrigin &o) {
     uint32_t bidx[3];
     uint32_t r = tile;
     bidx[2] = r % A.nb[2];
@@ -76,7 +89,7 @@ SZ_HD void box_origin(const BoxArgs &A, uint32_t tile, BoxOrigin &o) {
     bidx[1] = r % A.nb[1];
     bidx[0] = r / A.nb[1];
     const uint32_t B = kInterpBlock * A.s;
-    o.gbase = 0;
+    o.sbase = 0;
     o.g2base = 0;
     for (int d = 0; d < 3; d++) {
         const uint32_t b = bidx[d] * B;
@@ -84,7 +97,7 @@ SZ_HD void box_origin(const BoxArgs &A, uint32_t tile, BoxOrigin &o) {
         if (e > A.sh.dims[d] - 1) e = A.sh.dims[d] - 1;
         o.begin[d] = b;
         o.n[d] = (e - b) / A.s + 1;
-        o.gbase += static_cast<uint64_t>(b) * A.sh.stride[d];
+        o.sbase += static_cast<uint64_t>(b / S.odiv) * S.ost[d];
         o.g2base += static_cast<uint64_t>(b >> 1) * A.stride2[d];
     }
 }
@@ -115,7 +128,8 @@ SZ_HD void box_tile_setup(const BoxArgs &A, uint32_t tile, const BoxOrigin &o, B
     T.pb[1] = (T.mainc[0] + nbnd[0]) * T.other[0];
     T.pb[2] = T.pb[1] + (T.mainc[1] + nbnd[1]) * T.other[1];
     T.qbase = A.block_base[tile];
-    T.gbase = o.gbase;
+    T.sbase = o.sbase;
+    T.g2base = o.g2base;
 }
 
 // Sub-phase of target k (local index 2k + 1) on a line of n = 33 (n_odd) or 32 points: true = main sub-phase with
@@ -317,7 +331,7 @@ SZ_HD uint32_t box_off8(const BoxEmit &E, uint32_t h, bool n_odd, int t) {
 // ---------------------------------------------------------------------------------------------------------------------
 // phase A: EE fill, thread c fills z-line c (c = y' * 17 + x'); asynchronous 4-byte copies, one wait at the end
 // ---------------------------------------------------------------------------------------------------------------------
-SZ_HD void box_fill_column(const BoxArgs &A, const BoxOrigin &o, uint32_t c, float *EE) {
+SZ_HD void box_fill_column(const BoxArgs &A, const BoxSrc &S, const BoxOrigin &o, uint32_t c, float *EE) {
     const uint32_t yl = c / 17u, xl = c - yl * 17u;
     if (yl >= (o.n[1] + 1) / 2 || xl >= (o.n[2] + 1) / 2) return;
     const uint32_t s = A.s;
@@ -325,8 +339,8 @@ SZ_HD void box_fill_column(const BoxArgs &A, const BoxOrigin &o, uint32_t c, flo
     const float *rc = A.recon2 + o.g2base + static_cast<uint64_t>(yl) * s * A.stride2[1] + static_cast<uint64_t>(xl) * s;
     const uint64_t rstep = static_cast<uint64_t>(s) * A.stride2[0];
     // originals (z odd) at local (z, 2y', 2x')
-    const uint64_t gstep = static_cast<uint64_t>(s) * A.sh.stride[0];
-    const float *gp = A.data + o.gbase + static_cast<uint64_t>(2 * yl) * s * A.sh.stride[1] + static_cast<uint64_t>(2 * xl) * s + gstep;
+    const uint64_t gstep = S.st[0];
+    const float *gp = S.p + o.sbase + 2 * yl * S.st[1] + 2 * xl * S.st[2] + gstep;
     float *dst = EE + c;
 #pragma unroll
     for (int z = 0; z < 32; z += 2) {
@@ -336,6 +350,25 @@ SZ_HD void box_fill_column(const BoxArgs &A, const BoxOrigin &o, uint32_t c, flo
         gp += 2 * gstep;
     }
     if (o.n[0] & 1u) fill_copy(dst + 32 * kBoxEEPlane, rc);
+}
+
+// One raw plane of the tile into a warp's slot by per-element copies (levels whose source cannot feed the TMA path:
+// the input array at stride 2, unaligned rows): lane = x, walking over the rows; then the 33rd column.
+SZ_HD void box_gather_plane(const BoxSrc &S, const BoxTile &T, uint32_t lane, uint32_t z, float *slot) {
+    const float *src = S.p + T.sbase + z * S.st[0];
+    const uint32_t ny = T.n[1], nx = T.n[2];
+    if (lane < nx) {
+        const float *p = src + lane * S.st[2];
+        float *d = slot + lane;
+        for (uint32_t y = 0; y < ny; y++) {
+            fill_copy(d, p);
+            d += kBoxPitch;
+            p += S.st[1];
+        }
+    }
+    if (nx == 33) {
+        for (uint32_t y = lane; y < ny; y += 32) fill_copy(slot + y * kBoxPitch + 32, src + y * S.st[1] + 32 * S.st[2]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -354,7 +387,7 @@ SZ_HD void box_pass0_emit(const BoxArgs &A, const BoxTile &T, uint32_t yl, uint3
 }
 
 template <bool CUBIC, class Ctx>
-SZ_HD void box_pass0_line(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t c, float *EE) {
+SZ_HD void box_pass0_line(const BoxArgs &A, const BoxSrc &S, Ctx &ctx, const BoxTile &T, uint32_t c, float *EE) {
     const uint32_t yl = c / 17u, xl = c - yl * 17u;
     if (yl >= T.C[1] || xl >= T.C[2]) return;
     const bool n_odd = T.n[0] & 1u;
@@ -362,9 +395,9 @@ SZ_HD void box_pass0_line(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
     bool owned;
     box_pass0_emit<Ctx>(A, T, yl, xl, E, owned);
     const QuantParams qp = A.qp;
-    // where the line's originals sit in the input (rare path: value of an unpredictable point)
-    const uint64_t gstep = static_cast<uint64_t>(A.s) * A.sh.stride[0];
-    const float *const gcol = A.data + T.gbase + (static_cast<uint64_t>(2 * yl) * A.sh.stride[1] + 2 * xl) * A.s;
+    // where the line's originals sit in the source (rare path: value of an unpredictable point)
+    const uint64_t gstep = S.st[0];
+    const float *const gcol = S.p + T.sbase + 2 * yl * S.st[1] + 2 * xl * S.st[2];
 #pragma unroll 1
     for (uint32_t h = 0; h < 2; h++) {
         float *const col = EE + c + h * (16 * kBoxEEPlane);   // local z = 16h
@@ -443,8 +476,8 @@ SZ_HD void box_pass1_emit(const BoxArgs &A, const BoxTile &T, uint32_t z, uint32
 }
 
 template <bool CUBIC, class Ctx>
-SZ_HD void box_pass1_lane(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z, const float *EEz,
-                          float *slot) {
+SZ_HD void box_pass1_lane(const BoxArgs &A, const BoxSrc &S, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z,
+                          const float *EEz, float *slot) {
     const uint32_t xl = lane & 15u, h = lane >> 4;
     const bool n_odd = T.n[1] & 1u;
     float nb[11], og[8], rc[8];
@@ -471,8 +504,8 @@ SZ_HD void box_pass1_lane(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
     }
     H.finish(ctx, [&](int t) {
         // rare: the original of an unpredictable point, re-read from the input at local (z, 2k + 1, 2x')
-        const uint64_t g = T.gbase + (static_cast<uint64_t>(z) * A.sh.stride[0] + static_cast<uint64_t>(16 * h + 2 * t + 1) * A.sh.stride[1] + 2 * xl) * A.s;
-        E.um[box_off8<CUBIC>(E, h, n_odd, t)] = A.data[g];
+        const uint64_t g = T.sbase + z * S.st[0] + (16 * h + 2 * t + 1) * S.st[1] + 2 * xl * S.st[2];
+        E.um[box_off8<CUBIC>(E, h, n_odd, t)] = S.p[g];
     });
 }
 
@@ -534,8 +567,8 @@ SZ_HD void box_row_store(const BoxRowOut &R, bool in_main, uint32_t idx, int qv,
 }
 
 template <bool CUBIC, class Ctx>
-SZ_HD void box_pass2_row(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t ry, uint32_t z, const float *v,
-                         uint16_t *stage) {
+SZ_HD void box_pass2_row(const BoxArgs &A, const BoxSrc &S, Ctx &ctx, const BoxTile &T, uint32_t ry, uint32_t z,
+                         const float *v, uint16_t *stage, float *slot_row) {
     const bool n_odd = T.n[2] & 1u;
     BoxRowOut R;
     box_row_out(A, T, ry, z, stage, R);
@@ -553,6 +586,10 @@ SZ_HD void box_pass2_row(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t 
         for (int t = 0; t < 8; t++) og[t] = h ? v[17 + 2 * t] : v[2 * t + 1];
         BoxHist<Ctx, 8> H;
         box_run8<CUBIC>(nb, og, h, n_odd, qp, ctx, true, rc, H);
+        if (slot_row) {   // level stride >= 2: the plane's reconstructions leave for recon2 from the slot (box_plane_out)
+#pragma unroll
+            for (int t = 0; t < 8; t++) slot_row[16 * h + 2 * t + 1] = rc[t];
+        }
         uint16_t *const sm = R.srow + 8 * h - (CUBIC ? 1 : 0);   // regular main-phase target t at sm[t]
 #pragma unroll
         for (int t = 0; t < 8; t++) {
@@ -570,33 +607,57 @@ SZ_HD void box_pass2_row(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t 
         H.finish(ctx, [&](int t) {
             // rare: the original of an unpredictable point, re-read from the input at local (z, y, 2k + 1)
             const uint32_t k = 8 * h + t;
-            const uint64_t g = T.gbase + (static_cast<uint64_t>(z) * A.sh.stride[0] + static_cast<uint64_t>(ry + T.low[1]) * A.sh.stride[1] + (2 * k + 1)) * A.s;
+            const uint64_t g = T.sbase + z * S.st[0] + (ry + T.low[1]) * S.st[1] + (2 * k + 1) * S.st[2];
             uint32_t idx;
             if (box_class_rt<CUBIC>(k, n_odd, idx))
-                R.um[idx] = A.data[g];
+                R.um[idx] = S.p[g];
             else
-                R.ub[idx * R.other] = A.data[g];
+                R.ub[idx * R.other] = S.p[g];
         });
     }
 }
 
 // a 33rd owned row (tiles at y = 0 with 33 points): lane = target, values from the slot
 template <bool CUBIC, class Ctx>
-SZ_HD void box_pass2_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z, const float *slot,
-                          uint16_t *stage) {
+SZ_HD void box_pass2_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t lane, uint32_t z, float *slot,
+                          uint16_t *stage, bool write2) {
     if (T.c1[1] != 33 || lane >= 16) return;
     const bool n_odd = T.n[2] & 1u;
     BoxRowOut R;
     box_row_out(A, T, 32u, z, stage, R);   // low == 0 here: row 32 is local y = 32
-    const float *row = slot + 32 * kBoxPitch;
+    float *row = slot + 32 * kBoxPitch;
     box_target_rt<CUBIC>(
-        lane, n_odd, A.qp, [&](uint32_t l) { return row[l]; }, [&](uint32_t, float) {},
+        lane, n_odd, A.qp, [&](uint32_t l) { return row[l]; },
+        [&](uint32_t l, float r) {
+            if (write2) row[l] = r;
+        },
         [&](uint32_t kk, int qv, float orig) {
             uint32_t idx;
             const bool in_main = box_class_rt<CUBIC>(kk, n_odd, idx);
             box_row_store(R, in_main, idx, qv, orig);
             if (ctx.hist_fast(qv, true)) ctx.hist_rare(qv);
         });
+}
+
+// Level stride >= 2: every owned point of the finished plane goes to recon2, where the next finer level reads it as
+// a coarse point (rows are contiguous there at stride s / 2; lane = x, walking over the rows).
+SZ_HD void box_plane_out(const BoxArgs &A, const BoxTile &T, uint32_t lane, uint32_t z, const float *slot) {
+    const uint64_t h0 = static_cast<uint64_t>(A.s >> 1) * A.stride2[0], h1 = static_cast<uint64_t>(A.s >> 1) * A.stride2[1];
+    const uint32_t h2 = A.s >> 1;
+    float *const base = A.recon2 + T.g2base + z * h0;
+    const uint32_t ny = T.n[1], nx = T.n[2], lowy = T.low[1], lowx = T.low[2];
+    if (lane >= lowx && lane < nx) {
+        float *p = base + lowy * h1 + lane * h2;
+        const float *sl = slot + lowy * kBoxPitch + lane;
+        for (uint32_t y = lowy; y < ny; y++) {
+            *p = *sl;
+            p += h1;
+            sl += kBoxPitch;
+        }
+    }
+    if (nx == 33) {
+        for (uint32_t y = lowy + lane; y < ny; y += 32) base[y * h1 + 32 * h2] = slot[y * kBoxPitch + 32];
+    }
 }
 
 // staging buffer -> index stream: the plane's run [pos, pos + len) starts `mis` indices into a 16-byte chunk, and the

@@ -26,6 +26,7 @@
 #include "zhuf.cuh"
 #include "huffman_host.hpp"
 #include "interp_body.cuh"
+#include "interp_box.cuh"
 #include "interp_plan.hpp"
 #include "launch.hpp"
 #include "pipeline.hpp"
@@ -264,21 +265,86 @@ struct IndexStream {       // device-resident result of a decomposition
     bool wide = false;     // QT = uint32 (radius > 32768)
 };
 
-// Box schedule (interp_box.cu) for the tiles [A.tile0, A.tile0 + ntiles) of the finest level; false = not this type /
-// shape, the caller launches the line walker instead.
+// Box schedule (interp_box.cu).  BoxPlan says, per level, where the level's input values come from: the input array
+// (stride 1 by TMA, stride 2 by per-element copies) or a compact copy of the stride-4 / 8 / 16 lattices made by one
+// whole-GPU gather (a single coarse tile would otherwise gather its ~36 k scattered sectors with one SM).
+struct BoxPlan {
+    bool any = false;
+    float *compact[3] = {nullptr, nullptr, nullptr};   // lattices of stride 4, 8, 16
+    int ncompact = 0;
+};
+
 template <class T, class QT>
-static bool box_applicable(const InterpArgs<T, QT> &A, uint64_t ntiles_level) {
+static bool box_applicable(const InterpArgs<T, QT> &A) {
     if constexpr (std::is_same<T, float>::value && std::is_same<QT, uint16_t>::value)
-        return interp_box_applicable(A, ntiles_level);
+        return interp_box_applicable(A);
     else
         return false;
 }
+
 template <class T, class QT>
-static bool launch_box(const InterpArgs<T, QT> &A, uint64_t ntiles, cudaStream_t st) {
-    if constexpr (std::is_same<T, float>::value && std::is_same<QT, uint16_t>::value)
-        return interp_launch_box(A, ntiles, st);
-    else
+static void box_prepare(Workspace &ws, const InterpPlan &pl, InterpArgs<T, QT> A, uint32_t nbatch, BoxPlan &bp) {
+    if constexpr (std::is_same<T, float>::value && std::is_same<QT, uint16_t>::value) {
+        if (!(pl.box && pl.tile && pl.variant == 2 && nbatch == 1)) return;
+        int need = 0;
+        for (const LevelPlan &L : pl.levels) {
+            A.s = L.s;
+            if (!interp_box_applicable(A)) continue;
+            bp.any = true;
+            for (int k = 0; k < 3; k++)
+                if (L.s == (4u << k)) need = std::max(need, k + 1);
+        }
+        if (need) {
+            size_t total = 0, off[3];
+            for (int k = 0; k < need; k++) {
+                size_t e = 1;
+                for (int d = 0; d < 3; d++) e *= (pl.sh.dims[d] - 1) / (4u << k) + 1;
+                off[k] = total;
+                total += (e + 63) & ~static_cast<size_t>(63);
+            }
+            float *base = ws.compact.as<float>(total);
+            for (int k = 0; k < need; k++) bp.compact[k] = base + off[k];
+            bp.ncompact = need;
+            interp_launch_compact(A.data, pl.sh.dims, pl.sh.stride, 4, need, bp.compact, ws.st);
+        }
+    }
+}
+
+// Tiles [A.tile0, A.tile0 + ntiles) of the level A.s through the box kernel; false = not this type / shape.
+template <class T, class QT>
+static bool launch_box(const InterpArgs<T, QT> &A, const BoxPlan &bp, uint64_t ntiles, cudaStream_t st) {
+    if constexpr (std::is_same<T, float>::value && std::is_same<QT, uint16_t>::value) {
+        if (!bp.any || !interp_box_applicable(A)) return false;
+        BoxSrc S;
+        uint32_t sdims[3];
+        int k = -1;
+        for (int j = 0; j < bp.ncompact; j++)
+            if (A.s == (4u << j)) k = j;
+        if (k >= 0) {
+            for (int d = 0; d < 3; d++) sdims[d] = (A.sh.dims[d] - 1) / A.s + 1;
+            S.p = bp.compact[k];
+            S.st[2] = 1;
+            S.st[1] = sdims[2];
+            S.st[0] = static_cast<uint64_t>(sdims[1]) * sdims[2];
+            for (int d = 0; d < 3; d++) S.ost[d] = S.st[d];
+            S.odiv = A.s;
+            S.tma = (sdims[2] & 3u) == 0;
+        } else {
+            for (int d = 0; d < 3; d++) {
+                sdims[d] = A.sh.dims[d];
+                S.ost[d] = A.sh.stride[d];
+                S.st[d] = A.sh.stride[d] * A.s;
+            }
+            S.p = A.data;
+            S.odiv = 1;
+            S.tma = A.s == 1 && (sdims[2] & 3u) == 0 && (reinterpret_cast<uintptr_t>(A.data) & 15u) == 0;
+        }
+        if (S.tma && interp_launch_box(A, S, sdims, ntiles, st)) return true;
+        S.tma = 0;
+        return interp_launch_box(A, S, sdims, ntiles, st);
+    } else {
         return false;
+    }
 }
 
 template <class T, class QT>
@@ -319,6 +385,9 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         planes = false;
     }
     if (planes) SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.copy_plan.ev_even, 0));
+    BoxPlan bp;
+    box_prepare<T, QT>(ws, pl, A, nbatch, bp);
+    if (bp.ncompact) (*launches)++;
     interp_launch_anchors<T, QT>(A, pl.anchor_stride, pl.n_first, nbatch, ws.st);
     (*launches)++;
     for (const LevelPlan &L : pl.levels) {
@@ -326,7 +395,7 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         A.s = L.s;
         for (int d = 0; d < kMaxDim; d++) A.nb[d] = L.nb[d];
         A.block_base = d_table + L.table_off;
-        const bool box = pl.box && pl.variant == 2 && nbatch == 1 && L.s == 1 && box_applicable<T, QT>(A, L.nblocks);
+        const bool box = bp.any && box_applicable<T, QT>(A);
         if (pl.box_required && L.s == 1 && !box) fail(SZ3B_E_UNSUPPORTED, "box schedule does not apply to this shape / type");
         if (planes && L.s == 1) {
             // the finest level, block-row by block-row as the odd planes arrive
@@ -334,7 +403,7 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
             for (uint32_t b = 0; b < L.nb[0]; b++) {
                 SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.copy_plan.ev_row[b], 0));
                 A.tile0 = static_cast<uint32_t>(b * per_row);
-                if (!(box && launch_box<T, QT>(A, per_row, ws.st))) interp_launch_ltiles<T, QT>(A, per_row, nbatch, ws.st);
+                if (!(box && launch_box<T, QT>(A, bp, per_row, ws.st))) interp_launch_ltiles<T, QT>(A, per_row, nbatch, ws.st);
                 (*launches)++;
             }
             A.tile0 = 0;
@@ -342,7 +411,7 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
             continue;
         }
         if (pl.tile) {
-            if (box && launch_box<T, QT>(A, L.nblocks, ws.st)) {
+            if (box && launch_box<T, QT>(A, bp, L.nblocks, ws.st)) {
             } else if (pl.variant == 2)
                 interp_launch_ltiles<T, QT>(A, L.nblocks, nbatch, ws.st);
             else if (pl.variant == 1)

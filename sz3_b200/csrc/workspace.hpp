@@ -118,7 +118,7 @@ struct Workspace {
     cudaStream_t st_copy = nullptr;   // bulk H2D of the input, so that sampling/tuning can overlap it
     cudaEvent_t ev_copy = nullptr;
     // inputs / index stream
-    DevBuf data, q, unpred_tmp, recon, hist, tables;
+    DevBuf data, q, unpred_tmp, recon, hist, tables, compact;
     // encoder
     DevBuf code, len, chunk_bits, chunk_zeros, bit_off, zero_off, out_words, unpred_out;
     // tuner

@@ -47,47 +47,108 @@ struct SeqCtx {
 };
 
 template <bool CUBIC>
-static void box_tile_emul(const BoxArgs &A, uint32_t tile, unsigned long long *hist) {
+static void box_tile_emul(const BoxArgs &A, const BoxSrc &S, const uint32_t sdims[3], uint32_t tile, unsigned long long *hist) {
     static std::vector<float> EE(kBoxEEElems), slots(kBoxWarps * kBoxSlotStride);
     static std::vector<uint16_t> stage(kBoxWarps * kBoxStageU16);
     std::fill(EE.begin(), EE.end(), std::numeric_limits<float>::quiet_NaN());   // unfilled cells must never matter
     SeqCtx ctx{hist, A.qp.radius - 4};
     BoxOrigin o;
-    box_origin(A, tile, o);
+    box_origin(A, S, tile, o);
     BoxTile T;
     box_tile_setup<CUBIC>(A, tile, o, T);
+    const bool write2 = A.s >= 2;
     for (uint32_t t = 0; t < kBoxThreads; t++) {
-        box_fill_column(A, o, t, EE.data());
-        if (t < 33) box_fill_column(A, o, 256 + t, EE.data());
+        box_fill_column(A, S, o, t, EE.data());
+        if (t < 33) box_fill_column(A, S, o, 256 + t, EE.data());
     }
-    for (uint32_t t = kBoxThreads; t-- > 0;) box_pass0_line<CUBIC>(A, ctx, T, t, EE.data());
+    for (uint32_t t = kBoxThreads; t-- > 0;) box_pass0_line<CUBIC>(A, S, ctx, T, t, EE.data());
     for (uint32_t t = kBoxThreads; t-- > 0;)
         for (uint32_t e = t; e < 33 * 16; e += kBoxThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE.data());
     for (uint32_t w = kBoxWarps; w-- > 0;) {
         float *slot = slots.data() + w * kBoxSlotStride;
         uint16_t *stg = stage.data() + w * kBoxStageU16;
         for (uint32_t z = T.low[0] + w; z < T.n[0]; z += kBoxWarps) {
-            // TMA box (36, 33, 1) at (x0, y0, z0 + z)
-            for (uint32_t y = 0; y < 33; y++)
-                for (uint32_t x = 0; x < 36; x++) {
-                    const uint64_t gz = o.begin[0] + z, gy = o.begin[1] + y, gx = o.begin[2] + x;
-                    const bool in = gz < A.sh.dims[0] && gy < A.sh.dims[1] && gx < A.sh.dims[2];
-                    slot[y * kBoxPitch + x] = in ? A.data[gz * A.sh.stride[0] + gy * A.sh.stride[1] + gx] : 0.0f;
-                }
+            std::fill(slot, slot + kBoxSlotStride, std::numeric_limits<float>::quiet_NaN());
+            if (S.tma) {
+                // TMA box (36, 33, 1) at (x0, y0, z0 + z) of the dense source array: out-of-bounds elements read 0
+                for (uint32_t y = 0; y < 33; y++)
+                    for (uint32_t x = 0; x < 36; x++) {
+                        const uint64_t gz = o.begin[0] / S.odiv + z, gy = o.begin[1] / S.odiv + y, gx = o.begin[2] / S.odiv + x;
+                        const bool in = gz < sdims[0] && gy < sdims[1] && gx < sdims[2];
+                        slot[y * kBoxPitch + x] = in ? S.p[gz * S.st[0] + gy * S.st[1] + gx] : 0.0f;
+                    }
+            } else {
+                for (uint32_t l = 32; l-- > 0;) box_gather_plane(S, T, l, z, slot);
+            }
             const float *EEz = EE.data() + z * kBoxEEPlane;
             for (uint32_t l = 32; l-- > 0;) box_merge(T, l, EEz, slot);
-            for (uint32_t l = 32; l-- > 0;) box_pass1_lane<CUBIC>(A, ctx, T, l, z, EEz, slot);
+            for (uint32_t l = 32; l-- > 0;) box_pass1_lane<CUBIC>(A, S, ctx, T, l, z, EEz, slot);
             for (uint32_t l = 32; l-- > 0;) box_pass1_left<CUBIC>(A, ctx, T, l, z, EEz, slot);
             std::fill(stg, stg + kBoxStageU16, static_cast<uint16_t>(0xdead));
-            for (uint32_t l = 32; l-- > 0;) box_pass2_left<CUBIC>(A, ctx, T, l, z, slot, stg);
+            float rows[32][36];
+            for (uint32_t l = 0; l < 32; l++)
+                if (l < T.c1[1]) memcpy(rows[l], slot + (l + T.low[1]) * kBoxPitch, sizeof(rows[l]));
+            for (uint32_t l = 32; l-- > 0;) box_pass2_left<CUBIC>(A, ctx, T, l, z, slot, stg, write2);
             for (uint32_t l = 32; l-- > 0;) {
                 if (l >= T.c1[1]) continue;
-                float v[36];
-                memcpy(v, slot + (l + T.low[1]) * kBoxPitch, sizeof(v));
-                box_pass2_row<CUBIC>(A, ctx, T, l, z, v, stg);
+                box_pass2_row<CUBIC>(A, S, ctx, T, l, z, rows[l], stg, write2 ? slot + (l + T.low[1]) * kBoxPitch : nullptr);
             }
             for (uint32_t l = 32; l-- > 0;) box_copy_out(A, T, l, z, stg);
+            if (write2)
+                for (uint32_t l = 32; l-- > 0;) box_plane_out(A, T, l, z, slot);
         }
+    }
+}
+
+// mirrors pipeline.cu: launch_box (source of a level) with host-made compact lattices
+struct BoxEmulPlan {
+    std::vector<float> compact[3];
+};
+static bool box_level_ok(const BoxArgs &A) {
+    if (A.sh.N != 3 || A.sh.perm[0] != 0 || A.sh.perm[1] != 1 || A.sh.perm[2] != 2) return false;
+    for (int d = 0; d < 3; d++) {
+        const uint32_t B = kInterpBlock * A.s;
+        const uint32_t last_begin = ((A.sh.dims[d] - 1) / B) * B;
+        const uint32_t n_last = (A.sh.dims[d] - 1 - last_begin) / A.s + 1;
+        if (n_last != 32 && n_last != 33) return false;
+    }
+    return true;
+}
+static void box_level_emul(const BoxArgs &A, BoxEmulPlan &bp, uint64_t ntiles, unsigned long long *hist) {
+    BoxSrc S;
+    uint32_t sdims[3];
+    int k = -1;
+    for (int j = 0; j < 3; j++)
+        if (A.s == (4u << j)) k = j;
+    if (k >= 0) {
+        for (int d = 0; d < 3; d++) sdims[d] = (A.sh.dims[d] - 1) / A.s + 1;
+        std::vector<float> &c = bp.compact[k];
+        c.resize(static_cast<size_t>(sdims[0]) * sdims[1] * sdims[2]);
+        for (uint32_t z = 0; z < sdims[0]; z++)
+            for (uint32_t y = 0; y < sdims[1]; y++)
+                for (uint32_t x = 0; x < sdims[2]; x++)
+                    c[(static_cast<size_t>(z) * sdims[1] + y) * sdims[2] + x] =
+                        A.data[(z * A.sh.stride[0] + y * A.sh.stride[1] + x) * A.s];
+        S.p = c.data();
+        S.st[2] = 1;
+        S.st[1] = sdims[2];
+        S.st[0] = static_cast<uint64_t>(sdims[1]) * sdims[2];
+        for (int d = 0; d < 3; d++) S.ost[d] = S.st[d];
+        S.odiv = A.s;
+        S.tma = (sdims[2] & 3u) == 0;
+    } else {
+        for (int d = 0; d < 3; d++) {
+            sdims[d] = A.sh.dims[d];
+            S.ost[d] = A.sh.stride[d];
+            S.st[d] = A.sh.stride[d] * A.s;
+        }
+        S.p = A.data;
+        S.odiv = 1;
+        S.tma = A.s == 1 && (sdims[2] & 3u) == 0;
+    }
+    for (uint64_t tile = 0; tile < ntiles; tile++) {
+        if (A.sh.cubic) box_tile_emul<true>(A, S, sdims, static_cast<uint32_t>(tile), hist);
+        else box_tile_emul<false>(A, S, sdims, static_cast<uint32_t>(tile), hist);
     }
 }
 
@@ -154,27 +215,22 @@ static int run(const sz3b_config &c, double eb, const T *data, int schedule, int
         for (int d = 0; d < kMaxDim; d++) A.nb[d] = L.nb[d];
         A.block_base = pl.table.data() + L.table_off;
         std::barrier<> bar(nthreads);
-        // box schedule (schedule 6 of the emulation): every level-1 tile must qualify, else the line walker runs
+        // box schedule (schedule 6 of the emulation): every level whose tiles all qualify, the line walker elsewhere
         bool box_level = false;
-        if (box_schedule && pl.tile && L.s == 1 && sizeof(T) == 4 && sizeof(QT) == 2 && pl.sh.perm[0] == 0 && pl.sh.perm[1] == 1) {
-            box_level = true;
-            for (uint64_t tile = 0; tile < L.nblocks; tile++) {
-                BoxOrigin o;
-                box_origin(*reinterpret_cast<const BoxArgs *>(&A), static_cast<uint32_t>(tile), o);
-                if (!box_tile_ok(o)) box_level = false;
-            }
-            if (!box_level) return -7;
+        if (box_schedule && pl.tile && sizeof(T) == 4 && sizeof(QT) == 2) {
+            box_level = box_level_ok(*reinterpret_cast<const BoxArgs *>(&A));
+            if (!box_level && L.s == 1) return -7;
+        }
+        if (box_level) {
+            static BoxEmulPlan bplan;
+            box_level_emul(*reinterpret_cast<const BoxArgs *>(&A), bplan, L.nblocks, hist.data());
+            continue;
         }
         if (pl.tile) {
             auto worker = [&](int t) {
                 HostCtx ctx{static_cast<uint32_t>(t), static_cast<uint32_t>(nthreads), &bar, hist.data()};
                 for (uint64_t tile = 0; tile < L.nblocks; tile++) {
-                    if (box_level) {
-                        if (t == 0) {
-                            if (pl.sh.cubic) box_tile_emul<true>(*reinterpret_cast<const BoxArgs *>(&A), static_cast<uint32_t>(tile), hist.data());
-                            else box_tile_emul<false>(*reinterpret_cast<const BoxArgs *>(&A), static_cast<uint32_t>(tile), hist.data());
-                        }
-                    } else if (pl.variant == 2) {
+                    if (pl.variant == 2) {
                         static LineTile lt;   // shared by the worker threads like __shared__ memory
                         LineGeom lg;
                         line_geom(A, static_cast<uint32_t>(tile), 0, lg);

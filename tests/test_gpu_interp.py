@@ -129,7 +129,7 @@ def test_interp3d_g3_256(schedule):
 
 
 # ---- box schedule (interp_box.cu): finest level by TMA-staged planes; dims must be multiples of 32 -------------------------
-BOX_SHAPES = [(64, 64, 64), (32, 64, 96), (96, 64, 128), (128, 128, 160)]
+BOX_SHAPES = [(64, 64, 64), (32, 64, 96), (96, 64, 128), (128, 128, 160), (128, 128, 128), (256, 128, 256)]
 
 
 @pytest.mark.parametrize("schedule", [0, 6])
