@@ -59,6 +59,18 @@ __device__ __forceinline__ void tma_plane(float *dst, const CUtensorMap *map, ui
 
 __device__ __forceinline__ void gather_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+#ifdef SZ3B_BOX_TIMING
+__device__ unsigned long long g_box_timing[64];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define BOX_TICK(i) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) g_box_timing[i] = gtime(); } while (0)
+#else
+#define BOX_TICK(i) do { } while (0)
+#endif
+
 template <bool CUBIC>
 __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_constant__ CUtensorMap tmap, BoxArgs A, BoxSrc S) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -71,6 +83,7 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t tile = blockIdx.x + A.tile0;
+    BOX_TICK(0);
     BoxOrigin o;
     box_origin(A, S, tile, o);
     float *const slot = slots + warp * kBoxSlotStride;
@@ -95,12 +108,16 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
     // ---- phase A: EE, pass 0 ----------------------------------------------------------------------------------------
     box_fill_column(A, S, o, tid, EE);
     if (tid < 33) box_fill_column(A, S, o, 256 + tid, EE);
+    BOX_TICK(1);
     fill_copy_wait();
     __syncthreads();
+    BOX_TICK(2);
     if (!tma && z < nz) box_gather_plane(S, T, lane, z, slot);   // (needs T: after the barrier)
     box_pass0_line<CUBIC>(A, S, ctx, T, tid, EE);
     for (uint32_t e = tid; e < 33u * 16u; e += kBoxThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE);
+    BOX_TICK(3);
     __syncthreads();
+    BOX_TICK(4);
     // ---- phase B: the warp's planes -----------------------------------------------------------------------------------
     const uint32_t lowy = T.low[1], c1y = T.c1[1];
     unsigned parity = 0;
@@ -112,11 +129,13 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
             gather_wait();
             __syncwarp();
         }
+        BOX_TICK(5);
         const float *const EEz = EE + z * kBoxEEPlane;
         box_merge(T, lane, EEz, slot);
         box_pass1_lane<CUBIC>(A, S, ctx, T, lane, z, EEz, slot);
         box_pass1_left<CUBIC>(A, ctx, T, lane, z, EEz, slot);
         __syncwarp();
+        BOX_TICK(6);
         float v[36];
         float *const my_row = slot + (lane + lowy) * kBoxPitch;
         if (lane < c1y) {
@@ -148,6 +167,7 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
         }
         if (lane < c1y) box_pass2_row<CUBIC>(A, S, ctx, T, lane, z, v, stage, write2 ? my_row : nullptr);
         __syncwarp();
+        BOX_TICK(7);
         box_copy_out(A, T, lane, z, stage);
         if (write2) {   // the plane's reconstructions feed the next finer level; the slot is re-armed after that
             box_plane_out(A, T, lane, z, slot);
@@ -165,9 +185,11 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
             }
         }
         __syncwarp();
+        BOX_TICK(8);
     }
     ctx.pass_end();
     ctx.flush();
+    BOX_TICK(9);
 }
 
 // Compact copies of the coarse lattices: dst_k[z][y][x] = src[z * s_k][y * s_k][x * s_k] for up to three strides
@@ -277,5 +299,12 @@ bool interp_launch_box(const BoxArgs &A, const BoxSrc &S, const uint32_t sdims[3
         k_interp_box<false><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A, S);
     return true;
 }
+
+#ifdef SZ3B_BOX_TIMING
+extern "C" void sz3b_debug_box_timing(unsigned long long *out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_box_timing, sizeof(unsigned long long) * 64);
+}
+#endif
 
 }  // namespace sz3b
