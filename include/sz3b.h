@@ -124,7 +124,8 @@ int sz3b_tune(int dtype, sz3b_config *c, const void *data, int data_loc);
 /* ---- multi-GPU slab container (api/impl/SZImplOMP.hpp:16-117) -------------------------------------------------------
  * Rank r of `nslabs` compresses rows [r*d0/nslabs, (r+1)*d0/nslabs) of the outermost dimension as an independent
  * stream.  `slab` points at that slab only.  `range` is the global max-min (only read when the error-bound mode is
- * not ABS; ranks obtain it with an all-reduce of sz3b_minmax results).  The rank gets back its payload and its Config
+ * not ABS; ranks obtain it with an all-reduce of sz3b_minmax results; 0 -- a constant field -- is valid and leads to
+ * the lossless path as in the reference, a negative value or NaN means "not supplied" and is an error).  The rank gets back its payload and its Config
  * blob; rank 0 concatenates them with sz3b_omp_assemble after a gather of the sizes. */
 int sz3b_minmax(int dtype, const void *data, int data_loc, size_t num, double *min_out, double *max_out);
 int sz3b_compress_slab(int dtype, const sz3b_config *c, int rank, int nslabs, const void *slab, int data_loc,
@@ -149,6 +150,19 @@ void sz3b_last_transfer(size_t *h2d_bytes, size_t *d2h_bytes);
  * concurrency).  With one rank per GPU on a shared host, give each rank its share of the cores. */
 void sz3b_set_host_threads(int n);
 int sz3b_get_host_threads(void);   /* the value in force (after the defaults above) */
+/* Stream contract for SZ3B_DEVICE buffers.  The library works on its own non-blocking streams and returns when its work
+ * is complete (results are valid on return).  What the caller queued BEFORE the call on a stream of its own must be
+ * ordered explicitly: sz3b_set_caller_stream(stream, 1) (per host thread) makes every following call wait on an event
+ * recorded on that stream before it touches a device buffer; sz3b_set_caller_stream(NULL, 0) restores the default,
+ * which synchronises the legacy default stream (enough for callers that never create streams).  Work queued on other
+ * non-blocking streams must be synchronised by the caller. */
+void sz3b_set_caller_stream(void *cuda_stream, int enable);
+/* Devices one sz3b_compress call with conf.openmp > 0 spreads its slabs over (slab t on device t mod n, one host thread
+ * per device inside the call; api/impl/SZImplOMP.hpp:16-117 gives every slab to an OpenMP thread instead).
+ * 0 = every visible device; default: every visible device, or 1 when a one-process-per-GPU launcher is detected
+ * (LOCAL_WORLD_SIZE > 1), where each rank keeps to the device it selected. */
+void sz3b_set_device_fanout(int n);
+int sz3b_get_device_fanout(void);
 /* How host threads wait for the device: 0 = the driver's wait (spins; lowest latency when cores are plentiful),
  * 1 = poll and yield the core between polls (for hosts with more waiting threads than cores).  No reference
  * counterpart (the reference has no device); initial value from the environment variable SZ3B_HOST_WAIT. */

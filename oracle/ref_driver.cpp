@@ -15,6 +15,9 @@
 //   ref_abs_eb                                           -> calAbsErrorBound
 #include <cstdint>
 #include <cstdio>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cstring>
 #include <vector>
 
@@ -204,6 +207,24 @@ static int tune_t(ref_config *c, const void *data) {
 extern "C" {
 
 const char *ref_version() { return SZ3_VER; }
+
+// OpenMP team size of the following ref_compress / ref_decompress calls with conf.openmp (SZ_compress_OMP takes
+// omp_get_num_threads() as its slab count, SZImplOMP.hpp:26-31).  Launchers such as torchrun export OMP_NUM_THREADS=1;
+// the benchmark's reference arm and the container parity tests set the count they mean explicitly.
+void ref_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int ref_get_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 unsigned ref_zstd_version() { return ZSTD_versionNumber(); }
 

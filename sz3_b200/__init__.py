@@ -84,6 +84,9 @@ class szConfig:
         self.setDims(*(dims or (1,)))
 
     def setDims(self, *dims):
+        # pysz accepts both setDims(a, b, c) and setDims((a, b, c)) (tools/pysz/src/pysz/sz.pyx)
+        if len(dims) == 1 and isinstance(dims[0], (tuple, list)):
+            dims = tuple(dims[0])
         keep = {k: getattr(self._c, k) for k, _ in _Config._fields_} if self._c.quantbinCnt else None
         arr = (C.c_size_t * len(dims))(*[int(d) for d in dims])
         fresh = _Config()
@@ -141,6 +144,9 @@ def _buffer_of(data):
             if code is None:
                 raise TypeError(f"Unsupported dtype: {data.dtype}. Supported on the GPU path: float32, float64")
             if data.is_cuda:
+                # the library reads the buffer on its own streams: order it after what torch has queued on the current
+                # stream (a .contiguous() copy above included) -- include/sz3b.h, stream contract
+                lib().sz3b_set_caller_stream(C.c_void_p(torch.cuda.current_stream(data.device).cuda_stream), 1)
                 return data.data_ptr(), 1, code, tuple(data.shape), data
             data = data.numpy()
     except ImportError:
@@ -205,6 +211,7 @@ class sz:
         else:
             import torch
             out = torch.empty(shape, dtype=torch.float32 if code == 0 else torch.float64, device=device)
+            lib().sz3b_set_caller_stream(C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream), 1)
             ptr, loc = out.data_ptr(), 1
         _check(L.sz3b_decompress(code, compressed.ctypes.data_as(C.c_char_p), C.c_size_t(compressed.size),
                                  C.c_void_p(ptr), loc, C.byref(conf)))
@@ -241,6 +248,11 @@ class sz:
     @staticmethod
     def get_host_threads():
         return int(lib().sz3b_get_host_threads())
+
+    @staticmethod
+    def set_device_fanout(n):
+        """GPUs one compress call with config.openmp > 0 spreads its slabs over (0 = all visible; include/sz3b.h)."""
+        lib().sz3b_set_device_fanout(int(n))
 
     @staticmethod
     def set_host_wait(mode):

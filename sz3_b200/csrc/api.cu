@@ -20,6 +20,23 @@ namespace {
 thread_local std::string t_last_error;
 thread_local std::vector<StageRecord> t_profile;
 thread_local size_t t_h2d = 0, t_d2h = 0;
+thread_local cudaStream_t t_caller_stream = nullptr;
+thread_local bool t_caller_stream_set = false;
+
+// Device buffers handed in by the caller are read (or written) on the library's own non-blocking streams: order them
+// after what the caller has queued.  With sz3b_set_caller_stream the library streams wait on an event recorded on that
+// stream; without it the legacy default stream is synchronised (which covers callers that never create streams).
+void after_caller(Workspace &ws, int loc) {
+    if (loc != SZ3B_DEVICE) return;
+    if (t_caller_stream_set) {
+        cudaEvent_t e = ws.event();
+        SZ3B_CUDA(cudaEventRecord(e, t_caller_stream));
+        SZ3B_CUDA(cudaStreamWaitEvent(ws.st, e, 0));
+        SZ3B_CUDA(cudaStreamWaitEvent(ws.st_copy, e, 0));
+    } else {
+        SZ3B_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    }
+}
 
 template <class F>
 int guarded(F &&f) {
@@ -97,6 +114,12 @@ int sz3b_device_count(void) {
 void sz3b_set_host_threads(int n) { set_host_threads(n); }
 int sz3b_get_host_threads(void) { return host_threads(); }
 void sz3b_set_host_wait(int mode) { host_wait_mode().store(mode != 0); }
+void sz3b_set_caller_stream(void *cuda_stream, int enable) {
+    t_caller_stream = static_cast<cudaStream_t>(cuda_stream);
+    t_caller_stream_set = enable != 0;
+}
+void sz3b_set_device_fanout(int n) { set_device_fanout(n); }
+int sz3b_get_device_fanout(void) { return device_fanout(); }
 void sz3b_set_lossless_policy(int policy) { set_lossless_policy(policy); }
 int sz3b_get_lossless_policy(void) { return lossless_policy(); }
 
@@ -151,6 +174,7 @@ int sz3b_compress(int dtype, const sz3b_config *c, const void *data, int data_lo
         const size_t conf_est = config_save(conf, blob);
         const size_t cap = cmp_cap - 16 - conf_est * 2;
         WorkspaceLease ws;
+        after_caller(*ws, data_loc);
         uint64_t payload = 0;
         try {
             payload = dtype == SZ3B_FLOAT
@@ -200,6 +224,7 @@ int sz3b_decompress(int dtype, const char *cmp, size_t cmp_size, void *out, int 
         const uint8_t *p = reinterpret_cast<const uint8_t *>(cmp) + 8;
         const uint64_t payload = get<uint64_t>(p);
         WorkspaceLease ws;
+        after_caller(*ws, out_loc);
         try {
             if (dtype == SZ3B_FLOAT)
                 decompress_any<float>(*ws, conf, p, payload, static_cast<float *>(out), out_loc);
@@ -219,6 +244,7 @@ int sz3b_abs_error_bound(int dtype, const sz3b_config *c, const void *data, int 
         check_dtype(dtype);
         check_conf(c);
         WorkspaceLease ws;
+        after_caller(*ws, data_loc);
         *abs_eb = dtype == SZ3B_FLOAT ? abs_eb_stage<float>(*ws, *c, static_cast<const float *>(data), data_loc)
                                       : abs_eb_stage<double>(*ws, *c, static_cast<const double *>(data), data_loc);
     });
@@ -230,6 +256,7 @@ int sz3b_interp_decompose(int dtype, const sz3b_config *c, double abs_eb, const 
         check_dtype(dtype);
         check_conf(c);
         WorkspaceLease ws;
+        after_caller(*ws, data_loc);
         std::vector<uint8_t> blob;
         try {
             if (dtype == SZ3B_FLOAT)
@@ -257,6 +284,7 @@ int sz3b_blockwise_decompose(int dtype, const sz3b_config *c, double abs_eb, con
         check_dtype(dtype);
         check_conf(c);
         WorkspaceLease ws;
+        after_caller(*ws, data_loc);
         std::vector<uint8_t> blob;
         try {
             if (dtype == SZ3B_FLOAT)
@@ -282,6 +310,7 @@ int sz3b_huffman_encode(const int32_t *q, size_t n, int q_loc, unsigned char *ou
                         size_t *tree_len) {
     return guarded([&] {
         WorkspaceLease ws;
+        after_caller(*ws, q_loc);
         std::vector<uint8_t> buf;
         huffman_encode_stage(*ws, q, n, q_loc, buf, tree_len);
         finish_profile(*ws);
@@ -303,6 +332,7 @@ int sz3b_lossless_compress(const unsigned char *src, size_t src_len, int src_loc
                            size_t *out_len) {
     return guarded([&] {
         WorkspaceLease ws;
+        after_caller(*ws, src_loc);
         const size_t n = lossless_gpu_stage(*ws, src, src_len, src_loc, out, out_cap);
         finish_profile(*ws);
         if (out_len) *out_len = n;
@@ -314,6 +344,7 @@ int sz3b_tune(int dtype, sz3b_config *c, const void *data, int data_loc) {
         check_dtype(dtype);
         check_conf(c);
         WorkspaceLease ws;
+        after_caller(*ws, data_loc);
         try {
             if (dtype == SZ3B_FLOAT)
                 tune_stage<float>(*ws, *c, static_cast<const float *>(data), data_loc);
@@ -331,6 +362,7 @@ int sz3b_minmax(int dtype, const void *data, int data_loc, size_t num, double *m
     return guarded([&] {
         check_dtype(dtype);
         WorkspaceLease ws;
+        after_caller(*ws, data_loc);
         if (dtype == SZ3B_FLOAT)
             minmax_stage<float>(*ws, static_cast<const float *>(data), data_loc, num, min_out, max_out);
         else
@@ -354,8 +386,10 @@ int sz3b_compress_slab(int dtype, const sz3b_config *c, int rank, int nslabs, co
         uint64_t d[4];
         for (int i = 0; i < c->N; i++) d[i] = c->dims[i];
         d[0] = hi - lo;
-        if (c->errorBoundMode != SZ3B_EB_ABS && c->errorBoundMode != SZ3B_EB_L2NORM && !(range > 0))
-            fail(SZ3B_E_INVALID_ARGUMENT, "non-ABS error bound needs the global value range");
+        // range == 0 is a legitimate value (a constant field): the reference resolves the bound to 0 and stores the slab
+        // losslessly (SZImplOMP.hpp:57-68, Statistic.hpp:32-51); only a missing range (negative / NaN) is an error
+        if (c->errorBoundMode != SZ3B_EB_ABS && c->errorBoundMode != SZ3B_EB_L2NORM && !(range >= 0))
+            fail(SZ3B_E_INVALID_ARGUMENT, "non-ABS error bound needs the global value range (max - min >= 0)");
         if (sc.errorBoundMode == SZ3B_EB_L2NORM) {
             // resolved against the WHOLE array's element count, as the shared conf is in the reference (:61-65)
             sc.absErrorBound = sqrt(3.0 / config_num(*c)) * sc.l2normErrorBound;
@@ -363,6 +397,7 @@ int sz3b_compress_slab(int dtype, const sz3b_config *c, int rank, int nslabs, co
         }
         config_set_dims(sc, c->N, d);
         WorkspaceLease ws;
+        after_caller(*ws, data_loc);
         size_t sz = 0;
         try {
             sz = dtype == SZ3B_FLOAT
@@ -412,9 +447,18 @@ int sz3b_omp_assemble(int dtype, const sz3b_config *c, int nslabs, const unsigne
             p += payload_sizes[i];
         }
         put<uint64_t>(size_pos, static_cast<uint64_t>(p - body));
-        // outer Config: the caller's, marked openmp, error bound mode already resolved by the caller if needed
+        // outer Config: the caller's, marked openmp.  In the reference calAbsErrorBound rewrites the shared conf before
+        // the slabs copy it (SZImplOMP.hpp:57-72), so the trailing blob carries mode ABS and the resolved bound: take
+        // both from slab 0's blob (every slab holds the same pair).
         sz3b_config oc = *c;
         oc.openmp = 1;
+        if (oc.errorBoundMode != SZ3B_EB_ABS && nslabs > 0) {
+            sz3b_config s0;
+            if (config_load(s0, conf_blobs[0], conf_blob_sizes[0])) {
+                oc.errorBoundMode = s0.errorBoundMode;
+                oc.absErrorBound = s0.absErrorBound;
+            }
+        }
         p += config_save(oc, p);
         *cmp_size = static_cast<size_t>(p - reinterpret_cast<uint8_t *>(cmp));
     });

@@ -284,13 +284,10 @@ bool interp_launch_box(const BoxArgs &A, const BoxSrc &S, const uint32_t sdims[3
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return false;
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    static bool attr_set[64] = {false};
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (first_on_device(attr_set)) {
         cudaFuncSetAttribute(k_interp_box<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxSmem));
         cudaFuncSetAttribute(k_interp_box<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxSmem));
-        attr_set[dev] = true;
     }
     const dim3 grid(static_cast<unsigned>(ntiles));
     if (A.sh.cubic)

@@ -191,36 +191,31 @@ void interp_launch_anchors(const InterpArgs<T, QT> &A, uint32_t anchor_stride, u
 
 template <class T, class QT>
 void interp_launch_tiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<unsigned long long> attr_set{0};
     const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
-    if (!attr_set) {
+    if (first_on_device(attr_set))
         cudaFuncSetAttribute(k_interp_tile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr_set = true;
-    }
     dim3 grid(static_cast<unsigned>(ntiles), nbatch);
     k_interp_tile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
 }
 
 template <class T, class QT>
 void interp_launch_ftiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<unsigned long long> attr_set{0};
     const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
-    if (!attr_set) {
+    if (first_on_device(attr_set))
         cudaFuncSetAttribute(k_interp_ftile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr_set = true;
-    }
     dim3 grid(static_cast<unsigned>(ntiles), nbatch);
     k_interp_ftile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
 }
 
 template <class T, class QT>
 void interp_launch_ltiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
-    static bool attr_set = false;
+    static std::atomic<unsigned long long> attr_set{0};
     const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
-    if (!attr_set) {
+    if (first_on_device(attr_set)) {
         cudaFuncSetAttribute(k_interp_ltile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         cudaFuncSetAttribute(k_interp_ltile_wide<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr_set = true;
     }
     dim3 grid(static_cast<unsigned>(ntiles), nbatch);
     if (ntiles * nbatch <= 148 && sizeof(T) == 4)

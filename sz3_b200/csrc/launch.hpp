@@ -3,9 +3,22 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "core.cuh"
 
 namespace sz3b {
+
+// Function attributes (dynamic shared memory beyond 48 KB) are per device: true the first time a given call site runs
+// on the current device.  `mask` is a static of the call site (bit d = done on device d).
+inline bool first_on_device(std::atomic<unsigned long long> &mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask.load(std::memory_order_acquire) & bit) return false;
+    mask.fetch_or(bit, std::memory_order_release);
+    return true;
+}
 
 template <class T, class QT>
 struct InterpArgs;

@@ -207,12 +207,14 @@ void minmax_stage(Workspace &ws, const T *data, int loc, size_t num, double *mn,
     *mx = static_cast<double>(hmm[1]);
 }
 
-// calAbsErrorBound (Statistic.hpp:24-56); `range` > 0 skips the scan (OMP path).  d_data is device resident.
+// calAbsErrorBound (Statistic.hpp:24-56); with `have_range` the scan is skipped (OMP path: the slabs' min / max were
+// reduced by the caller; a range of 0 -- a constant field -- is a legitimate value and leads to the lossless path
+// exactly as in the reference).  d_data is device resident.
 template <class T>
-static void resolve_abs_eb(Workspace &ws, sz3b_config &conf, const T *d_data, T range) {
+static void resolve_abs_eb(Workspace &ws, sz3b_config &conf, const T *d_data, T range, bool have_range = false) {
     if (conf.errorBoundMode == SZ3B_EB_ABS) return;
     auto get_range = [&]() -> T {
-        if (range > 0) return range;
+        if (have_range) return range;
         double mn, mx;
         minmax_stage<T>(ws, d_data, SZ3B_DEVICE, config_num(conf), &mn, &mx);
         return static_cast<T>(static_cast<T>(mx) - static_cast<T>(mn));   // T subtraction as data_range()
@@ -1577,14 +1579,14 @@ static size_t lossless_compress(Workspace &ws, const sz3b_config &conf, const T 
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T>
 static size_t dispatch_compress(Workspace &ws, sz3b_config &conf, const T *data, int loc, uint8_t *dst, size_t cap,
-                                T range) {
+                                T range, bool have_range = false, bool strict_cap = false) {
     const uint64_t num = config_num(conf);
     const T *d_data = nullptr;
     auto dev = [&]() {
         if (!d_data) d_data = to_device(ws, data, loc, num);
         return d_data;
     };
-    if (conf.errorBoundMode != SZ3B_EB_ABS) resolve_abs_eb<T>(ws, conf, range > 0 ? nullptr : dev(), range);
+    if (conf.errorBoundMode != SZ3B_EB_ABS) resolve_abs_eb<T>(ws, conf, have_range ? nullptr : dev(), range, have_range);
     size_t cmp_size = 0;
     if (conf.absErrorBound == 0) conf.cmprAlgo = SZ3B_ALGO_LOSSLESS;
     bool cap_ok = true;
@@ -1619,6 +1621,7 @@ static size_t dispatch_compress(Workspace &ws, sz3b_config &conf, const T *data,
                 fail(SZ3B_E_INVALID_ARGUMENT, "Unknown compression algorithm");
             }
         } catch (TooSmall &) {
+            if (strict_cap) throw;   // the caller offered less than the reference's capacity and retries with all of it
             cap_ok = false;
         }
     }
@@ -1642,41 +1645,168 @@ static size_t dispatch_compress(Workspace &ws, sz3b_config &conf, const T *data,
 template <class T>
 size_t compress_slab(Workspace &ws, sz3b_config &slab_conf, const T *slab, int loc, double range, uint8_t *payload,
                      size_t cap) {
-    return dispatch_compress<T>(ws, slab_conf, slab, loc, payload, cap, static_cast<T>(range));
+    return dispatch_compress<T>(ws, slab_conf, slab, loc, payload, cap, static_cast<T>(range), range >= 0);
 }
 
-// SZ_compress_OMP (SZImplOMP.hpp:16-117) executed on ONE device: the slabs are independent streams, compressed one
-// after the other; the container is what the reference's SZ_decompress_OMP expects.  (Across GPUs the ranks call
-// sz3b_compress_slab themselves and rank 0 assembles, see api.cpp.)
+// ---------------------------------------------------------------------------------------------------------------------
+// SZ_compress_OMP (SZImplOMP.hpp:16-117): the array is cut into conf.openmp slabs along its outermost dimension, every
+// slab is an independent stream, the container is what the reference's SZ_decompress_OMP expects.
+//
+// The reference gives every slab to one OpenMP thread; here every visible GPU takes slabs (slab t on device t mod G),
+// each driven by its own host thread with its own workspace and streams, all inside this one call: a drop-in caller
+// that sets conf.openmp gets the whole box without launching ranks.  Nothing is exchanged between the devices but the
+// slabs' min / max (non-ABS bounds, :57-68) and their byte counts (:93-105), both through host memory; the payloads are
+// written into the caller's buffer at their final offsets by the host worker pool.
+// ---------------------------------------------------------------------------------------------------------------------
+static std::atomic<int> g_device_fanout{-1};   // -1: default (all visible devices; 1 under a multi-process launcher)
+void set_device_fanout(int n) { g_device_fanout.store(n < 0 ? -1 : n); }
+int device_fanout() {
+    int n = g_device_fanout.load();
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess) {
+        cudaGetLastError();
+        visible = 1;
+    }
+    if (n < 0) {
+        // one process per GPU (torchrun and friends export LOCAL_WORLD_SIZE): every rank keeps to its own device
+        const char *lws = getenv("LOCAL_WORLD_SIZE");
+        n = (lws && atoi(lws) > 1) ? 1 : visible;
+    }
+    if (n == 0 || n > visible) n = visible;
+    return std::max(1, n);
+}
+
+struct CopyPartsJob {
+    uint8_t *dst;
+    const std::vector<const uint8_t *> *src;
+    const std::vector<size_t> *size, *start;
+};
+static void copy_parts_fn(void *arg, int worker) {
+    CopyPartsJob &j = *static_cast<CopyPartsJob *>(arg);
+    memcpy(j.dst + (*j.start)[worker], (*j.src)[worker], (*j.size)[worker]);
+}
+
 template <class T>
 static size_t omp_compress(Workspace &ws, sz3b_config &conf, const T *data, int loc, uint8_t *dst, size_t cap) {
     int nslabs = conf.openmp;
     if (static_cast<uint64_t>(nslabs) > conf.dims[0]) nslabs = static_cast<int>(conf.dims[0]);
     const uint64_t num = config_num(conf);
     const uint64_t row = num / conf.dims[0];
-    const T *d_all = to_device(ws, data, loc, num);
-    if (conf.errorBoundMode != SZ3B_EB_ABS) {
-        // per-thread minmax + reduction (:57-68) == global range
-        resolve_abs_eb<T>(ws, conf, d_all, static_cast<T>(0));
+    const int ndev = std::min(device_fanout(), nslabs);
+    // the devices of this call: the current one first
+    int visible = 1;
+    cudaGetDeviceCount(&visible);
+    std::vector<int> devs(ndev);
+    for (int g = 0; g < ndev; g++) devs[g] = (ws.device + g) % std::max(1, visible);
+    int data_dev = ws.device;
+    if (loc == SZ3B_DEVICE) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, data) == cudaSuccess && at.type == cudaMemoryTypeDevice) data_dev = at.device;
+        cudaGetLastError();
     }
-    std::vector<std::vector<uint8_t>> parts(nslabs);
-    std::vector<size_t> sizes(nslabs);
+    std::vector<int> lo(nslabs), hi(nslabs);
     std::vector<sz3b_config> confs(nslabs, conf);
     for (int t = 0; t < nslabs; t++) {
-        int lo = static_cast<int>(static_cast<uint64_t>(t) * conf.dims[0] / nslabs);
-        int hi = static_cast<int>(static_cast<uint64_t>(t + 1) * conf.dims[0] / nslabs);
+        lo[t] = static_cast<int>(static_cast<uint64_t>(t) * conf.dims[0] / nslabs);
+        hi[t] = static_cast<int>(static_cast<uint64_t>(t + 1) * conf.dims[0] / nslabs);
+    }
+    // other devices read a device-resident input on their own streams: what the caller queued must be complete
+    if (ndev > 1 && loc == SZ3B_DEVICE) SZ3B_CUDA(stream_wait(ws.st));
+    std::vector<std::exception_ptr> errs(ndev);
+    // runs fn(g, workspace of device g) on one host thread per device (the calling thread drives the first one)
+    auto on_devices = [&](auto &&fn) {
+        auto body = [&](int g) {
+            try {
+                if (g == 0) {
+                    fn(g, ws);
+                } else {
+                    SZ3B_CUDA(cudaSetDevice(devs[g]));
+                    WorkspaceLease w;
+                    fn(g, *w);
+                }
+            } catch (...) {
+                errs[g] = std::current_exception();
+            }
+        };
+        std::vector<std::thread> th;
+        for (int g = 1; g < ndev; g++) th.emplace_back(body, g);
+        body(0);
+        for (auto &t : th) t.join();
+        for (int g = 0; g < ndev; g++)
+            if (errs[g]) std::rethrow_exception(errs[g]);
+    };
+    // slab t as device g sees it: the caller's host pointer, the device pointer itself, or a peer copy of it
+    auto slab_on = [&](int g, Workspace &w, int t, int *sloc) -> const T * {
+        const T *p = data + static_cast<uint64_t>(lo[t]) * row;
+        *sloc = loc;
+        if (loc == SZ3B_DEVICE && devs[g] != data_dev) {
+            const uint64_t n_t = static_cast<uint64_t>(hi[t] - lo[t]) * row;
+            T *d = w.data.as<T>(n_t);
+            SZ3B_CUDA(cudaMemcpyPeerAsync(d, devs[g], p, data_dev, n_t * sizeof(T), w.st));
+            return d;
+        }
+        return p;
+    };
+    // ---- the shared bound (SZImplOMP.hpp:57-68): min / max per slab, reduced, then calAbsErrorBound ------------------
+    const bool need_range = conf.errorBoundMode == SZ3B_EB_REL || conf.errorBoundMode == SZ3B_EB_PSNR ||
+                            conf.errorBoundMode == SZ3B_EB_ABS_AND_REL || conf.errorBoundMode == SZ3B_EB_ABS_OR_REL;
+    if (need_range) {
+        std::vector<double> mn(nslabs), mx(nslabs);
+        on_devices([&](int g, Workspace &w) {
+            for (int t = g; t < nslabs; t += ndev) {
+                int sloc;
+                const T *p = slab_on(g, w, t, &sloc);
+                minmax_stage<T>(w, p, sloc, static_cast<uint64_t>(hi[t] - lo[t]) * row, &mn[t], &mx[t]);
+            }
+        });
+        const T range = static_cast<T>(static_cast<T>(*std::max_element(mx.begin(), mx.end())) -
+                                       static_cast<T>(*std::min_element(mn.begin(), mn.end())));
+        resolve_abs_eb<T>(ws, conf, nullptr, range, true);
+    } else if (conf.errorBoundMode != SZ3B_EB_ABS) {
+        resolve_abs_eb<T>(ws, conf, nullptr, static_cast<T>(0), true);   // L2NORM: no scan
+    }
+    for (int t = 0; t < nslabs; t++) {
+        confs[t] = conf;
         uint64_t d[4];
         for (int i = 0; i < conf.N; i++) d[i] = conf.dims[i];
-        d[0] = hi - lo;
-        int keep_block = confs[t].blockSize;
-        (void)keep_block;
+        d[0] = hi[t] - lo[t];
         config_set_dims(confs[t], conf.N, d);
-        const uint64_t n_t = config_num(confs[t]);
-        size_t pcap = ZSTD_compressBound(n_t * sizeof(T));
-        parts[t].resize(pcap);
-        sizes[t] = dispatch_compress<T>(ws, confs[t], d_all + static_cast<uint64_t>(lo) * row, SZ3B_DEVICE,
-                                        parts[t].data(), pcap, static_cast<T>(0));
     }
+    // ---- the slabs ---------------------------------------------------------------------------------------------------
+    // A slab is first offered a third of its size (in a buffer the workspace keeps); only a slab that does not fit --
+    // nearly incompressible data -- is run again with the reference's full capacity ZSTD_compressBound(slab bytes).
+    std::vector<const uint8_t *> part(nslabs);
+    std::vector<size_t> sizes(nslabs), start(nslabs + 1);
+    std::vector<std::vector<uint8_t>> big(nslabs);
+    std::vector<std::vector<uint8_t>> own(nslabs);
+    on_devices([&](int g, Workspace &w) {
+        int k = 0;
+        for (int t = g; t < nslabs; t += ndev, k++) {
+            int sloc;
+            const T *p = slab_on(g, w, t, &sloc);
+            const uint64_t bytes = config_num(confs[t]) * sizeof(T);
+            const size_t full = ZSTD_compressBound(bytes);
+            const size_t small = std::min<size_t>(full, std::max<size_t>(bytes / 3, static_cast<size_t>(1) << 20));
+            uint8_t *out;
+            if (k == 0) {
+                out = static_cast<uint8_t *>(w.slab_out.ensure(small));
+            } else {   // further slabs of the same device: the first one's buffer is still waiting for the assembly
+                own[t].resize(small);
+                out = own[t].data();
+            }
+            const sz3b_config before = confs[t];
+            try {
+                sizes[t] = dispatch_compress<T>(w, confs[t], p, sloc, out, small, static_cast<T>(0), true, small < full);
+            } catch (TooSmall &) {
+                confs[t] = before;
+                big[t].resize(full);
+                out = big[t].data();
+                sizes[t] = dispatch_compress<T>(w, confs[t], p, sloc, out, full, static_cast<T>(0), true, false);
+            }
+            part[t] = out;
+        }
+    });
+    // ---- the container (:93-107) ---------------------------------------------------------------------------------------
     uint8_t *p = dst;
     size_t need = 4;
     uint8_t blob[256];
@@ -1685,11 +1815,14 @@ static size_t omp_compress(Workspace &ws, sz3b_config &conf, const T *data, int 
     put<int32_t>(p, nslabs);
     for (int t = 0; t < nslabs; t++) p += config_save(confs[t], p);
     for (int t = 0; t < nslabs; t++) put<uint64_t>(p, sizes[t]);
-    for (int t = 0; t < nslabs; t++) {
-        memcpy(p, parts[t].data(), sizes[t]);
-        p += sizes[t];
-    }
-    return static_cast<size_t>(p - dst);
+    start[0] = 0;
+    for (int t = 0; t < nslabs; t++) start[t + 1] = start[t] + sizes[t];
+    CopyPartsJob job{p, &part, &sizes, &start};
+    if (nslabs == 1)
+        copy_parts_fn(&job, 0);
+    else
+        host_parallel(nslabs, copy_parts_fn, &job);
+    return static_cast<size_t>(p - dst) + start[nslabs];
 }
 
 template <class T>

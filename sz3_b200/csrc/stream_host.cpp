@@ -90,38 +90,60 @@ size_t config_save(const sz3b_config &c, uint8_t *out) {
     return static_cast<size_t>(p - out);
 }
 
+// The blob comes from an untrusted stream (sz3b_peek_config, sz3b_decompress, the slab Configs of an OpenMP container):
+// every read is checked against min(confSize, len); a bit width beyond 64 or a zero dimension is rejected.
 bool config_load(sz3b_config &c, const uint8_t *in, size_t len) {
     if (len < 4) return false;
-    const uint8_t *p = in;
-    const uint8_t conf_size = get<uint8_t>(p);
-    const uint8_t *end = p + conf_size;   // the reference computes c1 after reading the size byte
-    if (conf_size + 1u > len + 1u && conf_size > len) return false;
+    const uint8_t conf_size = in[0];   // counts itself (Config::save stores the distance to the start of the blob)
+    if (conf_size < 4 || conf_size > len) return false;
+    const uint8_t *p = in + 1;
+    const uint8_t *const end = in + conf_size;
+    auto room = [&](size_t n) { return static_cast<size_t>(end - p) >= n; };
+    if (!room(2)) return false;
     c.N = get<char>(p);
     if (c.N < 1 || c.N > 4) return false;
     const uint8_t bw = get<uint8_t>(p);
+    if (bw < 1 || bw > 64) return false;
     const size_t nbits = static_cast<size_t>(bw) * c.N;
+    if (!room((nbits + 7) / 8)) return false;
     for (int i = 0; i < 4; i++) c.dims[i] = 0;
     size_t bit = 0;
     for (int i = 0; i < c.N; i++)
         for (int j = 0; j < bw; j++, bit++)
             c.dims[i] |= static_cast<uint64_t>((p[bit >> 3] >> (bit & 7)) & 1u) << j;
+    for (int i = 0; i < c.N; i++)
+        if (c.dims[i] == 0) return false;
     p += (nbits + 7) / 8;
+    if (!room(8 + 1 + 1)) return false;
     (void)get<uint64_t>(p);  // num
     c.cmprAlgo = get<uint8_t>(p);
     c.errorBoundMode = get<uint8_t>(p);
     switch (c.errorBoundMode) {
-        case SZ3B_EB_ABS: c.absErrorBound = get<double>(p); break;
-        case SZ3B_EB_REL: c.relErrorBound = get<double>(p); break;
-        case SZ3B_EB_PSNR: c.psnrErrorBound = get<double>(p); break;
-        case SZ3B_EB_L2NORM: c.l2normErrorBound = get<double>(p); break;
+        case SZ3B_EB_ABS:
+            if (!room(8)) return false;
+            c.absErrorBound = get<double>(p);
+            break;
+        case SZ3B_EB_REL:
+            if (!room(8)) return false;
+            c.relErrorBound = get<double>(p);
+            break;
+        case SZ3B_EB_PSNR:
+            if (!room(8)) return false;
+            c.psnrErrorBound = get<double>(p);
+            break;
+        case SZ3B_EB_L2NORM:
+            if (!room(8)) return false;
+            c.l2normErrorBound = get<double>(p);
+            break;
         case SZ3B_EB_ABS_OR_REL:
         case SZ3B_EB_ABS_AND_REL:
+            if (!room(16)) return false;
             c.absErrorBound = get<double>(p);
             c.relErrorBound = get<double>(p);
             break;
         default: break;
     }
-    if (p < end) {
+    if (room(1)) {
         uint8_t b = get<uint8_t>(p);
         c.lorenzo = (b >> 7) & 1;
         c.lorenzo2 = (b >> 6) & 1;
@@ -129,10 +151,10 @@ bool config_load(sz3b_config &c, const uint8_t *in, size_t len) {
         c.regression2 = (b >> 4) & 1;
         c.openmp = (b >> 3) & 1;
     }
-    if (p < end) c.dataType = get<uint8_t>(p);
-    if (p < end) c.quantbinCnt = get<int32_t>(p);
-    if (p < end) c.blockSize = get<int32_t>(p);
-    if (p < end) c.predDim = get<uint8_t>(p);
+    if (room(1)) c.dataType = get<uint8_t>(p);
+    if (room(4)) c.quantbinCnt = get<int32_t>(p);
+    if (room(4)) c.blockSize = get<int32_t>(p);
+    if (room(1)) c.predDim = get<uint8_t>(p);
     return true;
 }
 

@@ -132,7 +132,7 @@ struct Workspace {
     // Huffman decode
     DevBuf hd_bits, hd_tab, hd_over, hd_counts, hd_offs;
     // pinned staging
-    PinBuf stage, stage2, hist_host;
+    PinBuf stage, stage2, hist_host, slab_out;   // slab_out: payload of this device's slab of an OpenMP container
     std::vector<uint8_t> zscratch;   // per-chunk zstd frames before concatenation (host tail)
     std::vector<uint8_t> trial_out;  // compressed output of a tuner trial run on this workspace
     // profiling

@@ -92,9 +92,10 @@ def compress_sharded(slab, config, global_dims, group=None, dst=0, slab_compress
     buf = torch.zeros(width, dtype=torch.uint8)
     buf[:len(payload) + len(blob)] = torch.frombuffer(bytearray(payload + blob), dtype=torch.uint8)
     buf = buf.to(dev)
+    # `dst` is a rank of `group`; torch.distributed.gather wants the global rank
     gathered = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
     if world > 1:
-        dist.gather(buf, gathered, dst=dst, group=group)
+        dist.gather(buf, gathered, dst=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
     else:
         gathered = [buf]
     if rank != dst:

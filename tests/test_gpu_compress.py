@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from common import (field_g1, ALGO_INTERP, ALGO_INTERP_LORENZO, ALGO_LORENZO_REG, ALGO_LOSSLESS, EB_ABS, EB_PSNR, EB_REL, Config, dtype_code, field_g3,
+from common import (EB_ABS_AND_REL, EB_ABS_OR_REL, EB_L2NORM, field_g1, ALGO_INTERP, ALGO_INTERP_LORENZO, ALGO_LORENZO_REG, ALGO_LOSSLESS, EB_ABS, EB_PSNR, EB_REL, Config, dtype_code, field_g3,
                     field_g4, field_nd, make_config, product_lib, ref_lib)
 
 pytestmark = pytest.mark.gpu
@@ -76,6 +76,32 @@ def test_error_bound_modes(mode, val):
 
 
 @needs_ref
+@pytest.mark.parametrize("mode,kw", [
+    (EB_L2NORM, dict(l2normErrorBound=2.0)),
+    (EB_ABS_AND_REL, dict(absErrorBound=1e-3, relErrorBound=1e-3)),    # rel * range ~ 3.5e-3: the absolute bound wins
+    (EB_ABS_AND_REL, dict(absErrorBound=1e-2, relErrorBound=1e-4)),    # the relative bound wins
+    (EB_ABS_OR_REL, dict(absErrorBound=1e-3, relErrorBound=1e-3)),     # the relative bound wins
+    (EB_ABS_OR_REL, dict(absErrorBound=1e-2, relErrorBound=1e-4)),     # the absolute bound wins
+])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_error_bound_modes_l2_and_or(mode, kw, dtype):
+    """calAbsErrorBound (Statistic.hpp:32-56) for the modes that combine or derive bounds: the stream (whose trailing
+    Config carries the resolved absolute bound) must be the reference's byte for byte."""
+    data = field_g3((96, 96, 96), dtype)
+    conf = make_config(data.shape, cmprAlgo=ALGO_INTERP_LORENZO, errorBoundMode=mode, **kw)
+    ours, used = gpu_compress(data, conf)
+    theirs = ref_compress(data, conf)
+    assert ours.size == theirs.size and np.array_equal(ours, theirs)
+    dec, dconf = ref_decompress(ours, data)
+    assert dconf.errorBoundMode == EB_ABS and dconf.absErrorBound == used.absErrorBound
+    if mode == EB_L2NORM:
+        err = dec.astype(np.float64) - data.astype(np.float64)
+        assert np.sqrt((err ** 2).sum()) <= kw["l2normErrorBound"]
+    else:
+        assert np.max(np.abs(dec.astype(np.float64) - data.astype(np.float64))) <= dconf.absErrorBound
+
+
+@needs_ref
 def test_noise_falls_back_to_lossless():
     rng = np.random.default_rng(3)
     data = rng.standard_normal((64, 64, 64)).astype(np.float32)
@@ -118,6 +144,140 @@ def test_omp_container_decodes_with_reference():
     ours, used = gpu_compress(data, conf)
     dec, dconf = ref_decompress(ours, data)
     assert np.max(np.abs(dec - data)) <= 1e-3
+
+
+def _set_ref_threads(n):
+    R = ref_lib()
+    R.ref_set_threads(int(n))
+
+
+@needs_ref
+@pytest.mark.parametrize("shape,dtype,nslabs,kw", [
+    ((100, 64, 64), np.float32, 4, dict(absErrorBound=1e-3)),
+    ((128, 96, 96), np.float32, 2, dict(errorBoundMode=EB_REL, relErrorBound=1e-4)),
+    ((64, 72, 80), np.float64, 8, dict(errorBoundMode=EB_PSNR, psnrErrorBound=80.0)),
+    ((37, 50, 60), np.float32, 3, dict(absErrorBound=1e-2)),                       # uneven slabs
+    ((16, 40, 40, 24), np.float32, 2, dict(errorBoundMode=EB_REL, relErrorBound=1e-3)),
+])
+def test_omp_container_identical_to_reference(shape, dtype, nslabs, kw):
+    """conf.openmp = n on the GPU side against the reference's SZ_compress_OMP run with n OpenMP threads
+    (SZImplOMP.hpp:43-108): same slab bounds, same shared bound, same per-slab Configs -- the whole container byte for
+    byte, trailing outer Config included."""
+    data = field_nd(shape, dtype) if len(shape) == 4 else field_g3(shape, dtype)
+    conf = make_config(shape, cmprAlgo=ALGO_INTERP_LORENZO, openmp=nslabs, **kw)
+    ours, used = gpu_compress(data, conf)
+    _set_ref_threads(nslabs)
+    try:
+        rconf = make_config(shape, cmprAlgo=ALGO_INTERP_LORENZO, openmp=1, **kw)
+        theirs = ref_compress(data, rconf)
+    finally:
+        _set_ref_threads(len(__import__("os").sched_getaffinity(0)))
+    assert ours.size == theirs.size and np.array_equal(ours, theirs), (ours.size, theirs.size)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.max(np.abs(dec.astype(np.float64) - data.astype(np.float64))) <= dconf.absErrorBound
+
+
+@needs_ref
+def test_omp_container_constant_field_is_lossless():
+    """A constant array under a relative bound: range 0 -> absErrorBound 0 -> every slab stored losslessly, as the
+    reference does (no error about a missing range)."""
+    data = np.full((40, 30, 30), 2.5, dtype=np.float32)
+    conf = make_config(data.shape, cmprAlgo=ALGO_INTERP_LORENZO, openmp=4, errorBoundMode=EB_REL, relErrorBound=1e-3)
+    ours, used = gpu_compress(data, conf)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.array_equal(dec, data)
+    L = product_lib()
+    # the slab entry point with range 0 (what sharded callers pass after their all-reduce)
+    blob, blen, size = (C.c_ubyte * 256)(), C.c_size_t(0), C.c_size_t(0)
+    out = np.empty(data.nbytes + 4096, np.uint8)
+    rc = L.sz3b_compress_slab(0, C.byref(conf), 0, 4, data[:10].ctypes.data_as(C.c_void_p), 0, C.c_double(0.0),
+                              out.ctypes.data_as(C.c_char_p), C.c_size_t(out.size), C.byref(size), blob, C.byref(blen))
+    assert rc == 0, L.sz3b_last_error()
+    rc = L.sz3b_compress_slab(0, C.byref(conf), 0, 4, data[:10].ctypes.data_as(C.c_void_p), 0, C.c_double(-1.0),
+                              out.ctypes.data_as(C.c_char_p), C.c_size_t(out.size), C.byref(size), blob, C.byref(blen))
+    assert rc == -1
+
+
+@needs_ref
+@pytest.mark.parametrize("policy", [0, 2])
+def test_g3_512_headline_stream(policy):
+    """The headline array (512^3 G3, abs 1e-3) through sz3b_compress with both lossless policies: the unmodified
+    reference decodes it within the bound, the tuner picks what the reference picks, and the ratio is within 1 % of
+    the reference's serial stream (equal to it for policy 0 up to the multi-frame zstd framing)."""
+    L = product_lib()
+    data = field_g3((512, 512, 512))
+    conf = make_config(data.shape, absErrorBound=1e-3)
+    theirs = ref_compress(data, conf)
+    L.sz3b_set_lossless_policy(policy)
+    try:
+        ours, used = gpu_compress(data, conf)
+    finally:
+        L.sz3b_set_lossless_policy(2)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.max(np.abs(dec - data)) <= 1e-3
+    _, rconf = ref_decompress(theirs, data)
+    assert (used.cmprAlgo, used.interpAlgo, used.interpDirection) == (ALGO_INTERP, 1, 0)
+    assert dconf.cmprAlgo == rconf.cmprAlgo
+    r_ours, r_ref = data.nbytes / ours.size, data.nbytes / theirs.size
+    assert abs(r_ours - r_ref) / r_ref < 0.01, (r_ours, r_ref)
+
+
+@needs_ref
+def test_config3_full_size_stream_identical():
+    """BASELINE.json config #3 at its full size: 384^3 float64, regression predictor only, REL 1e-4 -- the compressed
+    file byte for byte (the coefficient chain, the side streams and the data indices all enter it)."""
+    L = product_lib()
+    data = field_g3((384, 384, 384), np.float64)
+    conf = make_config(data.shape, cmprAlgo=ALGO_LORENZO_REG, errorBoundMode=EB_REL, relErrorBound=1e-4, lorenzo=0, lorenzo2=0,
+                       regression=1)
+    theirs = ref_compress(data, conf)
+    L.sz3b_set_lossless_policy(0)
+    try:
+        ours, used = gpu_compress(data, conf)
+    finally:
+        L.sz3b_set_lossless_policy(2)
+    dec, dconf = ref_decompress(ours, data)
+    assert np.max(np.abs(dec - data)) <= dconf.absErrorBound
+    dec_ref, _ = ref_decompress(theirs, data)
+    assert np.array_equal(dec, dec_ref)                      # same indices, same coefficients -> same reconstruction
+    r_ours, r_ref = data.nbytes / ours.size, data.nbytes / theirs.size
+    assert abs(r_ours - r_ref) / r_ref < 0.001, (r_ours, r_ref)
+    if ours.size == theirs.size:                              # single-frame zstd: the file itself is identical
+        assert np.array_equal(ours, theirs)
+
+
+def test_multi_gpu_container_in_one_call():
+    """conf.openmp with several visible GPUs: one sz3b_compress call spreads the slabs over the devices (one host thread
+    per device inside the call) and must return the container a single device writes, byte for byte -- for host input,
+    for device-resident input (peer copies), with an absolute and with a range-dependent bound."""
+    import torch
+    L = product_lib()
+    ndev = L.sz3b_device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    data = field_g3((256, 128, 160))
+    for kw in (dict(absErrorBound=1e-3), dict(errorBoundMode=EB_REL, relErrorBound=1e-4)):
+        for nslabs in (ndev, 2 * ndev + 1):
+            conf = make_config(data.shape, cmprAlgo=ALGO_INTERP_LORENZO, openmp=nslabs, **kw)
+            L.sz3b_set_device_fanout(1)
+            one, _ = gpu_compress(data, conf)
+            L.sz3b_set_device_fanout(0)
+            try:
+                many, _ = gpu_compress(data, conf)
+                dev = torch.from_numpy(data).cuda()
+                cap = L.sz3b_compress_bound(0, C.byref(conf))
+                out = np.empty(cap, dtype=np.uint8)
+                size = C.c_size_t(0)
+                rc = L.sz3b_compress(0, C.byref(conf), C.c_void_p(dev.data_ptr()), 1, out.ctypes.data_as(C.c_char_p),
+                                     C.c_size_t(cap), C.byref(size), None)
+                assert rc == 0, L.sz3b_last_error()
+            finally:
+                L.sz3b_set_device_fanout(-1)
+            assert one.size == many.size and np.array_equal(one, many)
+            assert size.value == one.size and np.array_equal(out[:size.value], one)
+    if ref_lib() is not None:
+        dec, dconf = ref_decompress(many, data)
+        assert np.max(np.abs(dec - data)) <= dconf.absErrorBound
 
 
 def test_capacity_check():
