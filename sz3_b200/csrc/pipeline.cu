@@ -1558,8 +1558,10 @@ void blockwise_decompose_stage(Workspace &ws, const sz3b_config &conf, double eb
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T>
 static size_t lossless_compress(Workspace &ws, const sz3b_config &conf, const T *data, int loc, uint8_t *dst,
-                                size_t cap) {
+                                size_t cap, bool strict_cap = false) {
     const size_t bytes = config_num(conf) * sizeof(T);
+    // (strict_cap: the caller offered less than the reference's capacity and retries with all of it)
+    if (strict_cap && cap < ZSTD_compressBound(bytes) + sizeof(uint64_t)) throw TooSmall{};
     const uint8_t *src = reinterpret_cast<const uint8_t *>(data);
     if (loc == SZ3B_DEVICE) {
         uint8_t *h = static_cast<uint8_t *>(ws.stage.ensure(bytes));
@@ -1627,7 +1629,7 @@ static size_t dispatch_compress(Workspace &ws, sz3b_config &conf, const T *data,
     }
     if (conf.cmprAlgo == SZ3B_ALGO_LOSSLESS || !cap_ok) {
         conf.cmprAlgo = SZ3B_ALGO_LOSSLESS;
-        return lossless_compress<T>(ws, conf, data, loc, dst, cap);
+        return lossless_compress<T>(ws, conf, data, loc, dst, cap, strict_cap);
     }
     if (num * sizeof(T) / 1.0 / cmp_size < 3) {
         size_t zcap = ZSTD_compressBound(num * sizeof(T)) + sizeof(uint64_t);
@@ -1785,7 +1787,10 @@ static size_t omp_compress(Workspace &ws, sz3b_config &conf, const T *data, int 
             int sloc;
             const T *p = slab_on(g, w, t, &sloc);
             const uint64_t bytes = config_num(confs[t]) * sizeof(T);
-            const size_t full = ZSTD_compressBound(bytes);
+            // (the reference gives a slab ZSTD_compressBound(bytes), which its own lossless path -- bound + the 8-byte
+            //  length prefix, Lossless_zstd.hpp:29-33 -- cannot use: a lossless slab ends SZ_compress_OMP with an
+            //  uncaught std::length_error.  Eight bytes more and the slab is stored.)
+            const size_t full = ZSTD_compressBound(bytes) + sizeof(uint64_t);
             const size_t small = std::min<size_t>(full, std::max<size_t>(bytes / 3, static_cast<size_t>(1) << 20));
             uint8_t *out;
             if (k == 0) {
