@@ -285,10 +285,10 @@ bool interp_launch_box(const BoxArgs &A, const BoxSrc &S, const uint32_t sdims[3
             return false;
     }
     static std::atomic<unsigned long long> attr_set{0};
-    if (first_on_device(attr_set)) {
+    once_per_device(attr_set, [&] {
         cudaFuncSetAttribute(k_interp_box<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxSmem));
         cudaFuncSetAttribute(k_interp_box<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxSmem));
-    }
+    });
     const dim3 grid(static_cast<unsigned>(ntiles));
     if (A.sh.cubic)
         k_interp_box<true><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A, S);

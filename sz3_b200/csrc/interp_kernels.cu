@@ -193,8 +193,9 @@ template <class T, class QT>
 void interp_launch_tiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
     static std::atomic<unsigned long long> attr_set{0};
     const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
-    if (first_on_device(attr_set))
+    once_per_device(attr_set, [&] {
         cudaFuncSetAttribute(k_interp_tile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    });
     dim3 grid(static_cast<unsigned>(ntiles), nbatch);
     k_interp_tile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
 }
@@ -203,8 +204,9 @@ template <class T, class QT>
 void interp_launch_ftiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
     static std::atomic<unsigned long long> attr_set{0};
     const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
-    if (first_on_device(attr_set))
+    once_per_device(attr_set, [&] {
         cudaFuncSetAttribute(k_interp_ftile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    });
     dim3 grid(static_cast<unsigned>(ntiles), nbatch);
     k_interp_ftile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
 }
@@ -213,10 +215,10 @@ template <class T, class QT>
 void interp_launch_ltiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
     static std::atomic<unsigned long long> attr_set{0};
     const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
-    if (first_on_device(attr_set)) {
+    once_per_device(attr_set, [&] {
         cudaFuncSetAttribute(k_interp_ltile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         cudaFuncSetAttribute(k_interp_ltile_wide<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    }
+    });
     dim3 grid(static_cast<unsigned>(ntiles), nbatch);
     if (ntiles * nbatch <= 148 && sizeof(T) == 4)
         k_interp_ltile_wide<T, QT><<<grid, 1024, smem, st>>>(A);

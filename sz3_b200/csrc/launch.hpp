@@ -9,15 +9,18 @@
 
 namespace sz3b {
 
-// Function attributes (dynamic shared memory beyond 48 KB) are per device: true the first time a given call site runs
-// on the current device.  `mask` is a static of the call site (bit d = done on device d).
-inline bool first_on_device(std::atomic<unsigned long long> &mask) {
+// Function attributes (dynamic shared memory beyond 48 KB) are per device.  `mask` is a static of the call site (bit d =
+// done on device d): once_per_device(mask, fn) runs fn until one run has COMPLETED on the current device -- concurrent
+// first callers (tuner trials on pool threads, the per-device threads of a container call) may all run it, which is
+// harmless; none of them launches before its own run has finished.
+template <class F>
+inline void once_per_device(std::atomic<unsigned long long> &mask, F &&fn) {
     int dev = 0;
     cudaGetDevice(&dev);
     const unsigned long long bit = 1ull << (dev & 63);
-    if (mask.load(std::memory_order_acquire) & bit) return false;
+    if (mask.load(std::memory_order_acquire) & bit) return;
+    fn();
     mask.fetch_or(bit, std::memory_order_release);
-    return true;
 }
 
 template <class T, class QT>

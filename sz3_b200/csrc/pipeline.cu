@@ -390,8 +390,10 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
     BoxPlan bp;
     box_prepare<T, QT>(ws, pl, A, nbatch, bp);
     if (bp.ncompact) (*launches)++;
+    SZ3B_CUDA(cudaGetLastError());
     interp_launch_anchors<T, QT>(A, pl.anchor_stride, pl.n_first, nbatch, ws.st);
     (*launches)++;
+    SZ3B_CUDA(cudaGetLastError());
     for (const LevelPlan &L : pl.levels) {
         A.qp = make_quant(L.eb, radius);
         A.s = L.s;
@@ -406,6 +408,7 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
                 SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.copy_plan.ev_row[b], 0));
                 A.tile0 = static_cast<uint32_t>(b * per_row);
                 if (!(box && launch_box<T, QT>(A, bp, per_row, ws.st))) interp_launch_ltiles<T, QT>(A, per_row, nbatch, ws.st);
+                SZ3B_CUDA(cudaGetLastError());
                 (*launches)++;
             }
             A.tile0 = 0;
@@ -420,6 +423,7 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
                 interp_launch_ftiles<T, QT>(A, L.nblocks, nbatch, ws.st);
             else
                 interp_launch_tiles<T, QT>(A, L.nblocks, nbatch, ws.st);
+            SZ3B_CUDA(cudaGetLastError());
             (*launches)++;
         } else {
             for (int p = 0; p < pl.sh.N; p++) {
