@@ -4,24 +4,30 @@
     python bench.py --gpus N --steps K --warmup W            # the CUDA library (libsz3b200.so) through its C ABI
     python bench.py --impl reference --gpus N ...            # the reference's own OpenMP CPU path (oracle/_ref)
 
-One "step" = one pass of the whole hot path (tuner -> predict+quantize -> histogram/Huffman -> bit pack -> zstd) over
-one 512x512x512 float32 array per GPU.  For N > 1 rank r owns slab r of an (N*512)x512x512 array (outermost-dimension
-slabs, the reference's OpenMP decomposition, api/impl/SZImplOMP.hpp:43-86); the only exchange is an all-gather of the
-per-slab byte counts (weak scaling: work per GPU is fixed).
+One "step" = one pass of the whole hot path (tuner -> predict+quantize -> histogram/Huffman -> bit pack -> lossless
+stage) over one 512x512x512 float32 array per GPU.  For N > 1 the workload is an (N*512)x512x512 array cut into N
+outermost-dimension slabs (the reference's OpenMP decomposition, api/impl/SZImplOMP.hpp:43-108): rank r compresses
+slab r, the ranks all-gather their byte counts, and every rank's frames cross PCIe straight to their final offset in
+ONE shared container (a pinned shared-memory segment; rank 0 writes the header and the trailing Config) -- all inside
+the timed region.  After timing, the unmodified reference decodes that container and every rank checks its slab
+against the bound.  Weak scaling: work per GPU is fixed.
 
-  value     whole-job GB/s with the input already resident in HBM (compressed stream delivered to host memory)
-  e2e       same, input in pinned HOST memory: H2D of the array and D2H of the packed stream inside the timed region
-  roofline  the fused predict+quantize launches (k_interp_*): algorithmic bytes N*(sizeof(T)+4) / their device time
-            (CUDA events recorded by the library on its own stream), against MEASURED_PEAKS.json's HBM copy peak
-  cpu_baseline  oracle/_ref (the unmodified reference, conf.openmp = true) on the box's host cores, same array
-  extras    host_zstd_policy (the same two measurements with the reference's own host zstd call), e2e_two_callers
-            (N = 1: the e2e call issued by two host threads at once), config.host (cores, threads per rank);
-            --diag prints per-rank step times, the host-link rate and an A/B of the host thread settings on stderr
+  value     whole-job GB/s with the input already resident in HBM (compressed stream / container delivered to host)
+  e2e       same, input in pinned HOST memory: H2D of the array and D2H of the stream inside the timed region
+  roofline  the fused predict+quantize launches (compact lattices + anchors + k_interp_box per level): algorithmic
+            bytes N*(sizeof(T)+4) / their device time (CUDA events recorded by the library on its own stream),
+            against MEASURED_PEAKS.json's HBM copy peak
+  cpu_baseline / --impl reference: oracle/_ref (the unmodified reference, conf.openmp = true, OpenMP team = all host
+            cores, set explicitly: launchers export OMP_NUM_THREADS=1) on the same array(s)
+  extras    host_zstd_policy (the same two measurements with the reference's own host zstd call), e2e_two_callers,
+            other_configs (BASELINE.json configs #3 and one slab of #5: time, ratio, parity against the reference),
+            stages_ms (device / host stage times of the last timed `value` step); --diag prints per-rank details
 """
 import argparse
 import ctypes as C
 import json
 import os
+import struct
 import subprocess
 import sys
 import threading
@@ -35,16 +41,25 @@ import numpy as np  # noqa: E402
 
 EDGE = 512
 EB = 1e-3
+METRIC = "compress throughput, 3D f32 512^3 abs-eb 1e-3"
+
+
+def workload_name(edge, world):
+    s = f"3D float32 {edge}x{edge}x{edge} per GPU, ALGO_INTERP_LORENZO abs-eb 1e-3"
+    if world > 1:
+        s += f", {world * edge}x{edge}x{edge} slab-sharded over {world} GPUs (OpenMP container)"
+    return s
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--edge", type=int, default=EDGE, help="cube edge (default 512 = the metric's configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_configs / two-callers / host-zstd extras")
     ap.add_argument("--diag", action="store_true", help="per-rank step times and host-link rate on stderr")
     ap.add_argument("--host-threads", type=int, default=None, help="host threads per rank (default: this rank's share of the cores)")
     ap.add_argument("--host-wait", type=int, default=None, help="0 = spin while waiting for the device, 1 = poll and yield")
@@ -121,12 +136,14 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """dram bytes per predict+quantize step from the committed ncu --set full capture (profiles/traffic.json)."""
+    """dram bytes per predict+quantize step from a committed ncu --set full capture: (bytes, where it came from).
+    A capture of an earlier build, not of this run -- the label says which."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get("predict_quantize_dram_bytes")
+            d = json.load(f)
+            return d.get("predict_quantize_dram_bytes"), d.get("source", "profiles/traffic.json")
     except Exception:
-        return None
+        return None, None
 
 
 def make_conf(edge, **kw):
@@ -148,6 +165,19 @@ def cpu_checker():
     return None, None, None
 
 
+def host_cores():
+    return len(os.sched_getaffinity(0))
+
+
+def set_ref_threads(lib, prefix, n):
+    """OpenMP team of the reference's conf.openmp path, set explicitly (torchrun exports OMP_NUM_THREADS=1).
+    Returns the count in force."""
+    if prefix == "ref" and hasattr(lib, "ref_set_threads"):
+        lib.ref_set_threads(int(n))
+        return int(lib.ref_get_max_threads())
+    return 1
+
+
 class _StdoutToStderr:
     """The reference printf()s a line per OpenMP call; keep stdout for the one JSON line."""
 
@@ -161,26 +191,27 @@ class _StdoutToStderr:
         os.close(self.saved)
 
 
-def cpu_compress_time(lib, prefix, data, edge, reps, openmp=True):
+def cpu_compress_time(lib, prefix, data, conf, reps):
     with _StdoutToStderr():
-        return _cpu_compress_time(lib, prefix, data, edge, reps, openmp)
+        cap = getattr(lib, prefix + "_size_bound")(0 if data.dtype == np.float32 else 1, C.byref(conf))
+        out = np.empty(cap, dtype=np.uint8)
+        times, size = [], 0
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            size = getattr(lib, prefix + "_compress")(0 if data.dtype == np.float32 else 1, C.byref(conf),
+                                                      data.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_char_p), C.c_size_t(cap))
+            times.append(time.perf_counter() - t0)
+            assert size > 0, "reference compression failed"
+        return times, size, out
 
 
-def _cpu_compress_time(lib, prefix, data, edge, reps, openmp=True):
-    conf = make_conf(edge, openmp=1 if openmp else 0)
-    cap = getattr(lib, prefix + "_size_bound")(0, C.byref(conf))
-    out = np.empty(cap, dtype=np.uint8)
-    best, size = None, 0
-    times = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        size = getattr(lib, prefix + "_compress")(0, C.byref(conf), data.ctypes.data_as(C.c_void_p),
-                                                  out.ctypes.data_as(C.c_char_p), C.c_size_t(cap))
-        dt = time.perf_counter() - t0
-        assert size > 0, "reference compression failed"
-        times.append(dt)
-        best = dt if best is None else min(best, dt)
-    return best, times, size
+def cpu_decompress(lib, prefix, cmp_ptr, cmp_size, out_arr):
+    from common import Config
+    conf = Config()
+    with _StdoutToStderr():
+        rc = getattr(lib, prefix + "_decompress")(0 if out_arr.dtype == np.float32 else 1, C.c_char_p(cmp_ptr) if isinstance(cmp_ptr, bytes) else C.c_void_p(cmp_ptr),
+                                                  C.c_size_t(cmp_size), out_arr.ctypes.data_as(C.c_void_p), C.byref(conf))
+    return rc, conf
 
 
 def run_reference(args):
@@ -191,22 +222,26 @@ def run_reference(args):
     if lib is None:
         print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/libsz3ref.so nor oracle/libsz3oracle.so is built"}))
         return
-    cores = os.cpu_count() or 1
-    edge = args.edge
-    data = slab_field(0, edge)
-    _, _, _ = cpu_compress_time(lib, prefix, data, edge, max(args.warmup, 1))
-    _, times, size = cpu_compress_time(lib, prefix, data, edge, args.steps)
+    cores = host_cores()
+    threads = set_ref_threads(lib, prefix, cores)
+    edge, world = args.edge, max(1, args.gpus)
+    # the same array the GPU arm compresses: N slabs of edge^3 stacked along z
+    data = slab_field(0, edge) if world == 1 else np.concatenate([slab_field(r, edge) for r in range(world)], axis=0)
+    from common import ALGO_INTERP_LORENZO, make_config
+    conf = make_config(data.shape, cmprAlgo=ALGO_INTERP_LORENZO, absErrorBound=EB, openmp=1)
+    cpu_compress_time(lib, prefix, data, conf, max(args.warmup, 1) if world == 1 else 1)
+    times, size, _ = cpu_compress_time(lib, prefix, data, conf, args.steps)
     total = sum(times)
     gbs = data.nbytes * args.steps / total / 1e9
-    sample = (f"one {edge}^3 float32 array per step (the N=1 workload), SZ_compress with conf.openmp=true, "
-              f"OMP threads = {cores}; CPU throughput does not grow with --gpus")
+    sample = (f"the whole workload per step: {data.shape[0]}x{edge}x{edge} float32 ({world} slab(s) of the GPU arm), "
+              f"SZ_compress with conf.openmp=true, OpenMP team = {threads} threads on {cores} cores")
     line = {
-        "impl": "reference", "metric": "compress throughput, 3D f32 512^3 abs-eb 1e-3", "value": gbs, "unit": "GB/s",
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "ratio": data.nbytes / size,
-        "config": {"workload": f"3D float32 {edge}x{edge}x{edge} ALGO_INTERP_LORENZO abs-eb 1e-3", "field": "G3 (SURVEY.md 8d), seeded"},
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": workload_name(edge, world), "field": "G3 (SURVEY.md 8d), seeded"},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -216,6 +251,39 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # GPU side
 # ----------------------------------------------------------------------------------------------------------------------
+PLACE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class SharedContainer:
+    """One pinned shared-memory segment that all ranks of the node map: the OpenMP container of a step is assembled in
+    it (SZImplOMP.hpp:93-107: int nThreads | Config x n | size_t x n | payloads, inside the outer framing of sz.hpp)."""
+
+    def __init__(self, torch, dist, rank, world, nbytes, tag):
+        self.path = f"/dev/shm/sz3b_bench_{os.environ.get('MASTER_PORT', '0')}_{tag}"
+        self.rank, self.nbytes = rank, nbytes
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        dist.barrier()
+        self.map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(nbytes,))
+        self.ptr = self.map.ctypes.data
+        rc = torch.cuda.cudart().cudaHostRegister(self.ptr, nbytes, 0)
+        self.registered = int(rc) == 0 if not isinstance(rc, tuple) else int(rc[0]) == 0
+        self.torch = torch
+        dist.barrier()
+
+    def close(self, dist):
+        if self.registered:
+            self.torch.cuda.cudart().cudaHostUnregister(self.ptr)
+        del self.map
+        dist.barrier()
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -233,22 +301,23 @@ def run_ours(args):
     if L is None:
         raise SystemExit("bench.py: sz3_b200/lib/libsz3b200.so missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
     L.sz3b_last_error.restype = C.c_char_p
+    L.sz3b_slab_conf_blob_size.restype = C.c_size_t
     if args.lossless_policy is not None:
         L.sz3b_set_lossless_policy(args.lossless_policy)
     # one rank per GPU on one host: every rank gets its share of the cores (16 pool threads per rank on 2 cores per
     # rank cost half of e2e; tests/gpu_cores.sh).  Waiting threads keep spinning: yielding measured slower.
-    cores = len(os.sched_getaffinity(0))
+    cores = host_cores()
     host_threads = args.host_threads if args.host_threads is not None else (max(2, cores // world) if world > 1 else 0)
     host_wait = args.host_wait if args.host_wait is not None else 0
     L.sz3b_set_host_threads(host_threads)
     L.sz3b_set_host_wait(host_wait)
+    L.sz3b_set_device_fanout(1)   # one process per GPU here; the in-process fan-out is measured by extras
     edge = args.edge
     nbytes = edge ** 3 * 4
     host = slab_field(rank, edge)
     pinned = torch.from_numpy(host).pin_memory()
     dev = pinned.cuda(non_blocking=False)
 
-    # single GPU: SZ_compress.  N GPUs: rank r = slab r of the OpenMP container (SZImplOMP.hpp), sizes all-gathered.
     gconf = make_conf(edge)
     if world > 1:
         gconf.dims[0] = edge * world
@@ -259,20 +328,58 @@ def run_ours(args):
     blob = (C.c_ubyte * 256)()
     blob_len = C.c_size_t(0)
     size = C.c_size_t(0)
-    sizes_dev = torch.zeros(world, dtype=torch.int64, device="cuda") if world > 1 else None
+
+    # ---- N > 1: the shared container ---------------------------------------------------------------------------------
+    shared = None
+    if world > 1:
+        blob_sizes = [int(L.sz3b_slab_conf_blob_size(C.byref(gconf), r, world)) for r in range(world)]
+        header = 16 + 4 + sum(blob_sizes) + 8 * world          # outer header | nThreads | Configs | sizes
+        slab_room = 160 << 20                                   # far above the ~45 MB a slab takes
+        shared = SharedContainer(torch, dist, rank, world, header + world * slab_room + 4096, "c")
+        sizes_dev = torch.zeros(world, dtype=torch.int64, device="cuda")
+        blobs_dev = torch.zeros(world, 256, dtype=torch.uint8, device="cuda")
+        state = {"sizes": None}
+
+        def place(_user, payload_size):
+            # the one exchange of the path (SZImplOMP.hpp:93-99): every slab's byte count -> this slab's offset
+            mine = torch.tensor([payload_size], dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(sizes_dev, mine)
+            s = sizes_dev.cpu().numpy()
+            state["sizes"] = s
+            return shared.ptr + header + int(s[:rank].sum())
+
+        place_c = PLACE_FN(place)
 
     def step(ptr, loc):
         if world == 1:
             rc = L.sz3b_compress(0, C.byref(gconf), C.c_void_p(ptr), loc, out_np.ctypes.data_as(C.c_char_p), C.c_size_t(cap),
                                  C.byref(size), C.byref(used))
-        else:
-            rc = L.sz3b_compress_slab(0, C.byref(gconf), rank, world, C.c_void_p(ptr), loc, C.c_double(0.0),
-                                      out_np.ctypes.data_as(C.c_char_p), C.c_size_t(cap), C.byref(size), blob, C.byref(blob_len))
+            if rc != 0:
+                raise RuntimeError(L.sz3b_last_error().decode())
+            return size.value
+        rc = L.sz3b_compress_slab_placed(0, C.byref(gconf), rank, world, C.c_void_p(ptr), loc, C.c_double(0.0), place_c, None,
+                                         C.byref(size), blob, C.byref(blob_len))
         if rc != 0:
             raise RuntimeError(L.sz3b_last_error().decode())
-        if world > 1:   # the one exchange of the path: per-slab byte counts -> offsets (SZImplOMP.hpp:93-105)
-            mine = torch.tensor([size.value], dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(sizes_dev, mine)
+        # the slab Configs (fixed size, known before the payloads) -> rank 0, which writes the container's header
+        mine = torch.zeros(256, dtype=torch.uint8)
+        mine[:blob_len.value] = torch.frombuffer(bytearray(bytes(blob[:blob_len.value])), dtype=torch.uint8)
+        dist.all_gather_into_tensor(blobs_dev, mine.cuda())
+        if rank == 0:
+            s = state["sizes"]
+            blobs = blobs_dev.cpu().numpy()
+            body = struct.pack("<i", world) + b"".join(bytes(blobs[r, :blob_sizes[r]]) for r in range(world)) + \
+                struct.pack(f"<{world}Q", *[int(v) for v in s])
+            payload = len(body) + int(s.sum())
+            head = struct.pack("<IIQ", 0xF342F310, (3 << 24) | (3 << 16) | (2 << 8), payload) + body
+            shared.map[:len(head)] = np.frombuffer(head, dtype=np.uint8)
+            oc = Config.from_buffer_copy(bytes(gconf))
+            oc.openmp = 1
+            ob = (C.c_ubyte * 256)()
+            n = L.sz3b_config_save(C.byref(oc), ob)
+            end = 16 + payload
+            shared.map[end:end + n] = np.frombuffer(bytes(ob[:n]), dtype=np.uint8)
+            state["total"] = end + n
         return size.value
 
     def profile():
@@ -281,6 +388,9 @@ def run_ours(args):
         launches = (C.c_int * 64)()
         n = L.sz3b_last_profile(names, ms, launches, 64)
         return [(names[i].decode(), ms[i], launches[i]) for i in range(min(n, 64))]
+
+    local_ms = []
+    last_profile = {}
 
     def timed(ptr, loc, steps, collect):
         if world > 1:
@@ -292,7 +402,9 @@ def run_ours(args):
         for _ in range(steps):
             csize = step(ptr, loc)
             if collect:
-                for name, ms, nl in profile():
+                prof = profile()
+                last_profile["stages"] = prof
+                for name, ms, nl in prof:
                     launches += nl
                     if name == "predict_quantize":
                         pq_ms += ms
@@ -308,34 +420,48 @@ def run_ours(args):
             ms_total = float(t.item())
         return ms_total, pq_ms, launches, csize
 
-    local_ms = []
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step(dev.data_ptr(), 1)
-    # untimed settling beyond W: the first calls still grow per-workspace buffers and the SM clock is still ramping
-    # (the first three 512^3 steps run 30-50 % slower than the steady state); wait until two steps in a row agree
-    prev = None
-    for _ in range(40):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        step(dev.data_ptr(), 1)
-        dt = time.perf_counter() - t0
-        settled = prev is not None and abs(dt - prev) < 0.03 * prev
-        if world > 1:   # every rank must leave the loop in the same iteration (step() holds a collective)
-            flag = torch.tensor([1 if settled else 0], dtype=torch.int32, device="cuda")
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            settled = bool(flag.item())
-        if settled:
-            break
-        prev = dt
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_dev, pq_ms, launches, csize = timed(dev.data_ptr(), 1, args.steps, True)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         step(pinned.data_ptr(), 0)
     ms_e2e, _, _, _ = timed(pinned.data_ptr(), 0, args.steps, False)
     h2d, d2h = C.c_size_t(0), C.c_size_t(0)
     L.sz3b_last_transfer(C.byref(h2d), C.byref(d2h))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- N > 1: the reference decodes the container of the last step, every rank checks its slab ---------------------
+    container_check = None
+    if world > 1:
+        dist.barrier()
+        dec = SharedContainer(torch, dist, rank, world, world * nbytes, "d")
+        ok = 1
+        if rank == 0:
+            lib, prefix, kind = cpu_checker()
+            if lib is not None:
+                set_ref_threads(lib, prefix, cores)
+                arr = np.frombuffer(dec.map, dtype=np.float32)
+                rc, dconf = cpu_decompress(lib, prefix, shared.ptr, state["total"], arr)
+                ok = 1 if rc == 0 else 0
+            else:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        worst = -1.0
+        if int(flag.item()) == 1:
+            mine = np.frombuffer(dec.map, dtype=np.float32)[rank * edge ** 3:(rank + 1) * edge ** 3].reshape(edge, edge, edge)
+            worst = float(np.max(np.abs(mine.astype(np.float64) - host.astype(np.float64))))
+        t = torch.tensor([worst], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        container_check = {"decoded_by": "unmodified reference SZ_decompress (oracle/_ref), container of the last e2e step",
+                           "ok": bool(int(flag.item()) == 1 and float(t.item()) <= EB), "max_abs_error": float(t.item()),
+                           "bytes": int(state["total"]) if rank == 0 else None}
+        dec.close(dist)
+
     if args.diag:   # per-rank view: this rank's own step times and its share of the host link with all ranks copying
         if world > 1:
             dist.barrier()
@@ -351,28 +477,15 @@ def run_ours(args):
               + " ".join(f"{n}={m:.2f}" for n, m, _ in profile()), file=sys.stderr, flush=True)
         if world > 1:
             dist.barrier()
-        for th, wt in [(cores, 0), (max(2, cores // world), 0), (2, 0), (cores, 1), (max(2, cores // world), 1)]:
-            L.sz3b_set_host_threads(th)
-            L.sz3b_set_host_wait(wt)
-            for _ in range(3):
-                step(dev.data_ptr(), 1)
-            a, _, _, _ = timed(dev.data_ptr(), 1, args.steps, False)
-            for _ in range(2):
-                step(pinned.data_ptr(), 0)
-            b, _, _, _ = timed(pinned.data_ptr(), 0, args.steps, False)
-            if rank == 0:
-                print(f"[diag] host threads {th}, wait {['spin', 'yield'][wt]}: value path {a / args.steps:.2f} ms/step, "
-                      f"e2e path {b / args.steps:.2f} ms/step (max over ranks)", file=sys.stderr, flush=True)
-        L.sz3b_set_host_threads(host_threads)
-        L.sz3b_set_host_wait(host_wait)
-    clocks = sampler.stop() if rank == 0 else None
+
+    extras = not args.no_extras
     # the same two measurements with the lossless stage on the host (zstd level 3 on every chunk, the reference's own
     # call), reported next to the headline so that the effect of the GPU lossless stage is visible
     policy = L.sz3b_get_lossless_policy()
     host_zstd = None
-    if policy == 2:
+    if policy == 2 and extras and world == 1:
         L.sz3b_set_lossless_policy(0)
-        for _ in range(4):
+        for _ in range(3):
             step(dev.data_ptr(), 1)
         ms_dev0, _, _, csize0 = timed(dev.data_ptr(), 1, args.steps, False)
         for _ in range(2):
@@ -385,7 +498,7 @@ def run_ours(args):
     # the H2D of one array overlaps the encode / lossless / D2H tail of the other (the library is reentrant: every call
     # borrows its own workspace and streams).  Throughput of a caller that has a queue of arrays to compress.
     two_callers = None
-    if world == 1 and args.steps >= 2:
+    if world == 1 and args.steps >= 2 and extras:
         try:
             out2 = torch.empty(cap, dtype=torch.uint8).pin_memory().numpy()
             outs = [out_np, out2]
@@ -421,6 +534,13 @@ def run_ours(args):
         except Exception as ex:   # never let the extra measurement take the bench line down
             two_callers = {"error": str(ex)[:200]}
 
+    other = None
+    if world == 1 and extras:
+        try:
+            other = other_configs(L, torch)
+        except Exception as ex:
+            other = {"error": str(ex)[:300]}
+
     total_csize = csize
     if world > 1:
         t = torch.tensor([csize], dtype=torch.int64, device="cuda")
@@ -435,46 +555,140 @@ def run_ours(args):
         pq_avg_ms = pq_ms / args.steps
         alg_bytes = edge ** 3 * (4 + 4)
         achieved = alg_bytes / (pq_avg_ms * 1e-3) / 1e9 if pq_avg_ms > 0 else 0.0
+        traffic, traffic_src = ncu_traffic()
         line = {
-            "metric": "compress throughput, 3D f32 512^3 abs-eb 1e-3", "value": value, "unit": "GB/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "ratio": total_bytes / total_csize,
-            "config": {"workload": f"3D float32 {edge}x{edge}x{edge} per GPU, ALGO_INTERP_LORENZO abs-eb 1e-3"
-                                   + (f", slab-sharded over {world} GPUs (OpenMP container)" if world > 1 else ""),
+            "config": {"workload": workload_name(edge, world),
                        "field": "G3 (SURVEY.md 8d), seeded", "l2": "input 512 MiB per step > 126 MB L2 (no explicit flush)",
                        "lossless_policy": {0: "host zstd-3 on every chunk", 1: "adaptive host zstd: probes, raw zstd frames where zstd gains < 1 % (include/sz3b.h)",
                                            2: "GPU lossless stage: zstd frames of Huffman-only literal blocks, one table per 128 KiB (sz3_b200/csrc/zhuf.cuh); decodes with the unmodified reference"}[policy],
                        "host": {"cores": cores, "threads_per_rank": host_threads or cores, "device_wait": ["spin", "yield"][host_wait]},
-                       "value_path": "sz3b_compress, device-resident input, stream delivered to host",
-                       "e2e_path": "sz3b_compress, pinned host input (H2D + D2H inside the timed region)"},
-            "e2e": {"value": e2e, "unit": "GB/s", "h2d_bytes_per_step": h2d.value, "d2h_bytes_per_step": d2h.value,
+                       "value_path": ("sz3b_compress, device-resident input, stream delivered to host" if world == 1 else
+                                      "sz3b_compress_slab_placed per rank, device-resident slab; sizes all-gathered, frames delivered "
+                                      "to their offsets in one shared pinned container, header written by rank 0 (all timed)"),
+                       "e2e_path": ("sz3b_compress, pinned host input (H2D + D2H inside the timed region)" if world == 1 else
+                                    "same with pinned host slabs (H2D + D2H + container assembly inside the timed region)")},
+            "e2e": {"value": e2e, "unit": "GB/s", "h2d_bytes_per_step": h2d.value * world, "d2h_bytes_per_step": d2h.value * world,
                     "ms_per_step": ms_e2e / args.steps},
-            "e2e_two_callers": two_callers,
-            "host_zstd_policy": None if host_zstd is None or world > 1 else {
-                "value": total_bytes * args.steps / (host_zstd[0] * 1e-3) / 1e9, "e2e": total_bytes * args.steps / (host_zstd[1] * 1e-3) / 1e9,
-                "unit": "GB/s", "ratio": nbytes / host_zstd[2], "note": "same run with sz3b_set_lossless_policy(0): zstd level 3 on the host"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "predict_quantize (k_interp_anchor + k_interp_ltile x 5 levels)",
+            "roofline": {"bound": "hbm", "kernel": "predict_quantize (k_box_compact + k_interp_anchor + k_interp_box x 5 levels)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(), "algorithmic_bytes": alg_bytes,
-                         "ms_per_step": pq_avg_ms},
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes": alg_bytes, "ms_per_step": pq_avg_ms,
+                         "timing": "CUDA events recorded by the library on its own stream around the launches, timed `value` steps"},
             "clocks": clocks,
-            "stages_ms": {n: round(m, 4) for n, m, _ in _merge(profile())},
+            "stages_ms": {n: round(m, 4) for n, m, _ in _merge(last_profile.get("stages", []))},
         }
+        if two_callers is not None:
+            line["e2e_two_callers"] = two_callers
+        if host_zstd is not None:
+            line["host_zstd_policy"] = {
+                "value": total_bytes * args.steps / (host_zstd[0] * 1e-3) / 1e9, "e2e": total_bytes * args.steps / (host_zstd[1] * 1e-3) / 1e9,
+                "unit": "GB/s", "ratio": nbytes / host_zstd[2], "note": "same run with sz3b_set_lossless_policy(0): zstd level 3 on the host"}
+        if container_check is not None:
+            line["container_check"] = container_check
+        if other is not None:
+            line["other_configs"] = other
         if world == 1 and not args.no_cpu_baseline:
             lib, prefix, kind = cpu_checker()
             if lib is not None:
-                cores = os.cpu_count() or 1
-                best, times, rsize = cpu_compress_time(lib, prefix, host, edge, 3)
-                line["cpu_baseline"] = {"value": nbytes / best / 1e9, "unit": "GB/s", "cores": cores, "kind": kind,
-                                        "sample": f"the full {edge}^3 array, SZ_compress conf.openmp=true ({cores} OMP threads), best of 3",
+                threads = set_ref_threads(lib, prefix, cores)
+                times, rsize, _ = cpu_compress_time(lib, prefix, host, make_conf(edge, openmp=1), 3)
+                line["cpu_baseline"] = {"value": nbytes / min(times) / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
+                                        "sample": f"the full {edge}^3 array, SZ_compress conf.openmp=true (OpenMP team = {threads} threads on {cores} cores), best of 3",
                                         "ratio": nbytes / rsize}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "unavailable", "sample": "no oracle library built"}
         print(json.dumps(line))
     if world > 1:
+        shared.close(dist)
         dist.destroy_process_group()
+
+
+def other_configs(L, torch):
+    """BASELINE.json configs #3 (384^3 float64, regression predictor, REL 1e-4) and one slab of #5 (256x2048x2048 float32,
+    abs 1e-3): device-resident and pinned-host time through sz3b_compress, ratio, the reference's time on the host cores,
+    and parity (the reference decodes our stream within the bound; for #3 additionally the same reconstruction as the
+    reference's own stream, i.e. the same indices and coefficients)."""
+    from common import ALGO_INTERP_LORENZO, ALGO_LORENZO_REG, EB_REL, Config, field_g3, make_config
+    lib, prefix, kind = cpu_checker()
+    cores = host_cores()
+    res = {}
+
+    def run(name, data, conf, alg_bytes_name, reps):
+        code = 0 if data.dtype == np.float32 else 1
+        pinned = torch.from_numpy(data).pin_memory()
+        dev = pinned.cuda()
+        cap = L.sz3b_compress_bound(code, C.byref(conf))
+        out = torch.empty(cap, dtype=torch.uint8).pin_memory().numpy()
+        size = C.c_size_t(0)
+        used = Config()
+
+        def one(ptr, loc):
+            rc = L.sz3b_compress(code, C.byref(conf), C.c_void_p(ptr), loc, out.ctypes.data_as(C.c_char_p), C.c_size_t(cap), C.byref(size),
+                                 C.byref(used))
+            if rc != 0:
+                raise RuntimeError(L.sz3b_last_error().decode())
+
+        def timed(ptr, loc):
+            for _ in range(2):
+                one(ptr, loc)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                one(ptr, loc)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        ms_dev = timed(dev.data_ptr(), 1)
+        names, ms, ln = (C.c_char_p * 64)(), (C.c_double * 64)(), (C.c_int * 64)()
+        k = L.sz3b_last_profile(names, ms, ln, 64)
+        stages = {}
+        for i in range(k):
+            stages[names[i].decode()] = stages.get(names[i].decode(), 0.0) + ms[i]
+        ms_e2e = timed(pinned.data_ptr(), 0)
+        r = {"shape": list(data.shape), "dtype": str(data.dtype), "ms_device_resident": ms_dev, "ms_pinned_host": ms_e2e,
+             "GBps_device_resident": data.nbytes / ms_dev / 1e6, "GBps_pinned_host": data.nbytes / ms_e2e / 1e6,
+             "ratio": data.nbytes / size.value, "stages_ms": {a: round(b, 4) for a, b in stages.items()}}
+        pq = stages.get("predict_quantize")
+        if pq:
+            peak, _ = measured_peak()
+            alg = data.size * (data.itemsize + 4)
+            r["roofline"] = {"kernel": alg_bytes_name, "algorithmic_bytes": alg, "ms": pq, "achieved": alg / pq / 1e6,
+                             "frac": alg / pq / 1e6 / peak, "unit": "GB/s"}
+        if lib is not None:
+            threads = set_ref_threads(lib, prefix, cores)
+            rconf = Config.from_buffer_copy(bytes(conf))
+            rconf.openmp = 1
+            times, rsize, rout = cpu_compress_time(lib, prefix, data, rconf, 2)
+            r["reference"] = {"ms": min(times) * 1e3, "GBps": data.nbytes / min(times) / 1e9, "ratio": data.nbytes / rsize,
+                              "threads": threads, "kind": kind}
+            dec = np.empty_like(data)
+            rc, dconf = cpu_decompress(lib, prefix, out.ctypes.data, size.value, dec)
+            err = float(np.max(np.abs(dec.astype(np.float64) - data.astype(np.float64)))) if rc == 0 else None
+            r["parity"] = {"reference_decodes_ours": rc == 0, "max_abs_error": err, "bound": float(dconf.absErrorBound),
+                           "within_bound": bool(rc == 0 and err <= dconf.absErrorBound)}
+        return r
+
+    d3 = field_g3((384, 384, 384), np.float64)
+    c3 = make_config(d3.shape, cmprAlgo=ALGO_LORENZO_REG, errorBoundMode=EB_REL, relErrorBound=1e-4, lorenzo=0, lorenzo2=0, regression=1)
+    res["config3_384c_f64_regression_rel1e-4"] = run("c3", d3, c3, "regression fit + chain + k_reg_predict", 5)
+    del d3
+    z = np.arange(256, dtype=np.float32)[:, None, None]
+    y = np.arange(2048, dtype=np.float32)[None, :, None]
+    x = np.arange(2048, dtype=np.float32)[None, None, :]
+    tp = np.float32(2 * np.pi)
+    d5 = (np.sin(tp * x / np.float32(64)) * np.cos(tp * y / np.float32(96)) + np.float32(0.5) * np.sin(tp * z / np.float32(128) + np.float32(0.3))
+          + np.float32(0.25) * np.sin(tp * (x + y + z) / np.float32(37)))
+    d5 += np.float32(0.002) * np.random.default_rng(99).standard_normal(d5.shape, dtype=np.float32)
+    c5 = make_config(d5.shape, cmprAlgo=ALGO_INTERP_LORENZO, absErrorBound=EB)
+    res["config5_one_slab_256x2048x2048_f32_abs1e-3"] = run("c5", np.ascontiguousarray(d5), c5, "predict_quantize (box schedule)", 3)
+    return res
 
 
 def _merge(stages):

@@ -32,16 +32,19 @@ inline void raise(int rc) {
     throw std::runtime_error(msg);
 }
 // OpenMP analogue: conf.openmp = true emits the reference's slab container; the slab count plays the role of
-// omp_get_max_threads() (api/impl/SZImplOMP.hpp:29-35) and can be set here (default 1 slab per visible GPU).
+// omp_get_max_threads() (api/impl/SZImplOMP.hpp:29-35) and can be set here.  Default: one slab per GPU the call will
+// use (sz3b_get_device_fanout(): every visible device, driven from inside the one SZ_compress call; a single slab --
+// no loss of ratio -- on a one-GPU machine or under a one-process-per-GPU launcher).
 inline int &omp_slabs() {
     static int n = 0;
     return n;
 }
+inline int omp_slab_count() { return omp_slabs() > 0 ? omp_slabs() : sz3b_get_device_fanout(); }
 }  // namespace b200
 
 template <class T>
 size_t SZ_compress_size_bound(const Config &conf) {
-    const sz3b_config p = conf.to_pod(b200::omp_slabs() > 0 ? b200::omp_slabs() : sz3b_device_count());
+    const sz3b_config p = conf.to_pod(b200::omp_slab_count());
     return sz3b_compress_bound(b200::dtype_of<T>(), &p);
 }
 }  // namespace SZ3
@@ -51,7 +54,7 @@ template <class T>
 size_t SZ_compress_located(const SZ3::Config &config, const T *data, int data_loc, char *cmpData, size_t cmpCap) {
     using namespace SZ3;
     if (config.N > 4) throw std::invalid_argument("Data dimension higher than 4 is not supported.");
-    const sz3b_config p = config.to_pod(b200::omp_slabs() > 0 ? b200::omp_slabs() : sz3b_device_count());
+    const sz3b_config p = config.to_pod(b200::omp_slab_count());
     if (cmpCap < sz3b_compress_bound(b200::dtype_of<T>(), &p)) throw std::invalid_argument(SZ3_ERROR_COMP_BUFFER_NOT_LARGE_ENOUGH);
     size_t cmpSize = 0;
     b200::raise(sz3b_compress(b200::dtype_of<T>(), &p, data, data_loc, cmpData, cmpCap, &cmpSize, nullptr));

@@ -131,6 +131,17 @@ int sz3b_minmax(int dtype, const void *data, int data_loc, size_t num, double *m
 int sz3b_compress_slab(int dtype, const sz3b_config *c, int rank, int nslabs, const void *slab, int data_loc,
                        double range, char *payload, size_t payload_cap, size_t *payload_size,
                        unsigned char *conf_blob, size_t *conf_blob_size);
+/* Same, with the payload delivered where `place(user, size)` says.  The callback runs on the calling thread as soon as
+ * the size of the slab's payload is known -- with the GPU lossless stage the compressed frames are still on the device
+ * then -- and returns the destination (host memory, pinned for full PCIe rate): the place for a rank to exchange sizes
+ * with the other ranks (the all-gather of SZImplOMP.hpp:93-99) and to derive its offset in a shared container, so that
+ * the frames cross PCIe once, to their final position.  The blob's size does not depend on the outcome
+ * (sz3b_slab_conf_blob_size), so the container header can be laid out before any slab is finished. */
+typedef void *(*sz3b_place_fn)(void *user, size_t payload_size);
+int sz3b_compress_slab_placed(int dtype, const sz3b_config *c, int rank, int nslabs, const void *slab, int data_loc,
+                              double range, sz3b_place_fn place, void *user, size_t *payload_size,
+                              unsigned char *conf_blob, size_t *conf_blob_size);
+size_t sz3b_slab_conf_blob_size(const sz3b_config *c, int rank, int nslabs);
 size_t sz3b_omp_header_size(int nslabs, const size_t *conf_blob_sizes);
 int sz3b_omp_assemble(int dtype, const sz3b_config *c, int nslabs, const unsigned char *const *conf_blobs,
                       const size_t *conf_blob_sizes, const size_t *payload_sizes, const char *const *payloads,

@@ -370,32 +370,39 @@ int sz3b_minmax(int dtype, const void *data, int data_loc, size_t num, double *m
     });
 }
 
+namespace {
+// slab bounds and per-slab Config exactly as SZImplOMP.hpp:46-72
+sz3b_config slab_config(const sz3b_config *c, int rank, int nslabs, double range) {
+    if (nslabs < 1 || rank < 0 || rank >= nslabs || static_cast<uint64_t>(nslabs) > c->dims[0])
+        fail(SZ3B_E_INVALID_ARGUMENT, "bad slab index (nslabs must not exceed dims[0])");
+    sz3b_config sc = *c;
+    sc.openmp = 1;
+    int lo = static_cast<int>(static_cast<uint64_t>(rank) * c->dims[0] / nslabs);
+    int hi = static_cast<int>(static_cast<uint64_t>(rank + 1) * c->dims[0] / nslabs);
+    uint64_t d[4];
+    for (int i = 0; i < c->N; i++) d[i] = c->dims[i];
+    d[0] = hi - lo;
+    // range == 0 is a legitimate value (a constant field): the reference resolves the bound to 0 and stores the slab
+    // losslessly (SZImplOMP.hpp:57-68, Statistic.hpp:32-51); only a missing range (negative / NaN) is an error
+    if (c->errorBoundMode != SZ3B_EB_ABS && c->errorBoundMode != SZ3B_EB_L2NORM && !(range >= 0))
+        fail(SZ3B_E_INVALID_ARGUMENT, "non-ABS error bound needs the global value range (max - min >= 0)");
+    if (sc.errorBoundMode == SZ3B_EB_L2NORM) {
+        // resolved against the WHOLE array's element count, as the shared conf is in the reference (:61-65)
+        sc.absErrorBound = sqrt(3.0 / config_num(*c)) * sc.l2normErrorBound;
+        sc.errorBoundMode = SZ3B_EB_ABS;
+    }
+    config_set_dims(sc, c->N, d);
+    return sc;
+}
+}  // namespace
+
 int sz3b_compress_slab(int dtype, const sz3b_config *c, int rank, int nslabs, const void *slab, int data_loc,
                        double range, char *payload, size_t payload_cap, size_t *payload_size,
                        unsigned char *conf_blob, size_t *conf_blob_size) {
     return guarded([&] {
         check_dtype(dtype);
         check_conf(c);
-        if (nslabs < 1 || rank < 0 || rank >= nslabs || static_cast<uint64_t>(nslabs) > c->dims[0])
-            fail(SZ3B_E_INVALID_ARGUMENT, "bad slab index (nslabs must not exceed dims[0])");
-        // slab bounds and per-slab Config exactly as SZImplOMP.hpp:46-72
-        sz3b_config sc = *c;
-        sc.openmp = 1;
-        int lo = static_cast<int>(static_cast<uint64_t>(rank) * c->dims[0] / nslabs);
-        int hi = static_cast<int>(static_cast<uint64_t>(rank + 1) * c->dims[0] / nslabs);
-        uint64_t d[4];
-        for (int i = 0; i < c->N; i++) d[i] = c->dims[i];
-        d[0] = hi - lo;
-        // range == 0 is a legitimate value (a constant field): the reference resolves the bound to 0 and stores the slab
-        // losslessly (SZImplOMP.hpp:57-68, Statistic.hpp:32-51); only a missing range (negative / NaN) is an error
-        if (c->errorBoundMode != SZ3B_EB_ABS && c->errorBoundMode != SZ3B_EB_L2NORM && !(range >= 0))
-            fail(SZ3B_E_INVALID_ARGUMENT, "non-ABS error bound needs the global value range (max - min >= 0)");
-        if (sc.errorBoundMode == SZ3B_EB_L2NORM) {
-            // resolved against the WHOLE array's element count, as the shared conf is in the reference (:61-65)
-            sc.absErrorBound = sqrt(3.0 / config_num(*c)) * sc.l2normErrorBound;
-            sc.errorBoundMode = SZ3B_EB_ABS;
-        }
-        config_set_dims(sc, c->N, d);
+        sz3b_config sc = slab_config(c, rank, nslabs, range);
         WorkspaceLease ws;
         after_caller(*ws, data_loc);
         size_t sz = 0;
@@ -413,6 +420,43 @@ int sz3b_compress_slab(int dtype, const sz3b_config *c, int rank, int nslabs, co
         *payload_size = sz;
         *conf_blob_size = config_save(sc, conf_blob);
     });
+}
+
+int sz3b_compress_slab_placed(int dtype, const sz3b_config *c, int rank, int nslabs, const void *slab, int data_loc,
+                              double range, sz3b_place_fn place, void *user, size_t *payload_size,
+                              unsigned char *conf_blob, size_t *conf_blob_size) {
+    return guarded([&] {
+        check_dtype(dtype);
+        check_conf(c);
+        if (!place) fail(SZ3B_E_INVALID_ARGUMENT, "null placement callback");
+        sz3b_config sc = slab_config(c, rank, nslabs, range);
+        WorkspaceLease ws;
+        after_caller(*ws, data_loc);
+        size_t sz = 0;
+        try {
+            sz = dtype == SZ3B_FLOAT
+                     ? compress_slab_placed<float>(*ws, sc, static_cast<const float *>(slab), data_loc, range, place, user)
+                     : compress_slab_placed<double>(*ws, sc, static_cast<const double *>(slab), data_loc, range, place, user);
+        } catch (...) {
+            finish_profile(*ws);
+            throw;
+        }
+        finish_profile(*ws);
+        *payload_size = sz;
+        *conf_blob_size = config_save(sc, conf_blob);
+    });
+}
+
+size_t sz3b_slab_conf_blob_size(const sz3b_config *c, int rank, int nslabs) {
+    size_t n = 0;
+    guarded([&] {
+        check_conf(c);
+        sz3b_config sc = slab_config(c, rank, nslabs, 1.0);
+        sc.errorBoundMode = SZ3B_EB_ABS;   // what every slab carries once its bound is resolved
+        uint8_t blob[256];
+        n = config_save(sc, blob);
+    });
+    return n;
 }
 
 size_t sz3b_omp_header_size(int nslabs, const size_t *conf_blob_sizes) {

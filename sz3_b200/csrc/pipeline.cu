@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <exception>
 #include <mutex>
 #include <thread>
@@ -644,7 +645,9 @@ static size_t zhuf_run(Workspace &ws, const uint8_t *d_src, size_t len, uint8_t 
     const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
     const uint64_t nframes = (nblocks + kZhufBlocksPerFrame - 1) / kZhufBlocksPerFrame;
-    const int nslices = pinned && nframes >= 16 ? 4 : 1;
+    // a payload that will be placed later (ws.placer) stays on the device until its size is known: one slice
+    Placer *const placer = ws.placer && !ws.placer->used ? ws.placer : nullptr;
+    const int nslices = pinned && nframes >= 16 && !placer ? 4 : 1;
     unsigned long long *h_log = static_cast<unsigned long long *>(ws.hist_host.ensure(64));
     cudaEvent_t ev[4];
     size_t h = ws.stage_begin("lossless_gpu");
@@ -681,6 +684,17 @@ static size_t zhuf_run(Workspace &ws, const uint8_t *d_src, size_t len, uint8_t 
     if (nslices > 1) SZ3B_CUDA(stream_wait(ws.st_copy));
     SZ3B_CUDA(cudaGetLastError());
     if (small) throw TooSmall{};
+    if (placer && done && placer->raw_bytes / static_cast<double>(done + sizeof(uint64_t)) >= 3) {
+        // (a lossy result below ratio 3 may still be replaced by the lossless one, SZDispatcher.hpp:62-74: that one is
+        //  placed by dispatch_compress after the decision)
+        uint8_t *f = placer->place(done + sizeof(uint64_t));
+        placer->used = true;
+        uint8_t *q = f;
+        put<uint64_t>(q, static_cast<uint64_t>(len));
+        deliver_d2h(ws, q, d_out, done);
+        ws.host_stage("d2h_compressed", now_ms() - t0);
+        return done;
+    }
     if (nslices == 1 && done) deliver_d2h(ws, dst, d_out, done);
     ws.host_stage("d2h_compressed", now_ms() - t0);
     return done;
@@ -1584,8 +1598,36 @@ static size_t lossless_compress(Workspace &ws, const sz3b_config &conf, const T 
 // SZ_compress_dispatcher (SZDispatcher.hpp:13-76).  `range` > 0: precomputed value range (OMP slabs).
 // ---------------------------------------------------------------------------------------------------------------------
 template <class T>
+static size_t dispatch_compress_inner(Workspace &ws, sz3b_config &conf, const T *data, int loc, uint8_t *dst, size_t cap,
+                                      T range, bool have_range, bool strict_cap);
+
+// With a placer the payload ends up where placer->place(size) says: straight from the device when the GPU lossless
+// stage wrote it (zhuf_run), by a copy from `dst` otherwise.
+template <class T>
 static size_t dispatch_compress(Workspace &ws, sz3b_config &conf, const T *data, int loc, uint8_t *dst, size_t cap,
-                                T range, bool have_range = false, bool strict_cap = false) {
+                                T range, bool have_range = false, bool strict_cap = false, Placer *placer = nullptr) {
+    if (!placer) return dispatch_compress_inner<T>(ws, conf, data, loc, dst, cap, range, have_range, strict_cap);
+    placer->raw_bytes = config_num(conf) * sizeof(T);
+    ws.placer = placer;
+    size_t size = 0;
+    try {
+        size = dispatch_compress_inner<T>(ws, conf, data, loc, dst, cap, range, have_range, strict_cap);
+    } catch (...) {
+        ws.placer = nullptr;
+        throw;
+    }
+    ws.placer = nullptr;
+    if (!placer->used) {
+        uint8_t *f = placer->place(size);
+        placer->used = true;
+        memcpy(f, dst, size);
+    }
+    return size;
+}
+
+template <class T>
+static size_t dispatch_compress_inner(Workspace &ws, sz3b_config &conf, const T *data, int loc, uint8_t *dst, size_t cap,
+                                      T range, bool have_range, bool strict_cap) {
     const uint64_t num = config_num(conf);
     const T *d_data = nullptr;
     auto dev = [&]() {
@@ -1653,6 +1695,66 @@ size_t compress_slab(Workspace &ws, sz3b_config &slab_conf, const T *slab, int l
                      size_t cap) {
     return dispatch_compress<T>(ws, slab_conf, slab, loc, payload, cap, static_cast<T>(range), range >= 0);
 }
+
+// One slab of a container.  A slab is first offered a third of its size (in a pinned buffer the workspace keeps, or in
+// `own` when that one still holds an earlier slab of the same device); only a slab that does not fit -- nearly
+// incompressible data -- is run again with the capacity the reference gives it.  With a placer the payload goes where
+// placer->place(size) says (see Placer); *out is where it was staged otherwise.
+template <class T>
+static size_t compress_slab_buffered(Workspace &w, sz3b_config &sconf, const T *p, int sloc, T range, bool have_range,
+                                     Placer *placer, std::vector<uint8_t> *own, uint8_t **out) {
+    const uint64_t bytes = config_num(sconf) * sizeof(T);
+    // (the reference gives a slab ZSTD_compressBound(bytes), which its own lossless path -- bound + the 8-byte length
+    //  prefix, Lossless_zstd.hpp:29-33 -- cannot use: a lossless slab ends SZ_compress_OMP with an uncaught
+    //  std::length_error.  Eight bytes more and the slab is stored.)
+    const size_t full = ZSTD_compressBound(bytes) + sizeof(uint64_t);
+    const size_t small = std::min<size_t>(full, std::max<size_t>(bytes / 3, static_cast<size_t>(1) << 20));
+    uint8_t *buf;
+    if (own) {
+        own->resize(small);
+        buf = own->data();
+    } else {
+        buf = static_cast<uint8_t *>(w.slab_out.ensure(small));
+    }
+    const sz3b_config before = sconf;
+    size_t size;
+    try {
+        size = dispatch_compress<T>(w, sconf, p, sloc, buf, small, range, have_range, small < full, placer);
+    } catch (TooSmall &) {
+        sconf = before;
+        w.slab_big.resize(full);
+        buf = w.slab_big.data();
+        size = dispatch_compress<T>(w, sconf, p, sloc, buf, full, range, have_range, false, placer);
+        if (own) {   // keep it alive beyond the next slab of this device
+            own->assign(buf, buf + size);
+            buf = own->data();
+        }
+    }
+    *out = buf;
+    return size;
+}
+
+// sz3b_compress_slab_placed: one rank's slab, the payload delivered where the caller's callback says once its size is
+// known (the callback is where a rank exchanges sizes with the others and derives its offset in the shared container).
+template <class T>
+size_t compress_slab_placed(Workspace &ws, sz3b_config &slab_conf, const T *slab, int loc, double range,
+                            void *(*place)(void *user, size_t size), void *user) {
+    struct FnPlacer : Placer {
+        void *(*fn)(void *, size_t);
+        void *user;
+        uint8_t *place(size_t size) override {
+            uint8_t *p = static_cast<uint8_t *>(fn(user, size));
+            if (!p) fail(SZ3B_E_INVALID_ARGUMENT, "placement callback returned no destination");
+            return p;
+        }
+    } pl;
+    pl.fn = place;
+    pl.user = user;
+    uint8_t *out = nullptr;
+    return compress_slab_buffered<T>(ws, slab_conf, slab, loc, static_cast<T>(range), range >= 0, &pl, nullptr, &out);
+}
+template size_t compress_slab_placed<float>(Workspace &, sz3b_config &, const float *, int, double, void *(*)(void *, size_t), void *);
+template size_t compress_slab_placed<double>(Workspace &, sz3b_config &, const double *, int, double, void *(*)(void *, size_t), void *);
 
 // ---------------------------------------------------------------------------------------------------------------------
 // SZ_compress_OMP (SZImplOMP.hpp:16-117): the array is cut into conf.openmp slabs along its outermost dimension, every
@@ -1779,58 +1881,88 @@ static size_t omp_compress(Workspace &ws, sz3b_config &conf, const T *data, int 
         config_set_dims(confs[t], conf.N, d);
     }
     // ---- the slabs ---------------------------------------------------------------------------------------------------
-    // A slab is first offered a third of its size (in a buffer the workspace keeps); only a slab that does not fit --
-    // nearly incompressible data -- is run again with the reference's full capacity ZSTD_compressBound(slab bytes).
-    std::vector<const uint8_t *> part(nslabs);
+    // header of the container: its size does not depend on what the slabs turn out to be (Config blobs have fixed-width
+    // fields; the slabs' error-bound mode is ABS by now)
+    uint8_t blob[256];
+    size_t header = 4 + static_cast<size_t>(nslabs) * 8;
+    for (int t = 0; t < nslabs; t++) header += config_save(confs[t], blob);
+    if (header > cap) fail(SZ3B_E_RUNTIME, "compressed buffer not large enough for the OpenMP container");
     std::vector<size_t> sizes(nslabs), start(nslabs + 1);
-    std::vector<std::vector<uint8_t>> big(nslabs);
+    // One slab per device: the slabs meet once their sizes are known (frames still on the devices), and every device
+    // then delivers its frames straight to dst + header + offset.  More slabs than devices: staged and copied.
+    const bool direct = nslabs == ndev;
+    struct Meet {
+        std::mutex mu;
+        std::condition_variable cv;
+        int arrived = 0, n = 0;
+        bool failed = false;
+        std::vector<size_t> *sizes, *start;
+        uint8_t *base;
+        size_t room;
+    } meet;
+    meet.n = nslabs;
+    meet.sizes = &sizes;
+    meet.start = &start;
+    meet.base = dst + header;
+    meet.room = cap - header;
+    struct SlabPlacer : Placer {
+        Meet *m;
+        int t;
+        uint8_t *place(size_t size) override {
+            std::unique_lock<std::mutex> lk(m->mu);
+            (*m->sizes)[t] = size;
+            if (++m->arrived == m->n) {
+                (*m->start)[0] = 0;
+                for (int i = 0; i < m->n; i++) (*m->start)[i + 1] = (*m->start)[i] + (*m->sizes)[i];
+                if ((*m->start)[m->n] > m->room) m->failed = true;
+                m->cv.notify_all();
+            } else {
+                m->cv.wait(lk, [&] { return m->arrived >= m->n || m->failed; });
+            }
+            if (m->failed) fail(SZ3B_E_RUNTIME, "compressed buffer not large enough for the OpenMP container");
+            return m->base + (*m->start)[t];
+        }
+    };
+    std::vector<const uint8_t *> part(nslabs, nullptr);
     std::vector<std::vector<uint8_t>> own(nslabs);
     on_devices([&](int g, Workspace &w) {
-        int k = 0;
-        for (int t = g; t < nslabs; t += ndev, k++) {
-            int sloc;
-            const T *p = slab_on(g, w, t, &sloc);
-            const uint64_t bytes = config_num(confs[t]) * sizeof(T);
-            // (the reference gives a slab ZSTD_compressBound(bytes), which its own lossless path -- bound + the 8-byte
-            //  length prefix, Lossless_zstd.hpp:29-33 -- cannot use: a lossless slab ends SZ_compress_OMP with an
-            //  uncaught std::length_error.  Eight bytes more and the slab is stored.)
-            const size_t full = ZSTD_compressBound(bytes) + sizeof(uint64_t);
-            const size_t small = std::min<size_t>(full, std::max<size_t>(bytes / 3, static_cast<size_t>(1) << 20));
-            uint8_t *out;
-            if (k == 0) {
-                out = static_cast<uint8_t *>(w.slab_out.ensure(small));
-            } else {   // further slabs of the same device: the first one's buffer is still waiting for the assembly
-                own[t].resize(small);
-                out = own[t].data();
+        try {
+            int k = 0;
+            for (int t = g; t < nslabs; t += ndev, k++) {
+                int sloc;
+                const T *p = slab_on(g, w, t, &sloc);
+                SlabPlacer sp;
+                sp.m = &meet;
+                sp.t = t;
+                uint8_t *out = nullptr;
+                sizes[t] = compress_slab_buffered<T>(w, confs[t], p, sloc, static_cast<T>(0), true, direct ? &sp : nullptr,
+                                                     k == 0 ? nullptr : &own[t], &out);
+                part[t] = out;
             }
-            const sz3b_config before = confs[t];
-            try {
-                sizes[t] = dispatch_compress<T>(w, confs[t], p, sloc, out, small, static_cast<T>(0), true, small < full);
-            } catch (TooSmall &) {
-                confs[t] = before;
-                big[t].resize(full);
-                out = big[t].data();
-                sizes[t] = dispatch_compress<T>(w, confs[t], p, sloc, out, full, static_cast<T>(0), true, false);
+        } catch (...) {
+            if (direct) {   // release the devices waiting for this slab's size
+                std::lock_guard<std::mutex> lk(meet.mu);
+                meet.failed = true;
+                meet.cv.notify_all();
             }
-            part[t] = out;
+            throw;
         }
     });
     // ---- the container (:93-107) ---------------------------------------------------------------------------------------
     uint8_t *p = dst;
-    size_t need = 4;
-    uint8_t blob[256];
-    for (int t = 0; t < nslabs; t++) need += config_save(confs[t], blob) + 8 + sizes[t];
-    if (need > cap) fail(SZ3B_E_RUNTIME, "compressed buffer not large enough for the OpenMP container");
     put<int32_t>(p, nslabs);
     for (int t = 0; t < nslabs; t++) p += config_save(confs[t], p);
     for (int t = 0; t < nslabs; t++) put<uint64_t>(p, sizes[t]);
-    start[0] = 0;
-    for (int t = 0; t < nslabs; t++) start[t + 1] = start[t] + sizes[t];
-    CopyPartsJob job{p, &part, &sizes, &start};
-    if (nslabs == 1)
-        copy_parts_fn(&job, 0);
-    else
-        host_parallel(nslabs, copy_parts_fn, &job);
+    if (!direct) {
+        start[0] = 0;
+        for (int t = 0; t < nslabs; t++) start[t + 1] = start[t] + sizes[t];
+        if (header + start[nslabs] > cap) fail(SZ3B_E_RUNTIME, "compressed buffer not large enough for the OpenMP container");
+        CopyPartsJob job{p, &part, &sizes, &start};
+        if (nslabs == 1)
+            copy_parts_fn(&job, 0);
+        else
+            host_parallel(nslabs, copy_parts_fn, &job);
+    }
     return static_cast<size_t>(p - dst) + start[nslabs];
 }
 

@@ -44,6 +44,10 @@ template <class T>
 size_t compress_slab(Workspace &ws, sz3b_config &slab_conf, const T *slab, int loc, double range, uint8_t *payload,
                      size_t cap);
 
+template <class T>
+size_t compress_slab_placed(Workspace &ws, sz3b_config &slab_conf, const T *slab, int loc, double range,
+                            void *(*place)(void *user, size_t size), void *user);
+
 // devices one SZ_compress call with conf.openmp spreads its slabs over (pipeline.cu: omp_compress)
 void set_device_fanout(int n);
 int device_fanout();

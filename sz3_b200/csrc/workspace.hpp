@@ -105,6 +105,16 @@ struct PinBuf {
     }
 };
 
+// Where a finished payload goes once its size is known (slabs of an OpenMP container: the offset of a slab is the sum
+// of the sizes before it, so the compressed frames wait on the device until every slab has reported, and then cross
+// PCIe straight to their final place -- no host-side copy of the payloads).  pipeline.cu: zhuf_run, dispatch_compress.
+struct Placer {
+    virtual uint8_t *place(size_t size) = 0;
+    virtual ~Placer() {}
+    bool used = false;
+    uint64_t raw_bytes = 0;   // uncompressed size of the slab (the ratio < 3 rule decides before the payload is placed)
+};
+
 struct StageRecord {
     std::string name;
     double ms = 0;       // device time (CUDA events) or host wall time for host stages
@@ -135,6 +145,8 @@ struct Workspace {
     PinBuf stage, stage2, hist_host, slab_out;   // slab_out: payload of this device's slab of an OpenMP container
     std::vector<uint8_t> zscratch;   // per-chunk zstd frames before concatenation (host tail)
     std::vector<uint8_t> trial_out;  // compressed output of a tuner trial run on this workspace
+    std::vector<uint8_t> slab_big;   // a container slab that needed the full capacity (nearly incompressible data)
+    Placer *placer = nullptr;        // set for the duration of one dispatch_compress call
     // profiling
     std::vector<StageRecord> prof;
     std::vector<cudaEvent_t> ev_pool;

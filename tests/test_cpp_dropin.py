@@ -59,7 +59,25 @@ int main(int argc, char **argv) {
     free_buf(c);
     free_buf(d2);
     if (!(worst <= 1e-3)) return 23;
-    printf("roundtrip ok ratio %.2f\n", data.size() * 4.0 / cmpSize);
+    // conf.openmp: the slab container, one slab per GPU of the box, all driven from this one call
+    SZ3::Config c3(64, 50, 60);
+    c3.absErrorBound = 1e-3;
+    c3.openmp = true;
+    std::vector<float> big(c3.num);
+    for (size_t i = 0; i < big.size(); i++) big[i] = std::sin(0.01f * i) + 0.001f * (i % 7);
+    size_t cmpSize3 = 0;
+    char *cmp3 = SZ_compress<float>(c3, big.data(), cmpSize3);
+    int nslab = 0;
+    memcpy(&nslab, cmp3 + 16, 4);
+    SZ3::Config dc3;
+    float *dec3 = SZ_decompress<float>(dc3, cmp3, cmpSize3);
+    worst = 0;
+    for (size_t i = 0; i < big.size(); i++) worst = std::fmax(worst, std::fabs((double)dec3[i] - big[i]));
+    delete[] dec3;
+    delete[] cmp3;
+    if (!(worst <= 1e-3) || !dc3.openmp) return 24;
+    if (nslab != sz3b_device_count()) return 25;
+    printf("roundtrip ok ratio %.2f, openmp container: %d slabs on %d GPUs\n", data.size() * 4.0 / cmpSize, nslab, sz3b_device_count());
     return 0;
 }
 '''
