@@ -340,12 +340,16 @@ def run_ours(args):
         blobs_dev = torch.zeros(world, 256, dtype=torch.uint8, device="cuda")
         state = {"sizes": None}
 
+        trace = os.environ.get("SZ3B_STEP_TRACE") and rank == 0
+
         def place(_user, payload_size):
             # the one exchange of the path (SZImplOMP.hpp:93-99): every slab's byte count -> this slab's offset
+            t0 = time.perf_counter()
             mine = torch.tensor([payload_size], dtype=torch.int64, device="cuda")
             dist.all_gather_into_tensor(sizes_dev, mine)
             s = sizes_dev.cpu().numpy()
             state["sizes"] = s
+            state["t_place"] = time.perf_counter() - t0
             return shared.ptr + header + int(s[:rank].sum())
 
         place_c = PLACE_FN(place)
@@ -357,10 +361,12 @@ def run_ours(args):
             if rc != 0:
                 raise RuntimeError(L.sz3b_last_error().decode())
             return size.value
+        t0 = time.perf_counter()
         rc = L.sz3b_compress_slab_placed(0, C.byref(gconf), rank, world, C.c_void_p(ptr), loc, C.c_double(0.0), place_c, None,
                                          C.byref(size), blob, C.byref(blob_len))
         if rc != 0:
             raise RuntimeError(L.sz3b_last_error().decode())
+        t1 = time.perf_counter()
         # the slab Configs (fixed size, known before the payloads) -> rank 0, which writes the container's header
         mine = torch.zeros(256, dtype=torch.uint8)
         mine[:blob_len.value] = torch.frombuffer(bytearray(bytes(blob[:blob_len.value])), dtype=torch.uint8)
@@ -380,6 +386,9 @@ def run_ours(args):
             end = 16 + payload
             shared.map[end:end + n] = np.frombuffer(bytes(ob[:n]), dtype=np.uint8)
             state["total"] = end + n
+        if trace:
+            print(f"[trace] loc {loc}: slab call {1e3 * (t1 - t0):.2f} ms (of which size exchange {1e3 * state['t_place']:.2f}), "
+                  f"header {1e3 * (time.perf_counter() - t1):.2f} ms", file=sys.stderr, flush=True)
         return size.value
 
     def profile():

@@ -46,8 +46,11 @@ Workspace *workspace_acquire() {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) throw CudaError{e, "cudaGetDevice (is a CUDA device visible? this library has no CPU path)", __FILE__, __LINE__};
     {
+        // last in, first out: a call releases its own workspace after the ones its tuner trials borrowed, so the next
+        // call gets the workspace whose buffers already have the size of a whole array (the trial workspaces stay
+        // small; handing one of them to a call costs device and pinned allocations of hundreds of megabytes)
         std::lock_guard<std::mutex> lk(g_pool_mu);
-        for (size_t i = 0; i < g_pool.size(); i++) {
+        for (size_t i = g_pool.size(); i-- > 0;) {
             if (g_pool[i]->device == dev) {
                 Workspace *ws = g_pool[i];
                 g_pool.erase(g_pool.begin() + i);
