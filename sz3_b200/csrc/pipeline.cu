@@ -993,46 +993,88 @@ static void tune_interp(Workspace &ws, sz3b_config &conf, const T *d_data) {
         for (int d = 0; d < N; d++) cd[d] = sbs + 1;
         config_set_dims(tc, N, cd);
     }
-    {   // interpolator (SZAlgoInterp.hpp:176-184)
-        std::vector<sz3b_config> tcs(2, tc);
-        tcs[0].interpAlgo = SZ3B_INTERP_LINEAR;
-        tcs[1].interpAlgo = SZ3B_INTERP_CUBIC;
-        const std::vector<double> r = run_trials(tcs);
-        for (int k = 0; k < 2; k++)
-            if (r[k] > best_interp) {
-                best_interp = r[k];
-                conf.interpAlgo = tcs[k].interpAlgo;
-            }
-    }
-    tc.interpAlgo = conf.interpAlgo;
     int fact = 1;
     for (int i = 2; i <= N; i++) fact *= i;
-    // direction (:186-197) and the three (alpha, beta) candidates (:199-224) all compare against the running best,
-    // but an (alpha, beta) trial needs the chosen direction: the direction trial runs first, alone
-    {
-        std::vector<sz3b_config> tcs(1, tc);
-        tcs[0].interpDirection = fact - 1;
+    // The reference tries {linear, cubic}, then the other direction with the winner, then three (alpha, beta) pairs with
+    // the winner of that (SZAlgoInterp.hpp:176-224): six trial compressions in three dependent rounds.  A trial's ratio
+    // depends on its own configuration only, so the candidates the later decisions may ask for are compressed ahead of
+    // time, concurrently, and the reference's decision sequence is then replayed over the table of ratios: the same
+    // decisions, one round of latency (all 16 candidates) where the host has the threads for it, two (4 + 3) otherwise.
+    const double alphas[4] = {1.25, 1.0, 1.5, 2.0}, betas[4] = {2.0, 1.0, 2.5, 3.0};
+    double table[2][2][4];
+    bool have[2][2][4] = {};
+    auto cfg_of = [&](int a, int d, int ab) {
+        sz3b_config c = tc;
+        c.interpAlgo = a ? SZ3B_INTERP_CUBIC : SZ3B_INTERP_LINEAR;
+        c.interpDirection = d ? fact - 1 : 0;
+        c.interpAlpha = alphas[ab];
+        c.interpBeta = betas[ab];
+        return c;
+    };
+    struct Key {
+        int a, d, ab;
+    };
+    auto prefetch = [&](const std::vector<Key> &keys) {
+        std::vector<Key> todo;
+        std::vector<sz3b_config> tcs;
+        for (const Key &k : keys)
+            if (!have[k.a][k.d][k.ab] && !(k.d == 1 && fact == 1)) {
+                todo.push_back(k);
+                tcs.push_back(cfg_of(k.a, k.d, k.ab));
+            }
+        if (tcs.empty()) return;
         const std::vector<double> r = run_trials(tcs);
-        if (r[0] > best_interp * 1.02) {
-            best_interp = r[0];
+        for (size_t i = 0; i < todo.size(); i++) {
+            table[todo[i].a][todo[i].d][todo[i].ab] = r[i];
+            have[todo[i].a][todo[i].d][todo[i].ab] = true;
+        }
+    };
+    auto ratio_of = [&](int a, int d, int ab) {
+        if (fact == 1) d = 0;   // 1-D: the "other" direction is the same permutation
+        if (!have[a][d][ab]) prefetch({Key{a, d, ab}});
+        return table[a][d][ab];
+    };
+    const int threads = std::max(1, host_threads());
+    if (threads >= 12) {
+        std::vector<Key> all;
+        for (int a = 0; a < 2; a++)
+            for (int d = 0; d < 2; d++)
+                for (int ab = 0; ab < 4; ab++) all.push_back(Key{a, d, ab});
+        prefetch(all);
+    } else if (threads >= 4) {
+        prefetch({Key{0, 0, 0}, Key{1, 0, 0}, Key{0, 1, 0}, Key{1, 1, 0}});
+    } else {
+        prefetch({Key{0, 0, 0}, Key{1, 0, 0}});
+    }
+    int A = 1, D = 0;
+    {   // interpolator (:176-184)
+        for (int a = 0; a < 2; a++) {
+            const double r = ratio_of(a, 0, 0);
+            if (r > best_interp) {
+                best_interp = r;
+                A = a;
+            }
+        }
+        conf.interpAlgo = A ? SZ3B_INTERP_CUBIC : SZ3B_INTERP_LINEAR;
+    }
+    {   // direction (:186-197)
+        const double r = ratio_of(A, 1, 0);
+        if (r > best_interp * 1.02) {
+            best_interp = r;
+            D = 1;
             conf.interpDirection = fact - 1;
         }
     }
-    tc.interpDirection = conf.interpDirection;
-    {
-        const double alphas[3] = {1.0, 1.5, 2.0}, betas[3] = {1.0, 2.5, 3.0};
-        std::vector<sz3b_config> tcs(3, tc);
-        for (int i = 0; i < 3; i++) {
-            tcs[i].interpAlpha = alphas[i];
-            tcs[i].interpBeta = betas[i];
-        }
-        const std::vector<double> r = run_trials(tcs);
-        for (int i = 0; i < 3; i++)
-            if (r[i] > best_interp * 1.02) {
-                best_interp = r[i];
+    {   // (alpha, beta) (:199-224)
+        prefetch({Key{A, D, 1}, Key{A, D, 2}, Key{A, D, 3}});
+        for (int i = 1; i < 4; i++) {
+            const double r = ratio_of(A, D, i);
+            if (r > best_interp * 1.02) {
+                best_interp = r;
                 conf.interpAlpha = alphas[i];
                 conf.interpBeta = betas[i];
             }
+        }
     }
     sz3b_config lc = conf_entry;
     if (N == 1 && best_interp < 50) {   // only test lorenzo for 1D (:226-242)
