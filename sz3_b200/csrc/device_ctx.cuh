@@ -120,23 +120,4 @@ struct DevCtx2 {
     }
 };
 
-// Same counting scheme as DevCtx2, split for straight-line hot loops (box schedule, interp_box.cuh: BoxHist):
-// hist_fast counts a symbol of the 8-bin register window and reports the others, hist_rare counts one of those.
-struct DevCtxBox : DevCtx2 {
-    __device__ __forceinline__ DevCtxBox(unsigned *sh, unsigned long long *gh, int radius) : DevCtx2(sh, gh, radius) {}
-    __device__ __forceinline__ bool hist_fast(int sym, bool active) {
-        const unsigned k8 = static_cast<unsigned>(sym - lo8);
-        const bool in = k8 < 8u;
-        if (active && in) packed += 1ull << (k8 * 8u);
-        return active && !in;
-    }
-    __device__ __forceinline__ void hist_rare(int sym) {
-        const unsigned k = static_cast<unsigned>(sym - lo);
-        if (k < static_cast<unsigned>(kHistWindow))
-            atomicAdd(&shist[k], 1u);
-        else
-            atomicAdd(&ghist[sym], 1ull);
-    }
-};
-
 }  // namespace sz3b

@@ -56,6 +56,93 @@ __global__ void __launch_bounds__(256) k_histogram(const QT *__restrict__ q, uin
     }
 }
 
+// Histogram of a stretch of 16-bit quantization indices (the streams the box schedule writes, interp_box.cu: counting
+// inside that kernel cost a quarter of its time -- 14 instructions per point on its dependent path -- while a pass
+// over the indices afterwards is bound by reading them, mostly from L2).  A thread takes eight indices per 16-byte
+// load; the sixteen bins around the radius are counted in two registers of 4-bit fields (a shift and an add per index,
+// an index outside the window shifts its increment out), widened to 8-bit fields once per load, reduced across the
+// warp at the end; everything else (rare) goes to a 2048-bin shared-memory window or to the global histogram.
+constexpr int kHistChunk = 256 * 24 * 8;   // indices per CTA: 24 loads per thread (8-bit fields hold 24 * 8 = 192)
+__device__ __forceinline__ unsigned shl_clamp(unsigned v, unsigned sh) {
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(sh));   // 0 for sh >= 32
+    return r;
+}
+__global__ void __launch_bounds__(256) k_hist_u16(const uint16_t *__restrict__ q, uint64_t n, int radius, int nbins,
+                                                  unsigned long long *__restrict__ ghist) {
+    constexpr int W = 2048;
+    __shared__ unsigned sh[W];
+    for (int i = threadIdx.x; i < W; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int lo = radius - W / 2, lo16 = radius - 8;
+    auto rare = [&](int sym) {
+        const unsigned k = static_cast<unsigned>(sym - lo);
+        if (k < static_cast<unsigned>(W))
+            atomicAdd(&sh[k], 1u);
+        else if (sym >= 0 && sym < nbins)
+            atomicAdd(&ghist[sym], 1ull);
+    };
+    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kHistChunk;
+    const uint64_t end = base + kHistChunk < n ? base + kHistChunk : n;
+    // 16-byte loads need an aligned start: the indices before it (and a ragged tail) go one by one
+    const uint64_t a0 = (reinterpret_cast<uintptr_t>(q + base) & 15u) ? base + (16 - (reinterpret_cast<uintptr_t>(q + base) & 15u)) / 2 : base;
+    const uint64_t astart = a0 < end ? a0 : end;
+    const uint64_t nvec = (end - astart) / 8;
+    for (uint64_t i = base + threadIdx.x; i < astart; i += blockDim.x) rare(q[i]);
+    for (uint64_t i = astart + nvec * 8 + threadIdx.x; i < end; i += blockDim.x) rare(q[i]);
+    unsigned acc[4] = {0, 0, 0, 0};   // 8-bit fields: bins 0,2,4,6 | 1,3,5,7 | 8,10,12,14 | 9,11,13,15 of the window
+    const uint4 *v = reinterpret_cast<const uint4 *>(q + astart);
+    for (uint64_t j = threadIdx.x; j < nvec; j += blockDim.x) {
+        const uint4 w = v[j];
+        const unsigned words[4] = {w.x, w.y, w.z, w.w};
+        unsigned nl = 0, nh = 0, any = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned sym = (k & 1) ? words[k >> 1] >> 16 : words[k >> 1] & 0xffffu;
+            const unsigned k16 = sym - static_cast<unsigned>(lo16);
+            nl += shl_clamp(1u, k16 * 4u);
+            nh += shl_clamp(1u, k16 * 4u - 32u);
+            any |= k16;
+        }
+        acc[0] += nl & 0x0f0f0f0fu;
+        acc[1] += (nl >> 4) & 0x0f0f0f0fu;
+        acc[2] += nh & 0x0f0f0f0fu;
+        acc[3] += (nh >> 4) & 0x0f0f0f0fu;
+        if (any > 15u) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const unsigned sym = (k & 1) ? words[k >> 1] >> 16 : words[k >> 1] & 0xffffu;
+                if (sym - static_cast<unsigned>(lo16) > 15u) rare(static_cast<int>(sym));
+            }
+        }
+    }
+    // warp reduction of the sixteen counters: 8-bit fields widened to 16 bits (a warp's sum is at most 32 * 192)
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const unsigned e = __reduce_add_sync(0xffffffffu, acc[r] & 0x00ff00ffu);          // fields 0 | 2 of this register
+        const unsigned o = __reduce_add_sync(0xffffffffu, (acc[r] >> 8) & 0x00ff00ffu);   // fields 1 | 3
+        if (lane < 4) {
+            const unsigned cnt = (lane & 1u) ? ((lane & 2u) ? o >> 16 : o & 0xffffu) : ((lane & 2u) ? e >> 16 : e & 0xffffu);
+            // field f of register r counts window bin 8 * (r / 2) + 2 * f + (r & 1)
+            const unsigned bin = 8u * (r >> 1) + 2u * lane + (r & 1u);
+            if (cnt) atomicAdd(&sh[lo16 - lo + static_cast<int>(bin)], cnt);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < W; k += blockDim.x) {
+        const unsigned c = sh[k];
+        const int sym = lo + k;
+        if (c && sym >= 0 && sym < nbins) atomicAdd(&ghist[sym], static_cast<unsigned long long>(c));
+    }
+}
+
+void launch_hist_u16(const uint16_t *q, uint64_t n, int radius, int nbins, unsigned long long *ghist, cudaStream_t st) {
+    if (n == 0) return;
+    const uint64_t blocks = (n + kHistChunk - 1) / kHistChunk;
+    k_hist_u16<<<static_cast<unsigned>(blocks), 256, 0, st>>>(q, n, radius, nbins, ghist);
+}
+
 template <class QT>
 __global__ void __launch_bounds__(256) k_minmax_int(const QT *__restrict__ q, uint64_t n, int *__restrict__ mm) {
     int lo = 0x7fffffff, hi = static_cast<int>(0x80000000);

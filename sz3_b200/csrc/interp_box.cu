@@ -19,7 +19,8 @@ namespace {
 
 constexpr int kBoxEEPad = 9568;   // EE floats rounded up to a multiple of 32 (128 B)
 constexpr size_t kBoxSmem = sizeof(float) * (kBoxWarps * kBoxSlotStride + kBoxEEPad) + sizeof(uint16_t) * kBoxWarps * kBoxStageU16 +
-                            sizeof(unsigned) * kHistWindow + sizeof(uint64_t) * kBoxWarps;
+                            sizeof(uint64_t) * kBoxWarps;
+struct BoxNoCtx {};   // the box schedule keeps no per-thread context (its histogram is taken afterwards: k_hist_u16)
 constexpr unsigned kBoxPlaneBytes = kBoxSlotElems * sizeof(float);   // what one TMA box delivers (zero fill included)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -77,8 +78,7 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
     float *const slots = reinterpret_cast<float *>(smem_raw);
     float *const EE = slots + kBoxWarps * kBoxSlotStride;
     uint16_t *const stages = reinterpret_cast<uint16_t *>(EE + kBoxEEPad);
-    unsigned *const shist = reinterpret_cast<unsigned *>(stages + kBoxWarps * kBoxStageU16);
-    uint64_t *const bars = reinterpret_cast<uint64_t *>(shist + kHistWindow);
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(stages + kBoxWarps * kBoxStageU16);
     __shared__ BoxTile T;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
@@ -102,8 +102,7 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
             tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z));
         }
     }
-    DevCtxBox ctx(shist, A.hist, A.qp.radius);
-    for (int i = tid; i < kHistWindow; i += kBoxThreads) shist[i] = 0;
+    BoxNoCtx ctx;
     if (tid == 0) box_tile_setup<CUBIC>(A, tile, o, T);
     // ---- phase A: EE, pass 0 ----------------------------------------------------------------------------------------
     box_fill_column(A, S, o, tid, EE);
@@ -187,8 +186,6 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
         __syncwarp();
         BOX_TICK(8);
     }
-    ctx.pass_end();
-    ctx.flush();
     BOX_TICK(9);
 }
 

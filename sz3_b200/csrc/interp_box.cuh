@@ -206,28 +206,25 @@ SZ_HD bool box_class_rt(uint32_t k, bool n_odd, uint32_t &idx) {
     return in_main;
 }
 
-// Histogram bookkeeping of a run of up to 32 targets handled by one thread: symbols inside the context's register
-// window are counted on the spot (straight-line code, so that the compiler can interleave the arithmetic of
-// neighbouring targets); the rare others are remembered in a bit mask and counted after the run.
-// Index 0 (an unpredictable point) is always one of the rare ones: its original value is stored from the same place,
-// through `zero(k)` -- the caller re-reads the value from the input array, nothing stays in registers for it.
+// Indices of a run of N targets handled by one thread.  The box schedule does not count symbols itself (the histogram
+// of HuffmanEncoder::init is taken by a pass over the index stream afterwards, encode_kernels.cu: k_hist_u16 --
+// counting here cost a quarter of the kernel's time); what it has to notice is index 0, an unpredictable point, whose
+// original value goes to unpred_tmp: the run keeps the minimum of its indices, and only a run that saw a 0 looks for
+// it (`zero(k)`; the caller re-reads the value from the input array, nothing stays in registers for it).
 template <class Ctx, int N>
 struct BoxHist {
     int q[N];
-    uint32_t rare = 0;
-    SZ_HD void add(Ctx &ctx, int k, int qv, bool active) {
+    int qmin = 0x7fffffff;
+    SZ_HD void add(Ctx &, int k, int qv, bool) {
         q[k] = qv;
-        if (ctx.hist_fast(qv, active)) rare |= 1u << k;
+        qmin = qv < qmin ? qv : qmin;
     }
     template <class Zero>
-    SZ_HD void finish(Ctx &ctx, Zero &&zero) {
-        if (rare) {
+    SZ_HD void finish(Ctx &, bool owned, Zero &&zero) {
+        if (qmin == 0 && owned) {
 #pragma unroll
             for (int k = 0; k < N; k++)
-                if ((rare >> k) & 1u) {
-                    ctx.hist_rare(q[k]);
-                    if (q[k] == 0) zero(k);
-                }
+                if (q[k] == 0) zero(k);
         }
     }
 };
@@ -416,7 +413,7 @@ SZ_HD void box_pass0_line(const BoxArgs &A, const BoxSrc &S, Ctx &ctx, const Box
             col[(2 * t + 1) * kBoxEEPlane] = rc[t];
             if (owned) E.qm[box_off8<CUBIC>(E, h, n_odd, t)] = static_cast<uint16_t>(H.q[t]);
         }
-        H.finish(ctx, [&](int t) { E.um[box_off8<CUBIC>(E, h, n_odd, t)] = gcol[static_cast<uint64_t>(16 * h + 2 * t + 1) * gstep]; });
+        H.finish(ctx, owned, [&](int t) { E.um[box_off8<CUBIC>(E, h, n_odd, t)] = gcol[static_cast<uint64_t>(16 * h + 2 * t + 1) * gstep]; });
     }
 }
 
@@ -438,7 +435,6 @@ SZ_HD void box_pass0_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
             uint32_t idx;
             const bool in_main = box_class_rt<CUBIC>(kk, n_odd, idx);
             box_store(E, in_main, idx, qv, orig, owned);
-            if (ctx.hist_fast(qv, owned)) ctx.hist_rare(qv);
         });
 }
 
@@ -502,7 +498,7 @@ SZ_HD void box_pass1_lane(const BoxArgs &A, const BoxSrc &S, Ctx &ctx, const Box
         col[(2 * t + 1) * kBoxPitch] = rc[t];
         if (owned) E.qm[box_off8<CUBIC>(E, h, n_odd, t)] = static_cast<uint16_t>(H.q[t]);
     }
-    H.finish(ctx, [&](int t) {
+    H.finish(ctx, owned, [&](int t) {
         // rare: the original of an unpredictable point, re-read from the input at local (z, 2k + 1, 2x')
         const uint64_t g = T.sbase + z * S.st[0] + (16 * h + 2 * t + 1) * S.st[1] + 2 * xl * S.st[2];
         E.um[box_off8<CUBIC>(E, h, n_odd, t)] = S.p[g];
@@ -527,7 +523,6 @@ SZ_HD void box_pass1_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
             uint32_t idx;
             const bool in_main = box_class_rt<CUBIC>(kk, n_odd, idx);
             box_store(E, in_main, idx, qv, orig, true);
-            if (ctx.hist_fast(qv, true)) ctx.hist_rare(qv);
         });
 }
 
@@ -604,7 +599,7 @@ SZ_HD void box_pass2_row(const BoxArgs &A, const BoxSrc &S, Ctx &ctx, const BoxT
                 if (in_main) sm[t] = qv; else R.qb[idx * R.other] = qv;
             }
         }
-        H.finish(ctx, [&](int t) {
+        H.finish(ctx, true, [&](int t) {
             // rare: the original of an unpredictable point, re-read from the input at local (z, y, 2k + 1)
             const uint32_t k = 8 * h + t;
             const uint64_t g = T.sbase + z * S.st[0] + (ry + T.low[1]) * S.st[1] + (2 * k + 1) * S.st[2];
@@ -635,7 +630,6 @@ SZ_HD void box_pass2_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
             uint32_t idx;
             const bool in_main = box_class_rt<CUBIC>(kk, n_odd, idx);
             box_row_store(R, in_main, idx, qv, orig);
-            if (ctx.hist_fast(qv, true)) ctx.hist_rare(qv);
         });
 }
 

@@ -55,6 +55,8 @@ void interp_launch_compact(const float *src, const uint32_t dims[3], const uint6
 template <class QT>
 void launch_histogram(const QT *q, uint64_t n, int sym_min, int nbins, int center, unsigned long long *ghist,
                       cudaStream_t st);
+// histogram of a stretch of 16-bit indices around `radius` (the streams the box schedule writes)
+void launch_hist_u16(const uint16_t *q, uint64_t n, int radius, int nbins, unsigned long long *ghist, cudaStream_t st);
 template <class QT>
 void launch_minmax_int(const QT *q, uint64_t n, int *mm, cudaStream_t st);
 uint64_t pack_num_chunks(uint64_t n);

@@ -398,6 +398,22 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
     interp_launch_anchors<T, QT>(A, pl.anchor_stride, pl.n_first, nbatch, ws.st);
     (*launches)++;
     SZ3B_CUDA(cudaGetLastError());
+    uint64_t hist_from = 0, hist_to = 0;
+    // (stretches of consecutive levels are counted by one launch: hist_from .. hist_to is what is still owed)
+    auto flush_hist = [&]() {
+        if constexpr (std::is_same<QT, uint16_t>::value) {
+            if (hist_to > hist_from) {
+                launch_hist_u16(d_q + hist_from, hist_to - hist_from, radius, 2 * radius, d_hist, ws.st);
+                (*launches)++;
+            }
+        }
+        hist_from = hist_to = 0;
+    };
+    auto count_box = [&](uint64_t from, uint64_t to) {
+        if (hist_to != from) flush_hist();
+        if (hist_to == hist_from) hist_from = from;
+        hist_to = to;
+    };
     for (const LevelPlan &L : pl.levels) {
         A.qp = make_quant(L.eb, radius);
         A.s = L.s;
@@ -405,13 +421,20 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         A.block_base = d_table + L.table_off;
         const bool box = bp.any && box_applicable<T, QT>(A);
         if (pl.box_required && L.s == 1 && !box) fail(SZ3B_E_UNSUPPORTED, "box schedule does not apply to this shape / type");
+        // the box kernel does not count its indices: a pass over the stretch of the stream it wrote does (k_hist_u16)
+        const uint64_t lv_begin = pl.table[L.table_off];
+        const uint64_t lv_end = (&L == &pl.levels.back()) ? pl.num : pl.table[(&L + 1)->table_off];
         if (planes && L.s == 1) {
             // the finest level, block-row by block-row as the odd planes arrive
             const uint64_t per_row = static_cast<uint64_t>(L.nb[1]) * L.nb[2];
             for (uint32_t b = 0; b < L.nb[0]; b++) {
                 SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ws.copy_plan.ev_row[b], 0));
                 A.tile0 = static_cast<uint32_t>(b * per_row);
-                if (!(box && launch_box<T, QT>(A, bp, per_row, ws.st))) interp_launch_ltiles<T, QT>(A, per_row, nbatch, ws.st);
+                if (box && launch_box<T, QT>(A, bp, per_row, ws.st)) {
+                    count_box(pl.table[L.table_off + b * per_row], b + 1 < L.nb[0] ? pl.table[L.table_off + (b + 1) * per_row] : lv_end);
+                    flush_hist();   // counted while the next planes are still arriving
+                } else
+                    interp_launch_ltiles<T, QT>(A, per_row, nbatch, ws.st);
                 SZ3B_CUDA(cudaGetLastError());
                 (*launches)++;
             }
@@ -421,6 +444,7 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         }
         if (pl.tile) {
             if (box && launch_box<T, QT>(A, bp, L.nblocks, ws.st)) {
+                count_box(lv_begin, lv_end);
             } else if (pl.variant == 2)
                 interp_launch_ltiles<T, QT>(A, L.nblocks, nbatch, ws.st);
             else if (pl.variant == 1)
@@ -442,6 +466,7 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
             }
         }
     }
+    flush_hist();
     SZ3B_CUDA(cudaGetLastError());
 }
 
@@ -1524,8 +1549,10 @@ static void run_blockwise(Workspace &ws, const sz3b_config &conf, double eb, con
     SZ3B_CUDA(cudaGetLastError());
     *launches += 2;
     std::vector<std::pair<unsigned long long, T>> unp;
+    double t_side = now_ms();
     fetch_coef_unpred<T>(ws, hc[1], upos, uval, hc[0] * nc, unp);
     regression_save<T>(ws, N, hc[0], unp, coef_q, eb_indep, eb_liner, pred_blob);
+    ws.host_stage("regression_side_stream_wall", now_ms() - t_side);
     h = ws.stage_begin("predict_quantize");
     SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
     if (const char *e = launch_reg_predict<T, QT>(d_data, bs, c_rec, make_quant(eb, conf.quantbinCnt / 2), d_q,

@@ -35,23 +35,15 @@ struct HostCtx {
 
 // Box schedule (interp_box.cuh): the per-lane phase functions run lane by lane, warp by warp, in the order the
 // kernel's barriers impose; a host copy with zero fill stands in for the TMA box (out-of-bounds elements read 0).
-struct SeqCtx {
-    unsigned long long *hist;
-    int lo8;
-    bool hist_fast(int sym, bool active) {   // same split as DevCtxBox: an 8-bin window, the rest reported back
-        const unsigned k8 = static_cast<unsigned>(sym - lo8);
-        if (active && k8 < 8u) hist[sym]++;
-        return active && k8 >= 8u;
-    }
-    void hist_rare(int sym) { hist[sym]++; }
-};
+struct SeqCtx {};   // the box schedule counts nothing itself (k_hist_u16 runs over its indices afterwards)
 
 template <bool CUBIC>
 static void box_tile_emul(const BoxArgs &A, const BoxSrc &S, const uint32_t sdims[3], uint32_t tile, unsigned long long *hist) {
     static std::vector<float> EE(kBoxEEElems), slots(kBoxWarps * kBoxSlotStride);
     static std::vector<uint16_t> stage(kBoxWarps * kBoxStageU16);
     std::fill(EE.begin(), EE.end(), std::numeric_limits<float>::quiet_NaN());   // unfilled cells must never matter
-    SeqCtx ctx{hist, A.qp.radius - 4};
+    SeqCtx ctx;
+    (void)hist;
     BoxOrigin o;
     box_origin(A, S, tile, o);
     BoxTile T;
@@ -224,6 +216,10 @@ static int run(const sz3b_config &c, double eb, const T *data, int schedule, int
         if (box_level) {
             static BoxEmulPlan bplan;
             box_level_emul(*reinterpret_cast<const BoxArgs *>(&A), bplan, L.nblocks, hist.data());
+            // what k_hist_u16 does on the device: the level's stretch of the index stream, counted afterwards
+            const uint64_t lv_begin = pl.table[L.table_off];
+            const uint64_t lv_end = (&L == &pl.levels.back()) ? pl.num : pl.table[(&L + 1)->table_off];
+            for (uint64_t i = lv_begin; i < lv_end; i++) hist[q[i]]++;
             continue;
         }
         if (pl.tile) {
