@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
     __shared__ BoxTile T;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    const uint32_t tile = blockIdx.x + A.tile0;
+    const uint32_t split = S.split, part = blockIdx.x % split;
+    const uint32_t tile = blockIdx.x / split + A.tile0;
+    const uint32_t zstep = kBoxWarps * split;
     BOX_TICK(0);
     BoxOrigin o;
     box_origin(A, S, tile, o);
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
     uint64_t *const bar = bars + warp;
     const uint32_t nz = o.n[0];
     const bool tma = S.tma != 0, write2 = A.s >= 2;
-    uint32_t z = (o.begin[0] ? 1u : 0u) + warp;   // planes of this warp: z, z + 8, ...
+    uint32_t z = (o.begin[0] ? 1u : 0u) + part * kBoxWarps + warp;   // planes of this warp: z, z + zstep, ...
     const int x0 = static_cast<int>(o.begin[2] / S.odiv), y0 = static_cast<int>(o.begin[1] / S.odiv),
               z0 = static_cast<int>(o.begin[0] / S.odiv);
     if (tma && lane == 0) {
@@ -112,15 +114,15 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
     __syncthreads();
     BOX_TICK(2);
     if (!tma && z < nz) box_gather_plane(S, T, lane, z, slot);   // (needs T: after the barrier)
-    box_pass0_line<CUBIC>(A, S, ctx, T, tid, EE);
-    for (uint32_t e = tid; e < 33u * 16u; e += kBoxThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE);
+    box_pass0_line<CUBIC>(A, S, ctx, T, tid, EE, part == 0);
+    for (uint32_t e = tid; e < 33u * 16u; e += kBoxThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE, part == 0);
     BOX_TICK(3);
     __syncthreads();
     BOX_TICK(4);
     // ---- phase B: the warp's planes -----------------------------------------------------------------------------------
     const uint32_t lowy = T.low[1], c1y = T.c1[1];
     unsigned parity = 0;
-    for (; z < nz; z += kBoxWarps) {
+    for (; z < nz; z += zstep) {
         if (tma) {
             mbar_wait(bar, parity);
             parity ^= 1u;
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
             }
         }
         box_pass2_left<CUBIC>(A, ctx, T, lane, z, slot, stage, write2);
-        const bool more = z + kBoxWarps < nz;
+        const bool more = z + zstep < nz;
         if (!write2) {   // slot free: the next plane comes in under the arithmetic of this one
             __syncwarp();
             if (more) {
@@ -157,18 +159,18 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
                     if (lane == 0) {
                         fence_proxy_async();
                         mbar_expect_tx(bar, kBoxPlaneBytes);
-                        tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z + kBoxWarps));
+                        tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z + zstep));
                     }
                 } else {
-                    box_gather_plane(S, T, lane, z + kBoxWarps, slot);
+                    box_gather_plane(S, T, lane, z + zstep, slot);
                 }
             }
         }
         if (lane < c1y) box_pass2_row<CUBIC>(A, S, ctx, T, lane, z, v, stage, write2 ? my_row : nullptr);
         __syncwarp();
         BOX_TICK(7);
-        box_copy_out(A, T, lane, z, stage);
-        if (write2) {   // the plane's reconstructions feed the next finer level; the slot is re-armed after that
+        if (write2) {   // the plane's reconstructions feed the next finer level; the slot is re-armed right after that,
+                        // so that the next plane travels while the indices of this one leave
             box_plane_out(A, T, lane, z, slot);
             __syncwarp();
             if (more) {
@@ -176,13 +178,14 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
                     if (lane == 0) {
                         fence_proxy_async();
                         mbar_expect_tx(bar, kBoxPlaneBytes);
-                        tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z + kBoxWarps));
+                        tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z + zstep));
                     }
                 } else {
-                    box_gather_plane(S, T, lane, z + kBoxWarps, slot);
+                    box_gather_plane(S, T, lane, z + zstep, slot);
                 }
             }
         }
+        box_copy_out(A, T, lane, z, stage);
         __syncwarp();
         BOX_TICK(8);
     }
@@ -286,7 +289,7 @@ bool interp_launch_box(const BoxArgs &A, const BoxSrc &S, const uint32_t sdims[3
         cudaFuncSetAttribute(k_interp_box<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxSmem));
         cudaFuncSetAttribute(k_interp_box<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxSmem));
     });
-    const dim3 grid(static_cast<unsigned>(ntiles));
+    const dim3 grid(static_cast<unsigned>(ntiles * S.split));
     if (A.sh.cubic)
         k_interp_box<true><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A, S);
     else

@@ -58,6 +58,8 @@ struct BoxSrc {
     uint64_t st[3];    // one lattice step
     uint32_t odiv;
     uint32_t tma;      // planes arrive by TMA box copies (unit x step, 16-byte aligned rows) or by per-element copies
+    uint32_t split;    // CTAs per tile (coarse levels with fewer tiles than SMs): every CTA of a tile runs phase A, the
+                       // first one emits it, and the planes of phase B are dealt out over split * kBoxWarps warps
 };
 
 // Per-tile constants (shared memory; written by one thread while the others fill EE).
@@ -384,13 +386,14 @@ SZ_HD void box_pass0_emit(const BoxArgs &A, const BoxTile &T, uint32_t yl, uint3
 }
 
 template <bool CUBIC, class Ctx>
-SZ_HD void box_pass0_line(const BoxArgs &A, const BoxSrc &S, Ctx &ctx, const BoxTile &T, uint32_t c, float *EE) {
+SZ_HD void box_pass0_line(const BoxArgs &A, const BoxSrc &S, Ctx &ctx, const BoxTile &T, uint32_t c, float *EE, bool emit) {
     const uint32_t yl = c / 17u, xl = c - yl * 17u;
     if (yl >= T.C[1] || xl >= T.C[2]) return;
     const bool n_odd = T.n[0] & 1u;
     BoxEmit E;
     bool owned;
     box_pass0_emit<Ctx>(A, T, yl, xl, E, owned);
+    owned = owned && emit;
     const QuantParams qp = A.qp;
     // where the line's originals sit in the source (rare path: value of an unpredictable point)
     const uint64_t gstep = S.st[0];
@@ -419,7 +422,7 @@ SZ_HD void box_pass0_line(const BoxArgs &A, const BoxSrc &S, Ctx &ctx, const Box
 
 // z-lines 256..288 (the 17th lattice row / column spill-over of the 256-thread mapping): item e = (line, target)
 template <bool CUBIC, class Ctx>
-SZ_HD void box_pass0_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t e, float *EE) {
+SZ_HD void box_pass0_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t e, float *EE, bool emit) {
     const uint32_t c = 256u + (e >> 4), k = e & 15u;
     if (c >= static_cast<uint32_t>(kBoxEEPlane)) return;
     const uint32_t yl = c / 17u, xl = c - yl * 17u;
@@ -428,6 +431,7 @@ SZ_HD void box_pass0_left(const BoxArgs &A, Ctx &ctx, const BoxTile &T, uint32_t
     BoxEmit E;
     bool owned;
     box_pass0_emit<Ctx>(A, T, yl, xl, E, owned);
+    owned = owned && emit;
     float *const col = EE + c;
     box_target_rt<CUBIC>(
         k, n_odd, A.qp, [&](uint32_t l) { return col[l * kBoxEEPlane]; }, [&](uint32_t l, float r) { col[l * kBoxEEPlane] = r; },

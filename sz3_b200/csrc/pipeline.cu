@@ -345,6 +345,9 @@ static bool launch_box(const InterpArgs<T, QT> &A, const BoxPlan &bp, uint64_t n
             S.odiv = 1;
             S.tma = A.s == 1 && (sdims[2] & 3u) == 0 && (reinterpret_cast<uintptr_t>(A.data) & 15u) == 0;
         }
+        // a level with fewer tiles than the GPU has CTA slots: four (eight) CTAs per tile, so that a tile's latency is
+        // two (one) plane rounds instead of five (phase A is repeated by each of them; only the first emits it)
+        S.split = ntiles <= 8 ? 8u : (ntiles * 4 <= 2u * 148u ? 4u : 1u);
         if (S.tma && interp_launch_box(A, S, sdims, ntiles, st)) return true;
         S.tma = 0;
         return interp_launch_box(A, S, sdims, ntiles, st);

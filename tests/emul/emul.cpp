@@ -53,9 +53,9 @@ static void box_tile_emul(const BoxArgs &A, const BoxSrc &S, const uint32_t sdim
         box_fill_column(A, S, o, t, EE.data());
         if (t < 33) box_fill_column(A, S, o, 256 + t, EE.data());
     }
-    for (uint32_t t = kBoxThreads; t-- > 0;) box_pass0_line<CUBIC>(A, S, ctx, T, t, EE.data());
+    for (uint32_t t = kBoxThreads; t-- > 0;) box_pass0_line<CUBIC>(A, S, ctx, T, t, EE.data(), true);
     for (uint32_t t = kBoxThreads; t-- > 0;)
-        for (uint32_t e = t; e < 33 * 16; e += kBoxThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE.data());
+        for (uint32_t e = t; e < 33 * 16; e += kBoxThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE.data(), true);
     for (uint32_t w = kBoxWarps; w-- > 0;) {
         float *slot = slots.data() + w * kBoxSlotStride;
         uint16_t *stg = stage.data() + w * kBoxStageU16;
