@@ -583,7 +583,8 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "GB/s", "h2d_bytes_per_step": h2d.value * world, "d2h_bytes_per_step": d2h.value * world,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "predict_quantize (k_box_compact + k_interp_anchor + k_interp_box x 5 levels)",
+            "roofline": {"bound": "hbm", "kernel": ("predict_quantize (k_box_compact + k_interp_anchor + k_interp_box x 5 levels; the histogram of "
+                                                    "HuffmanEncoder::init is a pass of its own, stage huffman_histogram)"),
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes": alg_bytes, "ms_per_step": pq_avg_ms,

@@ -188,102 +188,181 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned *warp_s
     return r;
 }
 
+// The packer works on chunks of kPackChunk symbols; a CTA walks over chunks (a few CTAs per SM), a thread takes
+// kPackPerThread consecutive symbols of the chunk.
+//
+// Code table: index streams crowd around one symbol, so a window of kPackWin states around the most frequent one sits
+// in shared memory -- entry = len << 24 | code for codes of 1..24 bits, 0 for everything else (absent states, longer
+// codes, the unpredictable marker `zero_sym`, states outside the window: index kPackWin).  The hot loops are straight
+// line code over the window; a thread that met a 0 entry (rare) then visits just those symbols again with the tables
+// in global memory.
+
+// Symbols of one thread of a full chunk.  16-bit indices of a 16-byte aligned stream come in by two 16-byte loads (a
+// warp then touches every sector once); anything else element by element.
 template <class QT>
-__global__ void __launch_bounds__(kPackThreads) k_pack_count(const QT *__restrict__ q, uint64_t n, int sym_min,
-                                                             int zero_sym, const uint8_t *__restrict__ len,
-                                                             unsigned *__restrict__ chunk_bits,
-                                                             unsigned *__restrict__ chunk_zeros) {
-    __shared__ unsigned ws[kPackThreads / 32];
-    __shared__ unsigned wz[kPackThreads / 32];
-    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kPackChunk + static_cast<uint64_t>(threadIdx.x) * kPackPerThread;
-    unsigned bits = 0, zeros = 0;
+__device__ __forceinline__ void pack_load_full(const QT *__restrict__ q, uint64_t base, bool vec, int (&v)[kPackPerThread]) {
+    if (sizeof(QT) == 2 && vec) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(q + base);
+        const uint4 a = p[0], b = p[1];
+        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int k = 0; k < kPackPerThread; k++) {
-        uint64_t i = base + k;
-        if (i < n) {
-            int v = static_cast<int>(q[i]);
-            bits += len[v - sym_min];
-            zeros += (v == zero_sym);
+        for (int k = 0; k < 8; k++) {
+            v[2 * k] = static_cast<int>(w[k] & 0xffffu);
+            v[2 * k + 1] = static_cast<int>(w[k] >> 16);
         }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        bits += __shfl_xor_sync(0xffffffffu, bits, o);
-        zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        ws[threadIdx.x >> 5] = bits;
-        wz[threadIdx.x >> 5] = zeros;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned b = 0, z = 0;
-        for (int w = 0; w < kPackThreads / 32; w++) {
-            b += ws[w];
-            z += wz[w];
-        }
-        chunk_bits[blockIdx.x] = b;
-        chunk_zeros[blockIdx.x] = z;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kPackPerThread; k++) v[k] = static_cast<int>(q[base + k]);
     }
 }
 
-// single CTA; off arrays get nchunks+1 entries (last = total)
+constexpr int kPackWin = 256;
+__device__ __forceinline__ void pack_window(unsigned *swin, int wlo, unsigned nstates, int zero_state, const uint8_t *__restrict__ len,
+                                            const unsigned long long *__restrict__ code) {
+    for (int j = threadIdx.x; j <= kPackWin; j += blockDim.x) {
+        const int s = wlo + j;
+        unsigned e = 0;
+        if (j < kPackWin && s >= 0 && static_cast<unsigned>(s) < nstates && s != zero_state) {
+            const unsigned l = len[s];
+            if (l && l <= 24) e = (l << 24) | static_cast<unsigned>(code[s]);
+        }
+        swin[j] = e;
+    }
+}
+__device__ __forceinline__ unsigned pack_lookup(const unsigned *swin, int v, int woff) {
+    const unsigned u = static_cast<unsigned>(v - woff);   // woff = sym_min + wlo
+    return swin[u < static_cast<unsigned>(kPackWin) ? u : static_cast<unsigned>(kPackWin)];
+}
+
+template <class QT>
+__global__ void __launch_bounds__(kPackThreads) k_pack_count(const QT *__restrict__ q, uint64_t n, int sym_min,
+                                                             int zero_sym, const uint8_t *__restrict__ len,
+                                                             const unsigned long long *__restrict__ code, int wlo,
+                                                             unsigned nstates, bool vec, uint64_t nchunks,
+                                                             unsigned *__restrict__ chunk_bits,
+                                                             unsigned *__restrict__ chunk_zeros) {
+    __shared__ unsigned swin[kPackWin + 1];
+    __shared__ unsigned ws[2][kPackThreads / 32];
+    __shared__ unsigned wz[2][kPackThreads / 32];
+    pack_window(swin, wlo, nstates, zero_sym - sym_min, len, code);
+    __syncthreads();
+    const int woff = sym_min + wlo;
+    unsigned par = 0;
+    for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x, par ^= 1u) {
+        const uint64_t base = c * kPackChunk + static_cast<uint64_t>(threadIdx.x) * kPackPerThread;
+        unsigned bits = 0, zeros = 0;
+        if ((c + 1) * kPackChunk <= n) {
+            int v[kPackPerThread];
+            pack_load_full(q, base, vec, v);
+            unsigned lmin = 0xffu;
+#pragma unroll
+            for (int k = 0; k < kPackPerThread; k++) {
+                const unsigned l = pack_lookup(swin, v[k], woff) >> 24;
+                bits += l;
+                lmin = l < lmin ? l : lmin;
+            }
+            if (lmin == 0) {
+#pragma unroll
+                for (int k = 0; k < kPackPerThread; k++) {
+                    if (pack_lookup(swin, v[k], woff) == 0) {
+                        bits += len[v[k] - sym_min];
+                        zeros += (v[k] == zero_sym);
+                    }
+                }
+            }
+        } else {
+            for (int k = 0; k < kPackPerThread; k++) {
+                if (base + k < n) {
+                    const int vk = static_cast<int>(q[base + k]);
+                    bits += len[vk - sym_min];
+                    zeros += (vk == zero_sym);
+                }
+            }
+        }
+        bits = __reduce_add_sync(0xffffffffu, bits);
+        zeros = __reduce_add_sync(0xffffffffu, zeros);
+        if ((threadIdx.x & 31) == 0) {
+            ws[par][threadIdx.x >> 5] = bits;
+            wz[par][threadIdx.x >> 5] = zeros;
+        }
+        __syncthreads();   // (the two parities keep a fast warp of the next chunk off this chunk's sums)
+        if (threadIdx.x < 32) {
+            unsigned b = threadIdx.x < kPackThreads / 32 ? ws[par][threadIdx.x] : 0u;
+            unsigned z = threadIdx.x < kPackThreads / 32 ? wz[par][threadIdx.x] : 0u;
+            b = __reduce_add_sync(0xffffffffu, b);
+            z = __reduce_add_sync(0xffffffffu, z);
+            if (threadIdx.x == 0) {
+                chunk_bits[c] = b;
+                chunk_zeros[c] = z;
+            }
+        }
+    }
+}
+
+// single CTA; off arrays get nchunks+1 entries (last = total).  Rounds of 4096 chunks: a thread takes four consecutive
+// ones (coalesced across the CTA), the 1024 partial sums are scanned through shuffles and shared memory.
 __global__ void __launch_bounds__(1024) k_pack_scan(const unsigned *__restrict__ chunk_bits,
                                                     const unsigned *__restrict__ chunk_zeros, uint64_t nchunks,
                                                     unsigned long long *__restrict__ bit_off,
                                                     unsigned long long *__restrict__ zero_off) {
-    __shared__ unsigned long long wsum[2][32];
-    __shared__ unsigned long long carry[2];
-    if (threadIdx.x == 0) carry[0] = carry[1] = 0;
-    __syncthreads();
+    __shared__ unsigned long long wsum[2][2][32];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (uint64_t base = 0; base < nchunks; base += 1024) {
-        uint64_t i = base + threadIdx.x;
-        unsigned long long v[2] = {i < nchunks ? chunk_bits[i] : 0ull, i < nchunks ? chunk_zeros[i] : 0ull};
-        unsigned long long inc[2] = {v[0], v[1]};
+    unsigned long long carry0 = 0, carry1 = 0;
+    unsigned par = 0;
+    for (uint64_t base = 0; base < nchunks; base += 4096, par ^= 1u) {
+        const uint64_t i = base + 4ull * threadIdx.x;
+        unsigned b[4], z[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            b[k] = i + k < nchunks ? chunk_bits[i + k] : 0u;
+            z[k] = i + k < nchunks ? chunk_zeros[i + k] : 0u;
+        }
+        const unsigned long long v0 = static_cast<unsigned long long>(b[0]) + b[1] + b[2] + b[3];
+        const unsigned long long v1 = static_cast<unsigned long long>(z[0]) + z[1] + z[2] + z[3];
+        unsigned long long inc0 = v0, inc1 = v1;
         for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t0 = __shfl_up_sync(0xffffffffu, inc[0], o);
-            unsigned long long t1 = __shfl_up_sync(0xffffffffu, inc[1], o);
+            unsigned long long t0 = __shfl_up_sync(0xffffffffu, inc0, o);
+            unsigned long long t1 = __shfl_up_sync(0xffffffffu, inc1, o);
             if (lane >= static_cast<unsigned>(o)) {
-                inc[0] += t0;
-                inc[1] += t1;
+                inc0 += t0;
+                inc1 += t1;
             }
         }
         if (lane == 31) {
-            wsum[0][wid] = inc[0];
-            wsum[1][wid] = inc[1];
+            wsum[par][0][wid] = inc0;
+            wsum[par][1][wid] = inc1;
         }
         __syncthreads();
-        if (wid == 0) {
-            unsigned long long w0 = wsum[0][lane], w1 = wsum[1][lane];
-            unsigned long long i0 = w0, i1 = w1;
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long t0 = __shfl_up_sync(0xffffffffu, i0, o);
-                unsigned long long t1 = __shfl_up_sync(0xffffffffu, i1, o);
-                if (lane >= static_cast<unsigned>(o)) {
-                    i0 += t0;
-                    i1 += t1;
-                }
+        // every warp scans the 32 warp totals itself (no second barrier; the two parities keep rounds apart)
+        unsigned long long w0 = wsum[par][0][lane], w1 = wsum[par][1][lane];
+        unsigned long long a0 = w0, a1 = w1;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t0 = __shfl_up_sync(0xffffffffu, a0, o);
+            unsigned long long t1 = __shfl_up_sync(0xffffffffu, a1, o);
+            if (lane >= static_cast<unsigned>(o)) {
+                a0 += t0;
+                a1 += t1;
             }
-            wsum[0][lane] = i0 - w0;
-            wsum[1][lane] = i1 - w1;
         }
-        __syncthreads();
-        unsigned long long e0 = carry[0] + wsum[0][wid] + inc[0] - v[0];
-        unsigned long long e1 = carry[1] + wsum[1][wid] + inc[1] - v[1];
-        if (i < nchunks) {
-            bit_off[i] = e0;
-            zero_off[i] = e1;
+        const unsigned long long tot0 = __shfl_sync(0xffffffffu, a0, 31), tot1 = __shfl_sync(0xffffffffu, a1, 31);
+        const unsigned long long before0 = __shfl_sync(0xffffffffu, a0 - w0, wid), before1 = __shfl_sync(0xffffffffu, a1 - w1, wid);
+        unsigned long long e0 = carry0 + before0 + inc0 - v0;
+        unsigned long long e1 = carry1 + before1 + inc1 - v1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i + k < nchunks) {
+                bit_off[i + k] = e0;
+                zero_off[i + k] = e1;
+            }
+            e0 += b[k];
+            e1 += z[k];
         }
-        __syncthreads();
-        if (threadIdx.x == 1023) {
-            carry[0] = e0 + v[0];
-            carry[1] = e1 + v[1];
-        }
-        __syncthreads();
+        carry0 += tot0;
+        carry1 += tot1;
     }
     if (threadIdx.x == 0) {
-        bit_off[nchunks] = carry[0];
-        zero_off[nchunks] = carry[1];
+        bit_off[nchunks] = carry0;
+        zero_off[nchunks] = carry1;
     }
 }
 
@@ -315,11 +394,20 @@ __device__ __forceinline__ void acc_put(BitAcc &a, unsigned bits, unsigned l, un
     a.nacc += l;
     acc_flush(a, sbits);
 }
+__device__ __forceinline__ void acc_put_long(BitAcc &a, unsigned long long cw, unsigned l, unsigned *sbits) {  // l <= 64
+    if (l > 32) {
+        acc_put(a, static_cast<unsigned>(cw >> 32), l - 32, sbits);
+        acc_put(a, static_cast<unsigned>(cw), 32, sbits);
+    } else {
+        acc_put(a, static_cast<unsigned>(cw), l, sbits);
+    }
+}
 
 template <class QT, class T>
-__global__ void __launch_bounds__(kPackThreads) k_pack_write(const QT *__restrict__ q, uint64_t n, int sym_min,
+__global__ void __launch_bounds__(kPackThreads, 4) k_pack_write(const QT *__restrict__ q, uint64_t n, int sym_min,
                                                              int zero_sym, const uint8_t *__restrict__ len,
-                                                             const unsigned long long *__restrict__ code,
+                                                             const unsigned long long *__restrict__ code, int wlo,
+                                                             unsigned nstates, bool vec, uint64_t nchunks,
                                                              const unsigned long long *__restrict__ bit_off,
                                                              const unsigned long long *__restrict__ zero_off,
                                                              unsigned *__restrict__ out_words,
@@ -327,72 +415,117 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_write(const QT *__restric
                                                              T *__restrict__ unpred_out) {
     // worst case 4096 symbols x 64 bits + 31 leading bits
     __shared__ unsigned sbits[kPackChunk * 2 + 2];
+    __shared__ unsigned swin[kPackWin + 1];
     __shared__ unsigned warp_sums[kPackThreads / 32];
     __shared__ unsigned tot_bits, tot_zeros;
-    const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kPackChunk + static_cast<uint64_t>(threadIdx.x) * kPackPerThread;
-    int sym[kPackPerThread];
-    unsigned bits = 0, zeros = 0;
-#pragma unroll
-    for (int k = 0; k < kPackPerThread; k++) {
-        uint64_t i = base + k;
-        sym[k] = -1;
-        if (i < n) {
-            int v = static_cast<int>(q[i]);
-            sym[k] = v - sym_min;
-            bits += len[v - sym_min];
-            zeros += (v == zero_sym);
-        }
-    }
-    const unsigned long long B0 = bit_off[blockIdx.x];
-    const unsigned lead = static_cast<unsigned>(B0 & 31);
-    unsigned my_bit = block_excl_scan(bits, warp_sums, &tot_bits);
+    pack_window(swin, wlo, nstates, zero_sym - sym_min, len, code);
     __syncthreads();
-    const unsigned nwords = (lead + tot_bits + 31) >> 5;
-    for (unsigned i = threadIdx.x; i < nwords; i += kPackThreads) sbits[i] = 0;
-    __syncthreads();
-    if (bits) {
-        unsigned b = lead + my_bit;
-        BitAcc a;
-        a.acc = 0;
-        a.nacc = b & 31;
-        a.w = b >> 5;
-        a.first = true;
+    const int woff = sym_min + wlo;
+    constexpr unsigned kLong = 0xffffffffu;   // entry of a symbol whose code does not fit an entry: tables in global memory
+    for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const uint64_t base = c * kPackChunk + static_cast<uint64_t>(threadIdx.x) * kPackPerThread;
+        const bool full = (c + 1) * kPackChunk <= n;
+        int v[kPackPerThread];
+        unsigned ent[kPackPerThread];   // len << 24 | code; 0 = no symbol (ragged tail); kLong
+        unsigned bits = 0, zeros = 0;
+        bool has_long = false;
+        if (full) {
+            pack_load_full(q, base, vec, v);
+            unsigned emin = kLong;
 #pragma unroll
-        for (int k = 0; k < kPackPerThread; k++) {
-            if (sym[k] >= 0) {
-                unsigned l = len[sym[k]];
-                unsigned long long c = code[sym[k]];
-                if (l > 32) {
-                    acc_put(a, static_cast<unsigned>(c >> 32), l - 32, sbits);
-                    acc_put(a, static_cast<unsigned>(c), 32, sbits);
-                } else {
-                    acc_put(a, static_cast<unsigned>(c), l, sbits);
+            for (int k = 0; k < kPackPerThread; k++) {
+                ent[k] = pack_lookup(swin, v[k], woff);
+                bits += ent[k] >> 24;
+                emin = ent[k] < emin ? ent[k] : emin;
+            }
+            if (emin == 0) {
+#pragma unroll
+                for (int k = 0; k < kPackPerThread; k++) {
+                    if (ent[k] == 0) {
+                        const unsigned l = len[v[k] - sym_min];
+                        bits += l;
+                        zeros += (v[k] == zero_sym);
+                        ent[k] = (l && l <= 24) ? (l << 24) | static_cast<unsigned>(code[v[k] - sym_min]) : kLong;
+                        has_long = has_long || ent[k] == kLong;
+                    }
+                }
+            }
+        } else {
+            for (int k = 0; k < kPackPerThread; k++) {
+                ent[k] = 0;
+                v[k] = zero_sym + 1;
+                if (base + k < n) {
+                    v[k] = static_cast<int>(q[base + k]);
+                    bits += len[v[k] - sym_min];
+                    zeros += (v[k] == zero_sym);
+                    ent[k] = kLong;
+                    has_long = true;
                 }
             }
         }
-        if (a.nacc) atomicOr(&sbits[a.w], static_cast<unsigned>(a.acc >> 32));
-    }
-    __syncthreads();
-    // store: stream bit 0 of a word is its MSB -> byte-swap to memory order
-    const unsigned long long W0 = B0 >> 5;
-    for (unsigned i = threadIdx.x; i < nwords; i += kPackThreads) {
-        unsigned w = __byte_perm(sbits[i], 0, 0x0123);
-        if (i == 0 || i == nwords - 1) {
-            if (w) atomicOr(&out_words[W0 + i], w);
-        } else {
-            out_words[W0 + i] = w;
-        }
-    }
-    // ordered compaction of the unpredictable values (LinearQuantizer::unpred, reference LinearQuantizer.hpp:63,68)
-    if (unpred_out != nullptr) {
-        unsigned my_zero = block_excl_scan(zeros, warp_sums, &tot_zeros);
-        if (zeros) {
-            unsigned long long zo = zero_off[blockIdx.x] + my_zero;
+        const unsigned long long B0 = bit_off[c];
+        const unsigned lead = static_cast<unsigned>(B0 & 31);
+        unsigned my_bit = block_excl_scan(bits, warp_sums, &tot_bits);
+        __syncthreads();
+        const unsigned nwords = (lead + tot_bits + 31) >> 5;
+        for (unsigned i = threadIdx.x; i < nwords; i += kPackThreads) sbits[i] = 0;
+        __syncthreads();
+        const unsigned b = lead + my_bit;
+        if (full && !has_long && bits <= 64) {
+            // the usual case: the thread's sixteen codes fit one 64-bit register -- concatenated without any flush
+            // test, left-aligned, then dropped into (at most) three words of the CTA buffer
+            unsigned long long t = 0;
+#pragma unroll
+            for (int k = 0; k < kPackPerThread; k++) t = (t << (ent[k] >> 24)) | (ent[k] & 0x00ffffffu);
+            t <<= 64 - bits;   // bits >= 16 here (every symbol has a code of at least one bit)
+            const unsigned hi = static_cast<unsigned>(t >> 32), lo = static_cast<unsigned>(t), o = b & 31u, w = b >> 5;
+            const unsigned w0 = hi >> o, w1 = __funnelshift_r(lo, hi, o), w2 = __funnelshift_r(0u, lo, o);
+            atomicOr(&sbits[w], w0);
+            if (w1) atomicOr(&sbits[w + 1], w1);
+            if (w2) atomicOr(&sbits[w + 2], w2);
+        } else if (bits) {
+            BitAcc a;
+            a.acc = 0;
+            a.nacc = b & 31;
+            a.w = b >> 5;
+            a.first = true;
 #pragma unroll
             for (int k = 0; k < kPackPerThread; k++) {
-                if (sym[k] >= 0 && sym[k] + sym_min == zero_sym) unpred_out[zo++] = unpred_tmp[base + k];
+                const unsigned e = ent[k];
+                if (e == kLong) {
+                    acc_put_long(a, code[v[k] - sym_min], len[v[k] - sym_min], sbits);
+                } else if (full) {   // 1 <= len <= 24
+                    const unsigned l = e >> 24;
+                    a.acc |= static_cast<unsigned long long>(e & 0x00ffffffu) << (64 - a.nacc - l);
+                    a.nacc += l;
+                    acc_flush(a, sbits);
+                }
+            }
+            if (a.nacc) atomicOr(&sbits[a.w], static_cast<unsigned>(a.acc >> 32));
+        }
+        __syncthreads();
+        // store: stream bit 0 of a word is its MSB -> byte-swap to memory order
+        const unsigned long long W0 = B0 >> 5;
+        for (unsigned i = threadIdx.x; i < nwords; i += kPackThreads) {
+            unsigned w = __byte_perm(sbits[i], 0, 0x0123);
+            if (i == 0 || i == nwords - 1) {
+                if (w) atomicOr(&out_words[W0 + i], w);
+            } else {
+                out_words[W0 + i] = w;
             }
         }
+        // ordered compaction of the unpredictable values (LinearQuantizer::unpred, reference LinearQuantizer.hpp:63,68)
+        if (unpred_out != nullptr) {
+            unsigned my_zero = block_excl_scan(zeros, warp_sums, &tot_zeros);
+            if (zeros) {
+                unsigned long long zo = zero_off[c] + my_zero;
+#pragma unroll
+                for (int k = 0; k < kPackPerThread; k++) {
+                    if (v[k] == zero_sym) unpred_out[zo++] = unpred_tmp[base + k];
+                }
+            }
+        }
+        __syncthreads();   // sbits / warp_sums are reused by the next chunk
     }
 }
 
@@ -423,17 +556,22 @@ uint64_t pack_num_chunks(uint64_t n) { return (n + kPackChunk - 1) / kPackChunk;
 
 template <class QT, class T>
 void launch_pack(const QT *q, uint64_t n, int sym_min, int zero_sym, const uint8_t *len,
-                 const unsigned long long *code, unsigned *chunk_bits, unsigned *chunk_zeros,
-                 unsigned long long *bit_off, unsigned long long *zero_off, unsigned *out_words, const T *unpred_tmp,
-                 T *unpred_out, cudaStream_t st, cudaEvent_t after_scan) {
+                 const unsigned long long *code, unsigned nstates, int center_state, unsigned *chunk_bits,
+                 unsigned *chunk_zeros, unsigned long long *bit_off, unsigned long long *zero_off, unsigned *out_words,
+                 const T *unpred_tmp, T *unpred_out, cudaStream_t st, cudaEvent_t after_scan) {
     const uint64_t nchunks = pack_num_chunks(n);
     if (nchunks == 0) return;
-    k_pack_count<QT><<<static_cast<unsigned>(nchunks), kPackThreads, 0, st>>>(q, n, sym_min, zero_sym, len, chunk_bits,
-                                                                             chunk_zeros);
+    const bool vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
+    const int wlo = center_state - kPackWin / 2;
+    // CTAs walk over the chunks: 8 (count) / 4 (write: 34 KB of shared memory, 64 registers) resident CTAs per SM
+    const unsigned g1 = static_cast<unsigned>(nchunks < 148u * 8u ? nchunks : 148u * 8u);
+    const unsigned g2 = static_cast<unsigned>(nchunks < 148u * 4u ? nchunks : 148u * 4u);
+    k_pack_count<QT><<<g1, kPackThreads, 0, st>>>(q, n, sym_min, zero_sym, len, code, wlo, nstates, vec, nchunks, chunk_bits,
+                                                  chunk_zeros);
     k_pack_scan<<<1, 1024, 0, st>>>(chunk_bits, chunk_zeros, nchunks, bit_off, zero_off);
     if (after_scan) cudaEventRecord(after_scan, st);
-    k_pack_write<QT, T><<<static_cast<unsigned>(nchunks), kPackThreads, 0, st>>>(
-        q, n, sym_min, zero_sym, len, code, bit_off, zero_off, out_words, unpred_tmp, unpred_out);
+    k_pack_write<QT, T><<<g2, kPackThreads, 0, st>>>(q, n, sym_min, zero_sym, len, code, wlo, nstates, vec, nchunks, bit_off,
+                                                     zero_off, out_words, unpred_tmp, unpred_out);
 }
 
 #define SZ3B_INST_Q(QT)                                                                                              \
@@ -444,8 +582,8 @@ SZ3B_INST_Q(uint32_t)
 SZ3B_INST_Q(int32_t)
 #define SZ3B_INST_P(QT, T)                                                                                           \
     template void launch_pack<QT, T>(const QT *, uint64_t, int, int, const uint8_t *, const unsigned long long *,    \
-                                     unsigned *, unsigned *, unsigned long long *, unsigned long long *, unsigned *, \
-                                     const T *, T *, cudaStream_t, cudaEvent_t);
+                                     unsigned, int, unsigned *, unsigned *, unsigned long long *,                   \
+                                     unsigned long long *, unsigned *, const T *, T *, cudaStream_t, cudaEvent_t);
 SZ3B_INST_P(uint16_t, float)
 SZ3B_INST_P(uint16_t, double)
 SZ3B_INST_P(uint32_t, float)

@@ -62,9 +62,9 @@ void launch_minmax_int(const QT *q, uint64_t n, int *mm, cudaStream_t st);
 uint64_t pack_num_chunks(uint64_t n);
 template <class QT, class T>
 void launch_pack(const QT *q, uint64_t n, int sym_min, int zero_sym, const uint8_t *len,
-                 const unsigned long long *code, unsigned *chunk_bits, unsigned *chunk_zeros,
-                 unsigned long long *bit_off, unsigned long long *zero_off, unsigned *out_words, const T *unpred_tmp,
-                 T *unpred_out, cudaStream_t st, cudaEvent_t after_scan);
+                 const unsigned long long *code, unsigned nstates, int center_state, unsigned *chunk_bits,
+                 unsigned *chunk_zeros, unsigned long long *bit_off, unsigned long long *zero_off, unsigned *out_words,
+                 const T *unpred_tmp, T *unpred_out, cudaStream_t st, cudaEvent_t after_scan);
 
 // blockwise.cu
 struct BlockShape;

@@ -358,7 +358,8 @@ static bool launch_box(const InterpArgs<T, QT> &A, const BoxPlan &bp, uint64_t n
 
 template <class T, class QT>
 static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uint32_t nbatch, int radius, QT *d_q,
-                       T *d_unpred_tmp, unsigned long long *d_hist, DevBuf &recon_buf, int *launches) {
+                       T *d_unpred_tmp, unsigned long long *d_hist, DevBuf &recon_buf, int *launches,
+                       uint64_t *hist_owed = nullptr) {
     InterpArgs<T, QT> A;
     memset(&A, 0, sizeof(A));
     A.sh = pl.sh;
@@ -469,7 +470,14 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
             }
         }
     }
-    flush_hist();
+    // the stretch of the stream the box schedule left uncounted: handed to the caller (who times the histogram of
+    // HuffmanEncoder::init as its own stage) or counted here
+    if (hist_owed) {
+        hist_owed[0] = hist_from;
+        hist_owed[1] = hist_to;
+    } else {
+        flush_hist();
+    }
     SZ3B_CUDA(cudaGetLastError());
 }
 
@@ -531,8 +539,12 @@ static void encode_indices(Workspace &ws, const QT *d_q, uint64_t n, const unsig
     unsigned *d_words = ws.out_words.as<unsigned>(nwords);
     SZ3B_CUDA(cudaMemsetAsync(d_words, 0, nwords * sizeof(unsigned), ws.st));
     T *d_unpred_out = lay.n_unpred ? ws.unpred_out.as<T>(lay.n_unpred) : nullptr;
-    launch_pack<QT, T>(d_q, n, book.offset, 0, d_len, d_code, d_cb, d_cz, d_bo, d_zo, d_words, d_unpred_tmp,
-                       d_unpred_out, ws.st, nullptr);
+    // the packer keeps a window of the code table around the most frequent state in shared memory
+    size_t top = 0;
+    for (size_t k = 0; k < states && book.offset - sym_base + k < static_cast<size_t>(nbins); k++)
+        if (h_hist[book.offset - sym_base + k] > h_hist[book.offset - sym_base + top]) top = k;
+    launch_pack<QT, T>(d_q, n, book.offset, 0, d_len, d_code, static_cast<unsigned>(states), static_cast<int>(top), d_cb, d_cz,
+                       d_bo, d_zo, d_words, d_unpred_tmp, d_unpred_out, ws.st, nullptr);
     SZ3B_CUDA(cudaGetLastError());
     ws.stage_end(h, 3);
 }
@@ -816,8 +828,16 @@ static size_t interp_compress_t(Workspace &ws, const sz3b_config &conf, const T 
     size_t h = ws.stage_begin(tuner ? "tune_predict_quantize" : "predict_quantize");
     SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
     int launches = 0;
-    run_interp<T, QT>(ws, pl, d_data, nbatch, radius, d_q, d_unpred_tmp, d_hist, rb, &launches);
+    uint64_t owed[2] = {0, 0};
+    run_interp<T, QT>(ws, pl, d_data, nbatch, radius, d_q, d_unpred_tmp, d_hist, rb, &launches, owed);
     ws.stage_end(h, launches);
+    if constexpr (std::is_same<QT, uint16_t>::value) {
+        if (owed[1] > owed[0]) {   // HuffmanEncoder::init's histogram (:516-527) of what the box schedule wrote
+            h = ws.stage_begin(tuner ? "tune_huffman_histogram" : "huffman_histogram");
+            launch_hist_u16(d_q + owed[0], owed[1] - owed[0], radius, nbins, d_hist, ws.st);
+            ws.stage_end(h, 1);
+        }
+    }
 
     HuffmanBook book;
     EncodeLayout lay;

@@ -11,3 +11,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --c
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_interp_box -s 4 -c 1 -o gpurun_out/prof_box_$TAG \
     python tools/prof_decompose.py 0 1 > gpurun_out/ncu_full_$TAG.log 2>&1
+timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    -k regex:'k_box_compact|k_interp_anchor|k_interp_box' -s 7 -c 7 -o gpurun_out/traffic_$TAG python tools/prof_decompose.py 0 2 > /dev/null 2>&1
