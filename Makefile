@@ -25,7 +25,7 @@ $(OBJDIR)/%.o: $(SRC)/%.cpp $(HDRS)
 
 $(LIB): $(OBJS)
 	@mkdir -p sz3_b200/lib
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -l:libzstd.so.1 -lpthread
+	$(NVCC) $(ARCH) -shared -Xlinker --no-undefined -o $@ $(OBJS) -l:libzstd.so.1 -lpthread -ldl
 
 # libSZ3c: the reference's C shim (tools/sz3c) rebuilt on the drop-in headers; depends on libsz3b200 at run time
 $(LIBC): sz3_b200/sz3c/sz3c.cpp include/sz3c.h $(wildcard include/SZ3/*.hpp include/SZ3/*/*.hpp) $(LIB)

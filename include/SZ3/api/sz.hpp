@@ -21,9 +21,12 @@ namespace SZ3 {
 namespace b200 {
 template <class T>
 constexpr int dtype_of() {
-    static_assert(std::is_same<T, float>::value || std::is_same<T, double>::value,
-                  "sz3_b200: the GPU path is built for float and double");
-    return std::is_same<T, float>::value ? SZ3B_FLOAT : SZ3B_DOUBLE;
+    static_assert(std::is_same<T, float>::value || std::is_same<T, double>::value || std::is_same<T, int32_t>::value ||
+                      std::is_same<T, int64_t>::value,
+                  "sz3_b200: the GPU path is built for float, double, int32_t and int64_t");
+    return std::is_same<T, float>::value ? SZ3B_FLOAT
+           : std::is_same<T, double>::value ? SZ3B_DOUBLE
+           : std::is_same<T, int32_t>::value ? SZ3B_INT32 : SZ3B_INT64;
 }
 inline void raise(int rc) {
     if (rc == SZ3B_OK) return;

@@ -230,15 +230,23 @@ unsigned ref_zstd_version() { return ZSTD_versionNumber(); }
 
 size_t ref_size_bound(int dtype, const ref_config *c) {
     Config conf = to_conf(c);
+    if (dtype == SZ_INT32) return SZ_compress_size_bound<int32_t>(conf);
+    if (dtype == SZ_INT64) return SZ_compress_size_bound<int64_t>(conf);
     return dtype == 0 ? SZ_compress_size_bound<float>(conf) : SZ_compress_size_bound<double>(conf);
 }
 
-// dtype: 0 = float, 1 = double (SZ_FLOAT / SZ_DOUBLE, Config.hpp:27-28). Returns bytes written or -1.
+// dtype: 0 = float, 1 = double, 7 = int32, 9 = int64 (SZ_FLOAT / SZ_DOUBLE / SZ_INT32 / SZ_INT64, Config.hpp:27-36;
+// the integer types only through the whole-stream entry points, as tools/sz3/sz3.cpp:458-461 uses them).
+// Returns bytes written or -1.
 long long ref_compress(int dtype, const ref_config *c, const void *data, char *out, size_t cap) {
+    if (dtype == SZ_INT32) return compress_t<int32_t>(c, data, out, cap);
+    if (dtype == SZ_INT64) return compress_t<int64_t>(c, data, out, cap);
     return dtype == 0 ? compress_t<float>(c, data, out, cap) : compress_t<double>(c, data, out, cap);
 }
 
 int ref_decompress(int dtype, const char *cmp, size_t n, void *out, ref_config *conf_out) {
+    if (dtype == SZ_INT32) return decompress_t<int32_t>(cmp, n, out, conf_out);
+    if (dtype == SZ_INT64) return decompress_t<int64_t>(cmp, n, out, conf_out);
     return dtype == 0 ? decompress_t<float>(cmp, n, out, conf_out) : decompress_t<double>(cmp, n, out, conf_out);
 }
 
@@ -297,7 +305,11 @@ int ref_tune(int dtype, ref_config *c, const void *data) {
 
 double ref_abs_eb(int dtype, const ref_config *c, const void *data) {
     Config conf = to_conf(c);
-    if (dtype == 0)
+    if (dtype == SZ_INT32)
+        calAbsErrorBound<int32_t>(conf, static_cast<const int32_t *>(data));
+    else if (dtype == SZ_INT64)
+        calAbsErrorBound<int64_t>(conf, static_cast<const int64_t *>(data));
+    else if (dtype == 0)
         calAbsErrorBound<float>(conf, static_cast<const float *>(data));
     else
         calAbsErrorBound<double>(conf, static_cast<const double *>(data));

@@ -140,9 +140,9 @@ def _buffer_of(data):
         if isinstance(data, torch.Tensor):
             if not data.is_contiguous():
                 data = data.contiguous()
-            code = {torch.float32: 0, torch.float64: 1}.get(data.dtype)
+            code = {torch.float32: 0, torch.float64: 1, torch.int32: 7, torch.int64: 9}.get(data.dtype)
             if code is None:
-                raise TypeError(f"Unsupported dtype: {data.dtype}. Supported on the GPU path: float32, float64")
+                raise TypeError(f"Unsupported dtype: {data.dtype}. Supported on the GPU path: float32, float64, int32, int64")
             if data.is_cuda:
                 # the library reads the buffer on its own streams: order it after what torch has queued on the current
                 # stream (a .contiguous() copy above included) -- include/sz3b.h, stream contract
@@ -153,9 +153,9 @@ def _buffer_of(data):
         pass
     if not isinstance(data, np.ndarray):
         raise TypeError("data must be a numpy.ndarray or a torch.Tensor")
-    code = {np.dtype(np.float32): 0, np.dtype(np.float64): 1}.get(data.dtype)
+    code = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 7, np.dtype(np.int64): 9}.get(data.dtype)
     if code is None:
-        raise TypeError(f"Unsupported dtype: {data.dtype}. Supported on the GPU path: float32, float64")
+        raise TypeError(f"Unsupported dtype: {data.dtype}. Supported on the GPU path: float32, float64, int32, int64")
     if not data.flags["C_CONTIGUOUS"]:
         data = np.ascontiguousarray(data)
     return data.ctypes.data, 0, code, tuple(data.shape), data
@@ -194,7 +194,7 @@ class sz:
         """Returns (array, szConfig).  device=None -> numpy array; device='cuda' -> torch CUDA tensor."""
         compressed = np.ascontiguousarray(np.frombuffer(compressed, dtype=np.uint8))
         dt = np.dtype(dtype)
-        code = {np.dtype(np.float32): 0, np.dtype(np.float64): 1}.get(dt)
+        code = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 7, np.dtype(np.int64): 9}.get(dt)
         if code is None:
             raise TypeError(f"Unsupported dtype: {dtype}")
         L = lib()
@@ -210,7 +210,7 @@ class sz:
             ptr, loc = out.ctypes.data, 0
         else:
             import torch
-            out = torch.empty(shape, dtype=torch.float32 if code == 0 else torch.float64, device=device)
+            out = torch.empty(shape, dtype={0: torch.float32, 1: torch.float64, 7: torch.int32, 9: torch.int64}[code], device=device)
             lib().sz3b_set_caller_stream(C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream), 1)
             ptr, loc = out.data_ptr(), 1
         _check(L.sz3b_decompress(code, compressed.ctypes.data_as(C.c_char_p), C.c_size_t(compressed.size),

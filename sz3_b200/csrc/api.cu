@@ -58,10 +58,26 @@ int guarded(F &&f) {
     }
 }
 
-void check_dtype(int dtype) {
+void check_dtype(int dtype) {   // stage-level entry points: floating-point data only
     if (dtype != SZ3B_FLOAT && dtype != SZ3B_DOUBLE)
-        fail(SZ3B_E_UNSUPPORTED, "only float32 / float64 are on the GPU path");
+        fail(SZ3B_E_UNSUPPORTED, "this entry point takes float32 / float64 data");
 }
+void check_dtype_any(int dtype) {
+    if (dtype != SZ3B_FLOAT && dtype != SZ3B_DOUBLE && dtype != SZ3B_INT32 && dtype != SZ3B_INT64)
+        fail(SZ3B_E_UNSUPPORTED, "element types on the GPU path: float32, float64, int32, int64");
+}
+size_t dtype_size(int dtype) { return dtype == SZ3B_FLOAT || dtype == SZ3B_INT32 ? 4 : 8; }
+// f(T *) for the element type of `dtype` (a null pointer used as a type tag)
+template <class F>
+auto by_dtype(int dtype, F &&f) {
+    switch (dtype) {
+        case SZ3B_FLOAT: return f(static_cast<float *>(nullptr));
+        case SZ3B_DOUBLE: return f(static_cast<double *>(nullptr));
+        case SZ3B_INT32: return f(static_cast<int32_t *>(nullptr));
+        default: return f(static_cast<int64_t *>(nullptr));
+    }
+}
+#define SZ3B_TAG_T(tag) typename std::remove_pointer<decltype(tag)>::type
 
 void check_conf(const sz3b_config *c) {
     if (!c) fail(SZ3B_E_INVALID_ARGUMENT, "null config");
@@ -77,7 +93,7 @@ void finish_profile(Workspace &ws) {
 }
 
 size_t size_bound(int dtype, const sz3b_config &c) {
-    const size_t esz = dtype == SZ3B_FLOAT ? 4 : 8;
+    const size_t esz = dtype_size(dtype);
     uint8_t blob[256];
     const size_t conf_est = config_save(c, blob);
     const uint64_t num = config_num(c);
@@ -160,7 +176,7 @@ size_t sz3b_compress_bound(int dtype, const sz3b_config *c) { return size_bound(
 int sz3b_compress(int dtype, const sz3b_config *c, const void *data, int data_loc, char *cmp, size_t cmp_cap,
                   size_t *cmp_size, sz3b_config *conf_out) {
     return guarded([&] {
-        check_dtype(dtype);
+        check_dtype_any(dtype);
         check_conf(c);
         if (!data || !cmp || !cmp_size) fail(SZ3B_E_INVALID_ARGUMENT, "null buffer");
         sz3b_config conf = *c;
@@ -177,9 +193,10 @@ int sz3b_compress(int dtype, const sz3b_config *c, const void *data, int data_lo
         after_caller(*ws, data_loc);
         uint64_t payload = 0;
         try {
-            payload = dtype == SZ3B_FLOAT
-                          ? compress_any<float>(*ws, conf, static_cast<const float *>(data), data_loc, p, cap)
-                          : compress_any<double>(*ws, conf, static_cast<const double *>(data), data_loc, p, cap);
+            payload = by_dtype(dtype, [&](auto *tag) -> uint64_t {
+                using T = SZ3B_TAG_T(tag);
+                return compress_any<T>(*ws, conf, static_cast<const T *>(data), data_loc, p, cap);
+            });
         } catch (...) {
             finish_profile(*ws);
             throw;
@@ -219,17 +236,18 @@ int sz3b_decompress(int dtype, const char *cmp, size_t cmp_size, void *out, int 
     int rc = sz3b_peek_config(cmp, cmp_size, &conf);
     if (rc != SZ3B_OK) return rc;
     return guarded([&] {
-        check_dtype(dtype);
+        check_dtype_any(dtype);
         if (!out) fail(SZ3B_E_INVALID_ARGUMENT, "null output buffer");
         const uint8_t *p = reinterpret_cast<const uint8_t *>(cmp) + 8;
         const uint64_t payload = get<uint64_t>(p);
         WorkspaceLease ws;
         after_caller(*ws, out_loc);
         try {
-            if (dtype == SZ3B_FLOAT)
-                decompress_any<float>(*ws, conf, p, payload, static_cast<float *>(out), out_loc);
-            else
-                decompress_any<double>(*ws, conf, p, payload, static_cast<double *>(out), out_loc);
+            by_dtype(dtype, [&](auto *tag) {
+                using T = SZ3B_TAG_T(tag);
+                decompress_any<T>(*ws, conf, p, payload, static_cast<T *>(out), out_loc);
+                return 0;
+            });
         } catch (...) {
             finish_profile(*ws);
             throw;
@@ -241,12 +259,14 @@ int sz3b_decompress(int dtype, const char *cmp, size_t cmp_size, void *out, int 
 
 int sz3b_abs_error_bound(int dtype, const sz3b_config *c, const void *data, int data_loc, double *abs_eb) {
     return guarded([&] {
-        check_dtype(dtype);
+        check_dtype_any(dtype);
         check_conf(c);
         WorkspaceLease ws;
         after_caller(*ws, data_loc);
-        *abs_eb = dtype == SZ3B_FLOAT ? abs_eb_stage<float>(*ws, *c, static_cast<const float *>(data), data_loc)
-                                      : abs_eb_stage<double>(*ws, *c, static_cast<const double *>(data), data_loc);
+        *abs_eb = by_dtype(dtype, [&](auto *tag) -> double {
+            using T = SZ3B_TAG_T(tag);
+            return abs_eb_stage<T>(*ws, *c, static_cast<const T *>(data), data_loc);
+        });
     });
 }
 
@@ -360,13 +380,14 @@ int sz3b_tune(int dtype, sz3b_config *c, const void *data, int data_loc) {
 
 int sz3b_minmax(int dtype, const void *data, int data_loc, size_t num, double *min_out, double *max_out) {
     return guarded([&] {
-        check_dtype(dtype);
+        check_dtype_any(dtype);
         WorkspaceLease ws;
         after_caller(*ws, data_loc);
-        if (dtype == SZ3B_FLOAT)
-            minmax_stage<float>(*ws, static_cast<const float *>(data), data_loc, num, min_out, max_out);
-        else
-            minmax_stage<double>(*ws, static_cast<const double *>(data), data_loc, num, min_out, max_out);
+        by_dtype(dtype, [&](auto *tag) {
+            using T = SZ3B_TAG_T(tag);
+            minmax_stage<T>(*ws, static_cast<const T *>(data), data_loc, num, min_out, max_out);
+            return 0;
+        });
     });
 }
 
@@ -400,18 +421,18 @@ int sz3b_compress_slab(int dtype, const sz3b_config *c, int rank, int nslabs, co
                        double range, char *payload, size_t payload_cap, size_t *payload_size,
                        unsigned char *conf_blob, size_t *conf_blob_size) {
     return guarded([&] {
-        check_dtype(dtype);
+        check_dtype_any(dtype);
         check_conf(c);
         sz3b_config sc = slab_config(c, rank, nslabs, range);
         WorkspaceLease ws;
         after_caller(*ws, data_loc);
         size_t sz = 0;
         try {
-            sz = dtype == SZ3B_FLOAT
-                     ? compress_slab<float>(*ws, sc, static_cast<const float *>(slab), data_loc, range,
-                                            reinterpret_cast<uint8_t *>(payload), payload_cap)
-                     : compress_slab<double>(*ws, sc, static_cast<const double *>(slab), data_loc, range,
-                                             reinterpret_cast<uint8_t *>(payload), payload_cap);
+            sz = by_dtype(dtype, [&](auto *tag) -> size_t {
+                using T = SZ3B_TAG_T(tag);
+                return compress_slab<T>(*ws, sc, static_cast<const T *>(slab), data_loc, range, reinterpret_cast<uint8_t *>(payload),
+                                        payload_cap);
+            });
         } catch (...) {
             finish_profile(*ws);
             throw;
@@ -426,7 +447,7 @@ int sz3b_compress_slab_placed(int dtype, const sz3b_config *c, int rank, int nsl
                               double range, sz3b_place_fn place, void *user, size_t *payload_size,
                               unsigned char *conf_blob, size_t *conf_blob_size) {
     return guarded([&] {
-        check_dtype(dtype);
+        check_dtype_any(dtype);
         check_conf(c);
         if (!place) fail(SZ3B_E_INVALID_ARGUMENT, "null placement callback");
         sz3b_config sc = slab_config(c, rank, nslabs, range);
@@ -434,9 +455,10 @@ int sz3b_compress_slab_placed(int dtype, const sz3b_config *c, int rank, int nsl
         after_caller(*ws, data_loc);
         size_t sz = 0;
         try {
-            sz = dtype == SZ3B_FLOAT
-                     ? compress_slab_placed<float>(*ws, sc, static_cast<const float *>(slab), data_loc, range, place, user)
-                     : compress_slab_placed<double>(*ws, sc, static_cast<const double *>(slab), data_loc, range, place, user);
+            sz = by_dtype(dtype, [&](auto *tag) -> size_t {
+                using T = SZ3B_TAG_T(tag);
+                return compress_slab_placed<T>(*ws, sc, static_cast<const T *>(slab), data_loc, range, place, user);
+            });
         } catch (...) {
             finish_profile(*ws);
             throw;
@@ -469,7 +491,7 @@ int sz3b_omp_assemble(int dtype, const sz3b_config *c, int nslabs, const unsigne
                       const size_t *conf_blob_sizes, const size_t *payload_sizes, const char *const *payloads,
                       char *cmp, size_t cmp_cap, size_t *cmp_size) {
     return guarded([&] {
-        check_dtype(dtype);
+        check_dtype_any(dtype);
         check_conf(c);
         size_t need = sz3b_omp_header_size(nslabs, conf_blob_sizes) + 256;
         for (int i = 0; i < nslabs; i++) need += payload_sizes[i];

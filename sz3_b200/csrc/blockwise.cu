@@ -380,5 +380,7 @@ const char *launch_reg_predict(const T *data, const BlockShape &bs, const T *c_r
                                                          cudaStream_t);
 SZ3B_INST_BW(float)
 SZ3B_INST_BW(double)
+SZ3B_INST_BW(int32_t)
+SZ3B_INST_BW(int64_t)
 
 }  // namespace sz3b

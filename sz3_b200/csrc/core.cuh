@@ -10,6 +10,8 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <math.h>
+#include <limits>
+#include <type_traits>
 
 #if defined(__CUDACC__)
 #define SZ_HD __host__ __device__ __forceinline__
@@ -65,6 +67,35 @@ SZ_HD double int_to_double(int q) {
 #endif
 }
 
+// double -> T as the reference's compiled code does it.  Floating T: a plain conversion.  Integer T (int32_t /
+// int64_t, tools/sz3/sz3.cpp:458-461): truncation, and x86's "integer indefinite" (the most negative value) where
+// the value does not fit -- CUDA's own conversion would saturate instead.
+template <class T>
+SZ_HD T from_double(double v) {
+    if constexpr (std::is_integral<T>::value) {
+        constexpr double lim = sizeof(T) == 4 ? 2147483648.0 : 9223372036854775808.0;
+        if (!(v > -lim - (sizeof(T) == 4 ? 1.0 : 0.0) && v < lim)) {
+            if (!(sizeof(T) == 8 && v == -lim)) return std::numeric_limits<T>::min();
+        }
+        return static_cast<T>(v);
+    } else {
+        return static_cast<T>(v);
+    }
+}
+// wrapping integer arithmetic (what the reference's signed overflow does in practice), plain arithmetic otherwise
+template <class T>
+struct Arith {
+    using U = T;
+};
+template <>
+struct Arith<int32_t> {
+    using U = uint32_t;
+};
+template <>
+struct Arith<int64_t> {
+    using U = uint64_t;
+};
+
 // quantize_and_overwrite.  Returns the shifted index (0 = unpredictable); recon receives the value the reference
 // leaves in the working array (the reconstruction, or the untouched original when unpredictable).
 template <class T>
@@ -72,7 +103,8 @@ SZ_HD int quantize(T data, T pred, const QuantParams &qp, T &recon) {
     // Straight-line form (selects instead of the reference's nested ifs): unpredictable points are rare, so nothing
     // is wasted, and the hot loops keep no divergent region.  NaN / overflow make `inrange` false (comparisons with
     // NaN are false) and whatever the arithmetic below produced is discarded.
-    const T diff = data - pred;
+    using U = typename Arith<T>::U;
+    const T diff = static_cast<T>(static_cast<U>(data) - static_cast<U>(pred));
     const double v = fabs(static_cast<double>(diff)) * qp.ebr;
     const bool inrange = v < qp.vmax;
     const int qi = trunc_to_int(v) + 1;   // garbage when !inrange (discarded)
@@ -80,10 +112,11 @@ SZ_HD int quantize(T data, T pred, const QuantParams &qp, T &recon) {
     const bool neg = diff < 0;
     const int q2 = neg ? -(half << 1) : (half << 1);
     const int shifted = neg ? qp.radius - half : qp.radius + half;
-    const T dec = static_cast<T>(static_cast<double>(pred) + int_to_double(q2) * qp.eb);
-    const T err = static_cast<T>(fabs(dec - data));
+    const T dec = from_double<T>(static_cast<double>(pred) + int_to_double(q2) * qp.eb);
+    // fabs(decompressed_data - data), stored back into a T (LinearQuantizer.hpp:60-61)
+    const T err = from_double<T>(fabs(static_cast<double>(static_cast<T>(static_cast<U>(dec) - static_cast<U>(data)))));
     bool ok;
-    if (sizeof(T) == 4)
+    if (std::is_same<T, float>::value)
         ok = static_cast<float>(err) <= qp.ebf;
     else
         ok = static_cast<double>(err) <= qp.eb;
@@ -122,36 +155,62 @@ SZ_HD int quantize_f32(float data, float pred, const QuantParams &qp, float &rec
 // recover (LinearQuantizer.hpp:74-86) for a predictable index.
 template <class T>
 SZ_HD T recover_pred(T pred, int q, const QuantParams &qp) {
-    return static_cast<T>(static_cast<double>(pred) + static_cast<double>(2 * (q - qp.radius)) * qp.eb);
+    return from_double<T>(static_cast<double>(pred) + static_cast<double>(2 * (q - qp.radius)) * qp.eb);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Interpolators (reference include/SZ3/utils/Interpolators.hpp:12-39); T arithmetic, left to right.
 // Divisions by 2/8/16 are exact scalings, written as multiplications by the exact reciprocal.
 // ---------------------------------------------------------------------------------------------------------------------
+// Integer T: the same expressions in (wrapping) integer arithmetic, the divisions truncating as in C++.
 template <class T>
 SZ_HD T interp_linear(T a, T b) {
-    return (a + b) * static_cast<T>(0.5);
+    if constexpr (std::is_integral<T>::value) {
+        using U = typename Arith<T>::U;
+        return static_cast<T>(static_cast<U>(a) + static_cast<U>(b)) / 2;
+    } else {
+        return (a + b) * static_cast<T>(0.5);
+    }
 }
 template <class T>
 SZ_HD T interp_linear1(T a, T b) {  // double arithmetic in the reference (-0.5 and 1.5 are double literals)
-    return static_cast<T>(-0.5 * static_cast<double>(a) + 1.5 * static_cast<double>(b));
+    return from_double<T>(-0.5 * static_cast<double>(a) + 1.5 * static_cast<double>(b));
 }
 template <class T>
 SZ_HD T interp_quad_1(T a, T b, T c) {
-    return (static_cast<T>(3) * a + static_cast<T>(6) * b - c) * static_cast<T>(0.125);
+    if constexpr (std::is_integral<T>::value) {
+        using U = typename Arith<T>::U;
+        return static_cast<T>(U(3) * U(a) + U(6) * U(b) - U(c)) / 8;
+    } else {
+        return (static_cast<T>(3) * a + static_cast<T>(6) * b - c) * static_cast<T>(0.125);
+    }
 }
 template <class T>
 SZ_HD T interp_quad_2(T a, T b, T c) {
-    return (-a + static_cast<T>(6) * b + static_cast<T>(3) * c) * static_cast<T>(0.125);
+    if constexpr (std::is_integral<T>::value) {
+        using U = typename Arith<T>::U;
+        return static_cast<T>(U(0) - U(a) + U(6) * U(b) + U(3) * U(c)) / 8;
+    } else {
+        return (-a + static_cast<T>(6) * b + static_cast<T>(3) * c) * static_cast<T>(0.125);
+    }
 }
 template <class T>
 SZ_HD T interp_quad_3(T a, T b, T c) {
-    return (static_cast<T>(3) * a - static_cast<T>(10) * b + static_cast<T>(15) * c) * static_cast<T>(0.125);
+    if constexpr (std::is_integral<T>::value) {
+        using U = typename Arith<T>::U;
+        return static_cast<T>(U(3) * U(a) - U(10) * U(b) + U(15) * U(c)) / 8;
+    } else {
+        return (static_cast<T>(3) * a - static_cast<T>(10) * b + static_cast<T>(15) * c) * static_cast<T>(0.125);
+    }
 }
 template <class T>
 SZ_HD T interp_cubic(T a, T b, T c, T d) {
-    return (-a + static_cast<T>(9) * b + static_cast<T>(9) * c - d) * static_cast<T>(0.0625);
+    if constexpr (std::is_integral<T>::value) {
+        using U = typename Arith<T>::U;
+        return static_cast<T>(U(0) - U(a) + U(9) * U(b) + U(9) * U(c) - U(d)) / 16;
+    } else {
+        return (-a + static_cast<T>(9) * b + static_cast<T>(9) * c - d) * static_cast<T>(0.0625);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -334,11 +334,19 @@ SZ3B_INST_DEC(float, uint16_t)
 SZ3B_INST_DEC(float, uint32_t)
 SZ3B_INST_DEC(double, uint16_t)
 SZ3B_INST_DEC(double, uint32_t)
+SZ3B_INST_DEC(int32_t, uint16_t)
+SZ3B_INST_DEC(int32_t, uint32_t)
+SZ3B_INST_DEC(int64_t, uint16_t)
+SZ3B_INST_DEC(int64_t, uint32_t)
 template void launch_zero_count<uint16_t>(const uint16_t *, uint64_t, unsigned *, unsigned *, cudaStream_t);
 template void launch_zero_count<uint32_t>(const uint32_t *, uint64_t, unsigned *, unsigned *, cudaStream_t);
 template void launch_reg_chain_recover<float>(const int32_t *, const float *, uint64_t, int, const QuantParams &,
                                               const QuantParams &, float *, cudaStream_t);
 template void launch_reg_chain_recover<double>(const int32_t *, const double *, uint64_t, int, const QuantParams &,
                                                const QuantParams &, double *, cudaStream_t);
+template void launch_reg_chain_recover<int32_t>(const int32_t *, const int32_t *, uint64_t, int, const QuantParams &,
+                                                const QuantParams &, int32_t *, cudaStream_t);
+template void launch_reg_chain_recover<int64_t>(const int32_t *, const int64_t *, uint64_t, int, const QuantParams &,
+                                                const QuantParams &, int64_t *, cudaStream_t);
 
 }  // namespace sz3b

@@ -590,5 +590,11 @@ SZ3B_INST_P(uint32_t, float)
 SZ3B_INST_P(uint32_t, double)
 SZ3B_INST_P(int32_t, float)
 SZ3B_INST_P(int32_t, double)
+SZ3B_INST_P(uint16_t, int32_t)
+SZ3B_INST_P(uint16_t, int64_t)
+SZ3B_INST_P(uint32_t, int32_t)
+SZ3B_INST_P(uint32_t, int64_t)
+SZ3B_INST_P(int32_t, int32_t)
+SZ3B_INST_P(int32_t, int64_t)
 
 }  // namespace sz3b

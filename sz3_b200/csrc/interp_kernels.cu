@@ -247,5 +247,16 @@ SZ3B_INST(float, uint16_t)
 SZ3B_INST(float, uint32_t)
 SZ3B_INST(double, uint16_t)
 SZ3B_INST(double, uint32_t)
+// integer element types (tools/sz3/sz3.cpp:458-461): the per-pass kernels only
+#define SZ3B_INST_GEN(T, QT)                                                                                     \
+    template void interp_launch_anchors<T, QT>(const InterpArgs<T, QT> &, uint32_t, uint64_t, uint32_t,        \
+                                               cudaStream_t);                                                   \
+    template void interp_launch_pass<T, QT>(const InterpArgs<T, QT> &, int, uint32_t, cudaStream_t);           \
+    template bool interp_launch_lean<T, QT>(const InterpArgs<T, QT> &, int, uint32_t, bool, bool, const T *,  \
+                                            cudaStream_t);
+SZ3B_INST_GEN(int32_t, uint16_t)
+SZ3B_INST_GEN(int32_t, uint32_t)
+SZ3B_INST_GEN(int64_t, uint16_t)
+SZ3B_INST_GEN(int64_t, uint32_t)
 
 }  // namespace sz3b

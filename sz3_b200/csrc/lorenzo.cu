@@ -321,5 +321,7 @@ void launch_widen_u8(const uint8_t *in, uint64_t n, int32_t *out, cudaStream_t s
                                           T *, cudaStream_t);
 SZ3B_INST_LZ(float)
 SZ3B_INST_LZ(double)
+SZ3B_INST_LZ(int32_t)
+SZ3B_INST_LZ(int64_t)
 
 }  // namespace sz3b

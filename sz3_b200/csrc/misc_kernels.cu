@@ -61,6 +61,20 @@ __device__ __forceinline__ void atomic_max_f<double>(double *addr, double v) {
     }
 }
 
+// integer element types: the hardware's own signed atomics
+template <>
+__device__ __forceinline__ void atomic_min_f<int32_t>(int32_t *addr, int32_t v) { atomicMin(addr, v); }
+template <>
+__device__ __forceinline__ void atomic_max_f<int32_t>(int32_t *addr, int32_t v) { atomicMax(addr, v); }
+template <>
+__device__ __forceinline__ void atomic_min_f<int64_t>(int64_t *addr, int64_t v) {
+    atomicMin(reinterpret_cast<long long *>(addr), static_cast<long long>(v));
+}
+template <>
+__device__ __forceinline__ void atomic_max_f<int64_t>(int64_t *addr, int64_t v) {
+    atomicMax(reinterpret_cast<long long *>(addr), static_cast<long long>(v));
+}
+
 // mm[0], mm[1] must be pre-set to data[0] (k_minmax_init)
 template <class T>
 __global__ void k_minmax_init(const T *__restrict__ data, T *__restrict__ mm) {
@@ -216,6 +230,14 @@ template void launch_gather_cubes<float>(const float *, int, const uint32_t *, u
                                          float *, cudaStream_t);
 template void launch_gather_cubes<double>(const double *, int, const uint32_t *, uint32_t, const uint64_t *, uint32_t,
                                           double *, cudaStream_t);
+#define SZ3B_INST_MISC_INT(T)                                                                                          \
+    template void launch_minmax<T>(const T *, uint64_t, T *, cudaStream_t);                                            \
+    template void launch_profile_blocks<T>(const T *, int, const uint32_t *, uint32_t, uint32_t, double, uint8_t *,    \
+                                           uint64_t, cudaStream_t);                                                    \
+    template void launch_gather_cubes<T>(const T *, int, const uint32_t *, uint32_t, const uint64_t *, uint32_t, T *, \
+                                         cudaStream_t);
+SZ3B_INST_MISC_INT(int32_t)
+SZ3B_INST_MISC_INT(int64_t)
 template void launch_widen<uint16_t>(const uint16_t *, uint64_t, int32_t *, cudaStream_t);
 template void launch_widen<uint32_t>(const uint32_t *, uint64_t, int32_t *, cudaStream_t);
 

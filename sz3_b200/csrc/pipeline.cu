@@ -437,7 +437,7 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
                 if (box && launch_box<T, QT>(A, bp, per_row, ws.st)) {
                     count_box(pl.table[L.table_off + b * per_row], b + 1 < L.nb[0] ? pl.table[L.table_off + (b + 1) * per_row] : lv_end);
                     flush_hist();   // counted while the next planes are still arriving
-                } else
+                } else if constexpr (std::is_floating_point<T>::value)
                     interp_launch_ltiles<T, QT>(A, per_row, nbatch, ws.st);
                 SZ3B_CUDA(cudaGetLastError());
                 (*launches)++;
@@ -447,14 +447,19 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
             continue;
         }
         if (pl.tile) {
-            if (box && launch_box<T, QT>(A, bp, L.nblocks, ws.st)) {
-                count_box(lv_begin, lv_end);
-            } else if (pl.variant == 2)
-                interp_launch_ltiles<T, QT>(A, L.nblocks, nbatch, ws.st);
-            else if (pl.variant == 1)
-                interp_launch_ftiles<T, QT>(A, L.nblocks, nbatch, ws.st);
-            else
-                interp_launch_tiles<T, QT>(A, L.nblocks, nbatch, ws.st);
+            // (the tile schedules are floating-point kernels; integer element types run the per-pass kernels)
+            if constexpr (std::is_floating_point<T>::value) {
+                if (box && launch_box<T, QT>(A, bp, L.nblocks, ws.st)) {
+                    count_box(lv_begin, lv_end);
+                } else if (pl.variant == 2)
+                    interp_launch_ltiles<T, QT>(A, L.nblocks, nbatch, ws.st);
+                else if (pl.variant == 1)
+                    interp_launch_ftiles<T, QT>(A, L.nblocks, nbatch, ws.st);
+                else
+                    interp_launch_tiles<T, QT>(A, L.nblocks, nbatch, ws.st);
+            } else {
+                fail(SZ3B_E_RUNTIME, "tile schedule planned for an integer element type");
+            }
             SZ3B_CUDA(cudaGetLastError());
             (*launches)++;
         } else {
@@ -464,8 +469,10 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
                 const bool write_work = !(L.s == 1 && p == pl.sh.N - 1);
                 // (tuner batches of small cubes stay on the point-mapped kernel: a CTA of the row-mapped one would
                 //  spend its time on the block table)
-                if (!(pl.lean && nbatch == 1 && interp_launch_lean<T, QT>(A, p, nbatch, write_work, false, nullptr, ws.st)))
-                    interp_launch_pass<T, QT>(A, p, nbatch, ws.st);
+                bool done = false;
+                if constexpr (std::is_floating_point<T>::value)
+                    done = pl.lean && nbatch == 1 && interp_launch_lean<T, QT>(A, p, nbatch, write_work, false, nullptr, ws.st);
+                if (!done) interp_launch_pass<T, QT>(A, p, nbatch, ws.st);
                 (*launches)++;
             }
         }
@@ -814,7 +821,9 @@ static size_t interp_compress_t(Workspace &ws, const sz3b_config &conf, const T 
         const char *e = getenv("SZ3B_SCHEDULE");
         return e ? atoi(e) : 0;
     }();
-    const int schedule = (forced == 1 || (forced >= 2 && forced <= 4 && conf.N == 3) || (forced == 5 && conf.N >= 3)) ? forced : 0;
+    const int schedule = std::is_integral<T>::value
+                             ? 1   // integer element types: the per-pass kernels (core.cuh carries their arithmetic)
+                             : ((forced == 1 || (forced >= 2 && forced <= 4 && conf.N == 3) || (forced == 5 && conf.N >= 3)) ? forced : 0);
     if (const char *e = build_interp_plan(conf, conf.absErrorBound, schedule, pl)) fail(SZ3B_E_INVALID_ARGUMENT, e);
     const int radius = conf.quantbinCnt / 2;
     const int nbins = 2 * radius;
@@ -1626,6 +1635,10 @@ template <class T>
 static size_t blockwise_compress(Workspace &ws, const sz3b_config &conf, const T *d_data, uint8_t *dst, size_t cap,
                                  int zstd_threads) {
     if (conf.quantbinCnt < 2) fail(SZ3B_E_INVALID_ARGUMENT, "quantbinCnt must be >= 2");
+    // integer element types: the Lorenzo predictors only (the coefficient chain machinery of the regression predictors
+    // -- speculation on a floating-point lattice, blockwise.cu -- is built for float / double)
+    if (std::is_integral<T>::value && (conf.regression || conf.regression2))
+        fail(SZ3B_E_UNSUPPORTED, "regression predictors on integer data are outside the GPU path (set regression = false)");
     if (conf.quantbinCnt / 2 <= 32768) return blockwise_compress_t<T, uint16_t>(ws, conf, d_data, dst, cap, zstd_threads);
     return blockwise_compress_t<T, uint32_t>(ws, conf, d_data, dst, cap, zstd_threads);
 }
@@ -2379,6 +2392,8 @@ static void blockwise_decompress_lorenzo(Workspace &ws, const sz3b_config &conf,
 template <class T, class QT>
 static void blockwise_decompress_t(Workspace &ws, const sz3b_config &conf, Cursor &c, T *d_out) {
     const int N = conf.N;
+    if (std::is_integral<T>::value && (conf.regression || conf.regression2))
+        fail(SZ3B_E_UNSUPPORTED, "regression predictors on integer data are outside the GPU path");
     if (conf.lorenzo || conf.lorenzo2) {
         blockwise_decompress_lorenzo<T, QT>(ws, conf, c, d_out);
         return;
@@ -2641,5 +2656,15 @@ void huffman_decode_stage(Workspace &ws, const uint8_t *in, size_t in_len, size_
                                                std::vector<uint8_t> &);
 SZ3B_INST_PIPE(float)
 SZ3B_INST_PIPE(double)
+// integer element types (tools/sz3/sz3.cpp:458-461): the whole-array entry points
+#define SZ3B_INST_PIPE_INT(T)                                                                                         \
+    template size_t compress_any<T>(Workspace &, sz3b_config &, const T *, int, uint8_t *, size_t);                  \
+    template double abs_eb_stage<T>(Workspace &, const sz3b_config &, const T *, int);                               \
+    template void minmax_stage<T>(Workspace &, const T *, int, size_t, double *, double *);                          \
+    template size_t compress_slab<T>(Workspace &, sz3b_config &, const T *, int, double, uint8_t *, size_t);         \
+    template size_t compress_slab_placed<T>(Workspace &, sz3b_config &, const T *, int, double, void *(*)(void *, size_t), void *); \
+    template void decompress_any<T>(Workspace &, sz3b_config &, const uint8_t *, size_t, T *, int);
+SZ3B_INST_PIPE_INT(int32_t)
+SZ3B_INST_PIPE_INT(int64_t)
 
 }  // namespace sz3b

@@ -53,7 +53,7 @@ def make_config(shape, **kw):
 
 
 def dtype_code(a):
-    return {np.dtype(np.float32): 0, np.dtype(np.float64): 1}[a.dtype]
+    return {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 7, np.dtype(np.int64): 9}[a.dtype]
 
 
 def _load(path):
