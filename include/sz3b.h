@@ -23,8 +23,8 @@ extern "C" {
 
 #define SZ3B_FLOAT 0  /* SZ_FLOAT,  include/SZ3/def.hpp */
 #define SZ3B_DOUBLE 1 /* SZ_DOUBLE */
-#define SZ3B_INT32 7  /* SZ_INT32: whole-array entry points only (compress, decompress, bounds, slabs), as          */
-#define SZ3B_INT64 9  /* SZ_INT64  tools/sz3/sz3.cpp:458-461 uses them; regression predictors excluded */
+#define SZ3B_INT32 7  /* SZ_INT32: whole-array entry points only (compress, decompress, bounds, slabs), */
+#define SZ3B_INT64 9  /* SZ_INT64  as tools/sz3/sz3.cpp:458-461 uses them                               */
 
 #define SZ3B_OK 0
 #define SZ3B_E_INVALID_ARGUMENT (-1) /* the reference throws std::invalid_argument */

@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(32) k_reg_chain(const T *__restrict__ c_fit, c
                                                   int32_t *__restrict__ coef_q, T *__restrict__ c_rec,
                                                   unsigned long long *__restrict__ n_sel_out,
                                                   unsigned long long *__restrict__ n_unpred,
-                                                  unsigned long long *__restrict__ unpred_pos, T *__restrict__ unpred_val) {
+                                                  unsigned long long *__restrict__ unpred_pos, T *__restrict__ unpred_val,
+                                                  const T *__restrict__ init, unsigned long long pos_base) {
     __shared__ T s_fit[kChainChunk * (kMaxDim + 1)];
     __shared__ T s_rec[kChainChunk * (kMaxDim + 1)];
     __shared__ int32_t s_q[kChainChunk * (kMaxDim + 1)];
@@ -50,12 +51,12 @@ __global__ void __launch_bounds__(32) k_reg_chain(const T *__restrict__ c_fit, c
     const int lane = threadIdx.x;
     const int nc = N + 1;
     const QuantParams qp = lane < N ? q_liner : q_indep;
-    T prev = 0;
+    T prev = init && lane < nc ? init[lane] : static_cast<T>(0);   // chain continued from an earlier launch
     uint64_t nsel = 0;   // selected blocks so far (same on every lane)
     for (uint64_t base = 0; base < nblocks; base += kChainChunk) {
         const uint32_t cnt = static_cast<uint32_t>(nblocks - base < kChainChunk ? nblocks - base : kChainChunk);
         for (uint32_t i = lane; i < cnt * nc; i += 32) s_fit[i] = c_fit[base * nc + i];
-        for (uint32_t i = lane; i < cnt; i += 32) s_sel[i] = sel[base + i];
+        for (uint32_t i = lane; i < cnt; i += 32) s_sel[i] = sel ? sel[base + i] : 1;   // no selection array: every block
         __syncwarp();
         uint32_t local_sel = 0;
         if (lane < nc) {
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(32) k_reg_chain(const T *__restrict__ c_fit, c
                 const int qv = quantize<T>(c, prev, qp, rec);
                 if (qv == 0) {
                     const unsigned long long slot = atomicAdd(n_unpred, 1ull);
-                    unpred_pos[slot] = (nsel + local_sel) * nc + lane;
+                    unpred_pos[slot] = pos_base + (nsel + local_sel) * nc + lane;
                     unpred_val[slot] = c;
                 }
                 s_q[local_sel * nc + lane] = qv;
@@ -344,12 +345,14 @@ void launch_reg_chain(const T *c_fit, const uint8_t *sel, uint64_t nblocks, int 
                       const QuantParams &q_indep, int32_t *coef_q, T *c_rec, unsigned long long *counters,
                       unsigned long long *unpred_pos, T *unpred_val, cudaStream_t st, const T *init,
                       unsigned long long pos_base) {
-    if (sel == nullptr)   // dense: every block selected
+    // dense (every block selected): the speculative chain -- its lattice arithmetic is floating point; integer element
+    // types walk the chain block by block with the plain quantizer
+    if (sel == nullptr && std::is_floating_point<T>::value)
         k_reg_chain_spec2<T><<<1, 32 * (N + 1), 0, st>>>(c_fit, nblocks, N, q_liner, q_indep, coef_q, c_rec, counters,
                                                         counters + 1, unpred_pos, unpred_val, init, pos_base);
     else
         k_reg_chain<T><<<1, 32, 0, st>>>(c_fit, sel, nblocks, N, q_liner, q_indep, coef_q, c_rec, counters, counters + 1,
-                                        unpred_pos, unpred_val);
+                                        unpred_pos, unpred_val, sel ? nullptr : init, sel ? 0ull : pos_base);
 }
 template <class T, class QT>
 const char *launch_reg_predict(const T *data, const BlockShape &bs, const T *c_rec, const QuantParams &qp, QT *q,

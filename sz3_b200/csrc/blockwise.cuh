@@ -56,6 +56,17 @@ SZ_HD void block_decode(const BlockShape &bs, uint64_t b, uint32_t bi[kMaxDim], 
 // RegressionPredictor::precompress (RegressionPredictor.hpp:28-55) for block b.  Returns false when the block has an
 // extent <= 1 (the reference then falls back to Lorenzo).  Sequential row-major sums on purpose: for T = double the
 // accumulation order decides the coefficient bits.
+// index[i] * (*c) of the fit (RegressionPredictor.hpp:44): a size_t times a T -- a product in T for floating T; for
+// integer T the value is converted to size_t first, so the product is an unsigned 64-bit one (negative values wrap;
+// reproduced as is), then widened to double for the sum.
+template <class T>
+SZ_HD double reg_index_times(uint32_t i, T v) {
+    if constexpr (std::is_integral<T>::value)
+        return static_cast<double>(static_cast<uint64_t>(i) * static_cast<uint64_t>(static_cast<int64_t>(v)));
+    else
+        return static_cast<double>(static_cast<T>(i) * v);
+}
+
 template <class T>
 SZ_HD bool reg_fit_block(const T *data, const BlockShape &bs, uint64_t b, T coef[kMaxDim + 1]) {
     uint32_t bi[kMaxDim], ext[kMaxDim];
@@ -72,19 +83,19 @@ SZ_HD bool reg_fit_block(const T *data, const BlockShape &bs, uint64_t b, T coef
             for (uint32_t i2 = 0; i2 < e2; i2++)
                 for (uint32_t i3 = 0; i3 < e3; i3++) {
                     const T v = data[off0 + i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3];
-                    sum[0] += static_cast<double>(static_cast<T>(i0) * v);   // index * value in T, accumulated in double
-                    if (bs.N > 1) sum[1] += static_cast<double>(static_cast<T>(i1) * v);
-                    if (bs.N > 2) sum[2] += static_cast<double>(static_cast<T>(i2) * v);
-                    if (bs.N > 3) sum[3] += static_cast<double>(static_cast<T>(i3) * v);
+                    sum[0] += reg_index_times<T>(i0, v);   // index * value in T, accumulated in double
+                    if (bs.N > 1) sum[1] += reg_index_times<T>(i1, v);
+                    if (bs.N > 2) sum[2] += reg_index_times<T>(i2, v);
+                    if (bs.N > 3) sum[3] += reg_index_times<T>(i3, v);
                     sum[bs.N] += static_cast<double>(v);
                 }
     double num = 1;
     for (int d = 0; d < bs.N; d++) num *= static_cast<double>(ext[d]);
-    coef[bs.N] = static_cast<T>(sum[bs.N] / num);
+    coef[bs.N] = from_double<T>(sum[bs.N] / num);
     for (int d = 0; d < bs.N; d++) {
         const double dd = static_cast<double>(ext[d]);
-        coef[d] = static_cast<T>((2 * sum[d] / (dd - 1) - sum[bs.N]) * 6 / num / (dd + 1));
-        coef[bs.N] = static_cast<T>(static_cast<double>(coef[bs.N]) - (dd - 1) * static_cast<double>(coef[d]) / 2);
+        coef[d] = from_double<T>((2 * sum[d] / (dd - 1) - sum[bs.N]) * 6 / num / (dd + 1));
+        coef[bs.N] = from_double<T>(static_cast<double>(coef[bs.N]) - (dd - 1) * static_cast<double>(coef[d]) / 2);
     }
     return true;
 }
@@ -160,11 +171,15 @@ SZ_HD void reg_row_locate(const BlockShape &bs, const RegRow &rr, uint32_t x, ui
 // RegressionPredictor::predict (RegressionPredictor.hpp:77-91), T arithmetic, left to right
 template <class T>
 SZ_HD T reg_predict(int N, const T *c, const uint32_t li[kMaxDim]) {
-    if (N == 1) return c[0] * static_cast<T>(li[0]) + c[1];
-    if (N == 2) return c[0] * static_cast<T>(li[0]) + c[1] * static_cast<T>(li[1]) + c[2];
-    if (N == 3) return c[0] * static_cast<T>(li[0]) + c[1] * static_cast<T>(li[1]) + c[2] * static_cast<T>(li[2]) + c[3];
-    return c[0] * static_cast<T>(li[0]) + c[1] * static_cast<T>(li[1]) + c[2] * static_cast<T>(li[2]) +
-           c[3] * static_cast<T>(li[3]) + c[4];
+    using U = typename Arith<T>::U;   // (integer T: size_t arithmetic in the reference, i.e. wrapping)
+    const U c0 = static_cast<U>(c[0]), c1 = static_cast<U>(c[1]);
+    if (N == 1) return static_cast<T>(c0 * static_cast<U>(li[0]) + c1);
+    const U c2 = static_cast<U>(c[2]);
+    if (N == 2) return static_cast<T>(c0 * static_cast<U>(li[0]) + c1 * static_cast<U>(li[1]) + c2);
+    const U c3 = static_cast<U>(c[3]);
+    if (N == 3) return static_cast<T>(c0 * static_cast<U>(li[0]) + c1 * static_cast<U>(li[1]) + c2 * static_cast<U>(li[2]) + c3);
+    return static_cast<T>(c0 * static_cast<U>(li[0]) + c1 * static_cast<U>(li[1]) + c2 * static_cast<U>(li[2]) +
+                          c3 * static_cast<U>(li[3]) + static_cast<U>(c[4]));
 }
 
 }  // namespace sz3b

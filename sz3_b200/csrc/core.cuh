@@ -121,6 +121,19 @@ SZ_HD int quantize(T data, T pred, const QuantParams &qp, T &recon) {
     else
         ok = static_cast<double>(err) <= qp.eb;
     ok = ok && inrange;
+    if constexpr (std::is_integral<T>::value) {
+        // |diff| / eb >= 2^63 (64-bit data a long way from its prediction, e.g. the wrapped sums of a regression fit):
+        // the reference's static_cast<int64_t> yields x86's indefinite value and its code carries on with it
+        // (LinearQuantizer.hpp:45-61): quant_index = INT64_MIN + 1 -> half_index 0, quant_index -2^63 either sign,
+        // and the point is accepted with index `radius` when the (wrapped) error test happens to pass.
+        if (!(v < 9223372036854775808.0)) {
+            const T dec2 = from_double<T>(static_cast<double>(pred) + -9223372036854775808.0 * qp.eb);
+            const T err2 = from_double<T>(fabs(static_cast<double>(static_cast<T>(static_cast<U>(dec2) - static_cast<U>(data)))));
+            const bool ok2 = static_cast<double>(err2) <= qp.eb;
+            recon = ok2 ? dec2 : data;
+            return ok2 ? qp.radius : 0;
+        }
+    }
     recon = ok ? dec : data;
     return ok ? shifted : 0;
 }

@@ -1635,10 +1635,6 @@ template <class T>
 static size_t blockwise_compress(Workspace &ws, const sz3b_config &conf, const T *d_data, uint8_t *dst, size_t cap,
                                  int zstd_threads) {
     if (conf.quantbinCnt < 2) fail(SZ3B_E_INVALID_ARGUMENT, "quantbinCnt must be >= 2");
-    // integer element types: the Lorenzo predictors only (the coefficient chain machinery of the regression predictors
-    // -- speculation on a floating-point lattice, blockwise.cu -- is built for float / double)
-    if (std::is_integral<T>::value && (conf.regression || conf.regression2))
-        fail(SZ3B_E_UNSUPPORTED, "regression predictors on integer data are outside the GPU path (set regression = false)");
     if (conf.quantbinCnt / 2 <= 32768) return blockwise_compress_t<T, uint16_t>(ws, conf, d_data, dst, cap, zstd_threads);
     return blockwise_compress_t<T, uint32_t>(ws, conf, d_data, dst, cap, zstd_threads);
 }
@@ -2392,8 +2388,6 @@ static void blockwise_decompress_lorenzo(Workspace &ws, const sz3b_config &conf,
 template <class T, class QT>
 static void blockwise_decompress_t(Workspace &ws, const sz3b_config &conf, Cursor &c, T *d_out) {
     const int N = conf.N;
-    if (std::is_integral<T>::value && (conf.regression || conf.regression2))
-        fail(SZ3B_E_UNSUPPORTED, "regression predictors on integer data are outside the GPU path");
     if (conf.lorenzo || conf.lorenzo2) {
         blockwise_decompress_lorenzo<T, QT>(ws, conf, c, d_out);
         return;

@@ -2,8 +2,8 @@
 sz3b_decompress against the UNMODIFIED reference: whole compressed files byte-identical (the streams here stay below
 the multi-frame threshold, so the lossless stage is the reference's own zstd call), both decoders agree bit for bit,
 the bound holds.  Covered: ALGO_INTERP and ALGO_INTERP_LORENZO (tuner, 1-D Lorenzo hand-over included) for N = 1..4,
-both interpolators, the Lorenzo stacks of ALGO_LORENZO_REG, REL bounds, the lossless fallbacks.  Regression
-predictors on integer data are outside the GPU path and must say so."""
+both interpolators, every predictor stack of ALGO_LORENZO_REG (Lorenzo, regression, composed), REL bounds, the lossless
+fallbacks."""
 import ctypes as C
 
 import numpy as np
@@ -89,13 +89,17 @@ def test_int_lossless_fallbacks(dtype):
     check(const, make_config(const.shape, cmprAlgo=ALGO_INTERP_LORENZO, errorBoundMode=EB_REL, relErrorBound=1e-3))   # range 0
 
 
-def test_int_regression_is_refused():
-    L = product_lib()
-    data = int_field((32, 32, 32), np.int32, 100.0)
-    conf = make_config(data.shape, cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1.0)
-    cap = L.sz3b_compress_bound(7, C.byref(conf))
-    out = np.empty(cap, dtype=np.uint8)
-    size = C.c_size_t(0)
-    rc = L.sz3b_compress(7, C.byref(conf), data.ctypes.data_as(C.c_void_p), 0, out.ctypes.data_as(C.c_char_p), C.c_size_t(cap),
-                         C.byref(size), None)
-    assert rc == -4 and b"regression" in L.sz3b_last_error()
+@needs_ref
+@pytest.mark.parametrize("dtype", [np.int32, np.int64])
+@pytest.mark.parametrize("shape,offset", [((40, 36, 50), 40000.0), ((40, 36, 50), 0.0), ((150, 130), 9000.0), ((6, 20, 22, 24), 50000.0)])
+@pytest.mark.parametrize("l1,l2,reg", [(0, 0, 1), (1, 0, 1), (1, 1, 1)])
+def test_int_regression_stacks(dtype, shape, offset, l1, l2, reg):
+    # The reference's fit multiplies a size_t index by the value (RegressionPredictor.hpp:44): negative integers wrap
+    # to ~2^64, the coefficients become x86's indefinite conversion results, and the quantizer's int64 cast overflows
+    # in turn (LinearQuantizer.hpp:45) -- the reference's own round trip then breaks the bound on a few points.  The
+    # GPU path reproduces all of it bit for bit (offset 0 = data with negative values); the bound is only asserted
+    # where the reference itself keeps it.
+    g = field_nd(shape, np.float64)
+    data = np.ascontiguousarray(np.rint(g * 3000.0 + offset).astype(dtype))
+    check(data, make_config(shape, cmprAlgo=ALGO_LORENZO_REG, absErrorBound=2.0, lorenzo=l1, lorenzo2=l2, regression=reg, regression2=0),
+          2.0 if offset > 0 else None)

@@ -61,7 +61,17 @@ def test_pysz_bytes_match_reference(pysz, dtype, scale, eb):
     config.errorBoundMode = pysz.szErrorBoundMode.ABS
     config.absErrorBound = eb
     compressed, _ = pysz.sz.compress(data, config)
-    theirs = ref_compress(data, make_config(data.shape, errorBoundMode=EB_ABS, absErrorBound=eb))
+    # the reference with the capacity pysz offers (2 x the array, sz.pyx:230): the capacity decides whether a nearly
+    # incompressible array stays on the lossy path or falls back to the lossless one (SZDispatcher.hpp:55-61)
+    import ctypes as C
+    from common import dtype_code
+    R = ref_lib()
+    rconf = make_config(data.shape, errorBoundMode=EB_ABS, absErrorBound=eb)
+    buf = np.empty(data.nbytes * 2, dtype=np.uint8)
+    R.ref_compress.restype = C.c_longlong
+    n = R.ref_compress(dtype_code(data), C.byref(rconf), data.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_char_p), C.c_size_t(buf.size))
+    assert n > 0
+    theirs = buf[:n].copy()
     assert compressed.size == theirs.size and np.array_equal(compressed, theirs)
     dec, conf = pysz.sz.decompress(theirs, dtype, data.shape)
     dec_ref, conf_ref = ref_decompress(theirs, data)
