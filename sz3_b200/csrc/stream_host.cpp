@@ -326,7 +326,10 @@ size_t zstd_compress_framed(const uint8_t *src, size_t src_len, uint8_t *dst, si
     const size_t kChunk = static_cast<size_t>(1) << 20;
     if (threads <= 1 || src_len < 2 * kChunk) {
         if (ready) ready->wait(src_len);
-        size_t r = ZSTD_compress(p, dst_cap - 8, src, src_len, 3);
+        // (a context kept per thread: the tuner's trial streams are a few hundred KB each, where creating and
+        //  clearing a fresh context costs as much as the compression; same bytes as ZSTD_compress)
+        if (!t_cctx) t_cctx = ZSTD_createCCtx();
+        size_t r = t_cctx ? ZSTD_compressCCtx(t_cctx, p, dst_cap - 8, src, src_len, 3) : ZSTD_compress(p, dst_cap - 8, src, src_len, 3);
         if (ZSTD_isError(r)) return 0;
         return r + 8;
     }

@@ -21,6 +21,7 @@ constexpr int kZhufThreads = 256;
 __global__ void __launch_bounds__(kZhufThreads) k_zhuf_build(const uint8_t *__restrict__ src, uint64_t len,
                                                              ZhufBlockInfo *__restrict__ infos, uint64_t g0) {
     __shared__ uint32_t hist[256];
+    __shared__ uint32_t hist4[4][256];   // per stream (the block's four segments): their sizes follow from the code
     __shared__ uint8_t ss[256];
     __shared__ uint32_t sf[256];
     __shared__ ZhufScratch scratch;
@@ -30,23 +31,44 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_build(const uint8_t *__re
     const uint32_t bl = zhuf_block_len(len, g);
     const uint8_t *p = src + g * kZhufBlock;
     const int tid = threadIdx.x;
-    hist[tid] = 0;
+    for (int s = 0; s < 4; s++) hist4[s][tid] = 0;
     if (tid < 4) bits[tid] = 0;
     __syncthreads();
     const uint32_t nvec = bl / 16;   // blocks start 16-byte aligned (the stream buffer is, and 128 KiB divides evenly)
+    const uint32_t seg = (bl + 3) / 4;
     const uint4 *pv = reinterpret_cast<const uint4 *>(p);
     for (uint32_t i = tid; i < nvec; i += kZhufThreads) {
         const uint4 v = pv[i];
         const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t at = i * 16;
+        uint32_t s = at / seg;   // a 16-byte group lies in one stream whenever seg is a multiple of 16 (full blocks)
+        if (s > 3) s = 3;
+        if ((at + 15) / seg == at / seg || s == 3) {
+            uint32_t *h = hist4[s];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            atomicAdd(&hist[wv[k] & 0xff], 1u);
-            atomicAdd(&hist[(wv[k] >> 8) & 0xff], 1u);
-            atomicAdd(&hist[(wv[k] >> 16) & 0xff], 1u);
-            atomicAdd(&hist[wv[k] >> 24], 1u);
+            for (int k = 0; k < 4; k++) {
+                atomicAdd(&h[wv[k] & 0xff], 1u);
+                atomicAdd(&h[(wv[k] >> 8) & 0xff], 1u);
+                atomicAdd(&h[(wv[k] >> 16) & 0xff], 1u);
+                atomicAdd(&h[wv[k] >> 24], 1u);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t sj = (at + 4 * k + b) / seg;
+                    atomicAdd(&hist4[sj > 3 ? 3 : sj][(wv[k] >> (8 * b)) & 0xff], 1u);
+                }
+            }
         }
     }
-    for (uint32_t i = nvec * 16 + tid; i < bl; i += kZhufThreads) atomicAdd(&hist[p[i]], 1u);
+    for (uint32_t i = nvec * 16 + tid; i < bl; i += kZhufThreads) {
+        const uint32_t sj = i / seg;
+        atomicAdd(&hist4[sj > 3 ? 3 : sj][p[i]], 1u);
+    }
+    __syncthreads();
+    hist[tid] = hist4[0][tid] + hist4[1][tid] + hist4[2][tid] + hist4[3][tid];
     __syncthreads();
     // rank sort by (count, symbol): thread s places symbol s
     const uint32_t mine = hist[tid];
@@ -62,35 +84,13 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_build(const uint8_t *__re
     const int n = __syncthreads_count(mine != 0);
     zhuf_build_table(ss, sf, n, scratch, info, tid, kZhufThreads);
     __syncthreads();
-    // bytes of the four streams under this code
-    const uint32_t seg = (bl + 3) / 4;
-    unsigned long long acc[4] = {0, 0, 0, 0};
-    for (uint32_t i = tid; i < nvec; i += kZhufThreads) {
-        const uint4 v = pv[i];
-        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-        const uint32_t at = i * 16;
-        uint32_t s = at / seg;   // a 16-byte group lies in one stream whenever seg is a multiple of 16 (full blocks)
-        if (s > 3) s = 3;
-        const bool whole = (at + 15) / seg == at / seg || s == 3;
-        uint32_t sum = 0;
+    // bits of the four streams under this code: per-stream symbol counts times code lengths (no second pass over the
+    // source)
+    unsigned long long acc[4];
+    {
+        const unsigned long long l = info.sym[tid] >> 16;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const uint32_t l = info.sym[(wv[k] >> (8 * b)) & 0xff] >> 16;
-                if (whole) {
-                    sum += l;
-                } else {
-                    uint32_t sj = (at + 4 * k + b) / seg;
-                    acc[sj > 3 ? 3 : sj] += l;
-                }
-            }
-        }
-        acc[s] += sum;
-    }
-    for (uint32_t i = nvec * 16 + tid; i < bl; i += kZhufThreads) {
-        uint32_t sj = i / seg;
-        acc[sj > 3 ? 3 : sj] += info.sym[p[i]] >> 16;
+        for (int s = 0; s < 4; s++) acc[s] = l * hist4[s][tid];
     }
 #pragma unroll
     for (int s = 0; s < 4; s++) {
