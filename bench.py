@@ -544,7 +544,12 @@ def run_ours(args):
             two_callers = {"error": str(ex)[:200]}
 
     other = None
+    decomp = None
     if world == 1 and extras:
+        try:
+            decomp = decompress_extra(L, torch, dev, make_conf(edge), host, args.steps)
+        except Exception as ex:
+            decomp = {"error": str(ex)[:300]}
         try:
             other = other_configs(L, torch)
         except Exception as ex:
@@ -602,6 +607,8 @@ def run_ours(args):
             line["container_check"] = container_check
         if other is not None:
             line["other_configs"] = other
+        if decomp is not None:
+            line["decompress"] = decomp
         if world == 1 and not args.no_cpu_baseline:
             lib, prefix, kind = cpu_checker()
             if lib is not None:
@@ -616,6 +623,64 @@ def run_ours(args):
     if world > 1:
         shared.close(dist)
         dist.destroy_process_group()
+
+
+def decompress_extra(L, torch, dev_in, cconf, original, steps):
+    """sz3b_decompress of the stream the timed leg wrote (512^3 float32, GPU lossless stage): output left in HBM
+    (`value`-like) and delivered to pinned host memory (`e2e`-like), per-stage times, the reference decoder's time on
+    the host cores for the same stream, and parity (both decoders return the same bits)."""
+    from common import Config
+    n = original.size
+    cap = L.sz3b_compress_bound(0, C.byref(cconf))
+    cmp_buf = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    cmp_ptr = cmp_buf.data_ptr()
+    size = C.c_size_t(0)
+    if L.sz3b_compress(0, C.byref(cconf), C.c_void_p(dev_in.data_ptr()), 1, C.c_void_p(cmp_ptr), C.c_size_t(cap), C.byref(size), None) != 0:
+        raise RuntimeError(L.sz3b_last_error().decode())
+    csize = size.value
+    dev_out = torch.empty(n, dtype=torch.float32, device="cuda")
+    host_out = torch.empty(n, dtype=torch.float32).pin_memory()
+    conf = Config()
+
+    def one(ptr, loc):
+        rc = L.sz3b_decompress(0, C.c_void_p(cmp_ptr), C.c_size_t(csize), C.c_void_p(ptr), loc, C.byref(conf))
+        if rc != 0:
+            raise RuntimeError(L.sz3b_last_error().decode())
+
+    def timed(ptr, loc):
+        for _ in range(2):
+            one(ptr, loc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one(ptr, loc)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    ms_dev = timed(dev_out.data_ptr(), 1)
+    names, ms, ln = (C.c_char_p * 64)(), (C.c_double * 64)(), (C.c_int * 64)()
+    k = L.sz3b_last_profile(names, ms, ln, 64)
+    stages = {}
+    for i in range(k):
+        stages[names[i].decode()] = round(stages.get(names[i].decode(), 0.0) + ms[i], 4)
+    ms_host = timed(host_out.data_ptr(), 0)
+    r = {"workload": "a stream of the bench workload (512^3 float32, abs 1e-3, default lossless policy)", "compressed_bytes": csize,
+         "ms_device_resident": ms_dev, "ms_pinned_host": ms_host,
+         "GBps_device_resident": n * 4 / ms_dev / 1e6, "GBps_pinned_host": n * 4 / ms_host / 1e6, "stages_ms": stages}
+    lib, prefix, kind = cpu_checker()
+    if lib is not None:
+        dec = np.empty(n, dtype=np.float32)
+        t0 = time.perf_counter()
+        rc, _ = cpu_decompress(lib, prefix, cmp_ptr, csize, dec)
+        t_ref = time.perf_counter() - t0
+        same = bool(rc == 0 and np.array_equal(dec.view(np.uint32), host_out.numpy().view(np.uint32)))
+        r["reference"] = {"ms": t_ref * 1e3, "GBps": n * 4 / t_ref / 1e9, "kind": kind, "threads": 1,
+                          "note": "SZ_decompress of the same stream (the reference decodes a single stream on one thread)"}
+        r["parity"] = {"same_bits_as_reference_decoder": same,
+                       "max_abs_error": float(np.max(np.abs(dec.astype(np.float64) - original.reshape(-1).astype(np.float64))))}
+    return r
 
 
 def other_configs(L, torch):

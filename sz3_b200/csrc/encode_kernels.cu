@@ -547,9 +547,114 @@ void launch_minmax_int(const QT *q, uint64_t n, int *mm, cudaStream_t st) {
     k_minmax_int<QT><<<static_cast<unsigned>(blocks), 256, 0, st>>>(q, n, mm);
 }
 
+// Long inputs (the Huffman decoder's 10^5 .. 10^6 subsequence counts): three launches instead of one CTA walking over
+// everything -- sums of 4096-element tiles, their scan (k_pack_scan over the tile sums), then every tile scans itself
+// from its own offset.
+constexpr int kScanTile = 4096;
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(const unsigned *__restrict__ a, const unsigned *__restrict__ b, uint64_t n,
+                                                         unsigned *__restrict__ sa, unsigned *__restrict__ sb) {
+    __shared__ unsigned w[2][32];
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kScanTile + 4ull * threadIdx.x;
+    unsigned va = 0, vb = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (i + k < n) {
+            va += a[i + k];
+            vb += b[i + k];
+        }
+    }
+    va = __reduce_add_sync(0xffffffffu, va);
+    vb = __reduce_add_sync(0xffffffffu, vb);
+    if ((threadIdx.x & 31) == 0) {
+        w[0][threadIdx.x >> 5] = va;
+        w[1][threadIdx.x >> 5] = vb;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        va = __reduce_add_sync(0xffffffffu, w[0][threadIdx.x]);
+        vb = __reduce_add_sync(0xffffffffu, w[1][threadIdx.x]);
+        if (threadIdx.x == 0) {
+            sa[blockIdx.x] = va;   // (a tile's sum fits 32 bits wherever its elements' sum does: chunk bit counts
+            sb[blockIdx.x] = vb;   //  are < 2^18 each, symbol counts < 2^11)
+        }
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_tiles(const unsigned *__restrict__ a, const unsigned *__restrict__ b, uint64_t n,
+                                                     const unsigned long long *__restrict__ ta,
+                                                     const unsigned long long *__restrict__ tb, uint64_t ntiles,
+                                                     unsigned long long *__restrict__ oa, unsigned long long *__restrict__ ob) {
+    __shared__ unsigned long long wsum[2][32];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kScanTile + 4ull * threadIdx.x;
+    unsigned x[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = i + k < n ? a[i + k] : 0u;
+        y[k] = i + k < n ? b[i + k] : 0u;
+    }
+    const unsigned long long v0 = static_cast<unsigned long long>(x[0]) + x[1] + x[2] + x[3];
+    const unsigned long long v1 = static_cast<unsigned long long>(y[0]) + y[1] + y[2] + y[3];
+    unsigned long long inc0 = v0, inc1 = v1;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t0 = __shfl_up_sync(0xffffffffu, inc0, o);
+        unsigned long long t1 = __shfl_up_sync(0xffffffffu, inc1, o);
+        if (lane >= static_cast<unsigned>(o)) {
+            inc0 += t0;
+            inc1 += t1;
+        }
+    }
+    if (lane == 31) {
+        wsum[0][wid] = inc0;
+        wsum[1][wid] = inc1;
+    }
+    __syncthreads();
+    unsigned long long w0 = wsum[0][lane], w1 = wsum[1][lane];
+    unsigned long long a0 = w0, a1 = w1;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t0 = __shfl_up_sync(0xffffffffu, a0, o);
+        unsigned long long t1 = __shfl_up_sync(0xffffffffu, a1, o);
+        if (lane >= static_cast<unsigned>(o)) {
+            a0 += t0;
+            a1 += t1;
+        }
+    }
+    unsigned long long e0 = ta[blockIdx.x] + __shfl_sync(0xffffffffu, a0 - w0, wid) + inc0 - v0;
+    unsigned long long e1 = tb[blockIdx.x] + __shfl_sync(0xffffffffu, a1 - w1, wid) + inc1 - v1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (i + k < n) {
+            oa[i + k] = e0;
+            ob[i + k] = e1;
+        }
+        e0 += x[k];
+        e1 += y[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        oa[n] = ta[ntiles];
+        ob[n] = tb[ntiles];
+    }
+}
+
+// 64-bit words of scratch launch_scan_chunks wants for `nchunks` elements (0: the single-CTA scan does it)
+size_t scan_scratch_words(uint64_t nchunks) {
+    if (nchunks <= 4 * static_cast<uint64_t>(kScanTile)) return 0;
+    const uint64_t ntiles = (nchunks + kScanTile - 1) / kScanTile;
+    return static_cast<size_t>(2 * (ntiles + 1) + ntiles + 1);
+}
+
 void launch_scan_chunks(const unsigned *chunk_bits, const unsigned *chunk_zeros, uint64_t nchunks, unsigned long long *bit_off,
-                        unsigned long long *zero_off, cudaStream_t st) {
-    k_pack_scan<<<1, 1024, 0, st>>>(chunk_bits, chunk_zeros, nchunks, bit_off, zero_off);
+                        unsigned long long *zero_off, cudaStream_t st, unsigned long long *scratch) {
+    if (scratch == nullptr || scan_scratch_words(nchunks) == 0) {
+        k_pack_scan<<<1, 1024, 0, st>>>(chunk_bits, chunk_zeros, nchunks, bit_off, zero_off);
+        return;
+    }
+    const uint64_t ntiles = (nchunks + kScanTile - 1) / kScanTile;
+    // scratch: offsets of the tiles (2 x u64, one extra entry each for the totals), then their sums (2 x u32)
+    unsigned long long *ta = scratch, *tb = ta + ntiles + 1;
+    unsigned *sa = reinterpret_cast<unsigned *>(tb + ntiles + 1), *sb = sa + ntiles;
+    k_scan_tile_sums<<<static_cast<unsigned>(ntiles), 1024, 0, st>>>(chunk_bits, chunk_zeros, nchunks, sa, sb);
+    k_pack_scan<<<1, 1024, 0, st>>>(sa, sb, ntiles, ta, tb);
+    k_scan_tiles<<<static_cast<unsigned>(ntiles), 1024, 0, st>>>(chunk_bits, chunk_zeros, nchunks, ta, tb, ntiles, bit_off, zero_off);
 }
 
 uint64_t pack_num_chunks(uint64_t n) { return (n + kPackChunk - 1) / kPackChunk; }
@@ -558,7 +663,7 @@ template <class QT, class T>
 void launch_pack(const QT *q, uint64_t n, int sym_min, int zero_sym, const uint8_t *len,
                  const unsigned long long *code, unsigned nstates, int center_state, unsigned *chunk_bits,
                  unsigned *chunk_zeros, unsigned long long *bit_off, unsigned long long *zero_off, unsigned *out_words,
-                 const T *unpred_tmp, T *unpred_out, cudaStream_t st, cudaEvent_t after_scan) {
+                 const T *unpred_tmp, T *unpred_out, cudaStream_t st, cudaEvent_t after_scan, unsigned long long *scan_scratch) {
     const uint64_t nchunks = pack_num_chunks(n);
     if (nchunks == 0) return;
     const bool vec = (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
@@ -568,7 +673,7 @@ void launch_pack(const QT *q, uint64_t n, int sym_min, int zero_sym, const uint8
     const unsigned g2 = static_cast<unsigned>(nchunks < 148u * 4u ? nchunks : 148u * 4u);
     k_pack_count<QT><<<g1, kPackThreads, 0, st>>>(q, n, sym_min, zero_sym, len, code, wlo, nstates, vec, nchunks, chunk_bits,
                                                   chunk_zeros);
-    k_pack_scan<<<1, 1024, 0, st>>>(chunk_bits, chunk_zeros, nchunks, bit_off, zero_off);
+    launch_scan_chunks(chunk_bits, chunk_zeros, nchunks, bit_off, zero_off, st, scan_scratch);
     if (after_scan) cudaEventRecord(after_scan, st);
     k_pack_write<QT, T><<<g2, kPackThreads, 0, st>>>(q, n, sym_min, zero_sym, len, code, wlo, nstates, vec, nchunks, bit_off,
                                                      zero_off, out_words, unpred_tmp, unpred_out);
@@ -583,7 +688,8 @@ SZ3B_INST_Q(int32_t)
 #define SZ3B_INST_P(QT, T)                                                                                           \
     template void launch_pack<QT, T>(const QT *, uint64_t, int, int, const uint8_t *, const unsigned long long *,    \
                                      unsigned, int, unsigned *, unsigned *, unsigned long long *,                   \
-                                     unsigned long long *, unsigned *, const T *, T *, cudaStream_t, cudaEvent_t);
+                                     unsigned long long *, unsigned *, const T *, T *, cudaStream_t, cudaEvent_t,   \
+                                     unsigned long long *);
 SZ3B_INST_P(uint16_t, float)
 SZ3B_INST_P(uint16_t, double)
 SZ3B_INST_P(uint32_t, float)

@@ -37,7 +37,8 @@ struct HdTables {
     int offset;              // HuffmanEncoder::offset
 };
 
-// MSB-first bit reader over big-endian 32-bit words (the stream is copied to a 4-byte aligned, zero-padded buffer)
+// MSB-first bit reader over big-endian 32-bit words.  `words` is 4-byte aligned and the stream starts `shift` bits
+// (0, 8, 16 or 24) into it -- the stream sits wherever the assembled file put it; readable zero padding follows it.
 struct BitReader {
     const uint32_t *words;
     uint64_t acc;      // next bits, left aligned
@@ -91,8 +92,8 @@ __device__ __forceinline__ uint32_t hd_symbol(BitReader &br, const uint32_t *slu
 // successors of the subsequences whose overshoot moved in the previous round (list_in, n_in entries).  `over` is updated
 // in place: a reader may see its predecessor's overshoot of this or of the previous round, but a predecessor that moves
 // is listed, so its successor runs again in the next round and the loop can only stop at the fixed point.
-__global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restrict__ words, uint64_t total_bits, uint64_t nsub,
-                                                       HdTables t, uint8_t *over, const uint32_t *__restrict__ list_in,
+__global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restrict__ words, unsigned shift, uint64_t total_bits,
+                                                       uint64_t nsub, HdTables t, uint8_t *over, const uint32_t *__restrict__ list_in,
                                                        uint64_t n_in, uint32_t *__restrict__ list_out,
                                                        unsigned *__restrict__ counts, unsigned long long *__restrict__ n_out) {
     __shared__ uint32_t slut[1 << kHdLutBits];
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restri
     unsigned cnt = 0;
     if (pos < limit) {
         BitReader br;
-        br.init(words, pos);
+        br.init(words, pos + shift);
         while (pos < limit) {
             int len;
             hd_symbol(br, slut, t, &len);
@@ -130,13 +131,23 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_sync(const uint32_t *__restri
     }
 }
 
+// Final pass: every subsequence is decoded once more from its exact start and its symbols are written.  A thread's
+// symbols are contiguous in the output (offs[i] onwards), so they leave in groups of 16 bytes (8 or 4 symbols gathered
+// in two 64-bit registers, aligned stores; scalar stores up to the first aligned position and for the tail): one
+// 16-byte store per eight symbols instead of eight 2-byte stores that each dirty a sector of their own.  Codes inside
+// the first-level table take their symbol from a table in shared memory as well (no node -> symbol load from global).
 template <class QT>
-__global__ void __launch_bounds__(kHdThreads) k_hd_write(const uint32_t *__restrict__ words, uint64_t total_bits, uint64_t nsub,
-                                                        HdTables t, const uint8_t *__restrict__ over,
+__global__ void __launch_bounds__(kHdThreads) k_hd_write(const uint32_t *__restrict__ words, unsigned shift, uint64_t total_bits,
+                                                        uint64_t nsub, HdTables t, const uint8_t *__restrict__ over,
                                                         const unsigned long long *__restrict__ offs, uint64_t n,
                                                         QT *__restrict__ out) {
     __shared__ uint32_t slut[1 << kHdLutBits];
-    for (int k = threadIdx.x; k < (1 << kHdLutBits); k += blockDim.x) slut[k] = t.lut[k];
+    __shared__ QT ssym[1 << kHdLutBits];
+    for (int k = threadIdx.x; k < (1 << kHdLutBits); k += blockDim.x) {
+        const uint32_t e = t.lut[k];
+        slut[k] = e;
+        ssym[k] = (e >> 24) ? static_cast<QT>(t.C[e & 0xffffffu] + t.offset) : static_cast<QT>(0);
+    }
     __syncthreads();
     const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= nsub) return;
@@ -145,40 +156,81 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_write(const uint32_t *__restr
     if (limit > total_bits) limit = total_bits;
     uint64_t o = offs[i];
     if (pos >= limit) return;
+    constexpr int kSymBits = 8 * static_cast<int>(sizeof(QT));
+    constexpr int kPerWord = 64 / kSymBits;   // symbols per 64-bit register: 4 or 2
+    constexpr int kGroup = 2 * kPerWord;      // symbols per 16-byte store
+    unsigned long long lo = 0, hi = 0;
+    int nb = 0;   // symbols gathered; the group starts at out[o]
     BitReader br;
-    br.init(words, pos);
-    while (pos < limit && o < n) {
-        int len;
-        const uint32_t node = hd_symbol(br, slut, t, &len);
-        out[o++] = static_cast<QT>(t.C[node] + t.offset);
+    br.init(words, pos + shift);
+    while (pos < limit && o + nb < n) {
+        br.refill();
+        const uint32_t idx = static_cast<uint32_t>(br.acc >> (64 - kHdLutBits));
+        const uint32_t e = slut[idx];
+        uint32_t len = e >> 24;
+        unsigned long long sym;
+        if (len) {
+            sym = ssym[idx];
+            br.skip(static_cast<int>(len));
+        } else {   // code longer than the table: walk on bit by bit
+            uint32_t node = e & 0xffffffu;
+            br.skip(kHdLutBits);
+            len = kHdLutBits;
+            for (;;) {
+                br.refill();
+                node = (br.acc >> 63) ? t.R[node] : t.L[node];
+                br.skip(1);
+                len++;
+                if (t.leaf[node] || len >= 96) break;
+            }
+            sym = static_cast<QT>(t.C[node] + t.offset);
+        }
         pos += len;
+        if (nb == 0 && (o & (kGroup - 1)) != 0) {   // not yet at a 16-byte boundary of the output
+            out[o++] = static_cast<QT>(sym);
+            continue;
+        }
+        if (nb < kPerWord)
+            lo |= sym << (kSymBits * nb);
+        else
+            hi |= sym << (kSymBits * (nb - kPerWord));
+        if (++nb == kGroup) {
+            *reinterpret_cast<ulonglong2 *>(out + o) = make_ulonglong2(lo, hi);
+            o += kGroup;
+            nb = 0;
+            lo = hi = 0;
+        }
+    }
+    for (int k = 0; k < nb; k++) {
+        const unsigned long long w = k < kPerWord ? lo >> (kSymBits * k) : hi >> (kSymBits * (k - kPerWord));
+        out[o + k] = static_cast<QT>(w);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 uint64_t hd_num_sub(uint64_t total_bits) { return (total_bits + kSubBits - 1) / kSubBits; }
 
-void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, uint8_t *over, const uint32_t *list_in,
+void launch_hd_sync(const uint32_t *words, unsigned shift, uint64_t total_bits, const HdDeviceTables &tb, uint8_t *over, const uint32_t *list_in,
                     uint64_t n_in, uint32_t *list_out, unsigned *counts, unsigned long long *n_out, cudaStream_t st) {
     const uint64_t nsub = hd_num_sub(total_bits);
     const uint64_t nthreads = list_in ? n_in : nsub;
     if (nthreads == 0) return;
     HdTables t{tb.lut, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
-    k_hd_sync<<<static_cast<unsigned>((nthreads + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, total_bits, nsub, t, over,
-                                                                                                 list_in, n_in, list_out, counts, n_out);
+    k_hd_sync<<<static_cast<unsigned>((nthreads + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, shift, total_bits, nsub, t,
+                                                                                                 over, list_in, n_in, list_out, counts, n_out);
 }
 
 template <class QT>
-void launch_hd_write(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over,
+void launch_hd_write(const uint32_t *words, unsigned shift, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over,
                      const unsigned long long *offs, uint64_t n, QT *out, cudaStream_t st) {
     const uint64_t nsub = hd_num_sub(total_bits);
     HdTables t{tb.lut, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
-    k_hd_write<QT><<<static_cast<unsigned>((nsub + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, total_bits, nsub, t, over,
-                                                                                                  offs, n, out);
+    k_hd_write<QT><<<static_cast<unsigned>((nsub + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, shift, total_bits, nsub, t,
+                                                                                                  over, offs, n, out);
 }
-template void launch_hd_write<uint16_t>(const uint32_t *, uint64_t, const HdDeviceTables &, const uint8_t *,
+template void launch_hd_write<uint16_t>(const uint32_t *, unsigned, uint64_t, const HdDeviceTables &, const uint8_t *,
                                         const unsigned long long *, uint64_t, uint16_t *, cudaStream_t);
-template void launch_hd_write<uint32_t>(const uint32_t *, uint64_t, const HdDeviceTables &, const uint8_t *,
+template void launch_hd_write<uint32_t>(const uint32_t *, unsigned, uint64_t, const HdDeviceTables &, const uint8_t *,
                                         const unsigned long long *, uint64_t, uint32_t *, cudaStream_t);
 
 }  // namespace sz3b

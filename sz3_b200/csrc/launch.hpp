@@ -64,7 +64,8 @@ template <class QT, class T>
 void launch_pack(const QT *q, uint64_t n, int sym_min, int zero_sym, const uint8_t *len,
                  const unsigned long long *code, unsigned nstates, int center_state, unsigned *chunk_bits,
                  unsigned *chunk_zeros, unsigned long long *bit_off, unsigned long long *zero_off, unsigned *out_words,
-                 const T *unpred_tmp, T *unpred_out, cudaStream_t st, cudaEvent_t after_scan);
+                 const T *unpred_tmp, T *unpred_out, cudaStream_t st, cudaEvent_t after_scan,
+                 unsigned long long *scan_scratch = nullptr);
 
 // blockwise.cu
 struct BlockShape;
@@ -118,8 +119,11 @@ void launch_reg_chain_recover(const int32_t *coef_q, const T *coef_unp, uint64_t
 template <class T, class QT>
 const char *launch_reg_recover(T *out, const BlockShape &bs, const T *c_rec, const QuantParams &qp, const QT *q,
                                const T *unpred_tmp, cudaStream_t st);
+// exclusive scans of two arrays of 32-bit counts into 64-bit offsets (nchunks + 1 entries each, the last = total); with
+// `scratch` (scan_scratch_words(nchunks) 64-bit words) long inputs are scanned by tiles over the whole GPU
+size_t scan_scratch_words(uint64_t nchunks);
 void launch_scan_chunks(const unsigned *chunk_bits, const unsigned *chunk_zeros, uint64_t nchunks, unsigned long long *bit_off,
-                        unsigned long long *zero_off, cudaStream_t st);   // encode_kernels.cu (k_pack_scan)
+                        unsigned long long *zero_off, cudaStream_t st, unsigned long long *scratch = nullptr);   // encode_kernels.cu (k_pack_scan)
 
 // zhuf_kernels.cu: the GPU lossless stage (zstd frames of Huffman-only literal blocks, zhuf.cuh)
 struct ZhufBlockInfo;
@@ -136,10 +140,10 @@ struct HdDeviceTables {
     int offset;
 };
 uint64_t hd_num_sub(uint64_t total_bits);
-void launch_hd_sync(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, uint8_t *over, const uint32_t *list_in,
+void launch_hd_sync(const uint32_t *words, unsigned shift, uint64_t total_bits, const HdDeviceTables &tb, uint8_t *over, const uint32_t *list_in,
                     uint64_t n_in, uint32_t *list_out, unsigned *counts, unsigned long long *n_out, cudaStream_t st);
 template <class QT>
-void launch_hd_write(const uint32_t *words, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over,
+void launch_hd_write(const uint32_t *words, unsigned shift, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over,
                      const unsigned long long *offs, uint64_t n, QT *out, cudaStream_t st);
 
 // misc_kernels.cu

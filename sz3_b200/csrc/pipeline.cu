@@ -541,7 +541,7 @@ static void encode_indices(Workspace &ws, const QT *d_q, uint64_t n, const unsig
     unsigned *d_cb = ws.chunk_bits.as<unsigned>(nchunks + 1);
     unsigned *d_cz = ws.chunk_zeros.as<unsigned>(nchunks + 1);
     unsigned long long *d_bo = ws.bit_off.as<unsigned long long>(nchunks + 2);
-    unsigned long long *d_zo = ws.zero_off.as<unsigned long long>(nchunks + 2);
+    unsigned long long *d_zo = ws.zero_off.as<unsigned long long>(nchunks + 2 + scan_scratch_words(nchunks));
     const size_t nwords = (book.total_bits + 31) / 32 + 2;
     unsigned *d_words = ws.out_words.as<unsigned>(nwords);
     SZ3B_CUDA(cudaMemsetAsync(d_words, 0, nwords * sizeof(unsigned), ws.st));
@@ -551,7 +551,8 @@ static void encode_indices(Workspace &ws, const QT *d_q, uint64_t n, const unsig
     for (size_t k = 0; k < states && book.offset - sym_base + k < static_cast<size_t>(nbins); k++)
         if (h_hist[book.offset - sym_base + k] > h_hist[book.offset - sym_base + top]) top = k;
     launch_pack<QT, T>(d_q, n, book.offset, 0, d_len, d_code, static_cast<unsigned>(states), static_cast<int>(top), d_cb, d_cz,
-                       d_bo, d_zo, d_words, d_unpred_tmp, d_unpred_out, ws.st, nullptr);
+                       d_bo, d_zo, d_words, d_unpred_tmp, d_unpred_out, ws.st, nullptr,
+                       scan_scratch_words(nchunks) ? d_zo + nchunks + 2 : nullptr);
     SZ3B_CUDA(cudaGetLastError());
     ws.stage_end(h, 3);
 }
@@ -2134,7 +2135,7 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     const uint64_t enc_len = c.get<uint64_t>();
     const uint8_t *bits = c.take(enc_len);
     const uint64_t total_bits = enc_len * 8;
-    size_t h = ws.stage_begin("huffman_decode");
+    size_t h = ws.stage_begin("huffman_decode_upload");
     // tables: lut | L | R | C | leaf
     const uint32_t nc = dec.nc;
     const size_t lut_n = dec.lut.size();
@@ -2149,11 +2150,21 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     ws.h2d(d_R, dec.R.data(), nc * 4);
     ws.h2d(d_C, dec.C.data(), nc * 4);
     ws.h2d(d_leaf, dec.leaf.data(), nc);
-    // bitstream, 4-byte aligned and zero padded
-    const size_t padded = (enc_len + 3) / 4 * 4 + 64;
-    uint8_t *d_bits = ws.hd_bits.as<uint8_t>(padded);
-    SZ3B_CUDA(cudaMemsetAsync(d_bits + enc_len / 4 * 4, 0, padded - enc_len / 4 * 4, ws.st));
-    ws.h2d(d_bits, bits, enc_len);
+    // bitstream: already in device memory when the decoded file was mirrored there (decompress_one), wherever the file
+    // has it -- the readers take a 4-byte aligned base and a bit shift; otherwise uploaded here, aligned, zero padded
+    const uint8_t *d_bits;
+    unsigned bit_shift = 0;
+    if (ws.raw_dev && bits >= ws.raw_host) {
+        const size_t off = static_cast<size_t>(bits - ws.raw_host);
+        d_bits = ws.raw_dev + (off & ~static_cast<size_t>(3));
+        bit_shift = static_cast<unsigned>(off & 3) * 8;
+    } else {
+        const size_t padded = (enc_len + 3) / 4 * 4 + 64;
+        uint8_t *d = ws.hd_bits.as<uint8_t>(padded);
+        SZ3B_CUDA(cudaMemsetAsync(d + enc_len / 4 * 4, 0, padded - enc_len / 4 * 4, ws.st));
+        ws.h2d(d, bits, enc_len);
+        d_bits = d;
+    }
     const uint64_t nsub = hd_num_sub(total_bits);
     if (nsub >= 0xfffffff0ull) fail(SZ3B_E_UNSUPPORTED, "Huffman stream above 2^42 bits");
     // overshoots (1 byte each), then two work lists of subsequence indices (ping-pong)
@@ -2161,10 +2172,12 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     uint8_t *d_over = ws.hd_over.as<uint8_t>(over_bytes + 2 * (nsub + 1) * sizeof(uint32_t));
     uint32_t *list_a = reinterpret_cast<uint32_t *>(d_over + over_bytes), *list_b = list_a + nsub + 1;
     unsigned *d_counts = ws.hd_counts.as<unsigned>(nsub + 2);
-    unsigned long long *d_offs = ws.hd_offs.as<unsigned long long>(2 * (nsub + 2));
+    unsigned long long *d_offs = ws.hd_offs.as<unsigned long long>(2 * (nsub + 2) + scan_scratch_words(nsub));
     unsigned long long *d_moved = ws.counters.as<unsigned long long>(4);
     SZ3B_CUDA(cudaMemsetAsync(d_over, 0, over_bytes, ws.st));
     HdDeviceTables tb{d_lut, d_L, d_R, d_C, d_leaf, dec.offset};
+    ws.stage_end(h, 0);
+    h = ws.stage_begin("huffman_decode_sync");
     uint8_t *in = d_over;
     int launches = 0;
     bool converged = false;
@@ -2172,7 +2185,7 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     // every round makes at least the first not yet exact subsequence exact, so nsub rounds always suffice
     for (uint64_t round = 1; round <= nsub + 1 && !converged; round++) {
         SZ3B_CUDA(cudaMemsetAsync(d_moved, 0, sizeof(unsigned long long), ws.st));
-        launch_hd_sync(reinterpret_cast<const uint32_t *>(d_bits), total_bits, tb, in, round == 1 ? nullptr : list_a, n_in, list_b,
+        launch_hd_sync(reinterpret_cast<const uint32_t *>(d_bits), bit_shift, total_bits, tb, in, round == 1 ? nullptr : list_a, n_in, list_b,
                        d_counts, d_moved, ws.st);
         launches++;
         // read back through pinned memory (a pageable readback costs more than a late round itself)
@@ -2187,13 +2200,15 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     if (getenv("SZ3B_VERBOSE")) fprintf(stderr, "[sz3b] huffman decode: %d synchronisation rounds over %llu subsequences\n", launches,
                                         static_cast<unsigned long long>(nsub));
     // `in` now holds the fixed point, d_counts the matching symbol counts
-    launch_scan_chunks(d_counts, d_counts, nsub, d_offs, d_offs + nsub + 2, ws.st);
+    ws.stage_end(h, launches);
+    h = ws.stage_begin("huffman_decode_write");
+    launch_scan_chunks(d_counts, d_counts, nsub, d_offs, d_offs + nsub + 2, ws.st, scan_scratch_words(nsub) ? d_offs + 2 * (nsub + 2) : nullptr);
     unsigned long long total = 0;
     ws.d2h(&total, d_offs + nsub, sizeof(total));
     SZ3B_CUDA(stream_wait(ws.st));
     if (total < n) fail(SZ3B_E_INVALID_ARGUMENT, "huffman: bitstream exhausted");
-    launch_hd_write<QT>(reinterpret_cast<const uint32_t *>(d_bits), total_bits, tb, in, d_offs, n, d_q, ws.st);
-    ws.stage_end(h, launches + 2);
+    launch_hd_write<QT>(reinterpret_cast<const uint32_t *>(d_bits), bit_shift, total_bits, tb, in, d_offs, n, d_q, ws.st);
+    ws.stage_end(h, 4);
     SZ3B_CUDA(cudaGetLastError());
     return d_q;
 }
@@ -2208,10 +2223,10 @@ static T *place_unpred(Workspace &ws, const QT *d_q, uint64_t n, const T *h_unpr
     const uint64_t nch = zero_num_chunks(n);
     unsigned *cz = ws.chunk_zeros.as<unsigned>(nch + 1);
     unsigned *cb = ws.chunk_bits.as<unsigned>(nch + 1);
-    unsigned long long *zo = ws.zero_off.as<unsigned long long>(nch + 2);
+    unsigned long long *zo = ws.zero_off.as<unsigned long long>(nch + 2 + scan_scratch_words(nch));
     unsigned long long *bo = ws.bit_off.as<unsigned long long>(nch + 2);
     launch_zero_count<QT>(d_q, n, cz, cb, ws.st);
-    launch_scan_chunks(cb, cz, nch, bo, zo, ws.st);
+    launch_scan_chunks(cb, cz, nch, bo, zo, ws.st, scan_scratch_words(nch) ? zo + nch + 2 : nullptr);
     launch_zero_scatter<QT, T>(d_q, n, zo, d_un, n_unpred, d_tmp, ws.st);
     *launches += 3;
     return d_tmp;
@@ -2264,7 +2279,10 @@ static void interp_decompress_t(Workspace &ws, const sz3b_config &conf, Cursor &
         for (int p = 0; p < pl.sh.N; p++) {
             if (pass_points(A, p) == 0) continue;
             static const bool old_recover = getenv("SZ3B_RECOVER_OLD") != nullptr;   // diagnostics
-            if (!(pl.sh.N >= 3 && !old_recover && interp_launch_lean<T, QT>(A, p, 1, true, true, d_tmp, ws.st)))
+            // small passes (the coarse levels) on the point-mapped kernel: a row-mapped CTA walks whole rows, and with
+            // a handful of CTAs its latency (60-100 us per pass) is all there is
+            const bool big = pass_points(A, p) >= (2ull << 20);
+            if (!(pl.sh.N >= 3 && big && !old_recover && interp_launch_lean<T, QT>(A, p, 1, true, true, d_tmp, ws.st)))
                 launch_interp_recover<T, QT>(pl.sh, d_out, d_q, d_tmp, make_quant(L.eb, radius), L.s, L.nb,
                                              d_table + L.table_off, p, 0, 0, ws.st);
             launches++;
@@ -2478,11 +2496,37 @@ static void decompress_one(Workspace &ws, const sz3b_config &conf, const uint8_t
     if (raw_len == 0 || raw_len > (bytes + (static_cast<size_t>(1) << 20)) * 4) fail(SZ3B_E_INVALID_ARGUMENT, "implausible stream length");
     uint8_t *raw = static_cast<uint8_t *>(ws.stage.ensure(raw_len + 16));
     {
+        // every frame goes up to the device mirror of the file as soon as it is decoded (the Huffman decoder reads the
+        // bit stream there): the upload hides under the decoding of the other frames
+        struct Uploader : FrameDone {
+            uint8_t *d;
+            const uint8_t *h;
+            cudaStream_t st;
+            std::atomic<bool> failed{false};
+            void frame(size_t off, size_t len) override {
+                if (cudaMemcpyAsync(d + off, h + off, len, cudaMemcpyHostToDevice, st) != cudaSuccess) failed = true;
+            }
+        } up;
+        up.d = ws.hd_bits.as<uint8_t>(raw_len + 256);
+        up.h = raw;
+        up.st = ws.st_copy;
+        SZ3B_CUDA(cudaMemsetAsync(up.d + raw_len, 0, 256, ws.st_copy));
         size_t got = 0;
         double t0 = now_ms();
-        if (!zstd_decompress_parallel(cmp, cmp_size, raw, raw_len, &got, host_threads())) fail(SZ3B_E_RUNTIME, "zstd decompression failed");
+        if (!zstd_decompress_parallel(cmp, cmp_size, raw, raw_len, &got, host_threads(), &up)) fail(SZ3B_E_RUNTIME, "zstd decompression failed");
+        if (up.failed) fail(SZ3B_E_CUDA, "upload of the decoded stream failed");
+        cudaEvent_t ev = ws.event();
+        SZ3B_CUDA(cudaEventRecord(ev, ws.st_copy));
+        SZ3B_CUDA(cudaStreamWaitEvent(ws.st, ev, 0));
+        ws.h2d_bytes += raw_len;
+        ws.raw_host = raw;
+        ws.raw_dev = up.d;
         ws.host_stage("zstd_host", now_ms() - t0);
     }
+    struct RawReset {   // the mirror is only valid for this stream
+        Workspace &w;
+        ~RawReset() { w.raw_host = w.raw_dev = nullptr; }
+    } raw_reset{ws};
     Cursor c{raw, raw_len};
     T *d_out = loc == SZ3B_DEVICE ? out : ws.data.as<T>(num);
     const bool narrow = conf.quantbinCnt / 2 <= 32768;

@@ -415,6 +415,7 @@ struct DJob {
     uint8_t *dst;
     std::atomic<size_t> next{0};
     std::atomic<bool> failed{false};
+    FrameDone *done = nullptr;
 };
 void djob_worker(void *arg, int) {
     DJob &j = *static_cast<DJob *>(arg);
@@ -423,12 +424,16 @@ void djob_worker(void *arg, int) {
         if (k >= j.frames.size()) break;
         const DFrame &f = j.frames[k];
         size_t r = ZSTD_decompress(j.dst + f.off, f.dsize, f.src, f.csize);
-        if (ZSTD_isError(r) || r != f.dsize) j.failed = true;
+        if (ZSTD_isError(r) || r != f.dsize)
+            j.failed = true;
+        else if (j.done)
+            j.done->frame(f.off, f.dsize);
     }
 }
 }  // namespace
 
-bool zstd_decompress_parallel(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *raw_len, int threads) {
+bool zstd_decompress_parallel(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *raw_len, int threads,
+                              FrameDone *done) {
     if (src_len < 8) return false;
     const size_t n = zstd_framed_raw_len(src, src_len);
     *raw_len = n;
@@ -437,6 +442,7 @@ bool zstd_decompress_parallel(const uint8_t *src, size_t src_len, uint8_t *dst, 
     size_t rem = src_len - 8;
     DJob j;
     j.dst = dst;
+    j.done = done;
     size_t off = 0;
     bool splittable = true;
     while (rem > 0) {
@@ -457,7 +463,9 @@ bool zstd_decompress_parallel(const uint8_t *src, size_t src_len, uint8_t *dst, 
     }
     if (!splittable || off != n || j.frames.size() < 2 || threads < 2) {
         size_t r = ZSTD_decompress(dst, n, src + 8, src_len - 8);
-        return !ZSTD_isError(r) && r == n;
+        if (ZSTD_isError(r) || r != n) return false;
+        if (done) done->frame(0, n);
+        return true;
     }
     host_parallel(static_cast<int>(std::min<size_t>(threads, j.frames.size())), djob_worker, &j);
     return !j.failed;

@@ -65,7 +65,13 @@ bool zstd_decompress_framed(const uint8_t *src, size_t src_len, std::vector<uint
 bool zstd_decompress_into(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *dst_len);
 // Same stream, frames decompressed concurrently when every frame states its content size (the frames this library
 // writes do); falls back to one ZSTD_decompress call otherwise.  *raw_len = the size_t prefix.
-bool zstd_decompress_parallel(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *raw_len, int threads);
+// `done` (optional) hears about every stretch of `dst` as soon as it is decoded (from the worker threads)
+struct FrameDone {
+    virtual void frame(size_t off, size_t len) = 0;
+    virtual ~FrameDone() {}
+};
+bool zstd_decompress_parallel(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, size_t *raw_len, int threads,
+                              FrameDone *done = nullptr);
 size_t zstd_framed_raw_len(const uint8_t *src, size_t src_len);
 
 int host_threads();

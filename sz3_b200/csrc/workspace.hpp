@@ -126,6 +126,10 @@ struct Workspace {
     int device = 0;
     cudaStream_t st = nullptr;
     cudaStream_t st_copy = nullptr;   // bulk H2D of the input, so that sampling/tuning can overlap it
+    // decompression: the zstd-decoded stream (host, pinned) and its mirror in device memory, uploaded frame by frame
+    // while the other frames are still being decoded (pipeline.cu: decompress_one); null when there is no mirror
+    const uint8_t *raw_host = nullptr;
+    const uint8_t *raw_dev = nullptr;
     cudaEvent_t ev_copy = nullptr;
     // inputs / index stream
     DevBuf data, q, unpred_tmp, recon, hist, tables, compact;
