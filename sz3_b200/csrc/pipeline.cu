@@ -79,12 +79,83 @@ void workspace_release(Workspace *ws) {
 // ---------------------------------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------------------------------
+// Pageable host memory -> device: a cudaMemcpy from pageable memory runs at the speed of the driver's single staging
+// thread (a fraction of the link rate).  Here the host worker pool copies 8 MiB pieces into a ring of pinned buffers
+// and every piece crosses the link as soon as it is staged: the array travels at min(host memcpy rate, link rate).
+namespace {
+struct StageCopy {
+    uint8_t *dst;
+    const uint8_t *src;
+    size_t len;
+    int parts;
+};
+void stage_copy_part(void *arg, int worker) {
+    StageCopy &j = *static_cast<StageCopy *>(arg);
+    const size_t per = ((j.len + j.parts - 1) / j.parts + 63) & ~static_cast<size_t>(63);
+    const size_t a = std::min(j.len, per * worker), b = std::min(j.len, a + per);
+    if (b > a) memcpy(j.dst + a, j.src + a, b - a);
+}
+}  // namespace
+static void upload_pageable(Workspace &ws, void *d_dst, const void *h_src, size_t bytes) {
+    constexpr size_t kPiece = static_cast<size_t>(8) << 20;
+    constexpr int kRing = 4;
+    uint8_t *ring = static_cast<uint8_t *>(ws.upload_ring.ensure(kPiece * kRing));
+    cudaEvent_t ev[kRing];
+    for (int i = 0; i < kRing; i++) ev[i] = ws.event();
+    const int threads = std::max(1, std::min(host_threads(), 8));
+    size_t off = 0;
+    for (int k = 0; off < bytes; k++, off += kPiece) {
+        const size_t len = std::min(kPiece, bytes - off);
+        uint8_t *slot = ring + static_cast<size_t>(k % kRing) * kPiece;
+        if (k >= kRing) SZ3B_CUDA(event_wait(ev[k % kRing]));   // the slot's previous piece has left
+        StageCopy j{slot, static_cast<const uint8_t *>(h_src) + off, len, threads};
+        host_parallel(threads, stage_copy_part, &j);
+        SZ3B_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(d_dst) + off, slot, len, cudaMemcpyHostToDevice, ws.st));
+        SZ3B_CUDA(cudaEventRecord(ev[k % kRing], ws.st));
+    }
+    ws.h2d_bytes += bytes;
+}
+
+// ... and the way back: device -> pageable host memory through the same ring (the pieces are copied out by the pool
+// while the next ones cross the link).  Returns when `h_dst` is complete.
+static void download_pageable(Workspace &ws, void *h_dst, const void *d_src, size_t bytes) {
+    constexpr size_t kPiece = static_cast<size_t>(8) << 20;
+    constexpr int kRing = 4;
+    uint8_t *ring = static_cast<uint8_t *>(ws.upload_ring.ensure(kPiece * kRing));
+    cudaEvent_t ev[kRing];
+    for (int i = 0; i < kRing; i++) ev[i] = ws.event();
+    const int threads = std::max(1, std::min(host_threads(), 8));
+    const size_t npieces = (bytes + kPiece - 1) / kPiece;
+    auto issue = [&](size_t k) {
+        const size_t off = k * kPiece, len = std::min(kPiece, bytes - off);
+        SZ3B_CUDA(cudaMemcpyAsync(ring + (k % kRing) * kPiece, static_cast<const uint8_t *>(d_src) + off, len, cudaMemcpyDeviceToHost, ws.st));
+        SZ3B_CUDA(cudaEventRecord(ev[k % kRing], ws.st));
+    };
+    for (size_t k = 0; k < npieces && k < static_cast<size_t>(kRing - 1); k++) issue(k);
+    for (size_t k = 0; k < npieces; k++) {
+        if (k + kRing - 1 < npieces) issue(k + kRing - 1);   // (its slot was emptied in the previous iteration)
+        SZ3B_CUDA(event_wait(ev[k % kRing]));
+        const size_t off = k * kPiece, len = std::min(kPiece, bytes - off);
+        StageCopy j{static_cast<uint8_t *>(h_dst) + off, ring + (k % kRing) * kPiece, len, threads};
+        host_parallel(threads, stage_copy_part, &j);
+    }
+    ws.d2h_bytes += bytes;
+}
+
 template <class T>
 static const T *to_device(Workspace &ws, const T *data, int loc, size_t num) {
     if (loc == SZ3B_DEVICE) return data;
     T *d = ws.data.as<T>(num);
     size_t h = ws.stage_begin("h2d_input");
-    ws.h2d(d, data, num * sizeof(T));
+    const size_t bytes = num * sizeof(T);
+    static const bool plain = getenv("SZ3B_PLAIN_PAGEABLE_H2D") != nullptr;   // diagnostics
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, data) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();   // an unregistered pointer may leave an error behind on old drivers
+    if (!pinned && !plain && bytes >= (static_cast<size_t>(32) << 20))
+        upload_pageable(ws, d, data, bytes);
+    else
+        ws.h2d(d, data, bytes);
     ws.stage_end(h, 0);
     return d;
 }
@@ -2543,7 +2614,13 @@ static void decompress_one(Workspace &ws, const sz3b_config &conf, const uint8_t
     }
     if (loc == SZ3B_HOST) {
         size_t h = ws.stage_begin("d2h_output");
-        ws.d2h(out, d_out, bytes);
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (!pinned && bytes >= (static_cast<size_t>(32) << 20))
+            download_pageable(ws, out, d_out, bytes);
+        else
+            ws.d2h(out, d_out, bytes);
         ws.stage_end(h, 0);
     }
     SZ3B_CUDA(stream_wait(ws.st));

@@ -183,6 +183,7 @@ struct Workspace {
         std::vector<cudaEvent_t> ev_row;   // ev_row[b]: every plane the level-1 tiles of block-row b read has arrived
     } copy_plan;
     PinBuf upload_arena;
+    PinBuf upload_ring;   // staging ring of upload_pageable (pipeline.cu)
     size_t upload_used = 0;
     static constexpr size_t kUploadArena = static_cast<size_t>(16) << 20;
     void h2d(void *dst, const void *src, size_t bytes) {
