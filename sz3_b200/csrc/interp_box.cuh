@@ -287,26 +287,38 @@ SZ_HD void box_target_rt(uint32_t k, bool n_odd, const QuantParams &qp, Ld &&ld,
 template <bool CUBIC, class Ctx>
 SZ_HD void box_run8(const float (&nb)[11], const float (&og)[8], uint32_t h, bool n_odd, const QuantParams &qp, Ctx &ctx,
                     bool owned, float (&rc)[8], BoxHist<Ctx, 8> &H) {
-    float rec_prev = 0.0f;
+    // Predictions first, then the eight quantizer chains (interleaved by the compiler).  The stencils that differ from
+    // the plain cubic sit at the two ends of a line; which one applies depends on (h, n_odd) only -- uniform over the
+    // warp, so they are ordinary branches around the exact interpolator instead of a four-tap form with selected
+    // coefficients (which also evaluated the double-precision linear tail for every line).
+    float pred[8];
+    if (CUBIC) {
+#pragma unroll
+        for (int t = 1; t <= 5; t++) pred[t] = interp_cubic<float>(nb[t], nb[t + 1], nb[t + 2], nb[t + 3]);
+        if (h == 0) {
+            pred[0] = interp_quad_1<float>(nb[1], nb[2], nb[3]);
+            pred[6] = interp_cubic<float>(nb[6], nb[7], nb[8], nb[9]);
+            pred[7] = interp_cubic<float>(nb[7], nb[8], nb[9], nb[10]);
+        } else {
+            pred[0] = interp_cubic<float>(nb[0], nb[1], nb[2], nb[3]);
+            if (n_odd) {
+                pred[6] = interp_cubic<float>(nb[6], nb[7], nb[8], nb[9]);
+                pred[7] = interp_quad_2<float>(nb[7], nb[8], nb[9]);
+            } else {
+                pred[6] = interp_quad_2<float>(nb[6], nb[7], nb[8]);
+                pred[7] = interp_linear1<float>(nb[7], nb[8]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; t++) pred[t] = interp_linear<float>(nb[t + 1], nb[t + 2]);
+    }
+    const bool lin_tail = !CUBIC && h == 1 && !n_odd;   // linear, even line: the last target leans on its predecessor
 #pragma unroll
     for (int t = 0; t < 8; t++) {
-        float pred;
-        if (CUBIC) {
-            if (t >= 1 && t <= 5) {
-                pred = interp_cubic<float>(nb[t], nb[t + 1], nb[t + 2], nb[t + 3]);
-            } else {
-                uint32_t kind = BOX_ST_CUBIC;
-                if (t == 0 && h == 0) kind = BOX_ST_QUAD1;
-                if (t == 6 && h == 1 && !n_odd) kind = BOX_ST_QUAD2;
-                if (t == 7 && h == 1) kind = n_odd ? BOX_ST_QUAD2 : BOX_ST_LINEAR1;
-                pred = box_stencil4(kind, nb[t], nb[t + 1], nb[t + 2], nb[t + 3]);
-            }
-        } else {
-            pred = interp_linear<float>(nb[t + 1], nb[t + 2]);
-            if (t == 7 && h == 1 && !n_odd) pred = interp_linear1<float>(rec_prev, nb[t + 1]);
-        }
-        const int qv = quantize_f32(og[t], pred, qp, rc[t]);
-        rec_prev = rc[t];
+        float p = pred[t];
+        if (!CUBIC && t == 7 && lin_tail) p = interp_linear1<float>(rc[6], nb[8]);
+        const int qv = quantize_f32(og[t], p, qp, rc[t]);
         H.add(ctx, t, qv, owned);
     }
 }
