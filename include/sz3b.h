@@ -94,9 +94,10 @@ int sz3b_abs_error_bound(int dtype, const sz3b_config *c, const void *data, int 
 /* InterpolationDecomposition::compress + save (decomposition/InterpolationDecomposition.hpp:79-159).
  * quant_out: conf.num int32 indices in reference traversal order (host).  blob_out: what save() writes (dims,
  * blocksize, interp id, direction, anchor stride, alpha, beta, quantizer incl. unpredictable values).
- * schedule: 0 = automatic, 1 = force the generic per-pass kernels, 2 / 3 / 4 = force the first-generation / lean /
- * line-walker tile kernel (N == 3 only; automatic picks the line walker), 5 = force the row-mapped per-pass kernels
- * (N >= 3; automatic for N == 4). */
+ * schedule: 0 = automatic (N == 3: box schedule where it applies, line-walker tile kernel otherwise; N == 4: row-mapped
+ * per-pass kernels), 1 = force the generic per-pass kernels, 4 = force the line-walker tile kernel (N == 3), 5 = force
+ * the row-mapped per-pass kernels (N >= 3), 6 = box schedule or fail; 2 and 3 (the first two tile kernels) were
+ * retired in round 2. */
 int sz3b_interp_decompose(int dtype, const sz3b_config *c, double abs_eb, const void *data, int data_loc, int schedule,
                           int32_t *quant_out, unsigned char *blob_out, size_t blob_cap, size_t *blob_len);
 

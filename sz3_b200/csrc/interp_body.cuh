@@ -194,135 +194,4 @@ SZ_HD void tile_geom(const InterpArgs<T, QT> &A, uint32_t tile, uint32_t batch, 
     tg.sst[0] = tg.E[2] * tg.E[1];
 }
 
-// One predicted point of pass p inside a tile.  l[] = local indices (units of s) in natural order.
-template <class T, class QT, class Ctx>
-SZ_HD void tile_point(const InterpArgs<T, QT> &A, Ctx &ctx, const TileGeom &tg, T *sm, int p, const uint32_t l[3],
-                      bool active, uint32_t batch) {
-    const InterpShape &sh = A.sh;
-    const uint32_t s = A.s;
-    int qv = 0;
-    uint64_t pos = 0;
-    T orig = 0;
-    bool owned = false;
-    if (active) {
-        const int D = tg.a[p];
-        const int last = tg.a[2];
-        const uint32_t n = tg.g.n[D];
-        const uint32_t i = l[D];
-        const bool tail = !sh.cubic && i + 1 == n && n >= 4;          // linear i == n-1, done by the i == n-3 item
-        if (!tail) {
-            uint32_t x[kMaxDim];
-            uint64_t goff = 0, g2off = 0;
-            uint32_t soff = 0;  // smem offset of the point with l[D] replaced by 0
-            for (int d = 0; d < 3; d++) {
-                x[d] = tg.g.begin[d] + l[d] * s;
-                goff += x[d] * sh.stride[d];
-                g2off += (x[d] >> 1) * A.stride2[d];
-                if (d != D) soff += (d == last ? l[d] >> 1 : l[d]) * tg.sst[d];
-            }
-            const T *dat = A.data + batch * A.data_bstride;
-            T *rc2 = A.recon2 + batch * A.recon2_bstride;
-            const uint32_t sD = tg.sst[D];
-            const bool lastpass = p == 2;
-            // value at local index k along D (k even): smem coordinate is k/2 in the last pass, k otherwise
-            auto v = [&](uint32_t k) -> T { return sm[soff + (lastpass ? k >> 1 : k) * sD]; };
-            T pred = predict_line<T>(sh.cubic, i, n, v, static_cast<T>(0));
-            orig = lastpass ? dat[goff] : sm[soff + i * sD];
-            T rec;
-            qv = quantize<T>(orig, pred, A.qp, rec);
-            if (!lastpass) sm[soff + i * sD] = rec;
-            uint64_t ip = pass_offset(sh, tg.pg[p], x, i);
-            owned = ip != ~0ull;
-            pos = tg.pass_base[p] + ip;
-            if (owned && s >= 2) rc2[g2off] = rec;
-            if (!sh.cubic && i + 3 == n && n >= 4 && !(n & 1)) {
-                // flush this point, then do the linear tail i+2 = n-1: linear1(recon(i), value(i+1))
-                emit(A, ctx, pos, qv, orig, owned);
-                const int64_t sdg = static_cast<int64_t>(s) * static_cast<int64_t>(sh.stride[D]);
-                const uint32_t i2 = i + 2;
-                T pred2 = interp_linear1<T>(rec, v(i + 1));
-                uint32_t x2[kMaxDim] = {x[0], x[1], x[2], 0};
-                x2[D] += 2 * s;
-                orig = lastpass ? dat[static_cast<int64_t>(goff) + 2 * sdg] : sm[soff + i2 * sD];
-                qv = quantize<T>(orig, pred2, A.qp, rec);
-                if (!lastpass) sm[soff + i2 * sD] = rec;
-                ip = pass_offset(sh, tg.pg[p], x2, i2);
-                owned = ip != ~0ull;
-                pos = tg.pass_base[p] + ip;
-                if (owned && s >= 2) rc2[g2off + s * A.stride2[D]] = rec;
-            }
-        }
-    }
-    emit(A, ctx, pos, qv, orig, active && owned);
-}
-
-template <class T, class QT, class Ctx>
-SZ_HD void tile_body(const InterpArgs<T, QT> &A, Ctx &ctx, T *sm, const TileGeom &tg, uint32_t batch) {
-    const InterpShape &sh = A.sh;
-    const uint32_t s = A.s;
-    const uint32_t tid = ctx.tid(), nt = ctx.nthreads();
-    const int last = tg.a[2];
-    const T *dat = A.data + batch * A.data_bstride;
-    const T *rc2 = A.recon2 + batch * A.recon2_bstride;
-
-    // ---- load: the sub-lattice even along `last` -------------------------------------------------------------------
-    {
-        const uint32_t total = tg.E[0] * tg.E[1] * tg.E[2];
-        for (uint32_t it = tid; it < total; it += nt) {
-            uint32_t c2 = it % tg.E[2];
-            uint32_t r = it / tg.E[2];
-            uint32_t c1 = r % tg.E[1];
-            uint32_t c0 = r / tg.E[1];
-            uint32_t c[3] = {c0, c1, c2};
-            uint64_t goff = 0, g2off = 0;
-            bool coarse = true;
-            for (int d = 0; d < 3; d++) {
-                uint32_t l = d == last ? 2 * c[d] : c[d];
-                coarse = coarse && !(l & 1);
-                uint32_t x = tg.g.begin[d] + l * s;
-                goff += x * sh.stride[d];
-                g2off += (x >> 1) * A.stride2[d];
-            }
-            sm[it] = coarse ? rc2[g2off] : dat[goff];
-        }
-    }
-    ctx.sync();
-    // ---- passes ----------------------------------------------------------------------------------------------------
-    for (int p = 0; p < 3; p++) {
-        const int D = tg.a[p];
-        // item space in natural order; per dim: count and local-index step/start
-        uint32_t cnt[3], mul[3], add[3];
-        for (int q = 0; q < 3; q++) {
-            int d = tg.a[q];
-            uint32_t n = tg.g.n[d];
-            if (q == p) {
-                cnt[d] = n / 2; mul[d] = 2; add[d] = 1;          // odd local indices
-            } else if (q < p) {
-                cnt[d] = n; mul[d] = 1; add[d] = 0;              // already refined to step s
-            } else {
-                cnt[d] = (n + 1) / 2; mul[d] = 2; add[d] = 0;    // still on the 2s lattice
-            }
-        }
-        const uint32_t total = cnt[0] * cnt[1] * cnt[2];
-        const uint32_t rounds = (total + nt - 1) / nt;
-        for (uint32_t rd = 0; rd < rounds; rd++) {
-            uint32_t it = rd * nt + tid;
-            bool active = it < total;
-            uint32_t l[3] = {0, 0, 0};
-            if (active) {
-                uint32_t c2 = it % cnt[2];
-                uint32_t r = it / cnt[2];
-                uint32_t c1 = r % cnt[1];
-                uint32_t c0 = r / cnt[1];
-                l[0] = c0 * mul[0] + add[0];
-                l[1] = c1 * mul[1] + add[1];
-                l[2] = c2 * mul[2] + add[2];
-            }
-            tile_point(A, ctx, tg, sm, p, l, active, batch);
-        }
-        (void)D;
-        if (p < 2) ctx.sync();
-    }
-}
-
 }  // namespace sz3b

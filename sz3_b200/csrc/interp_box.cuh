@@ -1,4 +1,4 @@
-// sz3_b200/csrc/interp_box.cuh -- fifth-generation N == 3 tile schedule of the fused interpolation-predict +
+// sz3_b200/csrc/interp_box.cuh -- box schedule: the N == 3 tile schedule of the fused interpolation-predict +
 // LinearQuantizer kernel (InterpolationDecomposition::compress, reference
 // include/SZ3/decomposition/InterpolationDecomposition.hpp:99-143, :309-402; LinearQuantizer.hpp:43-71) for the
 // configuration the auto-tuner picks most often: float data, pass order z, y, x (interpDirection 0), tiles whose

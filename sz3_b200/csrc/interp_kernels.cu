@@ -4,7 +4,6 @@
 
 #include "device_ctx.cuh"
 #include "interp_body.cuh"
-#include "interp_fast.cuh"
 #include "interp_line.cuh"
 #include "interp_lean.cuh"
 #include "launch.hpp"
@@ -55,35 +54,6 @@ __global__ void __launch_bounds__(256) k_interp_anchor(InterpArgs<T, QT> A, uint
 // ---------------------------------------------------------------------------------------------------------------------
 // tile schedule, N == 3
 // ---------------------------------------------------------------------------------------------------------------------
-template <class T, class QT>
-__global__ void __launch_bounds__(kTileThreads) k_interp_tile(InterpArgs<T, QT> A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);
-    unsigned *shist = reinterpret_cast<unsigned *>(smem_raw + sizeof(T) * kTileSmemElems);
-    __shared__ TileGeom tg;
-    DevCtx ctx(shist, A.hist, A.qp.radius);
-    ctx.clear();
-    if (threadIdx.x == 0) tile_geom(A, blockIdx.x, blockIdx.y, tg);
-    __syncthreads();
-    tile_body(A, ctx, sm, tg, blockIdx.y);
-    ctx.flush();
-}
-
-// lean tile schedule (interp_fast.cuh): two CTAs per SM
-template <class T, class QT>
-__global__ void __launch_bounds__(kTileThreads, sizeof(T) == 4 ? 2 : 1) k_interp_ftile(InterpArgs<T, QT> A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sm = reinterpret_cast<T *>(smem_raw);
-    unsigned *shist = reinterpret_cast<unsigned *>(smem_raw + sizeof(T) * kTileSmemElems);
-    __shared__ FastTile ft;
-    DevCtx ctx(shist, A.hist, A.qp.radius);
-    ctx.clear();
-    if (threadIdx.x == 0) fast_tile_setup(A, blockIdx.x, blockIdx.y, ft);
-    __syncthreads();
-    fast_tile_body(A, ctx, sm, ft);
-    ctx.flush();
-}
-
 // line-walker tile schedule (interp_line.cuh): two CTAs per SM; three lanes build the pass tables while the
 // rest of the CTA already fills shared memory
 template <class T, class QT>
@@ -190,28 +160,6 @@ void interp_launch_anchors(const InterpArgs<T, QT> &A, uint32_t anchor_stride, u
 }
 
 template <class T, class QT>
-void interp_launch_tiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
-    static std::atomic<unsigned long long> attr_set{0};
-    const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
-    once_per_device(attr_set, [&] {
-        cudaFuncSetAttribute(k_interp_tile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    });
-    dim3 grid(static_cast<unsigned>(ntiles), nbatch);
-    k_interp_tile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
-}
-
-template <class T, class QT>
-void interp_launch_ftiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
-    static std::atomic<unsigned long long> attr_set{0};
-    const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
-    once_per_device(attr_set, [&] {
-        cudaFuncSetAttribute(k_interp_ftile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    });
-    dim3 grid(static_cast<unsigned>(ntiles), nbatch);
-    k_interp_ftile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
-}
-
-template <class T, class QT>
 void interp_launch_ltiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st) {
     static std::atomic<unsigned long long> attr_set{0};
     const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
@@ -237,8 +185,6 @@ void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cuda
 #define SZ3B_INST(T, QT)                                                                                         \
     template void interp_launch_anchors<T, QT>(const InterpArgs<T, QT> &, uint32_t, uint64_t, uint32_t,        \
                                                cudaStream_t);                                                   \
-    template void interp_launch_tiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);      \
-    template void interp_launch_ftiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);     \
     template void interp_launch_ltiles<T, QT>(const InterpArgs<T, QT> &, uint64_t, uint32_t, cudaStream_t);     \
     template void interp_launch_pass<T, QT>(const InterpArgs<T, QT> &, int, uint32_t, cudaStream_t);          \
     template bool interp_launch_lean<T, QT>(const InterpArgs<T, QT> &, int, uint32_t, bool, bool, const T *,  \

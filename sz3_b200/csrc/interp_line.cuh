@@ -1,4 +1,4 @@
-// sz3_b200/csrc/interp_line.cuh -- third-generation N == 3 tile schedule of the fused interpolation-predict +
+// sz3_b200/csrc/interp_line.cuh -- line-walker N == 3 tile schedule (fallback of the box schedule) of the fused interpolation-predict +
 // LinearQuantizer kernel (InterpolationDecomposition::compress, reference
 // include/SZ3/decomposition/InterpolationDecomposition.hpp:79-147, :309-454).
 //
@@ -17,9 +17,18 @@
 #pragma once
 #include "core.cuh"
 #include "interp_body.cuh"
-#include "interp_fast.cuh"
 
 namespace sz3b {
+
+// floor(x / c) == umulhi(x, magic(c)) for x * c < 2^32 (magic 0 stands for c <= 1)
+SZ_HD uint32_t fast_div(uint32_t x, uint32_t mg) {
+#if defined(__CUDA_ARCH__)
+    return mg ? __umulhi(x, mg) : x;
+#else
+    return mg ? static_cast<uint32_t>((static_cast<uint64_t>(x) * mg) >> 32) : x;
+#endif
+}
+
 
 struct LinePass {
     uint32_t kind;             // 0 = line items, 1 = row items

@@ -36,7 +36,6 @@ struct InterpPlan {
     uint64_t num2 = 0;
     bool tile = false;            // tile schedule (N == 3) or generic per-pass schedule
     bool lean = false;            // per-pass schedule through the row-mapped kernel (interp_lean.cuh, N >= 3)
-    int variant = 0;              // tile kernel: 0 = first generation, 1 = lean (interp_fast.cuh), 2 = line walker (interp_line.cuh)
     bool box_required = false;    // schedule 6: fail instead of falling back
     bool box = false;             // finest level through the box schedule (interp_box.cuh) where it applies; schedule 6 insists
     int interp_id = 1, direction = 0;
@@ -123,17 +122,17 @@ inline const char *build_interp_plan(const sz3b_config &c, double eb, int schedu
         if (d < N) acc *= pl.dims2[d];
     }
     pl.num2 = acc;
+    if (schedule == 2 || schedule == 3) return "tile schedules 2 and 3 (first tile kernels) were retired: use 4 (line walker) or 0";
     pl.tile = (N == 3) && schedule != 1 && schedule != 5;
+    // the tile kernels keep tile-relative element offsets in 32 bits: larger arrays take the row-mapped per-pass kernels
+    if (pl.tile && pl.num >= (1ull << 32)) {
+        if (schedule == 4 || schedule == 6) return "tile schedules need fewer than 2^32 elements";
+        pl.tile = false;
+    }
     pl.lean = N >= 3 && (schedule == 5 || (schedule == 0 && !pl.tile));
-    pl.variant = schedule == 2 ? 0 : (schedule == 3 ? 1 : 2);
     pl.box = pl.tile && (schedule == 0 || schedule == 6);
     pl.box_required = schedule == 6;
-    // the line walker keeps tile-relative element offsets in 32 bits
-    if (pl.variant == 2 && pl.num >= (1ull << 32)) {
-        if (schedule == 4 || schedule == 6) return "line-walker schedule needs fewer than 2^32 elements";
-        pl.variant = 1;
-    }
-    if (((schedule >= 2 && schedule <= 4) || schedule == 6) && N != 3) return "tile schedule needs N == 3";
+    if ((schedule == 4 || schedule == 6) && N != 3) return "tile schedule needs N == 3";
     if (schedule == 5 && N < 3) return "row-mapped per-pass schedule needs N >= 3";
     if (schedule < 0 || schedule > 6) return "unknown schedule";
 

@@ -31,10 +31,6 @@ template <class T, class QT>
 void interp_launch_anchors(const InterpArgs<T, QT> &A, uint32_t anchor_stride, uint64_t n_anchor, uint32_t nbatch,
                            cudaStream_t st);
 template <class T, class QT>
-void interp_launch_tiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st);
-template <class T, class QT>
-void interp_launch_ftiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st);
-template <class T, class QT>
 void interp_launch_ltiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t nbatch, cudaStream_t st);
 template <class T, class QT>
 void interp_launch_pass(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, cudaStream_t st);

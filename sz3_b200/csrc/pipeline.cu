@@ -362,7 +362,7 @@ static bool box_applicable(const InterpArgs<T, QT> &A) {
 template <class T, class QT>
 static void box_prepare(Workspace &ws, const InterpPlan &pl, InterpArgs<T, QT> A, uint32_t nbatch, BoxPlan &bp) {
     if constexpr (std::is_same<T, float>::value && std::is_same<QT, uint16_t>::value) {
-        if (!(pl.box && pl.tile && pl.variant == 2 && nbatch == 1)) return;
+        if (!(pl.box && pl.tile && nbatch == 1)) return;
         int need = 0;
         for (const LevelPlan &L : pl.levels) {
             A.s = L.s;
@@ -460,7 +460,7 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
     // input still arriving in plane order (to_device_planes): the line-walker tile path follows the copy, anything
     // else waits for all of it
     bool planes = ws.copy_plan.active && d_data == ws.data.p && nbatch == 1;
-    if (planes && !(pl.tile && pl.variant == 2 && !pl.levels.empty() && pl.levels.back().s == 1 &&
+    if (planes && !(pl.tile && !pl.levels.empty() && pl.levels.back().s == 1 &&
                     pl.levels.back().nb[0] == ws.copy_plan.ev_row.size())) {
         join_copy(ws);
         planes = false;
@@ -522,12 +522,9 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
             if constexpr (std::is_floating_point<T>::value) {
                 if (box && launch_box<T, QT>(A, bp, L.nblocks, ws.st)) {
                     count_box(lv_begin, lv_end);
-                } else if (pl.variant == 2)
+                } else {
                     interp_launch_ltiles<T, QT>(A, L.nblocks, nbatch, ws.st);
-                else if (pl.variant == 1)
-                    interp_launch_ftiles<T, QT>(A, L.nblocks, nbatch, ws.st);
-                else
-                    interp_launch_tiles<T, QT>(A, L.nblocks, nbatch, ws.st);
+                }
             } else {
                 fail(SZ3B_E_RUNTIME, "tile schedule planned for an integer element type");
             }
@@ -895,7 +892,7 @@ static size_t interp_compress_t(Workspace &ws, const sz3b_config &conf, const T 
     }();
     const int schedule = std::is_integral<T>::value
                              ? 1   // integer element types: the per-pass kernels (core.cuh carries their arithmetic)
-                             : ((forced == 1 || (forced >= 2 && forced <= 4 && conf.N == 3) || (forced == 5 && conf.N >= 3)) ? forced : 0);
+                             : ((forced == 1 || (forced == 4 && conf.N == 3) || (forced == 5 && conf.N >= 3)) ? forced : 0);
     if (const char *e = build_interp_plan(conf, conf.absErrorBound, schedule, pl)) fail(SZ3B_E_INVALID_ARGUMENT, e);
     const int radius = conf.quantbinCnt / 2;
     const int nbins = 2 * radius;

@@ -96,7 +96,7 @@ def port_lib():
 def emul_lib():
     src = os.path.join(ROOT, "tests", "emul", "emul.cpp")
     out = os.path.join(ROOT, "tests", "emul", "_build", "libemul.so")
-    deps = [src] + [os.path.join(ROOT, "sz3_b200", "csrc", f) for f in ("core.cuh", "interp_body.cuh", "interp_fast.cuh", "interp_line.cuh", "interp_lean.cuh", "interp_box.cuh", "interp_plan.hpp", "blockwise.cuh", "lorenzo.cuh")]
+    deps = [src] + [os.path.join(ROOT, "sz3_b200", "csrc", f) for f in ("core.cuh", "interp_body.cuh", "interp_line.cuh", "interp_lean.cuh", "interp_box.cuh", "interp_plan.hpp", "blockwise.cuh", "lorenzo.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-shared", "-pthread", src, "-o", out],

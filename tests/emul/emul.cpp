@@ -12,7 +12,6 @@
 #include <vector>
 
 #include "../../sz3_b200/csrc/interp_body.cuh"
-#include "../../sz3_b200/csrc/interp_fast.cuh"
 #include "../../sz3_b200/csrc/interp_line.cuh"
 #include "../../sz3_b200/csrc/interp_lean.cuh"
 #include "../../sz3_b200/csrc/interp_box.cuh"
@@ -226,7 +225,7 @@ static int run(const sz3b_config &c, double eb, const T *data, int schedule, int
             auto worker = [&](int t) {
                 HostCtx ctx{static_cast<uint32_t>(t), static_cast<uint32_t>(nthreads), &bar, hist.data()};
                 for (uint64_t tile = 0; tile < L.nblocks; tile++) {
-                    if (pl.variant == 2) {
+                    {
                         static LineTile lt;   // shared by the worker threads like __shared__ memory
                         LineGeom lg;
                         line_geom(A, static_cast<uint32_t>(tile), 0, lg);
@@ -234,14 +233,6 @@ static int run(const sz3b_config &c, double eb, const T *data, int schedule, int
                         line_fill(A, ctx, lg, sm.data());
                         ctx.sync();
                         line_tile_passes(A, ctx, sm.data(), lg, lt);
-                    } else if (pl.variant == 1) {
-                        FastTile ft;
-                        fast_tile_setup(A, static_cast<uint32_t>(tile), 0, ft);
-                        fast_tile_body(A, ctx, sm.data(), ft);
-                    } else {
-                        TileGeom tg;
-                        tile_geom(A, static_cast<uint32_t>(tile), 0, tg);
-                        tile_body(A, ctx, sm.data(), tg, 0);
                     }
                     ctx.sync();
                 }

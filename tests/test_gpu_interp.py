@@ -52,7 +52,7 @@ def check(shape, dtype, eb, schedule, data=None, **kw):
 SHAPES3 = [(40, 50, 70), (33, 65, 97), (100, 70, 130), (64, 64, 64), (20, 20, 20), (8, 8, 128), (2, 3, 200), (33, 33, 33)]
 
 
-@pytest.mark.parametrize("schedule", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("schedule", [1, 4, 5])
 @pytest.mark.parametrize("shape", SHAPES3)
 @pytest.mark.parametrize("algo", [0, 1])
 @pytest.mark.parametrize("direction", [0, 5, 2])
@@ -60,7 +60,7 @@ def test_interp3d_f32(shape, algo, direction, schedule):
     check(shape, np.float32, 1e-2, schedule, interpAlgo=algo, interpDirection=direction)
 
 
-@pytest.mark.parametrize("schedule", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("schedule", [1, 4, 5])
 @pytest.mark.parametrize("kw", [
     dict(interpAlgo=1, interpDirection=0), dict(interpAlgo=0, interpDirection=3),
     dict(interpAlgo=1, interpDirection=1, interpAlpha=-1.0), dict(interpAlgo=1, interpDirection=4, interpAlpha=2.0, interpBeta=3.0),
@@ -71,13 +71,13 @@ def test_interp3d_f64_variants(kw, schedule):
     check((50, 60, 70), np.float64, 1e-4, schedule, **kw)
 
 
-@pytest.mark.parametrize("schedule", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("schedule", [1, 4, 5])
 def test_interp3d_many_unpredictable(schedule):
     # eb far below the data resolution and a tiny quantizer: most points overflow the radius
     check((37, 41, 130), np.float32, 1e-6, schedule, interpAlgo=1, quantbinCnt=16)
 
 
-@pytest.mark.parametrize("schedule", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("schedule", [1, 4, 5])
 def test_interp3d_special_values(schedule):
     data = field_nd((40, 40, 40), np.float32)
     data[3, 4, 5] = np.nan
@@ -121,7 +121,7 @@ def test_interp_constant_and_tiny():
     check((2, 2, 2), np.float64, 1e-3, 0)
 
 
-@pytest.mark.parametrize("schedule", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("schedule", [1, 4, 5])
 def test_interp3d_g3_256(schedule):
     """The benchmark field at 256^3: 16.7 M indices, still seconds for the reference."""
     data = field_g3((256, 256, 256))
@@ -188,7 +188,7 @@ def test_schedules_agree_512():
     data = field_g3((512, 512, 512))
     conf = make_config(data.shape, cmprAlgo=ALGO_INTERP, interpAnchorStride=32)
     q1, b1 = gpu_interp(data, conf, 1e-3, 1)
-    q2, b2 = gpu_interp(data, conf, 1e-3, 2)
+    q2, b2 = gpu_interp(data, conf, 1e-3, 4)
     assert np.array_equal(q1, q2) and b1 == b2
     hist = np.bincount(q1, minlength=65536)
     assert hist.sum() == data.size and hist[0] >= 4096  # anchors are stored as unpredictables
