@@ -736,6 +736,34 @@ def other_configs(L, torch):
             alg = data.size * (data.itemsize + 4)
             r["roofline"] = {"kernel": alg_bytes_name, "algorithmic_bytes": alg, "ms": pq, "achieved": alg / pq / 1e6,
                              "frac": alg / pq / 1e6 / peak, "unit": "GB/s"}
+        # decompression of the stream just written, output left in HBM
+        try:
+            dev_out = torch.empty(data.size, dtype=torch.float32 if data.dtype == np.float32 else torch.float64, device="cuda")
+            dconf = Config()
+
+            def dec_one():
+                if L.sz3b_decompress(code, out.ctypes.data_as(C.c_char_p), C.c_size_t(size.value), C.c_void_p(dev_out.data_ptr()), 1,
+                                     C.byref(dconf)) != 0:
+                    raise RuntimeError(L.sz3b_last_error().decode())
+
+            dec_one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                dec_one()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_dec = e0.elapsed_time(e1) / reps
+            k = L.sz3b_last_profile(names, ms, ln, 64)
+            dstages = {}
+            for i in range(k):
+                dstages[names[i].decode()] = round(dstages.get(names[i].decode(), 0.0) + ms[i], 4)
+            r["decompress"] = {"ms_device_resident": ms_dec, "GBps_device_resident": data.nbytes / ms_dec / 1e6, "stages_ms": dstages,
+                               "max_abs_error": float(np.max(np.abs(dev_out.cpu().numpy().astype(np.float64) - data.reshape(-1).astype(np.float64))))}
+            del dev_out
+        except Exception as ex:
+            r["decompress"] = {"error": str(ex)[:200]}
         if lib is not None:
             threads = set_ref_threads(lib, prefix, cores)
             rconf = Config.from_buffer_copy(bytes(conf))

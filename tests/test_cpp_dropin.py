@@ -77,6 +77,34 @@ int main(int argc, char **argv) {
     delete[] cmp3;
     if (!(worst <= 1e-3) || !dc3.openmp) return 24;
     if (nslab != sz3b_device_count()) return 25;
+    // the integer element types the reference's CLI instantiates (tools/sz3/sz3.cpp:458-461)
+    {
+        SZ3::Config ci(40, 50, 60);
+        ci.absErrorBound = 2.0;
+        std::vector<int32_t> a32(ci.num);
+        std::vector<int64_t> a64(ci.num);
+        for (size_t i = 0; i < a32.size(); i++) {
+            a32[i] = static_cast<int32_t>(1000.0 * std::sin(0.01 * i)) + static_cast<int32_t>(i % 5);
+            a64[i] = static_cast<int64_t>(a32[i]) * 1000003;
+        }
+        size_t s32 = 0, s64 = 0;
+        char *k32 = SZ_compress<int32_t>(ci, a32.data(), s32);
+        ci.absErrorBound = 2.0e6;
+        char *k64 = SZ_compress<int64_t>(ci, a64.data(), s64);
+        SZ3::Config d32, d64;
+        int32_t *r32 = SZ_decompress<int32_t>(d32, k32, s32);
+        int64_t *r64 = SZ_decompress<int64_t>(d64, k64, s64);
+        double w32 = 0, w64 = 0;
+        for (size_t i = 0; i < a32.size(); i++) {
+            w32 = std::fmax(w32, std::fabs((double)r32[i] - (double)a32[i]));
+            w64 = std::fmax(w64, std::fabs((double)r64[i] - (double)a64[i]));
+        }
+        delete[] r32;
+        delete[] r64;
+        delete[] k32;
+        delete[] k64;
+        if (!(w32 <= 2.0) || !(w64 <= 2.0e6) || s32 >= a32.size() * 4 || s64 >= a64.size() * 8) return 26;
+    }
     printf("roundtrip ok ratio %.2f, openmp container: %d slabs on %d GPUs\n", data.size() * 4.0 / cmpSize, nslab, sz3b_device_count());
     return 0;
 }
