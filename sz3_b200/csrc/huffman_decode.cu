@@ -30,7 +30,8 @@ constexpr int kHdThreads = 256;
 constexpr int kHdLutBits = 12;
 
 struct HdTables {
-    const uint32_t *lut;     // 1 << kHdLutBits entries
+    const uint32_t *lut;     // 1 << kHdLutBits entries (HuffmanDecoder::dlut)
+    const uint32_t *lut2;    // second level (HuffmanDecoder::lut2)
     const uint32_t *L, *R;   // tree links (node count entries)
     const int *C;            // symbol (state) per node
     const uint8_t *leaf;
@@ -66,23 +67,44 @@ struct BitReader {
     }
 };
 
+// The rest of a code longer than the first-level table, the reader standing after its first kHdLutBits bits: one
+// lookup in the second-level table (entry e of the first level: bit 31, S = bits 24..30, base = (bits 0..23) << 4)
+// resolves codes of up to kHdLutBits + S bits; anything longer, and prefixes without a sub-table, walk the tree bit
+// by bit from where the tables leave off.  Returns the leaf, *len_out = total code length.
+__device__ __forceinline__ uint32_t hd_long_code(BitReader &br, uint32_t e, const HdTables &t, uint32_t *len_out) {
+    uint32_t node = e & 0xffffffu, len = kHdLutBits;
+    bool walk = true;
+    if (e & 0x80000000u) {
+        const uint32_t S = (e >> 24) & 0x7fu;
+        br.refill();
+        const uint32_t e2 = t.lut2[(static_cast<size_t>(e & 0xffffffu) << 4) + static_cast<uint32_t>(br.acc >> (64 - S))];
+        const uint32_t len2 = e2 >> 24;
+        node = e2 & 0xffffffu;
+        br.skip(static_cast<int>(len2 ? len2 : S));
+        len += len2 ? len2 : S;
+        walk = len2 == 0;
+    }
+    while (walk) {
+        br.refill();
+        node = (br.acc >> 63) ? t.R[node] : t.L[node];
+        br.skip(1);
+        len++;
+        if (t.leaf[node] || len >= 96) break;
+    }
+    *len_out = len;
+    return node;
+}
+
 // decodes one symbol; returns its node (leaf) and advances the reader; *len_out = code length
 __device__ __forceinline__ uint32_t hd_symbol(BitReader &br, const uint32_t *slut, const HdTables &t, int *len_out) {
     br.refill();
     const uint32_t e = slut[br.acc >> (64 - kHdLutBits)];
     uint32_t len = e >> 24, node = e & 0xffffffu;
-    if (len) {
+    if (len - 1u < static_cast<uint32_t>(kHdLutBits)) {
         br.skip(static_cast<int>(len));
-    } else {   // code longer than the table: walk on bit by bit
+    } else {   // code longer than the table
         br.skip(kHdLutBits);
-        len = kHdLutBits;
-        for (;;) {
-            br.refill();
-            node = (br.acc >> 63) ? t.R[node] : t.L[node];
-            br.skip(1);
-            len++;
-            if (t.leaf[node] || len >= 96) break;
-        }
+        node = hd_long_code(br, e, t, &len);
     }
     *len_out = static_cast<int>(len);
     return node;
@@ -146,7 +168,7 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_write(const uint32_t *__restr
     for (int k = threadIdx.x; k < (1 << kHdLutBits); k += blockDim.x) {
         const uint32_t e = t.lut[k];
         slut[k] = e;
-        ssym[k] = (e >> 24) ? static_cast<QT>(t.C[e & 0xffffffu] + t.offset) : static_cast<QT>(0);
+        ssym[k] = ((e >> 24) - 1u < static_cast<uint32_t>(kHdLutBits)) ? static_cast<QT>(t.C[e & 0xffffffu] + t.offset) : static_cast<QT>(0);
     }
     __syncthreads();
     const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -169,20 +191,12 @@ __global__ void __launch_bounds__(kHdThreads) k_hd_write(const uint32_t *__restr
         const uint32_t e = slut[idx];
         uint32_t len = e >> 24;
         unsigned long long sym;
-        if (len) {
+        if (len - 1u < static_cast<uint32_t>(kHdLutBits)) {
             sym = ssym[idx];
             br.skip(static_cast<int>(len));
-        } else {   // code longer than the table: walk on bit by bit
-            uint32_t node = e & 0xffffffu;
+        } else {   // code longer than the table
             br.skip(kHdLutBits);
-            len = kHdLutBits;
-            for (;;) {
-                br.refill();
-                node = (br.acc >> 63) ? t.R[node] : t.L[node];
-                br.skip(1);
-                len++;
-                if (t.leaf[node] || len >= 96) break;
-            }
+            const uint32_t node = hd_long_code(br, e, t, &len);
             sym = static_cast<QT>(t.C[node] + t.offset);
         }
         pos += len;
@@ -215,7 +229,7 @@ void launch_hd_sync(const uint32_t *words, unsigned shift, uint64_t total_bits, 
     const uint64_t nsub = hd_num_sub(total_bits);
     const uint64_t nthreads = list_in ? n_in : nsub;
     if (nthreads == 0) return;
-    HdTables t{tb.lut, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
+    HdTables t{tb.lut, tb.lut2, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
     k_hd_sync<<<static_cast<unsigned>((nthreads + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, shift, total_bits, nsub, t,
                                                                                                  over, list_in, n_in, list_out, counts, n_out);
 }
@@ -224,7 +238,7 @@ template <class QT>
 void launch_hd_write(const uint32_t *words, unsigned shift, uint64_t total_bits, const HdDeviceTables &tb, const uint8_t *over,
                      const unsigned long long *offs, uint64_t n, QT *out, cudaStream_t st) {
     const uint64_t nsub = hd_num_sub(total_bits);
-    HdTables t{tb.lut, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
+    HdTables t{tb.lut, tb.lut2, tb.L, tb.R, tb.C, tb.leaf, tb.offset};
     k_hd_write<QT><<<static_cast<unsigned>((nsub + kHdThreads - 1) / kHdThreads), kHdThreads, 0, st>>>(words, shift, total_bits, nsub, t,
                                                                                                   over, offs, n, out);
 }

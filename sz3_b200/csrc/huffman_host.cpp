@@ -313,6 +313,61 @@ bool HuffmanDecoder::load(const uint8_t *&pos, size_t &remaining, const char **e
             lut[pre] = e ? e : node;   // len == 0: continue walking from `node` after kLutBits bits
         }
     }
+    // second level for the device decoder: one global lookup instead of a bit-by-bit walk for codes up to
+    // kLutBits + 12 bits (0.5 % of the symbols of a typical index stream, but every one of them stalled its warp)
+    dlut = lut;
+    lut2.clear();
+    if (!leaf[0]) {
+        // height below every node (iterative post-order; links to node 0 are absent children)
+        std::vector<uint8_t> height(nc, 0);
+        {
+            std::vector<uint32_t> order;
+            order.reserve(nc);
+            std::vector<uint32_t> st{0};
+            std::vector<uint8_t> seen(nc, 0);
+            while (!st.empty()) {
+                const uint32_t v = st.back();
+                st.pop_back();
+                if (seen[v]) continue;
+                seen[v] = 1;
+                order.push_back(v);
+                if (!leaf[v]) {
+                    if (L[v] && !seen[L[v]]) st.push_back(L[v]);
+                    if (R[v] && !seen[R[v]]) st.push_back(R[v]);
+                }
+            }
+            for (size_t i = order.size(); i-- > 0;) {
+                const uint32_t v = order[i];
+                if (leaf[v]) continue;
+                const int hl = L[v] ? height[L[v]] + 1 : 0, hr = R[v] ? height[R[v]] + 1 : 0;
+                height[v] = static_cast<uint8_t>(std::min(255, std::max(hl, hr)));
+            }
+        }
+        constexpr size_t kMaxSecond = static_cast<size_t>(8) << 20;   // entries
+        for (uint32_t pre = 0; pre < (1u << kLutBits); pre++) {
+            const uint32_t e = lut[pre];
+            if ((e >> 24) != 0 || e == 0) continue;   // resolved, or a malformed path left at the root
+            const uint32_t top = e & 0xffffffu;
+            const int S = std::min<int>(12, std::max<int>(1, height[top]));
+            const size_t base = (lut2.size() + 15) & ~static_cast<size_t>(15);
+            if (base + (static_cast<size_t>(1) << S) > kMaxSecond || (base >> 4) >= (1u << 24)) continue;
+            lut2.resize(base + (static_cast<size_t>(1) << S), 0);
+            for (uint32_t sfx = 0; sfx < (1u << S); sfx++) {
+                uint32_t node = top, e2 = 0;
+                for (int b = 0; b < S; b++) {
+                    node = ((sfx >> (S - 1 - b)) & 1u) ? R[node] : L[node];
+                    if (node == 0) break;
+                    if (leaf[node]) {
+                        e2 = (static_cast<uint32_t>(b + 1) << 24) | node;
+                        break;
+                    }
+                }
+                lut2[base + sfx] = e2 ? e2 : node;
+            }
+            dlut[pre] = 0x80000000u | (static_cast<uint32_t>(S) << 24) | static_cast<uint32_t>(base >> 4);
+        }
+    }
+    if (lut2.empty()) lut2.push_back(0);
     return true;
 }
 

@@ -43,6 +43,11 @@ struct HuffmanDecoder {
     std::vector<int> C;
     std::vector<uint8_t> leaf;
     std::vector<uint32_t> lut;   // (len << 24) | node: len > 0 -> leaf `node` reached after len bits; len == 0 -> continue at `node`
+    // Device form of the table, two levels (huffman_decode.cu).  dlut[prefix]: (len << 24) | node as above for codes of
+    // at most kLutBits bits; a longer code has bit 31 set, S = bits 24..30 and base = (bits 0..23) << 4: its next S bits
+    // index lut2[base ..] -- (len2 << 24) | node for a leaf len2 more bits down, or (0 << 24) | node to keep walking
+    // after all S bits.  Prefixes whose sub-table would not fit keep the plain (0 << 24) | node entry.
+    std::vector<uint32_t> dlut, lut2;
     bool load(const uint8_t *&pos, size_t &remaining, const char **err);
     template <class Out>
     bool decode(const uint8_t *&pos, size_t &remaining, size_t n, Out *out, const char **err) const;

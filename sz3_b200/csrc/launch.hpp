@@ -129,7 +129,8 @@ void launch_zhuf_emit(const uint8_t *src, uint64_t len, uint64_t g0, uint64_t g1
 
 // huffman_decode.cu
 struct HdDeviceTables {
-    const uint32_t *lut;
+    const uint32_t *lut;     // HuffmanDecoder::dlut (two-level form)
+    const uint32_t *lut2;    // HuffmanDecoder::lut2
     const uint32_t *L, *R;
     const int *C;
     const uint8_t *leaf;

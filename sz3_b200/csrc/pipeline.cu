@@ -2206,14 +2206,16 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     size_t h = ws.stage_begin("huffman_decode_upload");
     // tables: lut | L | R | C | leaf
     const uint32_t nc = dec.nc;
-    const size_t lut_n = dec.lut.size();
-    const size_t tab_bytes = (lut_n + 3 * static_cast<size_t>(nc)) * 4 + nc + 64;
+    const size_t lut_n = dec.dlut.size(), lut2_n = dec.lut2.size();
+    const size_t tab_bytes = (lut_n + lut2_n + 3 * static_cast<size_t>(nc)) * 4 + nc + 64;
     uint8_t *d_tab = ws.hd_tab.as<uint8_t>(tab_bytes);
     uint32_t *d_lut = reinterpret_cast<uint32_t *>(d_tab);
-    uint32_t *d_L = d_lut + lut_n, *d_R = d_L + nc;
+    uint32_t *d_lut2 = d_lut + lut_n;
+    uint32_t *d_L = d_lut2 + lut2_n, *d_R = d_L + nc;
     int *d_C = reinterpret_cast<int *>(d_R + nc);
     uint8_t *d_leaf = reinterpret_cast<uint8_t *>(d_C + nc);
-    ws.h2d(d_lut, dec.lut.data(), lut_n * 4);
+    ws.h2d(d_lut, dec.dlut.data(), lut_n * 4);
+    ws.h2d(d_lut2, dec.lut2.data(), lut2_n * 4);
     ws.h2d(d_L, dec.L.data(), nc * 4);
     ws.h2d(d_R, dec.R.data(), nc * 4);
     ws.h2d(d_C, dec.C.data(), nc * 4);
@@ -2243,7 +2245,7 @@ static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
     unsigned long long *d_offs = ws.hd_offs.as<unsigned long long>(2 * (nsub + 2) + scan_scratch_words(nsub));
     unsigned long long *d_moved = ws.counters.as<unsigned long long>(4);
     SZ3B_CUDA(cudaMemsetAsync(d_over, 0, over_bytes, ws.st));
-    HdDeviceTables tb{d_lut, d_L, d_R, d_C, d_leaf, dec.offset};
+    HdDeviceTables tb{d_lut, d_lut2, d_L, d_R, d_C, d_leaf, dec.offset};
     ws.stage_end(h, 0);
     h = ws.stage_begin("huffman_decode_sync");
     uint8_t *in = d_over;
