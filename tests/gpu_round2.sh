@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,memory.total --format=csv,noheader; nproc
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -3 gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>/dev/null; cat gpurun_out/bench_ref_$TAG.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$TAG.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_interp_box -s 4 -c 1 -o gpurun_out/prof_box_$TAG \
     python tools/prof_decompose.py 0 1 > gpurun_out/ncu_full_$TAG.log 2>&1
