@@ -206,18 +206,68 @@ __global__ void __launch_bounds__(256) k_interp_recover_pass(RecoverArgs<T, QT> 
 // ---------------------------------------------------------------------------------------------------------------------
 // pred_and_recover_coefficients (RegressionPredictor.hpp:157-165): current = recover(current, index); the running
 // value is the previous block's coefficient.  coef_unp[pos] holds the stored exact value where coef_q[pos] == 0.
+// The recurrence is serial in the blocks (every step rounds), but everything except the dependent add can be taken
+// off it: a CTA stages chunks of blocks in shared memory -- the step 2 (q - radius) eb of every coefficient, computed
+// by all threads from coalesced loads -- then one lane per coefficient walks the chunk (an add and a select per
+// block, operands prefetched from shared memory), and the recovered coefficients leave coalesced.  (One lane reading
+// its index from global memory block by block paid a memory latency per block: 37 ms for the 262 144 blocks of C3.)
+constexpr int kRcChunk = 256;
+constexpr int kRcThreads = 128;
 template <class T>
-__global__ void __launch_bounds__(32) k_reg_chain_recover(const int32_t *__restrict__ coef_q, const T *__restrict__ coef_unp,
-                                                          uint64_t nblocks, int N, QuantParams q_liner, QuantParams q_indep,
-                                                          T *__restrict__ c_rec) {
-    const int lane = threadIdx.x, nc = N + 1;
-    if (lane >= nc) return;
-    const QuantParams qp = lane < N ? q_liner : q_indep;
+__global__ void __launch_bounds__(kRcThreads) k_reg_chain_recover(const int32_t *__restrict__ coef_q, const T *__restrict__ coef_unp,
+                                                                  uint64_t nblocks, int N, QuantParams q_liner, QuantParams q_indep,
+                                                                  T *__restrict__ c_rec) {
+    __shared__ double sd[kRcChunk * (kMaxDim + 1)];
+    __shared__ T sv[kRcChunk * (kMaxDim + 1)];         // the stored exact value where q == 0
+    __shared__ T so[kRcChunk * (kMaxDim + 1)];         // the recovered coefficients (an array of their own: the walk's
+                                                       // loads must not wait for its stores)
+    __shared__ uint8_t sz[kRcChunk * (kMaxDim + 1)];   // q == 0
+    const int tid = threadIdx.x, nc = N + 1;
     T cur = 0;
-    for (uint64_t b = 0; b < nblocks; b++) {
-        const int qv = coef_q[b * nc + lane];
-        cur = qv ? recover_pred<T>(cur, qv, qp) : coef_unp[b * nc + lane];
-        c_rec[b * nc + lane] = cur;
+    for (uint64_t base = 0; base < nblocks; base += kRcChunk) {
+        const uint32_t cnt = static_cast<uint32_t>(nblocks - base < kRcChunk ? nblocks - base : kRcChunk);
+        const uint32_t m = cnt * nc;
+        for (uint32_t i = tid; i < m; i += kRcThreads) {
+            const int qv = coef_q[base * nc + i];
+            const QuantParams &qp = static_cast<int>(i % nc) < N ? q_liner : q_indep;
+            sz[i] = qv == 0;
+            sd[i] = static_cast<double>(2 * (qv - qp.radius)) * qp.eb;
+            if (qv == 0) sv[i] = coef_unp[base * nc + i];
+        }
+        __syncthreads();
+        if (tid < nc) {
+            // eight blocks at a time: operands into registers first, then the eight dependent steps
+            // (recover_pred, core.cuh: pred + 2 (q - radius) eb in double, stored as T), then the results
+            for (uint32_t i0 = 0; i0 < cnt; i0 += 8) {
+                double d[8];
+                T u[8], r[8];
+                bool z[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {   // (reads past `cnt` stay inside the arrays; their results are dropped)
+                    const uint32_t k = (i0 + j) * nc + tid;
+                    d[j] = sd[k];
+                    u[j] = sv[k];
+                    z[j] = sz[k] != 0;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const T step = from_double<T>(static_cast<double>(cur) + d[j]);
+                    cur = z[j] ? u[j] : step;
+                    r[j] = cur;
+                }
+                T last = cur;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (i0 + j < cnt) {
+                        so[(i0 + j) * nc + tid] = r[j];
+                        last = r[j];
+                    }
+                cur = last;   // (differs from r[7] only in a ragged last group)
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < m; i += kRcThreads) c_rec[base * nc + i] = so[i];
+        __syncthreads();
     }
 }
 
@@ -304,7 +354,7 @@ void launch_interp_recover(const InterpShape &sh, T *out, const QT *q, const T *
 template <class T>
 void launch_reg_chain_recover(const int32_t *coef_q, const T *coef_unp, uint64_t nblocks, int N, const QuantParams &q_liner,
                               const QuantParams &q_indep, T *c_rec, cudaStream_t st) {
-    k_reg_chain_recover<T><<<1, 32, 0, st>>>(coef_q, coef_unp, nblocks, N, q_liner, q_indep, c_rec);
+    k_reg_chain_recover<T><<<1, kRcThreads, 0, st>>>(coef_q, coef_unp, nblocks, N, q_liner, q_indep, c_rec);
 }
 
 template <class T, class QT>

@@ -2187,11 +2187,13 @@ static void quantizer_load(Cursor &c, double *eb, int *radius, const T **unpred,
 // The tree is parsed on the host (a few thousand nodes); the bitstream is decoded on the GPU by the self-synchronising
 // decoder of huffman_decode.cu.  The host table decoder remains only for the degenerate one-symbol tree.
 template <class QT>
-static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n) {
+static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n, bool has_count = true) {
     HuffmanDecoder dec;
     const char *err = nullptr;
     if (!dec.load(c.p, c.rem, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
-    const uint64_t n = c.get<uint64_t>();
+    // (the main stream carries its symbol count between the tree and the bits, SZGenericCompressor.hpp:53; a
+    //  predictor's side stream does not -- RegressionPredictor::save wrote it up front)
+    const uint64_t n = has_count ? c.get<uint64_t>() : expect_n;
     if (n != expect_n) fail(SZ3B_E_INVALID_ARGUMENT, "index count does not match the array size");
     QT *d_q = ws.q.as<QT>(n);
     if (dec.leaf[0]) {   // every index identical: no bits in the stream (HuffmanEncoder.hpp:233-237)
@@ -2493,15 +2495,20 @@ static void blockwise_decompress_t(Workspace &ws, const sz3b_config &conf, Curso
     uint64_t nun_i, nun_l;
     quantizer_load<T>(c, &eb_i, &rad_i, &un_i, &nun_i);
     quantizer_load<T>(c, &eb_l, &rad_l, &un_l, &nun_l);
-    std::vector<int32_t> cq(n_coef);
+    // the coefficient indices through the GPU decoder as well (a million symbols took the host decoder ~10 ms); they
+    // come back through pinned memory for the one serial step left: handing out the stored exact coefficients
+    int32_t *d_cq = ws.coef_q.as<int32_t>(n_coef);
     {
-        HuffmanDecoder dec;
-        const char *err = nullptr;
-        if (!dec.load(c.p, c.rem, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
-        if (!dec.decode<int32_t>(c.p, c.rem, n_coef, cq.data(), &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+        uint32_t *d_tmpq = decode_indices<uint32_t>(ws, c, n_coef, false);   // (in ws.q, which the main indices take next)
+        SZ3B_CUDA(cudaMemcpyAsync(d_cq, d_tmpq, n_coef * sizeof(int32_t), cudaMemcpyDeviceToDevice, ws.st));
     }
+    uint8_t *pin = static_cast<uint8_t *>(ws.stage2.ensure(n_coef * (sizeof(int32_t) + sizeof(T)) + 64));
+    int32_t *cq = reinterpret_cast<int32_t *>(pin);
+    T *cun = reinterpret_cast<T *>(pin + ((n_coef * sizeof(int32_t) + 15) & ~static_cast<size_t>(15)));
+    ws.d2h(cq, d_cq, n_coef * sizeof(int32_t));
+    SZ3B_CUDA(stream_wait(ws.st));
     // stored exact coefficients, by position (both quantizers consume their lists in block order)
-    std::vector<T> cun(n_coef, 0);
+    memset(cun, 0, n_coef * sizeof(T));
     {
         uint64_t ki = 0, kl = 0;
         for (uint64_t pos = 0; pos < n_coef; pos++)
@@ -2524,11 +2531,9 @@ static void blockwise_decompress_t(Workspace &ws, const sz3b_config &conf, Curso
     QT *d_q = decode_indices<QT>(ws, c, bs.num);
     int launches = 0;
     size_t h = ws.stage_begin("recover");
-    int32_t *d_cq = ws.coef_q.as<int32_t>(n_coef);
     T *d_cun = ws.coef.as<T>(n_coef);
     T *d_crec = ws.coef2.as<T>(n_coef);
-    ws.h2d(d_cq, cq.data(), n_coef * sizeof(int32_t));
-    ws.h2d(d_cun, cun.data(), n_coef * sizeof(T));
+    ws.h2d(d_cun, cun, n_coef * sizeof(T));
     launch_reg_chain_recover<T>(d_cq, d_cun, bs.nblocks, N, make_quant(eb_l, rad_l), make_quant(eb_i, rad_i), d_crec, ws.st);
     T *d_tmp = place_unpred<T, QT>(ws, d_q, bs.num, h_unpred, n_unpred, &launches);
     if (const char *e = launch_reg_recover<T, QT>(d_out, bs, d_crec, make_quant(eb, radius), d_q, d_tmp, ws.st))
