@@ -186,16 +186,23 @@ struct Workspace {
     PinBuf upload_ring;   // staging ring of upload_pageable (pipeline.cu)
     size_t upload_used = 0;
     static constexpr size_t kUploadArena = static_cast<size_t>(16) << 20;
+    // Small uploads (code tables, block tables, headers: host vectors) go through a pinned arena: the copy is then truly
+    // asynchronous (a cudaMemcpyAsync from pageable memory stages and synchronises inside the driver, tens of
+    // microseconds each on the critical path), and while the bulk input copy owns the H2D engine an SM copy kernel
+    // reads the arena instead of queueing behind it.
     void h2d(void *dst, const void *src, size_t bytes) {
         h2d_bytes += bytes;
-        if (bulk_copy_in_flight && bytes <= (static_cast<size_t>(2) << 20)) {
+        if (bytes <= (static_cast<size_t>(2) << 20)) {
             const size_t need = (bytes + 255) & ~static_cast<size_t>(255);
             unsigned char *arena = static_cast<unsigned char *>(upload_arena.ensure(kUploadArena));
-            if (upload_used + need <= kUploadArena && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            if (upload_used + need <= kUploadArena) {
                 unsigned char *slot = arena + upload_used;
                 upload_used += need;
                 memcpy(slot, src, bytes);
-                launch_upload_bytes(dst, slot, bytes, st);
+                if (bulk_copy_in_flight && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
+                    launch_upload_bytes(dst, slot, bytes, st);
+                else
+                    SZ3B_CUDA(cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, st));
                 return;
             }
         }
