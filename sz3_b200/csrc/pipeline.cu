@@ -9,6 +9,8 @@
 // but every data-proportional loop is a CUDA kernel; the host only builds the Huffman tree from the histogram,
 // lays out the byte stream and runs zstd.  There is no CPU implementation of the kernels to fall back to.
 #include <cuda_runtime.h>
+
+#include <functional>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -70,6 +72,7 @@ Workspace *workspace_acquire() {
 void workspace_release(Workspace *ws) {
     // a call that failed half-way may still have its background copy / kernels in flight on this workspace's buffers
     if (ws->st_copy) stream_wait(ws->st_copy);
+    if (ws->st_low) stream_wait(ws->st_low);
     if (ws->st) stream_wait(ws->st);
     cudaGetLastError();
     std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -1249,7 +1252,8 @@ void tune_stage(Workspace &ws, sz3b_config &conf, const T *data, int loc) {
 // The regression-only stack runs on blockwise.cu (fit, speculative coefficient chain, fused predict+quantize); every
 // stack with a Lorenzo predictor on the block wavefront of lorenzo.cu (run_blockwise_lorenzo below).
 // ---------------------------------------------------------------------------------------------------------------------
-void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vector<uint8_t> &out, size_t *tree_len);
+void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vector<uint8_t> &out, size_t *tree_len,
+                           const std::function<void()> *after_hist = nullptr);
 
 // LinearQuantizer::save (LinearQuantizer.hpp:95-104)
 template <class T>
@@ -1284,7 +1288,8 @@ static void fetch_coef_unpred(Workspace &ws, unsigned long long n_unp, const uns
 // device (dense), the stored exact coefficients as (dense position, value).
 template <class T>
 static void regression_save(Workspace &ws, int N, unsigned long long nsel, std::vector<std::pair<unsigned long long, T>> &unp,
-                            const int32_t *coef_q, double eb_indep, double eb_liner, std::vector<uint8_t> &pred_blob) {
+                            const int32_t *coef_q, double eb_indep, double eb_liner, std::vector<uint8_t> &pred_blob,
+                            const std::function<void()> *after_hist = nullptr) {
     const int nc = N + 1;
     const int kCoefRadius = 32768;
     const uint64_t n_coef = nsel * nc;
@@ -1305,8 +1310,10 @@ static void regression_save(Workspace &ws, int N, unsigned long long nsel, std::
         quantizer_save<T>(pred_blob, eb_indep, kCoefRadius, un_indep);
         quantizer_save<T>(pred_blob, eb_liner, kCoefRadius, un_liner);
         std::vector<uint8_t> side;
-        huffman_encode_device(ws, coef_q, n_coef, side, nullptr);
+        huffman_encode_device(ws, coef_q, n_coef, side, nullptr, after_hist);
         pred_blob.insert(pred_blob.end(), side.begin(), side.end());
+    } else if (after_hist) {
+        (*after_hist)();
     }
 }
 
@@ -1649,19 +1656,37 @@ static void run_blockwise(Workspace &ws, const sz3b_config &conf, double eb, con
     SZ3B_CUDA(stream_wait(ws.st));
     SZ3B_CUDA(cudaGetLastError());
     *launches += 2;
+    // The data prediction needs the reconstructed coefficients only, not their encoded side stream: it is launched (on
+    // a second stream) once the side stream's histogram kernels are queued, and runs while the host builds that
+    // stream's tree (2 ms for C3's coefficient indices).
+    cudaStream_t st_main = ws.st, st_pred = ws.low_priority_stream();
+    cudaEvent_t ev_chain = ws.event(), ev_pred = ws.event();
+    SZ3B_CUDA(cudaEventRecord(ev_chain, st_main));
+    const char *perr = nullptr;
+    const std::function<void()> launch_predict = [&]() {
+        SZ3B_CUDA(cudaStreamWaitEvent(st_pred, ev_chain, 0));
+        ws.st = st_pred;   // (stage events and the launch go to the second stream)
+        try {
+            const size_t hp = ws.stage_begin("predict_quantize");
+            SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
+            perr = launch_reg_predict<T, QT>(d_data, bs, c_rec, make_quant(eb, conf.quantbinCnt / 2), d_q, d_unpred_tmp, d_hist, ws.st);
+            ws.stage_end(hp, 1);
+            SZ3B_CUDA(cudaEventRecord(ev_pred, st_pred));
+        } catch (...) {
+            ws.st = st_main;
+            throw;
+        }
+        ws.st = st_main;
+    };
+    *launches += 1;
     std::vector<std::pair<unsigned long long, T>> unp;
     double t_side = now_ms();
     fetch_coef_unpred<T>(ws, hc[1], upos, uval, hc[0] * nc, unp);
-    regression_save<T>(ws, N, hc[0], unp, coef_q, eb_indep, eb_liner, pred_blob);
+    regression_save<T>(ws, N, hc[0], unp, coef_q, eb_indep, eb_liner, pred_blob, &launch_predict);
     ws.host_stage("regression_side_stream_wall", now_ms() - t_side);
-    h = ws.stage_begin("predict_quantize");
-    SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
-    if (const char *e = launch_reg_predict<T, QT>(d_data, bs, c_rec, make_quant(eb, conf.quantbinCnt / 2), d_q,
-                                                  d_unpred_tmp, d_hist, ws.st))
-        fail(SZ3B_E_UNSUPPORTED, e);
-    ws.stage_end(h, 1);
+    if (perr) fail(SZ3B_E_UNSUPPORTED, perr);
+    SZ3B_CUDA(cudaStreamWaitEvent(st_main, ev_pred, 0));
     SZ3B_CUDA(cudaGetLastError());
-    *launches += 1;
 }
 
 template <class T>
@@ -2749,7 +2774,8 @@ void interp_decompose_stage(Workspace &ws, const sz3b_config &conf, double eb, c
 }
 
 // HuffmanEncoder<int> on an arbitrary int32 stream (side streams, tests)
-void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vector<uint8_t> &out, size_t *tree_len) {
+void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vector<uint8_t> &out, size_t *tree_len,
+                           const std::function<void()> *after_hist) {
     if (n == 0) fail(SZ3B_E_INVALID_ARGUMENT, "Huffman bins should not be empty");
     int *d_mm = ws.misc.as<int>(2);
     int init[2] = {0x7fffffff, static_cast<int>(0x80000000)};
@@ -2766,6 +2792,7 @@ void huffman_encode_device(Workspace &ws, const int32_t *d_q, size_t n, std::vec
     SZ3B_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, ws.st));
     launch_histogram<int32_t>(d_q, n, mm[0], nbins, nbins / 2, d_hist, ws.st);
     ws.stage_end(h, 2);
+    if (after_hist) (*after_hist)();   // (work the caller wants on the device while the host builds the tree)
     HuffmanBook book;
     EncodeLayout lay;
     encode_indices<int32_t, float>(ws, d_q, n, d_hist, nbins, mm[0], false, nullptr, book, lay);

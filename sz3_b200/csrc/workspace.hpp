@@ -126,6 +126,16 @@ struct Workspace {
     int device = 0;
     cudaStream_t st = nullptr;
     cudaStream_t st_copy = nullptr;   // bulk H2D of the input, so that sampling/tuning can overlap it
+    cudaStream_t st_low = nullptr;    // lowest-priority compute stream (created on first use): bulk kernels that may run
+                                      // under latency-critical small ones of `st`
+    cudaStream_t low_priority_stream() {
+        if (!st_low) {
+            int least = 0, greatest = 0;
+            SZ3B_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            SZ3B_CUDA(cudaStreamCreateWithPriority(&st_low, cudaStreamNonBlocking, least));
+        }
+        return st_low;
+    }
     // decompression: the zstd-decoded stream (host, pinned) and its mirror in device memory, uploaded frame by frame
     // while the other frames are still being decoded (pipeline.cu: decompress_one); null when there is no mirror
     const uint8_t *raw_host = nullptr;
