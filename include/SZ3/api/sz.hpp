@@ -8,6 +8,7 @@
 #ifndef SZ3_SZ_HPP
 #define SZ3_SZ_HPP
 
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -19,14 +20,20 @@
 
 namespace SZ3 {
 namespace b200 {
+// SZ_FLOAT ... SZ_INT64 (def.hpp) of the element type.  The templates instantiate for every arithmetic type the
+// reference's callers use (tools/H5Z-SZ3/src/H5Z_SZ3.cpp:195-225 switches over ten of them); the GPU path is built for
+// float, double, int32_t and int64_t, the others are refused at run time (SZ3B_E_UNSUPPORTED -> std::runtime_error).
 template <class T>
 constexpr int dtype_of() {
-    static_assert(std::is_same<T, float>::value || std::is_same<T, double>::value || std::is_same<T, int32_t>::value ||
-                      std::is_same<T, int64_t>::value,
-                  "sz3_b200: the GPU path is built for float, double, int32_t and int64_t");
-    return std::is_same<T, float>::value ? SZ3B_FLOAT
-           : std::is_same<T, double>::value ? SZ3B_DOUBLE
-           : std::is_same<T, int32_t>::value ? SZ3B_INT32 : SZ3B_INT64;
+    static_assert(std::is_arithmetic<T>::value, "sz3_b200: SZ_compress / SZ_decompress take arithmetic element types");
+    return std::is_same<T, float>::value    ? 0
+           : std::is_same<T, double>::value ? 1
+           : std::is_integral<T>::value
+               ? (sizeof(T) == 1 ? (std::is_signed<T>::value ? 3 : 2)
+                  : sizeof(T) == 2 ? (std::is_signed<T>::value ? 5 : 4)
+                  : sizeof(T) == 4 ? (std::is_signed<T>::value ? 7 : 6)
+                                   : (std::is_signed<T>::value ? 9 : 8))
+               : -1;
 }
 inline void raise(int rc) {
     if (rc == SZ3B_OK) return;

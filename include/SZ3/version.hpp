@@ -16,19 +16,17 @@
 #define SZ3_DATA_VER "3.3.2"
 #define SZ3_MAGIC_NUMBER 0xF342F310u
 
-namespace SZ3 {
+// (global functions, as in the reference: callers such as tools/H5Z-SZ3/src/H5Z_SZ3.cpp:147 use them unqualified)
 // "a.b.c" -> a<<24 | b<<16 | c<<8
 inline uint32_t versionInt(const std::string &version) {
-    uint32_t v[4] = {0, 0, 0, 0};
-    std::istringstream ss(version);
-    std::string part;
-    for (int i = 0; i < 4 && std::getline(ss, part, '.'); i++) v[i] = static_cast<uint32_t>(std::stoul(part));
-    return (v[0] << 24) | (v[1] << 16) | (v[2] << 8) | v[3];
+    uint32_t major = 0, minor = 0, patch = 0;
+    char dot;
+    std::stringstream ss(version);
+    ss >> major >> dot >> minor >> dot >> patch;
+    return (major << 24) | (minor << 16) | (patch << 8);
 }
-inline std::string versionStr(uint32_t v) {
-    std::ostringstream ss;
-    ss << ((v >> 24) & 0xff) << "." << ((v >> 16) & 0xff) << "." << ((v >> 8) & 0xff) << "." << (v & 0xff);
-    return ss.str();
+inline std::string versionStr(uint32_t version) {
+    return std::to_string((version >> 24) & 0xFF) + "." + std::to_string((version >> 16) & 0xFF) + "." +
+           std::to_string((version >> 8) & 0xFF);
 }
-}  // namespace SZ3
 #endif

@@ -66,7 +66,10 @@ void check_dtype_any(int dtype) {
     if (dtype != SZ3B_FLOAT && dtype != SZ3B_DOUBLE && dtype != SZ3B_INT32 && dtype != SZ3B_INT64)
         fail(SZ3B_E_UNSUPPORTED, "element types on the GPU path: float32, float64, int32, int64");
 }
-size_t dtype_size(int dtype) { return dtype == SZ3B_FLOAT || dtype == SZ3B_INT32 ? 4 : 8; }
+size_t dtype_size(int dtype) {   // SZ_FLOAT .. SZ_INT64 (def.hpp): sizes for the capacity rule, supported or not
+    static const size_t sz[10] = {4, 8, 1, 1, 2, 2, 4, 4, 8, 8};
+    return dtype >= 0 && dtype < 10 ? sz[dtype] : 8;
+}
 // f(T *) for the element type of `dtype` (a null pointer used as a type tag)
 template <class F>
 auto by_dtype(int dtype, F &&f) {
