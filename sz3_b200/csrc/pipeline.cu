@@ -188,6 +188,16 @@ UploadChain &upload_chain(int device) {
     static UploadChain chains[64];
     return chains[device >= 0 && device < 64 ? device : 0];
 }
+}  // namespace
+bool device_upload_busy(int device) {
+    UploadChain &c = upload_chain(device);
+    if (!c.mu.try_lock()) return true;   // someone is enqueueing a bulk upload right now
+    const bool busy = c.any && c.ring[c.head] && cudaEventQuery(c.ring[c.head]) == cudaErrorNotReady;
+    cudaGetLastError();
+    c.mu.unlock();
+    return busy;
+}
+namespace {
 struct UploadTurn {   // holds the chain while one call enqueues its copies on its copy stream
     UploadChain &c;
     cudaStream_t st;
@@ -2215,7 +2225,11 @@ template <class QT>
 static QT *decode_indices(Workspace &ws, Cursor &c, uint64_t expect_n, bool has_count = true) {
     HuffmanDecoder dec;
     const char *err = nullptr;
-    if (!dec.load(c.p, c.rem, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+    {
+        const double t0 = now_ms();
+        if (!dec.load(c.p, c.rem, &err)) fail(SZ3B_E_INVALID_ARGUMENT, err);
+        ws.host_stage("huffman_tables_host", now_ms() - t0);
+    }
     // (the main stream carries its symbol count between the tree and the bits, SZGenericCompressor.hpp:53; a
     //  predictor's side stream does not -- RegressionPredictor::save wrote it up front)
     const uint64_t n = has_count ? c.get<uint64_t>() : expect_n;

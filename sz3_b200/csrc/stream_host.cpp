@@ -423,11 +423,52 @@ void djob_worker(void *arg, int) {
         size_t k = j.next.fetch_add(1);
         if (k >= j.frames.size()) break;
         const DFrame &f = j.frames[k];
-        size_t r = ZSTD_decompress(j.dst + f.off, f.dsize, f.src, f.csize);
-        if (ZSTD_isError(r) || r != f.dsize)
+        if (!j.done) {
+            size_t r = ZSTD_decompress(j.dst + f.off, f.dsize, f.src, f.csize);
+            if (ZSTD_isError(r) || r != f.dsize) j.failed = true;
+            continue;
+        }
+        // with a listener: streaming decompression, so that every 256 KiB of the frame is reported (and travels on)
+        // while the rest is still being decoded
+        thread_local ZSTD_DCtx *dctx = nullptr;
+        if (!dctx) dctx = ZSTD_createDCtx();
+        if (!dctx) {
             j.failed = true;
-        else if (j.done)
-            j.done->frame(f.off, f.dsize);
+            continue;
+        }
+        ZSTD_outBuffer out{j.dst + f.off, f.dsize, 0};
+        size_t in_pos = 0, reported = 0, window = static_cast<size_t>(160) << 10;
+        bool ok = true;
+        for (;;) {
+            // (input is offered a block or so at a time: one call with the whole frame would decode all of it before
+            //  returning)
+            ZSTD_inBuffer piece{f.src, std::min(f.csize, in_pos + window), in_pos};
+            const size_t prev_out = out.pos;
+            const size_t r = ZSTD_decompressStream(dctx, &out, &piece);
+            if (ZSTD_isError(r)) {
+                ok = false;
+                break;
+            }
+            const bool progress = piece.pos > in_pos || out.pos > prev_out;
+            in_pos = piece.pos;
+            if (out.pos - reported >= (static_cast<size_t>(256) << 10) || r == 0 || out.pos == f.dsize) {
+                if (out.pos > reported) j.done->frame(f.off + reported, out.pos - reported);
+                reported = out.pos;
+            }
+            if (r == 0) break;   // frame complete
+            if (!progress) {
+                if (piece.size >= f.csize) {   // everything was on offer: truncated or oversized frame
+                    ok = false;
+                    break;
+                }
+                window *= 2;
+            }
+        }
+        if (!ok || out.pos != f.dsize) {
+            j.failed = true;
+            ZSTD_freeDCtx(dctx);   // (a context left in mid-frame state is not reused)
+            dctx = nullptr;
+        }
     }
 }
 }  // namespace

@@ -84,6 +84,9 @@ struct DevBuf {
     }
 };
 
+// true while a bulk input upload of any call is still on this device's H2D engine (pipeline.cu: UploadChain)
+bool device_upload_busy(int device);
+
 struct PinBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -209,7 +212,9 @@ struct Workspace {
                 unsigned char *slot = arena + upload_used;
                 upload_used += need;
                 memcpy(slot, src, bytes);
-                if (bulk_copy_in_flight && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
+                // (this call's bulk copy, or another caller's on the same device: a copy command would queue behind
+                //  that caller's whole array)
+                if ((bulk_copy_in_flight || device_upload_busy(device)) && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
                     launch_upload_bytes(dst, slot, bytes, st);
                 else
                     SZ3B_CUDA(cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, st));

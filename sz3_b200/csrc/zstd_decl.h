@@ -20,6 +20,21 @@ ZSTD_CCtx *ZSTD_createCCtx(void);
 size_t ZSTD_freeCCtx(ZSTD_CCtx *cctx);
 size_t ZSTD_compressCCtx(ZSTD_CCtx *cctx, void *dst, size_t dstCapacity, const void *src, size_t srcSize,
                          int compressionLevel);
+/* streaming decompression (stable API): output becomes available block by block */
+typedef struct ZSTD_DCtx_s ZSTD_DCtx;
+typedef struct ZSTD_inBuffer_s {
+    const void *src;
+    size_t size;
+    size_t pos;
+} ZSTD_inBuffer;
+typedef struct ZSTD_outBuffer_s {
+    void *dst;
+    size_t size;
+    size_t pos;
+} ZSTD_outBuffer;
+ZSTD_DCtx *ZSTD_createDCtx(void);
+size_t ZSTD_freeDCtx(ZSTD_DCtx *dctx);
+size_t ZSTD_decompressStream(ZSTD_DCtx *zds, ZSTD_outBuffer *output, ZSTD_inBuffer *input);
 const char *ZSTD_getErrorName(size_t code);
 unsigned ZSTD_versionNumber(void);
 #ifdef __cplusplus

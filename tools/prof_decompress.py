@@ -23,9 +23,11 @@ assert L.sz3b_compress(0, C.byref(conf), C.c_void_p(dev.data_ptr()), 1, C.c_void
 out = torch.empty(data.size, dtype=torch.float32, device="cuda")
 names, ms, ln = (C.c_char_p * 64)(), (C.c_double * 64)(), (C.c_int * 64)()
 c2 = Config()
+import time
 for r in range(reps):
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
     rc = L.sz3b_decompress(0, C.c_void_p(cmp.data_ptr()), C.c_size_t(size.value), C.c_void_p(out.data_ptr()), 1, C.byref(c2))
     assert rc == 0, L.sz3b_last_error()
     k = L.sz3b_last_profile(names, ms, ln, 64)
-    print(r, {names[i].decode(): (round(ms[i], 4), ln[i]) for i in range(k)})
+    print(r, f"{(time.perf_counter() - t0) * 1e3:.2f} ms wall", {names[i].decode(): (round(ms[i], 4), ln[i]) for i in range(k)})
