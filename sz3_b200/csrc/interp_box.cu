@@ -192,6 +192,70 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
     BOX_TICK(9);
 }
 
+// recover, last pass of the finest level (interp_box.cuh: box_recover_row): one CTA per tile, warp per plane; `out` is
+// both the source of the planes (tensor map over it) and the destination of the odd-x points.
+constexpr size_t kBoxRecSmem = sizeof(float) * (kBoxWarps * kBoxSlotStride) + sizeof(uint16_t) * kBoxWarps * kBoxStageU16 +
+                               sizeof(uint64_t) * kBoxWarps;
+template <bool CUBIC>
+__global__ void __launch_bounds__(kBoxThreads, 2) k_box_recover_x(const __grid_constant__ CUtensorMap tmap, BoxArgs A, BoxSrc S, float *out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *const slots = reinterpret_cast<float *>(smem_raw);
+    uint16_t *const stages = reinterpret_cast<uint16_t *>(slots + kBoxWarps * kBoxSlotStride);
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(stages + kBoxWarps * kBoxStageU16);
+    __shared__ BoxTile T;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t tile = blockIdx.x + A.tile0;
+    BoxOrigin o;
+    box_origin(A, S, tile, o);
+    float *const slot = slots + warp * kBoxSlotStride;
+    uint16_t *const stage = stages + warp * kBoxStageU16;
+    uint64_t *const bar = bars + warp;
+    const uint32_t nz = o.n[0];
+    uint32_t z = (o.begin[0] ? 1u : 0u) + warp;
+    const int x0 = static_cast<int>(o.begin[2]), y0 = static_cast<int>(o.begin[1]), z0 = static_cast<int>(o.begin[0]);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        if (z < nz) {
+            mbar_expect_tx(bar, kBoxPlaneBytes);
+            tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z));
+        }
+    }
+    if (tid == 0) box_tile_setup<CUBIC>(A, tile, o, T);
+    __syncthreads();
+    const uint32_t lowy = T.low[1], c1y = T.c1[1];
+    unsigned parity = 0;
+    for (; z < nz; z += kBoxWarps) {
+        box_copy_in(A, T, lane, z, stage);
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        __syncwarp();
+        float v[36];
+        float *const my_row = slot + (lane + lowy) * kBoxPitch;
+        if (lane < c1y) {
+            const float4 *row = reinterpret_cast<const float4 *>(my_row);
+#pragma unroll
+            for (int c = 0; c < 9; c++) {
+                const float4 f = row[c];
+                v[4 * c] = f.x;
+                v[4 * c + 1] = f.y;
+                v[4 * c + 2] = f.z;
+                v[4 * c + 3] = f.w;
+            }
+        }
+        box_recover_left<CUBIC>(A, T, lane, z, slot, stage);
+        if (lane < c1y) box_recover_row<CUBIC>(A, T, lane, z, v, stage, my_row);
+        __syncwarp();
+        box_recover_out(S, T, lane, z, slot, out);
+        __syncwarp();
+        if (z + kBoxWarps < nz && lane == 0) {   // the slot is free again: the warp's next plane
+            fence_proxy_async();
+            mbar_expect_tx(bar, kBoxPlaneBytes);
+            tma_plane(slot, &tmap, bar, x0, y0, z0 + static_cast<int>(z + kBoxWarps));
+        }
+    }
+}
+
 // Compact copies of the coarse lattices: dst_k[z][y][x] = src[z * s_k][y * s_k][x * s_k] for up to three strides
 // s_0 < s_1 < s_2 (each twice the previous).  A single tile of a coarse level would gather its ~36 k scattered sectors
 // with one SM (tens of microseconds of pure latency); here the whole GPU does it once, and the levels then read dense
@@ -294,6 +358,43 @@ bool interp_launch_box(const BoxArgs &A, const BoxSrc &S, const uint32_t sdims[3
         k_interp_box<true><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A, S);
     else
         k_interp_box<false><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A, S);
+    return true;
+}
+
+// Last pass (along x) of the finest level in recover mode, tiles [A.tile0, A.tile0 + ntiles): A.q = the decoded
+// indices, A.unpred_tmp = the stored values by stream position, `out` = the output array (dims A.sh.dims), whose even-x
+// points of the level are final.  Returns false where the kernel does not apply (the caller keeps its per-pass kernel).
+bool interp_launch_box_recover_x(const BoxArgs &A, float *out, uint64_t ntiles, cudaStream_t st) {
+    if (A.s != 1 || !interp_box_applicable(A)) return false;
+    if ((A.sh.dims[2] & 3u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return false;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    BoxSrc S;
+    memset(&S, 0, sizeof(S));
+    S.p = out;
+    for (int d = 0; d < 3; d++) S.ost[d] = S.st[d] = A.sh.stride[d];
+    S.odiv = 1;
+    S.tma = 1;
+    S.split = 1;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    const cuuint64_t gdim[3] = {A.sh.dims[2], A.sh.dims[1], A.sh.dims[0]};
+    const cuuint64_t gstr[2] = {A.sh.stride[1] * sizeof(float), A.sh.stride[0] * sizeof(float)};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(kBoxPitch), 33u, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    static std::atomic<unsigned long long> attr_set{0};
+    once_per_device(attr_set, [&] {
+        cudaFuncSetAttribute(k_box_recover_x<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxRecSmem));
+        cudaFuncSetAttribute(k_box_recover_x<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBoxRecSmem));
+    });
+    const dim3 grid(static_cast<unsigned>(ntiles));
+    if (A.sh.cubic)
+        k_box_recover_x<true><<<grid, kBoxThreads, kBoxRecSmem, st>>>(map, A, S, out);
+    else
+        k_box_recover_x<false><<<grid, kBoxThreads, kBoxRecSmem, st>>>(map, A, S, out);
     return true;
 }
 

@@ -689,4 +689,152 @@ SZ_HD void box_copy_out(const BoxArgs &A, const BoxTile &T, uint32_t lane, uint3
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// recover, last pass (along x) of the finest level.  The box schedule as a whole does not carry over to
+// decompression (a tile would need the reconstructions of its low faces from its neighbours), but its last phase
+// does: once passes 0 and 1 of the level are complete everywhere, the targets of a row depend on that row's even-x
+// points alone.  Same mapping as pass 2 above -- warp per plane, the plane by one TMA box copy (from the output array
+// itself), lane = row, the row in registers, the plane's run of main-phase indices through the staging buffer -- with
+// LinearQuantizer::recover (LinearQuantizer.hpp:74-86) instead of the quantizer.
+// ---------------------------------------------------------------------------------------------------------------------
+// index stream -> staging buffer: the mirror image of box_copy_out
+SZ_HD void box_copy_in(const BoxArgs &A, const BoxTile &T, uint32_t lane, uint32_t z, uint16_t *stage) {
+    const uint64_t pos = box_run_pos(T, z);
+    const uint32_t len = T.c1[1] * T.mainc[2];
+    const uint32_t mis = static_cast<uint32_t>(pos) & 7u;
+    const uint16_t *const g0 = A.q + (pos - mis);   // 16-byte aligned (A.q is)
+    const uint32_t end = mis + len;
+    const uint32_t nchunks = (end + 7) / 8;
+    for (uint32_t c = lane; c < nchunks; c += 32) {
+        const uint32_t a = c * 8, b = a + 8;
+        if (a >= mis && b <= end) {
+            *reinterpret_cast<BoxChunk *>(stage + a) = *reinterpret_cast<const BoxChunk *>(g0 + a);
+        } else {   // ragged ends: element by element (the chunk may reach outside the stream)
+            for (uint32_t e = a < mis ? mis : a; e < (b < end ? b : end); e++) stage[e] = g0[e];
+        }
+    }
+}
+
+// One row (lane = row): v = the row's 36 floats (even x valid), results to slot_row[odd x].
+template <bool CUBIC>
+SZ_HD void box_recover_row(const BoxArgs &A, const BoxTile &T, uint32_t ry, uint32_t z, const float *v, const uint16_t *stage,
+                           float *slot_row) {
+    const bool n_odd = T.n[2] & 1u;
+    BoxRowOut R;
+    box_row_out(A, T, ry, z, const_cast<uint16_t *>(stage), R);
+    const QuantParams qp = A.qp;
+#pragma unroll 1
+    for (uint32_t h = 0; h < 2; h++) {
+        float nb[11];
+        nb[0] = h ? v[14] : 0.0f;
+#pragma unroll
+        for (int m = 1; m < 9; m++) nb[m] = h ? v[14 + 2 * m] : v[2 * m - 2];
+        nb[9] = h ? (n_odd ? v[32] : 0.0f) : v[16];
+        nb[10] = h ? 0.0f : v[18];
+        // indices of the eight targets: main sub-phase from the staging buffer, boundary sub-phases from the stream
+        int qv[8];
+        const uint16_t *const sm = R.srow + 8 * h - (CUBIC ? 1 : 0);
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            uint32_t idx;
+            const bool in_main = box_class_rt<CUBIC>(8 * h + t, n_odd, idx);
+            qv[t] = in_main ? sm[t] : R.qb[idx * R.other];
+        }
+        float pred[8];
+        if (CUBIC) {
+#pragma unroll
+            for (int t = 1; t <= 5; t++) pred[t] = interp_cubic<float>(nb[t], nb[t + 1], nb[t + 2], nb[t + 3]);
+            if (h == 0) {
+                pred[0] = interp_quad_1<float>(nb[1], nb[2], nb[3]);
+                pred[6] = interp_cubic<float>(nb[6], nb[7], nb[8], nb[9]);
+                pred[7] = interp_cubic<float>(nb[7], nb[8], nb[9], nb[10]);
+            } else {
+                pred[0] = interp_cubic<float>(nb[0], nb[1], nb[2], nb[3]);
+                if (n_odd) {
+                    pred[6] = interp_cubic<float>(nb[6], nb[7], nb[8], nb[9]);
+                    pred[7] = interp_quad_2<float>(nb[7], nb[8], nb[9]);
+                } else {
+                    pred[6] = interp_quad_2<float>(nb[6], nb[7], nb[8]);
+                    pred[7] = interp_linear1<float>(nb[7], nb[8]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; t++) pred[t] = interp_linear<float>(nb[t + 1], nb[t + 2]);
+        }
+        const bool lin_tail = !CUBIC && h == 1 && !n_odd;
+        float rc[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            float p = pred[t];
+            if (!CUBIC && t == 7 && lin_tail) p = interp_linear1<float>(rc[6], nb[8]);
+            float r = recover_pred<float>(p, qv[t], qp);
+            if (qv[t] == 0) {   // unpredictable: the stored value, at the index's own position
+                uint32_t idx;
+                const bool in_main = box_class_rt<CUBIC>(8 * h + t, n_odd, idx);
+                r = in_main ? R.um[idx] : R.ub[idx * R.other];
+            }
+            rc[t] = r;
+            slot_row[16 * h + 2 * t + 1] = r;
+        }
+    }
+}
+
+// a 33rd owned row (tiles at y = 0 with 33 points): lane = target
+template <bool CUBIC>
+SZ_HD void box_recover_left(const BoxArgs &A, const BoxTile &T, uint32_t lane, uint32_t z, float *slot, const uint16_t *stage) {
+    if (T.c1[1] != 33 || lane >= 16) return;
+    const bool n_odd = T.n[2] & 1u;
+    BoxRowOut R;
+    box_row_out(A, T, 32u, z, const_cast<uint16_t *>(stage), R);
+    float *row = slot + 32 * kBoxPitch;
+    const bool tail_pair = !CUBIC && !n_odd;
+    if (tail_pair && lane == 15) return;   // done together with its predecessor
+    auto get = [&](uint32_t k, int *qv, float *un) {
+        uint32_t idx;
+        const bool in_main = box_class_rt<CUBIC>(k, n_odd, idx);
+        *qv = in_main ? R.srow[idx] : R.qb[idx * R.other];
+        *un = 0.0f;
+        if (*qv == 0) *un = in_main ? R.um[idx] : R.ub[idx * R.other];
+    };
+    const uint32_t k = lane;
+    float pred;
+    if (CUBIC) {
+        const uint32_t kind = k == 0 ? BOX_ST_QUAD1
+                                     : (k <= 13 ? BOX_ST_CUBIC : (k == 14 ? (n_odd ? BOX_ST_CUBIC : BOX_ST_QUAD2) : (n_odd ? BOX_ST_QUAD2 : BOX_ST_LINEAR1)));
+        const float w0 = k >= 1 ? row[2 * k - 2] : 0.0f;
+        const float w1 = row[2 * k];
+        const float w2 = kind != BOX_ST_LINEAR1 ? row[2 * k + 2] : 0.0f;
+        const float w3 = (kind == BOX_ST_CUBIC || kind == BOX_ST_QUAD1) ? row[2 * k + 4] : 0.0f;
+        pred = box_stencil4(kind, w0, w1, w2, w3);
+    } else {
+        pred = interp_linear<float>(row[2 * k], row[2 * k + 2]);
+    }
+    int qv;
+    float un;
+    get(k, &qv, &un);
+    float r = qv ? recover_pred<float>(pred, qv, A.qp) : un;
+    row[2 * k + 1] = r;
+    if (tail_pair && k == 14) {
+        pred = interp_linear1<float>(r, row[30]);
+        get(15, &qv, &un);
+        row[31] = qv ? recover_pred<float>(pred, qv, A.qp) : un;
+    }
+}
+
+// the plane's owned odd-x points -> the output array (rows contiguous; lane = x, walking over the rows)
+SZ_HD void box_recover_out(const BoxSrc &S, const BoxTile &T, uint32_t lane, uint32_t z, const float *slot, float *out) {
+    float *const base = out + T.sbase + z * S.st[0];
+    const uint32_t ny = T.n[1], nx = T.n[2], lowy = T.low[1];
+    if ((lane & 1u) && lane < nx) {
+        float *p = base + lowy * S.st[1] + lane;
+        const float *sl = slot + lowy * kBoxPitch + lane;
+        for (uint32_t y = lowy; y < ny; y++) {
+            *p = *sl;
+            p += S.st[1];
+            sl += kBoxPitch;
+        }
+    }
+}
+
 }  // namespace sz3b

@@ -42,6 +42,7 @@ bool interp_launch_lean(const InterpArgs<T, QT> &A, int p, uint32_t nbatch, bool
 // interp_box.cu: box schedule of the finest level (float data, 16-bit indices, pass order z, y, x)
 struct BoxSrc;
 bool interp_box_applicable(const InterpArgs<float, uint16_t> &A);
+bool interp_launch_box_recover_x(const InterpArgs<float, uint16_t> &A, float *out, uint64_t ntiles, cudaStream_t st);
 bool interp_launch_box(const InterpArgs<float, uint16_t> &A, const BoxSrc &S, const uint32_t sdims[3], uint64_t ntiles,
                        cudaStream_t st);
 void interp_launch_compact(const float *src, const uint32_t dims[3], const uint64_t stride[3], uint32_t s0, int n,

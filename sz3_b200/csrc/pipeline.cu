@@ -2393,6 +2393,17 @@ static void interp_decompress_t(Workspace &ws, const sz3b_config &conf, Cursor &
             // small passes (the coarse levels) on the point-mapped kernel: a row-mapped CTA walks whole rows, and with
             // a handful of CTAs its latency (60-100 us per pass) is all there is
             const bool big = pass_points(A, p) >= (2ull << 20);
+            // the last pass (along x) of the finest level: the box schedule's row phase in recover mode (interp_box.cuh)
+            if constexpr (std::is_same<T, float>::value && std::is_same<QT, uint16_t>::value) {
+                if (L.s == 1 && p == pl.sh.N - 1 && pl.sh.N == 3 && pl.sh.perm[2] == 2 && !old_recover && pl.num < (1ull << 32)) {
+                    InterpArgs<T, QT> B = A;
+                    B.unpred_tmp = d_tmp;
+                    if (interp_launch_box_recover_x(B, d_out, L.nblocks, ws.st)) {
+                        launches++;
+                        continue;
+                    }
+                }
+            }
             if (!(pl.sh.N >= 3 && big && !old_recover && interp_launch_lean<T, QT>(A, p, 1, true, true, d_tmp, ws.st)))
                 launch_interp_recover<T, QT>(pl.sh, d_out, d_q, d_tmp, make_quant(L.eb, radius), L.s, L.nb,
                                              d_table + L.table_off, p, 0, 0, ws.st);

@@ -56,6 +56,12 @@ def same_bits(a, b):
     ((3000,), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, blockSize=128, absErrorBound=1e-3)),
     ((9, 12, 20, 18), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1e-3)),
     ((25, 31, 37), np.float32, dict(cmprAlgo=ALGO_LORENZO_REG, absErrorBound=1e-3, quantbinCnt=16)),
+    # shapes of 32-multiples (+1): the last pass of the finest level through k_box_recover_x (TMA planes, lane = row)
+    ((64, 96, 128), np.float32, dict(cmprAlgo=ALGO_INTERP, absErrorBound=1e-3, interpAlgo=1, interpDirection=0)),
+    ((64, 96, 128), np.float32, dict(cmprAlgo=ALGO_INTERP, absErrorBound=1e-3, interpAlgo=0, interpDirection=0)),
+    ((97, 65, 129), np.float32, dict(cmprAlgo=ALGO_INTERP, absErrorBound=1e-2, interpAlgo=1, interpDirection=0)),
+    ((96, 64, 64), np.float32, dict(cmprAlgo=ALGO_INTERP, absErrorBound=1e-7, interpAlgo=1, interpDirection=0, quantbinCnt=64)),   # many stored values
+    ((128, 128, 128), np.float32, dict(cmprAlgo=ALGO_INTERP_LORENZO, absErrorBound=1e-3)),
 ])
 def test_decompress_bit_identical(shape, dtype, kw, writer):
     data = field_nd(shape, dtype)
