@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
 constexpr size_t kBoxRecSmem = sizeof(float) * (kBoxWarps * kBoxSlotStride) + sizeof(uint16_t) * kBoxWarps * kBoxStageU16 +
                                sizeof(uint64_t) * kBoxWarps;
 template <bool CUBIC>
-__global__ void __launch_bounds__(kBoxThreads, 2) k_box_recover_x(const __grid_constant__ CUtensorMap tmap, BoxArgs A, BoxSrc S, float *out) {
+__global__ void __launch_bounds__(kBoxThreads, 4) k_box_recover_x(const __grid_constant__ CUtensorMap tmap, BoxArgs A, BoxSrc S, float *out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *const slots = reinterpret_cast<float *>(smem_raw);
     uint16_t *const stages = reinterpret_cast<uint16_t *>(slots + kBoxWarps * kBoxSlotStride);
