@@ -906,7 +906,9 @@ static size_t interp_compress_t(Workspace &ws, const sz3b_config &conf, const T 
     const int schedule = std::is_integral<T>::value
                              ? 1   // integer element types: the per-pass kernels (core.cuh carries their arithmetic)
                              : ((forced == 1 || (forced == 4 && conf.N == 3) || (forced == 5 && conf.N >= 3)) ? forced : 0);
+    const double t_plan = now_ms();
     if (const char *e = build_interp_plan(conf, conf.absErrorBound, schedule, pl)) fail(SZ3B_E_INVALID_ARGUMENT, e);
+    if (!tuner) ws.host_stage("plan_host", now_ms() - t_plan);
     const int radius = conf.quantbinCnt / 2;
     const int nbins = 2 * radius;
     const uint64_t n = pl.num * nbatch;
@@ -1863,7 +1865,9 @@ static size_t dispatch_compress_inner(Workspace &ws, sz3b_config &conf, const T 
                     if (!(planes && conf.cmprAlgo == SZ3B_ALGO_INTERP)) join_copy(ws);
                     ws.host_stage("tune_overlapped_with_h2d", now_ms() - t0);
                 } else {
+                    const double t0 = now_ms();
                     tune_interp<T>(ws, conf, dev());   // rewrites cmprAlgo to ALGO_INTERP (N >= 2)
+                    ws.host_stage("tune_wall", now_ms() - t0);
                 }
             }
             if (conf.cmprAlgo == SZ3B_ALGO_INTERP) {
