@@ -165,13 +165,19 @@ void interp_launch_ltiles(const InterpArgs<T, QT> &A, uint64_t ntiles, uint32_t 
     const size_t smem = sizeof(T) * kTileSmemElems + sizeof(unsigned) * kHistWindow;
     once_per_device(attr_set, [&] {
         cudaFuncSetAttribute(k_interp_ltile<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        cudaFuncSetAttribute(k_interp_ltile_wide<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if constexpr (sizeof(T) == 4)
+            cudaFuncSetAttribute(k_interp_ltile_wide<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     });
     dim3 grid(static_cast<unsigned>(ntiles), nbatch);
-    if (ntiles * nbatch <= 148 && sizeof(T) == 4)
-        k_interp_ltile_wide<T, QT><<<grid, 1024, smem, st>>>(A);
-    else
-        k_interp_ltile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
+    // (the 1024-thread variant for launches that leave SMs idle exists for 4-byte elements only: at 64 registers the
+    //  double-precision body would spill)
+    if constexpr (sizeof(T) == 4) {
+        if (ntiles * nbatch <= 148) {
+            k_interp_ltile_wide<T, QT><<<grid, 1024, smem, st>>>(A);
+            return;
+        }
+    }
+    k_interp_ltile<T, QT><<<grid, kTileThreads, smem, st>>>(A);
 }
 
 template <class T, class QT>
