@@ -17,9 +17,15 @@ namespace sz3b {
 
 namespace {
 
+#ifndef SZ3B_BOX_CWARPS
+#define SZ3B_BOX_CWARPS 8
+#endif
+constexpr int kBoxCWarps = SZ3B_BOX_CWARPS;      // warps of a compressing CTA (k_interp_box)
+constexpr int kBoxCThreads = kBoxCWarps * 32;
+constexpr bool kBoxAllLines = kBoxCThreads >= kBoxEEPlane;   // every z-line of phase A has a thread of its own
 constexpr int kBoxEEPad = 9568;   // EE floats rounded up to a multiple of 32 (128 B)
-constexpr size_t kBoxSmem = sizeof(float) * (kBoxWarps * kBoxSlotStride + kBoxEEPad) + sizeof(uint16_t) * kBoxWarps * kBoxStageU16 +
-                            sizeof(uint64_t) * kBoxWarps;
+constexpr size_t kBoxSmem = sizeof(float) * (kBoxCWarps * kBoxSlotStride + kBoxEEPad) + sizeof(uint16_t) * kBoxCWarps * kBoxStageU16 +
+                            sizeof(uint64_t) * kBoxCWarps;
 struct BoxNoCtx {};   // the box schedule keeps no per-thread context (its histogram is taken afterwards: k_hist_u16)
 constexpr unsigned kBoxPlaneBytes = kBoxSlotElems * sizeof(float);   // what one TMA box delivers (zero fill included)
 
@@ -73,18 +79,18 @@ __device__ __forceinline__ unsigned long long gtime() {
 #endif
 
 template <bool CUBIC>
-__global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_constant__ CUtensorMap tmap, BoxArgs A, BoxSrc S) {
+__global__ void __launch_bounds__(kBoxCThreads, 2) k_interp_box(const __grid_constant__ CUtensorMap tmap, BoxArgs A, BoxSrc S) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *const slots = reinterpret_cast<float *>(smem_raw);
-    float *const EE = slots + kBoxWarps * kBoxSlotStride;
+    float *const EE = slots + kBoxCWarps * kBoxSlotStride;
     uint16_t *const stages = reinterpret_cast<uint16_t *>(EE + kBoxEEPad);
-    uint64_t *const bars = reinterpret_cast<uint64_t *>(stages + kBoxWarps * kBoxStageU16);
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(stages + kBoxCWarps * kBoxStageU16);
     __shared__ BoxTile T;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t split = S.split, part = blockIdx.x % split;
     const uint32_t tile = blockIdx.x / split + A.tile0;
-    const uint32_t zstep = kBoxWarps * split;
+    const uint32_t zstep = kBoxCWarps * split;
     BOX_TICK(0);
     BoxOrigin o;
     box_origin(A, S, tile, o);
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
     uint64_t *const bar = bars + warp;
     const uint32_t nz = o.n[0];
     const bool tma = S.tma != 0, write2 = A.s >= 2;
-    uint32_t z = (o.begin[0] ? 1u : 0u) + part * kBoxWarps + warp;   // planes of this warp: z, z + zstep, ...
+    uint32_t z = (o.begin[0] ? 1u : 0u) + part * kBoxCWarps + warp;   // planes of this warp: z, z + zstep, ...
     const int x0 = static_cast<int>(o.begin[2] / S.odiv), y0 = static_cast<int>(o.begin[1] / S.odiv),
               z0 = static_cast<int>(o.begin[0] / S.odiv);
     if (tma && lane == 0) {
@@ -108,14 +114,15 @@ __global__ void __launch_bounds__(kBoxThreads, 2) k_interp_box(const __grid_cons
     if (tid == 0) box_tile_setup<CUBIC>(A, tile, o, T);
     // ---- phase A: EE, pass 0 ----------------------------------------------------------------------------------------
     box_fill_column(A, S, o, tid, EE);
-    if (tid < 33) box_fill_column(A, S, o, 256 + tid, EE);
+    if (!kBoxAllLines && tid < 33) box_fill_column(A, S, o, 256 + tid, EE);
     BOX_TICK(1);
     fill_copy_wait();
     __syncthreads();
     BOX_TICK(2);
     if (!tma && z < nz) box_gather_plane(S, T, lane, z, slot);   // (needs T: after the barrier)
     box_pass0_line<CUBIC>(A, S, ctx, T, tid, EE, part == 0);
-    for (uint32_t e = tid; e < 33u * 16u; e += kBoxThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE, part == 0);
+    if (!kBoxAllLines)
+        for (uint32_t e = tid; e < 33u * 16u; e += kBoxCThreads) box_pass0_left<CUBIC>(A, ctx, T, e, EE, part == 0);
     BOX_TICK(3);
     __syncthreads();
     BOX_TICK(4);
@@ -355,9 +362,9 @@ bool interp_launch_box(const BoxArgs &A, const BoxSrc &S, const uint32_t sdims[3
     });
     const dim3 grid(static_cast<unsigned>(ntiles * S.split));
     if (A.sh.cubic)
-        k_interp_box<true><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A, S);
+        k_interp_box<true><<<grid, kBoxCThreads, kBoxSmem, st>>>(map, A, S);
     else
-        k_interp_box<false><<<grid, kBoxThreads, kBoxSmem, st>>>(map, A, S);
+        k_interp_box<false><<<grid, kBoxCThreads, kBoxSmem, st>>>(map, A, S);
     return true;
 }
 

@@ -533,11 +533,16 @@ static void run_interp(Workspace &ws, const InterpPlan &pl, const T *d_data, uin
         if (pl.tile) {
             // (the tile schedules are floating-point kernels; integer element types run the per-pass kernels)
             if constexpr (std::is_floating_point<T>::value) {
+                // the finest level is the dominant launch of the path (7/8 of the points): it gets a record of its
+                // own inside the predict_quantize stage (bench.py: roofline.dominant_launch)
+                const bool finest = L.s == 1 && nbatch == 1;
+                const size_t hf = finest ? ws.stage_begin("predict_quantize_finest_level") : 0;
                 if (box && launch_box<T, QT>(A, bp, L.nblocks, ws.st)) {
                     count_box(lv_begin, lv_end);
                 } else {
                     interp_launch_ltiles<T, QT>(A, L.nblocks, nbatch, ws.st);
                 }
+                if (finest) ws.stage_end(hf, 0);
             } else {
                 fail(SZ3B_E_RUNTIME, "tile schedule planned for an integer element type");
             }

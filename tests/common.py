@@ -181,7 +181,8 @@ def zhuf_cases():
 
 
 def product_lib():
-    lib = _load(os.path.join(ROOT, "sz3_b200", "lib", "libsz3b200.so"))
+    # (SZ3B_LIB_PATH: a differently built copy of the library, for A/B measurements of kernel variants)
+    lib = _load(os.environ.get("SZ3B_LIB_PATH") or os.path.join(ROOT, "sz3_b200", "lib", "libsz3b200.so"))
     if lib is None:
         return None
     lib.sz3b_last_error.restype = C.c_char_p
