@@ -27,6 +27,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import platform
 import struct
 import subprocess
 import sys
@@ -61,6 +62,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip other_configs / two-callers / host-zstd extras")
     ap.add_argument("--diag", action="store_true", help="per-rank step times and host-link rate on stderr")
+    ap.add_argument("--no-pin", action="store_true", help="N > 1: do not bind this rank to its share of the host cores")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: leave this rank's host buffers wherever the kernel puts them")
     ap.add_argument("--host-threads", type=int, default=None, help="host threads per rank (default: this rank's share of the cores)")
     ap.add_argument("--host-wait", type=int, default=None, help="0 = spin while waiting for the device, 1 = poll and yield")
     ap.add_argument("--lossless-policy", type=int, default=None, help="0 = host zstd on every chunk, 1 = adaptive host zstd, 2 = GPU lossless stage (library default)")
@@ -167,6 +170,28 @@ def cpu_checker():
 
 def host_cores():
     return len(os.sched_getaffinity(0))
+
+
+def prefer_gpu_numa_node(torch, local):
+    """Pinned host buffers of this rank on the NUMA node its GPU hangs off: set_mempolicy(MPOL_PREFERRED) before
+    anything is allocated.  A hint only (the kernel falls back to other nodes), and a no-op on single-node hosts or
+    where the container forbids the call.  With eight ranks copying at once the host side of the links is what bounds
+    e2e; buffers on the far socket make every DMA cross the inter-socket link as well."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2:
+            return {"gpu_node": node, "host_nodes": len(nodes), "policy": "default"}
+        libc = C.CDLL(None, use_errno=True)
+        mask = (C.c_ulong * 4)()
+        mask[node // 64] = 1 << (node % 64)
+        rc = libc.syscall(238, 1, mask, 257)   # x86-64 SYS_set_mempolicy, MPOL_PREFERRED
+        return {"gpu_node": node, "host_nodes": len(nodes), "policy": "preferred" if rc == 0 else f"default (errno {C.get_errno()})"}
+    except Exception as ex:   # placement is an optimisation, never a reason to fail
+        return {"policy": "default", "why": str(ex)[:80]}
 
 
 def set_ref_threads(lib, prefix, n):
@@ -294,6 +319,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; the product has no CPU path (use --impl reference for the CPU arm)")
+    numa = prefer_gpu_numa_node(torch, local) if (world > 1 and platform.machine() == "x86_64" and not args.no_numa) else None
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -307,7 +333,25 @@ def run_ours(args):
     # one rank per GPU on one host: every rank gets its share of the cores (16 pool threads per rank on 2 cores per
     # rank cost half of e2e; tests/gpu_cores.sh).  Waiting threads keep spinning: yielding measured slower.
     cores = host_cores()
-    host_threads = args.host_threads if args.host_threads is not None else (max(2, cores // world) if world > 1 else 0)
+    share = max(1, cores // world)
+    pinned_cores = None
+    k = int(os.environ.get("SZ3B_BENCH_PIN_CORES") or 0) or share   # (experiments: a smaller share than the host offers)
+    if world > 1 and not args.no_pin:
+        # One rank per GPU: every rank binds itself to its own share of the cores (what `mpirun --bind-to` / numactl do
+        # for an MPI job) and sizes its pool to that share.  The pool threads spin while they wait for the device, so
+        # ranks that roam over each other's cores stall one another: unbound, 12 threads per rank on 24 cores measured
+        # 6.1-6.9 / 14.4 ms per step (value / e2e) with stalls of up to 90 ms; bound to disjoint shares 5.5 / 13.3 ms
+        # (tests/gpu_2gpu_probe.sh).
+        allowed = sorted(os.sched_getaffinity(0))
+        mine_cores = allowed[local * k:(local + 1) * k]
+        if len(mine_cores) == k:
+            os.sched_setaffinity(0, set(mine_cores))
+            pinned_cores = [mine_cores[0], mine_cores[-1]]
+            share = k
+    # (pool size: every trial compression of the tuner has a thread spinning on its stream; 12 of them per rank measured
+    #  6.1 / 14.4-15.3 ms per step with stalls of 25-145 ms even when bound, 6: 5.1 / 13.0 ms, 4 on a 4-core share
+    #  5.0-5.8 / 12.7-13.3 ms)
+    host_threads = args.host_threads if args.host_threads is not None else (max(2, min(share, 6)) if world > 1 else 0)
     host_wait = args.host_wait if args.host_wait is not None else 0
     L.sz3b_set_host_threads(host_threads)
     L.sz3b_set_host_wait(host_wait)
@@ -589,7 +633,9 @@ def run_ours(args):
                        "field": "G3 (SURVEY.md 8d), seeded", "l2": "input 512 MiB per step > 126 MB L2 (no explicit flush)",
                        "lossless_policy": {0: "host zstd-3 on every chunk", 1: "adaptive host zstd: probes, raw zstd frames where zstd gains < 1 % (include/sz3b.h)",
                                            2: "GPU lossless stage: zstd frames of Huffman-only literal blocks, one table per 128 KiB (sz3_b200/csrc/zhuf.cuh); decodes with the unmodified reference"}[policy],
-                       "host": {"cores": cores, "threads_per_rank": host_threads or cores, "device_wait": ["spin", "yield"][host_wait]},
+                       "host": {"cores": cores, "threads_per_rank": host_threads or cores, "device_wait": ["spin", "yield"][host_wait],
+                                **({"rank0_bound_to_cores": pinned_cores} if pinned_cores else {}),
+                                **({"numa_rank0": numa} if numa else {})},
                        "value_path": ("sz3b_compress, device-resident input, stream delivered to host" if world == 1 else
                                       "sz3b_compress_slab_placed per rank, device-resident slab; sizes all-gathered, frames delivered "
                                       "to their offsets in one shared pinned container, header written by rank 0 (all timed)"),

@@ -17,7 +17,10 @@ int host_threads() {
     int n = g_host_threads.load();
     if (n <= 0) {
         // this process's share of the cores when a launcher says how many ranks share the host (torchrun, Open MPI):
-        // a full-size pool per rank oversubscribes the cores and halves the end-to-end rate (tests/gpu_cores.sh)
+        // a full-size pool per rank oversubscribes the cores and halves the end-to-end rate (tests/gpu_cores.sh).  At
+        // most six per rank: every concurrent tuner trial has a thread spinning on its stream, and twelve of them per
+        // rank on a 2 x 12-core host stalled the ranks' main threads and the NCCL proxies for up to 145 ms
+        // (tests/gpu_2gpu_probe.sh: 6.1 / 14.4 ms per step against 5.1 / 13.0 ms with six)
         static const int share = [] {
             int c = static_cast<int>(std::thread::hardware_concurrency());
             if (c <= 0) c = 1;
@@ -25,7 +28,7 @@ int host_threads() {
             int ranks = 1;
             for (const char *name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE"})
                 if (const char *e = getenv(name)) ranks = std::max(ranks, atoi(e));
-            return ranks > 1 ? std::max(2, c / ranks) : c;
+            return ranks > 1 ? std::max(2, std::min(c / ranks, 6)) : c;
         }();
         n = share;
     }

