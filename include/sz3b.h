@@ -192,6 +192,15 @@ void sz3b_set_host_wait(int mode);
  *   In every case the result is a concatenation of standard zstd frames that the unmodified reference decoder reads. */
 void sz3b_set_lossless_policy(int policy);
 int sz3b_get_lossless_policy(void);
+/* Decompression side of the same stage, lossless/Lossless_zstd.hpp:39-45 (ZSTD_decompress of the whole payload).
+ *   0 = every frame through libzstd on the host pool (any zstd stream);
+ *   1 = frames of the shape policy 2 writes (raw blocks and blocks of Huffman-only literals in four streams, no
+ *       sequences) are decoded on the GPU, one thread per stream (sz3_b200/csrc/zhuf_dec.cuh); the host decodes only
+ *       the frames that hold the head of the stream (headers, stored values, Huffman tree).  Any other payload, and
+ *       any block the GPU decoder does not take, goes through libzstd as with 0.  Interpolation streams only.
+ * Initial value: SZ3B_FRAME_DECODER from the environment, else the library default. */
+void sz3b_set_frame_decoder(int mode);
+int sz3b_get_frame_decoder(void);
 
 #ifdef __cplusplus
 }

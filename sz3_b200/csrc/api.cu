@@ -141,6 +141,8 @@ void sz3b_set_device_fanout(int n) { set_device_fanout(n); }
 int sz3b_get_device_fanout(void) { return device_fanout(); }
 void sz3b_set_lossless_policy(int policy) { set_lossless_policy(policy); }
 int sz3b_get_lossless_policy(void) { return lossless_policy(); }
+void sz3b_set_frame_decoder(int mode) { set_frame_decoder(mode); }
+int sz3b_get_frame_decoder(void) { return frame_decoder(); }
 
 int sz3b_config_init(sz3b_config *c, int ndims, const size_t *dims) {
     return guarded([&] {

@@ -124,6 +124,10 @@ void launch_scan_chunks(const unsigned *chunk_bits, const unsigned *chunk_zeros,
 
 // zhuf_kernels.cu: the GPU lossless stage (zstd frames of Huffman-only literal blocks, zhuf.cuh)
 struct ZhufBlockInfo;
+struct ZhufDecBlock;
+// decoder of zhuf-shaped frames (zhuf_dec.cuh): one CTA per block of `blocks` (device), cmp = the compressed payload
+// (device), raw = the decoded stream (device); *bad != 0 afterwards when a block did not decode
+void launch_zhuf_decode(const uint8_t *cmp, const ZhufDecBlock *blocks, size_t nblocks, uint8_t *raw, unsigned *bad, cudaStream_t st);
 void launch_zhuf_build(const uint8_t *src, uint64_t len, ZhufBlockInfo *infos, cudaStream_t st);
 void launch_zhuf_emit(const uint8_t *src, uint64_t len, uint64_t g0, uint64_t g1, ZhufBlockInfo *infos, uint8_t *out,
                       unsigned long long *total, unsigned long long *total_log, cudaStream_t st);

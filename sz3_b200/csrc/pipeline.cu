@@ -27,6 +27,7 @@
 #include "blockwise.cuh"
 #include "lorenzo.cuh"
 #include "zhuf.cuh"
+#include "zhuf_dec.cuh"
 #include "huffman_host.hpp"
 #include "interp_body.cuh"
 #include "interp_box.cuh"
@@ -2602,9 +2603,105 @@ static void blockwise_decompress_t(Workspace &ws, const sz3b_config &conf, Curso
     SZ3B_CUDA(cudaGetLastError());
 }
 
+// Length of the part of an interpolation stream the host parser reads (decomposition header, quantizer with its stored
+// values, Huffman tree, the two counts in front of the bits), from the first `valid` decoded bytes.  Returns false
+// with *need = the number of bytes that must be valid before the answer is known.
+template <class T>
+static bool interp_head_len(const uint8_t *raw, size_t valid, size_t raw_len, int N, size_t *need) {
+    const size_t a = static_cast<size_t>(N) * 8 + 36;   // dims | blocksize | interpAlgo | direction | anchor stride | alpha | beta
+    const size_t b = a + 21;                            // uid | eb | radius | number of stored values
+    if (valid < b) {
+        *need = b;
+        return false;
+    }
+    uint64_t n_unpred;
+    memcpy(&n_unpred, raw + a + 13, 8);
+    if (n_unpred > raw_len / sizeof(T)) fail(SZ3B_E_INVALID_ARGUMENT, "truncated stream (unpredictable values)");
+    const size_t c = b + static_cast<size_t>(n_unpred) * sizeof(T);   // Huffman tree: offset | node count (big endian) | ...
+    if (valid < c + 13) {
+        *need = c + 13;
+        return false;
+    }
+    const uint32_t nc = (static_cast<uint32_t>(raw[c + 4]) << 24) | (static_cast<uint32_t>(raw[c + 5]) << 16) |
+                        (static_cast<uint32_t>(raw[c + 6]) << 8) | raw[c + 7];
+    const size_t lw = nc <= 256 ? 1 : (nc <= 65536 ? 2 : 4);
+    *need = c + 13 + 2 * static_cast<size_t>(nc) * lw + static_cast<size_t>(nc) * 5 + 16;
+    return valid >= *need;
+}
+
+// Frames of the shape the GPU lossless stage writes, decoded on the GPU (zhuf_dec.cuh): the compressed payload goes up
+// once, one CTA per block writes the decoded stream into the device mirror the Huffman decoder reads, and the host
+// decodes (libzstd) only the leading frames that hold what its parser reads.  Returns false -- nothing changed -- when
+// the payload is not of that shape or the head is most of the stream; the caller then decodes every frame on the host.
+// `flag` receives the address the kernel's verdict arrives at (pinned; valid after the next synchronisation of ws.st).
+template <class T>
+static bool frames_on_gpu(Workspace &ws, const sz3b_config &conf, const uint8_t *cmp, size_t cmp_size, uint8_t *raw, size_t raw_len,
+                          const unsigned **flag) {
+    const uint8_t *pay = cmp + 8;
+    const size_t pay_size = cmp_size - 8;
+    const double t0 = now_ms();
+    const size_t cap = 2 * (raw_len / kZhufBlock + raw_len / kZhufFrame) + 64;
+    ZhufDecBlock *h_blocks = static_cast<ZhufDecBlock *>(ws.zdec_host.ensure((cap + 1) * sizeof(ZhufDecBlock) + 64));
+    size_t nblocks = 0;
+    uint64_t total = 0;
+    if (!zhuf_walk_frames(pay, pay_size, h_blocks, cap, &nblocks, &total) || total != raw_len || nblocks == 0) return false;
+    // the head of the stream on the host: libzstd's streaming decoder with the output capped at what the parser reads
+    // (it works block by block, so the first 128 KiB or so are decoded, not the whole first frame)
+    {
+        thread_local ZSTD_DCtx *dctx = nullptr;
+        if (!dctx) dctx = ZSTD_createDCtx();
+        if (!dctx) return false;
+        ZSTD_DCtx_reset(dctx, 1);
+        ZSTD_inBuffer in{pay, pay_size, 0};
+        ZSTD_outBuffer ob{raw, 0, 0};
+        size_t need = 0;
+        while (!interp_head_len<T>(raw, ob.pos, raw_len, conf.N, &need)) {
+            if (need > raw_len / 2) return false;
+            ob.size = need;
+            while (ob.pos < ob.size) {
+                const size_t before_in = in.pos, before_out = ob.pos;
+                const size_t r = ZSTD_decompressStream(dctx, &ob, &in);
+                if (ZSTD_isError(r)) return false;
+                if (in.pos == before_in && ob.pos == before_out) return false;   // no progress: truncated payload
+            }
+        }
+    }
+    ws.host_stage("frames_walk_head_host", now_ms() - t0);
+    uint8_t *d_cmp = ws.zcmp.as<uint8_t>(pay_size + 64);
+    size_t h = ws.stage_begin("frames_upload");
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, pay) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned && pay_size >= (static_cast<size_t>(32) << 20)) {
+        upload_pageable(ws, d_cmp, pay, pay_size);
+    } else {
+        SZ3B_CUDA(cudaMemcpyAsync(d_cmp, pay, pay_size, cudaMemcpyHostToDevice, ws.st));
+        ws.h2d_bytes += pay_size;
+    }
+    ws.stage_end(h, 0);
+    ZhufDecBlock *d_blocks = ws.zdec_blocks.as<ZhufDecBlock>(nblocks + 1);
+    h = ws.stage_begin("frames_gpu");
+    unsigned *d_bad = reinterpret_cast<unsigned *>(d_blocks + nblocks);
+    SZ3B_CUDA(cudaMemcpyAsync(d_blocks, h_blocks, nblocks * sizeof(ZhufDecBlock), cudaMemcpyHostToDevice, ws.st));
+    SZ3B_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(ZhufDecBlock), ws.st));
+    uint8_t *d_raw = ws.hd_bits.as<uint8_t>(raw_len + 256);
+    SZ3B_CUDA(cudaMemsetAsync(d_raw + raw_len, 0, 256, ws.st));
+    launch_zhuf_decode(d_cmp, d_blocks, nblocks, d_raw, d_bad, ws.st);
+    unsigned *h_flag = reinterpret_cast<unsigned *>(h_blocks + cap);
+    *h_flag = 0xffffffffu;
+    SZ3B_CUDA(cudaMemcpyAsync(h_flag, d_bad, sizeof(unsigned), cudaMemcpyDeviceToHost, ws.st));
+    ws.stage_end(h, 1);
+    SZ3B_CUDA(cudaGetLastError());
+    *flag = h_flag;
+    ws.raw_host = raw;
+    ws.raw_dev = d_raw;
+    return true;
+}
+
 // one non-OMP payload -> `out` (host or device pointer to config_num(conf) elements)
 template <class T>
-static void decompress_one(Workspace &ws, const sz3b_config &conf, const uint8_t *cmp, size_t cmp_size, T *out, int loc) {
+static void decompress_one(Workspace &ws, const sz3b_config &conf, const uint8_t *cmp, size_t cmp_size, T *out, int loc,
+                           bool gpu_frames_allowed = true) {
     const uint64_t num = config_num(conf);
     const size_t bytes = num * sizeof(T);
     if (conf.cmprAlgo == SZ3B_ALGO_LOSSLESS) {
@@ -2629,7 +2726,10 @@ static void decompress_one(Workspace &ws, const sz3b_config &conf, const uint8_t
     const size_t raw_len = zstd_framed_raw_len(cmp, cmp_size);
     if (raw_len == 0 || raw_len > (bytes + (static_cast<size_t>(1) << 20)) * 4) fail(SZ3B_E_INVALID_ARGUMENT, "implausible stream length");
     uint8_t *raw = static_cast<uint8_t *>(ws.stage.ensure(raw_len + 16));
-    {
+    const unsigned *gpu_flag = nullptr;
+    const bool on_gpu = gpu_frames_allowed && frame_decoder() == 1 && conf.cmprAlgo == SZ3B_ALGO_INTERP && cmp_size > 8 &&
+                        raw_len >= kZhufMinStream && frames_on_gpu<T>(ws, conf, cmp, cmp_size, raw, raw_len, &gpu_flag);
+    if (!on_gpu) {
         // every frame goes up to the device mirror of the file as soon as it is decoded (the Huffman decoder reads the
         // bit stream there): the upload hides under the decoding of the other frames
         struct Uploader : FrameDone {
@@ -2687,6 +2787,12 @@ static void decompress_one(Workspace &ws, const sz3b_config &conf, const uint8_t
         ws.stage_end(h, 0);
     }
     SZ3B_CUDA(stream_wait(ws.st));
+    if (on_gpu && *gpu_flag != 0) {
+        // a block the GPU frame decoder did not take (its verdict travelled behind the kernel): everything again with
+        // libzstd, which either decodes the payload or reports it as corrupt
+        ws.raw_host = ws.raw_dev = nullptr;
+        decompress_one<T>(ws, conf, cmp, cmp_size, out, loc, false);
+    }
 }
 
 template <class T>

@@ -317,6 +317,16 @@ std::atomic<int> g_lossless_policy{2};
 void set_lossless_policy(int p) { g_lossless_policy.store(p); }
 int lossless_policy() { return g_lossless_policy.load(); }
 
+namespace {
+constexpr int kFrameDecoderDefault = 1;   // 512^3 stream: 6.28 -> 5.55 ms (profiles/r2h_frames.log)
+std::atomic<int> g_frame_decoder{[] {
+    const char *e = getenv("SZ3B_FRAME_DECODER");
+    return e && *e ? (atoi(e) != 0 ? 1 : 0) : kFrameDecoderDefault;
+}()};
+}  // namespace
+void set_frame_decoder(int m) { g_frame_decoder.store(m != 0 ? 1 : 0); }
+int frame_decoder() { return g_frame_decoder.load(); }
+
 size_t zstd_compress_framed(const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_cap, int threads,
                             bool *too_small, ZstdReady *ready, std::vector<uint8_t> *scratch, bool allow_raw) {
     *too_small = false;

@@ -57,6 +57,8 @@ size_t zstd_compress_framed(const uint8_t *src, size_t src_len, uint8_t *dst, si
                             bool allow_raw = false);
 void set_lossless_policy(int p);
 int lossless_policy();
+void set_frame_decoder(int m);   // 1 = zhuf-shaped frames decode on the GPU (zhuf_dec.cuh), 0 = libzstd on the host
+int frame_decoder();
 
 // Persistent host worker threads of the host tail (zstd chunks, frame concatenation).
 void host_parallel(int nworkers, void (*fn)(void *arg, int worker), void *arg);

@@ -156,6 +156,9 @@ struct Workspace {
     DevBuf padded, bsel, bsel2, brank, cspec, cdense;
     // GPU lossless stage (zhuf_kernels.cu): assembled stream, per-block tables, compressed frames
     DevBuf zsrc, zinfo, zdst;
+    // ... and its decoder (zhuf_dec.cuh): compressed payload, block list + flag; the host's copy of the list
+    DevBuf zcmp, zdec_blocks;
+    PinBuf zdec_host;
     // Huffman decode
     DevBuf hd_bits, hd_tab, hd_over, hd_counts, hd_offs;
     // pinned staging

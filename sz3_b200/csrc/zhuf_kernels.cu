@@ -13,6 +13,7 @@
 
 #include "launch.hpp"
 #include "zhuf.cuh"
+#include "zhuf_dec.cuh"
 
 namespace sz3b {
 
@@ -272,6 +273,50 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_encode(const uint8_t *__r
     for (uint32_t i = tid; i < nwords; i += kZhufThreads)
         dw[i] = head ? __funnelshift_r(buf[i], buf[i + 1], 8 * head) : buf[i];
     for (uint32_t i = head + nwords * 4 + tid; i < sb; i += kZhufThreads) dst[i] = bb[i];
+}
+
+// Decoder of zhuf-shaped frames (zhuf_dec.cuh): one CTA per block.  Thread 0 reads the tree description (the FSE chain
+// over the weights is serial), all threads build the block's decode table in shared memory, then lane 0 of each of
+// the four warps decodes one of the four streams -- 32768 dependent table lookups each, so the kernel's time is one
+// stream's latency whatever the number of blocks.  Raw blocks are copied.  *bad is set when a block does not decode
+// (the caller then hands the whole payload to libzstd).
+constexpr int kZhufDecThreads = 128;
+__global__ void __launch_bounds__(kZhufDecThreads) k_zhuf_decode(const uint8_t *__restrict__ cmp, const ZhufDecBlock *__restrict__ blocks,
+                                                                 uint8_t *__restrict__ raw, unsigned *__restrict__ bad) {
+    __shared__ ZhufDecScratch S;
+    __shared__ uint16_t tab[1 << kZhufMaxBits];
+    __shared__ uint32_t sb[4], sn[4];
+    const ZhufDecBlock b = blocks[blockIdx.x];
+    const int tid = threadIdx.x;
+    if (!b.coded) {
+        const uint8_t *s = cmp + b.src;
+        uint8_t *d = raw + b.dst;
+        for (uint32_t i = tid; i < b.regen; i += kZhufDecThreads) d[i] = s[i];
+        return;
+    }
+    const uint8_t *d = cmp + b.src;
+    if (tid == 0) {
+        S.ok = zhuf_read_weights(d, b.lit, S) ? 1 : 0;
+        if (S.ok && !zhuf_stream_sizes(d, b.lit, S.desc_len, b.regen, sb, sn)) S.ok = 0;
+        if (!S.ok) atomicOr(bad, 1u);
+    }
+    __syncthreads();
+    if (!S.ok) return;
+    zhuf_dec_table(S, tab, tid, kZhufDecThreads);
+    if ((tid & 31) == 0) {
+        const int s = tid >> 5;
+        const uint8_t *sp = d + S.desc_len + 6;
+        uint8_t *dp = raw + b.dst;
+        for (int k = 0; k < s; k++) {
+            sp += sb[k];
+            dp += sn[k];
+        }
+        if (!zhuf_dec_stream(sp, sb[s], tab, S.maxbits, dp, sn[s])) atomicOr(bad, 2u);
+    }
+}
+
+void launch_zhuf_decode(const uint8_t *cmp, const ZhufDecBlock *blocks, size_t nblocks, uint8_t *raw, unsigned *bad, cudaStream_t st) {
+    if (nblocks) k_zhuf_decode<<<static_cast<unsigned>(nblocks), kZhufDecThreads, 0, st>>>(cmp, blocks, raw, bad);
 }
 
 // Tables and stream sizes of every block of src[0, len) (device).  One launch for the whole stream: the kernel's time

@@ -35,6 +35,7 @@ typedef struct ZSTD_outBuffer_s {
 ZSTD_DCtx *ZSTD_createDCtx(void);
 size_t ZSTD_freeDCtx(ZSTD_DCtx *dctx);
 size_t ZSTD_decompressStream(ZSTD_DCtx *zds, ZSTD_outBuffer *output, ZSTD_inBuffer *input);
+size_t ZSTD_DCtx_reset(ZSTD_DCtx *dctx, int reset); /* 1 = ZSTD_reset_session_only */
 const char *ZSTD_getErrorName(size_t code);
 unsigned ZSTD_versionNumber(void);
 #ifdef __cplusplus

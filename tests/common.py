@@ -123,13 +123,16 @@ def zhuf_emul_lib():
     """Sequential encoder of the GPU lossless stage's frames (tests/emul/zhuf_emul.cpp; test infrastructure)."""
     src = os.path.join(ROOT, "tests", "emul", "zhuf_emul.cpp")
     out = os.path.join(ROOT, "tests", "emul", "_build", "libzhuf_emul.so")
-    deps = [src, os.path.join(ROOT, "sz3_b200", "csrc", "zhuf.cuh"), os.path.join(ROOT, "sz3_b200", "csrc", "core.cuh")]
+    deps = [src, os.path.join(ROOT, "sz3_b200", "csrc", "zhuf.cuh"), os.path.join(ROOT, "sz3_b200", "csrc", "core.cuh"),
+            os.path.join(ROOT, "sz3_b200", "csrc", "zhuf_dec.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", src, "-o", out], check=True)
     lib = C.CDLL(out)
     lib.zhuf_emul_compress.restype = C.c_longlong
     lib.zhuf_emul_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.zhuf_emul_decompress.restype = C.c_longlong
+    lib.zhuf_emul_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
     return lib
 
 

@@ -78,3 +78,42 @@ extern "C" long long zhuf_emul_compress(const uint8_t *src, size_t len, uint8_t 
     }
     return static_cast<long long>(at);
 }
+
+// Sequential twin of k_zhuf_decode (sz3_b200/csrc/zhuf_dec.cuh): frames -> bytes.  Returns the decoded size, -1 when the
+// payload is not of the shape zhuf writes, -2 when a block does not decode.
+#include "../../sz3_b200/csrc/zhuf_dec.cuh"
+
+extern "C" long long zhuf_emul_decompress(const uint8_t *cmp, size_t size, uint8_t *out, size_t cap, int misalign) {
+    std::vector<ZhufDecBlock> blocks(size / 3 + 16);
+    size_t nb = 0;
+    uint64_t raw = 0;
+    if (!zhuf_walk_frames(cmp, size, blocks.data(), blocks.size(), &nb, &raw)) return -1;
+    if (raw > cap) return -3;
+    // (the kernel reads the payload from a device copy whose alignment differs from the host's: try a few)
+    std::vector<uint8_t> shifted(size + 16);
+    memcpy(shifted.data() + misalign, cmp, size);
+    const uint8_t *base = shifted.data() + misalign;
+    static ZhufDecScratch S;
+    static uint16_t tab[1 << kZhufMaxBits];
+    for (size_t g = 0; g < nb; g++) {
+        const ZhufDecBlock &b = blocks[g];
+        if (!b.coded) {
+            memcpy(out + b.dst, base + b.src, b.regen);
+            continue;
+        }
+        const uint8_t *d = base + b.src;
+        if (!zhuf_read_weights(d, b.lit, S)) return -2;
+        for (auto &t : tab) t = 0xffff;
+        zhuf_dec_table(S, tab, 0, 1);
+        uint32_t sb[4], sn[4];
+        if (!zhuf_stream_sizes(d, b.lit, S.desc_len, b.regen, sb, sn)) return -2;
+        const uint8_t *sp = d + S.desc_len + 6;
+        uint8_t *dp = out + b.dst;
+        for (int s = 0; s < 4; s++) {
+            if (!zhuf_dec_stream(sp, sb[s], tab, S.maxbits, dp, sn[s])) return -2;
+            sp += sb[s];
+            dp += sn[s];
+        }
+    }
+    return static_cast<long long>(raw);
+}

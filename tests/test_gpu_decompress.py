@@ -135,3 +135,74 @@ def test_g3_256_roundtrip_through_python_binding():
     assert np.max(np.abs(dec - data)) <= 1e-3
     want, _ = ref_decompress(np.ascontiguousarray(cmp), data)
     assert same_bits(dec, want)
+
+
+def _last_stages(L):
+    names, ms, ln = (C.c_char_p * 64)(), (C.c_double * 64)(), (C.c_int * 64)()
+    k = L.sz3b_last_profile(names, ms, ln, 64)
+    return [names[i].decode() for i in range(k)]
+
+
+@pytest.mark.parametrize("shape,dtype,eb,writer", [
+    ((256, 256, 256), np.float32, 1e-3, "gpu"),       # 5.6 MB of frames from the GPU lossless stage
+    ((256, 256, 256), np.float64, 1e-4, "gpu"),
+    ((200, 300, 260), np.float32, 1e-4, "gpu"),       # ragged last block / frame
+    ((256, 256, 256), np.float32, 1e-3, "ref"),       # libzstd's own frame: declined or decoded, same bits either way
+    ((256, 256, 256), np.float32, 1e-3, "host"),      # host zstd policy: multi-frame libzstd output
+])
+def test_frames_decoded_on_gpu(shape, dtype, eb, writer):
+    """Frame decoder 1 (sz3b_set_frame_decoder; sz3_b200/csrc/zhuf_dec.cuh): the frames of the GPU lossless stage are
+    decoded on the GPU -- the stage list of the call shows it -- and the array is bit-identical to the reference
+    decoder's; payloads of any other shape go through libzstd as before."""
+    L = product_lib()
+    data = field_g3(shape, dtype)
+    conf = make_config(shape, cmprAlgo=ALGO_INTERP, absErrorBound=eb)
+    if writer == "gpu":
+        cmp = gpu_compress(data, conf)[0]
+    elif writer == "ref":
+        cmp = ref_compress(data, conf)
+    else:
+        L.sz3b_set_lossless_policy(0)
+        try:
+            cmp = gpu_compress(data, conf)[0]
+        finally:
+            L.sz3b_set_lossless_policy(2)
+    want, _ = ref_decompress(cmp, data)
+    before = L.sz3b_get_frame_decoder()
+    try:
+        L.sz3b_set_frame_decoder(1)
+        got, _ = gpu_decompress(cmp, data)
+        stages = _last_stages(L)
+        got_dev, _ = gpu_decompress(cmp, data, device=True)
+        L.sz3b_set_frame_decoder(0)
+        plain, _ = gpu_decompress(cmp, data)
+        assert "frames_gpu" not in _last_stages(L)
+    finally:
+        L.sz3b_set_frame_decoder(before)
+    assert same_bits(got, want) and same_bits(got_dev, want) and same_bits(plain, want)
+    if writer == "gpu":
+        assert "frames_gpu" in stages and "zstd_host" not in stages, stages
+
+
+def test_frames_on_gpu_damaged_payload():
+    """Damage inside the frames: the call must end the way the host path ends (an error, or an array -- the frames carry
+    no checksum), never crash."""
+    L = product_lib()
+    data = field_g3((256, 256, 256))
+    conf = make_config(data.shape, cmprAlgo=ALGO_INTERP, absErrorBound=1e-3)
+    cmp = gpu_compress(data, conf)[0]
+    rng = np.random.default_rng(9)
+    before = L.sz3b_get_frame_decoder()
+    try:
+        L.sz3b_set_frame_decoder(1)
+        for _ in range(6):
+            bad = cmp.copy()
+            lo = 64
+            i = int(rng.integers(lo, bad.size - 512))
+            bad[i] ^= np.uint8(0x10)
+            out = np.empty_like(data)
+            c2 = Config()
+            rc = L.sz3b_decompress(0, bad.ctypes.data_as(C.c_char_p), C.c_size_t(bad.size), out.ctypes.data_as(C.c_void_p), 0, C.byref(c2))
+            assert rc in (0, -1, -2, -3, -4, -5), rc
+    finally:
+        L.sz3b_set_frame_decoder(before)

@@ -56,6 +56,77 @@ def test_gain_on_index_stream_matches_zstd():
     assert frames.size <= r * 1.005, (frames.size, r)
 
 
+def emul_decompress(frames, expect, misalign=0):
+    E = zhuf_emul_lib()
+    frames = np.ascontiguousarray(frames)
+    out = np.full(expect + 64, 0xEE, np.uint8)
+    n = E.zhuf_emul_decompress(frames.ctypes.data, frames.size, out.ctypes.data, out.size, misalign)
+    return n, out[:max(n, 0)]
+
+
+@pytest.mark.parametrize("name,src", CASES, ids=[c[0] for c in CASES])
+def test_own_decoder_reads_own_frames(name, src):
+    """The frame decoder of decompression (sz3_b200/csrc/zhuf_dec.cuh, run sequentially here) against libzstd's: same
+    bytes for every case, at every alignment of the payload."""
+    src = np.ascontiguousarray(src)
+    frames, _ = emul_compress(src)
+    want = zstd_decode(frames, src.size)
+    for mis in range(4):
+        n, got = emul_decompress(frames, src.size, mis)
+        assert n == src.size, n
+        assert np.array_equal(got, want)
+
+
+def test_own_decoder_on_libzstd_frames():
+    """Frames written by libzstd itself: either the walker declines them (sequences, other literal forms: the host path
+    decodes those) or the decoder must agree with libzstd byte for byte."""
+    z = zstd_lib()
+    rng = np.random.default_rng(11)
+    declined = agreed = 0
+    for k, (name, src) in enumerate(CASES):
+        src = np.ascontiguousarray(src)
+        if src.size == 0:
+            continue
+        for level in (1, 3):
+            ref = np.zeros(z.ZSTD_compressBound(src.size), np.uint8)
+            r = z.ZSTD_compress(ref.ctypes.data, ref.size, src.ctypes.data, src.size, level)
+            assert not z.ZSTD_isError(r)
+            n, got = emul_decompress(ref[:r], src.size)
+            if n == -1 or n == -2:      # not this decoder's kind of frame / a description it does not take
+                declined += 1
+                continue
+            assert n == src.size and np.array_equal(got, src), (name, level, n)
+            agreed += 1
+    # entropy-coded bytes without matches: literal-only blocks, which libzstd writes in the very form zhuf does
+    noise = rng.integers(0, 256, 300000, dtype=np.uint8)
+    skew = np.minimum(noise, rng.integers(0, 256, 300000, dtype=np.uint8))
+    for src in (skew, np.minimum(skew, 200).astype(np.uint8)):
+        ref = np.zeros(z.ZSTD_compressBound(src.size), np.uint8)
+        r = z.ZSTD_compress(ref.ctypes.data, ref.size, src.ctypes.data, src.size, 3)
+        n, got = emul_decompress(ref[:r], src.size)
+        if n >= 0:
+            assert n == src.size and np.array_equal(got, src)
+            agreed += 1
+        else:
+            declined += 1
+    assert declined + agreed > 0
+
+
+def test_own_decoder_rejects_damage():
+    src = np.ascontiguousarray(CASES[0][1])
+    frames, _ = emul_compress(src)
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        bad = frames.copy()
+        i = int(rng.integers(0, bad.size))
+        bad[i] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        n, got = emul_decompress(bad, src.size)     # must not crash or run outside its buffers; any verdict is fine
+        assert n <= src.size
+    for cut in (1, 5, 9, 100, frames.size // 2):
+        n, _ = emul_decompress(frames[:frames.size - cut], src.size)
+        assert n < 0
+
+
 # ---- GPU half ----------------------------------------------------------------------------------------------------------
 def gpu_lossless(src, device=False):
     L = product_lib()
