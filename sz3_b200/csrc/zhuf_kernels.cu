@@ -281,11 +281,13 @@ __global__ void __launch_bounds__(kZhufThreads) k_zhuf_encode(const uint8_t *__r
 // stream's latency whatever the number of blocks.  Raw blocks are copied.  *bad is set when a block does not decode
 // (the caller then hands the whole payload to libzstd).
 constexpr int kZhufDecThreads = 128;
+constexpr uint32_t kZhufDecStage = 192;
 __global__ void __launch_bounds__(kZhufDecThreads) k_zhuf_decode(const uint8_t *__restrict__ cmp, const ZhufDecBlock *__restrict__ blocks,
                                                                  uint8_t *__restrict__ raw, unsigned *__restrict__ bad) {
     __shared__ ZhufDecScratch S;
     __shared__ uint16_t tab[1 << kZhufMaxBits];
     __shared__ uint32_t sb[4], sn[4];
+    __shared__ uint8_t sdesc[kZhufDecStage];
     const ZhufDecBlock b = blocks[blockIdx.x];
     const int tid = threadIdx.x;
     if (!b.coded) {
@@ -295,9 +297,14 @@ __global__ void __launch_bounds__(kZhufDecThreads) k_zhuf_decode(const uint8_t *
         return;
     }
     const uint8_t *d = cmp + b.src;
+    // the tree description (at most 129 bytes) and the jump table behind it, staged in shared memory: thread 0 reads
+    // them bit by bit
+    const uint32_t nstage = b.lit < kZhufDecStage ? b.lit : kZhufDecStage;
+    for (uint32_t i = tid; i < nstage; i += kZhufDecThreads) sdesc[i] = d[i];
+    __syncthreads();
     if (tid == 0) {
-        S.ok = zhuf_read_weights(d, b.lit, S) ? 1 : 0;
-        if (S.ok && !zhuf_stream_sizes(d, b.lit, S.desc_len, b.regen, sb, sn)) S.ok = 0;
+        S.ok = zhuf_read_weights(sdesc, nstage, S) ? 1 : 0;
+        if (S.ok && (S.desc_len + 6 > nstage || !zhuf_stream_sizes(sdesc, b.lit, S.desc_len, b.regen, sb, sn))) S.ok = 0;
         if (!S.ok) atomicOr(bad, 1u);
     }
     __syncthreads();
