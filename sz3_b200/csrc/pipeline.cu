@@ -2648,8 +2648,15 @@ static bool frames_on_gpu(Workspace &ws, const sz3b_config &conf, const uint8_t 
     // the head of the stream on the host: libzstd's streaming decoder with the output capped at what the parser reads
     // (it works block by block, so the first 128 KiB or so are decoded, not the whole first frame)
     {
-        thread_local ZSTD_DCtx *dctx = nullptr;
-        if (!dctx) dctx = ZSTD_createDCtx();
+        struct Holder {   // (container slabs are decoded by short-lived threads: the context goes with its thread)
+            ZSTD_DCtx *p = nullptr;
+            ~Holder() {
+                if (p) ZSTD_freeDCtx(p);
+            }
+        };
+        thread_local Holder held;
+        if (!held.p) held.p = ZSTD_createDCtx();
+        ZSTD_DCtx *const dctx = held.p;
         if (!dctx) return false;
         ZSTD_DCtx_reset(dctx, 1);
         ZSTD_inBuffer in{pay, pay_size, 0};

@@ -206,3 +206,17 @@ def test_frames_on_gpu_damaged_payload():
             assert rc in (0, -1, -2, -3, -4, -5), rc
     finally:
         L.sz3b_set_frame_decoder(before)
+
+
+def test_container_slabs_frames_on_gpu():
+    """An OpenMP container whose slabs are large enough for the GPU lossless stage: every slab's frames go through the
+    GPU frame decoder, on the container's worker threads, and the array equals the reference decoder's."""
+    L = product_lib()
+    data = field_g3((512, 256, 256))
+    conf = make_config(data.shape, cmprAlgo=ALGO_INTERP, absErrorBound=1e-3, openmp=2)
+    cmp = gpu_compress(data, conf)[0]
+    want, _ = ref_decompress(cmp, data)
+    assert L.sz3b_get_frame_decoder() == 1
+    for _ in range(2):
+        got, _ = gpu_decompress(cmp, data)
+        assert same_bits(got, want)
