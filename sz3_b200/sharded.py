@@ -21,6 +21,30 @@ def slab_range(rank, world, d0):
     return (rank * d0) // world, ((rank + 1) * d0) // world
 
 
+def core_share(local_rank, local_world, allowed=None):
+    """The cores rank `local_rank` of `local_world` ranks on this host should keep to: a contiguous, disjoint share of
+    the cores the process may run on (what `mpirun --bind-to core` hands an MPI rank).  Empty when the host has fewer
+    cores than ranks."""
+    import os
+    cores = sorted(os.sched_getaffinity(0)) if allowed is None else sorted(allowed)
+    k = len(cores) // max(1, local_world)
+    return cores[local_rank * k:(local_rank + 1) * k]
+
+
+def bind_rank(local_rank, local_world):
+    """Binds the calling process to its `core_share` and sizes the library's host pool to it (at most six threads: every
+    concurrent tuner trial keeps a thread waiting on its stream, and ranks whose pools fill their whole share stall each
+    other's main threads and NCCL proxies -- DESIGN.md section 8).  Call it before the first compression of a rank
+    launched one-per-GPU; returns the cores it bound to ([] = left alone)."""
+    import os
+    mine = core_share(local_rank, local_world)
+    if not mine or local_world < 2:
+        return []
+    os.sched_setaffinity(0, set(mine))
+    lib().sz3b_set_host_threads(max(2, min(len(mine), 6)))
+    return mine
+
+
 def _gpu_slab_compress(slab, conf_c, rank, world, value_range):
     """(payload bytes, Config blob bytes) of this rank's slab via sz3b_compress_slab (GPU)."""
     ptr, loc, code, shape, keep = _buffer_of(slab)

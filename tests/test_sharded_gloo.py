@@ -98,3 +98,15 @@ def test_slab_ranges_match_reference_split():
         assert edges[0][0] == 0 and edges[-1][1] == d0
         for (a, b), (c, d) in zip(edges, edges[1:]):
             assert b == c and b > a
+
+
+def test_core_shares_are_disjoint_and_cover():
+    """sharded.core_share: the ranks of a host get contiguous, disjoint, equally sized shares of the allowed cores."""
+    from sz3_b200.sharded import core_share
+    allowed = list(range(3, 35))           # 32 cores, not starting at 0
+    for world in (1, 2, 4, 8):
+        shares = [core_share(r, world, allowed) for r in range(world)]
+        assert all(len(s) == 32 // world for s in shares)
+        flat = [c for s in shares for c in s]
+        assert flat == allowed[:len(flat)] and len(set(flat)) == len(flat)
+    assert core_share(5, 64, allowed) == []     # fewer cores than ranks: nothing to bind to
